@@ -1,0 +1,244 @@
+"""mujoco_b200 — B200-native batched implementation of MuJoCo's mj_step hot path.
+
+Thin ctypes binding over the C ABI in include/mjb.h (libmjb200.so, built in-tree by
+__graft_entry__.build()).  The Python surface mirrors the reference's batched caller,
+python/mujoco/rollout.py (`Rollout.rollout(model, data, initial_state, control, ...)`):
+C-contiguous float64 arrays in the reference's layouts, `initial_state` in mjSTATE_FULLPHYSICS order.
+
+The CUDA library is the only compute path: if it is missing, or no CUDA device is usable, loading or
+batch creation raises — there is no CPU fallback in this package.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmjb200.so")
+
+# mjtState bits (reference include/mujoco/mjtype.h:503-527)
+STATE_TIME, STATE_QPOS, STATE_QVEL, STATE_ACT, STATE_HISTORY = 1, 2, 4, 8, 16
+STATE_WARMSTART, STATE_CTRL, STATE_QFRC_APPLIED, STATE_PLUGIN = 32, 64, 128, 1 << 13
+STATE_FULLPHYSICS = STATE_TIME | STATE_QPOS | STATE_QVEL | STATE_ACT | STATE_HISTORY | STATE_PLUGIN
+
+SOLVER_PGS, SOLVER_CG, SOLVER_NEWTON = 0, 1, 2
+INT_EULER, INT_RK4 = 0, 1
+
+
+class MjbError(RuntimeError):
+    pass
+
+
+def _bind(cdll):
+    """declare argument / result types of every symbol in include/mjb.h on a loaded library"""
+    L = cdll
+    vp, cp, i, u, l = C.c_void_p, C.c_char_p, C.c_int, C.c_uint, C.c_long
+    dp = C.POINTER(C.c_double)
+    L.mjb_last_error.restype = cp
+    L.mjb_version.restype = i
+    L.mjb_load_model.restype = vp
+    L.mjb_load_model.argtypes = [cp]
+    L.mjb_free_model.argtypes = [vp]
+    L.mjb_check_model.argtypes = [vp]
+    L.mjb_model_size.restype = l
+    L.mjb_model_size.argtypes = [vp, cp]
+    L.mjb_get_option.argtypes = [vp, cp, dp]
+    L.mjb_set_option.argtypes = [vp, cp, C.c_double]
+    L.mjb_make_batch.restype = vp
+    L.mjb_make_batch.argtypes = [vp, i, i, i, i]
+    L.mjb_free_batch.argtypes = [vp]
+    L.mjb_nenv.argtypes = [vp]
+    L.mjb_reset.argtypes = [vp]
+    L.mjb_state_size.argtypes = [vp, u]
+    L.mjb_set_state.argtypes = [vp, vp, u]
+    L.mjb_get_state.argtypes = [vp, vp, u]
+    L.mjb_forward.argtypes = [vp]
+    L.mjb_step.argtypes = [vp, i]
+    L.mjb_rollout.argtypes = [vp, i, u, vp, vp, vp, vp, vp]
+    L.mjb_rollout_device.argtypes = [vp, i, vp, vp]
+    L.mjb_env_stride.restype = l
+    L.mjb_env_stride.argtypes = [vp]
+    L.mjb_field_size.restype = l
+    L.mjb_field_size.argtypes = [vp, cp]
+    L.mjb_get_field.argtypes = [vp, cp, vp]
+    L.mjb_get_field_int.argtypes = [vp, cp, vp]
+    L.mjb_set_field.argtypes = [vp, cp, vp]
+    L.mjb_kernel_launches.restype = l
+    L.mjb_kernel_launches.argtypes = [vp]
+    L.mjb_warning_counts.argtypes = [vp, vp]
+    L.mjb_run_stages.argtypes = [vp, i, i]
+    L.mjb_stream.restype = vp
+    L.mjb_stream.argtypes = [vp]
+    return L
+
+
+_lib = None
+
+
+def lib():
+    """the product library; raises if libmjb200.so has not been built"""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise MjbError(f"{LIB_PATH} not found: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "(the CUDA library is the only compute path; there is no CPU fallback)")
+        _lib = _bind(C.CDLL(LIB_PATH))
+    return _lib
+
+
+def _err(L):
+    return L.mjb_last_error().decode()
+
+
+class Model:
+    """an mjModel loaded from an MJB binary (reference mj_saveModel format) or wrapped from an address"""
+
+    def __init__(self, path=None, address=None, library=None):
+        self.L = library or lib()
+        self._own = False
+        if path is not None:
+            self.ptr = self.L.mjb_load_model(os.fsencode(path))
+            if not self.ptr:
+                raise MjbError(_err(self.L))
+            self._own = True
+        else:
+            self.ptr = address  # e.g. mujoco.MjModel._address of the stock Python bindings
+
+    def size(self, name):
+        v = self.L.mjb_model_size(self.ptr, name.encode())
+        if v < 0:
+            raise KeyError(name)
+        return int(v)
+
+    def get_option(self, name):
+        v = C.c_double()
+        if self.L.mjb_get_option(self.ptr, name.encode(), C.byref(v)):
+            raise KeyError(name)
+        return v.value
+
+    def set_option(self, name, value):
+        if self.L.mjb_set_option(self.ptr, name.encode(), float(value)):
+            raise KeyError(name)
+
+    def check(self):
+        if self.L.mjb_check_model(self.ptr):
+            raise MjbError(_err(self.L))
+
+    def __del__(self):
+        if getattr(self, "_own", False) and self.ptr:
+            self.L.mjb_free_model(self.ptr)
+            self.ptr = None
+
+
+class Batch:
+    """nenv environments of one model, resident on one GPU"""
+
+    def __init__(self, model, nenv, nconmax=0, njmax=0, device=-1):
+        self.L = model.L
+        self.model = model
+        self.ptr = self.L.mjb_make_batch(model.ptr, int(nenv), int(nconmax), int(njmax), int(device))
+        if not self.ptr:
+            raise MjbError(_err(self.L))
+        self.nenv = int(nenv)
+
+    def _chk(self, rc):
+        if rc:
+            raise MjbError(f"mjb error {rc}: {_err(self.L)}")
+
+    def close(self):
+        if self.ptr:
+            self.L.mjb_free_batch(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def reset(self):
+        self._chk(self.L.mjb_reset(self.ptr))
+
+    def state_size(self, sig=STATE_FULLPHYSICS):
+        n = self.L.mjb_state_size(self.ptr, sig)
+        if n < 0:
+            raise MjbError(_err(self.L))
+        return n
+
+    def set_state(self, state, sig=STATE_FULLPHYSICS):
+        s = np.ascontiguousarray(state, dtype=np.float64)
+        if s.shape != (self.nenv, self.state_size(sig)):
+            raise ValueError(f"state must have shape {(self.nenv, self.state_size(sig))}, got {s.shape}")
+        self._chk(self.L.mjb_set_state(self.ptr, s.ctypes.data, sig))
+
+    def get_state(self, sig=STATE_FULLPHYSICS):
+        out = np.zeros((self.nenv, self.state_size(sig)))
+        self._chk(self.L.mjb_get_state(self.ptr, out.ctypes.data, sig))
+        return out
+
+    def forward(self):
+        self._chk(self.L.mjb_forward(self.ptr))
+
+    def step(self, nstep=1):
+        self._chk(self.L.mjb_step(self.ptr, int(nstep)))
+
+    def run_stages(self, first, last):
+        self._chk(self.L.mjb_run_stages(self.ptr, first, last))
+
+    def field(self, name):
+        n = self.L.mjb_field_size(self.ptr, name.encode())
+        if n < 0:
+            raise KeyError(name)
+        out = np.zeros((self.nenv, n))
+        rc = self.L.mjb_get_field(self.ptr, name.encode(), out.ctypes.data)
+        if rc:
+            iout = np.zeros((self.nenv, n), dtype=np.int32)
+            self._chk(self.L.mjb_get_field_int(self.ptr, name.encode(), iout.ctypes.data))
+            return iout
+        return out
+
+    def set_field(self, name, value):
+        n = self.L.mjb_field_size(self.ptr, name.encode())
+        v = np.ascontiguousarray(np.broadcast_to(np.asarray(value, dtype=np.float64), (self.nenv, n)))
+        self._chk(self.L.mjb_set_field(self.ptr, name.encode(), v.ctypes.data))
+
+    def warnings(self):
+        out = np.zeros((self.nenv, 8), dtype=np.int32)
+        self._chk(self.L.mjb_warning_counts(self.ptr, out.ctypes.data))
+        return out
+
+    def kernel_launches(self):
+        return int(self.L.mjb_kernel_launches(self.ptr))
+
+    def rollout(self, initial_state, control=None, nstep=None, control_spec=STATE_CTRL,
+                initial_warmstart=None, return_state=True):
+        """mirror of mujoco.rollout.rollout: initial_state [nenv,nstate], control [nenv,nstep,ncontrol]
+        -> state [nenv,nstep,nstate] (mjSTATE_FULLPHYSICS)"""
+        s0 = np.ascontiguousarray(initial_state, dtype=np.float64)
+        nstate = self.state_size()
+        if s0.shape != (self.nenv, nstate):
+            raise ValueError(f"initial_state must have shape {(self.nenv, nstate)}, got {s0.shape}")
+        cptr = None
+        if control is not None:
+            ctl = np.ascontiguousarray(control, dtype=np.float64)
+            ncontrol = self.state_size(control_spec)
+            if ctl.ndim != 3 or ctl.shape[0] != self.nenv or ctl.shape[2] != ncontrol:
+                raise ValueError(f"control must have shape (nenv, nstep, {ncontrol}), got {ctl.shape}")
+            if nstep is None:
+                nstep = ctl.shape[1]
+            elif nstep != ctl.shape[1]:
+                raise ValueError("nstep does not match control.shape[1]")
+            cptr = ctl.ctypes.data
+        if nstep is None:
+            raise ValueError("nstep required when control is None")
+        wptr = None
+        if initial_warmstart is not None:
+            w = np.ascontiguousarray(initial_warmstart, dtype=np.float64)
+            nv = self.model.size("nv")
+            if w.shape != (self.nenv, nv):
+                raise ValueError(f"initial_warmstart must have shape {(self.nenv, nv)}")
+            wptr = w.ctypes.data
+        out = np.zeros((self.nenv, nstep, nstate)) if return_state else None
+        self._chk(self.L.mjb_rollout(self.ptr, int(nstep), control_spec, s0.ctypes.data, wptr, cptr,
+                                     out.ctypes.data if return_state else None, None))
+        return out

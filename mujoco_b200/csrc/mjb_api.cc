@@ -1,0 +1,338 @@
+// C ABI of libmjb200 (include/mjb.h): batch management, state I/O with the reference's mjtState
+// signature semantics (src/engine/engine_support.c:138-315), mj_step/mj_forward on all
+// environments and the batched rollout that mirrors python/mujoco/rollout.cc:67-178.
+// Device work goes through mjb_backend.h (CUDA in the product; host loops only in tests/hostemu).
+#include "../../include/mjb.h"
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "mjb_backend.h"
+#include "mjb_model.h"
+
+using namespace mjb;
+
+namespace {
+enum {  // mjtState bits (include/mujoco/mjtype.h:503-517)
+  ST_TIME = 1 << 0, ST_QPOS = 1 << 1, ST_QVEL = 1 << 2, ST_ACT = 1 << 3, ST_HISTORY = 1 << 4,
+  ST_WARMSTART = 1 << 5, ST_CTRL = 1 << 6, ST_QFRC_APPLIED = 1 << 7, ST_XFRC_APPLIED = 1 << 8,
+  ST_EQ_ACTIVE = 1 << 9, ST_MOCAP_POS = 1 << 10, ST_MOCAP_QUAT = 1 << 11, ST_USERDATA = 1 << 12,
+  ST_PLUGIN = 1 << 13
+};
+const unsigned kSupportedState = ST_TIME | ST_QPOS | ST_QVEL | ST_ACT | ST_HISTORY | ST_WARMSTART | ST_CTRL |
+                                 ST_QFRC_APPLIED | ST_EQ_ACTIVE | ST_MOCAP_POS | ST_MOCAP_QUAT | ST_USERDATA | ST_PLUGIN;
+}  // namespace
+
+struct mjbBatch_ {
+  HostModel hm;          // host copy (pointers into hm.ib / hm.db)
+  DModel dm;             // device copy (pointers into d_ib / d_db)
+  int* d_ib = nullptr;
+  double* d_db = nullptr;
+  Batch b;               // device storage
+  void* stream = nullptr;
+  int device = 0;
+};
+
+static int fail(int code, const std::string& msg) { set_error(msg); return code; }
+
+extern "C" {
+
+const char* mjb_last_error(void) { return get_error(); }
+int mjb_version(void) { return 100; }
+
+struct mjModel_* mjb_load_model(const char* path) { return (struct mjModel_*)load_mjb(path); }
+void mjb_free_model(struct mjModel_* m) { free_mjb((mjModel*)m); }
+int mjb_check_model(const struct mjModel_* m) { return check_model((const mjModel*)m); }
+long mjb_model_size(const struct mjModel_* m, const char* name) { return model_size((const mjModel*)m, name); }
+int mjb_get_option(const struct mjModel_* m, const char* name, double* v) { return get_option((const mjModel*)m, name, v) ? MJB_ERR_ARG : 0; }
+int mjb_set_option(struct mjModel_* m, const char* name, double v) { return set_option((mjModel*)m, name, v) ? MJB_ERR_ARG : 0; }
+
+mjbBatch* mjb_make_batch(const struct mjModel_* m, int nenv, int nconmax, int njmax, int device) {
+  if (!m || nenv <= 0) { set_error("mjb_make_batch: bad arguments"); return nullptr; }
+  if (int rc = backend::init(device)) { (void)rc; return nullptr; }
+  mjbBatch* B = new mjbBatch_();
+  if (build_host_model((const mjModel*)m, nconmax, njmax, &B->hm)) { delete B; return nullptr; }
+  const DModel& H = B->hm.dm;
+  if (H.opt.solver == SOL_NEWTON) {
+#ifndef MJB_HAVE_NEWTON
+    set_error("unsupported: Newton solver not built");
+    delete B;
+    return nullptr;
+#endif
+  }
+  if (H.sz.nu > 4 * H.sz.nv) { set_error("unsupported: nu > 4*nv"); delete B; return nullptr; }
+  B->device = device;
+  B->stream = backend::stream_create();
+  // device copy of the model blobs, pointers rebased
+  B->d_ib = (int*)backend::dev_alloc(B->hm.ib.size() * sizeof(int));
+  B->d_db = (double*)backend::dev_alloc(B->hm.db.size() * sizeof(double));
+  if (!B->d_ib || !B->d_db) { set_error("device allocation failed (model)"); delete B; return nullptr; }
+  backend::h2d(B->d_ib, B->hm.ib.data(), B->hm.ib.size() * sizeof(int), B->stream);
+  backend::h2d(B->d_db, B->hm.db.data(), B->hm.db.size() * sizeof(double), B->stream);
+  B->dm = H;
+#define X(name) B->dm.name = B->d_ib + (H.name - B->hm.ib.data());
+  MJB_MODEL_INT_FIELDS(X)
+#undef X
+#define X(name) B->dm.name = B->d_db + (H.name - B->hm.db.data());
+  MJB_MODEL_DBL_FIELDS(X)
+#undef X
+  // batch storage
+  Batch& b = B->b;
+  b.nenv = nenv;
+  b.stride = ((size_t)nenv + 31) / 32 * 32;
+  b.L = make_layout(H.sz);
+  size_t nd = (size_t)b.L.ndbl * b.stride, ni = (size_t)b.L.nint * b.stride;
+  b.dbl = (double*)backend::dev_alloc(nd * sizeof(double));
+  b.itg = (int*)backend::dev_alloc(ni * sizeof(int));
+  if (!b.dbl || !b.itg) { set_error("device allocation failed (batch)"); mjb_free_batch(B); return nullptr; }
+  backend::launch_reset(B->dm, b, B->stream);
+  if (backend::sync(B->stream)) { mjb_free_batch(B); return nullptr; }
+  return B;
+}
+
+void mjb_free_batch(mjbBatch* B) {
+  if (!B) return;
+  backend::sync(B->stream);
+  backend::dev_free(B->b.dbl);
+  backend::dev_free(B->b.itg);
+  backend::dev_free(B->d_ib);
+  backend::dev_free(B->d_db);
+  backend::stream_destroy(B->stream);
+  delete B;
+}
+
+int mjb_nenv(const mjbBatch* B) { return B ? B->b.nenv : 0; }
+long mjb_env_stride(const mjbBatch* B) { return B ? (long)B->b.stride : 0; }
+void* mjb_stream(mjbBatch* B) { return B ? B->stream : nullptr; }
+long mjb_kernel_launches(const mjbBatch*) { return backend::launches(); }
+
+int mjb_reset(mjbBatch* B) {
+  if (!B) return fail(MJB_ERR_ARG, "null batch");
+  if (int rc = backend::launch_reset(B->dm, B->b, B->stream)) return rc;
+  return backend::sync(B->stream);
+}
+
+// ---- state vector <-> fields ---------------------------------------------------------------------
+struct Seg { long off; int n; };   // field offset (elements) and count
+static int state_segments(const mjbBatch* B, unsigned sig, std::vector<Seg>* segs) {
+  const Sizes& S = B->hm.dm.sz;
+  const Layout& L = B->b.L;
+  if (sig & ~kSupportedState) return -1;
+  if (sig & ST_XFRC_APPLIED) return -1;
+  segs->clear();
+  if (sig & ST_TIME) segs->push_back({L.time, 1});
+  if (sig & ST_QPOS) segs->push_back({L.qpos, S.nq});
+  if (sig & ST_QVEL) segs->push_back({L.qvel, S.nv});
+  // ACT, HISTORY: zero-sized on supported models (na == 0, nhistory == 0)
+  if (sig & ST_WARMSTART) segs->push_back({L.qacc_warmstart, S.nv});
+  if (sig & ST_CTRL) segs->push_back({L.ctrl, S.nu});
+  if (sig & ST_QFRC_APPLIED) segs->push_back({L.qfrc_applied, S.nv});
+  // EQ_ACTIVE, MOCAP_*, USERDATA, PLUGIN: zero-sized on supported models
+  return 0;
+}
+
+int mjb_state_size(const mjbBatch* B, unsigned int sig) {
+  std::vector<Seg> segs;
+  if (!B || state_segments(B, sig, &segs)) { set_error("mjb_state_size: unsupported state signature"); return MJB_ERR_ARG; }
+  int n = 0;
+  for (auto& s : segs) n += s.n;
+  return n;
+}
+
+static int copy_rows_d2h(mjbBatch* B, long off, int n, std::vector<double>* host) {
+  host->resize((size_t)n * B->b.stride);
+  return backend::d2h(host->data(), B->b.dbl + (size_t)off * B->b.stride, host->size() * sizeof(double), B->stream);
+}
+
+int mjb_set_state(mjbBatch* B, const double* state, unsigned int sig) {
+  std::vector<Seg> segs;
+  if (!B || !state || state_segments(B, sig, &segs)) return fail(MJB_ERR_ARG, "mjb_set_state: bad arguments / unsupported signature");
+  int ns = 0;
+  for (auto& s : segs) ns += s.n;
+  const size_t st = B->b.stride;
+  std::vector<double> tmp;
+  int col = 0;
+  for (auto& s : segs) {
+    tmp.assign((size_t)s.n * st, 0.0);
+    for (int i = 0; i < s.n; i++)
+      for (int e = 0; e < B->b.nenv; e++) tmp[(size_t)i * st + e] = state[(size_t)e * ns + col + i];
+    if (int rc = backend::h2d(B->b.dbl + (size_t)s.off * st, tmp.data(), tmp.size() * sizeof(double), B->stream)) return rc;
+    if (int rc = backend::sync(B->stream)) return rc;
+    col += s.n;
+  }
+  return 0;
+}
+
+int mjb_get_state(mjbBatch* B, double* state, unsigned int sig) {
+  std::vector<Seg> segs;
+  if (!B || !state || state_segments(B, sig, &segs)) return fail(MJB_ERR_ARG, "mjb_get_state: bad arguments / unsupported signature");
+  int ns = 0;
+  for (auto& s : segs) ns += s.n;
+  const size_t st = B->b.stride;
+  std::vector<double> tmp;
+  int col = 0;
+  for (auto& s : segs) {
+    if (int rc = copy_rows_d2h(B, s.off, s.n, &tmp)) return rc;
+    if (int rc = backend::sync(B->stream)) return rc;
+    for (int i = 0; i < s.n; i++)
+      for (int e = 0; e < B->b.nenv; e++) state[(size_t)e * ns + col + i] = tmp[(size_t)i * st + e];
+    col += s.n;
+  }
+  return 0;
+}
+
+// ---- stepping --------------------------------------------------------------------------------------
+static int run_step(mjbBatch* B, int flags) {
+  for (int s = 0; s < 4; s++)
+    if (int rc = backend::launch_stage(B->dm, B->b, s, flags | 1, B->stream)) return rc;
+  return 0;
+}
+
+int mjb_forward(mjbBatch* B) {
+  if (!B) return fail(MJB_ERR_ARG, "null batch");
+  for (int s = 0; s < 3; s++)
+    if (int rc = backend::launch_stage(B->dm, B->b, s, 0, B->stream)) return rc;
+  if (int rc = backend::launch_stage(B->dm, B->b, 4, 0, B->stream)) return rc;   // finish without integrating
+  return backend::sync(B->stream);
+}
+
+int mjb_step(mjbBatch* B, int nstep) {
+  if (!B || nstep < 0) return fail(MJB_ERR_ARG, "mjb_step: bad arguments");
+  for (int t = 0; t < nstep; t++)
+    if (int rc = run_step(B, 0)) return rc;
+  return backend::sync(B->stream);
+}
+
+int mjb_run_stages(mjbBatch* B, int first, int last) {
+  if (!B || first < 0 || last > 4 || first > last) return fail(MJB_ERR_ARG, "mjb_run_stages: bad range");
+  for (int s = first; s <= last; s++)
+    if (int rc = backend::launch_stage(B->dm, B->b, s, 1, B->stream)) return rc;
+  return backend::sync(B->stream);
+}
+
+int mjb_rollout(mjbBatch* B, int nstep, unsigned int control_spec, const double* state0,
+                const double* warmstart0, const double* control, double* state, double* sensordata) {
+  if (!B || nstep < 0 || !state0) return fail(MJB_ERR_ARG, "mjb_rollout: bad arguments");
+  if (sensordata) return fail(MJB_ERR_ARG, "mjb_rollout: sensordata must be NULL (nsensordata == 0)");
+  const unsigned full = ST_TIME | ST_QPOS | ST_QVEL | ST_ACT | ST_HISTORY | ST_PLUGIN;
+  std::vector<Seg> csegs;
+  if (control && state_segments(B, control_spec, &csegs)) return fail(MJB_ERR_ARG, "mjb_rollout: unsupported control_spec");
+  const int nenv = B->b.nenv, nv = B->hm.dm.sz.nv;
+  const int nstate = mjb_state_size(B, full);
+  int ncontrol = 0;
+  for (auto& s : csegs) ncontrol += s.n;
+  // defaults for unspecified user inputs, initial state, warmstart, warning counters
+  {
+    const size_t st = B->b.stride;
+    if (!(control_spec & ST_CTRL) || !control)
+      backend::dev_zero(B->b.dbl + (size_t)B->b.L.ctrl * st, (size_t)B->hm.dm.sz.nu * st * sizeof(double), B->stream);
+    if (!(control_spec & ST_QFRC_APPLIED) || !control)
+      backend::dev_zero(B->b.dbl + (size_t)B->b.L.qfrc_applied * st, (size_t)nv * st * sizeof(double), B->stream);
+    backend::dev_zero(B->b.itg + (size_t)B->b.L.warning * st, (size_t)NWARNING * st * sizeof(int), B->stream);
+    if (int rc = mjb_set_state(B, state0, full)) return rc;
+    if (warmstart0) {
+      if (int rc = mjb_set_state(B, warmstart0, ST_WARMSTART)) return rc;
+    } else {
+      backend::dev_zero(B->b.dbl + (size_t)B->b.L.qacc_warmstart * st, (size_t)nv * st * sizeof(double), B->stream);
+    }
+  }
+  double* d_control = nullptr;
+  double* d_state = nullptr;
+  const size_t cbytes = (size_t)nenv * nstep * ncontrol * sizeof(double);
+  const size_t sbytes = (size_t)nenv * nstep * nstate * sizeof(double);
+  if (control && ncontrol && nstep) {
+    d_control = (double*)backend::dev_alloc(cbytes);
+    if (!d_control) return fail(MJB_ERR_CUDA, "device allocation failed (control)");
+    backend::h2d(d_control, control, cbytes, B->stream);
+  }
+  if (state && nstep) {
+    d_state = (double*)backend::dev_alloc(sbytes);
+    if (!d_state) { backend::dev_free(d_control); return fail(MJB_ERR_CUDA, "device allocation failed (state)"); }
+  }
+  int rc = 0;
+  for (int t = 0; t < nstep && !rc; t++) {
+    if (d_control) rc = backend::launch_set_control(B->dm, B->b, d_control, nstep, t, control_spec, ncontrol, B->stream);
+    for (int s = 0; s < 4 && !rc; s++) rc = backend::launch_stage(B->dm, B->b, s, 1 | 2, B->stream);
+    if (d_state && !rc) rc = backend::launch_get_state(B->dm, B->b, d_state, nstep, t, nstate, B->stream);
+  }
+  if (!rc && d_state) rc = backend::d2h(state, d_state, sbytes, B->stream);
+  if (!rc) rc = backend::sync(B->stream);
+  backend::dev_free(d_control);
+  backend::dev_free(d_state);
+  return rc;
+}
+
+int mjb_rollout_device(mjbBatch* B, int nstep, const double* d_ctrl, double* d_state) {
+  if (!B || nstep < 0) return fail(MJB_ERR_ARG, "mjb_rollout_device: bad arguments");
+  const unsigned full = ST_TIME | ST_QPOS | ST_QVEL;
+  const int nstate = mjb_state_size(B, full);
+  int rc = 0;
+  for (int t = 0; t < nstep && !rc; t++) {
+    if (d_ctrl) rc = backend::launch_set_control_native(B->dm, B->b, d_ctrl, t, B->stream);
+    for (int s = 0; s < 4 && !rc; s++) rc = backend::launch_stage(B->dm, B->b, s, 1, B->stream);
+    if (d_state && !rc) rc = backend::launch_get_state_native(B->dm, B->b, d_state, t, nstate, B->stream);
+  }
+  return rc;   // asynchronous: caller synchronises on mjb_stream()
+}
+
+// ---- field access ----------------------------------------------------------------------------------
+static bool find_field(const mjbBatch* B, const char* name, long* off, long* cnt, bool* is_int) {
+  const Sizes& S = B->hm.dm.sz;
+  const Layout& L = B->b.L;
+  (void)S;
+#define X(fname, count) if (!strcmp(name, #fname)) { *off = L.fname; *cnt = (long)(count); *is_int = false; return true; }
+  MJB_DATA_DBL_FIELDS(X, S)
+#undef X
+#define X(fname, count) if (!strcmp(name, #fname)) { *off = L.fname; *cnt = (long)(count); *is_int = true; return true; }
+  MJB_DATA_INT_FIELDS(X, S)
+#undef X
+  return false;
+}
+
+long mjb_field_size(const mjbBatch* B, const char* name) {
+  long off, cnt; bool is_int;
+  if (!B || !find_field(B, name, &off, &cnt, &is_int)) return -1;
+  return cnt;
+}
+
+int mjb_get_field(mjbBatch* B, const char* name, double* out) {
+  long off, cnt; bool is_int;
+  if (!B || !out || !find_field(B, name, &off, &cnt, &is_int) || is_int) return fail(MJB_ERR_ARG, std::string("mjb_get_field: unknown double field ") + (name ? name : ""));
+  std::vector<double> tmp;
+  if (int rc = copy_rows_d2h(B, off, (int)cnt, &tmp)) return rc;
+  if (int rc = backend::sync(B->stream)) return rc;
+  const size_t st = B->b.stride;
+  for (long i = 0; i < cnt; i++)
+    for (int e = 0; e < B->b.nenv; e++) out[(size_t)e * cnt + i] = tmp[(size_t)i * st + e];
+  return 0;
+}
+
+int mjb_get_field_int(mjbBatch* B, const char* name, int* out) {
+  long off, cnt; bool is_int;
+  if (!B || !out || !find_field(B, name, &off, &cnt, &is_int) || !is_int) return fail(MJB_ERR_ARG, std::string("mjb_get_field_int: unknown int field ") + (name ? name : ""));
+  const size_t st = B->b.stride;
+  std::vector<int> tmp((size_t)cnt * st);
+  if (int rc = backend::d2h(tmp.data(), B->b.itg + (size_t)off * st, tmp.size() * sizeof(int), B->stream)) return rc;
+  if (int rc = backend::sync(B->stream)) return rc;
+  for (long i = 0; i < cnt; i++)
+    for (int e = 0; e < B->b.nenv; e++) out[(size_t)e * cnt + i] = tmp[(size_t)i * st + e];
+  return 0;
+}
+
+int mjb_set_field(mjbBatch* B, const char* name, const double* in) {
+  long off, cnt; bool is_int;
+  if (!B || !in || !find_field(B, name, &off, &cnt, &is_int) || is_int) return fail(MJB_ERR_ARG, std::string("mjb_set_field: unknown double field ") + (name ? name : ""));
+  const size_t st = B->b.stride;
+  std::vector<double> tmp((size_t)cnt * st, 0.0);
+  for (long i = 0; i < cnt; i++)
+    for (int e = 0; e < B->b.nenv; e++) tmp[(size_t)i * st + e] = in[(size_t)e * cnt + i];
+  if (int rc = backend::h2d(B->b.dbl + (size_t)off * st, tmp.data(), tmp.size() * sizeof(double), B->stream)) return rc;
+  return backend::sync(B->stream);
+}
+
+int mjb_warning_counts(mjbBatch* B, int* out) { return mjb_get_field_int(B, "warning", out); }
+
+}  // extern "C"

@@ -1,0 +1,37 @@
+// Thin execution backend used by mjb_api.cc.  The product build (libmjb200.so) implements it with
+// CUDA (mjb_kernels.cu); tests/hostemu implements the same interface with host loops so that the
+// kernel SOURCE can be checked against the oracle in a container without a GPU.  The host
+// emulation is test infrastructure and is never linked into, or loaded by, the product.
+#pragma once
+#include <stddef.h>
+#include "mjb_types.h"
+
+namespace mjb {
+namespace backend {
+
+const char* name();
+int init(int device);                         // 0 or negative mjb error code (sets error text)
+void* dev_alloc(size_t bytes);                // zero-initialised
+void dev_free(void* p);
+int h2d(void* dst, const void* src, size_t bytes, void* stream);
+int d2h(void* dst, const void* src, size_t bytes, void* stream);
+int dev_zero(void* dst, size_t bytes, void* stream);
+void* stream_create();
+void stream_destroy(void* s);
+int sync(void* stream);
+
+// pipeline stage for every environment (stage ids: mjb_forward.h). flags: bit0 = part of mj_step
+// (run the qpos/qvel checks), bit1 = skip environments whose warning counters are non-zero
+int launch_stage(const DModel& dm, const Batch& b, int stage, int flags, void* stream);
+int launch_reset(const DModel& dm, const Batch& b, void* stream);
+// rollout helpers; control/state are DEVICE buffers laid out [nenv][nstep][n] (reference layout)
+int launch_set_control(const DModel& dm, const Batch& b, const double* control, int nstep, int t,
+                       unsigned spec, int ncontrol, void* stream);
+int launch_get_state(const DModel& dm, const Batch& b, double* state, int nstep, int t, int nstate, void* stream);
+// native-layout variants: ctrl [nstep][nu][stride], state [nstep][nstate][stride]
+int launch_set_control_native(const DModel& dm, const Batch& b, const double* ctrl, int t, void* stream);
+int launch_get_state_native(const DModel& dm, const Batch& b, double* state, int t, int nstate, void* stream);
+long launches();
+
+}  // namespace backend
+}  // namespace mjb

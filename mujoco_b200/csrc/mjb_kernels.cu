@@ -1,0 +1,156 @@
+// CUDA backend of libmjb200 for sm_100a (B200): kernels + the mjb_backend.h implementation.
+//
+// Thread mapping, first generation: one environment per lane.  Every mjData field is stored
+// field[elem][env] (mjb_types.h), so the 32 lanes of a warp touch 32 consecutive doubles = one
+// 256-byte line per element: every global access of every stage is perfectly coalesced, model
+// constants are warp-uniform broadcasts, and all lanes of a warp execute the same body/dof/pair
+// loops (same model), diverging only on contact hit/miss and solver iteration counts.
+// Kernels are launched with 32-thread blocks so that a 4096-env batch spreads its 128 warps over
+// 128 of the 148 SMs; larger batches fill the machine (multiple of 148 x resident CTAs).
+// Compiled with -fmad=false: contact in/out decisions must round like the reference's C build.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <string>
+
+#include "mjb_backend.h"
+#include "mjb_model.h"
+#include "mjb_stage.h"
+
+namespace mjb {
+
+__global__ void __launch_bounds__(32) k_stage(DModel m, Batch b, int stage, int flags) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= b.nenv) return;
+  run_stage(m, b, e, stage, flags);
+}
+
+__global__ void k_reset(DModel m, Batch b) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= b.nenv) return;
+  Env d(m, b, e);
+  reset_env(d, true);
+}
+
+__global__ void k_set_control(DModel m, Batch b, const double* control, int nstep, int t, unsigned spec, int ncontrol) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= b.nenv) return;
+  run_set_control(m, b, e, control, nstep, t, spec, ncontrol);
+}
+
+__global__ void k_get_state(DModel m, Batch b, double* state, int nstep, int t, int nstate) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= b.nenv) return;
+  run_get_state(m, b, e, state, nstep, t, nstate);
+}
+
+__global__ void k_set_control_native(DModel m, Batch b, const double* ctrl, int t) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= b.nenv) return;
+  run_set_control_native(m, b, e, ctrl, t);
+}
+
+__global__ void k_get_state_native(DModel m, Batch b, double* state, int t, int nstate) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= b.nenv) return;
+  run_get_state_native(m, b, e, state, t, nstate);
+}
+
+namespace backend {
+
+static long g_launches = 0;
+
+static int cuda_fail(cudaError_t e, const char* what) {
+  set_error(std::string("CUDA error in ") + what + ": " + cudaGetErrorString(e));
+  return -3;
+}
+#define CK(call, what) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return cuda_fail(e_, what); } while (0)
+
+const char* name() { return "cuda-sm100a"; }
+
+int init(int device) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    set_error(std::string("no usable CUDA device (") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count 0") +
+              "); libmjb200 has no CPU fallback");
+    return -3;
+  }
+  if (device >= 0) CK(cudaSetDevice(device), "cudaSetDevice");
+  return 0;
+}
+
+void* dev_alloc(size_t bytes) {
+  void* p = nullptr;
+  if (cudaMalloc(&p, bytes ? bytes : 1) != cudaSuccess) return nullptr;
+  cudaMemset(p, 0, bytes ? bytes : 1);
+  return p;
+}
+void dev_free(void* p) { if (p) cudaFree(p); }
+int h2d(void* dst, const void* src, size_t bytes, void* s) {
+  CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, (cudaStream_t)s), "h2d");
+  return 0;
+}
+int d2h(void* dst, const void* src, size_t bytes, void* s) {
+  CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)s), "d2h");
+  return 0;
+}
+int dev_zero(void* dst, size_t bytes, void* s) {
+  CK(cudaMemsetAsync(dst, 0, bytes, (cudaStream_t)s), "memset");
+  return 0;
+}
+void* stream_create() {
+  cudaStream_t s = nullptr;
+  cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking);
+  return (void*)s;
+}
+void stream_destroy(void* s) { if (s) cudaStreamDestroy((cudaStream_t)s); }
+int sync(void* s) {
+  CK(cudaStreamSynchronize((cudaStream_t)s), "stream synchronize");
+  CK(cudaGetLastError(), "kernel execution");
+  return 0;
+}
+long launches() { return g_launches; }
+
+static inline int nblocks(const Batch& b, int threads) { return (b.nenv + threads - 1) / threads; }
+
+int launch_stage(const DModel& dm, const Batch& b, int stage, int flags, void* s) {
+  k_stage<<<nblocks(b, 32), 32, 0, (cudaStream_t)s>>>(dm, b, stage, flags);
+  g_launches++;
+  CK(cudaPeekAtLastError(), "k_stage launch");
+  return 0;
+}
+int launch_reset(const DModel& dm, const Batch& b, void* s) {
+  k_reset<<<nblocks(b, 128), 128, 0, (cudaStream_t)s>>>(dm, b);
+  g_launches++;
+  CK(cudaPeekAtLastError(), "k_reset launch");
+  return 0;
+}
+int launch_set_control(const DModel& dm, const Batch& b, const double* control, int nstep, int t, unsigned spec,
+                       int ncontrol, void* s) {
+  k_set_control<<<nblocks(b, 128), 128, 0, (cudaStream_t)s>>>(dm, b, control, nstep, t, spec, ncontrol);
+  g_launches++;
+  CK(cudaPeekAtLastError(), "k_set_control launch");
+  return 0;
+}
+int launch_get_state(const DModel& dm, const Batch& b, double* state, int nstep, int t, int nstate, void* s) {
+  k_get_state<<<nblocks(b, 128), 128, 0, (cudaStream_t)s>>>(dm, b, state, nstep, t, nstate);
+  g_launches++;
+  CK(cudaPeekAtLastError(), "k_get_state launch");
+  return 0;
+}
+int launch_set_control_native(const DModel& dm, const Batch& b, const double* ctrl, int t, void* s) {
+  k_set_control_native<<<nblocks(b, 128), 128, 0, (cudaStream_t)s>>>(dm, b, ctrl, t);
+  g_launches++;
+  CK(cudaPeekAtLastError(), "k_set_control_native launch");
+  return 0;
+}
+int launch_get_state_native(const DModel& dm, const Batch& b, double* state, int t, int nstate, void* s) {
+  k_get_state_native<<<nblocks(b, 128), 128, 0, (cudaStream_t)s>>>(dm, b, state, t, nstate);
+  g_launches++;
+  CK(cudaPeekAtLastError(), "k_get_state_native launch");
+  return 0;
+}
+
+}  // namespace backend
+}  // namespace mjb

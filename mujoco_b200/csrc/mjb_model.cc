@@ -1,0 +1,584 @@
+// Host side of libmjb200: read a reference mjModel (same struct layout, public headers only),
+// check that it stays inside the accelerated hot path, and flatten it into the device model
+// (mjb_types.h: DModel) — including the static candidate geom-pair table that replaces the
+// reference's per-step broadphase/midphase bookkeeping with an order-preserving precomputation.
+//
+// Reference behaviour restated here (file:line under /root/reference):
+//   src/engine/engine_io.c:514-690          MJB binary layout (mj_saveModel / mj_loadModelBuffer)
+//   src/engine/engine_collision_driver.c:595-886  body-pair order, filters, per-pair geom order
+//   src/engine/engine_collision_driver.c:288-343  filterBodyPair / canCollide2
+//   src/engine/engine_collision_driver.c:410-443  contactcompare (midphase sort key)
+//   src/engine/engine_collision_driver.c:1740-1835 mj_contactParam (static per geom pair)
+//   src/engine/engine_core_util.c:1119-1215  mj_actuatorDamping / mj_actuatorArmature
+//   src/engine/engine_forward.c:1409-1421    which dofs trigger implicit Euler damping
+#include "mjb_model.h"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include <mujoco/mjmodel.h>
+#include <mujoco/mjxmacro.h>
+
+namespace mjb {
+
+static thread_local std::string g_err;
+void set_error(const std::string& s) { g_err = s; }
+const char* get_error() { return g_err.c_str(); }
+
+// ------------------------------------------------------------------------------------------------
+// MJB loader (header + sizes + option structs + arrays in MJMODEL_POINTERS order)
+static const int kMjbId = 54321;
+
+mjModel* load_mjb(const char* path) {
+  FILE* f = fopen(path, "rb");
+  if (!f) { set_error(std::string("cannot open ") + path); return nullptr; }
+  fseek(f, 0, SEEK_END);
+  long sz = ftell(f);
+  fseek(f, 0, SEEK_SET);
+  std::vector<unsigned char> buf(sz);
+  if (fread(buf.data(), 1, sz, f) != (size_t)sz) { fclose(f); set_error("short read"); return nullptr; }
+  fclose(f);
+  size_t p = 0;
+  auto rd = [&](void* dst, size_t n) -> bool {
+    if (p + n > (size_t)sz) return false;
+    memcpy(dst, buf.data() + p, n);
+    p += n;
+    return true;
+  };
+  int header[5];
+  if (!rd(header, sizeof(header)) || header[0] != kMjbId || header[1] != (int)sizeof(mjtNum)) {
+    set_error("not an MJB file (bad header) or precision mismatch");
+    return nullptr;
+  }
+  int nsize_expected = 0;
+#define X(name) nsize_expected++;
+  MJMODEL_SIZES
+#undef X
+  if (header[2] != nsize_expected) {
+    set_error("MJB was written by a different mjModel revision (size-field count differs)");
+    return nullptr;
+  }
+  std::vector<mjtSize> sizes(nsize_expected);
+  if (!rd(sizes.data(), sizeof(mjtSize) * nsize_expected)) { set_error("truncated MJB (sizes)"); return nullptr; }
+  mjModel* m = (mjModel*)calloc(1, sizeof(mjModel));
+  {
+    int k = 0;
+#define X(name) m->name = sizes[k++];
+    MJMODEL_SIZES
+#undef X
+  }
+  bool ok = rd(&m->opt, sizeof(mjOption)) && rd(&m->vis, sizeof(mjVisual)) && rd(&m->stat, sizeof(mjStatistic)) &&
+            rd(&m->flg_gravcomp, sizeof(mjtBool)) && rd(&m->flg_surfacevel, sizeof(mjtBool));
+  if (!ok) { free(m); set_error("truncated MJB (structs)"); return nullptr; }
+  // one allocation for all arrays, 64-byte aligned each
+  size_t total = 0;
+  {
+    MJMODEL_POINTERS_PREAMBLE(m)
+#define X(type, name, nr, nc) total += ((sizeof(type) * (size_t)(m->nr) * (size_t)(nc)) + 63) / 64 * 64;
+    MJMODEL_POINTERS
+#undef X
+  }
+  unsigned char* store = (unsigned char*)aligned_alloc(64, total + 64);
+  memset(store, 0, total + 64);
+  m->buffer = store;
+  size_t off = 0;
+  {
+    MJMODEL_POINTERS_PREAMBLE(m)
+#define X(type, name, nr, nc)                                                  \
+    {                                                                          \
+      size_t nb = sizeof(type) * (size_t)(m->nr) * (size_t)(nc);               \
+      m->name = (type*)(store + off);                                          \
+      if (!rd(m->name, nb)) ok = false;                                        \
+      off += (nb + 63) / 64 * 64;                                              \
+    }
+    MJMODEL_POINTERS
+#undef X
+  }
+  if (!ok || p != (size_t)sz) {
+    free(store); free(m);
+    set_error("MJB array section does not match this mjModel revision");
+    return nullptr;
+  }
+  return m;
+}
+
+void free_mjb(mjModel* m) {
+  if (!m) return;
+  free(m->buffer);
+  free(m);
+}
+
+long model_size(const mjModel* m, const char* name) {
+#define X(n) if (!strcmp(name, #n)) return (long)m->n;
+  MJMODEL_SIZES
+#undef X
+  return -1;
+}
+
+int get_option(const mjModel* m, const char* name, double* v) {
+#define X(T, n, sz) if (!strcmp(name, #n)) { *v = (double)m->opt.n; return 0; }
+#define XVEC(T, n, sz)
+  MJOPTION_FIELDS
+#undef X
+#undef XVEC
+  if (!strcmp(name, "gravity_z")) { *v = m->opt.gravity[2]; return 0; }
+  return -1;
+}
+int set_option(mjModel* m, const char* name, double v) {
+#define X(T, n, sz) if (!strcmp(name, #n)) { m->opt.n = (T)v; return 0; }
+#define XVEC(T, n, sz)
+  MJOPTION_FIELDS
+#undef X
+#undef XVEC
+  if (!strcmp(name, "gravity_z")) { m->opt.gravity[2] = v; return 0; }
+  return -1;
+}
+
+// ------------------------------------------------------------------------------------------------
+static bool is_sparse(const mjModel* m) {
+  return m->opt.jacobian == mjJAC_SPARSE || (m->opt.jacobian == mjJAC_AUTO && m->nv >= 60);
+}
+
+// actuator-inherited joint/tendon damping (+poly) and armature
+static double act_damping(const mjModel* m, bool tendon, int id, double poly[mjNPOLY]) {
+  int aid = tendon ? m->tendon_actuatorid[id] : m->jnt_actuatorid[id];
+  if (aid == -1) return 0;
+  double damping = 0;
+  auto add = [&](int k) {
+    double g = m->actuator_gear[6 * m->actuator_outadr[k]];
+    double g2 = g * g;
+    damping += m->actuator_damping[k] * g2;
+    for (int j = 0; j < mjNPOLY; j++) poly[j] += m->actuator_dampingpoly[mjNPOLY * k + j] * g2;
+  };
+  if (aid >= 0) {
+    double g = m->actuator_gear[6 * m->actuator_outadr[aid]];
+    double g2 = g * g;
+    damping = m->actuator_damping[aid] * g2;
+    for (int j = 0; j < mjNPOLY; j++) poly[j] += m->actuator_dampingpoly[mjNPOLY * aid + j] * g2;
+  } else {
+    for (int k = 0; k < m->nactuator; k++) {
+      if (m->actuator_trnid[2 * k] != id) continue;
+      int tt = m->actuator_trntype[k];
+      if (!tendon && tt != mjTRN_JOINT && tt != mjTRN_JOINTINPARENT) continue;
+      if (tendon && tt != mjTRN_TENDON) continue;
+      add(k);
+    }
+  }
+  return damping;
+}
+static double act_armature(const mjModel* m, bool tendon, int id) {
+  int aid = tendon ? m->tendon_actuatorid[id] : m->jnt_actuatorid[id];
+  if (aid == -1) return 0;
+  double arm = 0;
+  if (aid >= 0) {
+    double g = m->actuator_gear[6 * m->actuator_outadr[aid]];
+    arm = m->actuator_armature[aid] * (g * g);
+  } else {
+    for (int k = 0; k < m->nactuator; k++) {
+      if (m->actuator_trnid[2 * k] != id) continue;
+      int tt = m->actuator_trntype[k];
+      if (!tendon && tt != mjTRN_JOINT && tt != mjTRN_JOINTINPARENT) continue;
+      if (tendon && tt != mjTRN_TENDON) continue;
+      double g = m->actuator_gear[6 * m->actuator_outadr[k]];
+      arm += m->actuator_armature[k] * (g * g);
+    }
+  }
+  return arm;
+}
+
+static bool collider_supported(int t1, int t2) {  // t1 <= t2
+  auto is = [&](int a, int b) { return t1 == a && t2 == b; };
+  return is(mjGEOM_PLANE, mjGEOM_SPHERE) || is(mjGEOM_PLANE, mjGEOM_CAPSULE) ||
+         is(mjGEOM_SPHERE, mjGEOM_SPHERE) || is(mjGEOM_SPHERE, mjGEOM_CAPSULE) ||
+         is(mjGEOM_CAPSULE, mjGEOM_CAPSULE);
+}
+static bool collider_defined(int t1, int t2) {  // mjCOLLISIONFUNC != NULL, t1 <= t2
+  if (t1 == mjGEOM_PLANE) return t2 != mjGEOM_PLANE && t2 != mjGEOM_HFIELD;
+  return true;
+}
+
+struct Cand { int g1, g2; };
+
+// static per-pair contact parameters (mj_contactParam with no <pair> overrides)
+static void contact_param(const mjModel* m, int g1, int g2, int* condim, double* solref, double* solimp,
+                          double* friction) {
+  double fri[3];
+  int p1 = m->geom_priority[g1], p2 = m->geom_priority[g2];
+  if (p1 != p2) {
+    int g = p1 > p2 ? g1 : g2;
+    *condim = m->geom_condim[g];
+    memcpy(solref, m->geom_solref + g * mjNREF, mjNREF * sizeof(double));
+    memcpy(solimp, m->geom_solimp + g * mjNIMP, mjNIMP * sizeof(double));
+    memcpy(fri, m->geom_friction + 3 * g, 3 * sizeof(double));
+  } else {
+    *condim = std::max(m->geom_condim[g1], m->geom_condim[g2]);
+    double s1 = m->geom_solmix[g1], s2 = m->geom_solmix[g2], mix;
+    if (s1 >= mjMINVAL && s2 >= mjMINVAL) mix = s1 / (s1 + s2);
+    else if (s1 < mjMINVAL && s2 < mjMINVAL) mix = 0.5;
+    else if (s1 < mjMINVAL) mix = 0.0;
+    else mix = 1.0;
+    const double* r1 = m->geom_solref + g1 * mjNREF;
+    const double* r2 = m->geom_solref + g2 * mjNREF;
+    if (r1[0] > 0 && r2[0] > 0) {
+      for (int i = 0; i < mjNREF; i++) solref[i] = mix * r1[i] + (1 - mix) * r2[i];
+    } else {
+      for (int i = 0; i < mjNREF; i++) solref[i] = std::min(r1[i], r2[i]);
+    }
+    for (int i = 0; i < mjNIMP; i++)
+      solimp[i] = mix * m->geom_solimp[g1 * mjNIMP + i] + (1 - mix) * m->geom_solimp[g2 * mjNIMP + i];
+    for (int i = 0; i < 3; i++) fri[i] = std::max(m->geom_friction[3 * g1 + i], m->geom_friction[3 * g2 + i]);
+  }
+  friction[0] = fri[0]; friction[1] = fri[0]; friction[2] = fri[1]; friction[3] = fri[2]; friction[4] = fri[2];
+  for (int i = 0; i < 5; i++) friction[i] = std::max((double)mjMINMU, friction[i]);  // mj_assignFriction
+}
+
+// ------------------------------------------------------------------------------------------------
+int check_model(const mjModel* m) {
+  char msg[256];
+#define FAIL(...) do { snprintf(msg, sizeof(msg), __VA_ARGS__); set_error(std::string("unsupported: ") + msg); return -2; } while (0)
+  if (m->nv <= 0 || m->nbody < 2) FAIL("model without degrees of freedom");
+  if (m->nflex || m->nhfield || m->nmocap || m->nplugin) FAIL("flex / hfield / mocap / plugin present");
+  if (m->neq) FAIL("equality constraints (neq=%d) are a 'next' row of the scope table", (int)m->neq);
+  if (m->na) FAIL("stateful actuators (na=%d)", (int)m->na);
+  if (m->nsensor) FAIL("sensors (nsensor=%d)", (int)m->nsensor);
+  if (m->npair) FAIL("predefined contact pairs (npair=%d)", (int)m->npair);
+  if (m->nhistory) FAIL("history buffers / delays");
+  if (m->flg_gravcomp) FAIL("gravity compensation");
+  if (m->flg_surfacevel) FAIL("geom surface velocity");
+  if (m->opt.cone != mjCONE_PYRAMIDAL) FAIL("elliptic friction cones");
+  if (m->opt.integrator != mjINT_EULER && m->opt.integrator != mjINT_RK4) FAIL("implicit integrators");
+  if (m->opt.noslip_iterations > 0) FAIL("noslip solver");
+  if (m->opt.enableflags & (mjENBL_OVERRIDE | mjENBL_SLEEP | mjENBL_DIAGEXACT | mjENBL_ENERGY))
+    FAIL("enable flags override/sleep/diagexact/energy");
+  if (m->opt.density != 0 || m->opt.viscosity != 0) FAIL("fluid forces (density/viscosity)");
+  if (m->opt.disableflags & mjDSBL_ISLAND) { /* monolithic solve: fine for single-tree models */ }
+  for (int i = 0; i < m->ngeom; i++) {
+    if (m->geom_adhesion[i] != 0) FAIL("geom adhesion");
+  }
+  for (int i = 0; i < m->ntendon; i++) {
+    if (m->wrap_type[m->tendon_adr[i]] != mjWRAP_JOINT) FAIL("spatial tendons");
+    if (m->tendon_frictionloss[i] != 0) FAIL("tendon frictionloss");
+    if (m->tendon_actfrclimited[i]) FAIL("tendon actuator force limits");
+  }
+  if (m->nout != m->nu || m->nactuator != m->nu) FAIL("multi-input/multi-output actuators");
+  for (int i = 0; i < m->nactuator; i++) {
+    int tt = m->actuator_trntype[i];
+    if (tt != mjTRN_JOINT && tt != mjTRN_JOINTINPARENT) FAIL("actuator %d: non-joint transmission", i);
+    int jt = m->jnt_type[m->actuator_trnid[2 * i]];
+    if (jt != mjJNT_HINGE && jt != mjJNT_SLIDE) FAIL("actuator %d on ball/free joint", i);
+    if (m->actuator_dyntype[i] != mjDYN_NONE) FAIL("actuator %d: activation dynamics", i);
+    if (m->actuator_gaintype[i] != mjGAIN_FIXED && m->actuator_gaintype[i] != mjGAIN_AFFINE) FAIL("actuator %d: gain type", i);
+    if (m->actuator_biastype[i] != mjBIAS_NONE && m->actuator_biastype[i] != mjBIAS_AFFINE) FAIL("actuator %d: bias type", i);
+    if (m->actuator_ctrlnum[i] != 1 || m->actuator_outnum[i] != 1 || m->actuator_ctrladr[i] != i || m->actuator_outadr[i] != i)
+      FAIL("actuator %d: non-scalar control block", i);
+    if (m->actuator_delay[i] != 0) FAIL("actuator %d: delay", i);
+    if (m->actuator_plugin[i] >= 0) FAIL("actuator %d: plugin", i);
+    if (m->opt.disableactuator & (1 << m->actuator_group[i])) FAIL("disabled actuator groups");
+  }
+  for (int i = 0; i < m->ngeom; i++) {
+    int t = m->geom_type[i];
+    if (t == mjGEOM_HFIELD || t == mjGEOM_SDF) FAIL("geom %d: hfield/sdf", i);
+    if (m->geom_contype[i] == 0 && m->geom_conaffinity[i] == 0) continue;
+    if (t == mjGEOM_MESH || t == mjGEOM_ELLIPSOID) FAIL("geom %d: mesh/ellipsoid colliders are a 'next' row", i);
+  }
+#undef FAIL
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+struct Builder {
+  std::vector<int>& ib;
+  std::vector<double>& db;
+  std::vector<std::pair<const int**, size_t>> ifix;
+  std::vector<std::pair<const double**, size_t>> dfix;
+  template <class T>
+  void addI(const int** slot, const T* src, size_t n) {
+    size_t o = ib.size();
+    for (size_t i = 0; i < n; i++) ib.push_back((int)src[i]);
+    if (n == 0) ib.push_back(0);
+    ifix.push_back({slot, o});
+  }
+  void addD(const double** slot, const double* src, size_t n) {
+    size_t o = db.size();
+    for (size_t i = 0; i < n; i++) db.push_back(src[i]);
+    if (n == 0) db.push_back(0);
+    dfix.push_back({slot, o});
+  }
+  void fix() {
+    for (auto& f : ifix) *f.first = ib.data() + f.second;
+    for (auto& f : dfix) *f.first = db.data() + f.second;
+  }
+};
+
+int build_host_model(const mjModel* m, int nconmax, int njmax, HostModel* out) {
+  if (int rc = check_model(m)) return rc;
+  DModel& D = out->dm;
+  memset(&D, 0, sizeof(D));
+  Sizes& S = D.sz;
+  S.nq = m->nq; S.nv = m->nv; S.nu = m->nu; S.na = m->na; S.nbody = m->nbody; S.njnt = m->njnt;
+  S.ngeom = m->ngeom; S.ntendon = m->ntendon; S.nwrap = m->nwrap; S.nJten = m->nJten; S.nC = m->nC;
+  S.ntree = m->ntree;
+
+  Options& O = D.opt;
+  O.timestep = m->opt.timestep; O.impratio = m->opt.impratio; O.tolerance = m->opt.tolerance;
+  O.ls_tolerance = m->opt.ls_tolerance;
+  for (int i = 0; i < 3; i++) O.gravity[i] = m->opt.gravity[i];
+  O.meaninertia = m->stat.meaninertia;
+  O.integrator = m->opt.integrator; O.cone = m->opt.cone; O.solver = m->opt.solver;
+  O.iterations = m->opt.iterations; O.ls_iterations = m->opt.ls_iterations;
+  O.disableflags = m->opt.disableflags; O.enableflags = m->opt.enableflags;
+  O.dense = is_sparse(m) ? 0 : 1;
+
+  Builder B{out->ib, out->db, {}, {}};
+  out->ib.clear(); out->db.clear();
+  out->ib.reserve(1 << 16); out->db.reserve(1 << 16);
+
+  B.addI(&D.body_parentid, m->body_parentid, m->nbody);
+  B.addI(&D.body_rootid, m->body_rootid, m->nbody);
+  B.addI(&D.body_weldid, m->body_weldid, m->nbody);
+  B.addI(&D.body_jntnum, m->body_jntnum, m->nbody);
+  B.addI(&D.body_jntadr, m->body_jntadr, m->nbody);
+  B.addI(&D.body_dofnum, m->body_dofnum, m->nbody);
+  B.addI(&D.body_dofadr, m->body_dofadr, m->nbody);
+  B.addI(&D.body_geomnum, m->body_geomnum, m->nbody);
+  B.addI(&D.body_geomadr, m->body_geomadr, m->nbody);
+  B.addI(&D.body_sameframe, m->body_sameframe, m->nbody);
+  B.addI(&D.jnt_type, m->jnt_type, m->njnt);
+  B.addI(&D.jnt_qposadr, m->jnt_qposadr, m->njnt);
+  B.addI(&D.jnt_dofadr, m->jnt_dofadr, m->njnt);
+  B.addI(&D.jnt_bodyid, m->jnt_bodyid, m->njnt);
+  B.addI(&D.jnt_limited, m->jnt_limited, m->njnt);
+  B.addI(&D.jnt_actfrclimited, m->jnt_actfrclimited, m->njnt);
+  B.addI(&D.dof_bodyid, m->dof_bodyid, m->nv);
+  B.addI(&D.dof_jntid, m->dof_jntid, m->nv);
+  B.addI(&D.dof_parentid, m->dof_parentid, m->nv);
+  B.addI(&D.dof_simplenum, m->dof_simplenum, m->nv);
+  B.addI(&D.dof_treeid, m->dof_treeid, m->nv);
+  B.addI(&D.M_rownnz, m->M_rownnz, m->nv);
+  B.addI(&D.M_rowadr, m->M_rowadr, m->nv);
+  B.addI(&D.M_colind, m->M_colind, m->nC);
+  B.addI(&D.geom_type, m->geom_type, m->ngeom);
+  B.addI(&D.geom_bodyid, m->geom_bodyid, m->ngeom);
+  B.addI(&D.geom_sameframe, m->geom_sameframe, m->ngeom);
+  B.addI(&D.tendon_adr, m->tendon_adr, m->ntendon);
+  B.addI(&D.tendon_num, m->tendon_num, m->ntendon);
+  B.addI(&D.tendon_limited, m->tendon_limited, m->ntendon);
+  B.addI(&D.wrap_type, m->wrap_type, m->nwrap);
+  B.addI(&D.wrap_objid, m->wrap_objid, m->nwrap);
+  B.addI(&D.ten_J_rownnz, m->ten_J_rownnz, m->ntendon);
+  B.addI(&D.ten_J_rowadr, m->ten_J_rowadr, m->ntendon);
+  B.addI(&D.ten_J_colind, m->ten_J_colind, m->nJten);
+  {
+    std::vector<int> trn(m->nu);
+    for (int i = 0; i < m->nu; i++) trn[i] = m->actuator_trnid[2 * i];
+    B.addI(&D.actuator_trnjnt, trn.data(), m->nu);
+  }
+  B.addI(&D.actuator_gaintype, m->actuator_gaintype, m->nu);
+  B.addI(&D.actuator_biastype, m->actuator_biastype, m->nu);
+  B.addI(&D.actuator_ctrllimited, m->actuator_ctrllimited, m->nu);
+  B.addI(&D.actuator_forcelimited, m->actuator_forcelimited, m->nu);
+
+  B.addD(&D.qpos0, m->qpos0, m->nq);
+  B.addD(&D.qpos_spring, m->qpos_spring, m->nq);
+  B.addD(&D.body_pos, m->body_pos, 3 * m->nbody);
+  B.addD(&D.body_quat, m->body_quat, 4 * m->nbody);
+  B.addD(&D.body_ipos, m->body_ipos, 3 * m->nbody);
+  B.addD(&D.body_iquat, m->body_iquat, 4 * m->nbody);
+  B.addD(&D.body_mass, m->body_mass, m->nbody);
+  B.addD(&D.body_subtreemass, m->body_subtreemass, m->nbody);
+  B.addD(&D.body_inertia, m->body_inertia, 3 * m->nbody);
+  B.addD(&D.body_invweight0, m->body_invweight0, 2 * m->nbody);
+  B.addD(&D.jnt_pos, m->jnt_pos, 3 * m->njnt);
+  B.addD(&D.jnt_axis, m->jnt_axis, 3 * m->njnt);
+  B.addD(&D.jnt_stiffness, m->jnt_stiffness, m->njnt);
+  B.addD(&D.jnt_stiffnesspoly, m->jnt_stiffnesspoly, mjNPOLY * m->njnt);
+  B.addD(&D.jnt_range, m->jnt_range, 2 * m->njnt);
+  B.addD(&D.jnt_margin, m->jnt_margin, m->njnt);
+  B.addD(&D.jnt_solref, m->jnt_solref, mjNREF * m->njnt);
+  B.addD(&D.jnt_solimp, m->jnt_solimp, mjNIMP * m->njnt);
+  B.addD(&D.jnt_actfrcrange, m->jnt_actfrcrange, 2 * m->njnt);
+  {
+    std::vector<double> arm(m->nv), dmp(m->nv), dpoly(mjNPOLY * m->nv);
+    int eulerdamp = 0;
+    for (int i = 0; i < m->nv; i++) {
+      int j = m->dof_jntid[i];
+      arm[i] = m->dof_armature[i] + act_armature(m, false, j);
+      double poly[mjNPOLY];
+      for (int k = 0; k < mjNPOLY; k++) poly[k] = m->dof_dampingpoly[mjNPOLY * i + k];
+      dmp[i] = m->dof_damping[i] + act_damping(m, false, j, poly);
+      for (int k = 0; k < mjNPOLY; k++) dpoly[mjNPOLY * i + k] = poly[k];
+      bool polynz = false;
+      for (int k = 0; k < mjNPOLY; k++) polynz |= (m->dof_dampingpoly[mjNPOLY * i + k] != 0);
+      if (m->dof_damping[i] > 0 || polynz || m->jnt_actuatorid[j] != -1) eulerdamp = 1;
+    }
+    if ((m->opt.disableflags & mjDSBL_EULERDAMP) || (m->opt.disableflags & mjDSBL_DAMPER)) eulerdamp = 0;
+    O.eulerdamp = eulerdamp;
+    B.addD(&D.dof_armature_eff, arm.data(), m->nv);
+    B.addD(&D.dof_damping_eff, dmp.data(), m->nv);
+    B.addD(&D.dof_dampingpoly_eff, dpoly.data(), mjNPOLY * m->nv);
+  }
+  B.addD(&D.dof_invweight0, m->dof_invweight0, m->nv);
+  B.addD(&D.dof_M0, m->dof_M0, m->nv);
+  B.addD(&D.dof_frictionloss, m->dof_frictionloss, m->nv);
+  B.addD(&D.dof_solref, m->dof_solref, mjNREF * m->nv);
+  B.addD(&D.dof_solimp, m->dof_solimp, mjNIMP * m->nv);
+  B.addD(&D.geom_pos, m->geom_pos, 3 * m->ngeom);
+  B.addD(&D.geom_quat, m->geom_quat, 4 * m->ngeom);
+  B.addD(&D.geom_size, m->geom_size, 3 * m->ngeom);
+  B.addD(&D.geom_rbound, m->geom_rbound, m->ngeom);
+  B.addD(&D.wrap_prm, m->wrap_prm, m->nwrap);
+  B.addD(&D.tendon_range, m->tendon_range, 2 * m->ntendon);
+  B.addD(&D.tendon_margin, m->tendon_margin, m->ntendon);
+  B.addD(&D.tendon_solref_lim, m->tendon_solref_lim, mjNREF * m->ntendon);
+  B.addD(&D.tendon_solimp_lim, m->tendon_solimp_lim, mjNIMP * m->ntendon);
+  B.addD(&D.tendon_invweight0, m->tendon_invweight0, m->ntendon);
+  B.addD(&D.tendon_stiffness, m->tendon_stiffness, m->ntendon);
+  B.addD(&D.tendon_stiffnesspoly, m->tendon_stiffnesspoly, mjNPOLY * m->ntendon);
+  {
+    std::vector<double> tdmp(m->ntendon), tpoly(mjNPOLY * m->ntendon), tarm(m->ntendon);
+    for (int i = 0; i < m->ntendon; i++) {
+      double poly[mjNPOLY];
+      for (int k = 0; k < mjNPOLY; k++) poly[k] = m->tendon_dampingpoly[mjNPOLY * i + k];
+      tdmp[i] = m->tendon_damping[i] + act_damping(m, true, i, poly);
+      for (int k = 0; k < mjNPOLY; k++) tpoly[mjNPOLY * i + k] = poly[k];
+      tarm[i] = m->tendon_armature[i] + act_armature(m, true, i);
+    }
+    B.addD(&D.tendon_damping_eff, tdmp.data(), m->ntendon);
+    B.addD(&D.tendon_dampingpoly_eff, tpoly.data(), mjNPOLY * m->ntendon);
+    B.addD(&D.tendon_armature_eff, tarm.data(), m->ntendon);
+  }
+  B.addD(&D.tendon_lengthspring, m->tendon_lengthspring, 2 * m->ntendon);
+  {
+    std::vector<double> g0(m->nu), gp(kNGain * m->nu), bp(kNGain * m->nu);
+    for (int i = 0; i < m->nu; i++) {
+      g0[i] = m->actuator_gear[6 * i];
+      for (int k = 0; k < kNGain; k++) {
+        gp[kNGain * i + k] = m->actuator_gainprm[mjNGAIN * i + k];
+        bp[kNGain * i + k] = m->actuator_biasprm[mjNBIAS * i + k];
+      }
+    }
+    B.addD(&D.actuator_gear0, g0.data(), m->nu);
+    B.addD(&D.actuator_gainprm, gp.data(), kNGain * m->nu);
+    B.addD(&D.actuator_biasprm, bp.data(), kNGain * m->nu);
+  }
+  B.addD(&D.actuator_ctrlrange, m->actuator_ctrlrange, 2 * m->nu);
+  B.addD(&D.actuator_forcerange, m->actuator_forcerange, 2 * m->nu);
+
+  int has_lim = 0, has_fl = 0;
+  for (int i = 0; i < m->njnt; i++) has_lim |= m->jnt_limited[i];
+  for (int i = 0; i < m->ntendon; i++) has_lim |= m->tendon_limited[i];
+  for (int i = 0; i < m->nv; i++) has_fl |= (m->dof_frictionloss[i] != 0);
+  O.has_limits = has_lim; O.has_frictionloss = has_fl;
+
+  // ---- static candidate geom pairs, in the order the reference emits their contacts -----------
+  std::vector<int> pg1, pg2, pdim;
+  std::vector<double> pmargin, pinc, psolref, psolimp, pfric;
+  const bool filterparent = !(m->opt.disableflags & mjDSBL_FILTERPARENT);
+  const bool midphase = !(m->opt.disableflags & mjDSBL_MIDPHASE);
+  const bool contacts_on = !(m->opt.disableflags & (mjDSBL_CONSTRAINT | mjDSBL_CONTACT));
+  auto can_collide = [&](int b) { return m->body_contype[b] || m->body_conaffinity[b]; };
+  auto has_plane = [&](int b) {
+    for (int g = m->body_geomadr[b]; g < m->body_geomadr[b] + m->body_geomnum[b]; g++)
+      if (m->geom_type[g] == mjGEOM_PLANE) return true;
+    return false;
+  };
+  auto always = [&](int b) {
+    return (b == 0 && m->body_geomnum[b] > 0) || (m->body_dofnum[m->body_weldid[b]] == 0 && has_plane(b));
+  };
+  for (int b1 = 0; contacts_on && b1 < m->nbody; b1++) {
+    for (int b2 = b1 + 1; b2 < m->nbody; b2++) {
+      if (!can_collide(b1) || !can_collide(b2)) continue;
+      // broadphase membership: SAP covers bodies >= 1; the world body only through always-collide
+      if (b1 == 0 && !always(0)) continue;
+      int w1 = m->body_weldid[b1], w2 = m->body_weldid[b2];
+      int pw1 = m->body_weldid[m->body_parentid[w1]], pw2 = m->body_weldid[m->body_parentid[w2]];
+      if (w1 == w2) continue;
+      if (m->body_dofnum[w1] == 0 && m->body_dofnum[w2] == 0) continue;
+      if (filterparent && w1 != 0 && w2 != 0 && (w1 == pw2 || w2 == pw1)) continue;
+      // add_pair: OR of geom bitmasks
+      int ct1 = 0, ca1 = 0, ct2 = 0, ca2 = 0;
+      for (int g = m->body_geomadr[b1]; g < m->body_geomadr[b1] + m->body_geomnum[b1]; g++) { ct1 |= m->geom_contype[g]; ca1 |= m->geom_conaffinity[g]; }
+      for (int g = m->body_geomadr[b2]; g < m->body_geomadr[b2] + m->body_geomnum[b2]; g++) { ct2 |= m->geom_contype[g]; ca2 |= m->geom_conaffinity[g]; }
+      if (!(ct1 & ca2) && !(ct2 & ca1)) continue;
+      if (!(m->body_contype[b1] & m->body_conaffinity[b2]) && !(m->body_contype[b2] & m->body_conaffinity[b1])) continue;
+      unsigned sig = ((unsigned)b1 << 16) + (unsigned)b2;
+      bool excluded = false;
+      for (int e = 0; e < m->nexclude; e++) if ((unsigned)m->exclude_signature[e] == sig) excluded = true;
+      if (excluded) continue;
+
+      std::vector<Cand> cand;
+      int n1 = m->body_geomnum[b1], n2 = m->body_geomnum[b2];
+      int a1 = m->body_geomadr[b1], a2 = m->body_geomadr[b2];
+      for (int g1 = a1; g1 < a1 + n1; g1++)
+        for (int g2 = a2; g2 < a2 + n2; g2++) {
+          if (!(m->geom_contype[g1] & m->geom_conaffinity[g2]) && !(m->geom_contype[g2] & m->geom_conaffinity[g1])) continue;
+          int x = g1, y = g2;
+          if (m->geom_type[x] > m->geom_type[y]) std::swap(x, y);
+          if (!collider_defined(m->geom_type[x], m->geom_type[y])) continue;
+          cand.push_back({x, y});
+        }
+      bool single = (n1 == 1 && n2 == 1);
+      if (!single && midphase && m->body_bvhadr[b1] >= 0 && m->body_bvhadr[b2] >= 0) {
+        // midphase emits leaves in traversal order, then stable-sorts the pair's contacts by
+        // (geom[0], geom[1]) with geom[0] the lower-type geom: a static order
+        std::stable_sort(cand.begin(), cand.end(), [](const Cand& a, const Cand& b) {
+          if (a.g1 != b.g1) return a.g1 < b.g1;
+          return a.g2 < b.g2;
+        });
+      }
+      for (auto& c : cand) {
+        if (!collider_supported(m->geom_type[c.g1], m->geom_type[c.g2])) {
+          char msg[160];
+          snprintf(msg, sizeof(msg), "unsupported: collider for geom types (%d,%d) (geoms %d,%d) is a 'next' row",
+                   m->geom_type[c.g1], m->geom_type[c.g2], c.g1, c.g2);
+          set_error(msg);
+          return -2;
+        }
+        int condim; double solref[mjNREF], solimp[mjNIMP], fr[5];
+        contact_param(m, c.g1, c.g2, &condim, solref, solimp, fr);
+        double margin = m->geom_margin[c.g1] + m->geom_margin[c.g2];
+        double gap = m->geom_gap[c.g1] + m->geom_gap[c.g2];
+        pg1.push_back(c.g1); pg2.push_back(c.g2); pdim.push_back(condim);
+        pmargin.push_back(margin + gap); pinc.push_back(margin);
+        for (int k = 0; k < mjNREF; k++) psolref.push_back(solref[k]);
+        for (int k = 0; k < mjNIMP; k++) psolimp.push_back(solimp[k]);
+        for (int k = 0; k < 5; k++) pfric.push_back(fr[k]);
+      }
+    }
+  }
+  S.npair = (int)pg1.size();
+  B.addI(&D.pair_geom1, pg1.data(), pg1.size());
+  B.addI(&D.pair_geom2, pg2.data(), pg2.size());
+  B.addI(&D.pair_dim, pdim.data(), pdim.size());
+  B.addD(&D.pair_margin, pmargin.data(), pmargin.size());
+  B.addD(&D.pair_includemargin, pinc.data(), pinc.size());
+  B.addD(&D.pair_solref, psolref.data(), psolref.size());
+  B.addD(&D.pair_solimp, psolimp.data(), psolimp.size());
+  B.addD(&D.pair_friction, pfric.data(), pfric.size());
+
+  // caps replacing the reference arena
+  if (nconmax <= 0) nconmax = std::min(std::max(2 * S.npair, 8), 128);
+  if (njmax <= 0) {
+    int lim = 0;
+    for (int i = 0; i < m->njnt; i++) lim += m->jnt_limited[i] ? 1 : 0;
+    for (int i = 0; i < m->ntendon; i++) lim += m->tendon_limited[i] ? 1 : 0;
+    int fl = 0;
+    for (int i = 0; i < m->nv; i++) fl += (m->dof_frictionloss[i] != 0);
+    njmax = fl + lim + 4 * 24;
+  }
+  S.nconmax = nconmax;
+  S.njmax = njmax;
+  if (O.solver == mjSOL_PGS && !O.dense) { set_error("unsupported: PGS with sparse Jacobian (nv >= 60)"); return -2; }
+  if (!O.dense) { set_error("unsupported: sparse-Jacobian models (nv >= 60) are a 'next' row"); return -2; }
+  if (S.ntree != 1) { set_error("unsupported: multi-tree models (constraint islands) are a 'next' row"); return -2; }
+  if (O.solver != mjSOL_PGS && O.solver != mjSOL_NEWTON) { set_error("unsupported: CG solver"); return -2; }
+
+  B.fix();
+  return 0;
+}
+
+}  // namespace mjb

@@ -1,0 +1,66 @@
+// Per-environment bodies of the launchable operations; shared verbatim by the CUDA kernels
+// (mjb_kernels.cu) and the test-only host emulation (tests/hostemu/hostemu_backend.cc).
+#pragma once
+#include "mjb_forward.h"
+
+namespace mjb {
+
+MJB_HD bool env_has_warning(const Env& d) {
+  FI w = d.warning();
+  for (int i = 0; i < NWARNING; i++) if (w[i]) return true;
+  return false;
+}
+
+MJB_HD void run_stage(const DModel& m, const Batch& b, int e, int stage, int flags) {
+  Env d(m, b, e);
+  if ((flags & 2) && env_has_warning(d)) return;   // rollout: a warned env stops stepping
+  switch (stage) {
+    case 0: stage_position(d, (flags & 1) != 0); break;
+    case 1: stage_velocity(d); break;
+    case 2: stage_solve(d); break;
+    case 3: stage_integrate(d); break;
+    case 4: stage_finish_forward(d); break;
+    default: break;
+  }
+}
+
+// control [nenv][nstep][ncontrol] (reference layout): segments ctrl then qfrc_applied by spec bits
+MJB_HD void run_set_control(const DModel& m, const Batch& b, int e, const double* control, int nstep, int t,
+                            unsigned spec, int ncontrol) {
+  Env d(m, b, e);
+  if (env_has_warning(d)) return;
+  const double* src = control + ((size_t)e * nstep + t) * ncontrol;
+  int k = 0;
+  if (spec & (1u << 6)) { FD c = d.ctrl(); for (int i = 0; i < m.sz.nu; i++) c[i] = src[k++]; }
+  if (spec & (1u << 7)) { FD q = d.qfrc_applied(); for (int i = 0; i < m.sz.nv; i++) q[i] = src[k++]; }
+}
+
+// state [nenv][nstep][nstate] = (time, qpos, qvel)  (mjSTATE_FULLPHYSICS with na == 0)
+MJB_HD void run_get_state(const DModel& m, const Batch& b, int e, double* state, int nstep, int t, int nstate) {
+  Env d(m, b, e);
+  double* dst = state + ((size_t)e * nstep + t) * nstate;
+  int k = 0;
+  dst[k++] = d.time()[0];
+  FD qp = d.qpos(), qv = d.qvel();
+  for (int i = 0; i < m.sz.nq; i++) dst[k++] = qp[i];
+  for (int i = 0; i < m.sz.nv; i++) dst[k++] = qv[i];
+}
+
+// native layouts: ctrl [nstep][nu][stride], state [nstep][nstate][stride] — coalesced across envs
+MJB_HD void run_set_control_native(const DModel& m, const Batch& b, int e, const double* ctrl, int t) {
+  Env d(m, b, e);
+  FD c = d.ctrl();
+  const double* src = ctrl + (size_t)t * m.sz.nu * b.stride + e;
+  for (int i = 0; i < m.sz.nu; i++) c[i] = src[(size_t)i * b.stride];
+}
+MJB_HD void run_get_state_native(const DModel& m, const Batch& b, int e, double* state, int t, int nstate) {
+  Env d(m, b, e);
+  double* dst = state + (size_t)t * nstate * b.stride + e;
+  int k = 0;
+  dst[(size_t)(k++) * b.stride] = d.time()[0];
+  FD qp = d.qpos(), qv = d.qvel();
+  for (int i = 0; i < m.sz.nq; i++) dst[(size_t)(k++) * b.stride] = qp[i];
+  for (int i = 0; i < m.sz.nv; i++) dst[(size_t)(k++) * b.stride] = qv[i];
+}
+
+}  // namespace mjb

@@ -1,0 +1,240 @@
+// Device-side model (flattened, read-only, replicated per GPU) and the batch data layout
+// (structure-of-arrays across environments) for the batched mj_step path.
+//
+// Layout contract.  Every mjData field the hot path touches (reference include/mujoco/mjxmacro.h
+// :842-1030, MJDATA_POINTERS / MJDATA_ARENA_POINTERS) exists per environment, stored
+//   field[elem][env]   (env fastest, row stride = nenv_padded)
+// so that 32 consecutive environments (one warp, one environment per lane) read or write one
+// 256-byte line per element: fully coalesced HBM/L2 traffic, no per-env arena, no pointer chasing.
+// The per-env arena of the reference (contacts, efc_*) is replaced by fixed caps nconmax / njmax;
+// overflow raises the same warning ids (mjWARN_CONTACTFULL / mjWARN_CNSTRFULL).
+//
+// This header is shared by the CUDA build (nvcc, sm_100a) and the test-only host emulation.
+#pragma once
+#include <stddef.h>
+#include "mjb_math.h"
+
+namespace mjb {
+
+// ---- enum values mirrored from reference include/mujoco/mjtype.h (line numbers cited) ----------
+enum { JNT_FREE = 0, JNT_BALL = 1, JNT_SLIDE = 2, JNT_HINGE = 3 };                       // :92-95
+enum { GEOM_PLANE = 0, GEOM_HFIELD = 1, GEOM_SPHERE = 2, GEOM_CAPSULE = 3, GEOM_ELLIPSOID = 4,
+       GEOM_CYLINDER = 5, GEOM_BOX = 6, GEOM_MESH = 7, GEOM_SDF = 8 };                   // :101-109
+enum { CNSTR_EQUALITY = 0, CNSTR_FRICTION_DOF = 1, CNSTR_FRICTION_TENDON = 2, CNSTR_LIMIT_JOINT = 3,
+       CNSTR_LIMIT_TENDON = 4, CNSTR_CONTACT_FRICTIONLESS = 5, CNSTR_CONTACT_PYRAMIDAL = 6,
+       CNSTR_CONTACT_ELLIPTIC = 7 };                                                    // :532-539
+enum { STATE_SATISFIED = 0, STATE_QUADRATIC = 1, STATE_LINEARNEG = 2, STATE_LINEARPOS = 3,
+       STATE_CONE = 4 };                                                                // :544-548
+enum { WARN_INERTIA = 0, WARN_CONTACTFULL = 1, WARN_CNSTRFULL = 2, WARN_BADQPOS = 3,
+       WARN_BADQVEL = 4, WARN_BADQACC = 5, WARN_BADCTRL = 6, WARN_VGEOMFULL = 7, NWARNING = 8 };  // :553-561
+enum { SOL_PGS = 0, SOL_CG = 1, SOL_NEWTON = 2 };                                        // :202-204
+enum { INT_EULER = 0, INT_RK4 = 1, INT_IMPLICIT = 2, INT_IMPLICITFAST = 3 };             // :181-184
+enum { SAMEFRAME_NONE = 0, SAMEFRAME_BODY = 1, SAMEFRAME_INERTIA = 2, SAMEFRAME_BODYROT = 3,
+       SAMEFRAME_INERTIAROT = 4 };                                                      // :457-461
+enum { GAIN_FIXED = 0, GAIN_AFFINE = 1 };                                                // :256-257
+enum { BIAS_NONE = 0, BIAS_AFFINE = 1 };                                                 // :267-268
+enum { DSBL_CONSTRAINT = 1 << 0, DSBL_EQUALITY = 1 << 1, DSBL_FRICTIONLOSS = 1 << 2, DSBL_LIMIT = 1 << 3,
+       DSBL_CONTACT = 1 << 4, DSBL_SPRING = 1 << 5, DSBL_DAMPER = 1 << 6, DSBL_GRAVITY = 1 << 7,
+       DSBL_CLAMPCTRL = 1 << 8, DSBL_WARMSTART = 1 << 9, DSBL_FILTERPARENT = 1 << 10,
+       DSBL_ACTUATION = 1 << 11, DSBL_REFSAFE = 1 << 12, DSBL_EULERDAMP = 1 << 15,
+       DSBL_AUTORESET = 1 << 16, DSBL_ISLAND = 1 << 18 };                                // :54-73
+constexpr int kNPoly = 2;   // mjNPOLY (include/mujoco/mjmodel.h:44)
+constexpr int kNGain = 3;   // leading gain/bias parameters used by the supported actuator family
+
+// ---- model sizes and options --------------------------------------------------------------------
+struct Sizes {
+  int nq, nv, nu, na, nbody, njnt, ngeom, ntendon, nwrap, nJten, nC, ntree;
+  int npair;     // static candidate geom pairs (host-built, reference order)
+  int nconmax;   // per-env contact cap
+  int njmax;     // per-env constraint-row cap
+};
+
+struct Options {
+  double timestep, impratio, tolerance, ls_tolerance;
+  double gravity[3];
+  double meaninertia;   // m->stat.meaninertia
+  int integrator, cone, solver, iterations, ls_iterations, disableflags, enableflags;
+  int dense;            // mj_isSparse(m) == 0
+  int eulerdamp;        // any dof takes the implicit-damping branch of mj_EulerSkip
+  int has_limits;       // any limited joint or tendon
+  int has_frictionloss; // any dof/tendon frictionloss
+};
+
+// model arrays: one int blob and one double blob in device memory; members are pointers into them
+#define MJB_MODEL_INT_FIELDS(X)                                                             \
+  X(body_parentid) X(body_rootid) X(body_weldid) X(body_jntnum) X(body_jntadr) X(body_dofnum) \
+  X(body_dofadr) X(body_geomnum) X(body_geomadr) X(body_sameframe)                          \
+  X(jnt_type) X(jnt_qposadr) X(jnt_dofadr) X(jnt_bodyid) X(jnt_limited) X(jnt_actfrclimited) \
+  X(dof_bodyid) X(dof_jntid) X(dof_parentid) X(dof_simplenum) X(dof_treeid)                  \
+  X(M_rownnz) X(M_rowadr) X(M_colind)                                                       \
+  X(geom_type) X(geom_bodyid) X(geom_sameframe)                                              \
+  X(tendon_adr) X(tendon_num) X(tendon_limited) X(wrap_type) X(wrap_objid)                   \
+  X(ten_J_rownnz) X(ten_J_rowadr) X(ten_J_colind)                                            \
+  X(actuator_trnjnt) X(actuator_gaintype) X(actuator_biastype) X(actuator_ctrllimited)       \
+  X(actuator_forcelimited)                                                                   \
+  X(pair_geom1) X(pair_geom2) X(pair_dim)
+
+#define MJB_MODEL_DBL_FIELDS(X)                                                             \
+  X(qpos0) X(qpos_spring) X(body_pos) X(body_quat) X(body_ipos) X(body_iquat) X(body_mass)   \
+  X(body_subtreemass) X(body_inertia) X(body_invweight0)                                    \
+  X(jnt_pos) X(jnt_axis) X(jnt_stiffness) X(jnt_stiffnesspoly) X(jnt_range) X(jnt_margin)    \
+  X(jnt_solref) X(jnt_solimp) X(jnt_actfrcrange)                                            \
+  X(dof_armature_eff) X(dof_damping_eff) X(dof_dampingpoly_eff) X(dof_invweight0) X(dof_M0)  \
+  X(dof_frictionloss) X(dof_solref) X(dof_solimp)                                           \
+  X(geom_pos) X(geom_quat) X(geom_size) X(geom_rbound)                                       \
+  X(wrap_prm) X(tendon_range) X(tendon_margin) X(tendon_solref_lim) X(tendon_solimp_lim)     \
+  X(tendon_invweight0) X(tendon_stiffness) X(tendon_stiffnesspoly) X(tendon_damping_eff)     \
+  X(tendon_dampingpoly_eff) X(tendon_lengthspring) X(tendon_armature_eff)                    \
+  X(actuator_gear0) X(actuator_gainprm) X(actuator_biasprm) X(actuator_ctrlrange)            \
+  X(actuator_forcerange)                                                                     \
+  X(pair_margin) X(pair_includemargin) X(pair_solref) X(pair_solimp) X(pair_friction)
+
+struct DModel {
+  Sizes sz;
+  Options opt;
+#define X(name) const int* name;
+  MJB_MODEL_INT_FIELDS(X)
+#undef X
+#define X(name) const double* name;
+  MJB_MODEL_DBL_FIELDS(X)
+#undef X
+};
+
+// ---- batch data fields (per environment), sizes in elements -------------------------------------
+// X(name, count)  -- doubles
+#define MJB_DATA_DBL_FIELDS(X, S)                                                            \
+  X(time, 1) X(qpos, S.nq) X(qvel, S.nv) X(ctrl, S.nu) X(qacc_warmstart, S.nv)                \
+  X(qfrc_applied, S.nv)                                                                      \
+  X(xpos, 3 * S.nbody) X(xquat, 4 * S.nbody) X(xmat, 9 * S.nbody) X(xipos, 3 * S.nbody)      \
+  X(ximat, 9 * S.nbody) X(xanchor, 3 * S.njnt) X(xaxis, 3 * S.njnt)                          \
+  X(geom_xpos, 3 * S.ngeom) X(geom_xmat, 9 * S.ngeom) X(subtree_com, 3 * S.nbody)            \
+  X(cinert, 10 * S.nbody) X(cdof, 6 * S.nv) X(crb, 10 * S.nbody) X(M, S.nC) X(qLD, S.nC)      \
+  X(qLDiagInv, S.nv) X(ten_length, S.ntendon) X(ten_J, S.nJten)                              \
+  X(actuator_length, S.nu) X(actuator_moment, S.nu)                                          \
+  X(ten_velocity, S.ntendon) X(actuator_velocity, S.nu) X(cvel, 6 * S.nbody)                 \
+  X(cdof_dot, 6 * S.nv) X(qfrc_spring, S.nv) X(qfrc_damper, S.nv) X(qfrc_passive, S.nv)      \
+  X(qfrc_bias, S.nv) X(actuator_force, S.nu) X(qfrc_actuator, S.nv) X(qfrc_smooth, S.nv)     \
+  X(qacc_smooth, S.nv) X(qfrc_constraint, S.nv) X(qacc, S.nv) X(qH, S.nC)                    \
+  X(qHDiagInv, S.nv)                                                                         \
+  X(con_dist, S.nconmax) X(con_pos, 3 * S.nconmax) X(con_frame, 9 * S.nconmax)               \
+  X(con_includemargin, S.nconmax) X(con_friction, 5 * S.nconmax) X(con_solref, 2 * S.nconmax) \
+  X(con_solimp, 5 * S.nconmax) X(con_mu, S.nconmax)                                          \
+  X(efc_J, S.njmax * S.nv) X(efc_pos, S.njmax) X(efc_margin, S.njmax)                        \
+  X(efc_frictionloss, S.njmax) X(efc_diagA, S.njmax) X(efc_KBIP, 4 * S.njmax)                \
+  X(efc_D, S.njmax) X(efc_R, S.njmax) X(efc_vel, S.njmax) X(efc_aref, S.njmax)               \
+  X(efc_b, S.njmax) X(efc_force, S.njmax)                                                    \
+  X(efc_Y, S.njmax * S.nv) X(efc_AR, S.njmax * S.njmax)                                       \
+  X(scr_body, 12 * S.nbody) X(scr_nv, 8 * S.nv) X(scr_efc, 8 * S.njmax) X(scr_jac, 6 * S.nv)
+
+// ints
+#define MJB_DATA_INT_FIELDS(X, S)                                                            \
+  X(ncon, 1) X(nefc, 1) X(ne, 1) X(nf, 1) X(nl, 1) X(solver_niter, 1) X(warning, NWARNING)     \
+  X(con_geom1, S.nconmax) X(con_geom2, S.nconmax) X(con_dim, S.nconmax)                       \
+  X(con_exclude, S.nconmax) X(con_efcadr, S.nconmax)                                          \
+  X(efc_type, S.njmax) X(efc_id, S.njmax) X(efc_state, S.njmax) X(scr_int, 4 * S.njmax)
+
+struct Layout {
+#define X(name, cnt) long name;
+  MJB_DATA_DBL_FIELDS(X, _)
+  MJB_DATA_INT_FIELDS(X, _)
+#undef X
+  long ndbl, nint;   // elements per environment
+};
+
+inline Layout make_layout(const Sizes& S) {
+  Layout L;
+  long o = 0;
+#define X(name, cnt) L.name = o; o += (long)(cnt);
+  MJB_DATA_DBL_FIELDS(X, S)
+  L.ndbl = o;
+  o = 0;
+  MJB_DATA_INT_FIELDS(X, S)
+  L.nint = o;
+#undef X
+  return L;
+}
+
+// strided view of one field of one environment
+template <class T>
+struct Fld {
+  T* p;
+  size_t s;
+  MJB_HD T& operator[](long i) const { return p[(size_t)i * s]; }
+  MJB_HD Fld operator+(long k) const { return Fld{p + (size_t)k * s, s}; }
+};
+using FD = Fld<double>;
+using FI = Fld<int>;
+
+// batch storage handle (device or host pointers)
+struct Batch {
+  double* dbl;
+  int* itg;
+  size_t stride;   // padded number of environments (row stride)
+  int nenv;
+  Layout L;
+};
+
+// per-environment accessor
+struct Env {
+  const DModel& m;
+  const Batch& b;
+  int e;
+  MJB_HD Env(const DModel& m_, const Batch& b_, int e_) : m(m_), b(b_), e(e_) {}
+#define X(name, cnt) MJB_HD FD name() const { return FD{b.dbl + (size_t)b.L.name * b.stride + e, b.stride}; }
+  MJB_DATA_DBL_FIELDS(X, _)
+#undef X
+#define X(name, cnt) MJB_HD FI name() const { return FI{b.itg + (size_t)b.L.name * b.stride + e, b.stride}; }
+  MJB_DATA_INT_FIELDS(X, _)
+#undef X
+};
+
+// small load/store helpers between strided fields and value types
+MJB_HD V3 ld3(FD f, long i) { return V3{f[i], f[i + 1], f[i + 2]}; }
+MJB_HD void st3(FD f, long i, V3 v) { f[i] = v.x; f[i + 1] = v.y; f[i + 2] = v.z; }
+MJB_HD Q4 ld4(FD f, long i) { return Q4{f[i], f[i + 1], f[i + 2], f[i + 3]}; }
+MJB_HD void st4(FD f, long i, Q4 q) { f[i] = q.w; f[i + 1] = q.x; f[i + 2] = q.y; f[i + 3] = q.z; }
+MJB_HD M3 ld9(FD f, long i) { M3 r; for (int k = 0; k < 9; k++) r.m[k] = f[i + k]; return r; }
+MJB_HD void st9(FD f, long i, const M3& a) { for (int k = 0; k < 9; k++) f[i + k] = a.m[k]; }
+MJB_HD S6 ld6(FD f, long i) { S6 r; for (int k = 0; k < 6; k++) r.v[k] = f[i + k]; return r; }
+MJB_HD void st6(FD f, long i, const S6& a) { for (int k = 0; k < 6; k++) f[i + k] = a.v[k]; }
+MJB_HD I10 ld10(FD f, long i) { I10 r; for (int k = 0; k < 10; k++) r.v[k] = f[i + k]; return r; }
+MJB_HD void st10(FD f, long i, const I10& a) { for (int k = 0; k < 10; k++) f[i + k] = a.v[k]; }
+// dot products in the reference's accumulation order (the summation order is part of parity):
+// dense  : engine_util_blas.c:493-523 (mju_dot)   -> (r0+r2)+(r1+r3), tail added as one grouped sum
+// sparse : engine_util_sparse.h:197-222 (mju_dotSparse) -> same 4 lanes, tail added one by one
+template <class A, class B>
+MJB_HD double dot_ref(int n, A a, B b) {
+  double r0 = 0, r1 = 0, r2 = 0, r3 = 0;
+  int i = 0;
+  for (; i <= n - 4; i += 4) {
+    r0 += a(i) * b(i);
+    r1 += a(i + 1) * b(i + 1);
+    r2 += a(i + 2) * b(i + 2);
+    r3 += a(i + 3) * b(i + 3);
+  }
+  double res = (r0 + r2) + (r1 + r3);
+  const int t = n - i;
+  if (t == 3) res += a(i) * b(i) + a(i + 1) * b(i + 1) + a(i + 2) * b(i + 2);
+  else if (t == 2) res += a(i) * b(i) + a(i + 1) * b(i + 1);
+  else if (t == 1) res += a(i) * b(i);
+  return res;
+}
+template <class A, class B>
+MJB_HD double dot_sparse_ref(int n, A a, B b) {
+  double r0 = 0, r1 = 0, r2 = 0, r3 = 0;
+  int i = 0;
+  for (; i <= n - 4; i += 4) {
+    r0 += a(i) * b(i);
+    r1 += a(i + 1) * b(i + 1);
+    r2 += a(i + 2) * b(i + 2);
+    r3 += a(i + 3) * b(i + 3);
+  }
+  double res = (r0 + r2) + (r1 + r3);
+  for (; i < n; i++) res += a(i) * b(i);
+  return res;
+}
+
+MJB_HD V3 ldc3(const double* p, long i) { return V3{p[i], p[i + 1], p[i + 2]}; }
+MJB_HD Q4 ldc4(const double* p, long i) { return Q4{p[i], p[i + 1], p[i + 2], p[i + 3]}; }
+
+}  // namespace mjb

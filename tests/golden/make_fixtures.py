@@ -1,0 +1,53 @@
+"""Generate the committed fixtures from the reference (run HERE, where /root/reference exists).
+
+  models/*.mjb             compiled mjModel binaries written by the reference's own mj_saveModel
+                           (the GPU box has no /root/reference and no MJCF compiler in the product)
+  tests/golden/*.npz       golden trajectories / per-field dumps produced by the unmodified reference
+                           engine (oracle/_ref/libmujoco_ref.so) on seeded inputs
+
+Usage: python tests/golden/make_fixtures.py
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+from oracle_util import Oracle  # noqa: E402
+
+REF = os.environ.get("MJB_REFERENCE", "/root/reference")
+MODELS = {
+    "humanoid": os.path.join(REF, "model/humanoid/humanoid.xml"),
+}
+
+
+def random_ctrl(nbatch, nstep, nu, seed):
+    rng = np.random.default_rng(seed)
+    return rng.uniform(-1.0, 1.0, size=(nbatch, nstep, nu))
+
+
+def main():
+    os.makedirs(os.path.join(ROOT, "models"), exist_ok=True)
+    for name, path in MODELS.items():
+        o = Oracle(path)
+        o.save_mjb(os.path.join(ROOT, "models", name + ".mjb"))
+        print("wrote models/%s.mjb" % name)
+    # golden trajectories: humanoid, PGS + Euler (BASELINE config 2), 4 envs x 100 steps, random ctrl
+    for solver, tag in ((0, "pgs"), (2, "newton")):
+        o = Oracle(MODELS["humanoid"])
+        o.set_opt("solver", solver)
+        nb, ns = 4, 100
+        nu = o.size("nu")
+        ctrl = random_ctrl(nb, ns, nu, seed=1234)
+        o.reset()
+        s0 = np.tile(o.get_state(), (nb, 1))
+        states, stats, _ = o.rollout(s0, ctrl, nthread=1)
+        np.savez_compressed(os.path.join(ROOT, "tests", "golden", "humanoid_%s_traj.npz" % tag),
+                            state0=s0, ctrl=ctrl, states=states, stats=stats)
+        print("wrote tests/golden/humanoid_%s_traj.npz" % tag, "mean ncon/nefc/niter per step:",
+              stats[:, :3].mean(0) / ns)
+
+
+if __name__ == "__main__":
+    main()

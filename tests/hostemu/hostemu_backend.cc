@@ -1,0 +1,63 @@
+// TEST INFRASTRUCTURE — host emulation backend, never part of the product.
+//
+// Implements mujoco_b200/csrc/mjb_backend.h with plain host loops over environments so that the
+// exact kernel source (mjb_stage.h and everything it includes) can be compiled by g++ and checked
+// bit-for-bit against the oracle in a container that has no GPU.  The product library
+// (libmjb200.so) never links this file and the mujoco_b200 package never loads the resulting
+// tests/hostemu/libmjb_hostemu.so; GPU parity tests always go through the CUDA library.
+#include <cstdlib>
+#include <cstring>
+
+#include "../../mujoco_b200/csrc/mjb_backend.h"
+#include "../../mujoco_b200/csrc/mjb_stage.h"
+
+namespace mjb {
+namespace backend {
+
+static long g_launches = 0;
+const char* name() { return "hostemu"; }
+int init(int) { return 0; }
+void* dev_alloc(size_t bytes) { return calloc(bytes ? bytes : 1, 1); }
+void dev_free(void* p) { free(p); }
+int h2d(void* dst, const void* src, size_t bytes, void*) { memcpy(dst, src, bytes); return 0; }
+int d2h(void* dst, const void* src, size_t bytes, void*) { memcpy(dst, src, bytes); return 0; }
+int dev_zero(void* dst, size_t bytes, void*) { memset(dst, 0, bytes); return 0; }
+void* stream_create() { return nullptr; }
+void stream_destroy(void*) {}
+int sync(void*) { return 0; }
+long launches() { return g_launches; }
+
+int launch_stage(const DModel& dm, const Batch& b, int stage, int flags, void*) {
+  g_launches++;
+  for (int e = 0; e < b.nenv; e++) run_stage(dm, b, e, stage, flags);
+  return 0;
+}
+int launch_reset(const DModel& dm, const Batch& b, void*) {
+  g_launches++;
+  for (int e = 0; e < b.nenv; e++) { Env d(dm, b, e); reset_env(d, true); }
+  return 0;
+}
+int launch_set_control(const DModel& dm, const Batch& b, const double* control, int nstep, int t, unsigned spec,
+                       int ncontrol, void*) {
+  g_launches++;
+  for (int e = 0; e < b.nenv; e++) run_set_control(dm, b, e, control, nstep, t, spec, ncontrol);
+  return 0;
+}
+int launch_get_state(const DModel& dm, const Batch& b, double* state, int nstep, int t, int nstate, void*) {
+  g_launches++;
+  for (int e = 0; e < b.nenv; e++) run_get_state(dm, b, e, state, nstep, t, nstate);
+  return 0;
+}
+int launch_set_control_native(const DModel& dm, const Batch& b, const double* ctrl, int t, void*) {
+  g_launches++;
+  for (int e = 0; e < b.nenv; e++) run_set_control_native(dm, b, e, ctrl, t);
+  return 0;
+}
+int launch_get_state_native(const DModel& dm, const Batch& b, double* state, int t, int nstate, void*) {
+  g_launches++;
+  for (int e = 0; e < b.nenv; e++) run_get_state_native(dm, b, e, state, t, nstate);
+  return 0;
+}
+
+}  // namespace backend
+}  // namespace mjb
