@@ -1,0 +1,307 @@
+#!/usr/bin/env python
+"""bench.py — env-steps/sec of the batched mj_step hot path (BASELINE.json metric).
+
+Workload (config.workload): BASELINE configs[1] — model/humanoid/humanoid.xml, 4096 environments per
+GPU, PGS solver, Euler integrator, i.i.d. uniform random ctrl in [-1,1] (seeded), fp64.
+A "step" is one mj_step of every environment of the batch.  Before timing, every environment is
+rolled SETTLE steps (untimed, fixed, not part of --warmup) so the timed window is the contact-rich
+steady state (humanoids on the floor), then W warm-up steps, then exactly K timed steps.
+
+  value   : HBM-resident throughput — controls pre-generated on the device, states stay on the device
+  e2e     : through the reference-facing C-ABI call with HOST buffers: per step, ctrl [nenv,nu] is
+            copied from pinned host memory, the step runs, the FULLPHYSICS state [nenv,nstate] is
+            copied back (mjb_step_host)
+  roofline: for the dominant kernel (k_stage stage 2 = constraint solve unless the stage timing pass
+            says otherwise): algorithmic bytes / launch over its CUDA-event time
+  cpu_baseline / --impl reference: the UNMODIFIED reference engine (oracle/_ref/libmujoco_ref.so,
+            compiled from /root/reference) stepping the same workload on the host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+NENV = int(os.environ.get("MJB_BENCH_NENV", 4096))
+SETTLE = int(os.environ.get("MJB_BENCH_SETTLE", 300))
+MODEL = os.path.join(ROOT, "models", "humanoid.mjb")
+METRIC = "env-steps/sec (whole box) humanoid.xml batch 4096/GPU, PGS, Euler, random ctrl"
+WORKLOAD = "humanoid.xml x%d envs/GPU, solver=PGS, integrator=Euler, ctrl~U[-1,1] (configs[1])" % NENV
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p)).get("hbm_gbs", 6650.0), "measured"
+    return 6650.0, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    def __init__(self, index=0):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                self.rows.append([x.strip() for x in out.strip().split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        sm, mx, reasons = [], 0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = max(mx, float(r[1]))
+                for n, v in zip(names, r[2:6]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons)}
+
+
+def reference_arm(args, rank, world):
+    """the reference's own CPU mj_step (unmodified engine) on the same workload, all host threads"""
+    if rank != 0:
+        return
+    from oracle_util import Oracle, available
+    if not available():
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libmujoco_ref.so not built on this box"}))
+        return
+    o = Oracle(MODEL)
+    o.set_opt("solver", 0)
+    nu, cores = o.size("nu"), os.cpu_count() or 1
+    nthread = cores
+    # each "step" = one mj_step of a bounded sample of the batch, sized to ~0.25 s per step
+    sample = min(NENV, max(nthread * 8, 256))
+    rng = np.random.default_rng(0)
+    o.reset()
+    s0 = np.tile(o.get_state(), (sample, 1))
+    # settle to the contact-rich regime like the GPU arm
+    ctrl = rng.uniform(-1, 1, (sample, SETTLE, nu))
+    st, _, _ = o.rollout(s0, ctrl, nthread=nthread, want_state=True)
+    s0 = st[:, -1, :].copy()
+    if args.warmup:
+        ctrl = rng.uniform(-1, 1, (sample, args.warmup, nu))
+        st, _, _ = o.rollout(s0, ctrl, nthread=nthread, want_state=True)
+        s0 = st[:, -1, :].copy()
+    ctrl = rng.uniform(-1, 1, (sample, args.steps, nu))
+    _, stats, sec = o.rollout(s0, ctrl, nthread=nthread, want_state=False)
+    value = sample * args.steps / sec
+    line = {
+        "metric": METRIC, "value": value, "unit": "env-steps/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * sec / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "reference",
+        "config": {"workload": WORKLOAD, "sample": "%d of %d envs per step (bounded CPU sample)" % (sample, NENV)},
+        "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": nthread, "kind": "reference",
+                         "sample": "%d envs x %d steps, mjo_rollout threads=%d" % (sample, args.steps, nthread)},
+        "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "mean_ncon": float(stats[:, 0].mean() / args.steps), "mean_nefc": float(stats[:, 1].mean() / args.steps),
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", 0))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+
+    if args.impl == "reference":
+        reference_arm(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import mujoco_b200 as mb
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    K, W = args.steps, max(args.warmup, 3)
+
+    model = mb.Model(MODEL)
+    model.set_option("solver", mb.SOLVER_PGS)
+    model.set_option("integrator", mb.INT_EULER)
+    nu, nq, nv = model.size("nu"), model.size("nq"), model.size("nv")
+    batch = mb.Batch(model, NENV, device=local_rank)
+    stride = batch.env_stride()
+    stream = torch.cuda.ExternalStream(batch.stream(), device=local_rank)
+    nstate = 1 + nq + nv
+
+    gen = torch.Generator(device="cuda")
+    gen.manual_seed(1000 + rank)
+
+    def make_ctrl(n):   # native layout [n][nu][stride]
+        return (torch.rand((n, nu, stride), generator=gen, device="cuda", dtype=torch.float64) * 2 - 1).contiguous()
+
+    # ---- settle (untimed) + warm-up
+    batch.reset()
+    c = make_ctrl(SETTLE)
+    torch.cuda.synchronize()
+    batch.rollout_device(SETTLE, c.data_ptr(), 0)
+    stream.synchronize()
+    c = make_ctrl(W)
+    torch.cuda.synchronize()
+    batch.rollout_device(W, c.data_ptr(), 0)
+    stream.synchronize()
+
+    # ---- timed region: K steps, controls and states HBM-resident
+    c = make_ctrl(K)
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = batch.kernel_launches()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    d_last = torch.empty((1, nstate, stride), device="cuda", dtype=torch.float64)
+    batch.rollout_device(K - 1, c.data_ptr(), 0)
+    batch.rollout_device(1, c[K - 1:].data_ptr(), d_last.data_ptr())
+    if world > 1:
+        # boundary collective: ONE all-gather of per-env episode returns (final torso height),
+        # enqueued on the batch stream right behind the last step
+        with torch.cuda.stream(stream):
+            ret = d_last[0, 3, :NENV].contiguous()
+            gathered = torch.empty((world, NENV), device="cuda", dtype=torch.float64)
+            dist.all_gather_into_tensor(gathered, ret)
+    ev1.record(stream)
+    stream.synchronize()
+    torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1)
+    launches = batch.kernel_launches() - launches0
+    if world > 1:
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    sampler.stop_flag = True
+    value = NENV * world * K / (ms * 1e-3)
+
+    # workload statistics at the end of the timed window
+    ncon = batch.field("ncon")[:, 0].astype(np.float64)
+    nefc = batch.field("nefc")[:, 0].astype(np.float64)
+    niter = batch.field("solver_niter")[:, 0].astype(np.float64)
+    warn = int(batch.warnings().sum())
+
+    # ---- per-stage timing pass (CUDA events on the launching stream), 20 steps
+    stage_ms = np.zeros(4)
+    nprobe = 20
+    torch.cuda.synchronize()
+    for t_ in range(nprobe):
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+        for s in range(4):
+            evs[s].record(stream)
+            batch.run_stages(s, s)
+        evs[4].record(stream)
+        stream.synchronize()
+        for s in range(4):
+            stage_ms[s] += evs[s].elapsed_time(evs[s + 1])
+    stage_ms /= nprobe
+    dom = int(np.argmax(stage_ms))
+
+    # ---- roofline of the dominant kernel
+    peak, peak_src = peaks()
+    m_nefc, m_nefc2, m_ncon = float(nefc.mean()), float((nefc ** 2).mean()), float(ncon.mean())
+    m_iter = float(niter.mean())
+    L = batch.L
+    fixed = sum(int(L.mjb_field_size(batch.ptr, f.encode())) for f in
+                ["xpos", "xquat", "xmat", "xipos", "ximat", "xanchor", "xaxis", "geom_xpos", "geom_xmat", "subtree_com",
+                 "cinert", "cdof", "crb", "M", "qLD", "qLDiagInv", "ten_length", "ten_J", "actuator_length",
+                 "actuator_moment"])
+    b_pos = 8 * (nq + fixed) + m_ncon * 8 * 27 + m_nefc * 8 * (nv + 10) + 8 * m_nefc * nv + 8 * m_nefc2
+    fixed_v = sum(int(L.mjb_field_size(batch.ptr, f.encode())) for f in
+                  ["ten_velocity", "actuator_velocity", "cvel", "cdof_dot", "qfrc_spring", "qfrc_damper", "qfrc_passive",
+                   "qfrc_bias", "actuator_force", "qfrc_actuator", "qfrc_smooth", "qacc_smooth"])
+    b_vel = 8 * (nv + nu + fixed_v) + m_nefc * 8 * (nv + 6) + 8 * m_nefc2
+    b_sol = 8 * m_nefc2 + 8 * 6 * m_nefc            # AR read once + b, force, R, floss, state
+    b_int = 8 * (2 * 243 + 6 * nv + nq) + m_nefc * 8 * (nv + 1)
+    bytes_per_env = [b_pos, b_vel, b_sol, b_int]
+    achieved = NENV * bytes_per_env[dom] / (stage_ms[dom] * 1e-3) / 1e9
+    b_mjdata = sum(bytes_per_env)
+    roof = {"bound": "hbm", "kernel": "k_stage(stage=%d:%s)" % (dom, ["position", "velocity", "solve", "integrate"][dom]),
+            "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
+            "traffic": None, "algorithmic_bytes_per_env_step": b_mjdata,
+            "whole_step_achieved_gbs": value / world * b_mjdata / 1e9,
+            "stage_ms": [float(x) for x in stage_ms]}
+
+    # ---- e2e: per step H2D ctrl from pinned host, step, D2H state
+    ke = min(K, 100)
+    h_ctrl = torch.rand((ke, NENV, nu), dtype=torch.float64).mul_(2).sub_(1).pin_memory()
+    h_state = torch.empty((NENV, nstate), dtype=torch.float64).pin_memory()
+    for t_ in range(3):
+        batch.step_host(h_ctrl[t_], h_state)
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for t_ in range(ke):
+        batch.step_host(h_ctrl[t_], h_state)
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        tt = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e_s = float(tt.item())
+    e2e = {"value": NENV * world * ke / e2e_s, "unit": "env-steps/s", "h2d_bytes_per_step": NENV * nu * 8,
+           "d2h_bytes_per_step": NENV * nstate * 8, "steps": ke}
+
+    # ---- CPU baseline (rank 0, N=1 only): reference engine on a bounded sample, all host cores
+    cpu = None
+    if rank == 0 and world == 1:
+        try:
+            from oracle_util import Oracle, available
+            if available():
+                o = Oracle(MODEL)
+                o.set_opt("solver", 0)
+                cores = os.cpu_count() or 1
+                sample, csteps = max(cores * 8, 128), 50
+                s_now = batch.get_state()[:sample]
+                rng = np.random.default_rng(1)
+                cctrl = rng.uniform(-1, 1, (sample, csteps, nu))
+                _, cst, sec = o.rollout(s_now, cctrl, nthread=cores, want_state=False)
+                cpu = {"value": sample * csteps / sec, "unit": "env-steps/s", "cores": cores, "kind": "reference",
+                       "sample": "%d envs (GPU batch states at end of timed window) x %d steps, %d threads" % (sample, csteps, cores)}
+        except Exception as ex:  # noqa: BLE001
+            cpu = {"value": None, "unit": "env-steps/s", "cores": os.cpu_count(), "kind": "reference", "sample": "failed: %s" % ex}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": WORKLOAD, "nenv_per_gpu": NENV, "settle_steps": SETTLE,
+                       "l2": "per-step working set %.0f MB/GPU > 126 MB L2 (inputs larger than L2)" %
+                             (batch.L.mjb_field_size(batch.ptr, b"efc_AR") * 8 * NENV / 1e6),
+                       "mean_ncon": m_ncon, "mean_nefc": m_nefc, "mean_pgs_iter": m_iter, "warnings": warn},
+            "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+            "clocks": sampler.summary(),
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -100,6 +100,11 @@ MJB_API int mjb_rollout(mjbBatch* b, int nstep, unsigned int control_spec,
                         const double* state0, const double* warmstart0, const double* control,
                         double* state, double* sensordata);
 
+/* One mj_step for every environment with per-step host I/O (the end-to-end call an RL loop makes):
+ * ctrl [nenv][nu] host (pinned for best speed) is copied in, the step runs, and the new
+ * mjSTATE_FULLPHYSICS state [nenv][nstate] is copied back; returns after the copy completed. */
+MJB_API int mjb_step_host(mjbBatch* b, const double* ctrl, double* state_out);
+
 /* Same, with DEVICE-resident control / state buffers in the library's native layout
  * ([nstep][ncontrol][nenv_stride] and [nstep][nstate][nenv_stride]); used by bench.py's
  * HBM-resident throughput measurement.  Either pointer may be NULL. */

@@ -55,6 +55,7 @@ def _bind(cdll):
     L.mjb_forward.argtypes = [vp]
     L.mjb_step.argtypes = [vp, i]
     L.mjb_rollout.argtypes = [vp, i, u, vp, vp, vp, vp, vp]
+    L.mjb_step_host.argtypes = [vp, vp, vp]
     L.mjb_rollout_device.argtypes = [vp, i, vp, vp]
     L.mjb_env_stride.restype = l
     L.mjb_env_stride.argtypes = [vp]
@@ -181,6 +182,23 @@ class Batch:
 
     def step(self, nstep=1):
         self._chk(self.L.mjb_step(self.ptr, int(nstep)))
+
+    def step_host(self, ctrl, state_out):
+        """one step with host I/O: ctrl [nenv,nu] in, FULLPHYSICS state [nenv,nstate] out (numpy or
+        pinned torch tensors' data pointers)"""
+        cp_ = ctrl.ctypes.data if hasattr(ctrl, "ctypes") else ctrl.data_ptr()
+        sp_ = state_out.ctypes.data if hasattr(state_out, "ctypes") else state_out.data_ptr()
+        self._chk(self.L.mjb_step_host(self.ptr, cp_, sp_))
+
+    def rollout_device(self, nstep, d_ctrl=0, d_state=0):
+        """asynchronous device-resident rollout (native layouts); synchronise on self.stream()"""
+        self._chk(self.L.mjb_rollout_device(self.ptr, int(nstep), d_ctrl or None, d_state or None))
+
+    def stream(self):
+        return self.L.mjb_stream(self.ptr)
+
+    def env_stride(self):
+        return int(self.L.mjb_env_stride(self.ptr))
 
     def run_stages(self, first, last):
         self._chk(self.L.mjb_run_stages(self.ptr, first, last))

@@ -34,6 +34,8 @@ struct mjbBatch_ {
   Batch b;               // device storage
   void* stream = nullptr;
   int device = 0;
+  double* io_ctrl = nullptr;    // staging for mjb_step_host
+  double* io_state = nullptr;
 };
 
 static int fail(int code, const std::string& msg) { set_error(msg); return code; }
@@ -100,6 +102,8 @@ void mjb_free_batch(mjbBatch* B) {
   backend::dev_free(B->b.itg);
   backend::dev_free(B->d_ib);
   backend::dev_free(B->d_db);
+  backend::dev_free(B->io_ctrl);
+  backend::dev_free(B->io_state);
   backend::stream_destroy(B->stream);
   delete B;
 }
@@ -262,6 +266,24 @@ int mjb_rollout(mjbBatch* B, int nstep, unsigned int control_spec, const double*
   if (!rc) rc = backend::sync(B->stream);
   backend::dev_free(d_control);
   backend::dev_free(d_state);
+  return rc;
+}
+
+int mjb_step_host(mjbBatch* B, const double* ctrl, double* state_out) {
+  if (!B || !ctrl || !state_out) return fail(MJB_ERR_ARG, "mjb_step_host: bad arguments");
+  const int nenv = B->b.nenv, nu = B->hm.dm.sz.nu;
+  const int nstate = 1 + B->hm.dm.sz.nq + B->hm.dm.sz.nv;
+  if (!B->io_ctrl) {
+    B->io_ctrl = (double*)backend::dev_alloc((size_t)nenv * nu * sizeof(double));
+    B->io_state = (double*)backend::dev_alloc((size_t)nenv * nstate * sizeof(double));
+    if (!B->io_ctrl || !B->io_state) return fail(MJB_ERR_CUDA, "device allocation failed (io staging)");
+  }
+  int rc = backend::h2d(B->io_ctrl, ctrl, (size_t)nenv * nu * sizeof(double), B->stream);
+  if (!rc) rc = backend::launch_set_control(B->dm, B->b, B->io_ctrl, 1, 0, ST_CTRL, nu, B->stream);
+  for (int s = 0; s < 4 && !rc; s++) rc = backend::launch_stage(B->dm, B->b, s, 1, B->stream);
+  if (!rc) rc = backend::launch_get_state(B->dm, B->b, B->io_state, 1, 0, nstate, B->stream);
+  if (!rc) rc = backend::d2h(state_out, B->io_state, (size_t)nenv * nstate * sizeof(double), B->stream);
+  if (!rc) rc = backend::sync(B->stream);
   return rc;
 }
 
