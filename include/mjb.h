@@ -73,6 +73,9 @@ MJB_API int mjb_set_option(struct mjModel_* m, const char* name, double value);
  * (0 = library default for the model).  m->opt is captured at creation. */
 MJB_API mjbBatch* mjb_make_batch(const struct mjModel_* m, int nenv, int nconmax, int njmax, int device);
 MJB_API void mjb_free_batch(mjbBatch* b);
+/* thread mapping used by batches created afterwards: 1 (default) = one warp per environment with
+ * env-major storage, 0 = one lane per environment with field-major (SoA across envs) storage */
+MJB_API int mjb_set_thread_mapping(int warp_per_env);
 MJB_API int mjb_nenv(const mjbBatch* b);
 
 /* mj_resetData on every environment: qpos = qpos0, everything else zero */

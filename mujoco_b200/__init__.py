@@ -47,6 +47,7 @@ def _bind(cdll):
     L.mjb_make_batch.restype = vp
     L.mjb_make_batch.argtypes = [vp, i, i, i, i]
     L.mjb_free_batch.argtypes = [vp]
+    L.mjb_set_thread_mapping.argtypes = [i]
     L.mjb_nenv.argtypes = [vp]
     L.mjb_reset.argtypes = [vp]
     L.mjb_state_size.argtypes = [vp, u]
@@ -134,9 +135,10 @@ class Model:
 class Batch:
     """nenv environments of one model, resident on one GPU"""
 
-    def __init__(self, model, nenv, nconmax=0, njmax=0, device=-1):
+    def __init__(self, model, nenv, nconmax=0, njmax=0, device=-1, warp_per_env=True):
         self.L = model.L
         self.model = model
+        self.L.mjb_set_thread_mapping(1 if warp_per_env else 0)
         self.ptr = self.L.mjb_make_batch(model.ptr, int(nenv), int(nconmax), int(njmax), int(device))
         if not self.ptr:
             raise MjbError(_err(self.L))

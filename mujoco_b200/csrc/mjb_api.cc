@@ -36,9 +36,43 @@ struct mjbBatch_ {
   int device = 0;
   double* io_ctrl = nullptr;    // staging for mjb_step_host
   double* io_state = nullptr;
+  void* stage = nullptr;        // dense staging for field I/O
+  size_t stage_bytes = 0;
 };
 
 static int fail(int code, const std::string& msg) { set_error(msg); return code; }
+
+// thread mapping for new batches: 1 = one warp per environment (default), 0 = one lane per environment
+static int g_warp_per_env = 1;
+
+// ---- layout-agnostic field movement through a dense [nenv][cnt] device staging buffer ----------
+static int stage_reserve(mjbBatch* B, size_t bytes) {
+  if (B->stage_bytes >= bytes) return 0;
+  backend::sync(B->stream);
+  backend::dev_free(B->stage);
+  B->stage = backend::dev_alloc(bytes);
+  B->stage_bytes = B->stage ? bytes : 0;
+  return B->stage ? 0 : fail(MJB_ERR_CUDA, "device allocation failed (staging)");
+}
+static int field_to_host(mjbBatch* B, bool is_int, long off, long cnt, void* host) {
+  const size_t bytes = (size_t)B->b.nenv * cnt * (is_int ? sizeof(int) : sizeof(double));
+  if (!bytes) return 0;
+  if (int rc = stage_reserve(B, bytes)) return rc;
+  if (int rc = backend::launch_pack(B->b, is_int, off, cnt, B->stage, 1, B->stream)) return rc;
+  if (int rc = backend::d2h(host, B->stage, bytes, B->stream)) return rc;
+  return backend::sync(B->stream);
+}
+static int field_from_host(mjbBatch* B, bool is_int, long off, long cnt, const void* host) {
+  const size_t bytes = (size_t)B->b.nenv * cnt * (is_int ? sizeof(int) : sizeof(double));
+  if (!bytes) return 0;
+  if (int rc = stage_reserve(B, bytes)) return rc;
+  if (int rc = backend::h2d(B->stage, host, bytes, B->stream)) return rc;
+  if (int rc = backend::launch_pack(B->b, is_int, off, cnt, B->stage, 0, B->stream)) return rc;
+  return backend::sync(B->stream);
+}
+static int field_zero(mjbBatch* B, bool is_int, long off, long cnt) {
+  return backend::launch_fill_zero(B->b, is_int, off, cnt, B->stream);
+}
 
 extern "C" {
 
@@ -86,7 +120,16 @@ mjbBatch* mjb_make_batch(const struct mjModel_* m, int nenv, int nconmax, int nj
   b.nenv = nenv;
   b.stride = ((size_t)nenv + 31) / 32 * 32;
   b.L = make_layout(H.sz);
-  size_t nd = (size_t)b.L.ndbl * b.stride, ni = (size_t)b.L.nint * b.stride;
+  b.warp_per_env = g_warp_per_env;
+  if (b.warp_per_env) {
+    b.dpitch = ((size_t)b.L.ndbl + 15) / 16 * 16; b.dstep = 1;
+    b.ipitch = ((size_t)b.L.nint + 31) / 32 * 32; b.istep = 1;
+  } else {
+    b.dpitch = 1; b.dstep = b.stride;
+    b.ipitch = 1; b.istep = b.stride;
+  }
+  size_t nd = b.warp_per_env ? b.dpitch * b.stride : (size_t)b.L.ndbl * b.stride;
+  size_t ni = b.warp_per_env ? b.ipitch * b.stride : (size_t)b.L.nint * b.stride;
   b.dbl = (double*)backend::dev_alloc(nd * sizeof(double));
   b.itg = (int*)backend::dev_alloc(ni * sizeof(int));
   if (!b.dbl || !b.itg) { set_error("device allocation failed (batch)"); mjb_free_batch(B); return nullptr; }
@@ -104,6 +147,7 @@ void mjb_free_batch(mjbBatch* B) {
   backend::dev_free(B->d_db);
   backend::dev_free(B->io_ctrl);
   backend::dev_free(B->io_state);
+  backend::dev_free(B->stage);
   backend::stream_destroy(B->stream);
   delete B;
 }
@@ -146,25 +190,18 @@ int mjb_state_size(const mjbBatch* B, unsigned int sig) {
   return n;
 }
 
-static int copy_rows_d2h(mjbBatch* B, long off, int n, std::vector<double>* host) {
-  host->resize((size_t)n * B->b.stride);
-  return backend::d2h(host->data(), B->b.dbl + (size_t)off * B->b.stride, host->size() * sizeof(double), B->stream);
-}
-
 int mjb_set_state(mjbBatch* B, const double* state, unsigned int sig) {
   std::vector<Seg> segs;
   if (!B || !state || state_segments(B, sig, &segs)) return fail(MJB_ERR_ARG, "mjb_set_state: bad arguments / unsupported signature");
   int ns = 0;
   for (auto& s : segs) ns += s.n;
-  const size_t st = B->b.stride;
   std::vector<double> tmp;
   int col = 0;
   for (auto& s : segs) {
-    tmp.assign((size_t)s.n * st, 0.0);
-    for (int i = 0; i < s.n; i++)
-      for (int e = 0; e < B->b.nenv; e++) tmp[(size_t)i * st + e] = state[(size_t)e * ns + col + i];
-    if (int rc = backend::h2d(B->b.dbl + (size_t)s.off * st, tmp.data(), tmp.size() * sizeof(double), B->stream)) return rc;
-    if (int rc = backend::sync(B->stream)) return rc;
+    tmp.resize((size_t)s.n * B->b.nenv);
+    for (int e = 0; e < B->b.nenv; e++)
+      for (int i = 0; i < s.n; i++) tmp[(size_t)e * s.n + i] = state[(size_t)e * ns + col + i];
+    if (int rc = field_from_host(B, false, s.off, s.n, tmp.data())) return rc;
     col += s.n;
   }
   return 0;
@@ -175,14 +212,13 @@ int mjb_get_state(mjbBatch* B, double* state, unsigned int sig) {
   if (!B || !state || state_segments(B, sig, &segs)) return fail(MJB_ERR_ARG, "mjb_get_state: bad arguments / unsupported signature");
   int ns = 0;
   for (auto& s : segs) ns += s.n;
-  const size_t st = B->b.stride;
   std::vector<double> tmp;
   int col = 0;
   for (auto& s : segs) {
-    if (int rc = copy_rows_d2h(B, s.off, s.n, &tmp)) return rc;
-    if (int rc = backend::sync(B->stream)) return rc;
-    for (int i = 0; i < s.n; i++)
-      for (int e = 0; e < B->b.nenv; e++) state[(size_t)e * ns + col + i] = tmp[(size_t)i * st + e];
+    tmp.resize((size_t)s.n * B->b.nenv);
+    if (int rc = field_to_host(B, false, s.off, s.n, tmp.data())) return rc;
+    for (int e = 0; e < B->b.nenv; e++)
+      for (int i = 0; i < s.n; i++) state[(size_t)e * ns + col + i] = tmp[(size_t)e * s.n + i];
     col += s.n;
   }
   return 0;
@@ -230,17 +266,14 @@ int mjb_rollout(mjbBatch* B, int nstep, unsigned int control_spec, const double*
   for (auto& s : csegs) ncontrol += s.n;
   // defaults for unspecified user inputs, initial state, warmstart, warning counters
   {
-    const size_t st = B->b.stride;
-    if (!(control_spec & ST_CTRL) || !control)
-      backend::dev_zero(B->b.dbl + (size_t)B->b.L.ctrl * st, (size_t)B->hm.dm.sz.nu * st * sizeof(double), B->stream);
-    if (!(control_spec & ST_QFRC_APPLIED) || !control)
-      backend::dev_zero(B->b.dbl + (size_t)B->b.L.qfrc_applied * st, (size_t)nv * st * sizeof(double), B->stream);
-    backend::dev_zero(B->b.itg + (size_t)B->b.L.warning * st, (size_t)NWARNING * st * sizeof(int), B->stream);
+    if (!(control_spec & ST_CTRL) || !control) field_zero(B, false, B->b.L.ctrl, B->hm.dm.sz.nu);
+    if (!(control_spec & ST_QFRC_APPLIED) || !control) field_zero(B, false, B->b.L.qfrc_applied, nv);
+    field_zero(B, true, B->b.L.warning, NWARNING);
     if (int rc = mjb_set_state(B, state0, full)) return rc;
     if (warmstart0) {
       if (int rc = mjb_set_state(B, warmstart0, ST_WARMSTART)) return rc;
     } else {
-      backend::dev_zero(B->b.dbl + (size_t)B->b.L.qacc_warmstart * st, (size_t)nv * st * sizeof(double), B->stream);
+      field_zero(B, false, B->b.L.qacc_warmstart, nv);
     }
   }
   double* d_control = nullptr;
@@ -323,36 +356,24 @@ long mjb_field_size(const mjbBatch* B, const char* name) {
 int mjb_get_field(mjbBatch* B, const char* name, double* out) {
   long off, cnt; bool is_int;
   if (!B || !out || !find_field(B, name, &off, &cnt, &is_int) || is_int) return fail(MJB_ERR_ARG, std::string("mjb_get_field: unknown double field ") + (name ? name : ""));
-  std::vector<double> tmp;
-  if (int rc = copy_rows_d2h(B, off, (int)cnt, &tmp)) return rc;
-  if (int rc = backend::sync(B->stream)) return rc;
-  const size_t st = B->b.stride;
-  for (long i = 0; i < cnt; i++)
-    for (int e = 0; e < B->b.nenv; e++) out[(size_t)e * cnt + i] = tmp[(size_t)i * st + e];
-  return 0;
+  return field_to_host(B, false, off, cnt, out);
 }
 
 int mjb_get_field_int(mjbBatch* B, const char* name, int* out) {
   long off, cnt; bool is_int;
   if (!B || !out || !find_field(B, name, &off, &cnt, &is_int) || !is_int) return fail(MJB_ERR_ARG, std::string("mjb_get_field_int: unknown int field ") + (name ? name : ""));
-  const size_t st = B->b.stride;
-  std::vector<int> tmp((size_t)cnt * st);
-  if (int rc = backend::d2h(tmp.data(), B->b.itg + (size_t)off * st, tmp.size() * sizeof(int), B->stream)) return rc;
-  if (int rc = backend::sync(B->stream)) return rc;
-  for (long i = 0; i < cnt; i++)
-    for (int e = 0; e < B->b.nenv; e++) out[(size_t)e * cnt + i] = tmp[(size_t)i * st + e];
-  return 0;
+  return field_to_host(B, true, off, cnt, out);
 }
 
 int mjb_set_field(mjbBatch* B, const char* name, const double* in) {
   long off, cnt; bool is_int;
   if (!B || !in || !find_field(B, name, &off, &cnt, &is_int) || is_int) return fail(MJB_ERR_ARG, std::string("mjb_set_field: unknown double field ") + (name ? name : ""));
-  const size_t st = B->b.stride;
-  std::vector<double> tmp((size_t)cnt * st, 0.0);
-  for (long i = 0; i < cnt; i++)
-    for (int e = 0; e < B->b.nenv; e++) tmp[(size_t)i * st + e] = in[(size_t)e * cnt + i];
-  if (int rc = backend::h2d(B->b.dbl + (size_t)off * st, tmp.data(), tmp.size() * sizeof(double), B->stream)) return rc;
-  return backend::sync(B->stream);
+  return field_from_host(B, false, off, cnt, in);
+}
+
+int mjb_set_thread_mapping(int warp_per_env) {
+  g_warp_per_env = warp_per_env ? 1 : 0;
+  return 0;
 }
 
 int mjb_warning_counts(mjbBatch* B, int* out) { return mjb_get_field_int(B, "warning", out); }

@@ -37,14 +37,7 @@ MJB_HD void reset_env(const Env& d, bool clear_warnings) {
 MJB_HD bool check_vec(const Env& d, FD v, int n, int warn) {
   for (int i = 0; i < n; i++) {
     if (is_bad(v[i])) {
-      if (!(d.m.opt.disableflags & DSBL_AUTORESET)) {
-        // keep warning counters across the reset, as mj_checkPos does by incrementing afterwards
-        int w[NWARNING];
-        for (int k = 0; k < NWARNING; k++) w[k] = d.warning()[k];
-        reset_env(d, true);
-        for (int k = 0; k < NWARNING; k++) d.warning()[k] = 0;
-        (void)w;
-      }
+      if (!(d.m.opt.disableflags & DSBL_AUTORESET)) reset_env(d, true);   // clears warnings, like mj_resetData
       d.warning()[warn] += 1;
       return true;
     }
@@ -205,29 +198,39 @@ MJB_HD void euler_advance(const Env& d) {
 }
 
 // ---- stages ---------------------------------------------------------------------------------------
+// Every stage is entered by ALL lanes that share the environment (one lane in lane-per-env mode,
+// 32 in warp-per-env mode).  Cooperative routines use MJB_PFOR / MJB_PSYNC internally; routines
+// that are still serial run on lane 0 through MJB_SERIAL.
+#define MJB_SERIAL(call)                                   \
+  do {                                                     \
+    if (d.lane == 0) {                                     \
+      const Env mjb_s_(d.m, d.b, d.e, 0, 1);               \
+      const Env& d = mjb_s_;                               \
+      call;                                                \
+    }                                                      \
+    MJB_PSYNC();                                           \
+  } while (0)
+
 MJB_HD void stage_position(const Env& d, bool is_step) {
   if (is_step) {
-    if (check_vec(d, d.qpos(), d.m.sz.nq, WARN_BADQPOS)) { /* reset happened; continue from qpos0 */ }
-    check_vec(d, d.qvel(), d.m.sz.nv, WARN_BADQVEL);
+    MJB_SERIAL(check_vec(d, d.qpos(), d.m.sz.nq, WARN_BADQPOS); check_vec(d, d.qvel(), d.m.sz.nv, WARN_BADQVEL));
   }
-  fwd_position(d);
+  MJB_SERIAL(fwd_position(d));
 }
 MJB_HD void stage_velocity(const Env& d) {
-  fwd_velocity(d);
-  fwd_actuation(d);
-  fwd_acceleration(d);
-  constraint_begin(d);
+  MJB_SERIAL(fwd_velocity(d); fwd_actuation(d); fwd_acceleration(d); constraint_begin(d));
 }
 MJB_HD void stage_solve(const Env& d) {
-  if (d.m.opt.solver == SOL_PGS) solve_pgs(d);
-  else solve_newton(d);
+  if (d.m.opt.solver == SOL_PGS) MJB_SERIAL(solve_pgs(d));
+  else MJB_SERIAL(solve_newton(d));
 }
 MJB_HD void stage_finish_forward(const Env& d) {
-  if (d.m.opt.solver == SOL_PGS) dual_finish(d);
+  if (d.m.opt.solver == SOL_PGS) MJB_SERIAL(dual_finish(d));
 }
 MJB_HD void stage_integrate(const Env& d) {
   stage_finish_forward(d);
-  if (check_vec(d, d.qacc(), d.m.sz.nv, WARN_BADQACC)) {
+  MJB_SERIAL(d.scr_int()[0] = check_vec(d, d.qacc(), d.m.sz.nv, WARN_BADQACC) ? 1 : 0);
+  if (d.scr_int()[0]) {
     // mj_checkAcc: after the reset the reference re-runs mj_forward before integrating
     if (!(d.m.opt.disableflags & DSBL_AUTORESET)) {
       stage_position(d, false);
@@ -236,7 +239,7 @@ MJB_HD void stage_integrate(const Env& d) {
       stage_finish_forward(d);
     }
   }
-  euler_advance(d);
+  MJB_SERIAL(euler_advance(d));
 }
 
 }  // namespace mjb

@@ -25,6 +25,24 @@ __global__ void __launch_bounds__(32) k_stage(DModel m, Batch b, int stage, int 
   run_stage(m, b, e, stage, flags);
 }
 
+// one warp per environment (env-major storage): lane = threadIdx.x & 31
+__global__ void __launch_bounds__(128) k_stage_warp(DModel m, Batch b, int stage, int flags) {
+  const int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (e >= b.nenv) return;
+  run_stage(m, b, e, stage, flags, threadIdx.x & 31, 32);
+}
+
+__global__ void k_pack(Batch b, int is_int, long off, long cnt, void* dense, int to_dense) {
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long)b.nenv * cnt) return;
+  run_pack(b, is_int, off, cnt, dense, to_dense, idx);
+}
+__global__ void k_fill_zero(Batch b, int is_int, long off, long cnt) {
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long)b.nenv * cnt) return;
+  run_fill_zero(b, is_int, off, cnt, idx);
+}
+
 __global__ void k_reset(DModel m, Batch b) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= b.nenv) return;
@@ -114,8 +132,28 @@ long launches() { return g_launches; }
 
 static inline int nblocks(const Batch& b, int threads) { return (b.nenv + threads - 1) / threads; }
 
+int launch_pack(const Batch& b, int is_int, long off, long cnt, void* dense, int to_dense, void* s) {
+  const long n = (long)b.nenv * cnt;
+  k_pack<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)s>>>(b, is_int, off, cnt, dense, to_dense);
+  g_launches++;
+  CK(cudaPeekAtLastError(), "k_pack launch");
+  return 0;
+}
+int launch_fill_zero(const Batch& b, int is_int, long off, long cnt, void* s) {
+  const long n = (long)b.nenv * cnt;
+  k_fill_zero<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)s>>>(b, is_int, off, cnt);
+  g_launches++;
+  CK(cudaPeekAtLastError(), "k_fill_zero launch");
+  return 0;
+}
+
 int launch_stage(const DModel& dm, const Batch& b, int stage, int flags, void* s) {
-  k_stage<<<nblocks(b, 32), 32, 0, (cudaStream_t)s>>>(dm, b, stage, flags);
+  if (b.warp_per_env) {
+    const int wpb = 4;   // warps (environments) per CTA
+    k_stage_warp<<<(b.nenv + wpb - 1) / wpb, 32 * wpb, 0, (cudaStream_t)s>>>(dm, b, stage, flags);
+  } else {
+    k_stage<<<nblocks(b, 32), 32, 0, (cudaStream_t)s>>>(dm, b, stage, flags);
+  }
   g_launches++;
   CK(cudaPeekAtLastError(), "k_stage launch");
   return 0;

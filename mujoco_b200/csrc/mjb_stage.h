@@ -11,8 +11,8 @@ MJB_HD bool env_has_warning(const Env& d) {
   return false;
 }
 
-MJB_HD void run_stage(const DModel& m, const Batch& b, int e, int stage, int flags) {
-  Env d(m, b, e);
+MJB_HD void run_stage(const DModel& m, const Batch& b, int e, int stage, int flags, int lane = 0, int nlane = 1) {
+  Env d(m, b, e, lane, nlane);
   if ((flags & 2) && env_has_warning(d)) return;   // rollout: a warned env stops stepping
   switch (stage) {
     case 0: stage_position(d, (flags & 1) != 0); break;
@@ -61,6 +61,25 @@ MJB_HD void run_get_state_native(const DModel& m, const Batch& b, int e, double*
   FD qp = d.qpos(), qv = d.qvel();
   for (int i = 0; i < m.sz.nq; i++) dst[(size_t)(k++) * b.stride] = qp[i];
   for (int i = 0; i < m.sz.nv; i++) dst[(size_t)(k++) * b.stride] = qv[i];
+}
+
+// dense [nenv][cnt] <-> field of either layout; idx enumerates (env, elem)
+MJB_HD void run_pack(const Batch& b, int is_int, long off, long cnt, void* dense, int to_dense, long idx) {
+  const long e = idx / cnt, i = idx - e * cnt;
+  if (is_int) {
+    int* f = b.itg + (size_t)e * b.ipitch + (size_t)(off + i) * b.istep;
+    int* dn = (int*)dense + idx;
+    if (to_dense) *dn = *f; else *f = *dn;
+  } else {
+    double* f = b.dbl + (size_t)e * b.dpitch + (size_t)(off + i) * b.dstep;
+    double* dn = (double*)dense + idx;
+    if (to_dense) *dn = *f; else *f = *dn;
+  }
+}
+MJB_HD void run_fill_zero(const Batch& b, int is_int, long off, long cnt, long idx) {
+  const long e = idx / cnt, i = idx - e * cnt;
+  if (is_int) b.itg[(size_t)e * b.ipitch + (size_t)(off + i) * b.istep] = 0;
+  else b.dbl[(size_t)e * b.dpitch + (size_t)(off + i) * b.dstep] = 0;
 }
 
 }  // namespace mjb

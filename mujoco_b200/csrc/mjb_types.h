@@ -166,11 +166,17 @@ using FD = Fld<double>;
 using FI = Fld<int>;
 
 // batch storage handle (device or host pointers)
+// Two physical layouts share one addressing rule  addr(field o, elem i, env e) = e*pitch + (o+i)*step :
+//   lane-per-env kernels : field[elem][env]  (pitch 1, step = padded nenv)  -> a warp of 32 envs reads one line
+//   warp-per-env kernels : env[field][elem]  (pitch = per-env block, step 1) -> a warp reads one env's
+//                          consecutive elements: again one line per 32 elements
 struct Batch {
   double* dbl;
   int* itg;
-  size_t stride;   // padded number of environments (row stride)
+  size_t stride;   // padded number of environments
+  size_t dpitch, dstep, ipitch, istep;
   int nenv;
+  int warp_per_env;   // 0: one environment per lane, 1: one environment per warp
   Layout L;
 };
 
@@ -179,14 +185,27 @@ struct Env {
   const DModel& m;
   const Batch& b;
   int e;
-  MJB_HD Env(const DModel& m_, const Batch& b_, int e_) : m(m_), b(b_), e(e_) {}
-#define X(name, cnt) MJB_HD FD name() const { return FD{b.dbl + (size_t)b.L.name * b.stride + e, b.stride}; }
+  int lane, nlane;   // cooperative lanes working on this environment (1 lane in lane-per-env mode)
+  MJB_HD Env(const DModel& m_, const Batch& b_, int e_, int lane_ = 0, int nlane_ = 1)
+      : m(m_), b(b_), e(e_), lane(lane_), nlane(nlane_) {}
+#define X(name, cnt) MJB_HD FD name() const { return FD{b.dbl + (size_t)e * b.dpitch + (size_t)b.L.name * b.dstep, b.dstep}; }
   MJB_DATA_DBL_FIELDS(X, _)
 #undef X
-#define X(name, cnt) MJB_HD FI name() const { return FI{b.itg + (size_t)b.L.name * b.stride + e, b.stride}; }
+#define X(name, cnt) MJB_HD FI name() const { return FI{b.itg + (size_t)e * b.ipitch + (size_t)b.L.name * b.istep, b.istep}; }
   MJB_DATA_INT_FIELDS(X, _)
 #undef X
+  // barrier + memory ordering between the lanes that share this environment
+  MJB_HD void sync() const {
+#if defined(__CUDA_ARCH__)
+    if (nlane > 1) __syncwarp();
+#endif
+  }
 };
+
+// cooperative loop over n independent items, and the barrier that separates dependent regions
+#define MJB_PFOR(i, n) for (int i = d.lane; i < (n); i += d.nlane)
+#define MJB_PSYNC() d.sync()
+#define MJB_LANE0 if (d.lane == 0)
 
 // small load/store helpers between strided fields and value types
 MJB_HD V3 ld3(FD f, long i) { return V3{f[i], f[i + 1], f[i + 2]}; }

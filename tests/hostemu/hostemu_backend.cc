@@ -32,6 +32,14 @@ int launch_stage(const DModel& dm, const Batch& b, int stage, int flags, void*) 
   for (int e = 0; e < b.nenv; e++) run_stage(dm, b, e, stage, flags);
   return 0;
 }
+int launch_pack(const Batch& b, int is_int, long off, long cnt, void* dense, int to_dense, void*) {
+  for (long i = 0; i < (long)b.nenv * cnt; i++) run_pack(b, is_int, off, cnt, dense, to_dense, i);
+  return 0;
+}
+int launch_fill_zero(const Batch& b, int is_int, long off, long cnt, void*) {
+  for (long i = 0; i < (long)b.nenv * cnt; i++) run_fill_zero(b, is_int, off, cnt, i);
+  return 0;
+}
 int launch_reset(const DModel& dm, const Batch& b, void*) {
   g_launches++;
   for (int e = 0; e < b.nenv; e++) { Env d(dm, b, e); reset_env(d, true); }

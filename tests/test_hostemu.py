@@ -1,0 +1,106 @@
+"""Kernel SOURCE checked against the oracle without a GPU (CPU only).
+
+tests/hostemu/libmjb_hostemu.so is the product's kernel source (mujoco_b200/csrc/mjb_*.h) compiled
+by g++ with the same C ABI.  Built with -ffp-contract=off it performs the same IEEE operations in the
+same order as the reference engine, so every mjData field and every trajectory must be BIT-EXACT.
+This is a test of the algorithm restatement; GPU parity proper is tests/test_gpu_parity.py."""
+import os
+
+import numpy as np
+import pytest
+
+import mujoco_b200 as mb
+from mjb_util import HOSTEMU, HUMANOID, ROOT, compare_forward, hostemu_lib, make_pair, perturbed_states
+from oracle_util import available
+
+pytestmark = pytest.mark.skipif(not (available() and os.path.exists(HOSTEMU)), reason="oracle or hostemu not built")
+
+
+@pytest.mark.parametrize("solver", [mb.SOLVER_PGS, mb.SOLVER_NEWTON])
+def test_forward_every_field_bit_exact(solver):
+    m, b, o = make_pair(HUMANOID, solver, library=hostemu_lib(), nenv=12)
+    states = perturbed_states(o, 12, seed=3, height=[0.2, 0.3, 0.45, 0.9, 1.3, 2.0])
+    ctrl = np.random.default_rng(5).uniform(-1.5, 1.5, (12, o.size("nu")))   # beyond ctrlrange: clamp path
+    compare_forward(b, o, states, ctrl, rtol=0, exact=True, check_dual=(solver == mb.SOLVER_PGS))
+
+
+@pytest.mark.parametrize("tag,solver", [("pgs", mb.SOLVER_PGS), ("newton", mb.SOLVER_NEWTON)])
+def test_golden_trajectory_bit_exact(tag, solver):
+    g = np.load(os.path.join(ROOT, "tests", "golden", "humanoid_%s_traj.npz" % tag))
+    m = mb.Model(HUMANOID, library=hostemu_lib())
+    m.set_option("solver", solver)
+    b = mb.Batch(m, g["state0"].shape[0])
+    out = b.rollout(g["state0"], g["ctrl"])
+    assert np.array_equal(out, g["states"])
+
+
+@pytest.mark.parametrize("solver", [mb.SOLVER_PGS, mb.SOLVER_NEWTON])
+def test_contact_rich_rollout_bit_exact(solver):
+    nenv, nstep = 16, 120
+    m, b, o = make_pair(HUMANOID, solver, library=hostemu_lib(), nenv=nenv)
+    s0 = perturbed_states(o, nenv, seed=11, height=[0.2, 0.3, 0.5, 0.8], qvel_std=0.5, qpos_std=0.2)
+    ctrl = np.random.default_rng(12).uniform(-1, 1, (nenv, nstep, o.size("nu")))
+    out = b.rollout(s0, ctrl)
+    ref, stats, _ = o.rollout(s0, ctrl, nthread=4)
+    assert stats[:, 0].mean() / nstep > 1        # contacts present most of the time
+    assert np.array_equal(out, ref)
+
+
+def test_option_variants_bit_exact():
+    """disable flags and solver options that change control flow on the path"""
+    DSBL_WARMSTART, DSBL_CLAMPCTRL, DSBL_EULERDAMP, DSBL_REFSAFE, DSBL_FILTERPARENT = 1 << 9, 1 << 8, 1 << 15, 1 << 12, 1 << 10
+    DSBL_CONTACT, DSBL_LIMIT, DSBL_GRAVITY, DSBL_SPRING, DSBL_DAMPER, DSBL_CONSTRAINT = 1 << 4, 1 << 3, 1 << 7, 1 << 5, 1 << 6, 1
+    nenv, nstep = 4, 40
+    for flags, extra in [(DSBL_WARMSTART, {}), (DSBL_CLAMPCTRL | DSBL_EULERDAMP, {}), (DSBL_REFSAFE | DSBL_FILTERPARENT, {}),
+                         (DSBL_CONTACT, {}), (DSBL_LIMIT | DSBL_GRAVITY, {}), (DSBL_SPRING, {}), (DSBL_DAMPER, {}),
+                         (DSBL_CONSTRAINT, {}), (0, {"iterations": 7}), (0, {"tolerance": 1e-4, "impratio": 3.0}),
+                         (0, {"timestep": 0.002})]:
+        m, b, o = make_pair(HUMANOID, mb.SOLVER_PGS, library=hostemu_lib(), nenv=nenv, disableflags=flags, **extra)
+        s0 = perturbed_states(o, nenv, seed=31, height=[0.25, 0.6], qvel_std=0.3, qpos_std=0.15)
+        ctrl = np.random.default_rng(32).uniform(-1.2, 1.2, (nenv, nstep, o.size("nu")))
+        out = b.rollout(s0, ctrl)
+        ref, _, _ = o.rollout(s0, ctrl, nthread=2)
+        assert np.array_equal(out, ref), (flags, extra, np.abs(out - ref).max())
+
+
+def test_bad_state_warning_and_padding():
+    """rollout.cc:127-155: an env that raises a warning stops stepping and pads its outputs;
+    mj_checkPos auto-resets to qpos0 (engine_forward.c:54-69)"""
+    nenv, nstep = 3, 6
+    m, b, o = make_pair(HUMANOID, mb.SOLVER_PGS, library=hostemu_lib(), nenv=nenv)
+    o.reset()
+    s0 = np.tile(o.get_state(), (nenv, 1))
+    s0[1, 3] = np.nan                              # bad qpos in env 1
+    ctrl = np.zeros((nenv, nstep, o.size("nu")))
+    out = b.rollout(s0, ctrl)
+    ref, stats, _ = o.rollout(s0, ctrl, nthread=1)
+    assert np.array_equal(out[0], ref[0]) and np.array_equal(out[2], ref[2])
+    assert np.array_equal(out[1], ref[1])          # reset + one step, then padded
+    w = b.warnings()
+    assert w[1, 3] == 1 and w[0].sum() == 0
+
+
+def test_state_io_and_argument_errors():
+    m = mb.Model(HUMANOID, library=hostemu_lib())
+    b = mb.Batch(m, 5)
+    assert b.state_size() == 1 + 28 + 27
+    s = np.random.default_rng(0).normal(size=(5, b.state_size()))
+    b.set_state(s)
+    assert np.array_equal(b.get_state(), s)
+    with pytest.raises(ValueError):
+        b.set_state(s[:, :-1])
+    with pytest.raises(ValueError):
+        b.rollout(s, np.zeros((5, 3, 7)))
+    with pytest.raises(mb.MjbError):
+        b.state_size(1 << 8)        # xfrc_applied unsupported
+
+
+def test_unsupported_models_are_refused():
+    m = mb.Model(HUMANOID, library=hostemu_lib())
+    m.set_option("cone", 1)
+    with pytest.raises(mb.MjbError, match="elliptic"):
+        mb.Batch(m, 1)
+    m.set_option("cone", 0)
+    m.set_option("integrator", 3)
+    with pytest.raises(mb.MjbError, match="implicit"):
+        mb.Batch(m, 1)
