@@ -100,6 +100,7 @@ mjbBatch* mjb_make_batch(const struct mjModel_* m, int nenv, int nconmax, int nj
 #endif
   }
   if (H.sz.nu > 4 * H.sz.nv) { set_error("unsupported: nu > 4*nv"); delete B; return nullptr; }
+  if (H.sz.nlim > 6 * H.sz.njmax) { set_error("njmax too small for the model's limit candidates"); delete B; return nullptr; }
   B->device = device;
   B->stream = backend::stream_create();
   // device copy of the model blobs, pointers rebased
@@ -225,17 +226,13 @@ int mjb_get_state(mjbBatch* B, double* state, unsigned int sig) {
 }
 
 // ---- stepping --------------------------------------------------------------------------------------
-static int run_step(mjbBatch* B, int flags) {
-  for (int s = 0; s < 4; s++)
-    if (int rc = backend::launch_stage(B->dm, B->b, s, flags | 1, B->stream)) return rc;
-  return 0;
+static int run_step(mjbBatch* B, int flags) {   // all four stages of mj_step in ONE fused launch
+  return backend::launch_stages(B->dm, B->b, 0xF, flags | 1, B->stream);
 }
 
 int mjb_forward(mjbBatch* B) {
   if (!B) return fail(MJB_ERR_ARG, "null batch");
-  for (int s = 0; s < 3; s++)
-    if (int rc = backend::launch_stage(B->dm, B->b, s, 0, B->stream)) return rc;
-  if (int rc = backend::launch_stage(B->dm, B->b, 4, 0, B->stream)) return rc;   // finish without integrating
+  if (int rc = backend::launch_stages(B->dm, B->b, 0x17, 0, B->stream)) return rc;   // stages 0,1,2 + dual finish
   return backend::sync(B->stream);
 }
 
@@ -248,8 +245,9 @@ int mjb_step(mjbBatch* B, int nstep) {
 
 int mjb_run_stages(mjbBatch* B, int first, int last) {
   if (!B || first < 0 || last > 4 || first > last) return fail(MJB_ERR_ARG, "mjb_run_stages: bad range");
-  for (int s = first; s <= last; s++)
-    if (int rc = backend::launch_stage(B->dm, B->b, s, 1, B->stream)) return rc;
+  int mask = 0;
+  for (int s = first; s <= last; s++) mask |= 1 << s;
+  if (int rc = backend::launch_stages(B->dm, B->b, mask, 1, B->stream)) return rc;
   return backend::sync(B->stream);
 }
 
@@ -292,7 +290,7 @@ int mjb_rollout(mjbBatch* B, int nstep, unsigned int control_spec, const double*
   int rc = 0;
   for (int t = 0; t < nstep && !rc; t++) {
     if (d_control) rc = backend::launch_set_control(B->dm, B->b, d_control, nstep, t, control_spec, ncontrol, B->stream);
-    for (int s = 0; s < 4 && !rc; s++) rc = backend::launch_stage(B->dm, B->b, s, 1 | 2, B->stream);
+    if (!rc) rc = backend::launch_stages(B->dm, B->b, 0xF, 1 | 2, B->stream);
     if (d_state && !rc) rc = backend::launch_get_state(B->dm, B->b, d_state, nstep, t, nstate, B->stream);
   }
   if (!rc && d_state) rc = backend::d2h(state, d_state, sbytes, B->stream);
@@ -313,7 +311,7 @@ int mjb_step_host(mjbBatch* B, const double* ctrl, double* state_out) {
   }
   int rc = backend::h2d(B->io_ctrl, ctrl, (size_t)nenv * nu * sizeof(double), B->stream);
   if (!rc) rc = backend::launch_set_control(B->dm, B->b, B->io_ctrl, 1, 0, ST_CTRL, nu, B->stream);
-  for (int s = 0; s < 4 && !rc; s++) rc = backend::launch_stage(B->dm, B->b, s, 1, B->stream);
+  if (!rc) rc = backend::launch_stages(B->dm, B->b, 0xF, 1, B->stream);
   if (!rc) rc = backend::launch_get_state(B->dm, B->b, B->io_state, 1, 0, nstate, B->stream);
   if (!rc) rc = backend::d2h(state_out, B->io_state, (size_t)nenv * nstate * sizeof(double), B->stream);
   if (!rc) rc = backend::sync(B->stream);
@@ -327,7 +325,7 @@ int mjb_rollout_device(mjbBatch* B, int nstep, const double* d_ctrl, double* d_s
   int rc = 0;
   for (int t = 0; t < nstep && !rc; t++) {
     if (d_ctrl) rc = backend::launch_set_control_native(B->dm, B->b, d_ctrl, t, B->stream);
-    for (int s = 0; s < 4 && !rc; s++) rc = backend::launch_stage(B->dm, B->b, s, 1, B->stream);
+    if (!rc) rc = backend::launch_stages(B->dm, B->b, 0xF, 1, B->stream);
     if (d_state && !rc) rc = backend::launch_get_state_native(B->dm, B->b, d_state, t, nstate, B->stream);
   }
   return rc;   // asynchronous: caller synchronises on mjb_stream()
@@ -340,6 +338,7 @@ static bool find_field(const mjbBatch* B, const char* name, long* off, long* cnt
   (void)S;
 #define X(fname, count) if (!strcmp(name, #fname)) { *off = L.fname; *cnt = (long)(count); *is_int = false; return true; }
   MJB_DATA_DBL_FIELDS(X, S)
+  MJB_DATA_COLD_FIELDS(X, S)
 #undef X
 #define X(fname, count) if (!strcmp(name, #fname)) { *off = L.fname; *cnt = (long)(count); *is_int = true; return true; }
   MJB_DATA_INT_FIELDS(X, S)

@@ -20,9 +20,10 @@ void* stream_create();
 void stream_destroy(void* s);
 int sync(void* stream);
 
-// pipeline stage for every environment (stage ids: mjb_forward.h). flags: bit0 = part of mj_step
-// (run the qpos/qvel checks), bit1 = skip environments whose warning counters are non-zero
-int launch_stage(const DModel& dm, const Batch& b, int stage, int flags, void* stream);
+// run the pipeline stages selected by `mask` (bit s = stage s, see mjb_forward.h) for every
+// environment in ONE launch.  flags: bit0 = part of mj_step (run the qpos/qvel checks), bit1 = skip
+// environments whose warning counters are non-zero
+int launch_stages(const DModel& dm, const Batch& b, int mask, int flags, void* stream);
 int launch_reset(const DModel& dm, const Batch& b, void* stream);
 // rollout helpers; control/state are DEVICE buffers laid out [nenv][nstep][n] (reference layout)
 int launch_set_control(const DModel& dm, const Batch& b, const double* control, int nstep, int t,

@@ -114,69 +114,106 @@ MJB_HD int collide_capsule_capsule(PreCon* c, double margin, V3 p1, const M3& m1
   return n1 + n2 + n3 + n4;
 }
 
-// walk the static candidate table; fills the contact arrays and ncon
+// walk the static candidate table cooperatively: every lane tests its candidates and parks up to two
+// pre-contacts per pair in scratch; a serial scan then assigns contact slots IN TABLE ORDER (the
+// reference's emission order), and the lanes copy their pairs' contacts into place.
 MJB_HD void collision(const Env& d) {
   const DModel& m = d.m;
   FI ncon_f = d.ncon();
-  ncon_f[0] = 0;
-  if (m.opt.disableflags & (DSBL_CONSTRAINT | DSBL_CONTACT)) return;
+  if (m.opt.disableflags & (DSBL_CONSTRAINT | DSBL_CONTACT)) {
+    MJB_LANE0 ncon_f[0] = 0;
+    MJB_PSYNC();
+    return;
+  }
   FD gx = d.geom_xpos(), gm = d.geom_xmat();
-  FD cdist = d.con_dist(), cpos = d.con_pos(), cframe = d.con_frame(), cinc = d.con_includemargin();
-  FD cfri = d.con_friction(), csolref = d.con_solref(), csolimp = d.con_solimp(), cmu = d.con_mu();
-  FI cg1 = d.con_geom1(), cg2 = d.con_geom2(), cdim = d.con_dim(), cexc = d.con_exclude(), cadr = d.con_efcadr();
-  const int nconmax = m.sz.nconmax;
-  int ncon = 0;
-  for (int p = 0; p < m.sz.npair; p++) {
+  FD sp = d.scr_pair();          // per pair: 2 slots x (dist, pos3, normal3, tangent3) padded to 12 doubles
+  FI cnt = d.scr_ipair();        // per pair: number of pre-contacts, then exclusive offsets
+  const int npair = m.sz.npair, nconmax = m.sz.nconmax;
+  MJB_PFOR(p, npair) {
     const int g1 = m.pair_geom1[p], g2 = m.pair_geom2[p];
     const int t1 = m.geom_type[g1], t2 = m.geom_type[g2];
     const double margin = m.pair_margin[p];
     const double rb1 = m.geom_rbound[g1], rb2 = m.geom_rbound[g2];
     V3 p1 = ld3(gx, 3 * g1), p2 = ld3(gx, 3 * g2);
+    int n = 0;
+    bool pass = true;
     // per-pair filter (mj_filterSphere)
     if (rb1 > 0 && rb2 > 0) {
       V3 dif = p1 - p2;
       double dsq = dif.x * dif.x + dif.y * dif.y + dif.z * dif.z;
       double bound = rb1 + rb2 + margin;
-      if (dsq > bound * bound) continue;
+      if (dsq > bound * bound) pass = false;
     } else if (t1 == GEOM_PLANE && rb2 > 0) {
       V3 nrm{gm[9 * g1 + 2], gm[9 * g1 + 5], gm[9 * g1 + 8]};
       V3 dif = p2 - p1;
-      if (dot(dif, nrm) > margin + rb2) continue;
+      if (dot(dif, nrm) > margin + rb2) pass = false;
     }
-    M3 m1 = ld9(gm, 9 * g1), m2 = ld9(gm, 9 * g2);
-    const double* s1 = m.geom_size + 3 * g1;
-    const double* s2 = m.geom_size + 3 * g2;
-    PreCon pc[2];
-    int n = 0;
-    if (t1 == GEOM_PLANE && t2 == GEOM_SPHERE) n = raw_plane_sphere(pc[0], margin, p1, m1, p2, s2[0]);
-    else if (t1 == GEOM_PLANE && t2 == GEOM_CAPSULE) n = collide_plane_capsule(pc, margin, p1, m1, p2, m2, s2);
-    else if (t1 == GEOM_SPHERE && t2 == GEOM_SPHERE) n = raw_sphere_sphere(pc[0], margin, p1, m1, s1[0], p2, m2, s2[0]);
-    else if (t1 == GEOM_SPHERE && t2 == GEOM_CAPSULE) n = collide_sphere_capsule(pc, margin, p1, m1, s1, p2, m2, s2);
-    else if (t1 == GEOM_CAPSULE && t2 == GEOM_CAPSULE) n = collide_capsule_capsule(pc, margin, p1, m1, s1, p2, m2, s2);
+    if (pass) {
+      M3 m1 = ld9(gm, 9 * g1), m2 = ld9(gm, 9 * g2);
+      const double* s1 = m.geom_size + 3 * g1;
+      const double* s2 = m.geom_size + 3 * g2;
+      PreCon pc[2];
+      if (t1 == GEOM_PLANE && t2 == GEOM_SPHERE) n = raw_plane_sphere(pc[0], margin, p1, m1, p2, s2[0]);
+      else if (t1 == GEOM_PLANE && t2 == GEOM_CAPSULE) n = collide_plane_capsule(pc, margin, p1, m1, p2, m2, s2);
+      else if (t1 == GEOM_SPHERE && t2 == GEOM_SPHERE) n = raw_sphere_sphere(pc[0], margin, p1, m1, s1[0], p2, m2, s2[0]);
+      else if (t1 == GEOM_SPHERE && t2 == GEOM_CAPSULE) n = collide_sphere_capsule(pc, margin, p1, m1, s1, p2, m2, s2);
+      else if (t1 == GEOM_CAPSULE && t2 == GEOM_CAPSULE) n = collide_capsule_capsule(pc, margin, p1, m1, s1, p2, m2, s2);
+      for (int k = 0; k < n; k++) {
+        FD o = sp + (24 * p + 12 * k);   // slot k: [0]=dist [1..3]=pos [4..6]=normal [7..9]=tangent
+        o[0] = pc[k].dist;
+        o[1] = pc[k].pos.x; o[2] = pc[k].pos.y; o[3] = pc[k].pos.z;
+        o[4] = pc[k].normal.x; o[5] = pc[k].normal.y; o[6] = pc[k].normal.z;
+        o[7] = pc[k].tangent.x; o[8] = pc[k].tangent.y; o[9] = pc[k].tangent.z;
+      }
+    }
+    cnt[p] = n;
+  }
+  MJB_PSYNC();
+  MJB_LANE0 {   // exclusive scan in table order, capped at nconmax
+    int total = 0;
+    bool full = false;
+    for (int p = 0; p < npair; p++) {
+      int n = cnt[p];
+      if (total + n > nconmax) { n = nconmax - total; full = true; }
+      cnt[p] = total | (n << 24);
+      total += n;
+    }
+    if (full) d.warning()[WARN_CONTACTFULL] += 1;
+    ncon_f[0] = total;
+  }
+  MJB_PSYNC();
+  FD cdist = d.con_dist(), cpos = d.con_pos(), cframe = d.con_frame(), cinc = d.con_includemargin();
+  FD cfri = d.con_friction(), csolref = d.con_solref(), csolimp = d.con_solimp(), cmu = d.con_mu();
+  FI cg1 = d.con_geom1(), cg2 = d.con_geom2(), cdim = d.con_dim(), cexc = d.con_exclude(), cadr = d.con_efcadr();
+  FI cpair = d.con_pair();
+  MJB_PFOR(p, npair) {
+    const int off = cnt[p] & 0xFFFFFF, n = cnt[p] >> 24;
     for (int k = 0; k < n; k++) {
-      if (ncon >= nconmax) { d.warning()[WARN_CONTACTFULL] += 1; break; }
-      const int c = ncon++;
-      cdist[c] = pc[k].dist;
-      st3(cpos, 3 * c, pc[k].pos);
+      const int c = off + k;
+      FD o = sp + (24 * p + 12 * k);
+      const double dist = o[0];
+      cdist[c] = dist;
+      cpos[3 * c] = o[1]; cpos[3 * c + 1] = o[2]; cpos[3 * c + 2] = o[3];
       M3 fr;
-      fr.m[0] = pc[k].normal.x; fr.m[1] = pc[k].normal.y; fr.m[2] = pc[k].normal.z;
-      fr.m[3] = pc[k].tangent.x; fr.m[4] = pc[k].tangent.y; fr.m[5] = pc[k].tangent.z;
+      fr.m[0] = o[4]; fr.m[1] = o[5]; fr.m[2] = o[6];
+      fr.m[3] = o[7]; fr.m[4] = o[8]; fr.m[5] = o[9];
       fr.m[6] = 0; fr.m[7] = 0; fr.m[8] = 0;
       make_frame(fr);
       st9(cframe, 9 * c, fr);
-      cg1[c] = g1; cg2[c] = g2;
+      cg1[c] = m.pair_geom1[p]; cg2[c] = m.pair_geom2[p];
+      cpair[c] = p;
       cdim[c] = m.pair_dim[p];
       const double inc = m.pair_includemargin[p];
       cinc[c] = inc;
       for (int j = 0; j < 5; j++) cfri[5 * c + j] = m.pair_friction[5 * p + j];
       for (int j = 0; j < 2; j++) csolref[2 * c + j] = m.pair_solref[2 * p + j];
       for (int j = 0; j < 5; j++) csolimp[5 * c + j] = m.pair_solimp[5 * p + j];
-      cexc[c] = (pc[k].dist >= inc) ? 1 : 0;
+      cexc[c] = (dist >= inc) ? 1 : 0;
       cadr[c] = -1;
       cmu[c] = 0;
     }
   }
-  ncon_f[0] = ncon;
+  MJB_PSYNC();
 }
 
 }  // namespace mjb

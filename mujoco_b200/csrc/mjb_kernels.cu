@@ -19,17 +19,25 @@
 
 namespace mjb {
 
-__global__ void __launch_bounds__(32) k_stage(DModel m, Batch b, int stage, int flags) {
+// one environment per lane, field-major storage
+__global__ void __launch_bounds__(32) k_step_lane(DModel m, Batch b, int mask, int flags) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= b.nenv) return;
-  run_stage(m, b, e, stage, flags);
+  run_env(m, b, e, mask, flags, 0, 1, nullptr, nullptr);
 }
 
-// one warp per environment (env-major storage): lane = threadIdx.x & 31
-__global__ void __launch_bounds__(128) k_stage_warp(DModel m, Batch b, int stage, int flags) {
-  const int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+// FUSED STEP KERNEL: one warp (= one CTA) per environment, env-major storage.  The hot block of the
+// environment (state + every smooth-dynamics / contact / constraint-vector field, ~45 KB for the
+// humanoid) is staged into shared memory with coalesced 256-byte row reads, all pipeline stages run
+// out of shared memory with the 32 lanes cooperating (MJB_PFOR / __syncwarp), and the block is
+// written back once.  efc_J / efc_Y / efc_AR stay in global memory (L2-resident per-env regions).
+extern __shared__ double mjb_smem[];
+__global__ void __launch_bounds__(32) k_step_warp(DModel m, Batch b, int mask, int flags) {
+  const int e = blockIdx.x;
   if (e >= b.nenv) return;
-  run_stage(m, b, e, stage, flags, threadIdx.x & 31, 32);
+  double* shot = mjb_smem;
+  int* sint = (int*)(mjb_smem + b.L.nhot);
+  run_env(m, b, e, mask, flags, threadIdx.x, 32, shot, sint);
 }
 
 __global__ void k_pack(Batch b, int is_int, long off, long cnt, void* dense, int to_dense) {
@@ -147,15 +155,20 @@ int launch_fill_zero(const Batch& b, int is_int, long off, long cnt, void* s) {
   return 0;
 }
 
-int launch_stage(const DModel& dm, const Batch& b, int stage, int flags, void* s) {
+int launch_stages(const DModel& dm, const Batch& b, int mask, int flags, void* s) {
   if (b.warp_per_env) {
-    const int wpb = 4;   // warps (environments) per CTA
-    k_stage_warp<<<(b.nenv + wpb - 1) / wpb, 32 * wpb, 0, (cudaStream_t)s>>>(dm, b, stage, flags);
+    const size_t smem = (size_t)b.L.nhot * sizeof(double) + (size_t)b.L.nint * sizeof(int);
+    static size_t configured = 0;
+    if (smem > configured) {
+      CK(cudaFuncSetAttribute(k_step_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem opt-in");
+      configured = smem;
+    }
+    k_step_warp<<<b.nenv, 32, smem, (cudaStream_t)s>>>(dm, b, mask, flags);
   } else {
-    k_stage<<<nblocks(b, 32), 32, 0, (cudaStream_t)s>>>(dm, b, stage, flags);
+    k_step_lane<<<nblocks(b, 32), 32, 0, (cudaStream_t)s>>>(dm, b, mask, flags);
   }
   g_launches++;
-  CK(cudaPeekAtLastError(), "k_stage launch");
+  CK(cudaPeekAtLastError(), "step kernel launch");
   return 0;
 }
 int launch_reset(const DModel& dm, const Batch& b, void* s) {

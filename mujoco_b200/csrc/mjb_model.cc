@@ -560,16 +560,116 @@ int build_host_model(const mjModel* m, int nconmax, int njmax, HostModel* out) {
   B.addD(&D.pair_solimp, psolimp.data(), psolimp.size());
   B.addD(&D.pair_friction, pfric.data(), pfric.size());
 
-  // caps replacing the reference arena
-  if (nconmax <= 0) nconmax = std::min(std::max(2 * S.npair, 8), 128);
-  if (njmax <= 0) {
-    int lim = 0;
-    for (int i = 0; i < m->njnt; i++) lim += m->jnt_limited[i] ? 1 : 0;
-    for (int i = 0; i < m->ntendon; i++) lim += m->tendon_limited[i] ? 1 : 0;
-    int fl = 0;
-    for (int i = 0; i < m->nv; i++) fl += (m->dof_frictionloss[i] != 0);
-    njmax = fl + lim + 4 * 24;
+  // ---- schedules for the cooperative (warp-per-env) tree recursions --------------------------------
+  // Every schedule reproduces the reference's SERIAL accumulation order per output element, so the
+  // level-parallel recursions stay bit-compatible with engine_core_smooth.c.
+  {
+    // body depth levels (level 0 = world) and per-body child lists in DESCENDING id order:
+    // the reference's backward passes run i = nbody-1..1 and add body i into its parent, so each
+    // parent receives its children in descending id order (mj_comPos :262-275, mj_crb :1911-1917)
+    std::vector<int> depth(m->nbody, 0);
+    int nlevel = 1;
+    for (int i = 1; i < m->nbody; i++) { depth[i] = depth[m->body_parentid[i]] + 1; nlevel = std::max(nlevel, depth[i] + 1); }
+    std::vector<int> ladr(nlevel + 1, 0), lbody;
+    for (int l = 0; l < nlevel; l++) {
+      ladr[l] = (int)lbody.size();
+      for (int i = 0; i < m->nbody; i++) if (depth[i] == l) lbody.push_back(i);
+    }
+    ladr[nlevel] = (int)lbody.size();
+    std::vector<int> cadr(m->nbody + 1, 0), cid;
+    for (int p = 0; p < m->nbody; p++) {
+      cadr[p] = (int)cid.size();
+      for (int i = m->nbody - 1; i >= 1; i--) if (m->body_parentid[i] == p) cid.push_back(i);
+    }
+    cadr[m->nbody] = (int)cid.size();
+    S.nlevel = nlevel;
+    B.addI(&D.lvl_adr, ladr.data(), ladr.size());
+    B.addI(&D.lvl_body, lbody.data(), lbody.size());
+    B.addI(&D.child_adr, cadr.data(), cadr.size());
+    B.addI(&D.child_id, cid.data(), cid.size());
+
+    // dof depth levels (depth = number of dof ancestors) and, per dof j, its strict descendants i in
+    // DESCENDING order with the CSR address of M(i,j): gather form of the L^-T pass of mj_solveLD
+    int nv = m->nv, ndl = 1;
+    std::vector<int> dd(nv, 0);
+    for (int i = 0; i < nv; i++) { dd[i] = m->M_rownnz[i] - 1; ndl = std::max(ndl, dd[i] + 1); }
+    std::vector<int> dadr(ndl + 1, 0), ddof;
+    for (int l = 0; l < ndl; l++) {
+      dadr[l] = (int)ddof.size();
+      for (int i = 0; i < nv; i++) if (dd[i] == l) ddof.push_back(i);
+    }
+    dadr[ndl] = (int)ddof.size();
+    std::vector<int> madr(nv + 1, 0), mdof, mq;
+    for (int j = 0; j < nv; j++) {
+      madr[j] = (int)mdof.size();
+      for (int i = nv - 1; i > j; i--) {
+        int start = m->M_rowadr[i], nnz = m->M_rownnz[i];
+        for (int a = start; a < start + nnz - 1; a++)
+          if (m->M_colind[a] == j) { mdof.push_back(i); mq.push_back(a); }
+      }
+    }
+    madr[nv] = (int)mdof.size();
+    S.ndlevel = ndl;
+    B.addI(&D.dlvl_adr, dadr.data(), dadr.size());
+    B.addI(&D.dlvl_dof, ddof.data(), ddof.size());
+    B.addI(&D.mt_adr, madr.data(), madr.size());
+    B.addI(&D.mt_dof, mdof.data(), mdof.size());
+    B.addI(&D.mt_qadr, mq.data(), mq.size());
+
+    // L'DL "program": for pivot row k the independent element updates
+    //   mat[dst] += mat[src] * (-mat[cf] * invD)      (mj_factorI :1997-2029)
+    std::vector<int> fadr(nv + 1, 0), fdst, fsrc, fcf;
+    for (int k = 0; k < nv; k++) {
+      fadr[k] = (int)fdst.size();
+      int start = m->M_rowadr[k], diag = m->M_rownnz[k] - 1, end = start + diag;
+      for (int adr = end - 1; adr >= start; adr--) {
+        int i = m->M_colind[adr];
+        for (int c = 0; c < m->M_rownnz[i]; c++) { fdst.push_back(m->M_rowadr[i] + c); fsrc.push_back(start + c); fcf.push_back(adr); }
+      }
+    }
+    fadr[nv] = (int)fdst.size();
+    B.addI(&D.fac_adr, fadr.data(), fadr.size());
+    B.addI(&D.fac_dst, fdst.data(), fdst.size());
+    B.addI(&D.fac_src, fsrc.data(), fsrc.size());
+    B.addI(&D.fac_cf, fcf.data(), fcf.size());
+
+    // limit candidates in the reference's row order (mj_instantiateLimit :1388-1517) and
+    // friction-loss dofs (mj_instantiateFriction :1291-1320)
+    std::vector<int> lk, lid, ls, fl;
+    for (int i = 0; i < m->njnt; i++) {
+      if (!m->jnt_limited[i]) continue;
+      if (m->jnt_type[i] == mjJNT_SLIDE || m->jnt_type[i] == mjJNT_HINGE) {
+        for (int side = -1; side <= 1; side += 2) { lk.push_back(LIM_HINGE); lid.push_back(i); ls.push_back(side); }
+      } else if (m->jnt_type[i] == mjJNT_BALL) {
+        lk.push_back(LIM_BALL); lid.push_back(i); ls.push_back(0);
+      }
+    }
+    for (int i = 0; i < m->ntendon; i++) {
+      if (!m->tendon_limited[i]) continue;
+      for (int side = -1; side <= 1; side += 2) { lk.push_back(LIM_TENDON); lid.push_back(i); ls.push_back(side); }
+    }
+    for (int i = 0; i < nv; i++) if (m->dof_frictionloss[i] != 0) fl.push_back(i);
+    S.nlim = (int)lk.size();
+    S.nfl = (int)fl.size();
+    B.addI(&D.lim_kind, lk.data(), lk.size());
+    B.addI(&D.lim_id, lid.data(), lid.size());
+    B.addI(&D.lim_side, ls.data(), ls.size());
+    B.addI(&D.fl_dof, fl.data(), fl.size());
+
+    // body x dof ancestry: 1 if dof c is on the kinematic chain of body b's weld root (mj_jac :197-225)
+    std::vector<int> anc((size_t)m->nbody * nv, 0);
+    for (int b = 0; b < m->nbody; b++) {
+      int wb = m->body_weldid[b];
+      if (m->body_dofnum[wb] == 0) continue;
+      int i = m->body_dofadr[wb] + m->body_dofnum[wb] - 1;
+      while (i >= 0) { anc[(size_t)b * nv + i] = 1; i = m->dof_parentid[i]; }
+    }
+    B.addI(&D.body_dofanc, anc.data(), anc.size());
   }
+
+  // caps replacing the reference arena
+  if (nconmax <= 0) nconmax = std::min(std::max(S.npair / 2, 16), 32);
+  if (njmax <= 0) njmax = S.nfl + 64;
   S.nconmax = nconmax;
   S.njmax = njmax;
   if (O.solver == mjSOL_PGS && !O.dense) { set_error("unsupported: PGS with sparse Jacobian (nv >= 60)"); return -2; }

@@ -1,83 +1,99 @@
-// Smooth dynamics of the batched mj_step path, one environment per call (one GPU lane per env).
+// Smooth dynamics of the batched mj_step path for ONE environment, executed cooperatively by the
+// lanes that own it (32 lanes of a warp in the fused kernel, 1 lane in lane-per-env mode).
 //
 // Replaces (reference file:line)  src/engine/engine_core_smooth.c  mj_kinematics :40-242,
 // mj_comPos :246-350, mj_tendon (fixed tendons) :927-985, mj_transmission (joint) :1265-1330,
 // mj_crb/mj_tendonArmature :1845-1971, mj_factorI :1997-2029, mj_solveLD :2033-2117,
 // mj_comVel :2179-2245, mj_rne :2328-2390;  src/engine/engine_passive.c mj_springdamper :655-842.
-// Same recurrences and operation order, re-expressed over the SoA batch layout (mjb_types.h).
+//
+// Parallel structure: the tree recursions run level by level (MJB_PFOR over the bodies / dofs of a
+// level, MJB_PSYNC between levels).  Every output element is still produced by ONE lane with the
+// reference's operation order — backward accumulations use host-built child / descendant lists in
+// the order in which the serial loops of the reference would have added them — so results are
+// bit-identical to the serial restatement whatever the lane count.
 #pragma once
 #include "mjb_types.h"
 
 namespace mjb {
 
 // ------------------------------------------------------------------------------------------------
-// forward kinematics: body frames down the tree, then inertial and geom frames
+// forward kinematics: body frames level by level, then inertial and geom frames
 MJB_HD void kinematics(const Env& d) {
   const DModel& m = d.m;
   const int nbody = m.sz.nbody;
   FD qpos = d.qpos(), xpos = d.xpos(), xquat = d.xquat(), xmat = d.xmat();
   FD xipos = d.xipos(), ximat = d.ximat(), xanchor = d.xanchor(), xaxis = d.xaxis();
 
-  // world body
-  st3(xpos, 0, V3{0, 0, 0});
-  st4(xquat, 0, Q4{1, 0, 0, 0});
-  st3(xipos, 0, V3{0, 0, 0});
-  for (int k = 0; k < 9; k++) { xmat[k] = (k % 4 == 0) ? 1.0 : 0.0; ximat[k] = (k % 4 == 0) ? 1.0 : 0.0; }
+  MJB_LANE0 {   // world body
+    st3(xpos, 0, V3{0, 0, 0});
+    st4(xquat, 0, Q4{1, 0, 0, 0});
+    st3(xipos, 0, V3{0, 0, 0});
+    for (int k = 0; k < 9; k++) { xmat[k] = (k % 4 == 0) ? 1.0 : 0.0; ximat[k] = (k % 4 == 0) ? 1.0 : 0.0; }
+  }
+  MJB_PSYNC();
 
-  for (int i = 1; i < nbody; i++) {
-    V3 p; Q4 q;
-    const int jadr = m.body_jntadr[i], jnum = m.body_jntnum[i];
-    if (jnum == 1 && m.jnt_type[jadr] == JNT_FREE) {
-      const int qa = m.jnt_qposadr[jadr];
-      p = ld3(qpos, qa);
-      q = ld4(qpos, qa + 3);
-      normalize(q);
-      st3(xanchor, 3 * jadr, p);
-      st3(xaxis, 3 * jadr, ldc3(m.jnt_axis, 3 * jadr));
-    } else {
-      const int pid = m.body_parentid[i];
-      V3 bpos = ldc3(m.body_pos, 3 * i);
-      Q4 bquat = ldc4(m.body_quat, 4 * i);
-      if (pid) {
-        p = mulmv(ld9(xmat, 9 * pid), bpos);
-        p = p + ld3(xpos, 3 * pid);
-        q = qmul(ld4(xquat, 4 * pid), bquat);
+  for (int l = 1; l < m.sz.nlevel; l++) {
+    const int adr = m.lvl_adr[l], cnt = m.lvl_adr[l + 1] - adr;
+    MJB_PFOR(k_, cnt) {
+      const int i = m.lvl_body[adr + k_];
+      V3 p; Q4 q;
+      const int jadr = m.body_jntadr[i], jnum = m.body_jntnum[i];
+      if (jnum == 1 && m.jnt_type[jadr] == JNT_FREE) {
+        const int qa = m.jnt_qposadr[jadr];
+        p = ld3(qpos, qa);
+        q = ld4(qpos, qa + 3);
+        normalize(q);
+        st3(xanchor, 3 * jadr, p);
+        st3(xaxis, 3 * jadr, ldc3(m.jnt_axis, 3 * jadr));
       } else {
-        p = bpos;
-        q = bquat;
-      }
-      for (int j = 0; j < jnum; j++) {
-        const int jid = jadr + j, qa = m.jnt_qposadr[jid], jt = m.jnt_type[jid];
-        V3 jaxis = ldc3(m.jnt_axis, 3 * jid), jpos = ldc3(m.jnt_pos, 3 * jid);
-        V3 ax = rotate(jaxis, q);
-        V3 an = rotate(jpos, q);
-        an = an + p;
-        if (jt == JNT_SLIDE) {
-          p = addscl(p, ax, qpos[qa] - m.qpos0[qa]);
-        } else {  // ball or hinge
-          Q4 ql;
-          if (jt == JNT_BALL) {
-            ql = ld4(qpos, qa);
-            normalize(ql);
-          } else {
-            ql = axis_angle(jaxis, qpos[qa] - m.qpos0[qa]);
-          }
-          q = qmul(q, ql);
-          V3 off = rotate(jpos, q);
-          p = an - off;
+        const int pid = m.body_parentid[i];
+        V3 bpos = ldc3(m.body_pos, 3 * i);
+        Q4 bquat = ldc4(m.body_quat, 4 * i);
+        if (pid) {
+          p = mulmv(ld9(xmat, 9 * pid), bpos);
+          p = p + ld3(xpos, 3 * pid);
+          q = qmul(ld4(xquat, 4 * pid), bquat);
+        } else {
+          p = bpos;
+          q = bquat;
         }
-        st3(xanchor, 3 * jid, an);
-        st3(xaxis, 3 * jid, ax);
+        for (int j = 0; j < jnum; j++) {
+          const int jid = jadr + j, qa = m.jnt_qposadr[jid], jt = m.jnt_type[jid];
+          V3 jaxis = ldc3(m.jnt_axis, 3 * jid), jpos = ldc3(m.jnt_pos, 3 * jid);
+          V3 ax = rotate(jaxis, q);
+          V3 an = rotate(jpos, q);
+          an = an + p;
+          if (jt == JNT_SLIDE) {
+            p = addscl(p, ax, qpos[qa] - m.qpos0[qa]);
+          } else {  // ball or hinge
+            Q4 ql;
+            if (jt == JNT_BALL) {
+              ql = ld4(qpos, qa);
+              normalize(ql);
+            } else {
+              ql = axis_angle(jaxis, qpos[qa] - m.qpos0[qa]);
+            }
+            q = qmul(q, ql);
+            V3 off = rotate(jpos, q);
+            p = an - off;
+          }
+          st3(xanchor, 3 * jid, an);
+          st3(xaxis, 3 * jid, ax);
+        }
       }
+      normalize(q);
+      st4(xquat, 4 * i, q);
+      st3(xpos, 3 * i, p);
+      st9(xmat, 9 * i, quat2mat(q));
     }
-    normalize(q);
-    st4(xquat, 4 * i, q);
-    st3(xpos, 3 * i, p);
-    st9(xmat, 9 * i, quat2mat(q));
+    MJB_PSYNC();
   }
 
-  // inertial frames (mj_local2Global, engine_core_util.c)
-  for (int i = 1; i < nbody; i++) {
+  // inertial frames (mj_local2Global, engine_core_util.c) and geom frames: independent items
+  FD gpos = d.geom_xpos(), gmat = d.geom_xmat();
+  const int ngeom = m.sz.ngeom;
+  MJB_PFOR(i_, nbody - 1) {
+    const int i = i_ + 1;
     const int sf = m.body_sameframe[i];
     V3 bp = ld3(xpos, 3 * i);
     M3 bm = ld9(xmat, 9 * i);
@@ -86,11 +102,8 @@ MJB_HD void kinematics(const Env& d) {
     if (sf == SAMEFRAME_NONE) st9(ximat, 9 * i, quat2mat(qmul(ld4(xquat, 4 * i), ldc4(m.body_iquat, 4 * i))));
     else st9(ximat, 9 * i, bm);
   }
-
-  // geom frames
-  FD gpos = d.geom_xpos(), gmat = d.geom_xmat();
-  const int ngeom = m.sz.ngeom;
-  for (int g = 0; g < ngeom; g++) {
+  MJB_PSYNC();
+  MJB_PFOR(g, ngeom) {
     const int b = m.geom_bodyid[g], sf = m.geom_sameframe[g];
     V3 bp = ld3(xpos, 3 * b);
     if (sf == SAMEFRAME_BODY) st3(gpos, 3 * g, bp);
@@ -99,6 +112,27 @@ MJB_HD void kinematics(const Env& d) {
     if (sf == SAMEFRAME_NONE) st9(gmat, 9 * g, quat2mat(qmul(ld4(xquat, 4 * b), ldc4(m.geom_quat, 4 * g))));
     else if (sf == SAMEFRAME_BODY || sf == SAMEFRAME_BODYROT) st9(gmat, 9 * g, ld9(xmat, 9 * b));
     else st9(gmat, 9 * g, ld9(ximat, 9 * b));
+  }
+  MJB_PSYNC();
+}
+
+// backward accumulation over the body tree: acc[parent] += acc[child] for `width` components,
+// children added in descending id order, deepest level first (== serial loop i = nbody-1..1).
+// skip_world: do not accumulate into the world body (mj_crb) / do (mj_comPos, mj_rne)
+MJB_HD void tree_accumulate(const Env& d, FD acc, int width, bool skip_world) {
+  const DModel& m = d.m;
+  for (int l = m.sz.nlevel - 2; l >= (skip_world ? 1 : 0); l--) {
+    const int adr = m.lvl_adr[l], cnt = m.lvl_adr[l + 1] - adr;
+    MJB_PFOR(it, cnt * width) {
+      const int p = m.lvl_body[adr + it / width], k = it % width;
+      const int ca = m.child_adr[p], cn = m.child_adr[p + 1] - ca;
+      if (cn) {
+        double s = acc[(long)width * p + k];
+        for (int c = 0; c < cn; c++) s += acc[(long)width * m.child_id[ca + c] + k];
+        acc[(long)width * p + k] = s;
+      }
+    }
+    MJB_PSYNC();
   }
 }
 
@@ -110,52 +144,49 @@ MJB_HD void com_pos(const Env& d) {
   FD sc = d.subtree_com(), xipos = d.xipos(), ximat = d.ximat(), xmat = d.xmat();
   FD cinert = d.cinert(), cdof = d.cdof(), xanchor = d.xanchor(), xaxis = d.xaxis();
 
-  for (int i = 0; i < nbody; i++) st3(sc, 3 * i, ld3(xipos, 3 * i) * m.body_mass[i]);
-  for (int i = nbody - 1; i > 0; i--) {
-    const int p = m.body_parentid[i];
-    st3(sc, 3 * p, ld3(sc, 3 * p) + ld3(sc, 3 * i));
-  }
-  for (int i = 0; i < nbody; i++) {
+  MJB_PFOR(i, nbody) st3(sc, 3 * i, ld3(xipos, 3 * i) * m.body_mass[i]);
+  MJB_PSYNC();
+  tree_accumulate(d, sc, 3, false);
+  MJB_PFOR(i, nbody) {
     if (m.body_subtreemass[i] < kMinVal) st3(sc, 3 * i, ld3(xipos, 3 * i));
     else st3(sc, 3 * i, ld3(sc, 3 * i) * (1.0 / m.body_subtreemass[i]));
   }
+  MJB_PSYNC();
 
-  for (int k = 0; k < 10; k++) cinert[k] = 0;
-  for (int i = 1; i < nbody; i++) {
-    V3 off = ld3(xipos, 3 * i) - ld3(sc, 3 * m.body_rootid[i]);
-    st10(cinert, 10 * i, inert_com(ldc3(m.body_inertia, 3 * i), ld9(ximat, 9 * i), off, m.body_mass[i]));
-  }
-
-  for (int i = 1; i < nbody; i++) {
-    const int jnum = m.body_jntnum[i];
-    if (!jnum) continue;
-    const int start = m.body_jntadr[i];
-    V3 root = ld3(sc, 3 * m.body_rootid[i]);
-    for (int j = start; j < start + jnum; j++) {
-      int da = 6 * m.jnt_dofadr[j];
-      V3 off = root - ld3(xanchor, 3 * j);
-      const int jt = m.jnt_type[j];
-      if (jt == JNT_FREE || jt == JNT_BALL) {
-        if (jt == JNT_FREE) {
-          for (int k = 0; k < 18; k++) cdof[da + k] = 0;
-          cdof[da + 3] = 1; cdof[da + 10] = 1; cdof[da + 17] = 1;
-          da += 18;
-        }
-        for (int k = 0; k < 3; k++) {
-          V3 ax{xmat[9 * i + k], xmat[9 * i + k + 3], xmat[9 * i + k + 6]};
-          st3(cdof, da + 6 * k, ax);
-          st3(cdof, da + 6 * k + 3, cross(ax, off));
-        }
-      } else if (jt == JNT_SLIDE) {
-        st3(cdof, da, V3{0, 0, 0});
-        st3(cdof, da + 3, ld3(xaxis, 3 * j));
-      } else {
-        V3 ax = ld3(xaxis, 3 * j);
-        st3(cdof, da, ax);
-        st3(cdof, da + 3, cross(ax, off));
-      }
+  MJB_PFOR(i, nbody) {
+    if (i == 0) { for (int k = 0; k < 10; k++) cinert[k] = 0; }
+    else {
+      V3 off = ld3(xipos, 3 * i) - ld3(sc, 3 * m.body_rootid[i]);
+      st10(cinert, 10 * i, inert_com(ldc3(m.body_inertia, 3 * i), ld9(ximat, 9 * i), off, m.body_mass[i]));
     }
   }
+  MJB_PFOR(j, m.sz.njnt) {
+    const int i = m.jnt_bodyid[j];
+    V3 root = ld3(sc, 3 * m.body_rootid[i]);
+    int da = 6 * m.jnt_dofadr[j];
+    V3 off = root - ld3(xanchor, 3 * j);
+    const int jt = m.jnt_type[j];
+    if (jt == JNT_FREE || jt == JNT_BALL) {
+      if (jt == JNT_FREE) {
+        for (int k = 0; k < 18; k++) cdof[da + k] = 0;
+        cdof[da + 3] = 1; cdof[da + 10] = 1; cdof[da + 17] = 1;
+        da += 18;
+      }
+      for (int k = 0; k < 3; k++) {
+        V3 ax{xmat[9 * i + k], xmat[9 * i + k + 3], xmat[9 * i + k + 6]};
+        st3(cdof, da + 6 * k, ax);
+        st3(cdof, da + 6 * k + 3, cross(ax, off));
+      }
+    } else if (jt == JNT_SLIDE) {
+      st3(cdof, da, V3{0, 0, 0});
+      st3(cdof, da + 3, ld3(xaxis, 3 * j));
+    } else {
+      V3 ax = ld3(xaxis, 3 * j);
+      st3(cdof, da, ax);
+      st3(cdof, da + 3, cross(ax, off));
+    }
+  }
+  MJB_PSYNC();
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -165,22 +196,24 @@ MJB_HD void tendon(const Env& d) {
   const int nt = m.sz.ntendon;
   if (!nt) return;
   FD L = d.ten_length(), J = d.ten_J(), qpos = d.qpos();
-  for (int i = 0; i < nt; i++) L[i] = 0;
-  for (int i = 0; i < m.sz.nJten; i++) J[i] = 0;
-  for (int i = 0; i < nt; i++) {
+  MJB_PFOR(i, nt) {
     const int adr = m.tendon_adr[i], num = m.tendon_num[i];
     const int radr = m.ten_J_rowadr[i], rnnz = m.ten_J_rownnz[i];
+    double len = 0;
+    for (int a = 0; a < rnnz; a++) J[radr + a] = 0;
     for (int j = 0; j < num; j++) {
       const int k = m.wrap_objid[adr + j];
       const double c = m.wrap_prm[adr + j];
-      L[i] += c * qpos[m.jnt_qposadr[k]];
-      // J(row i, col dofadr) += c * 1     (mju_combineSparseInc with a single source entry)
+      len += c * qpos[m.jnt_qposadr[k]];
+      // J(row i, col dofadr) = 1*J + c*1   (mju_combineSparseInc with a single source entry)
       const int dof = m.jnt_dofadr[k];
       for (int a = 0; a < rnnz; a++) {
         if (m.ten_J_colind[radr + a] == dof) { J[radr + a] = 1.0 * J[radr + a] + c * 1.0; break; }
       }
     }
+    L[i] = len;
   }
+  MJB_PSYNC();
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -188,12 +221,13 @@ MJB_HD void tendon(const Env& d) {
 MJB_HD void transmission(const Env& d) {
   const DModel& m = d.m;
   FD len = d.actuator_length(), mom = d.actuator_moment(), qpos = d.qpos();
-  for (int i = 0; i < m.sz.nu; i++) {
+  MJB_PFOR(i, m.sz.nu) {
     const int j = m.actuator_trnjnt[i];
     const double g = m.actuator_gear0[i];
     len[i] = qpos[m.jnt_qposadr[j]] * g;
     mom[i] = g;
   }
+  MJB_PSYNC();
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -202,129 +236,162 @@ MJB_HD void make_M(const Env& d) {
   const DModel& m = d.m;
   const int nbody = m.sz.nbody, nv = m.sz.nv;
   FD crb = d.crb(), cinert = d.cinert(), cdof = d.cdof(), M = d.M();
-  for (int i = 0; i < 10 * nbody; i++) crb[i] = cinert[i];
-  for (int i = nbody - 1; i > 0; i--) {
-    const int p = m.body_parentid[i];
-    if (p > 0) for (int k = 0; k < 10; k++) crb[10 * p + k] += crb[10 * i + k];
-  }
-  for (int i = 0; i < m.sz.nC; i++) M[i] = 0;
-  for (int i = 0; i < nv; i++) {
+  MJB_PFOR(i, 10 * nbody) crb[i] = cinert[i];
+  MJB_PFOR(i, m.sz.nC) M[i] = 0;
+  MJB_PSYNC();
+  tree_accumulate(d, crb, 10, true);
+  MJB_PFOR(i, nv) {
     const int adr = m.M_rowadr[i];
-    if (m.dof_simplenum[i]) { M[adr] = m.dof_M0[i]; continue; }
-    int a = adr + m.M_rownnz[i] - 1;
-    M[a] = m.dof_armature_eff[i];
-    S6 buf = mul_inert(ld10(crb, 10 * m.dof_bodyid[i]), ld6(cdof, 6 * i));
-    for (int j = i; j >= 0; j = m.dof_parentid[j]) {
-      M[a] += dot6(ld6(cdof, 6 * j), buf);
-      a--;
-    }
-  }
-  // tendon armature: M += armature * J' J  over the tendon's sparsity pattern
-  FD tJ = d.ten_J();
-  for (int k = 0; k < m.sz.ntendon; k++) {
-    const double arm = m.tendon_armature_eff[k];
-    if (!arm) continue;
-    const int jadr = m.ten_J_rowadr[k], jnnz = m.ten_J_rownnz[k];
-    for (int j = 0; j < jnnz; j++) {
-      const double Ji = tJ[jadr + j];
-      if (!Ji) continue;
-      const int i = m.ten_J_colind[jadr + j];
-      const int madr = m.M_rowadr[i], mnnz = m.M_rownnz[i];
-      const double scl = arm * Ji;
-      // walk both sorted index lists (mju_addToSclSparseInc)
-      int a = 0, b = 0;
-      while (a < mnnz && b < jnnz) {
-        const int ca = m.M_colind[madr + a], cb = m.ten_J_colind[jadr + b];
-        if (ca == cb) { M[madr + a] += scl * tJ[jadr + b]; a++; b++; }
-        else if (ca < cb) a++;
-        else b++;
+    if (m.dof_simplenum[i]) { M[adr] = m.dof_M0[i]; }
+    else {
+      int a = adr + m.M_rownnz[i] - 1;
+      double acc = m.dof_armature_eff[i];
+      S6 buf = mul_inert(ld10(crb, 10 * m.dof_bodyid[i]), ld6(cdof, 6 * i));
+      for (int j = i; j >= 0; j = m.dof_parentid[j]) {
+        M[a] = acc + dot6(ld6(cdof, 6 * j), buf);
+        acc = 0;
+        a--;
       }
     }
+  }
+  MJB_PSYNC();
+  // tendon armature: M += armature * J' J  over the tendon's sparsity pattern (rare; serial)
+  bool any = false;
+  for (int k = 0; k < m.sz.ntendon; k++) any = any || (m.tendon_armature_eff[k] != 0);
+  if (any) {
+    MJB_LANE0 {
+      FD tJ = d.ten_J();
+      for (int k = 0; k < m.sz.ntendon; k++) {
+        const double arm = m.tendon_armature_eff[k];
+        if (!arm) continue;
+        const int jadr = m.ten_J_rowadr[k], jnnz = m.ten_J_rownnz[k];
+        for (int j = 0; j < jnnz; j++) {
+          const double Ji = tJ[jadr + j];
+          if (!Ji) continue;
+          const int i = m.ten_J_colind[jadr + j];
+          const int madr = m.M_rowadr[i], mnnz = m.M_rownnz[i];
+          const double scl = arm * Ji;
+          int a = 0, b = 0;   // walk both sorted index lists (mju_addToSclSparseInc)
+          while (a < mnnz && b < jnnz) {
+            const int ca = m.M_colind[madr + a], cb = m.ten_J_colind[jadr + b];
+            if (ca == cb) { M[madr + a] += scl * tJ[jadr + b]; a++; b++; }
+            else if (ca < cb) a++;
+            else b++;
+          }
+        }
+      }
+    }
+    MJB_PSYNC();
   }
 }
 
 // ------------------------------------------------------------------------------------------------
-// in-place sparse L'DL of a tree-sparse matrix in M's CSR pattern
-MJB_HD void factor_I(const DModel& m, FD mat, FD diaginv) {
+// in-place sparse L'DL of a tree-sparse matrix in M's CSR pattern.  Pivot rows are processed
+// serially (nv-1..0) as in the reference; the element updates of one pivot are independent and
+// come from the host-built program (fac_*).
+MJB_HD void factor_I(const Env& d, FD mat, FD diaginv) {
+  const DModel& m = d.m;
   const int nv = m.sz.nv;
   for (int k = nv - 1; k >= 0; k--) {
     const int start = m.M_rowadr[k];
     const int diag = m.M_rownnz[k] - 1;
-    const int end = start + diag;
-    const double invD = 1 / mat[end];
-    diaginv[k] = invD;
-    for (int adr = end - 1; adr >= start; adr--) {
-      const int i = m.M_colind[adr];
-      const double s = -mat[adr] * invD;
-      const int ri = m.M_rowadr[i], ni = m.M_rownnz[i];
-      for (int c = 0; c < ni; c++) mat[ri + c] += mat[start + c] * s;
+    const double invD = 1 / mat[start + diag];
+    MJB_LANE0 diaginv[k] = invD;
+    if (diag == 0) continue;
+    const int pa = m.fac_adr[k], pn = m.fac_adr[k + 1] - pa;
+    MJB_PFOR(t, pn) {
+      const int dst = m.fac_dst[pa + t];
+      mat[dst] += mat[m.fac_src[pa + t]] * (-mat[m.fac_cf[pa + t]] * invD);
     }
-    for (int c = 0; c < diag; c++) mat[start + c] = mat[start + c] * invD;
+    MJB_PSYNC();
+    MJB_PFOR(c, diag) mat[start + c] = mat[start + c] * invD;
+    MJB_PSYNC();
   }
+  MJB_PSYNC();
 }
 
-// in-place x <- (L'DL)^-1 x for one right-hand side
-MJB_HD void solve_LD(const DModel& m, FD x, FD qLD, FD qLDiagInv) {
+// in-place x <- (L'DL)^-1 x for one right-hand side, by dof-tree levels
+MJB_HD void solve_LD(const Env& d, FD x, FD qLD, FD qLDiagInv) {
+  const DModel& m = d.m;
   const int nv = m.sz.nv;
-  for (int i = nv - 1; i >= 0; i--) {
-    const int nnz = m.M_rownnz[i];
-    if (nnz == 1) continue;
-    const double xi = x[i];
-    if (xi != 0) {
-      const int start = m.M_rowadr[i], end = start + nnz - 1;
-      for (int adr = start; adr < end; adr++) x[m.M_colind[adr]] -= qLD[adr] * xi;
+  // x <- L^-T x : deepest dofs are final; each dof then gathers its descendants' contributions in
+  // descending descendant order (the order of the serial scatter loop)
+  for (int l = m.sz.ndlevel - 2; l >= 0; l--) {
+    const int adr = m.dlvl_adr[l], cnt = m.dlvl_adr[l + 1] - adr;
+    MJB_PFOR(t, cnt) {
+      const int j = m.dlvl_dof[adr + t];
+      const int a0 = m.mt_adr[j], an = m.mt_adr[j + 1] - a0;
+      if (an) {
+        double s = x[j];
+        for (int c = 0; c < an; c++) {
+          const double xi = x[m.mt_dof[a0 + c]];
+          if (xi != 0) s -= qLD[m.mt_qadr[a0 + c]] * xi;
+        }
+        x[j] = s;
+      }
     }
+    MJB_PSYNC();
   }
-  for (int i = 0; i < nv; i++) x[i] *= qLDiagInv[i];
-  for (int i = 0; i < nv; i++) {
-    const int nnz = m.M_rownnz[i];
-    if (nnz == 1) continue;
-    const int adr = m.M_rowadr[i], dn = nnz - 1;
-    x[i] -= dot_sparse_ref(dn, [&](int c) { return qLD[adr + c]; },
-                           [&](int c) { return x[m.M_colind[adr + c]]; });
+  MJB_PFOR(i, nv) x[i] *= qLDiagInv[i];
+  MJB_PSYNC();
+  // x <- L^-1 x : shallow dofs are final first
+  for (int l = 1; l < m.sz.ndlevel; l++) {
+    const int adr = m.dlvl_adr[l], cnt = m.dlvl_adr[l + 1] - adr;
+    MJB_PFOR(t, cnt) {
+      const int i = m.dlvl_dof[adr + t];
+      const int ra = m.M_rowadr[i], dn = m.M_rownnz[i] - 1;
+      x[i] -= dot_sparse_ref(dn, [&](int c) { return qLD[ra + c]; },
+                             [&](int c) { return x[m.M_colind[ra + c]]; });
+    }
+    MJB_PSYNC();
   }
 }
 
 // ------------------------------------------------------------------------------------------------
-// com-frame body velocities and time derivatives of the motion axes
+// com-frame body velocities and time derivatives of the motion axes, level by level
 MJB_HD void com_vel(const Env& d) {
   const DModel& m = d.m;
-  const int nbody = m.sz.nbody;
   FD cvel = d.cvel(), cdof = d.cdof(), cdd = d.cdof_dot(), qvel = d.qvel();
-  for (int k = 0; k < 6; k++) cvel[k] = 0;
-  for (int i = 1; i < nbody; i++) {
-    S6 cv = ld6(cvel, 6 * m.body_parentid[i]);
-    const int dn = m.body_dofnum[i], bda = m.body_dofadr[i];
-    for (int j = 0; j < dn; j++) {
-      const int jt = m.jnt_type[m.dof_jntid[bda + j]];
-      if (jt == JNT_FREE || jt == JNT_BALL) {
-        if (jt == JNT_FREE) {
-          for (int k = 0; k < 18; k++) cdd[6 * bda + k] = 0;
-          // cvel += cdof[0..2]' * qvel[0..2]   (mju_mulMatTVec: skip exact zeros, row by row)
+  MJB_LANE0 { for (int k = 0; k < 6; k++) cvel[k] = 0; }
+  MJB_PSYNC();
+  for (int l = 1; l < m.sz.nlevel; l++) {
+    const int ladr = m.lvl_adr[l], cnt = m.lvl_adr[l + 1] - ladr;
+    MJB_PFOR(k_, cnt) {
+      const int i = m.lvl_body[ladr + k_];
+      S6 cv = ld6(cvel, 6 * m.body_parentid[i]);
+      const int dn = m.body_dofnum[i], bda = m.body_dofadr[i];
+      for (int j = 0; j < dn; j++) {
+        const int jt = m.jnt_type[m.dof_jntid[bda + j]];
+        if (jt == JNT_FREE || jt == JNT_BALL) {
+          if (jt == JNT_FREE) {
+            for (int k = 0; k < 18; k++) cdd[6 * bda + k] = 0;
+            // cvel += cdof[0..2]' * qvel[0..2]   (mju_mulMatTVec: skip exact zeros, row by row)
+            S6 t; for (int k = 0; k < 6; k++) t.v[k] = 0;
+            for (int r = 0; r < 3; r++) {
+              const double s = qvel[bda + r];
+              if (s != 0) for (int k = 0; k < 6; k++) t.v[k] += cdof[6 * (bda + r) + k] * s;
+            }
+            for (int k = 0; k < 6; k++) cv.v[k] += t.v[k];
+            j += 3;
+          }
+          for (int r = 0; r < 3; r++) st6(cdd, 6 * (bda + j + r), cross_motion(cv, ld6(cdof, 6 * (bda + j + r))));
           S6 t; for (int k = 0; k < 6; k++) t.v[k] = 0;
           for (int r = 0; r < 3; r++) {
-            const double s = qvel[bda + r];
-            if (s != 0) for (int k = 0; k < 6; k++) t.v[k] += cdof[6 * (bda + r) + k] * s;
+            const double s = qvel[bda + j + r];
+            if (s != 0) for (int k = 0; k < 6; k++) t.v[k] += cdof[6 * (bda + j + r) + k] * s;
           }
           for (int k = 0; k < 6; k++) cv.v[k] += t.v[k];
-          j += 3;
+          j += 2;
+        } else {
+          S6 cd = ld6(cdof, 6 * (bda + j));
+          st6(cdd, 6 * (bda + j), cross_motion(cv, cd));
+          const double s = qvel[bda + j];
+          for (int k = 0; k < 6; k++) cv.v[k] += cd.v[k] * s;
         }
-        for (int r = 0; r < 3; r++) st6(cdd, 6 * (bda + j + r), cross_motion(cv, ld6(cdof, 6 * (bda + j + r))));
-        S6 t; for (int k = 0; k < 6; k++) t.v[k] = 0;
-        for (int r = 0; r < 3; r++) {
-          const double s = qvel[bda + j + r];
-          if (s != 0) for (int k = 0; k < 6; k++) t.v[k] += cdof[6 * (bda + j + r) + k] * s;
-        }
-        for (int k = 0; k < 6; k++) cv.v[k] += t.v[k];
-        j += 2;
-      } else {
-        S6 cd = ld6(cdof, 6 * (bda + j));
-        st6(cdd, 6 * (bda + j), cross_motion(cv, cd));
-        const double s = qvel[bda + j];
-        for (int k = 0; k < 6; k++) cv.v[k] += cd.v[k] * s;
       }
+      st6(cvel, 6 * i, cv);
     }
-    st6(cvel, 6 * i, cv);
+    MJB_PSYNC();
   }
 }
 
@@ -349,31 +416,37 @@ MJB_HD void rne_bias(const Env& d) {
   const int nbody = m.sz.nbody, nv = m.sz.nv;
   FD cacc = d.scr_body(), cfrc = d.scr_body() + 6 * nbody;
   FD cinert = d.cinert(), cvel = d.cvel(), cdof = d.cdof(), cdd = d.cdof_dot(), qvel = d.qvel();
-  for (int k = 0; k < 6; k++) cacc[k] = 0;
-  if (!(m.opt.disableflags & DSBL_GRAVITY)) {
-    cacc[3] = m.opt.gravity[0] * -1; cacc[4] = m.opt.gravity[1] * -1; cacc[5] = m.opt.gravity[2] * -1;
+  MJB_LANE0 {
+    for (int k = 0; k < 6; k++) { cacc[k] = 0; cfrc[k] = 0; }
+    if (!(m.opt.disableflags & DSBL_GRAVITY)) {
+      cacc[3] = m.opt.gravity[0] * -1; cacc[4] = m.opt.gravity[1] * -1; cacc[5] = m.opt.gravity[2] * -1;
+    }
   }
-  for (int i = 1; i < nbody; i++) {
-    const int bda = m.body_dofadr[i];
-    S6 t = mul_dof_vec(cdd + 6 * bda, qvel + bda, m.body_dofnum[i]);
-    S6 a = ld6(cacc, 6 * m.body_parentid[i]);
-    for (int k = 0; k < 6; k++) a.v[k] = a.v[k] + t.v[k];
-    st6(cacc, 6 * i, a);
-    I10 I = ld10(cinert, 10 * i);
-    S6 f = mul_inert(I, a);
-    S6 v = ld6(cvel, 6 * i);
-    S6 Iv = mul_inert(I, v);
-    S6 c = cross_force(v, Iv);
-    for (int k = 0; k < 6; k++) f.v[k] += c.v[k];
-    st6(cfrc, 6 * i, f);
+  MJB_PSYNC();
+  for (int l = 1; l < m.sz.nlevel; l++) {
+    const int ladr = m.lvl_adr[l], cnt = m.lvl_adr[l + 1] - ladr;
+    MJB_PFOR(k_, cnt) {
+      const int i = m.lvl_body[ladr + k_];
+      const int bda = m.body_dofadr[i];
+      S6 t = mul_dof_vec(cdd + 6 * bda, qvel + bda, m.body_dofnum[i]);
+      S6 a = ld6(cacc, 6 * m.body_parentid[i]);
+      for (int k = 0; k < 6; k++) a.v[k] = a.v[k] + t.v[k];
+      st6(cacc, 6 * i, a);
+      I10 I = ld10(cinert, 10 * i);
+      S6 f = mul_inert(I, a);
+      S6 v = ld6(cvel, 6 * i);
+      S6 Iv = mul_inert(I, v);
+      S6 c = cross_force(v, Iv);
+      for (int k = 0; k < 6; k++) f.v[k] += c.v[k];
+      st6(cfrc, 6 * i, f);
+    }
+    MJB_PSYNC();
   }
-  for (int k = 0; k < 6; k++) cfrc[k] = 0;
-  for (int i = nbody - 1; i > 0; i--) {
-    const int p = m.body_parentid[i];
-    if (p) for (int k = 0; k < 6; k++) cfrc[6 * p + k] += cfrc[6 * i + k];
-  }
+  // backward accumulation; the reference zeroes the world force first and never adds into it
+  tree_accumulate(d, cfrc, 6, true);
   FD out = d.qfrc_bias();
-  for (int i = 0; i < nv; i++) out[i] = dot6(ld6(cdof, 6 * i), ld6(cfrc, 6 * m.dof_bodyid[i]));
+  MJB_PFOR(i, nv) out[i] = dot6(ld6(cdof, 6 * i), ld6(cfrc, 6 * m.dof_bodyid[i]));
+  MJB_PSYNC();
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -382,11 +455,12 @@ MJB_HD void passive(const Env& d) {
   const DModel& m = d.m;
   const int nv = m.sz.nv;
   FD fs = d.qfrc_spring(), fd = d.qfrc_damper(), fp = d.qfrc_passive(), qpos = d.qpos(), qvel = d.qvel();
-  for (int i = 0; i < nv; i++) { fs[i] = 0; fd[i] = 0; fp[i] = 0; }
+  MJB_PFOR(i, nv) { fs[i] = 0; fd[i] = 0; fp[i] = 0; }
+  MJB_PSYNC();
   const bool spring = !(m.opt.disableflags & DSBL_SPRING), damper = !(m.opt.disableflags & DSBL_DAMPER);
   if (!spring && !damper) return;
   if (spring) {
-    for (int j = 0; j < m.sz.njnt; j++) {
+    MJB_PFOR(j, m.sz.njnt) {
       const double k0 = m.jnt_stiffness[j];
       const double* sp = m.jnt_stiffnesspoly + kNPoly * j;
       if (k0 == 0 && sp[0] == 0 && sp[1] == 0) continue;
@@ -413,7 +487,7 @@ MJB_HD void passive(const Env& d) {
     }
   }
   if (damper) {
-    for (int i = 0; i < nv; i++) {
+    MJB_PFOR(i, nv) {
       const double b = m.dof_damping_eff[i];
       const double* bp = m.dof_dampingpoly_eff + kNPoly * i;
       if (b != 0 || bp[0] != 0 || bp[1] != 0) {
@@ -422,30 +496,37 @@ MJB_HD void passive(const Env& d) {
       }
     }
   }
-  FD tl = d.ten_length(), tv = d.ten_velocity(), tJ = d.ten_J();
-  for (int i = 0; i < m.sz.ntendon; i++) {
-    double k0 = 0, b0 = 0;
-    const double* sp = m.tendon_stiffnesspoly + kNPoly * i;
-    double dp[kNPoly] = {0, 0};
-    if (spring) k0 = m.tendon_stiffness[i];
-    if (damper) { b0 = m.tendon_damping_eff[i]; dp[0] = m.tendon_dampingpoly_eff[kNPoly * i]; dp[1] = m.tendon_dampingpoly_eff[kNPoly * i + 1]; }
-    if (k0 == 0 && (!spring || (sp[0] == 0 && sp[1] == 0)) && b0 == 0 && dp[0] == 0 && dp[1] == 0) continue;
-    const double len = tl[i], lo = m.tendon_lengthspring[2 * i], hi = m.tendon_lengthspring[2 * i + 1];
-    const double x = (len > hi) ? len - hi : (len < lo) ? len - lo : 0;
-    const double f_s = spring ? -x * poly_force(k0, sp, kNPoly, x, false) : 0;
-    const double v = tv[i];
-    const double f_d = damper ? -v * poly_force(b0, dp, kNPoly, v, true) : 0;
-    if (f_s || f_d) {
-      const int adr = m.ten_J_rowadr[i], end = adr + m.ten_J_rownnz[i];
-      for (int j = adr; j < end; j++) {
-        const int k = m.ten_J_colind[j];
-        const double Jv = tJ[j];
-        fs[k] += Jv * f_s;
-        fd[k] += Jv * f_d;
+  MJB_PSYNC();
+  if (m.sz.ntendon) {
+    MJB_LANE0 {   // tendons may share dofs: keep the reference's serial accumulation order
+      FD tl = d.ten_length(), tv = d.ten_velocity(), tJ = d.ten_J();
+      for (int i = 0; i < m.sz.ntendon; i++) {
+        double k0 = 0, b0 = 0;
+        const double* sp = m.tendon_stiffnesspoly + kNPoly * i;
+        double dp[kNPoly] = {0, 0};
+        if (spring) k0 = m.tendon_stiffness[i];
+        if (damper) { b0 = m.tendon_damping_eff[i]; dp[0] = m.tendon_dampingpoly_eff[kNPoly * i]; dp[1] = m.tendon_dampingpoly_eff[kNPoly * i + 1]; }
+        if (k0 == 0 && (!spring || (sp[0] == 0 && sp[1] == 0)) && b0 == 0 && dp[0] == 0 && dp[1] == 0) continue;
+        const double len = tl[i], lo = m.tendon_lengthspring[2 * i], hi = m.tendon_lengthspring[2 * i + 1];
+        const double x = (len > hi) ? len - hi : (len < lo) ? len - lo : 0;
+        const double f_s = spring ? -x * poly_force(k0, sp, kNPoly, x, false) : 0;
+        const double v = tv[i];
+        const double f_d = damper ? -v * poly_force(b0, dp, kNPoly, v, true) : 0;
+        if (f_s || f_d) {
+          const int adr = m.ten_J_rowadr[i], end = adr + m.ten_J_rownnz[i];
+          for (int j = adr; j < end; j++) {
+            const int k = m.ten_J_colind[j];
+            const double Jv = tJ[j];
+            fs[k] += Jv * f_s;
+            fd[k] += Jv * f_d;
+          }
+        }
       }
     }
+    MJB_PSYNC();
   }
-  for (int i = 0; i < nv; i++) fp[i] = fs[i] + fd[i];
+  MJB_PFOR(i, nv) fp[i] = fs[i] + fd[i];
+  MJB_PSYNC();
 }
 
 }  // namespace mjb

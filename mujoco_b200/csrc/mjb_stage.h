@@ -11,16 +11,33 @@ MJB_HD bool env_has_warning(const Env& d) {
   return false;
 }
 
-MJB_HD void run_stage(const DModel& m, const Batch& b, int e, int stage, int flags, int lane = 0, int nlane = 1) {
+// stage mask bits: 1<<stage.  forward = stages 0,1,2,4 ; step = stages 0,1,2,3
+constexpr int kMaskStep = 0xF, kMaskForward = 0x17;
+
+// run the selected stages of one environment with its cooperative lanes.
+// flags: bit0 = part of mj_step (qpos/qvel checks), bit1 = skip environments that raised a warning.
+// shot/sint: optional staging area (shared memory) for the hot block; only with env-major storage.
+MJB_HD void run_env(const DModel& m, const Batch& b, int e, int mask, int flags, int lane, int nlane,
+                    double* shot, int* sint) {
   Env d(m, b, e, lane, nlane);
-  if ((flags & 2) && env_has_warning(d)) return;   // rollout: a warned env stops stepping
-  switch (stage) {
-    case 0: stage_position(d, (flags & 1) != 0); break;
-    case 1: stage_velocity(d); break;
-    case 2: stage_solve(d); break;
-    case 3: stage_integrate(d); break;
-    case 4: stage_finish_forward(d); break;
-    default: break;
+  if ((flags & 2) && env_has_warning(d)) return;   // rollout: a warned env stops stepping (uniform per env)
+  double* g = b.dbl + (size_t)e * b.dpitch;
+  int* gi = b.itg + (size_t)e * b.ipitch;
+  if (shot) {
+    for (long i = lane; i < b.L.nhot; i += nlane) shot[i] = g[i];
+    for (long i = lane; i < b.L.nint; i += nlane) sint[i] = gi[i];
+    d.sync();
+    d.stage(shot, sint);
+  }
+  if (mask & 1) stage_position(d, (flags & 1) != 0);
+  if (mask & 2) stage_velocity(d);
+  if (mask & 4) stage_solve(d);
+  if (mask & 8) stage_integrate(d);
+  if (mask & 16) stage_finish_forward(d);
+  if (shot) {
+    d.sync();
+    for (long i = lane; i < b.L.nhot; i += nlane) g[i] = shot[i];
+    for (long i = lane; i < b.L.nint; i += nlane) gi[i] = sint[i];
   }
 }
 

@@ -1,13 +1,18 @@
-// Device-side model (flattened, read-only, replicated per GPU) and the batch data layout
-// (structure-of-arrays across environments) for the batched mj_step path.
+// Device-side model (flattened, read-only, replicated per GPU) and the batch data layout for the
+// batched mj_step path.
 //
-// Layout contract.  Every mjData field the hot path touches (reference include/mujoco/mjxmacro.h
-// :842-1030, MJDATA_POINTERS / MJDATA_ARENA_POINTERS) exists per environment, stored
-//   field[elem][env]   (env fastest, row stride = nenv_padded)
-// so that 32 consecutive environments (one warp, one environment per lane) read or write one
-// 256-byte line per element: fully coalesced HBM/L2 traffic, no per-env arena, no pointer chasing.
-// The per-env arena of the reference (contacts, efc_*) is replaced by fixed caps nconmax / njmax;
-// overflow raises the same warning ids (mjWARN_CONTACTFULL / mjWARN_CNSTRFULL).
+// Thread mappings and storage (both address a field element as  e*pitch + (offset+i)*step):
+//   warp-per-env (default): one warp owns one environment.  Storage is env-major: every
+//       environment has one contiguous block, so the 32 lanes of the warp read/write 32 consecutive
+//       elements = one 256-byte line.  The fused step kernel stages the block's HOT part (state and
+//       every smooth-dynamics / contact / constraint-vector field, MJB_DATA_DBL_FIELDS below) into
+//       shared memory, runs all pipeline stages there, and writes it back once; the COLD part
+//       (efc_J, efc_Y, efc_AR: njmax*nv / njmax^2 doubles) stays in global memory / L2.
+//   lane-per-env (mapping 0): one lane owns one environment, storage is field[elem][env]
+//       (SoA across environments): a warp of 32 environments reads one line per element.
+// Every mjData field the hot path touches (reference include/mujoco/mjxmacro.h:842-1030) exists
+// per environment.  The per-env arena of the reference (contacts, efc_*) is replaced by fixed caps
+// nconmax / njmax; overflow raises the same warning ids (mjWARN_CONTACTFULL / mjWARN_CNSTRFULL).
 //
 // This header is shared by the CUDA build (nvcc, sm_100a) and the test-only host emulation.
 #pragma once
@@ -38,6 +43,7 @@ enum { DSBL_CONSTRAINT = 1 << 0, DSBL_EQUALITY = 1 << 1, DSBL_FRICTIONLOSS = 1 <
        DSBL_CLAMPCTRL = 1 << 8, DSBL_WARMSTART = 1 << 9, DSBL_FILTERPARENT = 1 << 10,
        DSBL_ACTUATION = 1 << 11, DSBL_REFSAFE = 1 << 12, DSBL_EULERDAMP = 1 << 15,
        DSBL_AUTORESET = 1 << 16, DSBL_ISLAND = 1 << 18 };                                // :54-73
+enum { LIM_HINGE = 0, LIM_BALL = 1, LIM_TENDON = 2 };   // kinds of limit candidates (host-built table)
 constexpr int kNPoly = 2;   // mjNPOLY (include/mujoco/mjmodel.h:44)
 constexpr int kNGain = 3;   // leading gain/bias parameters used by the supported actuator family
 
@@ -47,6 +53,10 @@ struct Sizes {
   int npair;     // static candidate geom pairs (host-built, reference order)
   int nconmax;   // per-env contact cap
   int njmax;     // per-env constraint-row cap
+  int nlevel;    // depth levels of the body tree (level 0 = world)
+  int ndlevel;   // depth levels of the dof tree
+  int nlim;      // limit candidates (joint sides, ball joints, tendon sides) in row order
+  int nfl;       // dofs with frictionloss, in row order
 };
 
 struct Options {
@@ -60,7 +70,9 @@ struct Options {
   int has_frictionloss; // any dof/tendon frictionloss
 };
 
-// model arrays: one int blob and one double blob in device memory; members are pointers into them
+// model arrays: one int blob and one double blob in device memory; members are pointers into them.
+// The last group are host-built schedules that let a warp run the tree recursions level by level
+// while reproducing the reference's serial accumulation order (see mjb_model.cc).
 #define MJB_MODEL_INT_FIELDS(X)                                                             \
   X(body_parentid) X(body_rootid) X(body_weldid) X(body_jntnum) X(body_jntadr) X(body_dofnum) \
   X(body_dofadr) X(body_geomnum) X(body_geomadr) X(body_sameframe)                          \
@@ -72,7 +84,11 @@ struct Options {
   X(ten_J_rownnz) X(ten_J_rowadr) X(ten_J_colind)                                            \
   X(actuator_trnjnt) X(actuator_gaintype) X(actuator_biastype) X(actuator_ctrllimited)       \
   X(actuator_forcelimited)                                                                   \
-  X(pair_geom1) X(pair_geom2) X(pair_dim)
+  X(pair_geom1) X(pair_geom2) X(pair_dim)                                                     \
+  X(lvl_adr) X(lvl_body) X(child_adr) X(child_id)                                             \
+  X(dlvl_adr) X(dlvl_dof) X(mt_adr) X(mt_dof) X(mt_qadr)                                      \
+  X(fac_adr) X(fac_dst) X(fac_src) X(fac_cf)                                                  \
+  X(lim_kind) X(lim_id) X(lim_side) X(fl_dof) X(body_dofanc)
 
 #define MJB_MODEL_DBL_FIELDS(X)                                                             \
   X(qpos0) X(qpos_spring) X(body_pos) X(body_quat) X(body_ipos) X(body_iquat) X(body_mass)   \
@@ -101,7 +117,7 @@ struct DModel {
 };
 
 // ---- batch data fields (per environment), sizes in elements -------------------------------------
-// X(name, count)  -- doubles
+// HOT doubles: staged in shared memory by the fused warp-per-env kernel
 #define MJB_DATA_DBL_FIELDS(X, S)                                                            \
   X(time, 1) X(qpos, S.nq) X(qvel, S.nv) X(ctrl, S.nu) X(qacc_warmstart, S.nv)                \
   X(qfrc_applied, S.nv)                                                                      \
@@ -119,26 +135,33 @@ struct DModel {
   X(con_dist, S.nconmax) X(con_pos, 3 * S.nconmax) X(con_frame, 9 * S.nconmax)               \
   X(con_includemargin, S.nconmax) X(con_friction, 5 * S.nconmax) X(con_solref, 2 * S.nconmax) \
   X(con_solimp, 5 * S.nconmax) X(con_mu, S.nconmax)                                          \
-  X(efc_J, S.njmax * S.nv) X(efc_pos, S.njmax) X(efc_margin, S.njmax)                        \
+  X(efc_pos, S.njmax) X(efc_margin, S.njmax)                                                 \
   X(efc_frictionloss, S.njmax) X(efc_diagA, S.njmax) X(efc_KBIP, 4 * S.njmax)                \
   X(efc_D, S.njmax) X(efc_R, S.njmax) X(efc_vel, S.njmax) X(efc_aref, S.njmax)               \
   X(efc_b, S.njmax) X(efc_force, S.njmax)                                                    \
-  X(efc_Y, S.njmax * S.nv) X(efc_AR, S.njmax * S.njmax)                                       \
-  X(scr_body, 12 * S.nbody) X(scr_nv, 8 * S.nv) X(scr_efc, 8 * S.njmax) X(scr_jac, 6 * S.nv)
+  X(scr_body, 12 * S.nbody) X(scr_nv, 8 * S.nv) X(scr_efc, 6 * S.njmax)                      \
+  X(scr_pair, 24 * S.npair)
 
-// ints
+// COLD doubles: stay in global memory / L2 in every mapping
+#define MJB_DATA_COLD_FIELDS(X, S)                                                           \
+  X(efc_J, S.njmax * S.nv) X(efc_Y, S.njmax * S.nv) X(efc_AR, S.njmax * S.njmax)
+
+// ints (all hot)
 #define MJB_DATA_INT_FIELDS(X, S)                                                            \
   X(ncon, 1) X(nefc, 1) X(ne, 1) X(nf, 1) X(nl, 1) X(solver_niter, 1) X(warning, NWARNING)     \
   X(con_geom1, S.nconmax) X(con_geom2, S.nconmax) X(con_dim, S.nconmax)                       \
-  X(con_exclude, S.nconmax) X(con_efcadr, S.nconmax)                                          \
-  X(efc_type, S.njmax) X(efc_id, S.njmax) X(efc_state, S.njmax) X(scr_int, 4 * S.njmax)
+  X(con_exclude, S.nconmax) X(con_efcadr, S.nconmax) X(con_pair, S.nconmax)                    \
+  X(efc_type, S.njmax) X(efc_id, S.njmax) X(efc_state, S.njmax) X(scr_int, 4 * S.njmax)        \
+  X(scr_ipair, S.npair + 4) X(scr_ilim, 2 * S.nlim + 4)
 
 struct Layout {
 #define X(name, cnt) long name;
   MJB_DATA_DBL_FIELDS(X, _)
+  MJB_DATA_COLD_FIELDS(X, _)
   MJB_DATA_INT_FIELDS(X, _)
 #undef X
-  long ndbl, nint;   // elements per environment
+  long nhot;         // hot doubles per environment (offsets [0, nhot))
+  long ndbl, nint;   // total doubles / ints per environment
 };
 
 inline Layout make_layout(const Sizes& S) {
@@ -146,6 +169,9 @@ inline Layout make_layout(const Sizes& S) {
   long o = 0;
 #define X(name, cnt) L.name = o; o += (long)(cnt);
   MJB_DATA_DBL_FIELDS(X, S)
+  o = (o + 15) / 16 * 16;
+  L.nhot = o;
+  MJB_DATA_COLD_FIELDS(X, S)
   L.ndbl = o;
   o = 0;
   MJB_DATA_INT_FIELDS(X, S)
@@ -166,10 +192,6 @@ using FD = Fld<double>;
 using FI = Fld<int>;
 
 // batch storage handle (device or host pointers)
-// Two physical layouts share one addressing rule  addr(field o, elem i, env e) = e*pitch + (o+i)*step :
-//   lane-per-env kernels : field[elem][env]  (pitch 1, step = padded nenv)  -> a warp of 32 envs reads one line
-//   warp-per-env kernels : env[field][elem]  (pitch = per-env block, step 1) -> a warp reads one env's
-//                          consecutive elements: again one line per 32 elements
 struct Batch {
   double* dbl;
   int* itg;
@@ -180,18 +202,33 @@ struct Batch {
   Layout L;
 };
 
-// per-environment accessor
+// per-environment accessor.  hd/hi may point at a shared-memory copy of the hot block.
 struct Env {
   const DModel& m;
   const Batch& b;
   int e;
   int lane, nlane;   // cooperative lanes working on this environment (1 lane in lane-per-env mode)
+  double* hd; size_t hstep;   // hot doubles
+  double* cd; size_t cstep;   // cold doubles (same offsets, global memory)
+  int* hi; size_t istep;      // ints
   MJB_HD Env(const DModel& m_, const Batch& b_, int e_, int lane_ = 0, int nlane_ = 1)
-      : m(m_), b(b_), e(e_), lane(lane_), nlane(nlane_) {}
-#define X(name, cnt) MJB_HD FD name() const { return FD{b.dbl + (size_t)e * b.dpitch + (size_t)b.L.name * b.dstep, b.dstep}; }
+      : m(m_), b(b_), e(e_), lane(lane_), nlane(nlane_) {
+    hd = b.dbl + (size_t)e * b.dpitch; hstep = b.dstep;
+    cd = hd; cstep = b.dstep;
+    hi = b.itg + (size_t)e * b.ipitch; istep = b.istep;
+  }
+  MJB_HD Env(const Env& o, int lane_, int nlane_)
+      : m(o.m), b(o.b), e(o.e), lane(lane_), nlane(nlane_), hd(o.hd), hstep(o.hstep), cd(o.cd), cstep(o.cstep),
+        hi(o.hi), istep(o.istep) {}
+  // redirect the hot block (doubles and ints) to a staged copy with unit stride
+  MJB_HD void stage(double* hot, int* ints) { hd = hot; hstep = 1; hi = ints; istep = 1; }
+#define X(name, cnt) MJB_HD FD name() const { return FD{hd + (size_t)b.L.name * hstep, hstep}; }
   MJB_DATA_DBL_FIELDS(X, _)
 #undef X
-#define X(name, cnt) MJB_HD FI name() const { return FI{b.itg + (size_t)e * b.ipitch + (size_t)b.L.name * b.istep, b.istep}; }
+#define X(name, cnt) MJB_HD FD name() const { return FD{cd + (size_t)b.L.name * cstep, cstep}; }
+  MJB_DATA_COLD_FIELDS(X, _)
+#undef X
+#define X(name, cnt) MJB_HD FI name() const { return FI{hi + (size_t)b.L.name * istep, istep}; }
   MJB_DATA_INT_FIELDS(X, _)
 #undef X
   // barrier + memory ordering between the lanes that share this environment
@@ -218,6 +255,7 @@ MJB_HD S6 ld6(FD f, long i) { S6 r; for (int k = 0; k < 6; k++) r.v[k] = f[i + k
 MJB_HD void st6(FD f, long i, const S6& a) { for (int k = 0; k < 6; k++) f[i + k] = a.v[k]; }
 MJB_HD I10 ld10(FD f, long i) { I10 r; for (int k = 0; k < 10; k++) r.v[k] = f[i + k]; return r; }
 MJB_HD void st10(FD f, long i, const I10& a) { for (int k = 0; k < 10; k++) f[i + k] = a.v[k]; }
+
 // dot products in the reference's accumulation order (the summation order is part of parity):
 // dense  : engine_util_blas.c:493-523 (mju_dot)   -> (r0+r2)+(r1+r3), tail added as one grouped sum
 // sparse : engine_util_sparse.h:197-222 (mju_dotSparse) -> same 4 lanes, tail added one by one

@@ -145,6 +145,14 @@ static void roll_range(RollJob* j, int lo, int hi) {
     for (int i = 0; i < mjNWARNING; i++) d->warning[i].number = 0;
     long sc = 0, se = 0, si = 0;
     for (int t = 0; t < j->nstep; t++) {
+      /* rollout.cc:127-155: once any warning fired, pad the remaining outputs with the current state */
+      int nwarning = 0;
+      for (int i = 0; i < mjNWARNING; i++) if (d->warning[i].number) { nwarning = 1; break; }
+      if (nwarning) {
+        for (; t < j->nstep; t++)
+          if (j->state) mj_getState(m, d, j->state + ((size_t)r*j->nstep + t)*j->nstate, mjSTATE_FULLPHYSICS);
+        break;
+      }
       if (j->ctrl) mju_copy(d->ctrl, j->ctrl + ((size_t)r*j->nstep + t)*j->nu, j->nu);
       mj_step(m, d);
       sc += d->ncon; se += d->nefc;

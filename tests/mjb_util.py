@@ -22,7 +22,7 @@ def hostemu_lib():
     return _hostemu
 
 
-def make_pair(path, solver, library=None, nenv=4, **opts):
+def make_pair(path, solver, library=None, nenv=4, nconmax=64, njmax=200, warp_per_env=True, **opts):
     """(product/hostemu model+batch, oracle) with identical option overrides"""
     m = mb.Model(path, library=library)
     o = Oracle(path)
@@ -31,7 +31,7 @@ def make_pair(path, solver, library=None, nenv=4, **opts):
     for k, v in opts.items():
         m.set_option(k, v)
         o.set_opt(k, v)
-    b = mb.Batch(m, nenv)
+    b = mb.Batch(m, nenv, nconmax=nconmax, njmax=njmax, warp_per_env=warp_per_env)
     return m, b, o
 
 

@@ -47,9 +47,16 @@ def test_mjb_fixture_equals_fresh_compile():
 
 @pytest.mark.skipif(not os.path.exists("/root/reference/test/engine/testdata/collision_driver/humanoid.xml"),
                     reason="reference test data not present")
-def test_reference_known_answer_contact_count():
-    """test/engine/engine_collision_driver_test.cc:98-129 (ContactCount): exactly 8 contacts"""
-    o = Oracle("/root/reference/test/engine/testdata/collision_driver/humanoid.xml")
+def test_reference_known_answer_contact_count(tmp_path):
+    """test/engine/engine_collision_driver_test.cc:98-129 (ContactCount): a free body carrying eight
+    unit spheres resting on a plane gives exactly 8 contacts (scene restated from the test's text)"""
+    spheres = "".join('<geom type="sphere" size="1" pos="%d %d 0"/>' % (s * a, s * b)
+                      for s in (1, 2) for a in (-1, 1) for b in (-1, 1))
+    xml = ('<mujoco><worldbody><body><geom type="plane" size="5 5 .01"/></body>'
+           '<body pos="0 0 0.9"><freejoint/>%s</body></worldbody></mujoco>' % spheres)
+    p = tmp_path / "contact_count.xml"
+    p.write_text(xml)
+    o = Oracle(str(p))
     o.forward()
     assert int(o.scalar("ncon")) == 8
 
