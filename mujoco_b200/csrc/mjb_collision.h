@@ -114,9 +114,40 @@ MJB_HD int collide_capsule_capsule(PreCon* c, double margin, V3 p1, const M3& m1
   return n1 + n2 + n3 + n4;
 }
 
-// walk the static candidate table cooperatively: every lane tests its candidates and parks up to two
-// pre-contacts per pair in scratch; a serial scan then assigns contact slots IN TABLE ORDER (the
-// reference's emission order), and the lanes copy their pairs' contacts into place.
+// filter + narrowphase of candidate pair p; returns the number of pre-contacts written to pc[0..1]
+MJB_HD int pair_collide(const Env& d, int p, PreCon* pc) {
+  const DModel& m = d.m;
+  FD gx = d.geom_xpos(), gm = d.geom_xmat();
+  const int g1 = m.pair_geom1[p], g2 = m.pair_geom2[p];
+  const int t1 = m.geom_type[g1], t2 = m.geom_type[g2];
+  const double margin = m.pair_margin[p];
+  const double rb1 = m.geom_rbound[g1], rb2 = m.geom_rbound[g2];
+  V3 p1 = ld3(gx, 3 * g1), p2 = ld3(gx, 3 * g2);
+  // per-pair filter (mj_filterSphere)
+  if (rb1 > 0 && rb2 > 0) {
+    V3 dif = p1 - p2;
+    double dsq = dif.x * dif.x + dif.y * dif.y + dif.z * dif.z;
+    double bound = rb1 + rb2 + margin;
+    if (dsq > bound * bound) return 0;
+  } else if (t1 == GEOM_PLANE && rb2 > 0) {
+    V3 nrm{gm[9 * g1 + 2], gm[9 * g1 + 5], gm[9 * g1 + 8]};
+    V3 dif = p2 - p1;
+    if (dot(dif, nrm) > margin + rb2) return 0;
+  }
+  M3 m1 = ld9(gm, 9 * g1), m2 = ld9(gm, 9 * g2);
+  const double* s1 = m.geom_size + 3 * g1;
+  const double* s2 = m.geom_size + 3 * g2;
+  if (t1 == GEOM_PLANE && t2 == GEOM_SPHERE) return raw_plane_sphere(pc[0], margin, p1, m1, p2, s2[0]);
+  if (t1 == GEOM_PLANE && t2 == GEOM_CAPSULE) return collide_plane_capsule(pc, margin, p1, m1, p2, m2, s2);
+  if (t1 == GEOM_SPHERE && t2 == GEOM_SPHERE) return raw_sphere_sphere(pc[0], margin, p1, m1, s1[0], p2, m2, s2[0]);
+  if (t1 == GEOM_SPHERE && t2 == GEOM_CAPSULE) return collide_sphere_capsule(pc, margin, p1, m1, s1, p2, m2, s2);
+  if (t1 == GEOM_CAPSULE && t2 == GEOM_CAPSULE) return collide_capsule_capsule(pc, margin, p1, m1, s1, p2, m2, s2);
+  return 0;
+}
+
+// walk the static candidate table cooperatively in two passes: (1) every lane counts the
+// pre-contacts of its candidates, (2) after a serial scan that assigns contact slots IN TABLE ORDER
+// (the reference's emission order) the few hitting pairs are evaluated again and written in place.
 MJB_HD void collision(const Env& d) {
   const DModel& m = d.m;
   FI ncon_f = d.ncon();
@@ -125,48 +156,11 @@ MJB_HD void collision(const Env& d) {
     MJB_PSYNC();
     return;
   }
-  FD gx = d.geom_xpos(), gm = d.geom_xmat();
-  FD sp = d.scr_pair();          // per pair: 2 slots x (dist, pos3, normal3, tangent3) padded to 12 doubles
-  FI cnt = d.scr_ipair();        // per pair: number of pre-contacts, then exclusive offsets
+  FI cnt = d.scr_ipair();        // per pair: number of pre-contacts, then packed (offset | n << 24)
   const int npair = m.sz.npair, nconmax = m.sz.nconmax;
   MJB_PFOR(p, npair) {
-    const int g1 = m.pair_geom1[p], g2 = m.pair_geom2[p];
-    const int t1 = m.geom_type[g1], t2 = m.geom_type[g2];
-    const double margin = m.pair_margin[p];
-    const double rb1 = m.geom_rbound[g1], rb2 = m.geom_rbound[g2];
-    V3 p1 = ld3(gx, 3 * g1), p2 = ld3(gx, 3 * g2);
-    int n = 0;
-    bool pass = true;
-    // per-pair filter (mj_filterSphere)
-    if (rb1 > 0 && rb2 > 0) {
-      V3 dif = p1 - p2;
-      double dsq = dif.x * dif.x + dif.y * dif.y + dif.z * dif.z;
-      double bound = rb1 + rb2 + margin;
-      if (dsq > bound * bound) pass = false;
-    } else if (t1 == GEOM_PLANE && rb2 > 0) {
-      V3 nrm{gm[9 * g1 + 2], gm[9 * g1 + 5], gm[9 * g1 + 8]};
-      V3 dif = p2 - p1;
-      if (dot(dif, nrm) > margin + rb2) pass = false;
-    }
-    if (pass) {
-      M3 m1 = ld9(gm, 9 * g1), m2 = ld9(gm, 9 * g2);
-      const double* s1 = m.geom_size + 3 * g1;
-      const double* s2 = m.geom_size + 3 * g2;
-      PreCon pc[2];
-      if (t1 == GEOM_PLANE && t2 == GEOM_SPHERE) n = raw_plane_sphere(pc[0], margin, p1, m1, p2, s2[0]);
-      else if (t1 == GEOM_PLANE && t2 == GEOM_CAPSULE) n = collide_plane_capsule(pc, margin, p1, m1, p2, m2, s2);
-      else if (t1 == GEOM_SPHERE && t2 == GEOM_SPHERE) n = raw_sphere_sphere(pc[0], margin, p1, m1, s1[0], p2, m2, s2[0]);
-      else if (t1 == GEOM_SPHERE && t2 == GEOM_CAPSULE) n = collide_sphere_capsule(pc, margin, p1, m1, s1, p2, m2, s2);
-      else if (t1 == GEOM_CAPSULE && t2 == GEOM_CAPSULE) n = collide_capsule_capsule(pc, margin, p1, m1, s1, p2, m2, s2);
-      for (int k = 0; k < n; k++) {
-        FD o = sp + (24 * p + 12 * k);   // slot k: [0]=dist [1..3]=pos [4..6]=normal [7..9]=tangent
-        o[0] = pc[k].dist;
-        o[1] = pc[k].pos.x; o[2] = pc[k].pos.y; o[3] = pc[k].pos.z;
-        o[4] = pc[k].normal.x; o[5] = pc[k].normal.y; o[6] = pc[k].normal.z;
-        o[7] = pc[k].tangent.x; o[8] = pc[k].tangent.y; o[9] = pc[k].tangent.z;
-      }
-    }
-    cnt[p] = n;
+    PreCon pc[2];
+    cnt[p] = pair_collide(d, p, pc);
   }
   MJB_PSYNC();
   MJB_LANE0 {   // exclusive scan in table order, capped at nconmax
@@ -188,15 +182,17 @@ MJB_HD void collision(const Env& d) {
   FI cpair = d.con_pair();
   MJB_PFOR(p, npair) {
     const int off = cnt[p] & 0xFFFFFF, n = cnt[p] >> 24;
+    if (!n) continue;
+    PreCon pc[2];
+    pair_collide(d, p, pc);
     for (int k = 0; k < n; k++) {
       const int c = off + k;
-      FD o = sp + (24 * p + 12 * k);
-      const double dist = o[0];
+      const double dist = pc[k].dist;
       cdist[c] = dist;
-      cpos[3 * c] = o[1]; cpos[3 * c + 1] = o[2]; cpos[3 * c + 2] = o[3];
+      st3(cpos, 3 * c, pc[k].pos);
       M3 fr;
-      fr.m[0] = o[4]; fr.m[1] = o[5]; fr.m[2] = o[6];
-      fr.m[3] = o[7]; fr.m[4] = o[8]; fr.m[5] = o[9];
+      fr.m[0] = pc[k].normal.x; fr.m[1] = pc[k].normal.y; fr.m[2] = pc[k].normal.z;
+      fr.m[3] = pc[k].tangent.x; fr.m[4] = pc[k].tangent.y; fr.m[5] = pc[k].tangent.z;
       fr.m[6] = 0; fr.m[7] = 0; fr.m[8] = 0;
       make_frame(fr);
       st9(cframe, 9 * c, fr);

@@ -311,12 +311,13 @@ MJB_HD void project_constraint(const Env& d) {
   const DModel& m = d.m;
   const int nefc = d.nefc()[0], nv = m.sz.nv;
   if (!nefc || m.opt.solver != SOL_PGS) return;
-  FD J = d.efc_J(), Y = d.efc_Y(), AR = d.efc_AR(), qLD = d.qLD(), R = d.efc_R();
+  FD J = d.efc_J(), Y = d.efc_Y(), AR = d.efc_AR(), ARt = d.efc_ARt(), qLD = d.qLD(), R = d.efc_R();
   FD sq = d.scr_nv();
   MJB_PFOR(i, nv) sq[i] = 1 / sqrt(qLD[m.M_rowadr[i] + m.M_rownnz[i] - 1]);
   MJB_PSYNC();
-  MJB_PFOR(r, nefc) {   // one lane per row: serial half back-substitution (mj_solveM2)
-    FD x = Y + (long)r * nv, src = J + (long)r * nv;
+  MJB_PFOR(r, nefc) {   // one lane per row: serial half back-substitution (mj_solveM2) in a
+    double x[kMaxDenseNv];   // lane-private array (the dependent read-modify-write chain never leaves the SM)
+    FD src = J + (long)r * nv, dst = Y + (long)r * nv;
     for (int c = 0; c < nv; c++) x[c] = src[c];
     for (int i = nv - 1; i > 0; i--) {
       if (m.dof_simplenum[i]) continue;
@@ -326,7 +327,7 @@ MJB_HD void project_constraint(const Env& d) {
         for (int adr = start; adr < end; adr++) x[m.M_colind[adr]] -= qLD[adr] * xi;
       }
     }
-    for (int i = 0; i < nv; i++) x[i] *= sq[i];
+    for (int i = 0; i < nv; i++) dst[i] = x[i] * sq[i];
   }
   MJB_PSYNC();
   // AR[i][c] = sum_j Y[c][j] * Y[i][j], j ascending, skipping Y[i][j] == 0 (mju_sqrMatTD); one lane
@@ -344,11 +345,15 @@ MJB_HD void project_constraint(const Env& d) {
       if (v != 0) s += yc[j] * v;
     }
     if (i == c) s += R[i];
-    AR[(long)i * nefc + c] = s;
+    ARt[t] = s;
+    AR[(long)i * nefc + c] = s;   // full square copy for the mjData field (global memory)
     AR[(long)c * nefc + i] = s;
   }
   MJB_PSYNC();
 }
+
+// element (i, c) of the symmetric AR from its packed lower triangle
+MJB_HD double ar_at(FD ARt, int i, int c) { return (c <= i) ? ARt[(long)i * (i + 1) / 2 + c] : ARt[(long)c * (c + 1) / 2 + i]; }
 
 // ---- efc_vel, efc_aref ---------------------------------------------------------------------------
 MJB_HD void reference_constraint(const Env& d) {
@@ -445,10 +450,9 @@ MJB_HD void constraint_begin(const Env& d) {
     MJB_PSYNC();
     double cost_ws = constraint_update(d, jar, m.opt.solver != SOL_PGS);
     if (m.opt.solver == SOL_PGS) {
-      FD AR = d.efc_AR(), ARf = d.scr_efc() + nefc;
+      FD ARt = d.efc_ARt(), ARf = d.scr_efc() + nefc;
       MJB_PFOR(r, nefc) {
-        FD row = AR + (long)r * nefc;
-        ARf[r] = dot_ref(nefc, [&](int c) { return row[c]; }, [&](int c) { return force[c]; });
+        ARf[r] = dot_ref(nefc, [&](int c) { return ar_at(ARt, r, c); }, [&](int c) { return force[c]; });
       }
       MJB_PSYNC();
       // two serial dots of length nefc, evaluated identically by every lane (uniform decision)
@@ -486,12 +490,12 @@ MJB_HD void solve_pgs(const Env& d) {
   const DModel& m = d.m;
   const int nefc = d.nefc()[0], nf = d.nf()[0], nv = m.sz.nv;
   if (!nefc) return;
-  FD force = d.efc_force(), floss = d.efc_frictionloss(), AR = d.efc_AR(), b = d.efc_b();
+  FD force = d.efc_force(), floss = d.efc_frictionloss(), ARt = d.efc_ARt(), b = d.efc_b();
   FD ARinv = d.scr_efc(), fprev = d.scr_efc() + nefc, fmom = d.scr_efc() + 2 * (long)nefc;
   FD shared = d.scr_efc() + 3 * (long)nefc;   // [0] improvement of the sweep (lane 0 -> all)
   FI order = d.scr_int() + nefc;
   const double scale = 1 / (m.opt.meaninertia * (nv > 1 ? nv : 1));
-  MJB_PFOR(i, nefc) { fprev[i] = force[i]; ARinv[i] = 1 / AR[(long)i * (nefc + 1)]; order[i] = i; }
+  MJB_PFOR(i, nefc) { fprev[i] = force[i]; ARinv[i] = 1 / ARt[(long)i * (i + 1) / 2 + i]; order[i] = i; }
   MJB_PSYNC();
   dual_state(d);
   Pcg32 rng{0, 1};
@@ -523,8 +527,7 @@ MJB_HD void solve_pgs(const Env& d) {
       }
       for (int bi = 0; bi < nefc; bi++) {
         const int i = order[bi];
-        FD row = AR + (long)i * nefc;
-        const double res = b[i] + dot_ref(nefc, [&](int c) { return row[c]; }, [&](int c) { return force[c]; });
+        const double res = b[i] + dot_ref(nefc, [&](int c) { return ar_at(ARt, i, c); }, [&](int c) { return force[c]; });
         const double old = force[i];
         double f = old - res * ARinv[i];
         if (i < nf) {

@@ -139,9 +139,10 @@ struct DModel {
   X(efc_frictionloss, S.njmax) X(efc_diagA, S.njmax) X(efc_KBIP, 4 * S.njmax)                \
   X(efc_D, S.njmax) X(efc_R, S.njmax) X(efc_vel, S.njmax) X(efc_aref, S.njmax)               \
   X(efc_b, S.njmax) X(efc_force, S.njmax)                                                    \
-  X(scr_body, 12 * S.nbody) X(scr_nv, 8 * S.nv) X(scr_efc, 6 * S.njmax)                      \
-  X(scr_pair, 24 * S.npair)
+  X(efc_ARt, S.njmax * (S.njmax + 1) / 2)                                                      \
+  X(scr_body, 12 * S.nbody) X(scr_nv, 8 * S.nv) X(scr_efc, 6 * S.njmax)
 
+// (efc_ARt: packed lower triangle of the symmetric AR, the copy the PGS sweep reads)
 // COLD doubles: stay in global memory / L2 in every mapping
 #define MJB_DATA_COLD_FIELDS(X, S)                                                           \
   X(efc_J, S.njmax * S.nv) X(efc_Y, S.njmax * S.nv) X(efc_AR, S.njmax * S.njmax)
