@@ -122,15 +122,10 @@ mjbBatch* mjb_make_batch(const struct mjModel_* m, int nenv, int nconmax, int nj
   b.stride = ((size_t)nenv + 31) / 32 * 32;
   b.L = make_layout(H.sz);
   b.warp_per_env = g_warp_per_env;
-  if (b.warp_per_env) {
-    b.dpitch = ((size_t)b.L.ndbl + 15) / 16 * 16; b.dstep = 1;
-    b.ipitch = ((size_t)b.L.nint + 31) / 32 * 32; b.istep = 1;
-  } else {
-    b.dpitch = 1; b.dstep = b.stride;
-    b.ipitch = 1; b.istep = b.stride;
-  }
-  size_t nd = b.warp_per_env ? b.dpitch * b.stride : (size_t)b.L.ndbl * b.stride;
-  size_t ni = b.warp_per_env ? b.ipitch * b.stride : (size_t)b.L.nint * b.stride;
+  b.dpitch = ((size_t)b.L.ndbl + 15) / 16 * 16;   // env-major blocks, 128-byte aligned
+  b.ipitch = ((size_t)b.L.nint + 31) / 32 * 32;
+  size_t nd = b.dpitch * b.stride;
+  size_t ni = b.ipitch * b.stride;
   b.dbl = (double*)backend::dev_alloc(nd * sizeof(double));
   b.itg = (int*)backend::dev_alloc(ni * sizeof(int));
   if (!b.dbl || !b.itg) { set_error("device allocation failed (batch)"); mjb_free_batch(B); return nullptr; }

@@ -306,6 +306,10 @@ MJB_HD void mul_jacT_vec(const Env& d, FD res, FD vec) {
   MJB_PSYNC();
 }
 
+// the on-chip AR copy (efc_ARt, capacity njmax*(njmax+1)/2) is a full nefc x nefc square whenever it
+// fits (direct row access for the PGS sweep) and a packed lower triangle otherwise
+MJB_HD bool ar_square(const DModel& m, int nefc) { return nefc * nefc <= m.sz.njmax * (m.sz.njmax + 1) / 2; }
+
 // ---- dual projection: Y = J L^-T D^-1/2, AR = Y Y' + diag(R) (dense) ---------------------------
 MJB_HD void project_constraint(const Env& d) {
   const DModel& m = d.m;
@@ -345,15 +349,39 @@ MJB_HD void project_constraint(const Env& d) {
       if (v != 0) s += yc[j] * v;
     }
     if (i == c) s += R[i];
-    ARt[t] = s;
+    if (ar_square(m, nefc)) { ARt[i * nefc + c] = s; ARt[c * nefc + i] = s; }
+    else ARt[t] = s;
     AR[(long)i * nefc + c] = s;   // full square copy for the mjData field (global memory)
     AR[(long)c * nefc + i] = s;
   }
   MJB_PSYNC();
 }
 
-// element (i, c) of the symmetric AR from its packed lower triangle
-MJB_HD double ar_at(FD ARt, int i, int c) { return (c <= i) ? ARt[(long)i * (i + 1) / 2 + c] : ARt[(long)c * (c + 1) / 2 + i]; }
+// element (i, c) of the symmetric AR from its packed lower triangle (large-nefc fallback layout)
+MJB_HD double ar_at(FD ARt, int i, int c) { return (c <= i) ? ARt[i * (i + 1) / 2 + c] : ARt[c * (c + 1) / 2 + i]; }
+
+// row i of AR dotted with f in mju_dot's accumulation order, from the on-chip copy
+MJB_HD double ar_row_dot(const DModel& m, FD ARt, int nefc, int i, FD f) {
+  if (ar_square(m, nefc)) {
+    const double* row = ARt.p + i * nefc;
+    const double* fv = f.p;
+    double r0 = 0, r1 = 0, r2 = 0, r3 = 0;
+    int c = 0;
+    for (; c <= nefc - 4; c += 4) {
+      r0 += row[c] * fv[c];
+      r1 += row[c + 1] * fv[c + 1];
+      r2 += row[c + 2] * fv[c + 2];
+      r3 += row[c + 3] * fv[c + 3];
+    }
+    double res = (r0 + r2) + (r1 + r3);
+    const int t = nefc - c;
+    if (t == 3) res += row[c] * fv[c] + row[c + 1] * fv[c + 1] + row[c + 2] * fv[c + 2];
+    else if (t == 2) res += row[c] * fv[c] + row[c + 1] * fv[c + 1];
+    else if (t == 1) res += row[c] * fv[c];
+    return res;
+  }
+  return dot_ref(nefc, [&](int c) { return ar_at(ARt, i, c); }, [&](int c) { return f[c]; });
+}
 
 // ---- efc_vel, efc_aref ---------------------------------------------------------------------------
 MJB_HD void reference_constraint(const Env& d) {
@@ -452,7 +480,7 @@ MJB_HD void constraint_begin(const Env& d) {
     if (m.opt.solver == SOL_PGS) {
       FD ARt = d.efc_ARt(), ARf = d.scr_efc() + nefc;
       MJB_PFOR(r, nefc) {
-        ARf[r] = dot_ref(nefc, [&](int c) { return ar_at(ARt, r, c); }, [&](int c) { return force[c]; });
+        ARf[r] = ar_row_dot(m, ARt, nefc, r, force);
       }
       MJB_PSYNC();
       // two serial dots of length nefc, evaluated identically by every lane (uniform decision)
@@ -495,7 +523,7 @@ MJB_HD void solve_pgs(const Env& d) {
   FD shared = d.scr_efc() + 3 * (long)nefc;   // [0] improvement of the sweep (lane 0 -> all)
   FI order = d.scr_int() + nefc;
   const double scale = 1 / (m.opt.meaninertia * (nv > 1 ? nv : 1));
-  MJB_PFOR(i, nefc) { fprev[i] = force[i]; ARinv[i] = 1 / ARt[(long)i * (i + 1) / 2 + i]; order[i] = i; }
+  MJB_PFOR(i, nefc) { fprev[i] = force[i]; ARinv[i] = 1 / (ar_square(m, nefc) ? ARt[i * nefc + i] : ARt[i * (i + 1) / 2 + i]); order[i] = i; }
   MJB_PSYNC();
   dual_state(d);
   Pcg32 rng{0, 1};
@@ -527,7 +555,7 @@ MJB_HD void solve_pgs(const Env& d) {
       }
       for (int bi = 0; bi < nefc; bi++) {
         const int i = order[bi];
-        const double res = b[i] + dot_ref(nefc, [&](int c) { return ar_at(ARt, i, c); }, [&](int c) { return force[c]; });
+        const double res = b[i] + ar_row_dot(m, ARt, nefc, i, force);
         const double old = force[i];
         double f = old - res * ARinv[i];
         if (i < nf) {

@@ -84,19 +84,19 @@ MJB_HD void run_get_state_native(const DModel& m, const Batch& b, int e, double*
 MJB_HD void run_pack(const Batch& b, int is_int, long off, long cnt, void* dense, int to_dense, long idx) {
   const long e = idx / cnt, i = idx - e * cnt;
   if (is_int) {
-    int* f = b.itg + (size_t)e * b.ipitch + (size_t)(off + i) * b.istep;
+    int* f = b.itg + (size_t)e * b.ipitch + (size_t)(off + i);
     int* dn = (int*)dense + idx;
     if (to_dense) *dn = *f; else *f = *dn;
   } else {
-    double* f = b.dbl + (size_t)e * b.dpitch + (size_t)(off + i) * b.dstep;
+    double* f = b.dbl + (size_t)e * b.dpitch + (size_t)(off + i);
     double* dn = (double*)dense + idx;
     if (to_dense) *dn = *f; else *f = *dn;
   }
 }
 MJB_HD void run_fill_zero(const Batch& b, int is_int, long off, long cnt, long idx) {
   const long e = idx / cnt, i = idx - e * cnt;
-  if (is_int) b.itg[(size_t)e * b.ipitch + (size_t)(off + i) * b.istep] = 0;
-  else b.dbl[(size_t)e * b.dpitch + (size_t)(off + i) * b.dstep] = 0;
+  if (is_int) b.itg[(size_t)e * b.ipitch + (size_t)(off + i)] = 0;
+  else b.dbl[(size_t)e * b.dpitch + (size_t)(off + i)] = 0;
 }
 
 }  // namespace mjb

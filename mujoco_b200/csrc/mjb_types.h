@@ -181,25 +181,24 @@ inline Layout make_layout(const Sizes& S) {
   return L;
 }
 
-// strided view of one field of one environment
+// view of one field of one environment (unit stride: storage is env-major in every mapping)
 template <class T>
 struct Fld {
   T* p;
-  size_t s;
-  MJB_HD T& operator[](long i) const { return p[(size_t)i * s]; }
-  MJB_HD Fld operator+(long k) const { return Fld{p + (size_t)k * s, s}; }
+  MJB_HD T& operator[](long i) const { return p[i]; }
+  MJB_HD Fld operator+(long k) const { return Fld{p + k}; }
 };
 using FD = Fld<double>;
 using FI = Fld<int>;
 
-// batch storage handle (device or host pointers)
+// batch storage handle (device or host pointers): env e owns dbl[e*dpitch ...] and itg[e*ipitch ...]
 struct Batch {
   double* dbl;
   int* itg;
-  size_t stride;   // padded number of environments
-  size_t dpitch, dstep, ipitch, istep;
+  size_t stride;   // padded number of environments (native ctrl/state buffers of the rollout)
+  size_t dpitch, ipitch;
   int nenv;
-  int warp_per_env;   // 0: one environment per lane, 1: one environment per warp
+  int warp_per_env;   // 0: one environment per lane (validation mapping), 1: one environment per warp
   Layout L;
 };
 
@@ -209,27 +208,24 @@ struct Env {
   const Batch& b;
   int e;
   int lane, nlane;   // cooperative lanes working on this environment (1 lane in lane-per-env mode)
-  double* hd; size_t hstep;   // hot doubles
-  double* cd; size_t cstep;   // cold doubles (same offsets, global memory)
-  int* hi; size_t istep;      // ints
+  double* hd;        // hot doubles
+  double* cd;        // cold doubles (same offsets, global memory)
+  int* hi;           // ints
   MJB_HD Env(const DModel& m_, const Batch& b_, int e_, int lane_ = 0, int nlane_ = 1)
       : m(m_), b(b_), e(e_), lane(lane_), nlane(nlane_) {
-    hd = b.dbl + (size_t)e * b.dpitch; hstep = b.dstep;
-    cd = hd; cstep = b.dstep;
-    hi = b.itg + (size_t)e * b.ipitch; istep = b.istep;
+    hd = b.dbl + (size_t)e * b.dpitch;
+    cd = hd;
+    hi = b.itg + (size_t)e * b.ipitch;
   }
-  MJB_HD Env(const Env& o, int lane_, int nlane_)
-      : m(o.m), b(o.b), e(o.e), lane(lane_), nlane(nlane_), hd(o.hd), hstep(o.hstep), cd(o.cd), cstep(o.cstep),
-        hi(o.hi), istep(o.istep) {}
-  // redirect the hot block (doubles and ints) to a staged copy with unit stride
-  MJB_HD void stage(double* hot, int* ints) { hd = hot; hstep = 1; hi = ints; istep = 1; }
-#define X(name, cnt) MJB_HD FD name() const { return FD{hd + (size_t)b.L.name * hstep, hstep}; }
+  // redirect the hot block (doubles and ints) to a staged copy
+  MJB_HD void stage(double* hot, int* ints) { hd = hot; hi = ints; }
+#define X(name, cnt) MJB_HD FD name() const { return FD{hd + b.L.name}; }
   MJB_DATA_DBL_FIELDS(X, _)
 #undef X
-#define X(name, cnt) MJB_HD FD name() const { return FD{cd + (size_t)b.L.name * cstep, cstep}; }
+#define X(name, cnt) MJB_HD FD name() const { return FD{cd + b.L.name}; }
   MJB_DATA_COLD_FIELDS(X, _)
 #undef X
-#define X(name, cnt) MJB_HD FI name() const { return FI{hi + (size_t)b.L.name * istep, istep}; }
+#define X(name, cnt) MJB_HD FI name() const { return FI{hi + b.L.name}; }
   MJB_DATA_INT_FIELDS(X, _)
 #undef X
   // barrier + memory ordering between the lanes that share this environment

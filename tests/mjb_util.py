@@ -22,7 +22,7 @@ def hostemu_lib():
     return _hostemu
 
 
-def make_pair(path, solver, library=None, nenv=4, nconmax=64, njmax=200, warp_per_env=True, **opts):
+def make_pair(path, solver, library=None, nenv=4, nconmax=48, njmax=128, warp_per_env=True, **opts):
     """(product/hostemu model+batch, oracle) with identical option overrides"""
     m = mb.Model(path, library=library)
     o = Oracle(path)
