@@ -510,20 +510,32 @@ MJB_HD void constraint_begin(const Env& d) {
 }
 
 // ---- projected Gauss-Seidel on the dual ------------------------------------------------------------
-// The sweep is inherently serial (row i needs every earlier update of the same sweep) and short
-// for this workload (median nefc 9): lane 0 runs it with the reference's exact arithmetic
-// (mju_dot order, PCG32 Fisher-Yates visit order, Nesterov extrapolation and restart); the
-// per-iteration vector updates are spread over the lanes.
+// The sweep is a Gauss-Seidel recurrence: row i needs every earlier update of the same sweep, so
+// rows are visited one after the other (PCG32 Fisher-Yates order of the reference).  Inside a row
+// the residual dot product keeps mju_dot's exact accumulation structure — four independent
+// stride-4 partial sums combined as (r0+r2)+(r1+r3), then the grouped tail — and those four
+// chains run on four lanes; lane 0 combines them, applies the projected update and the cost-change
+// guard.  Vector updates between sweeps (Nesterov extrapolation, projection, dual state) are
+// spread over all lanes.  Results are bit-identical to the serial reference arithmetic.
 MJB_HD void solve_pgs(const Env& d) {
   const DModel& m = d.m;
-  const int nefc = d.nefc()[0], nf = d.nf()[0], nv = m.sz.nv;
+  const int nefc = d.nefc()[0], nf = d.nf()[0], nv = m.sz.nv, njmax = m.sz.njmax;
   if (!nefc) return;
   FD force = d.efc_force(), floss = d.efc_frictionloss(), ARt = d.efc_ARt(), b = d.efc_b();
-  FD ARinv = d.scr_efc(), fprev = d.scr_efc() + nefc, fmom = d.scr_efc() + 2 * (long)nefc;
-  FD shared = d.scr_efc() + 3 * (long)nefc;   // [0] improvement of the sweep (lane 0 -> all)
-  FI order = d.scr_int() + nefc;
+  FD ARinv = d.scr_efc(), fprev = d.scr_efc() + njmax, fmom = d.scr_efc() + 2 * (long)njmax;
+  FD Adiag = d.scr_efc() + 3 * (long)njmax;    // 1 / ARinv (the reference's Athis[0])
+  FD shared = d.scr_efc() + 4 * (long)njmax;   // [0] improvement of the sweep, [1..4] partial sums
+  FI order = d.scr_int() + njmax;
+  const bool square = ar_square(m, nefc);
+  const int n4 = nefc & ~3, tail = nefc - n4;
   const double scale = 1 / (m.opt.meaninertia * (nv > 1 ? nv : 1));
-  MJB_PFOR(i, nefc) { fprev[i] = force[i]; ARinv[i] = 1 / (ar_square(m, nefc) ? ARt[i * nefc + i] : ARt[i * (i + 1) / 2 + i]); order[i] = i; }
+  MJB_PFOR(i, nefc) {
+    fprev[i] = force[i];
+    const double ai = 1 / (square ? ARt[i * nefc + i] : ARt[i * (i + 1) / 2 + i]);
+    ARinv[i] = ai;
+    Adiag[i] = 1 / ai;
+    order[i] = i;
+  }
   MJB_PSYNC();
   dual_state(d);
   Pcg32 rng{0, 1};
@@ -548,29 +560,50 @@ MJB_HD void solve_pgs(const Env& d) {
     }
     MJB_PSYNC();
     MJB_LANE0 {
-      double improvement = 0;
       for (int i = nefc - 1; i > 0; i--) {   // Fisher-Yates, same draws as the reference
         const uint32_t j = pcg32_next(rng) % (uint32_t)(i + 1);
         const int t = order[i]; order[i] = order[j]; order[j] = t;
       }
-      for (int bi = 0; bi < nefc; bi++) {
-        const int i = order[bi];
-        const double res = b[i] + ar_row_dot(m, ARt, nefc, i, force);
+    }
+    MJB_PSYNC();
+    double impr = 0;   // meaningful on lane 0
+    for (int bi = 0; bi < nefc; bi++) {
+      const int i = order[bi];
+      // four stride-4 partial sums of AR[i,:] . force, one per lane (all four on lane 0 when alone)
+      for (int k = d.lane; k < 4; k += d.nlane) {
+        double r = 0;
+        if (square) {
+          const double* row = ARt.p + i * nefc;
+          const double* fv = force.p;
+          for (int c = k; c < n4; c += 4) r += row[c] * fv[c];
+        } else {
+          for (int c = k; c < n4; c += 4) r += ar_at(ARt, i, c) * force[c];
+        }
+        shared[1 + k] = r;
+      }
+      MJB_PSYNC();
+      MJB_LANE0 {
+        double res = (shared[1] + shared[3]) + (shared[2] + shared[4]);
+        auto a_ic = [&](int c) { return square ? ARt[i * nefc + c] : ar_at(ARt, i, c); };
+        if (tail == 3) res += a_ic(n4) * force[n4] + a_ic(n4 + 1) * force[n4 + 1] + a_ic(n4 + 2) * force[n4 + 2];
+        else if (tail == 2) res += a_ic(n4) * force[n4] + a_ic(n4 + 1) * force[n4 + 1];
+        else if (tail == 1) res += a_ic(n4) * force[n4];
+        res = b[i] + res;
         const double old = force[i];
         double f = old - res * ARinv[i];
         if (i < nf) {
           if (f < -floss[i]) f = -floss[i];
           else if (f > floss[i]) f = floss[i];
         } else if (f < 0) f = 0;
-        const double A = 1 / ARinv[i];
         const double delta = f - old;
-        double change = 0.5 * delta * delta * A + delta * res;
+        double change = 0.5 * delta * delta * Adiag[i] + delta * res;
         if (change > 1e-10) { f = old; change = 0; }
         force[i] = f;
-        improvement -= change;
+        impr -= change;
       }
-      shared[0] = improvement * scale;
+      MJB_PSYNC();
     }
+    MJB_LANE0 shared[0] = impr * scale;
     MJB_PSYNC();
     const double improvement = shared[0];
     dual_state(d);

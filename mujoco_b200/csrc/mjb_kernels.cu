@@ -23,7 +23,7 @@ namespace mjb {
 __global__ void __launch_bounds__(32) k_step_lane(DModel m, Batch b, int mask, int flags) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= b.nenv) return;
-  run_env(m, b, e, mask, flags, 0, 1, nullptr, nullptr);
+  run_env<false>(m, b, e, mask, flags, 0, 1, nullptr, nullptr);
 }
 
 // FUSED STEP KERNEL: one warp (= one CTA) per environment, env-major storage.  The hot block of the
@@ -37,7 +37,7 @@ __global__ void __launch_bounds__(32) k_step_warp(DModel m, Batch b, int mask, i
   if (e >= b.nenv) return;
   double* shot = mjb_smem;
   int* sint = (int*)(mjb_smem + b.L.nhot);
-  run_env(m, b, e, mask, flags, threadIdx.x, 32, shot, sint);
+  run_env<true>(m, b, e, mask, flags, threadIdx.x, 32, shot, sint);
 }
 
 __global__ void k_pack(Batch b, int is_int, long off, long cnt, void* dense, int to_dense) {

@@ -17,27 +17,38 @@ constexpr int kMaskStep = 0xF, kMaskForward = 0x17;
 // run the selected stages of one environment with its cooperative lanes.
 // flags: bit0 = part of mj_step (qpos/qvel checks), bit1 = skip environments that raised a warning.
 // shot/sint: optional staging area (shared memory) for the hot block; only with env-major storage.
-MJB_HD void run_env(const DModel& m, const Batch& b, int e, int mask, int flags, int lane, int nlane,
-                    double* shot, int* sint) {
-  Env d(m, b, e, lane, nlane);
-  if ((flags & 2) && env_has_warning(d)) return;   // rollout: a warned env stops stepping (uniform per env)
-  double* g = b.dbl + (size_t)e * b.dpitch;
-  int* gi = b.itg + (size_t)e * b.ipitch;
-  if (shot) {
-    for (long i = lane; i < b.L.nhot; i += nlane) shot[i] = g[i];
-    for (long i = lane; i < b.L.nint; i += nlane) sint[i] = gi[i];
-    d.sync();
-    d.stage(shot, sint);
-  }
+MJB_HD void run_stage_mask(const Env& d, int mask, int flags) {
   if (mask & 1) stage_position(d, (flags & 1) != 0);
   if (mask & 2) stage_velocity(d);
   if (mask & 4) stage_solve(d);
   if (mask & 8) stage_integrate(d);
   if (mask & 16) stage_finish_forward(d);
-  if (shot) {
+}
+
+// STAGED = true: the hot block is copied to shot/sint (shared memory in the fused kernel), every
+// stage runs on the copy, and it is written back once.  The staged Env is built directly from the
+// staging pointers so that the compiler can keep them in the shared address space.
+template <bool STAGED>
+MJB_HD void run_env(const DModel& m, const Batch& b, int e, int mask, int flags, int lane, int nlane,
+                    double* shot, int* sint) {
+  double* g = b.dbl + (size_t)e * b.dpitch;
+  int* gi = b.itg + (size_t)e * b.ipitch;
+  if (flags & 2) {   // rollout: a warned env stops stepping (uniform per env)
+    const int* w = gi + b.L.warning;
+    for (int i = 0; i < NWARNING; i++) if (w[i]) return;
+  }
+  if (STAGED) {
+    for (long i = lane; i < b.L.nhot; i += nlane) shot[i] = g[i];
+    for (long i = lane; i < b.L.nint; i += nlane) sint[i] = gi[i];
+    Env d(m, b, e, lane, nlane, shot, sint);
+    d.sync();
+    run_stage_mask(d, mask, flags);
     d.sync();
     for (long i = lane; i < b.L.nhot; i += nlane) g[i] = shot[i];
     for (long i = lane; i < b.L.nint; i += nlane) gi[i] = sint[i];
+  } else {
+    Env d(m, b, e, lane, nlane);
+    run_stage_mask(d, mask, flags);
   }
 }
 

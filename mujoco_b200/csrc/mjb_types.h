@@ -217,8 +217,13 @@ struct Env {
     cd = hd;
     hi = b.itg + (size_t)e * b.ipitch;
   }
-  // redirect the hot block (doubles and ints) to a staged copy
-  MJB_HD void stage(double* hot, int* ints) { hd = hot; hi = ints; }
+  // hot block (doubles and ints) in a staged copy (shared memory in the fused kernel)
+  MJB_HD Env(const DModel& m_, const Batch& b_, int e_, int lane_, int nlane_, double* hot, int* ints)
+      : m(m_), b(b_), e(e_), lane(lane_), nlane(nlane_) {
+    hd = hot;
+    cd = b.dbl + (size_t)e * b.dpitch;
+    hi = ints;
+  }
 #define X(name, cnt) MJB_HD FD name() const { return FD{hd + b.L.name}; }
   MJB_DATA_DBL_FIELDS(X, _)
 #undef X
