@@ -306,16 +306,12 @@ MJB_HD void mul_jacT_vec(const Env& d, FD res, FD vec) {
   MJB_PSYNC();
 }
 
-// the on-chip AR copy (efc_ARt, capacity njmax*(njmax+1)/2) is a full nefc x nefc square whenever it
-// fits (direct row access for the PGS sweep) and a packed lower triangle otherwise
-MJB_HD bool ar_square(const DModel& m, int nefc) { return nefc * nefc <= m.sz.njmax * (m.sz.njmax + 1) / 2; }
-
 // ---- dual projection: Y = J L^-T D^-1/2, AR = Y Y' + diag(R) (dense) ---------------------------
 MJB_HD void project_constraint(const Env& d) {
   const DModel& m = d.m;
   const int nefc = d.nefc()[0], nv = m.sz.nv;
   if (!nefc || m.opt.solver != SOL_PGS) return;
-  FD J = d.efc_J(), Y = d.efc_Y(), AR = d.efc_AR(), ARt = d.efc_ARt(), qLD = d.qLD(), R = d.efc_R();
+  FD J = d.efc_J(), Y = d.efc_Y(), AR = d.efc_AR(), qLD = d.qLD(), R = d.efc_R();
   FD sq = d.scr_nv();
   MJB_PFOR(i, nv) sq[i] = 1 / sqrt(qLD[m.M_rowadr[i] + m.M_rownnz[i] - 1]);
   MJB_PSYNC();
@@ -349,38 +345,28 @@ MJB_HD void project_constraint(const Env& d) {
       if (v != 0) s += yc[j] * v;
     }
     if (i == c) s += R[i];
-    if (ar_square(m, nefc)) { ARt[i * nefc + c] = s; ARt[c * nefc + i] = s; }
-    else ARt[t] = s;
-    AR[(long)i * nefc + c] = s;   // full square copy for the mjData field (global memory)
+    AR[(long)i * nefc + c] = s;
     AR[(long)c * nefc + i] = s;
   }
   MJB_PSYNC();
 }
 
-// element (i, c) of the symmetric AR from its packed lower triangle (large-nefc fallback layout)
-MJB_HD double ar_at(FD ARt, int i, int c) { return (c <= i) ? ARt[i * (i + 1) / 2 + c] : ARt[c * (c + 1) / 2 + i]; }
-
-// row i of AR dotted with f in mju_dot's accumulation order, from the on-chip copy
-MJB_HD double ar_row_dot(const DModel& m, FD ARt, int nefc, int i, FD f) {
-  if (ar_square(m, nefc)) {
-    const double* row = ARt.p + i * nefc;
-    const double* fv = f.p;
-    double r0 = 0, r1 = 0, r2 = 0, r3 = 0;
-    int c = 0;
-    for (; c <= nefc - 4; c += 4) {
-      r0 += row[c] * fv[c];
-      r1 += row[c + 1] * fv[c + 1];
-      r2 += row[c + 2] * fv[c + 2];
-      r3 += row[c + 3] * fv[c + 3];
-    }
-    double res = (r0 + r2) + (r1 + r3);
-    const int t = nefc - c;
-    if (t == 3) res += row[c] * fv[c] + row[c + 1] * fv[c + 1] + row[c + 2] * fv[c + 2];
-    else if (t == 2) res += row[c] * fv[c] + row[c + 1] * fv[c + 1];
-    else if (t == 1) res += row[c] * fv[c];
-    return res;
+// row . f in mju_dot's accumulation order on raw pointers
+MJB_HD double dot_ptr(const double* a, const double* f, int n) {
+  double r0 = 0, r1 = 0, r2 = 0, r3 = 0;
+  int c = 0;
+  for (; c <= n - 4; c += 4) {
+    r0 += a[c] * f[c];
+    r1 += a[c + 1] * f[c + 1];
+    r2 += a[c + 2] * f[c + 2];
+    r3 += a[c + 3] * f[c + 3];
   }
-  return dot_ref(nefc, [&](int c) { return ar_at(ARt, i, c); }, [&](int c) { return f[c]; });
+  double res = (r0 + r2) + (r1 + r3);
+  const int t = n - c;
+  if (t == 3) res += a[c] * f[c] + a[c + 1] * f[c + 1] + a[c + 2] * f[c + 2];
+  else if (t == 2) res += a[c] * f[c] + a[c + 1] * f[c + 1];
+  else if (t == 1) res += a[c] * f[c];
+  return res;
 }
 
 // ---- efc_vel, efc_aref ---------------------------------------------------------------------------
@@ -478,10 +464,8 @@ MJB_HD void constraint_begin(const Env& d) {
     MJB_PSYNC();
     double cost_ws = constraint_update(d, jar, m.opt.solver != SOL_PGS);
     if (m.opt.solver == SOL_PGS) {
-      FD ARt = d.efc_ARt(), ARf = d.scr_efc() + nefc;
-      MJB_PFOR(r, nefc) {
-        ARf[r] = ar_row_dot(m, ARt, nefc, r, force);
-      }
+      FD AR = d.efc_AR(), ARf = d.scr_efc() + nefc;
+      MJB_PFOR(r, nefc) ARf[r] = dot_ptr(AR.p + (long)r * nefc, force.p, nefc);
       MJB_PSYNC();
       // two serial dots of length nefc, evaluated identically by every lane (uniform decision)
       double pw = dot_ref(nefc, [&](int i) { return force[i]; }, [&](int i) { return b[i]; });
@@ -509,6 +493,19 @@ MJB_HD void constraint_begin(const Env& d) {
   }
 }
 
+// dual state from forces on raw pointers (engine_solver.c dualState, scalar rows)
+MJB_HD void dual_state_ptr(const Env& d, const double* force, const double* floss, int nefc, int nf) {
+  FI state = d.efc_state();
+  MJB_PFOR(i, nefc) {
+    if (i < nf) {
+      if (force[i] <= -floss[i]) state[i] = STATE_LINEARPOS;
+      else if (force[i] >= floss[i]) state[i] = STATE_LINEARNEG;
+      else state[i] = STATE_QUADRATIC;
+    } else state[i] = (force[i] <= 0) ? STATE_SATISFIED : STATE_QUADRATIC;
+  }
+  MJB_PSYNC();
+}
+
 // ---- projected Gauss-Seidel on the dual ------------------------------------------------------------
 // The sweep is a Gauss-Seidel recurrence: row i needs every earlier update of the same sweep, so
 // rows are visited one after the other (PCG32 Fisher-Yates order of the reference).  Inside a row
@@ -516,28 +513,42 @@ MJB_HD void constraint_begin(const Env& d) {
 // stride-4 partial sums combined as (r0+r2)+(r1+r3), then the grouped tail — and those four
 // chains run on four lanes; lane 0 combines them, applies the projected update and the cost-change
 // guard.  Vector updates between sweeps (Nesterov extrapolation, projection, dual state) are
-// spread over all lanes.  Results are bit-identical to the serial reference arithmetic.
+// spread over all lanes.  In the fused kernel AR and the sweep vectors are first copied into the
+// warp's shared-memory scratch (when nefc^2 + 7 nefc + 8 doubles fit), so the serial chain never
+// waits on L2.  Results are bit-identical to the serial reference arithmetic.
 MJB_HD void solve_pgs(const Env& d) {
   const DModel& m = d.m;
   const int nefc = d.nefc()[0], nf = d.nf()[0], nv = m.sz.nv, njmax = m.sz.njmax;
   if (!nefc) return;
-  FD force = d.efc_force(), floss = d.efc_frictionloss(), ARt = d.efc_ARt(), b = d.efc_b();
-  FD ARinv = d.scr_efc(), fprev = d.scr_efc() + njmax, fmom = d.scr_efc() + 2 * (long)njmax;
-  FD Adiag = d.scr_efc() + 3 * (long)njmax;    // 1 / ARinv (the reference's Athis[0])
-  FD shared = d.scr_efc() + 4 * (long)njmax;   // [0] improvement of the sweep, [1..4] partial sums
+  const bool onchip = d.sm && ((long)nefc * nefc + 7L * nefc + 8 <= d.smcap);
+  double* AR; double* force; double* b; double* floss; double* ARinv; double* fprev; double* fmom;
+  double* Adiag; double* shared;
+  if (onchip) {
+    AR = d.sm; force = AR + nefc * nefc; b = force + nefc; floss = b + nefc; ARinv = floss + nefc;
+    fprev = ARinv + nefc; fmom = fprev + nefc; Adiag = fmom + nefc; shared = Adiag + nefc;
+    const double* gAR = d.efc_AR().p; const double* gf = d.efc_force().p; const double* gb = d.efc_b().p;
+    const double* gfl = d.efc_frictionloss().p;
+    MJB_PFOR(i, nefc * nefc) AR[i] = gAR[i];
+    MJB_PFOR(i, nefc) { force[i] = gf[i]; b[i] = gb[i]; floss[i] = gfl[i]; }
+  } else {
+    AR = d.efc_AR().p; force = d.efc_force().p; b = d.efc_b().p; floss = d.efc_frictionloss().p;
+    double* scr = d.scr_efc().p;
+    ARinv = scr; fprev = scr + njmax; fmom = scr + 2 * (long)njmax; Adiag = scr + 3 * (long)njmax;
+    shared = scr + 4 * (long)njmax;
+  }
   FI order = d.scr_int() + njmax;
-  const bool square = ar_square(m, nefc);
+  MJB_PSYNC();
   const int n4 = nefc & ~3, tail = nefc - n4;
   const double scale = 1 / (m.opt.meaninertia * (nv > 1 ? nv : 1));
   MJB_PFOR(i, nefc) {
     fprev[i] = force[i];
-    const double ai = 1 / (square ? ARt[i * nefc + i] : ARt[i * (i + 1) / 2 + i]);
+    const double ai = 1 / AR[(long)i * (nefc + 1)];
     ARinv[i] = ai;
-    Adiag[i] = 1 / ai;
+    Adiag[i] = 1 / ai;    // the reference's Athis[0] = 1/ARinv
     order[i] = i;
   }
   MJB_PSYNC();
-  dual_state(d);
+  dual_state_ptr(d, force, floss, nefc, nf);
   Pcg32 rng{0, 1};
   pcg32_next(rng);
   int iter = 0, nk = 0;
@@ -558,7 +569,6 @@ MJB_HD void solve_pgs(const Env& d) {
     } else {
       MJB_PFOR(i, nefc) { fprev[i] = force[i]; fmom[i] = force[i]; }
     }
-    MJB_PSYNC();
     MJB_LANE0 {
       for (int i = nefc - 1; i > 0; i--) {   // Fisher-Yates, same draws as the reference
         const uint32_t j = pcg32_next(rng) % (uint32_t)(i + 1);
@@ -569,25 +579,19 @@ MJB_HD void solve_pgs(const Env& d) {
     double impr = 0;   // meaningful on lane 0
     for (int bi = 0; bi < nefc; bi++) {
       const int i = order[bi];
+      const double* row = AR + (long)i * nefc;
       // four stride-4 partial sums of AR[i,:] . force, one per lane (all four on lane 0 when alone)
       for (int k = d.lane; k < 4; k += d.nlane) {
         double r = 0;
-        if (square) {
-          const double* row = ARt.p + i * nefc;
-          const double* fv = force.p;
-          for (int c = k; c < n4; c += 4) r += row[c] * fv[c];
-        } else {
-          for (int c = k; c < n4; c += 4) r += ar_at(ARt, i, c) * force[c];
-        }
+        for (int c = k; c < n4; c += 4) r += row[c] * force[c];
         shared[1 + k] = r;
       }
       MJB_PSYNC();
       MJB_LANE0 {
         double res = (shared[1] + shared[3]) + (shared[2] + shared[4]);
-        auto a_ic = [&](int c) { return square ? ARt[i * nefc + c] : ar_at(ARt, i, c); };
-        if (tail == 3) res += a_ic(n4) * force[n4] + a_ic(n4 + 1) * force[n4 + 1] + a_ic(n4 + 2) * force[n4 + 2];
-        else if (tail == 2) res += a_ic(n4) * force[n4] + a_ic(n4 + 1) * force[n4 + 1];
-        else if (tail == 1) res += a_ic(n4) * force[n4];
+        if (tail == 3) res += row[n4] * force[n4] + row[n4 + 1] * force[n4 + 1] + row[n4 + 2] * force[n4 + 2];
+        else if (tail == 2) res += row[n4] * force[n4] + row[n4 + 1] * force[n4 + 1];
+        else if (tail == 1) res += row[n4] * force[n4];
         res = b[i] + res;
         const double old = force[i];
         double f = old - res * ARinv[i];
@@ -606,7 +610,7 @@ MJB_HD void solve_pgs(const Env& d) {
     MJB_LANE0 shared[0] = impr * scale;
     MJB_PSYNC();
     const double improvement = shared[0];
-    dual_state(d);
+    dual_state_ptr(d, force, floss, nefc, nf);
     bool restart = false;
     if (iter > 0) {   // every lane evaluates the same serial sum: uniform restart decision
       double dce = 0;
@@ -618,6 +622,7 @@ MJB_HD void solve_pgs(const Env& d) {
     if (improvement < m.opt.tolerance) break;
   }
   MJB_PSYNC();
+  if (onchip) { double* gf = d.efc_force().p; MJB_PFOR(i, nefc) gf[i] = force[i]; }
   MJB_LANE0 d.solver_niter()[0] += iter;
   MJB_PSYNC();
 }

@@ -25,31 +25,15 @@ MJB_HD void run_stage_mask(const Env& d, int mask, int flags) {
   if (mask & 16) stage_finish_forward(d);
 }
 
-// STAGED = true: the hot block is copied to shot/sint (shared memory in the fused kernel), every
-// stage runs on the copy, and it is written back once.  The staged Env is built directly from the
-// staging pointers so that the compiler can keep them in the shared address space.
-template <bool STAGED>
+// run the selected stages of one environment with its cooperative lanes.
+// flags: bit0 = part of mj_step (qpos/qvel checks), bit1 = skip environments that raised a warning.
+// sm/smcap: optional per-warp shared-memory scratch (doubles) used by the latency-critical loops.
 MJB_HD void run_env(const DModel& m, const Batch& b, int e, int mask, int flags, int lane, int nlane,
-                    double* shot, int* sint) {
-  double* g = b.dbl + (size_t)e * b.dpitch;
-  int* gi = b.itg + (size_t)e * b.ipitch;
-  if (flags & 2) {   // rollout: a warned env stops stepping (uniform per env)
-    const int* w = gi + b.L.warning;
-    for (int i = 0; i < NWARNING; i++) if (w[i]) return;
-  }
-  if (STAGED) {
-    for (long i = lane; i < b.L.nhot; i += nlane) shot[i] = g[i];
-    for (long i = lane; i < b.L.nint; i += nlane) sint[i] = gi[i];
-    Env d(m, b, e, lane, nlane, shot, sint);
-    d.sync();
-    run_stage_mask(d, mask, flags);
-    d.sync();
-    for (long i = lane; i < b.L.nhot; i += nlane) g[i] = shot[i];
-    for (long i = lane; i < b.L.nint; i += nlane) gi[i] = sint[i];
-  } else {
-    Env d(m, b, e, lane, nlane);
-    run_stage_mask(d, mask, flags);
-  }
+                    double* sm, int smcap) {
+  Env d(m, b, e, lane, nlane);
+  d.sm = sm; d.smcap = smcap;
+  if ((flags & 2) && env_has_warning(d)) return;   // rollout: a warned env stops stepping (uniform per env)
+  run_stage_mask(d, mask, flags);
 }
 
 // control [nenv][nstep][ncontrol] (reference layout): segments ctrl then qfrc_applied by spec bits

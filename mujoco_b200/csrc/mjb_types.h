@@ -139,10 +139,8 @@ struct DModel {
   X(efc_frictionloss, S.njmax) X(efc_diagA, S.njmax) X(efc_KBIP, 4 * S.njmax)                \
   X(efc_D, S.njmax) X(efc_R, S.njmax) X(efc_vel, S.njmax) X(efc_aref, S.njmax)               \
   X(efc_b, S.njmax) X(efc_force, S.njmax)                                                    \
-  X(efc_ARt, S.njmax * (S.njmax + 1) / 2)                                                      \
   X(scr_body, 12 * S.nbody) X(scr_nv, 8 * S.nv) X(scr_efc, 6 * S.njmax)
 
-// (efc_ARt: packed lower triangle of the symmetric AR, the copy the PGS sweep reads)
 // COLD doubles: stay in global memory / L2 in every mapping
 #define MJB_DATA_COLD_FIELDS(X, S)                                                           \
   X(efc_J, S.njmax * S.nv) X(efc_Y, S.njmax * S.nv) X(efc_AR, S.njmax * S.njmax)
@@ -211,6 +209,8 @@ struct Env {
   double* hd;        // hot doubles
   double* cd;        // cold doubles (same offsets, global memory)
   int* hi;           // ints
+  double* sm = nullptr;   // per-warp shared-memory scratch (fused kernel only) and its capacity in doubles
+  int smcap = 0;
   MJB_HD Env(const DModel& m_, const Batch& b_, int e_, int lane_ = 0, int nlane_ = 1)
       : m(m_), b(b_), e(e_), lane(lane_), nlane(nlane_) {
     hd = b.dbl + (size_t)e * b.dpitch;

@@ -29,14 +29,7 @@ long launches() { return g_launches; }
 
 int launch_stages(const DModel& dm, const Batch& b, int mask, int flags, void*) {
   g_launches++;
-  // env-major batches: stage the hot block like the CUDA kernel does (heap copy instead of smem)
-  double* shot = b.warp_per_env ? (double*)malloc(sizeof(double) * b.L.nhot) : nullptr;
-  int* sint = b.warp_per_env ? (int*)malloc(sizeof(int) * b.L.nint) : nullptr;
-  for (int e = 0; e < b.nenv; e++) {
-    if (shot) run_env<true>(dm, b, e, mask, flags, 0, 1, shot, sint);
-    else run_env<false>(dm, b, e, mask, flags, 0, 1, nullptr, nullptr);
-  }
-  free(shot); free(sint);
+  for (int e = 0; e < b.nenv; e++) run_env(dm, b, e, mask, flags, 0, 1, nullptr, 0);
   return 0;
 }
 int launch_pack(const Batch& b, int is_int, long off, long cnt, void* dense, int to_dense, void*) {
