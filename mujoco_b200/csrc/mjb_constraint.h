@@ -520,18 +520,25 @@ MJB_HD void solve_pgs(const Env& d) {
   const DModel& m = d.m;
   const int nefc = d.nefc()[0], nf = d.nf()[0], nv = m.sz.nv, njmax = m.sz.njmax;
   if (!nefc) return;
-  const bool onchip = d.sm && ((long)nefc * nefc + 7L * nefc + 8 <= d.smcap);
-  double* AR; double* force; double* b; double* floss; double* ARinv; double* fprev; double* fmom;
-  double* Adiag; double* shared;
-  if (onchip) {
-    AR = d.sm; force = AR + nefc * nefc; b = force + nefc; floss = b + nefc; ARinv = floss + nefc;
+  // where the sweep's data lives:  2 = AR and vectors in the warp's shared-memory scratch,
+  // 1 = vectors on chip, AR rows streamed from L2 through a 3-deep ring of row buffers (each row is
+  // requested two rows ahead of its use, its order being known from the shuffle),  0 = global memory
+  int mode = 0;
+  if (d.sm && (long)nefc * nefc + 7L * nefc + 8 <= d.smcap) mode = 2;
+  else if (d.sm && nefc <= 64 && 10L * nefc + 8 <= d.smcap) mode = 1;
+  const double* gAR = d.efc_AR().p;
+  double* AR = nullptr; double* ring = nullptr;
+  double* force; double* b; double* floss; double* ARinv; double* fprev; double* fmom; double* Adiag; double* shared;
+  if (mode) {
+    double* v = d.sm;
+    if (mode == 2) { AR = v; v += nefc * nefc; } else { ring = v; v += 3 * nefc; }
+    force = v; b = force + nefc; floss = b + nefc; ARinv = floss + nefc;
     fprev = ARinv + nefc; fmom = fprev + nefc; Adiag = fmom + nefc; shared = Adiag + nefc;
-    const double* gAR = d.efc_AR().p; const double* gf = d.efc_force().p; const double* gb = d.efc_b().p;
-    const double* gfl = d.efc_frictionloss().p;
-    MJB_PFOR(i, nefc * nefc) AR[i] = gAR[i];
+    const double* gf = d.efc_force().p; const double* gb = d.efc_b().p; const double* gfl = d.efc_frictionloss().p;
+    if (mode == 2) { MJB_PFOR(i, nefc * nefc) AR[i] = gAR[i]; }
     MJB_PFOR(i, nefc) { force[i] = gf[i]; b[i] = gb[i]; floss[i] = gfl[i]; }
   } else {
-    AR = d.efc_AR().p; force = d.efc_force().p; b = d.efc_b().p; floss = d.efc_frictionloss().p;
+    force = d.efc_force().p; b = d.efc_b().p; floss = d.efc_frictionloss().p;
     double* scr = d.scr_efc().p;
     ARinv = scr; fprev = scr + njmax; fmom = scr + 2 * (long)njmax; Adiag = scr + 3 * (long)njmax;
     shared = scr + 4 * (long)njmax;
@@ -542,7 +549,7 @@ MJB_HD void solve_pgs(const Env& d) {
   const double scale = 1 / (m.opt.meaninertia * (nv > 1 ? nv : 1));
   MJB_PFOR(i, nefc) {
     fprev[i] = force[i];
-    const double ai = 1 / AR[(long)i * (nefc + 1)];
+    const double ai = 1 / gAR[(long)i * (nefc + 1)];
     ARinv[i] = ai;
     Adiag[i] = 1 / ai;    // the reference's Athis[0] = 1/ARinv
     order[i] = i;
@@ -576,10 +583,25 @@ MJB_HD void solve_pgs(const Env& d) {
       }
     }
     MJB_PSYNC();
+    if (mode == 1) {   // prime the ring with the first two rows of this sweep
+      for (int q = 0; q < 2 && q < nefc; q++) {
+        const double* g = gAR + (long)order[q] * nefc;
+        MJB_PFOR(c, nefc) ring[q * nefc + c] = g[c];
+      }
+      MJB_PSYNC();
+    }
     double impr = 0;   // meaningful on lane 0
     for (int bi = 0; bi < nefc; bi++) {
       const int i = order[bi];
-      const double* row = AR + (long)i * nefc;
+      // request the row needed two iterations from now (values land in registers; stored below)
+      double p0 = 0, p1 = 0;
+      const bool pre = (mode == 1) && (bi + 2 < nefc);
+      if (pre) {
+        const double* g = gAR + (long)order[bi + 2] * nefc;
+        if (d.lane < nefc) p0 = g[d.lane];
+        if (d.lane + 32 < nefc) p1 = g[d.lane + 32];
+      }
+      const double* row = (mode == 2) ? AR + (long)i * nefc : (mode == 1) ? ring + (bi % 3) * nefc : gAR + (long)i * nefc;
       // four stride-4 partial sums of AR[i,:] . force, one per lane (all four on lane 0 when alone)
       for (int k = d.lane; k < 4; k += d.nlane) {
         double r = 0;
@@ -605,6 +627,11 @@ MJB_HD void solve_pgs(const Env& d) {
         force[i] = f;
         impr -= change;
       }
+      if (pre) {
+        double* dst = ring + ((bi + 2) % 3) * nefc;
+        if (d.lane < nefc) dst[d.lane] = p0;
+        if (d.lane + 32 < nefc) dst[d.lane + 32] = p1;
+      }
       MJB_PSYNC();
     }
     MJB_LANE0 shared[0] = impr * scale;
@@ -622,7 +649,7 @@ MJB_HD void solve_pgs(const Env& d) {
     if (improvement < m.opt.tolerance) break;
   }
   MJB_PSYNC();
-  if (onchip) { double* gf = d.efc_force().p; MJB_PFOR(i, nefc) gf[i] = force[i]; }
+  if (mode) { double* gf = d.efc_force().p; MJB_PFOR(i, nefc) gf[i] = force[i]; }
   MJB_LANE0 d.solver_niter()[0] += iter;
   MJB_PSYNC();
 }

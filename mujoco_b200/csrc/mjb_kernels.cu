@@ -34,8 +34,11 @@ __global__ void __launch_bounds__(32) k_step_lane(DModel m, Batch b, int mask, i
 // shared memory, which capped residency at 3 warps/SM).  Each warp owns kSmemPerWarp doubles of
 // shared memory used by the one truly serial loop, the PGS sweep (AR + sweep vectors on chip).
 constexpr int kWarpsPerCta = 4;
-constexpr int kSmemPerWarp = 1280;   // doubles = 10 KB: AR up to 32x32 plus seven sweep vectors
-__global__ void __launch_bounds__(32 * kWarpsPerCta, 5) k_step_warp(DModel m, Batch b, int mask, int flags) {
+#ifndef MJB_CTAS_PER_SM
+#define MJB_CTAS_PER_SM 7   // 28 warps/SM: a 4096-env batch is resident in ONE wave on 148 SMs (needs <= 72 regs)
+#endif
+constexpr int kSmemPerWarp = 648;    // doubles = 5 KB: seven sweep vectors + a 3-row ring for nefc <= 64 (or all of AR for nefc <= 22)
+__global__ void __launch_bounds__(32 * kWarpsPerCta, MJB_CTAS_PER_SM) k_step_warp(DModel m, Batch b, int mask, int flags) {
   __shared__ double smem[kWarpsPerCta * kSmemPerWarp];
   const int w = threadIdx.x >> 5;
   const int e = blockIdx.x * kWarpsPerCta + w;
