@@ -315,15 +315,10 @@ int mjb_step_host(mjbBatch* B, const double* ctrl, double* state_out) {
 
 int mjb_rollout_device(mjbBatch* B, int nstep, const double* d_ctrl, double* d_state) {
   if (!B || nstep < 0) return fail(MJB_ERR_ARG, "mjb_rollout_device: bad arguments");
-  const unsigned full = ST_TIME | ST_QPOS | ST_QVEL;
-  const int nstate = mjb_state_size(B, full);
-  int rc = 0;
-  for (int t = 0; t < nstep && !rc; t++) {
-    if (d_ctrl) rc = backend::launch_set_control_native(B->dm, B->b, d_ctrl, t, B->stream);
-    if (!rc) rc = backend::launch_stages(B->dm, B->b, 0xF, 1, B->stream);
-    if (d_state && !rc) rc = backend::launch_get_state_native(B->dm, B->b, d_state, t, nstate, B->stream);
-  }
-  return rc;   // asynchronous: caller synchronises on mjb_stream()
+  const int nstate = 1 + B->hm.dm.sz.nq + B->hm.dm.sz.nv;
+  if (!nstep) return 0;
+  // one persistent launch: every environment runs its nstep steps back to back
+  return backend::launch_rollout_native(B->dm, B->b, d_ctrl, d_state, nstep, nstate, B->stream);   // asynchronous
 }
 
 // ---- field access ----------------------------------------------------------------------------------

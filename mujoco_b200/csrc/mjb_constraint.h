@@ -524,16 +524,19 @@ MJB_HD void solve_pgs(const Env& d) {
   // 1 = vectors on chip, AR rows streamed from L2 through a 3-deep ring of row buffers (each row is
   // requested two rows ahead of its use, its order being known from the shuffle),  0 = global memory
   int mode = 0;
-  if (d.sm && (long)nefc * nefc + 7L * nefc + 8 <= d.smcap) mode = 2;
-  else if (d.sm && nefc <= 64 && 10L * nefc + 8 <= d.smcap) mode = 1;
+  const int nord = (nefc + 1) / 2;   // doubles that hold the visit order (ints)
+  if (d.sm && (long)nefc * nefc + 7L * nefc + nord + 8 <= d.smcap) mode = 2;
+  else if (d.sm && nefc <= 64 && 10L * nefc + nord + 8 <= d.smcap) mode = 1;
   const double* gAR = d.efc_AR().p;
   double* AR = nullptr; double* ring = nullptr;
   double* force; double* b; double* floss; double* ARinv; double* fprev; double* fmom; double* Adiag; double* shared;
+  int* order = d.scr_int().p + njmax;
   if (mode) {
     double* v = d.sm;
     if (mode == 2) { AR = v; v += nefc * nefc; } else { ring = v; v += 3 * nefc; }
     force = v; b = force + nefc; floss = b + nefc; ARinv = floss + nefc;
     fprev = ARinv + nefc; fmom = fprev + nefc; Adiag = fmom + nefc; shared = Adiag + nefc;
+    order = (int*)(shared + 8);
     const double* gf = d.efc_force().p; const double* gb = d.efc_b().p; const double* gfl = d.efc_frictionloss().p;
     if (mode == 2) { MJB_PFOR(i, nefc * nefc) AR[i] = gAR[i]; }
     MJB_PFOR(i, nefc) { force[i] = gf[i]; b[i] = gb[i]; floss[i] = gfl[i]; }
@@ -543,7 +546,6 @@ MJB_HD void solve_pgs(const Env& d) {
     ARinv = scr; fprev = scr + njmax; fmom = scr + 2 * (long)njmax; Adiag = scr + 3 * (long)njmax;
     shared = scr + 4 * (long)njmax;
   }
-  FI order = d.scr_int() + njmax;
   MJB_PSYNC();
   const int n4 = nefc & ~3, tail = nefc - n4;
   const double scale = 1 / (m.opt.meaninertia * (nv > 1 ? nv : 1));

@@ -37,13 +37,32 @@ constexpr int kWarpsPerCta = 4;
 #ifndef MJB_CTAS_PER_SM
 #define MJB_CTAS_PER_SM 7   // 28 warps/SM: a 4096-env batch is resident in ONE wave on 148 SMs (needs <= 72 regs)
 #endif
-constexpr int kSmemPerWarp = 648;    // doubles = 5 KB: seven sweep vectors + a 3-row ring for nefc <= 64 (or all of AR for nefc <= 22)
+constexpr int kSmemPerWarp = 688;    // doubles = 5 KB: seven sweep vectors + a 3-row ring for nefc <= 64 (or all of AR for nefc <= 22)
 __global__ void __launch_bounds__(32 * kWarpsPerCta, MJB_CTAS_PER_SM) k_step_warp(DModel m, Batch b, int mask, int flags) {
   __shared__ double smem[kWarpsPerCta * kSmemPerWarp];
   const int w = threadIdx.x >> 5;
   const int e = blockIdx.x * kWarpsPerCta + w;
   if (e >= b.nenv) return;
   run_env(m, b, e, mask, flags, threadIdx.x & 31, 32, smem + w * kSmemPerWarp, kSmemPerWarp);
+}
+
+// PERSISTENT ROLLOUT KERNEL: each warp advances its environment through nstep steps without any
+// grid-wide barrier between steps, reading that step's controls from / recording its state to
+// device buffers in the native [step][elem][env] layout.  Because environments are independent, a
+// slow environment (a PGS solve that runs to the iteration cap) only delays itself: throughput is
+// set by the MEAN per-environment step time instead of the per-step maximum.
+__global__ void __launch_bounds__(32 * kWarpsPerCta, MJB_CTAS_PER_SM)
+k_rollout_warp(DModel m, Batch b, const double* ctrl, double* state, int nstep, int nstate) {
+  __shared__ double smem[kWarpsPerCta * kSmemPerWarp];
+  const int w = threadIdx.x >> 5;
+  const int e = blockIdx.x * kWarpsPerCta + w;
+  if (e >= b.nenv) return;
+  run_env_rollout(m, b, e, nstep, ctrl, state, nstate, threadIdx.x & 31, 32, smem + w * kSmemPerWarp, kSmemPerWarp);
+}
+__global__ void __launch_bounds__(32) k_rollout_lane(DModel m, Batch b, const double* ctrl, double* state, int nstep, int nstate) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= b.nenv) return;
+  run_env_rollout(m, b, e, nstep, ctrl, state, nstate, 0, 1, nullptr, 0);
 }
 
 __global__ void k_pack(Batch b, int is_int, long off, long cnt, void* dense, int to_dense) {
@@ -169,6 +188,16 @@ int launch_stages(const DModel& dm, const Batch& b, int mask, int flags, void* s
   }
   g_launches++;
   CK(cudaPeekAtLastError(), "step kernel launch");
+  return 0;
+}
+int launch_rollout_native(const DModel& dm, const Batch& b, const double* ctrl, double* state, int nstep, int nstate, void* s) {
+  if (b.warp_per_env) {
+    k_rollout_warp<<<(b.nenv + kWarpsPerCta - 1) / kWarpsPerCta, 32 * kWarpsPerCta, 0, (cudaStream_t)s>>>(dm, b, ctrl, state, nstep, nstate);
+  } else {
+    k_rollout_lane<<<nblocks(b, 32), 32, 0, (cudaStream_t)s>>>(dm, b, ctrl, state, nstep, nstate);
+  }
+  g_launches++;
+  CK(cudaPeekAtLastError(), "rollout kernel launch");
   return 0;
 }
 int launch_reset(const DModel& dm, const Batch& b, void* s) {

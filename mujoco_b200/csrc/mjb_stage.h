@@ -36,6 +36,32 @@ MJB_HD void run_env(const DModel& m, const Batch& b, int e, int mask, int flags,
   run_stage_mask(d, mask, flags);
 }
 
+// nstep consecutive steps of one environment: controls from ctrl [nstep][nu][stride] (or unchanged
+// when NULL), optional state record into state [nstep][nstate][stride] (time, qpos, qvel)
+MJB_HD void run_env_rollout(const DModel& m, const Batch& b, int e, int nstep, const double* ctrl, double* state,
+                            int nstate, int lane, int nlane, double* sm, int smcap) {
+  Env d(m, b, e, lane, nlane);
+  d.sm = sm; d.smcap = smcap;
+  const int nu = m.sz.nu, nq = m.sz.nq, nv = m.sz.nv;
+  for (int t = 0; t < nstep; t++) {
+    if (ctrl) {
+      FD c = d.ctrl();
+      const double* src = ctrl + (size_t)t * nu * b.stride + e;
+      MJB_PFOR(i, nu) c[i] = src[(size_t)i * b.stride];
+      MJB_PSYNC();
+    }
+    run_stage_mask(d, 0xF, 1);
+    if (state) {
+      double* dst = state + (size_t)t * nstate * b.stride + e;
+      FD qp = d.qpos(), qv = d.qvel();
+      MJB_LANE0 dst[0] = d.time()[0];
+      MJB_PFOR(i, nq) dst[(size_t)(1 + i) * b.stride] = qp[i];
+      MJB_PFOR(i, nv) dst[(size_t)(1 + nq + i) * b.stride] = qv[i];
+      MJB_PSYNC();
+    }
+  }
+}
+
 // control [nenv][nstep][ncontrol] (reference layout): segments ctrl then qfrc_applied by spec bits
 MJB_HD void run_set_control(const DModel& m, const Batch& b, int e, const double* control, int nstep, int t,
                             unsigned spec, int ncontrol) {
