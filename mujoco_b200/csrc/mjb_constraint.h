@@ -516,48 +516,20 @@ MJB_HD void dual_state_ptr(const Env& d, const double* force, const double* flos
 // spread over all lanes.  In the fused kernel AR and the sweep vectors are first copied into the
 // warp's shared-memory scratch (when nefc^2 + 7 nefc + 8 doubles fit), so the serial chain never
 // waits on L2.  Results are bit-identical to the serial reference arithmetic.
-MJB_HD void solve_pgs(const Env& d) {
+// sweep iterations, specialised on where AR rows come from so that every pointer has a single
+// provenance (shared vs global) and the compiler emits LDS/STS for the on-chip data:
+//   MODE 2: AR and vectors in the warp's shared-memory scratch
+//   MODE 1: vectors on chip; AR rows streamed from L2 through a 3-deep ring of row buffers (each row is
+//           requested two rows ahead of its use, its position in the sweep being known from the shuffle)
+//   MODE 0: everything in global memory (host emulation, lane-per-env mapping, oversized problems)
+template <int MODE>
+MJB_HD int pgs_sweeps(const Env& d, int nefc, int nf, const double* gAR, const double* AR, double* ring,
+                      double* force, const double* b, const double* floss, const double* ARinv, double* fprev,
+                      double* fmom, const double* Adiag, double* shared, int* order) {
   const DModel& m = d.m;
-  const int nefc = d.nefc()[0], nf = d.nf()[0], nv = m.sz.nv, njmax = m.sz.njmax;
-  if (!nefc) return;
-  // where the sweep's data lives:  2 = AR and vectors in the warp's shared-memory scratch,
-  // 1 = vectors on chip, AR rows streamed from L2 through a 3-deep ring of row buffers (each row is
-  // requested two rows ahead of its use, its order being known from the shuffle),  0 = global memory
-  int mode = 0;
-  const int nord = (nefc + 1) / 2;   // doubles that hold the visit order (ints)
-  if (d.sm && (long)nefc * nefc + 7L * nefc + nord + 8 <= d.smcap) mode = 2;
-  else if (d.sm && nefc <= 64 && 10L * nefc + nord + 8 <= d.smcap) mode = 1;
-  const double* gAR = d.efc_AR().p;
-  double* AR = nullptr; double* ring = nullptr;
-  double* force; double* b; double* floss; double* ARinv; double* fprev; double* fmom; double* Adiag; double* shared;
-  int* order = d.scr_int().p + njmax;
-  if (mode) {
-    double* v = d.sm;
-    if (mode == 2) { AR = v; v += nefc * nefc; } else { ring = v; v += 3 * nefc; }
-    force = v; b = force + nefc; floss = b + nefc; ARinv = floss + nefc;
-    fprev = ARinv + nefc; fmom = fprev + nefc; Adiag = fmom + nefc; shared = Adiag + nefc;
-    order = (int*)(shared + 8);
-    const double* gf = d.efc_force().p; const double* gb = d.efc_b().p; const double* gfl = d.efc_frictionloss().p;
-    if (mode == 2) { MJB_PFOR(i, nefc * nefc) AR[i] = gAR[i]; }
-    MJB_PFOR(i, nefc) { force[i] = gf[i]; b[i] = gb[i]; floss[i] = gfl[i]; }
-  } else {
-    force = d.efc_force().p; b = d.efc_b().p; floss = d.efc_frictionloss().p;
-    double* scr = d.scr_efc().p;
-    ARinv = scr; fprev = scr + njmax; fmom = scr + 2 * (long)njmax; Adiag = scr + 3 * (long)njmax;
-    shared = scr + 4 * (long)njmax;
-  }
-  MJB_PSYNC();
+  const int nv = m.sz.nv;
   const int n4 = nefc & ~3, tail = nefc - n4;
   const double scale = 1 / (m.opt.meaninertia * (nv > 1 ? nv : 1));
-  MJB_PFOR(i, nefc) {
-    fprev[i] = force[i];
-    const double ai = 1 / gAR[(long)i * (nefc + 1)];
-    ARinv[i] = ai;
-    Adiag[i] = 1 / ai;    // the reference's Athis[0] = 1/ARinv
-    order[i] = i;
-  }
-  MJB_PSYNC();
-  dual_state_ptr(d, force, floss, nefc, nf);
   Pcg32 rng{0, 1};
   pcg32_next(rng);
   int iter = 0, nk = 0;
@@ -585,9 +557,9 @@ MJB_HD void solve_pgs(const Env& d) {
       }
     }
     MJB_PSYNC();
-    if (mode == 1) {   // prime the ring with the first two rows of this sweep
+    if (MODE == 1) {   // prime the ring with the first two rows of this sweep
       for (int q = 0; q < 2 && q < nefc; q++) {
-        const double* g = gAR + (long)order[q] * nefc;
+        const double* g = gAR + order[q] * nefc;
         MJB_PFOR(c, nefc) ring[q * nefc + c] = g[c];
       }
       MJB_PSYNC();
@@ -595,24 +567,35 @@ MJB_HD void solve_pgs(const Env& d) {
     double impr = 0;   // meaningful on lane 0
     for (int bi = 0; bi < nefc; bi++) {
       const int i = order[bi];
-      // request the row needed two iterations from now (values land in registers; stored below)
       double p0 = 0, p1 = 0;
-      const bool pre = (mode == 1) && (bi + 2 < nefc);
-      if (pre) {
-        const double* g = gAR + (long)order[bi + 2] * nefc;
+      const bool pre = (MODE == 1) && (bi + 2 < nefc);
+      if (pre) {   // request the row needed two iterations from now (lands in registers; stored below)
+        const double* g = gAR + order[bi + 2] * nefc;
         if (d.lane < nefc) p0 = g[d.lane];
         if (d.lane + 32 < nefc) p1 = g[d.lane + 32];
       }
-      const double* row = (mode == 2) ? AR + (long)i * nefc : (mode == 1) ? ring + (bi % 3) * nefc : gAR + (long)i * nefc;
-      // four stride-4 partial sums of AR[i,:] . force, one per lane (all four on lane 0 when alone)
-      for (int k = d.lane; k < 4; k += d.nlane) {
+      const double* row = (MODE == 2) ? AR + i * nefc : (MODE == 1) ? ring + (bi % 3) * nefc : gAR + (long)i * nefc;
+      // mju_dot structure: four stride-4 partial sums, one per lane, combined as (r0+r2)+(r1+r3)
+      double dotv;
+#if defined(__CUDA_ARCH__)
+      if (d.nlane == 32) {
         double r = 0;
-        for (int c = k; c < n4; c += 4) r += row[c] * force[c];
-        shared[1 + k] = r;
+        if (d.lane < 4) for (int c = d.lane; c < n4; c += 4) r += row[c] * force[c];
+        const double v = r + __shfl_down_sync(0xffffffffu, r, 2);    // lane 0: r0+r2   lane 1: r1+r3
+        dotv = v + __shfl_down_sync(0xffffffffu, v, 1);              // lane 0: (r0+r2)+(r1+r3)
+      } else
+#endif
+      {
+        for (int k = d.lane; k < 4; k += d.nlane) {
+          double r = 0;
+          for (int c = k; c < n4; c += 4) r += row[c] * force[c];
+          shared[1 + k] = r;
+        }
+        MJB_PSYNC();
+        dotv = (shared[1] + shared[3]) + (shared[2] + shared[4]);
       }
-      MJB_PSYNC();
       MJB_LANE0 {
-        double res = (shared[1] + shared[3]) + (shared[2] + shared[4]);
+        double res = dotv;
         if (tail == 3) res += row[n4] * force[n4] + row[n4 + 1] * force[n4 + 1] + row[n4 + 2] * force[n4 + 2];
         else if (tail == 2) res += row[n4] * force[n4] + row[n4 + 1] * force[n4 + 1];
         else if (tail == 1) res += row[n4] * force[n4];
@@ -650,8 +633,61 @@ MJB_HD void solve_pgs(const Env& d) {
     iter++;
     if (improvement < m.opt.tolerance) break;
   }
+  return iter;
+}
+
+MJB_HD void solve_pgs(const Env& d) {
+  const DModel& m = d.m;
+  const int nefc = d.nefc()[0], nf = d.nf()[0], njmax = m.sz.njmax;
+  if (!nefc) return;
+  int mode = 0;
+  const int nord = (nefc + 1) / 2;   // doubles that hold the visit order (ints)
+  if (d.sm && (long)nefc * nefc + 7L * nefc + nord + 8 <= d.smcap) mode = 2;
+  else if (d.sm && nefc <= 64 && 10L * nefc + nord + 8 <= d.smcap) mode = 1;
+  const double* gAR = d.efc_AR().p;
+  int iter;
+  if (mode) {
+    double* v = d.sm;
+    double* AR = nullptr; double* ring = nullptr;
+    if (mode == 2) { AR = v; v += nefc * nefc; } else { ring = v; v += 3 * nefc; }
+    double* force = v; double* b = force + nefc; double* floss = b + nefc; double* ARinv = floss + nefc;
+    double* fprev = ARinv + nefc; double* fmom = fprev + nefc; double* Adiag = fmom + nefc; double* shared = Adiag + nefc;
+    int* order = (int*)(shared + 8);
+    const double* gf = d.efc_force().p; const double* gb = d.efc_b().p; const double* gfl = d.efc_frictionloss().p;
+    if (mode == 2) { MJB_PFOR(i, nefc * nefc) AR[i] = gAR[i]; }
+    MJB_PFOR(i, nefc) {
+      const double f0 = gf[i];
+      force[i] = f0; fprev[i] = f0; b[i] = gb[i]; floss[i] = gfl[i];
+      const double ai = 1 / gAR[(long)i * (nefc + 1)];
+      ARinv[i] = ai;
+      Adiag[i] = 1 / ai;    // the reference's Athis[0] = 1/ARinv
+      order[i] = i;
+    }
+    MJB_PSYNC();
+    dual_state_ptr(d, force, floss, nefc, nf);
+    if (mode == 2) iter = pgs_sweeps<2>(d, nefc, nf, gAR, AR, ring, force, b, floss, ARinv, fprev, fmom, Adiag, shared, order);
+    else iter = pgs_sweeps<1>(d, nefc, nf, gAR, AR, ring, force, b, floss, ARinv, fprev, fmom, Adiag, shared, order);
+    MJB_PSYNC();
+    double* gfo = d.efc_force().p;
+    MJB_PFOR(i, nefc) gfo[i] = force[i];
+  } else {
+    double* force = d.efc_force().p; const double* b = d.efc_b().p; const double* floss = d.efc_frictionloss().p;
+    double* scr = d.scr_efc().p;
+    double* ARinv = scr; double* fprev = scr + njmax; double* fmom = scr + 2 * (long)njmax; double* Adiag = scr + 3 * (long)njmax;
+    double* shared = scr + 4 * (long)njmax;
+    int* order = d.scr_int().p + njmax;
+    MJB_PFOR(i, nefc) {
+      fprev[i] = force[i];
+      const double ai = 1 / gAR[(long)i * (nefc + 1)];
+      ARinv[i] = ai;
+      Adiag[i] = 1 / ai;
+      order[i] = i;
+    }
+    MJB_PSYNC();
+    dual_state_ptr(d, force, floss, nefc, nf);
+    iter = pgs_sweeps<0>(d, nefc, nf, gAR, nullptr, nullptr, force, b, floss, ARinv, fprev, fmom, Adiag, shared, order);
+  }
   MJB_PSYNC();
-  if (mode) { double* gf = d.efc_force().p; MJB_PFOR(i, nefc) gf[i] = force[i]; }
   MJB_LANE0 d.solver_niter()[0] += iter;
   MJB_PSYNC();
 }
