@@ -519,8 +519,8 @@ MJB_HD void dual_state_ptr(const Env& d, const double* force, const double* flos
 // sweep iterations, specialised on where AR rows come from so that every pointer has a single
 // provenance (shared vs global) and the compiler emits LDS/STS for the on-chip data:
 //   MODE 2: AR and vectors in the warp's shared-memory scratch
-//   MODE 1: vectors on chip; AR rows streamed from L2 through a 3-deep ring of row buffers (each row is
-//           requested two rows ahead of its use, its position in the sweep being known from the shuffle)
+//   MODE 1: vectors on chip; AR rows streamed from L2 through a 4-slot ring of row buffers (each row is
+//           requested four rows ahead of its use, its position in the sweep being known from the shuffle)
 //   MODE 0: everything in global memory (host emulation, lane-per-env mapping, oversized problems)
 template <int MODE>
 MJB_HD int pgs_sweeps(const Env& d, int nefc, int nf, const double* gAR, const double* AR, double* ring,
@@ -557,24 +557,23 @@ MJB_HD int pgs_sweeps(const Env& d, int nefc, int nf, const double* gAR, const d
       }
     }
     MJB_PSYNC();
-    if (MODE == 1) {   // prime the ring with the first two rows of this sweep
-      for (int q = 0; q < 2 && q < nefc; q++) {
+    double p0 = 0, p1 = 0;   // MODE 1: row in flight from L2 (requested one iteration before it is parked)
+    if (MODE == 1) {   // prime the ring with the first three rows of this sweep, request the fourth
+      for (int q = 0; q < 3 && q < nefc; q++) {
         const double* g = gAR + order[q] * nefc;
         MJB_PFOR(c, nefc) ring[q * nefc + c] = g[c];
+      }
+      if (3 < nefc) {
+        const double* g = gAR + order[3] * nefc;
+        if (d.lane < nefc) p0 = g[d.lane];
+        if (d.lane + 32 < nefc) p1 = g[d.lane + 32];
       }
       MJB_PSYNC();
     }
     double impr = 0;   // meaningful on lane 0
     for (int bi = 0; bi < nefc; bi++) {
       const int i = order[bi];
-      double p0 = 0, p1 = 0;
-      const bool pre = (MODE == 1) && (bi + 2 < nefc);
-      if (pre) {   // request the row needed two iterations from now (lands in registers; stored below)
-        const double* g = gAR + order[bi + 2] * nefc;
-        if (d.lane < nefc) p0 = g[d.lane];
-        if (d.lane + 32 < nefc) p1 = g[d.lane + 32];
-      }
-      const double* row = (MODE == 2) ? AR + i * nefc : (MODE == 1) ? ring + (bi % 3) * nefc : gAR + (long)i * nefc;
+      const double* row = (MODE == 2) ? AR + i * nefc : (MODE == 1) ? ring + (bi & 3) * nefc : gAR + (long)i * nefc;
       // mju_dot structure: four stride-4 partial sums, one per lane, combined as (r0+r2)+(r1+r3)
       double dotv;
 #if defined(__CUDA_ARCH__)
@@ -612,10 +611,17 @@ MJB_HD int pgs_sweeps(const Env& d, int nefc, int nf, const double* gAR, const d
         force[i] = f;
         impr -= change;
       }
-      if (pre) {
-        double* dst = ring + ((bi + 2) % 3) * nefc;
+      if (MODE == 1 && bi + 3 < nefc) {
+        // park row bi+3 (requested during the previous iteration) in the slot freed by row bi-1, then
+        // request row bi+4: every row has a full iteration in flight before it is parked
+        double* dst = ring + ((bi + 3) & 3) * nefc;
         if (d.lane < nefc) dst[d.lane] = p0;
         if (d.lane + 32 < nefc) dst[d.lane + 32] = p1;
+        if (bi + 4 < nefc) {
+          const double* g = gAR + order[bi + 4] * nefc;
+          if (d.lane < nefc) p0 = g[d.lane];
+          if (d.lane + 32 < nefc) p1 = g[d.lane + 32];
+        }
       }
       MJB_PSYNC();
     }
@@ -643,13 +649,13 @@ MJB_HD void solve_pgs(const Env& d) {
   int mode = 0;
   const int nord = (nefc + 1) / 2;   // doubles that hold the visit order (ints)
   if (d.sm && (long)nefc * nefc + 7L * nefc + nord + 8 <= d.smcap) mode = 2;
-  else if (d.sm && nefc <= 64 && 10L * nefc + nord + 8 <= d.smcap) mode = 1;
+  else if (d.sm && nefc <= 64 && 11L * nefc + nord + 8 <= d.smcap) mode = 1;
   const double* gAR = d.efc_AR().p;
   int iter;
   if (mode) {
     double* v = d.sm;
     double* AR = nullptr; double* ring = nullptr;
-    if (mode == 2) { AR = v; v += nefc * nefc; } else { ring = v; v += 3 * nefc; }
+    if (mode == 2) { AR = v; v += nefc * nefc; } else { ring = v; v += 4 * nefc; }
     double* force = v; double* b = force + nefc; double* floss = b + nefc; double* ARinv = floss + nefc;
     double* fprev = ARinv + nefc; double* fmom = fprev + nefc; double* Adiag = fmom + nefc; double* shared = Adiag + nefc;
     int* order = (int*)(shared + 8);
