@@ -89,7 +89,7 @@ def reference_arm(args, rank, world):
     nu, cores = o.size("nu"), os.cpu_count() or 1
     nthread = cores
     # each "step" = one mj_step of a bounded sample of the batch, sized to ~0.25 s per step
-    sample = min(NENV, max(nthread * 8, 256))
+    sample = NENV
     rng = np.random.default_rng(0)
     o.reset()
     s0 = np.tile(o.get_state(), (sample, 1))
@@ -221,32 +221,41 @@ def main():
         for s in range(4):
             stage_ms[s] += evs[s].elapsed_time(evs[s + 1])
     stage_ms /= nprobe
-    dom = int(np.argmax(stage_ms))
 
     # ---- roofline of the dominant kernel
     peak, peak_src = peaks()
     m_nefc, m_nefc2, m_ncon = float(nefc.mean()), float((nefc ** 2).mean()), float(ncon.mean())
     m_iter = float(niter.mean())
-    L = batch.L
-    fixed = sum(int(L.mjb_field_size(batch.ptr, f.encode())) for f in
-                ["xpos", "xquat", "xmat", "xipos", "ximat", "xanchor", "xaxis", "geom_xpos", "geom_xmat", "subtree_com",
-                 "cinert", "cdof", "crb", "M", "qLD", "qLDiagInv", "ten_length", "ten_J", "actuator_length",
-                 "actuator_moment"])
-    b_pos = 8 * (nq + fixed) + m_ncon * 8 * 27 + m_nefc * 8 * (nv + 10) + 8 * m_nefc * nv + 8 * m_nefc2
-    fixed_v = sum(int(L.mjb_field_size(batch.ptr, f.encode())) for f in
-                  ["ten_velocity", "actuator_velocity", "cvel", "cdof_dot", "qfrc_spring", "qfrc_damper", "qfrc_passive",
-                   "qfrc_bias", "actuator_force", "qfrc_actuator", "qfrc_smooth", "qacc_smooth"])
-    b_vel = 8 * (nv + nu + fixed_v) + m_nefc * 8 * (nv + 6) + 8 * m_nefc2
-    b_sol = 8 * m_nefc2 + 8 * 6 * m_nefc            # AR read once + b, force, R, floss, state
-    b_int = 8 * (2 * 243 + 6 * nv + nq) + m_nefc * 8 * (nv + 1)
+    # ALGORITHMIC bytes per env-step, SURVEY.md section 8(d) convention "B_mjdata" (DESIGN.md section 5):
+    #   B_state + 8 * (hot-path mjData fields written once) + ncon*584 + nefc*(8*(nv+14)+12)
+    #   + PGS: 8*nefc*nv (efc_Y... the A = J M^-1 J^T factor) + 8*nefc^2 (efc_AR)
+    # with the batch's own mean ncon / nefc / nefc^2 at the end of the timed window.  Split per stage for
+    # the stage table only (position: kinematic fields + contacts + rows + Y + AR; velocity; solve: AR re-read;
+    # integrate: state out).
+    b_state = 8 * ((1 + nq + nv + nu + nv) + (1 + nq + nv + nv))
+    b_pos = 8 * 2010 + m_ncon * 584 + m_nefc * (8 * (nv + 14) + 12) + 8 * m_nefc * nv + 8 * m_nefc2
+    b_vel = 8 * 746
+    b_sol = 8 * 156
+    b_int = b_state
     bytes_per_env = [b_pos, b_vel, b_sol, b_int]
-    achieved = NENV * bytes_per_env[dom] / (stage_ms[dom] * 1e-3) / 1e9
     b_mjdata = sum(bytes_per_env)
-    roof = {"bound": "hbm", "kernel": "k_stage(stage=%d:%s)" % (dom, ["position", "velocity", "solve", "integrate"][dom]),
-            "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
-            "traffic": None, "algorithmic_bytes_per_env_step": b_mjdata,
-            "whole_step_achieved_gbs": value / world * b_mjdata / 1e9,
-            "stage_ms": [float(x) for x in stage_ms]}
+    # dominant kernel = the fused per-step launch k_step_warp (stages 0-3 of every env, one launch per
+    # step); its average duration over the timed region = ms / K (launches are back to back on the
+    # stream; the tiny k_set_control launch in between is included, which only lowers `achieved`)
+    launch_ms = ms / K
+    achieved = NENV * b_mjdata / (launch_ms * 1e-3) / 1e9
+    traffic, traffic_src = None, None
+    tp = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if os.path.exists(tp):
+        tj = json.load(open(tp))
+        traffic, traffic_src = tj.get("dram_bytes_per_launch"), tj.get("source")
+    roof = {"bound": "hbm", "kernel": "k_step_warp (fused mj_step, 1 launch/step)", "achieved": achieved, "peak": peak,
+            "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+            "traffic_source": traffic_src, "algorithmic_bytes_per_launch": NENV * b_mjdata,
+            "algorithmic_bytes_per_env_step": b_mjdata, "launch_ms": launch_ms,
+            "note": "latency-bound (serial PGS dependency chain of the slowest env), not bandwidth-bound: see DESIGN.md",
+            "stage_ms": dict(zip(["position", "velocity", "solve", "integrate"], [float(x) for x in stage_ms])),
+            "stage_bytes_per_env": dict(zip(["position", "velocity", "solve", "integrate"], [float(x) for x in bytes_per_env]))}
 
     # ---- e2e: per step H2D ctrl from pinned host, step, D2H state
     ke = min(K, 100)
@@ -276,7 +285,7 @@ def main():
                 o = Oracle(MODEL)
                 o.set_opt("solver", 0)
                 cores = os.cpu_count() or 1
-                sample, csteps = max(cores * 8, 128), 50
+                sample, csteps = NENV, 100
                 s_now = batch.get_state()[:sample]
                 rng = np.random.default_rng(1)
                 cctrl = rng.uniform(-1, 1, (sample, csteps, nu))
@@ -292,8 +301,8 @@ def main():
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
             "config": {"workload": WORKLOAD, "nenv_per_gpu": NENV, "settle_steps": SETTLE,
-                       "l2": "per-step working set %.0f MB/GPU > 126 MB L2 (inputs larger than L2)" %
-                             (batch.L.mjb_field_size(batch.ptr, b"efc_AR") * 8 * NENV / 1e6),
+                       "l2": "no flush: bytes touched per step %.0f MB/GPU > 126 MB L2 (inputs larger than L2)" %
+                             (b_mjdata * NENV / 1e6),
                        "mean_ncon": m_ncon, "mean_nefc": m_nefc, "mean_pgs_iter": m_iter, "warnings": warn},
             "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
             "clocks": sampler.summary(),

@@ -642,41 +642,196 @@ MJB_HD int pgs_sweeps(const Env& d, int nefc, int nf, const double* gAR, const d
   return iter;
 }
 
+#if defined(__CUDACC__)
+// PCG32 skip-ahead (state after `delta` < 128 draws; increment 1): lets every lane produce its own
+// draw of a sweep, so the LCG and the modulo leave the serial Fisher-Yates chain
+__device__ inline uint64_t pcg32_skip(uint64_t state, uint32_t delta) {
+  uint64_t cur_mult = 6364136223846793005ULL, cur_plus = 1, acc_mult = 1, acc_plus = 0;
+#pragma unroll
+  for (int bit = 0; bit < 7; bit++) {
+    if (delta & 1u) { acc_mult *= cur_mult; acc_plus = acc_plus * cur_mult + cur_plus; }
+    cur_plus = (cur_mult + 1) * cur_plus;
+    cur_mult *= cur_mult;
+    delta >>= 1;
+  }
+  return acc_mult * state + acc_plus;
+}
+
+// Warp-per-env PGS sweeps with all sweep data on chip (MODE 2: AR in shared memory, MODE 1: AR rows
+// through the 4-slot ring).  Same arithmetic as pgs_sweeps, organised so that the row body is
+// uniform across the warp — every lane runs chain (lane & 3) of the mju_dot structure, an xor
+// butterfly gives every lane the identical (r0+r2)+(r1+r3) (IEEE addition commutes), and every lane
+// evaluates the projected update redundantly — which removes all divergence/reconvergence from the
+// serial chain.  lo/hi are the projection bounds (-floss/floss for friction rows, 0/inf otherwise).
+template <int MODE>
+__device__ int pgs_sweeps_warp(const Env& d, int nefc, int nf, const double* __restrict__ gAR, const double* AR,
+                               double* ring, double* force, const double* b, const double* lo, const double* hi,
+                               const double* ARinv, double* fprev, double* fmom, const double* Adiag,
+                               int* order, int* jdraw) {
+  const unsigned full = 0xffffffffu;
+  const DModel& m = d.m;
+  const int nv = m.sz.nv, lane = d.lane, k = lane & 3;
+  const int n4 = nefc & ~3, tail = nefc - n4, nq = n4 >> 2;
+  const double scale = 1 / (m.opt.meaninertia * (nv > 1 ? nv : 1));
+  Pcg32 rng{0, 1};
+  pcg32_next(rng);
+  uint64_t s0 = rng.state;
+  int iter = 0, nk = 0;
+  const int maxiter = m.opt.iterations;
+  while (iter < maxiter) {
+    double beta = 0;
+    if (iter > 0) beta = (double)(nk - 1) / (double)(nk + 2);
+    if (beta > 0) {
+      for (int i = lane; i < nefc; i += 32) {
+        const double fs = force[i];
+        double f = fs + beta * (fs - fprev[i]);
+        fprev[i] = fs;
+        f = dclip(f, lo[i], hi[i]);
+        force[i] = f;
+        fmom[i] = f;
+      }
+    } else {
+      for (int i = lane; i < nefc; i += 32) { fprev[i] = force[i]; fmom[i] = force[i]; }
+    }
+    // Fisher-Yates draws of this sweep (draw t serves position i = nefc-1-t), one per lane
+    for (int t = lane; t < nefc - 1; t += 32) {
+      const uint64_t old = pcg32_skip(s0, (uint32_t)t);
+      const uint32_t xs = (uint32_t)(((old >> 18u) ^ old) >> 27u), rot = (uint32_t)(old >> 59u);
+      const uint32_t out = (xs >> rot) | (xs << ((0u - rot) & 31));
+      const int i = nefc - 1 - t;
+      jdraw[i] = (int)(out % (uint32_t)(i + 1));
+    }
+    s0 = pcg32_skip(s0, (uint32_t)(nefc - 1));
+    __syncwarp();
+    if (lane == 0) {
+      for (int i = nefc - 1; i > 0; i--) {
+        const int j = jdraw[i];
+        const int t = order[i]; order[i] = order[j]; order[j] = t;
+      }
+    }
+    __syncwarp();
+    double p0 = 0, p1 = 0;
+    if (MODE == 1) {
+      for (int q = 0; q < 3 && q < nefc; q++) {
+        const double* g = gAR + order[q] * nefc;
+        for (int c = lane; c < nefc; c += 32) ring[q * nefc + c] = g[c];
+      }
+      if (3 < nefc) {
+        const double* g = gAR + order[3] * nefc;
+        if (lane < nefc) p0 = g[lane];
+        if (lane + 32 < nefc) p1 = g[lane + 32];
+      }
+      __syncwarp();
+    }
+    double impr = 0;
+    int inext = order[0];
+    const double* glane = gAR + lane;
+    asm volatile("" : "+l"(glane));   // keep the lane's AR base in registers (no per-row re-derivation)
+    for (int bi = 0; bi < nefc; bi++) {
+      const int i = inext;
+      inext = order[bi + 1 < nefc ? bi + 1 : bi];
+      const double* row = (MODE == 2) ? AR + i * nefc : ring + (bi & 3) * nefc;
+      const double bi_ = b[i], ainv = ARinv[i], ad = Adiag[i], l = lo[i], h = hi[i], old = force[i];
+      double r = 0;
+      {   // chain k of the mju_dot structure: nq = n4/4 terms for every lane (uniform trip count)
+        const double* rk = row + k;
+        const double* fk = force + k;
+#pragma unroll 4
+        for (int q = 0; q < nq; q++) r += rk[4 * q] * fk[4 * q];
+      }
+      const double v = r + __shfl_xor_sync(full, r, 2);
+      double res = v + __shfl_xor_sync(full, v, 1);
+      if (tail) {
+        double t = row[n4] * force[n4];
+        if (tail >= 2) t += row[n4 + 1] * force[n4 + 1];
+        if (tail == 3) t += row[n4 + 2] * force[n4 + 2];
+        res += t;
+      }
+      res = bi_ + res;
+      double f = old - res * ainv;
+      f = f < l ? l : (f > h ? h : f);
+      const double delta = f - old;
+      double change = 0.5 * delta * delta * ad + delta * res;
+      if (change > 1e-10) { f = old; change = 0; }
+      if (lane == 0) force[i] = f;
+      impr -= change;
+      if (MODE == 1 && bi + 3 < nefc) {
+        double* dst = ring + ((bi + 3) & 3) * nefc;
+        if (lane < nefc) dst[lane] = p0;
+        if (lane + 32 < nefc) dst[lane + 32] = p1;
+        if (bi + 4 < nefc) {
+          const double* g = glane + order[bi + 4] * nefc;
+          if (lane < nefc) p0 = g[0];
+          if (lane + 32 < nefc) p1 = g[32];
+        }
+      }
+      __syncwarp();
+    }
+    const double improvement = impr * scale;
+    bool restart = false;
+    if (iter > 0) {   // serial-order sum of the per-row products, products formed one per lane
+      double q0 = 0, q1 = 0;
+      if (lane < nefc) q0 = (force[lane] - fmom[lane]) * (fmom[lane] - fprev[lane]);
+      if (lane + 32 < nefc) q1 = (force[lane + 32] - fmom[lane + 32]) * (fmom[lane + 32] - fprev[lane + 32]);
+      double dce = 0;
+      const int nlo = nefc < 32 ? nefc : 32;
+      for (int i = 0; i < nlo; i++) dce += __shfl_sync(full, q0, i);
+      for (int i = 32; i < nefc; i++) dce += __shfl_sync(full, q1, i - 32);
+      restart = dce < 0;
+    }
+    if (restart) nk = 0; else nk++;
+    iter++;
+    if (improvement < m.opt.tolerance) break;
+  }
+  return iter;
+}
+#endif
+
 MJB_HD void solve_pgs(const Env& d) {
   const DModel& m = d.m;
   const int nefc = d.nefc()[0], nf = d.nf()[0], njmax = m.sz.njmax;
   if (!nefc) return;
-  int mode = 0;
-  const int nord = (nefc + 1) / 2;   // doubles that hold the visit order (ints)
-  if (d.sm && (long)nefc * nefc + 7L * nefc + nord + 8 <= d.smcap) mode = 2;
-  else if (d.sm && nefc <= 64 && 11L * nefc + nord + 8 <= d.smcap) mode = 1;
   const double* gAR = d.efc_AR().p;
   int iter;
+#if defined(__CUDA_ARCH__)
+  int mode = 0;
+  const int nord = (nefc + 1) / 2;   // doubles that hold nefc ints
+  if (d.sm && d.nlane == 32 && nefc <= 64) {
+    if ((long)nefc * nefc + 8L * nefc + 2 * nord <= d.smcap) mode = 2;
+    else if (12L * nefc + 2 * nord <= d.smcap) mode = 1;
+  }
   if (mode) {
     double* v = d.sm;
     double* AR = nullptr; double* ring = nullptr;
     if (mode == 2) { AR = v; v += nefc * nefc; } else { ring = v; v += 4 * nefc; }
-    double* force = v; double* b = force + nefc; double* floss = b + nefc; double* ARinv = floss + nefc;
-    double* fprev = ARinv + nefc; double* fmom = fprev + nefc; double* Adiag = fmom + nefc; double* shared = Adiag + nefc;
-    int* order = (int*)(shared + 8);
+    double* force = v; double* b = force + nefc; double* lo = b + nefc; double* hi = lo + nefc; double* ARinv = hi + nefc;
+    double* fprev = ARinv + nefc; double* fmom = fprev + nefc; double* Adiag = fmom + nefc;
+    int* order = (int*)(Adiag + nefc);
+    int* jdraw = order + 2 * nord;
     const double* gf = d.efc_force().p; const double* gb = d.efc_b().p; const double* gfl = d.efc_frictionloss().p;
     if (mode == 2) { MJB_PFOR(i, nefc * nefc) AR[i] = gAR[i]; }
     MJB_PFOR(i, nefc) {
       const double f0 = gf[i];
-      force[i] = f0; fprev[i] = f0; b[i] = gb[i]; floss[i] = gfl[i];
+      force[i] = f0; fprev[i] = f0; b[i] = gb[i];
+      const double fl = gfl[i];
+      lo[i] = (i < nf) ? -fl : 0.0;
+      hi[i] = (i < nf) ? fl : HUGE_VAL;
       const double ai = 1 / gAR[(long)i * (nefc + 1)];
       ARinv[i] = ai;
       Adiag[i] = 1 / ai;    // the reference's Athis[0] = 1/ARinv
       order[i] = i;
     }
     MJB_PSYNC();
-    dual_state_ptr(d, force, floss, nefc, nf);
-    if (mode == 2) iter = pgs_sweeps<2>(d, nefc, nf, gAR, AR, ring, force, b, floss, ARinv, fprev, fmom, Adiag, shared, order);
-    else iter = pgs_sweeps<1>(d, nefc, nf, gAR, AR, ring, force, b, floss, ARinv, fprev, fmom, Adiag, shared, order);
+    if (mode == 2) iter = pgs_sweeps_warp<2>(d, nefc, nf, gAR, AR, ring, force, b, lo, hi, ARinv, fprev, fmom, Adiag, order, jdraw);
+    else iter = pgs_sweeps_warp<1>(d, nefc, nf, gAR, AR, ring, force, b, lo, hi, ARinv, fprev, fmom, Adiag, order, jdraw);
     MJB_PSYNC();
     double* gfo = d.efc_force().p;
     MJB_PFOR(i, nefc) gfo[i] = force[i];
-  } else {
+    MJB_PSYNC();
+    dual_state_ptr(d, gfo, gfl, nefc, nf);
+  } else
+#endif
+  {
     double* force = d.efc_force().p; const double* b = d.efc_b().p; const double* floss = d.efc_frictionloss().p;
     double* scr = d.scr_efc().p;
     double* ARinv = scr; double* fprev = scr + njmax; double* fmom = scr + 2 * (long)njmax; double* Adiag = scr + 3 * (long)njmax;

@@ -37,7 +37,7 @@ constexpr int kWarpsPerCta = 4;
 #ifndef MJB_CTAS_PER_SM
 #define MJB_CTAS_PER_SM 7   // 28 warps/SM: a 4096-env batch is resident in ONE wave on 148 SMs (needs <= 72 regs)
 #endif
-constexpr int kSmemPerWarp = 752;    // doubles = 5 KB: seven sweep vectors + a 4-row ring for nefc <= 64 (or all of AR for nefc <= 22)
+constexpr int kSmemPerWarp = 832;    // doubles = 6.5 KB: eight sweep vectors, order + draws, and a 4-row ring for nefc <= 64 (or all of AR for nefc <= 24)
 __global__ void __launch_bounds__(32 * kWarpsPerCta, MJB_CTAS_PER_SM) k_step_warp(DModel m, Batch b, int mask, int flags) {
   __shared__ double smem[kWarpsPerCta * kSmemPerWarp];
   const int w = threadIdx.x >> 5;
