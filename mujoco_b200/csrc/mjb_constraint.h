@@ -427,23 +427,22 @@ MJB_HD void dual_state(const Env& d) {
 
 // M * vec over the tree-sparse symmetric M (mju_mulSymVecSparse): one lane per output dof
 // res[i] = dotSparse(row i incl. diagonal) + sum over descendants k (ascending k) M(k,i)*vec[k]
+// res = M * vec (mj_mulM -> mju_mulSymVecSparse, engine_util_sparse.c): per output dof the order is
+// the diagonal term, the own-row off-diagonals from the last column to the first, then the rows of
+// the descendants in ascending order
 MJB_HD void mul_M(const Env& d, FD res, FD vec) {
   const DModel& m = d.m;
   FD M = d.M();
   MJB_PFOR(i, m.sz.nv) {
     const int adr = m.M_rowadr[i], nnz = m.M_rownnz[i];
-    double s = dot_sparse_ref(nnz, [&](int c) { return M[adr + c]; }, [&](int c) { return vec[m.M_colind[adr + c]]; });
+    double s = M[adr + nnz - 1] * vec[i];
+    for (int k = nnz - 2; k >= 0; k--) s += M[adr + k] * vec[m.M_colind[adr + k]];
     const int a0 = m.mt_adr[i], an = m.mt_adr[i + 1] - a0;
-    for (int c = an - 1; c >= 0; c--) {   // descendants in ASCENDING order
-      const double vk = vec[m.mt_dof[a0 + c]];
-      s += M[m.mt_qadr[a0 + c]] * vk;
-    }
+    for (int c = an - 1; c >= 0; c--) s += M[m.mt_qadr[a0 + c]] * vec[m.mt_dof[a0 + c]];
     res[i] = s;
   }
   MJB_PSYNC();
 }
-
-// ---- efc_b and solver start point (mj_fwdConstraint head + warmstart) ----------------------------
 MJB_HD void constraint_begin(const Env& d) {
   const DModel& m = d.m;
   const int nv = m.sz.nv, nefc = d.nefc()[0];

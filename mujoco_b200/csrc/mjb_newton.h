@@ -1,13 +1,412 @@
-// Newton solver of the batched mj_step path (primal), one environment per call.
-// Replaces reference src/engine/engine_solver.c mj_solPrimal / Newton :1095-2563.
+// Newton solver (primal) of the batched mj_step path for ONE environment, cooperative lanes.
+//
+// Replaces (reference file:line) src/engine/engine_solver.c: mjPrimalContext :979-1092,
+// PrimalUpdateConstraint :1370-1404, PrimalUpdateGrad/Mgrad :1407-1448, PrimalPrepare :1451-1524,
+// frictionCost/frictionCostDif :1536-1571, PrimalEval :1675-1822, updateBracket :1826-1853,
+// PrimalSearch :1856-2052, MakeHessian (dense) :2133-2141, FactorizeHessian (dense) :2196-2208,
+// HessianIncremental :2285-2340, mj_solPrimal (Newton branch) :2344-2563; and the dense Cholesky
+// kernels of src/engine/engine_util_solve.c: mju_cholFactor :33-70, mju_cholSolve :74-100,
+// mju_cholUpdate :104-147; mju_sqrMatTD_impl (engine_util_blas.c), mju_addToSymSparse and
+// mju_mulSymVecSparse (engine_util_sparse.c).
+//
+// Scope: dense Jacobian (nv < 60), pyramidal cones, no equality rows, one kinematic tree (so the
+// constraint island, when islands are enabled, is the whole system and its dof / row order is the
+// global one: engine_island.c:455-650; only the cost scale differs, 1/trace(M) instead of
+// 1/(meaninertia*nv), engine_solver.c:2383-2394).
+//
+// Parallel structure: matrix-shaped work is spread over the lanes element by element (Hessian
+// elements, Cholesky column updates, Jacobian rows), every element keeping the reference's
+// accumulation order.  The scalar control flow of the line search and all order-sensitive scalar
+// sums are evaluated by every lane redundantly on identical data, so decisions are warp-uniform
+// without broadcasts.  The two triangular solves are inherently serial chains (lane 0).
 #pragma once
 #include "mjb_constraint.h"
 
 namespace mjb {
 
+struct LsPoint { double alpha, cost, d0, d1; };
+
+struct NewtonCtx {
+  int nv, nefc, nf;
+  FD J, Jaref, Jv, quad, Dq, Ma, Mv, grad, Mgrad, search, cholupd, L;
+  FD efcD, efcR, floss, qfs, qas, qacc;
+  FI state, oldstate;
+  double quadGauss[3];
+  double scale, cost;
+  int lsiter;
+};
+
+// Huber cost of a friction row and its difference between two points
+MJB_HD double friction_cost(double x, double f, double Rf, double D) {
+  if (-Rf < x && x < Rf) return 0.5 * D * x * x;
+  else if (x <= -Rf) return f * (-0.5 * Rf - x);
+  else return f * (-0.5 * Rf + x);
+}
+MJB_HD double friction_cost_dif(double start, double x, double f, double Rf, double D) {
+  const int s0 = (-Rf < start && start < Rf) ? 0 : (start <= -Rf ? -1 : 1);
+  const int s1 = (-Rf < x && x < Rf) ? 0 : (x <= -Rf ? -1 : 1);
+  if (s0 == 0 && s1 == 0) return 0.5 * D * (x - start) * (x + start);
+  if (s0 == -1 && s1 == -1) return f * (start - x);
+  if (s0 == 1 && s1 == 1) return f * (x - start);
+  return friction_cost(x, f, Rf, D) - friction_cost(start, f, Rf, D);
+}
+
+// efc_force / efc_state / cost from Jaref, qfrc_constraint = J' force, plus the Gauss term
+MJB_HD void newton_update_constraint(const Env& d, NewtonCtx& c) {
+  double s = constraint_update(d, c.Jaref, true);
+  MJB_PSYNC();
+  double gauss = 0;
+  for (int i = 0; i < c.nv; i++) gauss += 0.5 * (c.Ma[i] - c.qfs[i]) * (c.qacc[i] - c.qas[i]);
+  c.quadGauss[0] = gauss;
+  s += gauss;
+  c.cost = s;
+}
+
+MJB_HD void newton_update_grad(const Env& d, NewtonCtx& c) {
+  FD qfc = d.qfrc_constraint();
+  MJB_PFOR(i, c.nv) c.grad[i] = c.Ma[i] - c.qfs[i] - qfc[i];
+  MJB_PSYNC();
+}
+
+// in-place dense Cholesky of the lower triangle; returns the rank (uniform)
+MJB_HD int chol_factor(const Env& d, FD mat, int n, double mindiag) {
+  int rank = n;
+  for (int j = 0; j < n; j++) {
+    double tmp = mat[j * (n + 1)];
+    if (j) tmp -= dot_ref(j, [&](int k) { return mat[j * n + k]; }, [&](int k) { return mat[j * n + k]; });
+    const bool deficient = tmp < mindiag;
+    if (deficient) { tmp = mindiag; rank--; }
+    const double diag = sqrt(tmp);
+    MJB_PSYNC();
+    MJB_LANE0 mat[j * (n + 1)] = diag;
+    if (deficient) {
+      MJB_PFOR(i_, n - 1 - j) mat[(j + 1 + i_) * n + j] = 0;
+    } else {
+      const double inv = 1 / diag;
+      MJB_PFOR(i_, n - 1 - j) {
+        const int i = j + 1 + i_;
+        mat[i * n + j] = (mat[i * n + j] - dot_ref(j, [&](int k) { return mat[i * n + k]; },
+                                                   [&](int k) { return mat[j * n + k]; })) * inv;
+      }
+    }
+    MJB_PSYNC();
+  }
+  return rank;
+}
+
+// res = (L L')^-1 vec: forward then backward substitution, serial chains
+MJB_HD void chol_solve(const Env& d, FD res, FD mat, FD vec, int n) {
+  MJB_LANE0 {
+    for (int i = 0; i < n; i++) res[i] = vec[i];
+    for (int i = 0; i < n; i++) {
+      if (i) res[i] -= dot_ref(i, [&](int k) { return mat[i * n + k]; }, [&](int k) { return res[k]; });
+      res[i] /= mat[i * (n + 1)];
+    }
+    for (int i = n - 1; i >= 0; i--) {
+      double r = res[i];
+      for (int j = i + 1; j < n; j++) r -= mat[j * n + i] * res[j];
+      res[i] = r / mat[i * (n + 1)];
+    }
+  }
+  MJB_PSYNC();
+}
+
+// rank-one update (plus) or downdate of the factor with x (destroyed); returns the rank (uniform)
+MJB_HD int chol_update(const Env& d, FD mat, FD x, int n, bool plus) {
+  int rank = n;
+  for (int k = 0; k < n; k++) {
+    const double xk = x[k];
+    if (xk != 0) {
+      const double Lkk = mat[k * (n + 1)];
+      double tmp = Lkk * Lkk + (plus ? xk * xk : -xk * xk);
+      if (tmp < kMinVal) { tmp = kMinVal; rank--; }
+      const double r = sqrt(tmp);
+      const double cc = r / Lkk;
+      const double cinv = 1 / cc;
+      const double s = xk / Lkk;
+      MJB_PSYNC();
+      MJB_LANE0 mat[k * (n + 1)] = r;
+      MJB_PFOR(i_, n - 1 - k) {
+        const int i = k + 1 + i_;
+        double mv = mat[i * n + k];
+        mv = plus ? (mv + s * x[i]) * cinv : (mv - s * x[i]) * cinv;
+        mat[i * n + k] = mv;
+        x[i] = cc * x[i] - s * mv;
+      }
+      MJB_PSYNC();
+    }
+  }
+  return rank;
+}
+
+// L <- lower triangle of H = M + J' diag(Dq) J, then its Cholesky factor
+MJB_HD void newton_factorize(const Env& d, NewtonCtx& c, bool recompute) {
+  const DModel& m = d.m;
+  const int nv = c.nv, nefc = c.nefc;
+  if (recompute) {
+    MJB_PFOR(i, nefc) c.Dq[i] = (c.state[i] == STATE_QUADRATIC) ? c.efcD[i] : 0.0;
+    MJB_PSYNC();
+    MJB_PFOR(e, nv * nv) {
+      const int i = e / nv, k = e - i * nv;
+      double s = 0;
+      if (k <= i) {
+        for (int j = 0; j < nefc; j++) {
+          const double dj = c.Dq[j];
+          if (dj != 0) {
+            const double t = c.J[j * nv + i];
+            if (t != 0) s += c.J[j * nv + k] * (t * dj);
+          }
+        }
+      }
+      c.L[e] = s;
+    }
+    MJB_PSYNC();
+    FD M = d.M();
+    MJB_PFOR(i, nv) {
+      const int adr = m.M_rowadr[i], nnz = m.M_rownnz[i];
+      for (int a = 0; a < nnz; a++) c.L[i * nv + m.M_colind[adr + a]] += M[adr + a];
+    }
+    MJB_PSYNC();
+  }
+  chol_factor(d, c.L, nv, kMinVal);
+}
+
+MJB_HD void newton_update_mgrad(const Env& d, NewtonCtx& c) { chol_solve(d, c.Mgrad, c.L, c.grad, c.nv); }
+
+// rank-one updates of the factor for the rows whose QUADRATIC membership changed
+MJB_HD void newton_hessian_incremental(const Env& d, NewtonCtx& c) {
+  const int nv = c.nv, nefc = c.nefc;
+  for (int i = 0; i < nefc; i++) {
+    const bool was = c.oldstate[i] == STATE_QUADRATIC, is = c.state[i] == STATE_QUADRATIC;
+    if (was == is) continue;
+    const double sq = sqrt(c.efcD[i]);
+    MJB_PFOR(k, nv) c.cholupd[k] = c.J[i * nv + k] * sq;
+    MJB_PSYNC();
+    const int rank = chol_update(d, c.L, c.cholupd, nv, is);
+    if (rank < nv) {
+      newton_factorize(d, c, true);
+      return;
+    }
+  }
+}
+
+// line-search objective and its first two derivatives at p.alpha (cost relative to alpha = 0)
+MJB_HD void newton_eval(NewtonCtx& c, LsPoint& p) {
+  const double alpha = p.alpha;
+  double cost = 0, d0 = 0, d1 = 0;
+  double q0 = 0, q1 = c.quadGauss[1], q2 = c.quadGauss[2];
+  for (int i = 0; i < c.nefc; i++) {
+    if (i < c.nf) {
+      const double start = c.Jaref[i], dir = c.Jv[i];
+      const double x = start + alpha * dir;
+      const double f = c.floss[i], D = c.efcD[i];
+      const double Rf = c.efcR[i] * f;
+      cost += friction_cost_dif(start, x, f, Rf, D);
+      if (-Rf < x && x < Rf) { d0 += D * x * dir; d1 += D * dir * dir; }
+      else if (x <= -Rf) d0 += -f * dir;
+      else d0 += f * dir;
+      continue;
+    }
+    const double start = c.Jaref[i];
+    const double x = start + alpha * c.Jv[i];
+    const double cost0 = start < 0 ? c.quad[3 * i] : 0;
+    if (x < 0) {
+      q0 += c.quad[3 * i] - cost0;
+      q1 += c.quad[3 * i + 1];
+      q2 += c.quad[3 * i + 2];
+    } else {
+      cost -= cost0;
+    }
+  }
+  cost += alpha * alpha * q2 + alpha * q1 + q0;
+  d0 += 2 * alpha * q2 + q1;
+  d1 += 2 * q2;
+  if (d1 <= 0) d1 = kMinVal;
+  p.cost = cost; p.d0 = d0; p.d1 = d1;
+  c.lsiter++;
+}
+
+MJB_HD int newton_update_bracket(NewtonCtx& c, LsPoint& p, const LsPoint* cand, LsPoint& pnext) {
+  int flag = 0;
+  for (int i = 0; i < 3; i++) {
+    if (p.d0 < 0 && cand[i].d0 < 0 && p.d0 < cand[i].d0) { p = cand[i]; flag = 1; }
+    else if (p.d0 > 0 && cand[i].d0 > 0 && p.d0 > cand[i].d0) { p = cand[i]; flag = 2; }
+  }
+  if (flag) {
+    pnext.alpha = p.alpha - p.d0 / p.d1;
+    newton_eval(c, pnext);
+  }
+  return flag;
+}
+
+// exact line search along `search`; returns the step and the cost improvement
+MJB_HD double newton_search(const Env& d, NewtonCtx& c, double tolerance, int ls_iterations, double& improvement) {
+  const int nv = c.nv, nefc = c.nefc;
+  c.lsiter = 0;
+  improvement = 0;
+  const double snorm = sqrt(dot_ref(nv, [&](int i) { return c.search[i]; }, [&](int i) { return c.search[i]; }));
+  if (snorm < kMinVal) return 0;
+  const double gtol = tolerance * snorm / c.scale;
+
+  mul_M(d, c.Mv, c.search);
+  mul_jac_vec(d, c.Jv, c.search);
+
+  // quadratic polynomials (PrimalPrepare)
+  c.quadGauss[1] = dot_ref(nv, [&](int i) { return c.search[i]; }, [&](int i) { return c.Ma[i]; }) -
+                   dot_ref(nv, [&](int i) { return c.qfs[i]; }, [&](int i) { return c.search[i]; });
+  c.quadGauss[2] = 0.5 * dot_ref(nv, [&](int i) { return c.search[i]; }, [&](int i) { return c.Mv[i]; });
+  MJB_PFOR(i, nefc) {
+    const double D = c.efcD[i], ja = c.Jaref[i], jv = c.Jv[i];
+    const double DJ0 = D * ja;
+    c.quad[3 * i] = ja * DJ0 * 0.5;
+    c.quad[3 * i + 1] = jv * DJ0;
+    c.quad[3 * i + 2] = jv * D * jv * 0.5;
+  }
+  MJB_PSYNC();
+
+  LsPoint p0, p1, p2, pmid, p1next, p2next;
+  p0.alpha = 0;
+  newton_eval(c, p0);
+  p1.alpha = p0.alpha - p0.d0 / p0.d1;
+  newton_eval(c, p1);
+  if (fabs(p1.d0) < gtol && (p1.alpha == 0 || p1.cost < 0)) {
+    improvement = -p1.cost;
+    return p1.alpha;
+  }
+  const int dir = (p1.d0 < 0 ? +1 : -1);
+
+  // one-sided search
+  p2 = p0;
+  while (p1.d0 * dir <= -gtol && c.lsiter < ls_iterations) {
+    p2 = p1;
+    p1.alpha -= p1.d0 / p1.d1;
+    newton_eval(c, p1);
+    if (fabs(p1.d0) < gtol && p1.cost < 0) {
+      improvement = -p1.cost;
+      return p1.alpha;
+    }
+  }
+  if (c.lsiter >= ls_iterations) {
+    improvement = -p1.cost;
+    return p1.alpha;
+  }
+
+  // bracketed search
+  p2next = p1;
+  p1next.alpha = p1.alpha - p1.d0 / p1.d1;
+  newton_eval(c, p1next);
+  while (c.lsiter < ls_iterations) {
+    pmid.alpha = 0.5 * (p1.alpha + p2.alpha);
+    newton_eval(c, pmid);
+    LsPoint cand[3] = {p1next, p2next, pmid};
+    double bestcost = 0;
+    int bestind = -1;
+    for (int i = 0; i < 3; i++) {
+      if (fabs(cand[i].d0) < gtol && (bestind == -1 || cand[i].cost < bestcost)) {
+        bestcost = cand[i].cost;
+        bestind = i;
+      }
+    }
+    if (bestind >= 0) {
+      improvement = -cand[bestind].cost;
+      return cand[bestind].alpha;
+    }
+    const int b1 = newton_update_bracket(c, p1, cand, p1next);
+    const int b2 = newton_update_bracket(c, p2, cand, p2next);
+    if (!b1 && !b2) {
+      improvement = -pmid.cost;
+      return pmid.alpha;
+    }
+  }
+  if (p1.cost <= p2.cost && p1.cost < 0) { improvement = -p1.cost; return p1.alpha; }
+  else if (p2.cost <= p1.cost && p2.cost < 0) { improvement = -p2.cost; return p2.alpha; }
+  return 0;
+}
+
 MJB_HD void solve_newton(const Env& d) {
-  // implemented in a later milestone; the host refuses solver=Newton until then
-  (void)d;
+  const DModel& m = d.m;
+  const int nv = m.sz.nv, nefc = d.nefc()[0], njmax = m.sz.njmax;
+  if (!nefc) return;
+  NewtonCtx c;
+  c.nv = nv; c.nefc = nefc; c.nf = d.nf()[0];
+  c.J = d.efc_J();
+  FD se = d.nwt_efc(), sv = d.nwt_nv();
+  c.Jaref = se; c.Jv = se + njmax; c.quad = se + 2 * (long)njmax; c.Dq = se + 5 * (long)njmax;
+  c.Ma = sv; c.Mv = sv + nv; c.grad = sv + 2 * nv; c.Mgrad = sv + 3 * nv; c.search = sv + 4 * nv; c.cholupd = sv + 5 * nv;
+  c.L = d.nwt_L();
+  c.efcD = d.efc_D(); c.efcR = d.efc_R(); c.floss = d.efc_frictionloss();
+  c.qfs = d.qfrc_smooth(); c.qas = d.qacc_smooth(); c.qacc = d.qacc();
+  c.state = d.efc_state(); c.oldstate = d.nwt_state();
+  const double tol = m.opt.tolerance;
+
+  mul_M(d, c.Ma, c.qacc);
+  mul_jac_vec(d, c.Jaref, c.qacc);
+  {
+    FD aref = d.efc_aref();
+    MJB_PFOR(i, nefc) c.Jaref[i] -= aref[i];
+    MJB_PSYNC();
+  }
+  newton_update_constraint(d, c);
+  newton_update_grad(d, c);
+
+  // cost scale: the island's (trace of M) when islands are enabled, the global one otherwise
+  if (!(m.opt.disableflags & DSBL_ISLAND)) {
+    FD M = d.M();
+    double tr = 0;
+    for (int i = 0; i < nv; i++) tr += M[m.M_rowadr[i] + m.M_rownnz[i] - 1];
+    c.scale = 1 / tr;
+  } else {
+    c.scale = 1 / (m.opt.meaninertia * (nv > 1 ? nv : 1));
+  }
+  const double scale = c.scale;
+
+  // convergence certificate with the M-preconditioned gradient
+  MJB_PFOR(i, nv) c.Mgrad[i] = c.grad[i];
+  MJB_PSYNC();
+  solve_LD(d, c.Mgrad, d.qLD(), d.qLDiagInv());
+  auto grad_dot_mgrad = [&]() { return dot_ref(nv, [&](int i) { return c.grad[i]; }, [&](int i) { return c.Mgrad[i]; }); };
+  auto grad_norm = [&]() { return sqrt(dot_ref(nv, [&](int i) { return c.grad[i]; }, [&](int i) { return c.grad[i]; })); };
+  const bool flg_gap = dmax(0.0, 0.5 * scale * grad_dot_mgrad()) < tol;
+  const bool flg_gradient = scale * grad_norm() < tol;
+  bool done = flg_gap && flg_gradient;
+  MJB_PSYNC();
+
+  if (!done) {
+    newton_factorize(d, c, true);
+    newton_update_mgrad(d, c);
+    done = flg_gradient && dmax(0.0, 0.5 * scale * grad_dot_mgrad()) < tol;
+  }
+  if (!done) {
+    MJB_PFOR(i, nv) c.search[i] = c.Mgrad[i] * -1;
+    MJB_PSYNC();
+  }
+
+  int iter = 0;
+  const int maxiter = m.opt.iterations;
+  while (!done && iter < maxiter) {
+    double ls_improvement;
+    const double alpha = newton_search(d, c, tol * m.opt.ls_tolerance, m.opt.ls_iterations, ls_improvement);
+    if (alpha == 0) break;
+    MJB_PSYNC();
+    MJB_PFOR(i, nv) { c.qacc[i] += c.search[i] * alpha; c.Ma[i] += c.Mv[i] * alpha; }
+    MJB_PFOR(i, nefc) { c.Jaref[i] += c.Jv[i] * alpha; c.oldstate[i] = c.state[i]; }
+    MJB_PSYNC();
+    newton_update_constraint(d, c);
+    newton_hessian_incremental(d, c);
+    newton_update_grad(d, c);
+    newton_update_mgrad(d, c);
+    const double improvement = scale * ls_improvement;
+    const double gradient = scale * grad_norm();
+    const double decrement = dmax(0.0, 0.5 * scale * grad_dot_mgrad());
+    iter++;
+    if ((improvement > 0 && improvement < tol) || gradient < tol || decrement < tol) break;
+    MJB_PSYNC();
+    MJB_PFOR(i, nv) c.search[i] = c.Mgrad[i] * -1;
+    MJB_PSYNC();
+  }
+  MJB_PSYNC();
+  MJB_LANE0 d.solver_niter()[0] += iter;
+  MJB_PSYNC();
 }
 
 }  // namespace mjb

@@ -18,19 +18,24 @@ RTOL_TRAJ = 1e-6      # north_star bound
 RTOL_TIGHT = 1e-9     # what this implementation is actually held to
 
 
-def test_forward_fields_match_oracle_pgs():
+SOLVERS = [pytest.param(mb.SOLVER_PGS, id="pgs"), pytest.param(mb.SOLVER_NEWTON, id="newton")]
+
+
+@pytest.mark.parametrize("solver", SOLVERS)
+def test_forward_fields_match_oracle(solver):
     assert available()
-    m, b, o = make_pair(HUMANOID, mb.SOLVER_PGS, nenv=8)
+    m, b, o = make_pair(HUMANOID, solver, nenv=8)
     states = perturbed_states(o, 8, seed=3, height=[0.25, 0.4, 0.9, 1.3])
     ctrl = np.random.default_rng(5).uniform(-1, 1, (8, o.size("nu")))
-    worst = compare_forward(b, o, states, ctrl, rtol=RTOL_TIGHT)
+    worst = compare_forward(b, o, states, ctrl, rtol=RTOL_TIGHT, check_dual=(solver == mb.SOLVER_PGS))
     print("worst rel err", worst)
 
 
-def test_golden_trajectory_pgs():
-    g = np.load(os.path.join(ROOT, "tests", "golden", "humanoid_pgs_traj.npz"))
+@pytest.mark.parametrize("solver,name", [(mb.SOLVER_PGS, "pgs"), (mb.SOLVER_NEWTON, "newton")])
+def test_golden_trajectory(solver, name):
+    g = np.load(os.path.join(ROOT, "tests", "golden", "humanoid_%s_traj.npz" % name))
     m = mb.Model(HUMANOID)
-    m.set_option("solver", mb.SOLVER_PGS)
+    m.set_option("solver", solver)
     b = mb.Batch(m, g["state0"].shape[0])
     out = b.rollout(g["state0"], g["ctrl"])
     ref = g["states"]
@@ -39,11 +44,12 @@ def test_golden_trajectory_pgs():
     assert rel < RTOL_TIGHT
 
 
-def test_rollout_100_steps_contact_rich_vs_oracle():
+@pytest.mark.parametrize("solver", SOLVERS)
+def test_rollout_100_steps_contact_rich_vs_oracle(solver):
     """64 envs dropped from low heights with random controls: contacts from step ~1; 100 steps"""
     assert available()
     nenv, nstep = 64, 100
-    m, b, o = make_pair(HUMANOID, mb.SOLVER_PGS, nenv=nenv)
+    m, b, o = make_pair(HUMANOID, solver, nenv=nenv)
     s0 = perturbed_states(o, nenv, seed=11, height=[0.2, 0.3, 0.5, 0.8], qvel_std=0.5, qpos_std=0.2)
     ctrl = np.random.default_rng(12).uniform(-1, 1, (nenv, nstep, o.size("nu")))
     out = b.rollout(s0, ctrl)
