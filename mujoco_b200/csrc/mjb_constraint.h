@@ -310,7 +310,7 @@ MJB_HD void mul_jacT_vec(const Env& d, FD res, FD vec) {
 MJB_HD void project_constraint(const Env& d) {
   const DModel& m = d.m;
   const int nefc = d.nefc()[0], nv = m.sz.nv;
-  if (!nefc || m.opt.solver != SOL_PGS) return;
+  if (!nefc || d.solver != SOL_PGS) return;
   FD J = d.efc_J(), Y = d.efc_Y(), AR = d.efc_AR(), qLD = d.qLD(), R = d.efc_R();
   FD sq = d.scr_nv();
   MJB_PFOR(i, nv) sq[i] = 1 / sqrt(qLD[m.M_rowadr[i] + m.M_rownnz[i] - 1]);
@@ -461,8 +461,8 @@ MJB_HD void constraint_begin(const Env& d) {
     mul_jac_vec(d, jar, ws);
     MJB_PFOR(i, nefc) jar[i] -= aref[i];
     MJB_PSYNC();
-    double cost_ws = constraint_update(d, jar, m.opt.solver != SOL_PGS);
-    if (m.opt.solver == SOL_PGS) {
+    double cost_ws = constraint_update(d, jar, d.solver != SOL_PGS);
+    if (d.solver == SOL_PGS) {
       FD AR = d.efc_AR(), ARf = d.scr_efc() + nefc;
       MJB_PFOR(r, nefc) ARf[r] = dot_ptr(AR.p + (long)r * nefc, force.p, nefc);
       MJB_PSYNC();

@@ -236,11 +236,11 @@ MJB_HD void stage_velocity(const Env& d) {
   constraint_begin(d);
 }
 MJB_HD void stage_solve(const Env& d) {
-  if (d.m.opt.solver == SOL_PGS) solve_pgs(d);
+  if (d.solver == SOL_PGS) solve_pgs(d);
   else solve_newton(d);
 }
 MJB_HD void stage_finish_forward(const Env& d) {
-  if (d.m.opt.solver == SOL_PGS) dual_finish(d);
+  if (d.solver == SOL_PGS) dual_finish(d);
 }
 MJB_HD void stage_integrate(const Env& d) {
   stage_finish_forward(d);

@@ -38,12 +38,15 @@ constexpr int kWarpsPerCta = 4;
 #define MJB_CTAS_PER_SM 7   // 28 warps/SM: a 4096-env batch is resident in ONE wave on 148 SMs (needs <= 72 regs)
 #endif
 constexpr int kSmemPerWarp = 832;    // doubles = 6.5 KB: eight sweep vectors, order + draws, and a 4-row ring for nefc <= 64 (or all of AR for nefc <= 24)
+// Specialised per constraint solver (template constant propagated through Env::solver) so that each
+// instantiation carries only its own solver's code and register pressure.
+template <int SOLVER>
 __global__ void __launch_bounds__(32 * kWarpsPerCta, MJB_CTAS_PER_SM) k_step_warp(DModel m, Batch b, int mask, int flags) {
   __shared__ double smem[kWarpsPerCta * kSmemPerWarp];
   const int w = threadIdx.x >> 5;
   const int e = blockIdx.x * kWarpsPerCta + w;
   if (e >= b.nenv) return;
-  run_env(m, b, e, mask, flags, threadIdx.x & 31, 32, smem + w * kSmemPerWarp, kSmemPerWarp);
+  run_env(m, b, e, mask, flags, threadIdx.x & 31, 32, smem + w * kSmemPerWarp, kSmemPerWarp, SOLVER);
 }
 
 // PERSISTENT ROLLOUT KERNEL: each warp advances its environment through nstep steps without any
@@ -182,7 +185,9 @@ int launch_fill_zero(const Batch& b, int is_int, long off, long cnt, void* s) {
 
 int launch_stages(const DModel& dm, const Batch& b, int mask, int flags, void* s) {
   if (b.warp_per_env) {
-    k_step_warp<<<(b.nenv + kWarpsPerCta - 1) / kWarpsPerCta, 32 * kWarpsPerCta, 0, (cudaStream_t)s>>>(dm, b, mask, flags);
+    const int grid = (b.nenv + kWarpsPerCta - 1) / kWarpsPerCta;
+    if (dm.opt.solver == SOL_PGS) k_step_warp<SOL_PGS><<<grid, 32 * kWarpsPerCta, 0, (cudaStream_t)s>>>(dm, b, mask, flags);
+    else k_step_warp<SOL_NEWTON><<<grid, 32 * kWarpsPerCta, 0, (cudaStream_t)s>>>(dm, b, mask, flags);
   } else {
     k_step_lane<<<nblocks(b, 32), 32, 0, (cudaStream_t)s>>>(dm, b, mask, flags);
   }

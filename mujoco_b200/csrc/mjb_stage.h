@@ -29,9 +29,10 @@ MJB_HD void run_stage_mask(const Env& d, int mask, int flags) {
 // flags: bit0 = part of mj_step (qpos/qvel checks), bit1 = skip environments that raised a warning.
 // sm/smcap: optional per-warp shared-memory scratch (doubles) used by the latency-critical loops.
 MJB_HD void run_env(const DModel& m, const Batch& b, int e, int mask, int flags, int lane, int nlane,
-                    double* sm, int smcap) {
+                    double* sm, int smcap, int solver = -1) {
   Env d(m, b, e, lane, nlane);
   d.sm = sm; d.smcap = smcap;
+  d.solver = solver < 0 ? m.opt.solver : solver;
   if ((flags & 2) && env_has_warning(d)) return;   // rollout: a warned env stops stepping (uniform per env)
   run_stage_mask(d, mask, flags);
 }
@@ -42,6 +43,7 @@ MJB_HD void run_env_rollout(const DModel& m, const Batch& b, int e, int nstep, c
                             int nstate, int lane, int nlane, double* sm, int smcap) {
   Env d(m, b, e, lane, nlane);
   d.sm = sm; d.smcap = smcap;
+  d.solver = m.opt.solver;
   const int nu = m.sz.nu, nq = m.sz.nq, nv = m.sz.nv;
   for (int t = 0; t < nstep; t++) {
     if (ctrl) {

@@ -213,6 +213,7 @@ struct Env {
   int* hi;           // ints
   double* sm = nullptr;   // per-warp shared-memory scratch (fused kernel only) and its capacity in doubles
   int smcap = 0;
+  int solver = -1;   // constraint solver; a compile-time constant in the specialised fused kernels
   MJB_HD Env(const DModel& m_, const Batch& b_, int e_, int lane_ = 0, int nlane_ = 1)
       : m(m_), b(b_), e(e_), lane(lane_), nlane(nlane_) {
     hd = b.dbl + (size_t)e * b.dpitch;
