@@ -19,6 +19,7 @@ from oracle_util import Oracle  # noqa: E402
 REF = os.environ.get("MJB_REFERENCE", "/root/reference")
 MODELS = {
     "humanoid": os.path.join(REF, "model/humanoid/humanoid.xml"),
+    "ant": os.path.join(ROOT, "models", "ant.xml"),          # authored here (BASELINE config 3)
 }
 
 
@@ -34,8 +35,8 @@ def main():
         o.save_mjb(os.path.join(ROOT, "models", name + ".mjb"))
         print("wrote models/%s.mjb" % name)
     # golden trajectories: humanoid, PGS + Euler (BASELINE config 2), 4 envs x 100 steps, random ctrl
-    for solver, tag in ((0, "pgs"), (2, "newton")):
-        o = Oracle(MODELS["humanoid"])
+    for model, solver, tag in (("humanoid", 0, "pgs"), ("humanoid", 2, "newton"), ("ant", 2, "newton")):
+        o = Oracle(MODELS[model])
         o.set_opt("solver", solver)
         nb, ns = 4, 100
         nu = o.size("nu")
@@ -43,9 +44,9 @@ def main():
         o.reset()
         s0 = np.tile(o.get_state(), (nb, 1))
         states, stats, _ = o.rollout(s0, ctrl, nthread=1)
-        np.savez_compressed(os.path.join(ROOT, "tests", "golden", "humanoid_%s_traj.npz" % tag),
+        np.savez_compressed(os.path.join(ROOT, "tests", "golden", "%s_%s_traj.npz" % (model, tag)),
                             state0=s0, ctrl=ctrl, states=states, stats=stats)
-        print("wrote tests/golden/humanoid_%s_traj.npz" % tag, "mean ncon/nefc/niter per step:",
+        print("wrote tests/golden/%s_%s_traj.npz" % (model, tag), "mean ncon/nefc/niter per step:",
               stats[:, :3].mean(0) / ns)
 
 

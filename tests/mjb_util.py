@@ -10,6 +10,7 @@ from oracle_util import Oracle
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 HOSTEMU = os.path.join(ROOT, "tests", "hostemu", "libmjb_hostemu.so")
 HUMANOID = os.path.join(ROOT, "models", "humanoid.mjb")
+ANT = os.path.join(ROOT, "models", "ant.mjb")
 
 _hostemu = None
 

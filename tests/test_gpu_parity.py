@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 
 import mujoco_b200 as mb
-from mjb_util import HUMANOID, ROOT, compare_forward, make_pair, perturbed_states
+from mjb_util import ANT, HUMANOID, ROOT, compare_forward, make_pair, perturbed_states
 from oracle_util import Oracle, available
 
 pytestmark = pytest.mark.gpu
@@ -31,10 +31,11 @@ def test_forward_fields_match_oracle(solver):
     print("worst rel err", worst)
 
 
-@pytest.mark.parametrize("solver,name", [(mb.SOLVER_PGS, "pgs"), (mb.SOLVER_NEWTON, "newton")])
-def test_golden_trajectory(solver, name):
-    g = np.load(os.path.join(ROOT, "tests", "golden", "humanoid_%s_traj.npz" % name))
-    m = mb.Model(HUMANOID)
+@pytest.mark.parametrize("model,solver,name", [("humanoid", mb.SOLVER_PGS, "pgs"), ("humanoid", mb.SOLVER_NEWTON, "newton"),
+                                               ("ant", mb.SOLVER_NEWTON, "newton")])
+def test_golden_trajectory(model, solver, name):
+    g = np.load(os.path.join(ROOT, "tests", "golden", "%s_%s_traj.npz" % (model, name)))
+    m = mb.Model(os.path.join(ROOT, "models", model + ".mjb"))
     m.set_option("solver", solver)
     b = mb.Batch(m, g["state0"].shape[0])
     out = b.rollout(g["state0"], g["ctrl"])
@@ -81,6 +82,46 @@ def test_batch_4096_consistency():
     assert (b.warnings() == 0).all()
     for r in range(1, nenv // 64):
         assert np.array_equal(out[:64], out[64 * r:64 * (r + 1)])
+    if available():
+        ref, _, _ = o.rollout(s64, c64, nthread=os.cpu_count() or 1)
+        rel = np.abs(out[:64] - ref).max() / max(1.0, np.abs(ref).max())
+        assert rel < RTOL_TIGHT
+
+
+@pytest.mark.parametrize("solver", SOLVERS)
+def test_ant_rollout_vs_oracle(solver):
+    """BASELINE config 3 model (ant, native solver Newton): forward fields + 150-step rollout"""
+    assert available()
+    m, b, o = make_pair(ANT, solver, nenv=32)
+    states = perturbed_states(o, 32, seed=4, height=[0.3, 0.45, 0.6, 0.9], qpos_std=0.2)
+    ctrl = np.random.default_rng(6).uniform(-1.5, 1.5, (32, o.size("nu")))
+    compare_forward(b, o, states, ctrl, rtol=RTOL_TIGHT, check_dual=(solver == mb.SOLVER_PGS))
+    nstep = 150
+    s0 = perturbed_states(o, 32, seed=14, height=[0.35, 0.5, 0.75], qvel_std=0.5, qpos_std=0.15)
+    c = np.random.default_rng(15).uniform(-1, 1, (32, nstep, o.size("nu")))
+    out = b.rollout(s0, c)
+    ref, stats, _ = o.rollout(s0, c, nthread=os.cpu_count() or 1)
+    assert stats[:, 3].sum() == 0 and (b.warnings() == 0).all()
+    rel = (np.abs(out - ref) / np.maximum(1.0, np.abs(ref).max(axis=(0, 1)))).max()
+    print("ant rollout rel err %.3e" % rel)
+    assert rel < RTOL_TIGHT
+
+
+def test_ant_batch_65536_newton():
+    """BASELINE config 3 size: 65536 ant envs, Newton; replicas of 64 seeded envs agree bit-for-bit and with
+    the oracle"""
+    nenv, nstep = 65536, 10
+    m = mb.Model(ANT)
+    m.set_option("solver", mb.SOLVER_NEWTON)
+    b = mb.Batch(m, nenv)
+    o = Oracle(ANT)
+    o.set_opt("solver", 2)
+    s64 = perturbed_states(o, 64, seed=41, height=[0.4, 0.55, 0.75], qpos_std=0.1)
+    c64 = np.random.default_rng(42).uniform(-1, 1, (64, nstep, o.size("nu")))
+    out = b.rollout(np.tile(s64, (nenv // 64, 1)), np.tile(c64, (nenv // 64, 1, 1)))
+    assert np.isfinite(out).all() and (b.warnings() == 0).all()
+    blocks = out.reshape(nenv // 64, 64, nstep, -1)
+    assert (blocks == blocks[0]).all()
     if available():
         ref, _, _ = o.rollout(s64, c64, nthread=os.cpu_count() or 1)
         rel = np.abs(out[:64] - ref).max() / max(1.0, np.abs(ref).max())

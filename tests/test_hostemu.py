@@ -10,7 +10,7 @@ import numpy as np
 import pytest
 
 import mujoco_b200 as mb
-from mjb_util import HOSTEMU, HUMANOID, ROOT, compare_forward, hostemu_lib, make_pair, perturbed_states
+from mjb_util import ANT, HOSTEMU, HUMANOID, ROOT, compare_forward, hostemu_lib, make_pair, perturbed_states
 from oracle_util import available
 
 pytestmark = pytest.mark.skipif(not (available() and os.path.exists(HOSTEMU)), reason="oracle or hostemu not built")
@@ -24,10 +24,11 @@ def test_forward_every_field_bit_exact(solver):
     compare_forward(b, o, states, ctrl, rtol=0, exact=True, check_dual=(solver == mb.SOLVER_PGS))
 
 
-@pytest.mark.parametrize("tag,solver", [("pgs", mb.SOLVER_PGS), ("newton", mb.SOLVER_NEWTON)])
-def test_golden_trajectory_bit_exact(tag, solver):
-    g = np.load(os.path.join(ROOT, "tests", "golden", "humanoid_%s_traj.npz" % tag))
-    m = mb.Model(HUMANOID, library=hostemu_lib())
+@pytest.mark.parametrize("model,tag,solver", [("humanoid", "pgs", mb.SOLVER_PGS), ("humanoid", "newton", mb.SOLVER_NEWTON),
+                                              ("ant", "newton", mb.SOLVER_NEWTON)])
+def test_golden_trajectory_bit_exact(model, tag, solver):
+    g = np.load(os.path.join(ROOT, "tests", "golden", "%s_%s_traj.npz" % (model, tag)))
+    m = mb.Model(os.path.join(ROOT, "models", model + ".mjb"), library=hostemu_lib())
     m.set_option("solver", solver)
     b = mb.Batch(m, g["state0"].shape[0])
     out = b.rollout(g["state0"], g["ctrl"])
@@ -43,6 +44,24 @@ def test_contact_rich_rollout_bit_exact(solver):
     out = b.rollout(s0, ctrl)
     ref, stats, _ = o.rollout(s0, ctrl, nthread=4)
     assert stats[:, 0].mean() / nstep > 1        # contacts present most of the time
+    assert np.array_equal(out, ref)
+
+
+@pytest.mark.parametrize("solver", [mb.SOLVER_NEWTON, mb.SOLVER_PGS])
+def test_ant_forward_and_rollout_bit_exact(solver):
+    """BASELINE config 3 model (models/ant.xml: free root + 4 legs x 2 hinges, condim-3 floor contacts with
+    margin, armature, gear-150 motors); native solver Newton"""
+    m, b, o = make_pair(ANT, solver, library=hostemu_lib(), nenv=8)
+    states = perturbed_states(o, 8, seed=4, height=[0.3, 0.45, 0.6, 0.9], qpos_std=0.2)
+    ctrl = np.random.default_rng(6).uniform(-1.5, 1.5, (8, o.size("nu")))
+    compare_forward(b, o, states, ctrl, rtol=0, exact=True, check_dual=(solver == mb.SOLVER_PGS))
+    nenv, nstep = 8, 150
+    s0 = perturbed_states(o, nenv, seed=14, height=[0.35, 0.5, 0.75], qvel_std=0.5, qpos_std=0.15)
+    c = np.random.default_rng(15).uniform(-1, 1, (nenv, nstep, o.size("nu")))
+    out = b.rollout(s0, c)
+    ref, stats, _ = o.rollout(s0, c, nthread=4)
+    assert stats[:, 0].mean() / nstep > 0.2      # floor contacts on a good share of the steps
+    assert stats[:, 3].sum() == 0
     assert np.array_equal(out, ref)
 
 
