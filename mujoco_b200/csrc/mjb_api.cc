@@ -221,8 +221,21 @@ int mjb_get_state(mjbBatch* B, double* state, unsigned int sig) {
 }
 
 // ---- stepping --------------------------------------------------------------------------------------
-static int run_step(mjbBatch* B, int flags) {   // all four stages of mj_step in ONE fused launch
-  return backend::launch_stages(B->dm, B->b, 0xF, flags | 1, B->stream);
+// one mj_step of every environment.  skip_warned: rollout rule (environments carrying a warning do
+// not step).  Euler: all four stages in ONE fused launch.  RK4 (mj_RungeKutta): forward + acceleration
+// check, then three (phase, forward) pairs and the final combination = 8 launches.
+static int run_step(mjbBatch* B, bool skip_warned) {
+  const int first = 1 | (skip_warned ? 2 : 0), later = skip_warned ? 4 : 0;
+  if (B->hm.dm.opt.integrator == INT_RK4) {
+    int rc = backend::launch_stages(B->dm, B->b, 0x7 | 32, first, B->stream);
+    for (int phase = 1; phase <= 3 && !rc; phase++) {
+      rc = backend::launch_rk4(B->dm, B->b, phase, later, B->stream);
+      if (!rc) rc = backend::launch_stages(B->dm, B->b, 0x17, later, B->stream);
+    }
+    if (!rc) rc = backend::launch_rk4(B->dm, B->b, 4, later, B->stream);
+    return rc;
+  }
+  return backend::launch_stages(B->dm, B->b, 0xF, first, B->stream);
 }
 
 int mjb_forward(mjbBatch* B) {
@@ -234,7 +247,7 @@ int mjb_forward(mjbBatch* B) {
 int mjb_step(mjbBatch* B, int nstep) {
   if (!B || nstep < 0) return fail(MJB_ERR_ARG, "mjb_step: bad arguments");
   for (int t = 0; t < nstep; t++)
-    if (int rc = run_step(B, 0)) return rc;
+    if (int rc = run_step(B, false)) return rc;
   return backend::sync(B->stream);
 }
 
@@ -285,7 +298,7 @@ int mjb_rollout(mjbBatch* B, int nstep, unsigned int control_spec, const double*
   int rc = 0;
   for (int t = 0; t < nstep && !rc; t++) {
     if (d_control) rc = backend::launch_set_control(B->dm, B->b, d_control, nstep, t, control_spec, ncontrol, B->stream);
-    if (!rc) rc = backend::launch_stages(B->dm, B->b, 0xF, 1 | 2, B->stream);
+    if (!rc) rc = run_step(B, true);
     if (d_state && !rc) rc = backend::launch_get_state(B->dm, B->b, d_state, nstep, t, nstate, B->stream);
   }
   if (!rc && d_state) rc = backend::d2h(state, d_state, sbytes, B->stream);
@@ -306,7 +319,7 @@ int mjb_step_host(mjbBatch* B, const double* ctrl, double* state_out) {
   }
   int rc = backend::h2d(B->io_ctrl, ctrl, (size_t)nenv * nu * sizeof(double), B->stream);
   if (!rc) rc = backend::launch_set_control(B->dm, B->b, B->io_ctrl, 1, 0, ST_CTRL, nu, B->stream);
-  if (!rc) rc = backend::launch_stages(B->dm, B->b, 0xF, 1, B->stream);
+  if (!rc) rc = run_step(B, false);
   if (!rc) rc = backend::launch_get_state(B->dm, B->b, B->io_state, 1, 0, nstate, B->stream);
   if (!rc) rc = backend::d2h(state_out, B->io_state, (size_t)nenv * nstate * sizeof(double), B->stream);
   if (!rc) rc = backend::sync(B->stream);
@@ -321,11 +334,11 @@ int mjb_rollout_device(mjbBatch* B, int nstep, const double* d_ctrl, double* d_s
   // ~1 MB of straight-line SASS no longer fits the instruction caches); MJB_PERSISTENT=1 selects it
   static int persistent = -1;
   if (persistent < 0) persistent = getenv("MJB_PERSISTENT") ? 1 : 0;
-  if (persistent && nstep) return backend::launch_rollout_native(B->dm, B->b, d_ctrl, d_state, nstep, nstate, B->stream);
+  if (persistent && nstep && B->hm.dm.opt.integrator == INT_EULER) return backend::launch_rollout_native(B->dm, B->b, d_ctrl, d_state, nstep, nstate, B->stream);
   int rc = 0;
   for (int t = 0; t < nstep && !rc; t++) {
     if (d_ctrl) rc = backend::launch_set_control_native(B->dm, B->b, d_ctrl, t, B->stream);
-    if (!rc) rc = backend::launch_stages(B->dm, B->b, 0xF, 1, B->stream);
+    if (!rc) rc = run_step(B, false);
     if (d_state && !rc) rc = backend::launch_get_state_native(B->dm, B->b, d_state, t, nstate, B->stream);
   }
   return rc;   // asynchronous: caller synchronises on mjb_stream()

@@ -24,6 +24,7 @@ int sync(void* stream);
 // environment in ONE launch.  flags: bit0 = part of mj_step (run the qpos/qvel checks), bit1 = skip
 // environments whose warning counters are non-zero
 int launch_stages(const DModel& dm, const Batch& b, int mask, int flags, void* stream);
+int launch_rk4(const DModel& dm, const Batch& b, int phase, int flags, void* stream);   // rk4_phase of every env
 int launch_reset(const DModel& dm, const Batch& b, void* stream);
 // rollout helpers; control/state are DEVICE buffers laid out [nenv][nstep][n] (reference layout)
 int launch_set_control(const DModel& dm, const Batch& b, const double* control, int nstep, int t,

@@ -166,9 +166,8 @@ MJB_HD void fwd_acceleration(const Env& d) {
 }
 
 // position integration on the configuration manifold (one lane per joint)
-MJB_HD void integrate_pos(const Env& d, double dt) {
+MJB_HD void integrate_pos(const Env& d, FD qpos, FD qvel, double dt) {
   const DModel& m = d.m;
-  FD qpos = d.qpos(), qvel = d.qvel();
   MJB_PFOR(j, m.sz.njnt) {
     int pa = m.jnt_qposadr[j], va = m.jnt_dofadr[j];
     const int jt = m.jnt_type[j];
@@ -213,7 +212,7 @@ MJB_HD void euler_advance(const Env& d) {
   }
   MJB_PFOR(i, nv) qvel[i] += acc[i] * h;
   MJB_PSYNC();
-  integrate_pos(d, h);
+  integrate_pos(d, d.qpos(), d.qvel(), h);
   FD ws = d.qacc_warmstart();
   MJB_PFOR(i, nv) ws[i] = qacc[i];
   MJB_LANE0 d.time()[0] += h;
@@ -242,7 +241,73 @@ MJB_HD void stage_solve(const Env& d) {
 MJB_HD void stage_finish_forward(const Env& d) {
   if (d.solver == SOL_PGS) dual_finish(d);
 }
-MJB_HD void stage_integrate(const Env& d) {
+// explicit Runge-Kutta 4 (mj_RungeKutta, engine_forward.c:1486-1591) split into phases around the
+// forward passes, which are separate launches of the fused kernel:
+//   phase 1..3 (after forward #phase-1): record F[phase-1] = qacc, form X[phase] = X[0] (+) h*dX with the
+//              tableau row A[phase-1], install it as the state at time T[phase-1]
+//   phase 4    (after forward #3): record F[3], combine with B, restore X[0] and advance (mj_advance)
+// rk_scr layout: x0 qpos[nq] | x0 qvel[nv] | X[1..3] qvel [3 nv] | F[0..3] [4 nv] | t0
+MJB_HD void rk4_phase(const Env& d, int phase) {
+  const DModel& m = d.m;
+  const int nq = m.sz.nq, nv = m.sz.nv;
+  const double h = m.opt.timestep;
+  FD scr = d.rk_scr();
+  FD x0q = scr, x0v = scr + nq, xv = scr + nq + nv, F = scr + nq + 4 * nv, t0 = scr + nq + 8 * nv;
+  FD dXv = d.scr_nv(), dXa = d.scr_nv() + nv;
+  FD qpos = d.qpos(), qvel = d.qvel(), qacc = d.qacc();
+  const double A[9] = {0.5, 0, 0, 0, 0.5, 0, 0, 0, 1};
+  const double B[4] = {1.0 / 6.0, 1.0 / 3.0, 1.0 / 3.0, 1.0 / 6.0};
+  if (phase == 1) {
+    MJB_PFOR(i, nq) x0q[i] = qpos[i];
+    MJB_PFOR(i, nv) x0v[i] = qvel[i];
+    MJB_LANE0 t0[0] = d.time()[0];
+  }
+  MJB_PFOR(i, nv) F[(phase - 1) * nv + i] = qacc[i];
+  MJB_PSYNC();
+  auto Xv = [&](int j, int i) { return j == 0 ? x0v[i] : xv[(j - 1) * nv + i]; };
+  if (phase < 4) {
+    MJB_PFOR(i, nv) {
+      double sv = 0, sa = 0;
+      for (int j = 0; j < phase; j++) {
+        const double a = A[(phase - 1) * 3 + j];
+        sv += Xv(j, i) * a;
+        sa += F[j * nv + i] * a;
+      }
+      dXv[i] = sv; dXa[i] = sa;
+    }
+    MJB_PFOR(i, nq) qpos[i] = x0q[i];
+    MJB_PSYNC();
+    integrate_pos(d, qpos, dXv, h);
+    MJB_PFOR(i, nv) {
+      const double v = x0v[i] + dXa[i] * h;
+      qvel[i] = v;
+      xv[(phase - 1) * nv + i] = v;
+    }
+    MJB_LANE0 {
+      double c = 0;
+      for (int j = 0; j < phase; j++) c += A[(phase - 1) * 3 + j];
+      d.time()[0] = t0[0] + c * h;
+    }
+    MJB_PSYNC();
+  } else {
+    MJB_PFOR(i, nv) {
+      double sv = 0, sa = 0;
+      for (int j = 0; j < 4; j++) { sv += Xv(j, i) * B[j]; sa += F[j * nv + i] * B[j]; }
+      dXv[i] = sv; dXa[i] = sa;
+    }
+    MJB_PFOR(i, nq) qpos[i] = x0q[i];
+    MJB_PSYNC();
+    MJB_PFOR(i, nv) qvel[i] = x0v[i] + dXa[i] * h;
+    integrate_pos(d, qpos, dXv, h);
+    FD ws = d.qacc_warmstart();
+    MJB_PFOR(i, nv) ws[i] = qacc[i];
+    MJB_LANE0 d.time()[0] = t0[0] + h;
+    MJB_PSYNC();
+  }
+}
+
+// with_euler: semi-implicit Euler + advance (mj_Euler); without: the step continues with rk4_phase
+MJB_HD void stage_integrate(const Env& d, bool with_euler = true) {
   stage_finish_forward(d);
   check_vec(d, d.qacc(), d.m.sz.nv, WARN_BADQACC);
   const int bad = d.scr_int()[0];
@@ -254,7 +319,7 @@ MJB_HD void stage_integrate(const Env& d) {
     stage_solve(d);
     stage_finish_forward(d);
   }
-  euler_advance(d);
+  if (with_euler) euler_advance(d);
 }
 
 }  // namespace mjb

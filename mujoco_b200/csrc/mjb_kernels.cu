@@ -68,6 +68,13 @@ __global__ void __launch_bounds__(32) k_rollout_lane(DModel m, Batch b, const do
   run_env_rollout(m, b, e, nstep, ctrl, state, nstate, 0, 1, nullptr, 0);
 }
 
+// Runge-Kutta phase between forward launches: one warp per environment (coalesced env-major access)
+__global__ void __launch_bounds__(32 * kWarpsPerCta) k_rk4(DModel m, Batch b, int phase, int flags) {
+  const int e = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
+  if (e >= b.nenv) return;
+  run_rk4(m, b, e, phase, flags, threadIdx.x & 31, 32);
+}
+
 __global__ void k_pack(Batch b, int is_int, long off, long cnt, void* dense, int to_dense) {
   const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long)b.nenv * cnt) return;
@@ -193,6 +200,12 @@ int launch_stages(const DModel& dm, const Batch& b, int mask, int flags, void* s
   }
   g_launches++;
   CK(cudaPeekAtLastError(), "step kernel launch");
+  return 0;
+}
+int launch_rk4(const DModel& dm, const Batch& b, int phase, int flags, void* s) {
+  k_rk4<<<(b.nenv + kWarpsPerCta - 1) / kWarpsPerCta, 32 * kWarpsPerCta, 0, (cudaStream_t)s>>>(dm, b, phase, flags);
+  g_launches++;
+  CK(cudaPeekAtLastError(), "rk4 kernel launch");
   return 0;
 }
 int launch_rollout_native(const DModel& dm, const Batch& b, const double* ctrl, double* state, int nstep, int nstate, void* s) {

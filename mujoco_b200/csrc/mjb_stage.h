@@ -23,18 +23,43 @@ MJB_HD void run_stage_mask(const Env& d, int mask, int flags) {
   if (mask & 4) stage_solve(d);
   if (mask & 8) stage_integrate(d);
   if (mask & 16) stage_finish_forward(d);
+  if (mask & 32) stage_integrate(d, false);   // dual finish + acceleration check, no integration (RK4)
+}
+
+// rollout rule (rollout.cc:127-155): an environment that carries a warning when a step BEGINS does not
+// step.  flags bit1: evaluate that now (first launch of a step) and remember it in step_skip;
+// flags bit2: a later launch of the same multi-launch step (RK4) reuses the remembered decision, so
+// a warning raised inside the step does not cut the step short.
+MJB_HD bool step_enabled(const Env& d, int flags) {
+  if (flags & 2) {
+    const bool skip = env_has_warning(d);
+    MJB_PSYNC();
+    MJB_LANE0 d.step_skip()[0] = skip ? 1 : 0;
+    MJB_PSYNC();
+    return !skip;
+  }
+  if (flags & 4) return d.step_skip()[0] == 0;
+  return true;
 }
 
 // run the selected stages of one environment with its cooperative lanes.
-// flags: bit0 = part of mj_step (qpos/qvel checks), bit1 = skip environments that raised a warning.
+// flags: bit0 = part of mj_step (qpos/qvel checks), bit1/bit2 = rollout skip rule (step_enabled).
 // sm/smcap: optional per-warp shared-memory scratch (doubles) used by the latency-critical loops.
 MJB_HD void run_env(const DModel& m, const Batch& b, int e, int mask, int flags, int lane, int nlane,
                     double* sm, int smcap, int solver = -1) {
   Env d(m, b, e, lane, nlane);
   d.sm = sm; d.smcap = smcap;
   d.solver = solver < 0 ? m.opt.solver : solver;
-  if ((flags & 2) && env_has_warning(d)) return;   // rollout: a warned env stops stepping (uniform per env)
+  if (!step_enabled(d, flags)) return;
   run_stage_mask(d, mask, flags);
+}
+
+// one phase of the Runge-Kutta step (between forward launches)
+MJB_HD void run_rk4(const DModel& m, const Batch& b, int e, int phase, int flags, int lane, int nlane) {
+  Env d(m, b, e, lane, nlane);
+  d.solver = m.opt.solver;
+  if (!step_enabled(d, flags)) return;
+  rk4_phase(d, phase);
 }
 
 // nstep consecutive steps of one environment: controls from ctrl [nstep][nu][stride] (or unchanged

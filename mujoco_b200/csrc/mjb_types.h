@@ -140,7 +140,7 @@ struct DModel {
   X(efc_D, S.njmax) X(efc_R, S.njmax) X(efc_vel, S.njmax) X(efc_aref, S.njmax)               \
   X(efc_b, S.njmax) X(efc_force, S.njmax)                                                    \
   X(scr_body, 12 * S.nbody) X(scr_nv, 8 * S.nv) X(scr_efc, 6 * S.njmax)                         \
-  X(nwt_nv, 6 * S.nv) X(nwt_efc, 6 * S.njmax)
+  X(nwt_nv, 6 * S.nv) X(nwt_efc, 6 * S.njmax) X(rk_scr, S.nq + 8 * S.nv + 4)
 
 // COLD doubles: stay in global memory / L2 in every mapping
 #define MJB_DATA_COLD_FIELDS(X, S)                                                           \
@@ -149,7 +149,7 @@ struct DModel {
 
 // ints (all hot)
 #define MJB_DATA_INT_FIELDS(X, S)                                                            \
-  X(ncon, 1) X(nefc, 1) X(ne, 1) X(nf, 1) X(nl, 1) X(solver_niter, 1) X(warning, NWARNING)     \
+  X(ncon, 1) X(nefc, 1) X(ne, 1) X(nf, 1) X(nl, 1) X(solver_niter, 1) X(step_skip, 1) X(warning, NWARNING)     \
   X(con_geom1, S.nconmax) X(con_geom2, S.nconmax) X(con_dim, S.nconmax)                       \
   X(con_exclude, S.nconmax) X(con_efcadr, S.nconmax) X(con_pair, S.nconmax)                    \
   X(efc_type, S.njmax) X(efc_id, S.njmax) X(efc_state, S.njmax) X(nwt_state, S.njmax) X(scr_int, 4 * S.njmax)        \

@@ -32,6 +32,11 @@ int launch_stages(const DModel& dm, const Batch& b, int mask, int flags, void*) 
   for (int e = 0; e < b.nenv; e++) run_env(dm, b, e, mask, flags, 0, 1, nullptr, 0);
   return 0;
 }
+int launch_rk4(const DModel& dm, const Batch& b, int phase, int flags, void*) {
+  g_launches++;
+  for (int e = 0; e < b.nenv; e++) run_rk4(dm, b, e, phase, flags, 0, 1);
+  return 0;
+}
 int launch_rollout_native(const DModel& dm, const Batch& b, const double* ctrl, double* state, int nstep, int nstate, void*) {
   g_launches++;
   for (int e = 0; e < b.nenv; e++) run_env_rollout(dm, b, e, nstep, ctrl, state, nstate, 0, 1, nullptr, 0);

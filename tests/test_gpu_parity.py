@@ -126,3 +126,19 @@ def test_ant_batch_65536_newton():
         ref, _, _ = o.rollout(s64, c64, nthread=os.cpu_count() or 1)
         rel = np.abs(out[:64] - ref).max() / max(1.0, np.abs(ref).max())
         assert rel < RTOL_TIGHT
+
+
+@pytest.mark.parametrize("model,solver", [(HUMANOID, mb.SOLVER_PGS), (ANT, mb.SOLVER_NEWTON)])
+def test_rk4_rollout_vs_oracle(model, solver):
+    """integrator = RK4 (8 launches per step: forward+check, 3 x (phase, forward), final phase)"""
+    assert available()
+    nenv, nstep = 32, 60
+    m, b, o = make_pair(model, solver, nenv=nenv, integrator=mb.INT_RK4)
+    s0 = perturbed_states(o, nenv, seed=51, height=[0.3, 0.5, 0.8], qvel_std=0.5, qpos_std=0.15)
+    ctrl = np.random.default_rng(52).uniform(-1, 1, (nenv, nstep, o.size("nu")))
+    out = b.rollout(s0, ctrl)
+    ref, stats, _ = o.rollout(s0, ctrl, nthread=os.cpu_count() or 1)
+    assert stats[:, 3].sum() == 0 and (b.warnings() == 0).all()
+    rel = (np.abs(out - ref) / np.maximum(1.0, np.abs(ref).max(axis=(0, 1)))).max()
+    print("rk4 rollout rel err %.3e" % rel)
+    assert rel < RTOL_TIGHT

@@ -65,6 +65,25 @@ def test_ant_forward_and_rollout_bit_exact(solver):
     assert np.array_equal(out, ref)
 
 
+@pytest.mark.parametrize("model,solver", [(HUMANOID, mb.SOLVER_PGS), (HUMANOID, mb.SOLVER_NEWTON), (ANT, mb.SOLVER_NEWTON)])
+def test_rk4_rollout_bit_exact(model, solver):
+    """integrator = RK4 (mj_RungeKutta): 4 forward passes per step; BASELINE config 5's integrator"""
+    nenv, nstep = 6, 60
+    m, b, o = make_pair(model, solver, library=hostemu_lib(), nenv=nenv, integrator=mb.INT_RK4)
+    s0 = perturbed_states(o, nenv, seed=51, height=[0.3, 0.5, 0.8], qvel_std=0.5, qpos_std=0.15)
+    ctrl = np.random.default_rng(52).uniform(-1, 1, (nenv, nstep, o.size("nu")))
+    out = b.rollout(s0, ctrl)
+    ref, stats, _ = o.rollout(s0, ctrl, nthread=3)
+    assert stats[:, 0].sum() > 0 and stats[:, 3].sum() == 0
+    assert np.array_equal(out, ref)
+    # a bad state inside a rollout: reset + finish the step (RK4 is a multi-launch step), then pad
+    s0[2, 5] = np.inf
+    out = b.rollout(s0, ctrl[:, :8])
+    ref, stats, _ = o.rollout(s0, ctrl[:, :8], nthread=1)
+    assert stats[2, 3] > 0
+    assert np.array_equal(out, ref)
+
+
 def test_option_variants_bit_exact():
     """disable flags and solver options that change control flow on the path"""
     DSBL_WARMSTART, DSBL_CLAMPCTRL, DSBL_EULERDAMP, DSBL_REFSAFE, DSBL_FILTERPARENT = 1 << 9, 1 << 8, 1 << 15, 1 << 12, 1 << 10
