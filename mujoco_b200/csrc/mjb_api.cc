@@ -329,12 +329,8 @@ int mjb_step_host(mjbBatch* B, const double* ctrl, double* state_out) {
 int mjb_rollout_device(mjbBatch* B, int nstep, const double* d_ctrl, double* d_state) {
   if (!B || nstep < 0) return fail(MJB_ERR_ARG, "mjb_rollout_device: bad arguments");
   const int nstate = 1 + B->hm.dm.sz.nq + B->hm.dm.sz.nv;
-  // one fused launch per step keeps the warps of an SM in the same code region (the persistent
-  // multi-step variant, launch_rollout_native, measured ~2x slower: the warps drift apart and the
-  // ~1 MB of straight-line SASS no longer fits the instruction caches); MJB_PERSISTENT=1 selects it
-  static int persistent = -1;
-  if (persistent < 0) persistent = getenv("MJB_PERSISTENT") ? 1 : 0;
-  if (persistent && nstep && B->hm.dm.opt.integrator == INT_EULER) return backend::launch_rollout_native(B->dm, B->b, d_ctrl, d_state, nstep, nstate, B->stream);
+  // one fused launch per step: a persistent multi-step kernel measured ~2x slower (warps drift apart and
+  // the instruction working set no longer fits the instruction caches; per-step launches re-converge them)
   int rc = 0;
   for (int t = 0; t < nstep && !rc; t++) {
     if (d_ctrl) rc = backend::launch_set_control_native(B->dm, B->b, d_ctrl, t, B->stream);

@@ -34,7 +34,6 @@ int launch_get_state(const DModel& dm, const Batch& b, double* state, int nstep,
 int launch_set_control_native(const DModel& dm, const Batch& b, const double* ctrl, int t, void* stream);
 int launch_get_state_native(const DModel& dm, const Batch& b, double* state, int t, int nstate, void* stream);
 // nstep steps of every environment in ONE persistent launch (no barrier between steps)
-int launch_rollout_native(const DModel& dm, const Batch& b, const double* ctrl, double* state, int nstep, int nstate, void* stream);
 // dense [nenv][cnt] staging buffer <-> batch field (either layout); to_dense=1 gathers, 0 scatters
 int launch_pack(const Batch& b, int is_int, long off, long cnt, void* dense, int to_dense, void* stream);
 int launch_fill_zero(const Batch& b, int is_int, long off, long cnt, void* stream);

@@ -236,7 +236,7 @@ MJB_HD void stage_velocity(const Env& d) {
 }
 MJB_HD void stage_solve(const Env& d) {
   if (d.solver == SOL_PGS) solve_pgs(d);
-  else solve_newton(d);
+  else solve_primal(d, d.solver == SOL_NEWTON);
 }
 MJB_HD void stage_finish_forward(const Env& d) {
   if (d.solver == SOL_PGS) dual_finish(d);
@@ -304,22 +304,6 @@ MJB_HD void rk4_phase(const Env& d, int phase) {
     MJB_LANE0 d.time()[0] = t0[0] + h;
     MJB_PSYNC();
   }
-}
-
-// with_euler: semi-implicit Euler + advance (mj_Euler); without: the step continues with rk4_phase
-MJB_HD void stage_integrate(const Env& d, bool with_euler = true) {
-  stage_finish_forward(d);
-  check_vec(d, d.qacc(), d.m.sz.nv, WARN_BADQACC);
-  const int bad = d.scr_int()[0];
-  MJB_PSYNC();
-  if (bad && !(d.m.opt.disableflags & DSBL_AUTORESET)) {
-    // mj_checkAcc: after the reset the reference re-runs mj_forward before integrating
-    stage_position(d, false);
-    stage_velocity(d);
-    stage_solve(d);
-    stage_finish_forward(d);
-  }
-  if (with_euler) euler_advance(d);
 }
 
 }  // namespace mjb

@@ -37,7 +37,10 @@ constexpr int kWarpsPerCta = 4;
 #ifndef MJB_CTAS_PER_SM
 #define MJB_CTAS_PER_SM 7   // 28 warps/SM: a 4096-env batch is resident in ONE wave on 148 SMs (needs <= 72 regs)
 #endif
-constexpr int kSmemPerWarp = 832;    // doubles = 6.5 KB: eight sweep vectors, order + draws, and a 4-row ring for nefc <= 64 (or all of AR for nefc <= 24)
+#ifndef MJB_SMEM_PER_WARP
+#define MJB_SMEM_PER_WARP 832
+#endif
+constexpr int kSmemPerWarp = MJB_SMEM_PER_WARP;    // doubles = 6.5 KB: eight sweep vectors, order + draws, and a 4-row ring for nefc <= 64 (or all of AR for nefc <= 24)
 // Specialised per constraint solver (template constant propagated through Env::solver) so that each
 // instantiation carries only its own solver's code and register pressure.
 template <int SOLVER>
@@ -47,25 +50,6 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta, MJB_CTAS_PER_SM) k_step_war
   const int e = blockIdx.x * kWarpsPerCta + w;
   if (e >= b.nenv) return;
   run_env(m, b, e, mask, flags, threadIdx.x & 31, 32, smem + w * kSmemPerWarp, kSmemPerWarp, SOLVER);
-}
-
-// PERSISTENT ROLLOUT KERNEL: each warp advances its environment through nstep steps without any
-// grid-wide barrier between steps, reading that step's controls from / recording its state to
-// device buffers in the native [step][elem][env] layout.  Because environments are independent, a
-// slow environment (a PGS solve that runs to the iteration cap) only delays itself: throughput is
-// set by the MEAN per-environment step time instead of the per-step maximum.
-__global__ void __launch_bounds__(32 * kWarpsPerCta, MJB_CTAS_PER_SM)
-k_rollout_warp(DModel m, Batch b, const double* ctrl, double* state, int nstep, int nstate) {
-  __shared__ double smem[kWarpsPerCta * kSmemPerWarp];
-  const int w = threadIdx.x >> 5;
-  const int e = blockIdx.x * kWarpsPerCta + w;
-  if (e >= b.nenv) return;
-  run_env_rollout(m, b, e, nstep, ctrl, state, nstate, threadIdx.x & 31, 32, smem + w * kSmemPerWarp, kSmemPerWarp);
-}
-__global__ void __launch_bounds__(32) k_rollout_lane(DModel m, Batch b, const double* ctrl, double* state, int nstep, int nstate) {
-  const int e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= b.nenv) return;
-  run_env_rollout(m, b, e, nstep, ctrl, state, nstate, 0, 1, nullptr, 0);
 }
 
 // Runge-Kutta phase between forward launches: one warp per environment (coalesced env-major access)
@@ -194,7 +178,8 @@ int launch_stages(const DModel& dm, const Batch& b, int mask, int flags, void* s
   if (b.warp_per_env) {
     const int grid = (b.nenv + kWarpsPerCta - 1) / kWarpsPerCta;
     if (dm.opt.solver == SOL_PGS) k_step_warp<SOL_PGS><<<grid, 32 * kWarpsPerCta, 0, (cudaStream_t)s>>>(dm, b, mask, flags);
-    else k_step_warp<SOL_NEWTON><<<grid, 32 * kWarpsPerCta, 0, (cudaStream_t)s>>>(dm, b, mask, flags);
+    else if (dm.opt.solver == SOL_NEWTON) k_step_warp<SOL_NEWTON><<<grid, 32 * kWarpsPerCta, 0, (cudaStream_t)s>>>(dm, b, mask, flags);
+    else k_step_warp<SOL_CG><<<grid, 32 * kWarpsPerCta, 0, (cudaStream_t)s>>>(dm, b, mask, flags);
   } else {
     k_step_lane<<<nblocks(b, 32), 32, 0, (cudaStream_t)s>>>(dm, b, mask, flags);
   }
@@ -206,16 +191,6 @@ int launch_rk4(const DModel& dm, const Batch& b, int phase, int flags, void* s) 
   k_rk4<<<(b.nenv + kWarpsPerCta - 1) / kWarpsPerCta, 32 * kWarpsPerCta, 0, (cudaStream_t)s>>>(dm, b, phase, flags);
   g_launches++;
   CK(cudaPeekAtLastError(), "rk4 kernel launch");
-  return 0;
-}
-int launch_rollout_native(const DModel& dm, const Batch& b, const double* ctrl, double* state, int nstep, int nstate, void* s) {
-  if (b.warp_per_env) {
-    k_rollout_warp<<<(b.nenv + kWarpsPerCta - 1) / kWarpsPerCta, 32 * kWarpsPerCta, 0, (cudaStream_t)s>>>(dm, b, ctrl, state, nstep, nstate);
-  } else {
-    k_rollout_lane<<<nblocks(b, 32), 32, 0, (cudaStream_t)s>>>(dm, b, ctrl, state, nstep, nstate);
-  }
-  g_launches++;
-  CK(cudaPeekAtLastError(), "rollout kernel launch");
   return 0;
 }
 int launch_reset(const DModel& dm, const Batch& b, void* s) {

@@ -675,7 +675,7 @@ int build_host_model(const mjModel* m, int nconmax, int njmax, HostModel* out) {
   if (O.solver == mjSOL_PGS && !O.dense) { set_error("unsupported: PGS with sparse Jacobian (nv >= 60)"); return -2; }
   if (!O.dense) { set_error("unsupported: sparse-Jacobian models (nv >= 60) are a 'next' row"); return -2; }
   if (S.ntree != 1) { set_error("unsupported: multi-tree models (constraint islands) are a 'next' row"); return -2; }
-  if (O.solver != mjSOL_PGS && O.solver != mjSOL_NEWTON) { set_error("unsupported: CG solver"); return -2; }
+  if (O.solver != mjSOL_PGS && O.solver != mjSOL_NEWTON && O.solver != mjSOL_CG) { set_error("unsupported: unknown solver"); return -2; }
 
   B.fix();
   return 0;

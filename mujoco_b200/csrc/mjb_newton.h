@@ -323,7 +323,9 @@ MJB_HD double newton_search(const Env& d, NewtonCtx& c, double tolerance, int ls
   return 0;
 }
 
-MJB_HD void solve_newton(const Env& d) {
+// Newton (newton = true) or conjugate gradient (mj_solCG: M-preconditioned, Hager-Zhang direction
+// update, engine_solver.c:2489-2518) on the primal problem
+MJB_HD void solve_primal(const Env& d, bool newton) {
   const DModel& m = d.m;
   const int nv = m.sz.nv, nefc = d.nefc()[0], njmax = m.sz.njmax;
   if (!nefc) return;
@@ -333,6 +335,7 @@ MJB_HD void solve_newton(const Env& d) {
   FD se = d.nwt_efc(), sv = d.nwt_nv();
   c.Jaref = se; c.Jv = se + njmax; c.quad = se + 2 * (long)njmax; c.Dq = se + 5 * (long)njmax;
   c.Ma = sv; c.Mv = sv + nv; c.grad = sv + 2 * nv; c.Mgrad = sv + 3 * nv; c.search = sv + 4 * nv; c.cholupd = sv + 5 * nv;
+  FD gradold = d.scr_nv(), Mgradold = d.scr_nv() + nv;   // CG only
   c.L = d.nwt_L();
   c.efcD = d.efc_D(); c.efcR = d.efc_R(); c.floss = d.efc_frictionloss();
   c.qfs = d.qfrc_smooth(); c.qas = d.qacc_smooth(); c.qacc = d.qacc();
@@ -368,10 +371,10 @@ MJB_HD void solve_newton(const Env& d) {
   auto grad_norm = [&]() { return sqrt(dot_ref(nv, [&](int i) { return c.grad[i]; }, [&](int i) { return c.grad[i]; })); };
   const bool flg_gap = dmax(0.0, 0.5 * scale * grad_dot_mgrad()) < tol;
   const bool flg_gradient = scale * grad_norm() < tol;
-  bool done = flg_gap && flg_gradient;
+  bool done = flg_gap && (!newton || flg_gradient);
   MJB_PSYNC();
 
-  if (!done) {
+  if (!done && newton) {
     newton_factorize(d, c, true);
     newton_update_mgrad(d, c);
     done = flg_gradient && dmax(0.0, 0.5 * scale * grad_dot_mgrad()) < tol;
@@ -390,18 +393,48 @@ MJB_HD void solve_newton(const Env& d) {
     MJB_PSYNC();
     MJB_PFOR(i, nv) { c.qacc[i] += c.search[i] * alpha; c.Ma[i] += c.Mv[i] * alpha; }
     MJB_PFOR(i, nefc) { c.Jaref[i] += c.Jv[i] * alpha; c.oldstate[i] = c.state[i]; }
+    if (!newton) { MJB_PFOR(i, nv) { gradold[i] = c.grad[i]; Mgradold[i] = c.Mgrad[i]; } }
     MJB_PSYNC();
     newton_update_constraint(d, c);
-    newton_hessian_incremental(d, c);
+    if (newton) newton_hessian_incremental(d, c);
     newton_update_grad(d, c);
-    newton_update_mgrad(d, c);
+    if (newton) {
+      newton_update_mgrad(d, c);
+    } else {
+      MJB_PFOR(i, nv) c.Mgrad[i] = c.grad[i];
+      MJB_PSYNC();
+      solve_LD(d, c.Mgrad, d.qLD(), d.qLDiagInv());
+    }
     const double improvement = scale * ls_improvement;
     const double gradient = scale * grad_norm();
-    const double decrement = dmax(0.0, 0.5 * scale * grad_dot_mgrad());
+    const double decrement = newton ? dmax(0.0, 0.5 * scale * grad_dot_mgrad()) : 0.0;
     iter++;
-    if ((improvement > 0 && improvement < tol) || gradient < tol || decrement < tol) break;
+    if ((improvement > 0 && improvement < tol) || gradient < tol || (newton && decrement < tol)) break;
     MJB_PSYNC();
-    MJB_PFOR(i, nv) c.search[i] = c.Mgrad[i] * -1;
+    if (newton) {
+      MJB_PFOR(i, nv) c.search[i] = c.Mgrad[i] * -1;
+    } else {
+      // Hager-Zhang: every lane evaluates the same dot products (uniform beta)
+      auto dotf = [&](auto a, auto b) { return dot_ref(nv, a, b); };
+      auto S = [&](int i) { return c.search[i]; };
+      auto Y = [&](int i) { return c.grad[i] - gradold[i]; };
+      auto MY = [&](int i) { return c.Mgrad[i] - Mgradold[i]; };
+      auto G = [&](int i) { return c.grad[i]; };
+      auto MG = [&](int i) { return c.Mgrad[i]; };
+      double beta;
+      const double d_dot_y = dotf(S, Y);
+      if (d_dot_y < kMinVal) {
+        beta = 0;
+      } else {
+        const double y_dot_My = dotf(Y, MY), y_dot_Mgrad = dotf(Y, MG), d_dot_grad = dotf(S, G);
+        const double beta_hz = (y_dot_Mgrad - 2 * (y_dot_My / d_dot_y) * d_dot_grad) / d_dot_y;
+        const double d_norm = sqrt(dotf(S, S)), g_norm = sqrt(dotf(G, G));
+        const double eta_k = -1.0 / dmax(kMinVal, d_norm * dmin(0.01, g_norm));
+        beta = dmax(eta_k, beta_hz);
+      }
+      MJB_PSYNC();
+      MJB_PFOR(i, nv) c.search[i] = -c.Mgrad[i] + beta * c.search[i];
+    }
     MJB_PSYNC();
   }
   MJB_PSYNC();

@@ -17,13 +17,31 @@ constexpr int kMaskStep = 0xF, kMaskForward = 0x17;
 // run the selected stages of one environment with its cooperative lanes.
 // flags: bit0 = part of mj_step (qpos/qvel checks), bit1 = skip environments that raised a warning.
 // shot/sint: optional staging area (shared memory) for the hot block; only with env-major storage.
+// mask bits: 1 position, 2 velocity, 4 solve, 8 finish + acceleration check + Euler, 16 finish only
+// (mj_forward), 32 finish + acceleration check without integration (first forward of an RK4 step).
+// mj_checkAcc (engine_forward.c:99-113): a bad acceleration resets the environment and the forward
+// pass is run again before integrating; that second pass is the SAME code (one loop iteration more),
+// not a second inlined copy of the pipeline.
 MJB_HD void run_stage_mask(const Env& d, int mask, int flags) {
-  if (mask & 1) stage_position(d, (flags & 1) != 0);
-  if (mask & 2) stage_velocity(d);
-  if (mask & 4) stage_solve(d);
-  if (mask & 8) stage_integrate(d);
-  if (mask & 16) stage_finish_forward(d);
-  if (mask & 32) stage_integrate(d, false);   // dual finish + acceleration check, no integration (RK4)
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+  for (int pass = 0; pass < 2; pass++) {
+    const bool redo = pass == 1;
+    if ((mask & 1) || redo) stage_position(d, (flags & 1) != 0 && !redo);
+    if ((mask & 2) || redo) stage_velocity(d);
+    if ((mask & 4) || redo) stage_solve(d);
+    if (mask & (8 | 16 | 32)) stage_finish_forward(d);
+    if (!(mask & (8 | 32))) return;
+    if (!redo) {
+      check_vec(d, d.qacc(), d.m.sz.nv, WARN_BADQACC);
+      const int bad = d.scr_int()[0];
+      MJB_PSYNC();
+      if (bad && !(d.m.opt.disableflags & DSBL_AUTORESET)) continue;
+    }
+    if (mask & 8) euler_advance(d);
+    return;
+  }
 }
 
 // rollout rule (rollout.cc:127-155): an environment that carries a warning when a step BEGINS does not
@@ -60,33 +78,6 @@ MJB_HD void run_rk4(const DModel& m, const Batch& b, int e, int phase, int flags
   d.solver = m.opt.solver;
   if (!step_enabled(d, flags)) return;
   rk4_phase(d, phase);
-}
-
-// nstep consecutive steps of one environment: controls from ctrl [nstep][nu][stride] (or unchanged
-// when NULL), optional state record into state [nstep][nstate][stride] (time, qpos, qvel)
-MJB_HD void run_env_rollout(const DModel& m, const Batch& b, int e, int nstep, const double* ctrl, double* state,
-                            int nstate, int lane, int nlane, double* sm, int smcap) {
-  Env d(m, b, e, lane, nlane);
-  d.sm = sm; d.smcap = smcap;
-  d.solver = m.opt.solver;
-  const int nu = m.sz.nu, nq = m.sz.nq, nv = m.sz.nv;
-  for (int t = 0; t < nstep; t++) {
-    if (ctrl) {
-      FD c = d.ctrl();
-      const double* src = ctrl + (size_t)t * nu * b.stride + e;
-      MJB_PFOR(i, nu) c[i] = src[(size_t)i * b.stride];
-      MJB_PSYNC();
-    }
-    run_stage_mask(d, 0xF, 1);
-    if (state) {
-      double* dst = state + (size_t)t * nstate * b.stride + e;
-      FD qp = d.qpos(), qv = d.qvel();
-      MJB_LANE0 dst[0] = d.time()[0];
-      MJB_PFOR(i, nq) dst[(size_t)(1 + i) * b.stride] = qp[i];
-      MJB_PFOR(i, nv) dst[(size_t)(1 + nq + i) * b.stride] = qv[i];
-      MJB_PSYNC();
-    }
-  }
 }
 
 // control [nenv][nstep][ncontrol] (reference layout): segments ctrl then qfrc_applied by spec bits

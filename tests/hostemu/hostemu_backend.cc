@@ -37,11 +37,6 @@ int launch_rk4(const DModel& dm, const Batch& b, int phase, int flags, void*) {
   for (int e = 0; e < b.nenv; e++) run_rk4(dm, b, e, phase, flags, 0, 1);
   return 0;
 }
-int launch_rollout_native(const DModel& dm, const Batch& b, const double* ctrl, double* state, int nstep, int nstate, void*) {
-  g_launches++;
-  for (int e = 0; e < b.nenv; e++) run_env_rollout(dm, b, e, nstep, ctrl, state, nstate, 0, 1, nullptr, 0);
-  return 0;
-}
 int launch_pack(const Batch& b, int is_int, long off, long cnt, void* dense, int to_dense, void*) {
   for (long i = 0; i < (long)b.nenv * cnt; i++) run_pack(b, is_int, off, cnt, dense, to_dense, i);
   return 0;

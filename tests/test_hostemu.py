@@ -65,6 +65,41 @@ def test_ant_forward_and_rollout_bit_exact(solver):
     assert np.array_equal(out, ref)
 
 
+@pytest.mark.parametrize("solver", [mb.SOLVER_PGS, mb.SOLVER_NEWTON, mb.SOLVER_CG])
+def test_frictionloss_rows_bit_exact(solver):
+    """dry joint friction (mjCNSTR_FRICTION_DOF rows, nf > 0): Huber cost in the primal solvers, box
+    projection in PGS; model = ant with frictionloss on every hinge (cube_3x3x3 relies on these rows)"""
+    path = os.path.join(ROOT, "models", "ant_frictionloss.mjb")
+    nenv, nstep = 8, 100
+    m, b, o = make_pair(path, solver, library=hostemu_lib(), nenv=nenv)
+    states = perturbed_states(o, nenv, seed=7, height=[0.3, 0.45, 0.6, 0.9], qpos_std=0.2)
+    ctrl1 = np.random.default_rng(8).uniform(-1.5, 1.5, (nenv, o.size("nu")))
+    compare_forward(b, o, states, ctrl1, rtol=0, exact=True, check_dual=(solver == mb.SOLVER_PGS))
+    assert (b.field("nf")[:, 0] == 14).all()      # 8 hinges + the 6 dofs of the free root (class default)
+    s0 = perturbed_states(o, nenv, seed=71, height=[0.35, 0.5, 0.75], qvel_std=0.5, qpos_std=0.15)
+    ctrl = np.random.default_rng(72).uniform(-1, 1, (nenv, nstep, o.size("nu")))
+    out = b.rollout(s0, ctrl)
+    ref, stats, _ = o.rollout(s0, ctrl, nthread=4)
+    assert stats[:, 3].sum() == 0
+    assert np.array_equal(out, ref)
+
+
+@pytest.mark.parametrize("model", [HUMANOID, ANT])
+def test_cg_solver_bit_exact(model):
+    """mj_solCG: the primal machinery with M-preconditioning and the Hager-Zhang direction update"""
+    nenv, nstep = 8, 80
+    m, b, o = make_pair(model, mb.SOLVER_CG, library=hostemu_lib(), nenv=nenv)
+    states = perturbed_states(o, nenv, seed=3, height=[0.25, 0.4, 0.9, 1.3])
+    ctrl1 = np.random.default_rng(5).uniform(-1.5, 1.5, (nenv, o.size("nu")))
+    compare_forward(b, o, states, ctrl1, rtol=0, exact=True, check_dual=False)
+    s0 = perturbed_states(o, nenv, seed=61, height=[0.3, 0.5, 0.8], qvel_std=0.5, qpos_std=0.15)
+    ctrl = np.random.default_rng(62).uniform(-1, 1, (nenv, nstep, o.size("nu")))
+    out = b.rollout(s0, ctrl)
+    ref, stats, _ = o.rollout(s0, ctrl, nthread=4)
+    assert stats[:, 0].sum() > 0 and stats[:, 3].sum() == 0
+    assert np.array_equal(out, ref)
+
+
 @pytest.mark.parametrize("model,solver", [(HUMANOID, mb.SOLVER_PGS), (HUMANOID, mb.SOLVER_NEWTON), (ANT, mb.SOLVER_NEWTON)])
 def test_rk4_rollout_bit_exact(model, solver):
     """integrator = RK4 (mj_RungeKutta): 4 forward passes per step; BASELINE config 5's integrator"""

@@ -9,7 +9,9 @@ import mujoco_b200 as mb
 path, solver, nenv = sys.argv[1], int(sys.argv[2]), int(sys.argv[3])
 nstep = int(sys.argv[4]) if len(sys.argv) > 4 else 200
 settle = int(sys.argv[5]) if len(sys.argv) > 5 else 300
-m = mb.Model(path); m.set_option('solver', solver)
+import os, ctypes
+variant = os.environ.get('MJB_VARIANT_LIB')   # development only: A/B a differently-built library
+m = mb.Model(path, library=mb._bind(ctypes.CDLL(variant)) if variant else None); m.set_option('solver', solver)
 for kv in sys.argv[6:]:
     k, v = kv.split('='); m.set_option(k, float(v))
 b = mb.Batch(m, nenv)
