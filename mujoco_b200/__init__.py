@@ -8,7 +8,10 @@ C-contiguous float64 arrays in the reference's layouts, `initial_state` in mjSTA
 The CUDA library is the only compute path: if it is missing, or no CUDA device is usable, loading or
 batch creation raises — there is no CPU fallback in this package.
 """
+import atexit
 import ctypes as C
+import sys
+import weakref
 import os
 
 import numpy as np
@@ -75,6 +78,18 @@ def _bind(cdll):
 
 
 _lib = None
+_live = weakref.WeakSet()     # Batch / Model objects that still own native memory
+
+
+@atexit.register
+def _close_all():
+    """release native objects before interpreter teardown (batches first: they reference their model)"""
+    for cls in (Batch, Model):
+        for o in [x for x in list(_live) if isinstance(x, cls)]:
+            try:
+                o.close()
+            except Exception:  # noqa: BLE001
+                pass
 
 
 def lib():
@@ -103,6 +118,7 @@ class Model:
             if not self.ptr:
                 raise MjbError(_err(self.L))
             self._own = True
+            _live.add(self)
         else:
             self.ptr = address  # e.g. mujoco.MjModel._address of the stock Python bindings
 
@@ -126,10 +142,15 @@ class Model:
         if self.L.mjb_check_model(self.ptr):
             raise MjbError(_err(self.L))
 
-    def __del__(self):
+    def close(self):
         if getattr(self, "_own", False) and self.ptr:
             self.L.mjb_free_model(self.ptr)
             self.ptr = None
+
+    def __del__(self):
+        if sys is None or sys.is_finalizing():
+            return      # interpreter teardown: _close_all already ran, the libraries may be gone
+        self.close()
 
 
 class Batch:
@@ -143,6 +164,7 @@ class Batch:
         if not self.ptr:
             raise MjbError(_err(self.L))
         self.nenv = int(nenv)
+        _live.add(self)
 
     def _chk(self, rc):
         if rc:
@@ -154,6 +176,8 @@ class Batch:
             self.ptr = None
 
     def __del__(self):
+        if sys is None or sys.is_finalizing():
+            return
         try:
             self.close()
         except Exception:

@@ -128,7 +128,12 @@ int init(int device) {
 void* dev_alloc(size_t bytes) {
   void* p = nullptr;
   if (cudaMalloc(&p, bytes ? bytes : 1) != cudaSuccess) return nullptr;
-  cudaMemset(p, 0, bytes ? bytes : 1);
+  // zero-fill, then WAIT: the memset runs on the legacy default stream while every batch works on its
+  // own non-blocking stream, so without this barrier it could land after (and wipe) the first upload
+  if (cudaMemset(p, 0, bytes ? bytes : 1) != cudaSuccess || cudaStreamSynchronize(0) != cudaSuccess) {
+    cudaFree(p);
+    return nullptr;
+  }
   return p;
 }
 void dev_free(void* p) { if (p) cudaFree(p); }
