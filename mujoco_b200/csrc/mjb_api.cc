@@ -38,6 +38,7 @@ struct mjbBatch_ {
   double* io_state = nullptr;
   void* stage = nullptr;        // dense staging for field I/O
   size_t stage_bytes = 0;
+  std::vector<void*> gstreams;  // extra streams of the grouped multi-step execution (see env_groups)
 };
 
 static int fail(int code, const std::string& msg) { set_error(msg); return code; }
@@ -137,6 +138,7 @@ mjbBatch* mjb_make_batch(const struct mjModel_* m, int nenv, int nconmax, int nj
 void mjb_free_batch(mjbBatch* B) {
   if (!B) return;
   backend::sync(B->stream);
+  for (void* gs : B->gstreams) { backend::sync(gs); backend::stream_destroy(gs); }
   backend::dev_free(B->b.dbl);
   backend::dev_free(B->b.itg);
   backend::dev_free(B->d_ib);
@@ -224,18 +226,56 @@ int mjb_get_state(mjbBatch* B, double* state, unsigned int sig) {
 // one mj_step of every environment.  skip_warned: rollout rule (environments carrying a warning do
 // not step).  Euler: all four stages in ONE fused launch.  RK4 (mj_RungeKutta): forward + acceleration
 // check, then three (phase, forward) pairs and the final combination = 8 launches.
-static int run_step(mjbBatch* B, bool skip_warned) {
+static int run_step_on(mjbBatch* B, const Batch& b, void* stream, bool skip_warned) {
   const int first = 1 | (skip_warned ? 2 : 0), later = skip_warned ? 4 : 0;
   if (B->hm.dm.opt.integrator == INT_RK4) {
-    int rc = backend::launch_stages(B->dm, B->b, 0x7 | 32, first, B->stream);
+    int rc = backend::launch_stages(B->dm, b, 0x7 | 32, first, stream);
     for (int phase = 1; phase <= 3 && !rc; phase++) {
-      rc = backend::launch_rk4(B->dm, B->b, phase, later, B->stream);
-      if (!rc) rc = backend::launch_stages(B->dm, B->b, 0x17, later, B->stream);
+      rc = backend::launch_rk4(B->dm, b, phase, later, stream);
+      if (!rc) rc = backend::launch_stages(B->dm, b, 0x17, later, stream);
     }
-    if (!rc) rc = backend::launch_rk4(B->dm, B->b, 4, later, B->stream);
+    if (!rc) rc = backend::launch_rk4(B->dm, b, 4, later, stream);
     return rc;
   }
-  return backend::launch_stages(B->dm, B->b, 0xF, first, B->stream);
+  return backend::launch_stages(B->dm, b, 0xF, first, stream);
+}
+static int run_step(mjbBatch* B, bool skip_warned) { return run_step_on(B, B->b, B->stream, skip_warned); }
+
+// Grouped execution of MULTI-step calls.  A step of the whole batch ends when its slowest environment
+// ends (a PGS solve at the iteration cap), and while that tail drains most SMs idle.  Environments never
+// interact, so a multi-step rollout does not need that barrier: the batch is cut into contiguous env
+// groups, each advanced through all steps on its own stream; a group's tail overlaps the other groups'
+// next steps.  Results are unchanged (same kernels, same per-env arithmetic).  Calls that must return
+// every environment after ONE step (mjb_step_host, mjb_step(1)) keep the single launch.
+struct EnvGroup { Batch b; long e0; void* stream; };
+static std::vector<EnvGroup> env_groups(mjbBatch* B, int nstep) {
+  static int want = -1;
+  if (want < 0) { const char* s = getenv("MJB_GROUPS"); want = s ? atoi(s) : 4; if (want < 1) want = 1; }
+  int G = want;
+  const int nenv = B->b.nenv;
+  if (nstep < 2 || nenv < 64 * G) G = 1;
+  std::vector<EnvGroup> out;
+  const int per = ((nenv + G - 1) / G + 3) / 4 * 4;   // whole CTAs (4 envs) per group
+  for (int g = 0, e0 = 0; e0 < nenv; g++, e0 += per) {
+    EnvGroup v{B->b, e0, B->stream};
+    v.b.nenv = (e0 + per <= nenv) ? per : nenv - e0;
+    v.b.dbl = B->b.dbl + (size_t)e0 * B->b.dpitch;
+    v.b.itg = B->b.itg + (size_t)e0 * B->b.ipitch;
+    if (g > 0) {
+      while ((int)B->gstreams.size() < g) B->gstreams.push_back(backend::stream_create());
+      v.stream = B->gstreams[g - 1];
+    }
+    out.push_back(v);
+  }
+  return out;
+}
+static int groups_fork(mjbBatch* B, std::vector<EnvGroup>& gs) {
+  for (size_t g = 1; g < gs.size(); g++) if (int rc = backend::stream_order(B->stream, gs[g].stream)) return rc;
+  return 0;
+}
+static int groups_join(mjbBatch* B, std::vector<EnvGroup>& gs) {
+  for (size_t g = 1; g < gs.size(); g++) if (int rc = backend::stream_order(gs[g].stream, B->stream)) return rc;
+  return 0;
 }
 
 int mjb_forward(mjbBatch* B) {
@@ -246,8 +286,12 @@ int mjb_forward(mjbBatch* B) {
 
 int mjb_step(mjbBatch* B, int nstep) {
   if (!B || nstep < 0) return fail(MJB_ERR_ARG, "mjb_step: bad arguments");
+  std::vector<EnvGroup> gs = env_groups(B, nstep);
+  if (int rc = groups_fork(B, gs)) return rc;
   for (int t = 0; t < nstep; t++)
-    if (int rc = run_step(B, false)) return rc;
+    for (auto& g : gs)
+      if (int rc = run_step_on(B, g.b, g.stream, false)) return rc;
+  if (int rc = groups_join(B, gs)) return rc;
   return backend::sync(B->stream);
 }
 
@@ -295,12 +339,16 @@ int mjb_rollout(mjbBatch* B, int nstep, unsigned int control_spec, const double*
     d_state = (double*)backend::dev_alloc(sbytes);
     if (!d_state) { backend::dev_free(d_control); return fail(MJB_ERR_CUDA, "device allocation failed (state)"); }
   }
-  int rc = 0;
+  std::vector<EnvGroup> gs = env_groups(B, nstep);
+  int rc = groups_fork(B, gs);
   for (int t = 0; t < nstep && !rc; t++) {
-    if (d_control) rc = backend::launch_set_control(B->dm, B->b, d_control, nstep, t, control_spec, ncontrol, B->stream);
-    if (!rc) rc = run_step(B, true);
-    if (d_state && !rc) rc = backend::launch_get_state(B->dm, B->b, d_state, nstep, t, nstate, B->stream);
+    for (auto& g : gs) {
+      if (d_control && !rc) rc = backend::launch_set_control(B->dm, g.b, d_control + (size_t)g.e0 * nstep * ncontrol, nstep, t, control_spec, ncontrol, g.stream);
+      if (!rc) rc = run_step_on(B, g.b, g.stream, true);
+      if (d_state && !rc) rc = backend::launch_get_state(B->dm, g.b, d_state + (size_t)g.e0 * nstep * nstate, nstep, t, nstate, g.stream);
+    }
   }
+  if (!rc) rc = groups_join(B, gs);
   if (!rc && d_state) rc = backend::d2h(state, d_state, sbytes, B->stream);
   if (!rc) rc = backend::sync(B->stream);
   backend::dev_free(d_control);
@@ -331,12 +379,16 @@ int mjb_rollout_device(mjbBatch* B, int nstep, const double* d_ctrl, double* d_s
   const int nstate = 1 + B->hm.dm.sz.nq + B->hm.dm.sz.nv;
   // one fused launch per step: a persistent multi-step kernel measured ~2x slower (warps drift apart and
   // the instruction working set no longer fits the instruction caches; per-step launches re-converge them)
-  int rc = 0;
+  std::vector<EnvGroup> gs = env_groups(B, nstep);
+  int rc = groups_fork(B, gs);
   for (int t = 0; t < nstep && !rc; t++) {
-    if (d_ctrl) rc = backend::launch_set_control_native(B->dm, B->b, d_ctrl, t, B->stream);
-    if (!rc) rc = run_step(B, false);
-    if (d_state && !rc) rc = backend::launch_get_state_native(B->dm, B->b, d_state, t, nstate, B->stream);
+    for (auto& g : gs) {   // native layouts are [..][elem][env]: a group starts e0 elements further
+      if (d_ctrl && !rc) rc = backend::launch_set_control_native(B->dm, g.b, d_ctrl + g.e0, t, g.stream);
+      if (!rc) rc = run_step_on(B, g.b, g.stream, false);
+      if (d_state && !rc) rc = backend::launch_get_state_native(B->dm, g.b, d_state + g.e0, t, nstate, g.stream);
+    }
   }
+  if (!rc) rc = groups_join(B, gs);
   return rc;   // asynchronous: caller synchronises on mjb_stream()
 }
 

@@ -19,6 +19,8 @@ int dev_zero(void* dst, size_t bytes, void* stream);
 void* stream_create();
 void stream_destroy(void* s);
 int sync(void* stream);
+// order `waiter` after everything enqueued on `signaller` so far (event record + stream wait)
+int stream_order(void* signaller, void* waiter);
 
 // run the pipeline stages selected by `mask` (bit s = stage s, see mjb_forward.h) for every
 // environment in ONE launch.  flags: bit0 = part of mj_step (run the qpos/qvel checks), bit1 = skip
@@ -33,7 +35,6 @@ int launch_get_state(const DModel& dm, const Batch& b, double* state, int nstep,
 // native-layout variants: ctrl [nstep][nu][stride], state [nstep][nstate][stride]
 int launch_set_control_native(const DModel& dm, const Batch& b, const double* ctrl, int t, void* stream);
 int launch_get_state_native(const DModel& dm, const Batch& b, double* state, int t, int nstate, void* stream);
-// nstep steps of every environment in ONE persistent launch (no barrier between steps)
 // dense [nenv][cnt] staging buffer <-> batch field (either layout); to_dense=1 gathers, 0 scatters
 int launch_pack(const Batch& b, int is_int, long off, long cnt, void* dense, int to_dense, void* stream);
 int launch_fill_zero(const Batch& b, int is_int, long off, long cnt, void* stream);

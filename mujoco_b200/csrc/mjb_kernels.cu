@@ -160,6 +160,14 @@ int sync(void* s) {
   CK(cudaGetLastError(), "kernel execution");
   return 0;
 }
+int stream_order(void* signaller, void* waiter) {
+  cudaEvent_t ev;
+  CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming), "event create");
+  CK(cudaEventRecord(ev, (cudaStream_t)signaller), "event record");
+  CK(cudaStreamWaitEvent((cudaStream_t)waiter, ev, 0), "stream wait");
+  CK(cudaEventDestroy(ev), "event destroy");   // released once the wait has been satisfied
+  return 0;
+}
 long launches() { return g_launches; }
 
 static inline int nblocks(const Batch& b, int threads) { return (b.nenv + threads - 1) / threads; }

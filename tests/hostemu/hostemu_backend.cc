@@ -25,6 +25,7 @@ int dev_zero(void* dst, size_t bytes, void*) { memset(dst, 0, bytes); return 0; 
 void* stream_create() { return nullptr; }
 void stream_destroy(void*) {}
 int sync(void*) { return 0; }
+int stream_order(void*, void*) { return 0; }
 long launches() { return g_launches; }
 
 int launch_stages(const DModel& dm, const Batch& b, int mask, int flags, void*) {
