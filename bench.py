@@ -221,17 +221,6 @@ def main():
         for s in range(4):
             stage_ms[s] += evs[s].elapsed_time(evs[s + 1])
     stage_ms /= nprobe
-    # the fused step kernel timed alone: one launch over the whole batch (mjb_step(1)), CUDA events
-    fused_ms = 0.0
-    for t_ in range(nprobe):
-        e0_, e1_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0_.record(stream)
-        batch.step(1)
-        e1_.record(stream)
-        stream.synchronize()
-        fused_ms += e0_.elapsed_time(e1_)
-    fused_ms /= nprobe
-
     # ---- roofline of the dominant kernel
     peak, peak_src = peaks()
     m_nefc, m_nefc2, m_ncon = float(nefc.mean()), float((nefc ** 2).mean()), float(ncon.mean())
@@ -249,20 +238,20 @@ def main():
     b_int = b_state
     bytes_per_env = [b_pos, b_vel, b_sol, b_int]
     b_mjdata = sum(bytes_per_env)
-    # dominant kernel = the fused launch k_step_warp (stages 0-3 of every env).  Inside the timed region the
-    # batch is advanced as overlapping env groups (several smaller launches in flight), so the kernel's
-    # duration is taken from the probe above: one launch over the whole batch, timed alone with events
-    launch_ms = fused_ms
+    # dominant kernel = the fused per-step launch k_step_warp (stages 0-3 of every env, one launch per
+    # step); its average duration over the timed region = ms / K (launches are back to back on the
+    # stream; the tiny k_set_control launch in between is included, which only lowers `achieved`)
+    launch_ms = ms / K
     achieved = NENV * b_mjdata / (launch_ms * 1e-3) / 1e9
     traffic, traffic_src = None, None
     tp = os.path.join(ROOT, "profiles", "r01_traffic.json")
     if os.path.exists(tp):
         tj = json.load(open(tp))
         traffic, traffic_src = tj.get("dram_bytes_per_launch"), tj.get("source")
-    roof = {"bound": "hbm", "kernel": "k_step_warp<PGS> (fused mj_step of the whole batch in one launch, timed alone)", "achieved": achieved, "peak": peak,
+    roof = {"bound": "hbm", "kernel": "k_step_warp<PGS,32> (fused mj_step, 1 launch/step)", "achieved": achieved, "peak": peak,
             "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
             "traffic_source": traffic_src, "algorithmic_bytes_per_launch": NENV * b_mjdata,
-            "algorithmic_bytes_per_env_step": b_mjdata, "launch_ms": launch_ms, "env_groups": int(os.environ.get("MJB_GROUPS", 4)),
+            "algorithmic_bytes_per_env_step": b_mjdata, "launch_ms": launch_ms,
             "note": "latency-bound (serial PGS dependency chain of the slowest env), not bandwidth-bound: see DESIGN.md",
             "stage_ms": dict(zip(["position", "velocity", "solve", "integrate"], [float(x) for x in stage_ms])),
             "stage_bytes_per_env": dict(zip(["position", "velocity", "solve", "integrate"], [float(x) for x in bytes_per_env]))}

@@ -123,6 +123,10 @@ mjbBatch* mjb_make_batch(const struct mjModel_* m, int nenv, int nconmax, int nj
   b.stride = ((size_t)nenv + 31) / 32 * 32;
   b.L = make_layout(H.sz);
   b.warp_per_env = g_warp_per_env;
+  // small models (<= 16 bodies and dofs) with a primal solver: two environments per warp.  PGS keeps a
+  // whole warp per environment (its on-chip sweep uses warp-wide shuffles).  MJB_LANES=32|16 overrides.
+  b.nlane = (H.sz.nbody <= 16 && H.sz.nv <= 16 && H.opt.solver != SOL_PGS) ? 16 : 32;
+  if (const char* ls = getenv("MJB_LANES")) { const int v = atoi(ls); if (v == 16 || v == 32) b.nlane = v; }
   b.dpitch = ((size_t)b.L.ndbl + 15) / 16 * 16;   // env-major blocks, 128-byte aligned
   b.ipitch = ((size_t)b.L.nint + 31) / 32 * 32;
   size_t nd = b.dpitch * b.stride;
@@ -241,21 +245,21 @@ static int run_step_on(mjbBatch* B, const Batch& b, void* stream, bool skip_warn
 }
 static int run_step(mjbBatch* B, bool skip_warned) { return run_step_on(B, B->b, B->stream, skip_warned); }
 
-// Grouped execution of MULTI-step calls.  A step of the whole batch ends when its slowest environment
-// ends (a PGS solve at the iteration cap), and while that tail drains most SMs idle.  Environments never
-// interact, so a multi-step rollout does not need that barrier: the batch is cut into contiguous env
-// groups, each advanced through all steps on its own stream; a group's tail overlaps the other groups'
-// next steps.  Results are unchanged (same kernels, same per-env arithmetic).  Calls that must return
-// every environment after ONE step (mjb_step_host, mjb_step(1)) keep the single launch.
+// Optional grouped execution of MULTI-step calls (MJB_GROUPS=n, default 1 = off): the batch is cut into
+// contiguous env groups, each advanced through all steps on its own stream.  Measured on B200
+// (humanoid x4096, PGS): 2.23 / 2.18 / 2.21 / 2.24 ms per step for 1 / 2 / 4 / 8 groups - no gain, because
+// every group still waits for ITS slowest environment each step and the per-step maximum over 1024
+// environments is almost the maximum over 4096.  Kept (bit-identical results, tests/test_groups.py) as
+// the scaffold for a finer-grained scheme; calls that return after ONE step always use a single launch.
 struct EnvGroup { Batch b; long e0; void* stream; };
 static std::vector<EnvGroup> env_groups(mjbBatch* B, int nstep) {
   static int want = -1;
-  if (want < 0) { const char* s = getenv("MJB_GROUPS"); want = s ? atoi(s) : 4; if (want < 1) want = 1; }
+  if (want < 0) { const char* s = getenv("MJB_GROUPS"); want = s ? atoi(s) : 1; if (want < 1) want = 1; }
   int G = want;
   const int nenv = B->b.nenv;
   if (nstep < 2 || nenv < 64 * G) G = 1;
   std::vector<EnvGroup> out;
-  const int per = ((nenv + G - 1) / G + 3) / 4 * 4;   // whole CTAs (4 envs) per group
+  const int per = ((nenv + G - 1) / G + 7) / 8 * 8;   // whole CTAs (4 or 8 envs) per group
   for (int g = 0, e0 = 0; e0 < nenv; g++, e0 += per) {
     EnvGroup v{B->b, e0, B->stream};
     v.b.nenv = (e0 + per <= nenv) ? per : nenv - e0;

@@ -43,13 +43,21 @@ constexpr int kWarpsPerCta = 4;
 constexpr int kSmemPerWarp = MJB_SMEM_PER_WARP;    // doubles = 6.5 KB: eight sweep vectors, order + draws, and a 4-row ring for nefc <= 64 (or all of AR for nefc <= 24)
 // Specialised per constraint solver (template constant propagated through Env::solver) so that each
 // instantiation carries only its own solver's code and register pressure.
-template <int SOLVER>
+// NLANE = 16 maps TWO small environments onto each warp (models with <= 16 bodies and dofs leave half
+// of a warp idle in every cooperative loop); the two halves synchronise with their own lane masks.
+template <int SOLVER, int NLANE>
 __global__ void __launch_bounds__(32 * kWarpsPerCta, MJB_CTAS_PER_SM) k_step_warp(DModel m, Batch b, int mask, int flags) {
-  __shared__ double smem[kWarpsPerCta * kSmemPerWarp];
-  const int w = threadIdx.x >> 5;
-  const int e = blockIdx.x * kWarpsPerCta + w;
+  constexpr int kPerWarp = 32 / NLANE;
+  __shared__ double smem[NLANE == 32 ? kWarpsPerCta * kSmemPerWarp : 1];
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  const int e = (blockIdx.x * kWarpsPerCta + w) * kPerWarp + l / NLANE;
   if (e >= b.nenv) return;
-  run_env(m, b, e, mask, flags, threadIdx.x & 31, 32, smem + w * kSmemPerWarp, kSmemPerWarp, SOLVER);
+  if (NLANE == 32) {
+    run_env(m, b, e, mask, flags, l, 32, smem + w * kSmemPerWarp, kSmemPerWarp, SOLVER);
+  } else {
+    const unsigned lanes = ((1u << NLANE) - 1u) << ((l / NLANE) * NLANE);
+    run_env(m, b, e, mask, flags, l % NLANE, NLANE, nullptr, 0, SOLVER, lanes);
+  }
 }
 
 // Runge-Kutta phase between forward launches: one warp per environment (coalesced env-major access)
@@ -189,10 +197,15 @@ int launch_fill_zero(const Batch& b, int is_int, long off, long cnt, void* s) {
 
 int launch_stages(const DModel& dm, const Batch& b, int mask, int flags, void* s) {
   if (b.warp_per_env) {
-    const int grid = (b.nenv + kWarpsPerCta - 1) / kWarpsPerCta;
-    if (dm.opt.solver == SOL_PGS) k_step_warp<SOL_PGS><<<grid, 32 * kWarpsPerCta, 0, (cudaStream_t)s>>>(dm, b, mask, flags);
-    else if (dm.opt.solver == SOL_NEWTON) k_step_warp<SOL_NEWTON><<<grid, 32 * kWarpsPerCta, 0, (cudaStream_t)s>>>(dm, b, mask, flags);
-    else k_step_warp<SOL_CG><<<grid, 32 * kWarpsPerCta, 0, (cudaStream_t)s>>>(dm, b, mask, flags);
+    const int per_cta = kWarpsPerCta * (32 / b.nlane);
+    const int grid = (b.nenv + per_cta - 1) / per_cta;
+    cudaStream_t st = (cudaStream_t)s;
+    if (b.nlane == 16) {
+      if (dm.opt.solver == SOL_NEWTON) k_step_warp<SOL_NEWTON, 16><<<grid, 32 * kWarpsPerCta, 0, st>>>(dm, b, mask, flags);
+      else k_step_warp<-1, 16><<<grid, 32 * kWarpsPerCta, 0, st>>>(dm, b, mask, flags);
+    } else if (dm.opt.solver == SOL_PGS) k_step_warp<SOL_PGS, 32><<<grid, 32 * kWarpsPerCta, 0, st>>>(dm, b, mask, flags);
+    else if (dm.opt.solver == SOL_NEWTON) k_step_warp<SOL_NEWTON, 32><<<grid, 32 * kWarpsPerCta, 0, st>>>(dm, b, mask, flags);
+    else k_step_warp<SOL_CG, 32><<<grid, 32 * kWarpsPerCta, 0, st>>>(dm, b, mask, flags);
   } else {
     k_step_lane<<<nblocks(b, 32), 32, 0, (cudaStream_t)s>>>(dm, b, mask, flags);
   }

@@ -64,9 +64,9 @@ MJB_HD bool step_enabled(const Env& d, int flags) {
 // flags: bit0 = part of mj_step (qpos/qvel checks), bit1/bit2 = rollout skip rule (step_enabled).
 // sm/smcap: optional per-warp shared-memory scratch (doubles) used by the latency-critical loops.
 MJB_HD void run_env(const DModel& m, const Batch& b, int e, int mask, int flags, int lane, int nlane,
-                    double* sm, int smcap, int solver = -1) {
+                    double* sm, int smcap, int solver = -1, unsigned lanes = 0xffffffffu) {
   Env d(m, b, e, lane, nlane);
-  d.sm = sm; d.smcap = smcap;
+  d.sm = sm; d.smcap = smcap; d.mask = lanes;
   d.solver = solver < 0 ? m.opt.solver : solver;
   if (!step_enabled(d, flags)) return;
   run_stage_mask(d, mask, flags);

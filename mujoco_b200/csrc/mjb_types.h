@@ -198,7 +198,8 @@ struct Batch {
   size_t stride;   // padded number of environments (native ctrl/state buffers of the rollout)
   size_t dpitch, ipitch;
   int nenv;
-  int warp_per_env;   // 0: one environment per lane (validation mapping), 1: one environment per warp
+  int warp_per_env;   // 0: one environment per lane (validation mapping), 1: cooperative lanes
+  int nlane;          // cooperative lanes per environment: 32 (one warp) or 16 (two small environments per warp)
   Layout L;
 };
 
@@ -214,6 +215,7 @@ struct Env {
   double* sm = nullptr;   // per-warp shared-memory scratch (fused kernel only) and its capacity in doubles
   int smcap = 0;
   int solver = -1;   // constraint solver; a compile-time constant in the specialised fused kernels
+  unsigned mask = 0xffffffffu;   // lanes of the warp that share this environment (sub-warp mapping)
   MJB_HD Env(const DModel& m_, const Batch& b_, int e_, int lane_ = 0, int nlane_ = 1)
       : m(m_), b(b_), e(e_), lane(lane_), nlane(nlane_) {
     hd = b.dbl + (size_t)e * b.dpitch;
@@ -239,7 +241,7 @@ struct Env {
   // barrier + memory ordering between the lanes that share this environment
   MJB_HD void sync() const {
 #if defined(__CUDA_ARCH__)
-    if (nlane > 1) __syncwarp();
+    if (nlane > 1) __syncwarp(mask);
 #endif
   }
 };

@@ -42,3 +42,23 @@ def test_mappings_agree_on_large_batch():
     rel = np.abs(outs[0] - outs[1]).max()
     print("mapping difference", rel)
     assert rel < 1e-9
+
+
+@pytest.mark.parametrize("lanes,solver", [("16", mb.SOLVER_NEWTON), ("32", mb.SOLVER_NEWTON), ("16", mb.SOLVER_PGS), ("16", mb.SOLVER_CG)])
+def test_ant_lane_mappings_vs_golden_and_oracle(lanes, solver, monkeypatch):
+    """small models run two environments per warp (16 cooperative lanes each, own sync masks); every
+    mapping must reproduce the oracle.  MJB_LANES overrides the automatic choice at batch creation."""
+    import os
+    from mjb_util import ANT, make_pair, perturbed_states
+    from oracle_util import available
+    assert available()
+    monkeypatch.setenv("MJB_LANES", lanes)
+    nenv, nstep = 37, 80          # odd count: the last warp holds a single environment
+    m, b, o = make_pair(ANT, solver, nenv=nenv)
+    s0 = perturbed_states(o, nenv, seed=81, height=[0.35, 0.5, 0.75], qvel_std=0.5, qpos_std=0.15)
+    ctrl = np.random.default_rng(82).uniform(-1, 1, (nenv, nstep, o.size("nu")))
+    out = b.rollout(s0, ctrl)
+    ref, stats, _ = o.rollout(s0, ctrl, nthread=os.cpu_count() or 1)
+    assert stats[:, 3].sum() == 0 and (b.warnings() == 0).all()
+    rel = (np.abs(out - ref) / np.maximum(1.0, np.abs(ref).max(axis=(0, 1)))).max()
+    assert rel < 1e-9, rel
