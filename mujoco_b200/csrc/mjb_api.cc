@@ -126,7 +126,7 @@ mjbBatch* mjb_make_batch(const struct mjModel_* m, int nenv, int nconmax, int nj
   // small models (<= 16 bodies and dofs) with a primal solver: two environments per warp.  PGS keeps a
   // whole warp per environment (its on-chip sweep uses warp-wide shuffles).  MJB_LANES=32|16 overrides.
   b.nlane = (H.sz.nbody <= 16 && H.sz.nv <= 16 && H.opt.solver != SOL_PGS) ? 16 : 32;
-  if (const char* ls = getenv("MJB_LANES")) { const int v = atoi(ls); if (v == 16 || v == 32) b.nlane = v; }
+  if (const char* ls = getenv("MJB_LANES")) { const int v = atoi(ls); if (v == 8 || v == 16 || v == 32) b.nlane = v; }
   b.dpitch = ((size_t)b.L.ndbl + 15) / 16 * 16;   // env-major blocks, 128-byte aligned
   b.ipitch = ((size_t)b.L.nint + 31) / 32 * 32;
   size_t nd = b.dpitch * b.stride;
@@ -259,7 +259,7 @@ static std::vector<EnvGroup> env_groups(mjbBatch* B, int nstep) {
   const int nenv = B->b.nenv;
   if (nstep < 2 || nenv < 64 * G) G = 1;
   std::vector<EnvGroup> out;
-  const int per = ((nenv + G - 1) / G + 7) / 8 * 8;   // whole CTAs (4 or 8 envs) per group
+  const int per = ((nenv + G - 1) / G + 15) / 16 * 16;   // whole CTAs (4, 8 or 16 envs) per group
   for (int g = 0, e0 = 0; e0 < nenv; g++, e0 += per) {
     EnvGroup v{B->b, e0, B->stream};
     v.b.nenv = (e0 + per <= nenv) ? per : nenv - e0;

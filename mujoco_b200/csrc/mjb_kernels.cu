@@ -203,6 +203,9 @@ int launch_stages(const DModel& dm, const Batch& b, int mask, int flags, void* s
     if (b.nlane == 16) {
       if (dm.opt.solver == SOL_NEWTON) k_step_warp<SOL_NEWTON, 16><<<grid, 32 * kWarpsPerCta, 0, st>>>(dm, b, mask, flags);
       else k_step_warp<-1, 16><<<grid, 32 * kWarpsPerCta, 0, st>>>(dm, b, mask, flags);
+    } else if (b.nlane == 8) {
+      if (dm.opt.solver == SOL_NEWTON) k_step_warp<SOL_NEWTON, 8><<<grid, 32 * kWarpsPerCta, 0, st>>>(dm, b, mask, flags);
+      else k_step_warp<-1, 8><<<grid, 32 * kWarpsPerCta, 0, st>>>(dm, b, mask, flags);
     } else if (dm.opt.solver == SOL_PGS) k_step_warp<SOL_PGS, 32><<<grid, 32 * kWarpsPerCta, 0, st>>>(dm, b, mask, flags);
     else if (dm.opt.solver == SOL_NEWTON) k_step_warp<SOL_NEWTON, 32><<<grid, 32 * kWarpsPerCta, 0, st>>>(dm, b, mask, flags);
     else k_step_warp<SOL_CG, 32><<<grid, 32 * kWarpsPerCta, 0, st>>>(dm, b, mask, flags);
