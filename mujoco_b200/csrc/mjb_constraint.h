@@ -448,7 +448,7 @@ MJB_HD void constraint_begin(const Env& d) {
   const int nv = m.sz.nv, nefc = d.nefc()[0];
   FD qfc = d.qfrc_constraint(), qacc = d.qacc(), qas = d.qacc_smooth();
   MJB_PFOR(i, nv) qfc[i] = 0;
-  MJB_LANE0 d.solver_niter()[0] = 0;
+  MJB_LANE0 { for (int k = 0; k < NISLAND; k++) d.solver_niter()[k] = 0; }
   if (!nefc) { MJB_PFOR(i, nv) qacc[i] = qas[i]; MJB_PSYNC(); return; }
   MJB_PSYNC();
   FD b = d.efc_b(), aref = d.efc_aref(), force = d.efc_force();
@@ -505,6 +505,94 @@ MJB_HD void dual_state_ptr(const Env& d, const double* force, const double* flos
   MJB_PSYNC();
 }
 
+// ---- constraint islands (mj_island, engine_island.c:455-650) ----------------------------------------
+// Trees coupled by a constraint row belong to one island; islands are numbered by their smallest tree,
+// rows keep their global order inside an island.  Union-find over the (few) kinematic trees, serial on
+// lane 0: unionConstraintTrees :359-455 with the tree iterator :205-330 (friction dof / joint limit: the
+// dof's tree; contact: the two geoms' body trees, -1 = static; tendon rows: scan of the dense Jacobian
+// row), mj_dsuMerge/mj_dsuRoot/mj_dsuAssign :84-160.
+MJB_HD int dsu_root(int* parent, int tree) {
+  int root = tree;
+  while (parent[root] != root) root = parent[root];
+  while (parent[tree] != tree) { const int next = parent[tree]; parent[tree] = root; tree = next; }
+  return root;
+}
+MJB_HD void dsu_merge(int* parent, int t1, int t2) {
+  if (t1 == -1 && t2 == -1) return;
+  if (t1 == -1) t1 = t2;
+  if (t2 == -1) t2 = t1;
+  if (parent[t1] == -1) parent[t1] = t1;
+  if (parent[t2] == -1) parent[t2] = t2;
+  if (parent[t1] == parent[t2]) return;
+  const int r1 = dsu_root(parent, t1), r2 = dsu_root(parent, t2);
+  if (r1 < r2) parent[r2] = r1;
+  else if (r2 < r1) parent[r1] = r2;
+}
+
+// islands are used when the model has several trees and mjDSBL_ISLAND is not set (a single tree is one
+// island that coincides with the monolithic problem)
+MJB_HD bool use_islands(const Env& d) { return d.m.sz.ntree > 1 && !(d.m.opt.disableflags & DSBL_ISLAND); }
+
+MJB_HD void make_islands(const Env& d) {
+  const DModel& m = d.m;
+  if (!use_islands(d)) return;
+  const int nefc = d.nefc()[0], ntree = m.sz.ntree, nv = m.sz.nv;
+  MJB_LANE0 {
+    int* parent = d.tree_island().p + ntree + 1;
+    int* tisl = d.tree_island().p;
+    int* eisl = d.efc_island().p;        // first: the row's tree, then its island
+    FI type = d.efc_type(), id = d.efc_id(), cg1 = d.con_geom1(), cg2 = d.con_geom2();
+    FD J = d.efc_J();
+    for (int t = 0; t < ntree; t++) parent[t] = -1;
+    int ptype = -1, pid = -1;
+    for (int i = 0; i < nefc; i++) {
+      if (i > 0 && ptype == type[i] && pid == id[i]) { eisl[i] = eisl[i - 1]; continue; }
+      ptype = type[i]; pid = id[i];
+      int t1 = -2, t2 = -2;
+      bool scan = false;
+      if (ptype == CNSTR_FRICTION_DOF) t1 = m.dof_treeid[pid];
+      else if (ptype == CNSTR_LIMIT_JOINT) t1 = m.dof_treeid[m.jnt_dofadr[pid]];
+      else if (ptype == CNSTR_CONTACT_PYRAMIDAL || ptype == CNSTR_CONTACT_FRICTIONLESS) {
+        t1 = m.body_treeid[m.geom_bodyid[cg1[pid]]];
+        t2 = m.body_treeid[m.geom_bodyid[cg2[pid]]];
+      } else scan = true;
+      if (!scan) {
+        eisl[i] = t1 >= 0 ? t1 : t2;
+        if (t2 == -2) dsu_merge(parent, t1, -1);
+        else dsu_merge(parent, t1, t2);
+      } else {   // tendon rows: the trees of the nonzero Jacobian entries, in dof order
+        int first = -2, prev = -1;
+        for (int j = 0; j < nv; j++) {
+          if (J[(long)i * nv + j] != 0) {
+            const int tj = m.dof_treeid[j];
+            if (tj == prev) continue;
+            if (first == -2) { first = tj; dsu_merge(parent, tj, -1); }
+            else dsu_merge(parent, prev, tj);
+            prev = tj;
+          }
+        }
+        eisl[i] = first;
+      }
+    }
+    int nisland = 0;
+    for (int t = 0; t < ntree; t++) {
+      if (parent[t] == -1) { tisl[t] = -1; continue; }
+      if (parent[t] == t) tisl[t] = nisland++;
+      else { parent[t] = parent[parent[t]]; tisl[t] = tisl[parent[t]]; }
+    }
+    d.nisland()[0] = nisland;
+    int* adr = d.island_iefcadr().p;
+    int* map = d.map_iefc2efc().p;
+    for (int k = 0; k <= nisland; k++) adr[k] = 0;
+    for (int i = 0; i < nefc; i++) { eisl[i] = tisl[eisl[i]]; adr[eisl[i] + 1]++; }
+    for (int k = 0; k < nisland; k++) adr[k + 1] += adr[k];
+    int* fill = parent;   // reuse as per-island fill counters
+    for (int k = 0; k < nisland; k++) fill[k] = 0;
+    for (int i = 0; i < nefc; i++) { const int k = eisl[i]; map[adr[k] + fill[k]++] = i; }
+  }
+  MJB_PSYNC();
+}
+
 // ---- projected Gauss-Seidel on the dual ------------------------------------------------------------
 // The sweep is a Gauss-Seidel recurrence: row i needs every earlier update of the same sweep, so
 // rows are visited one after the other (PCG32 Fisher-Yates order of the reference).  Inside a row
@@ -521,14 +609,18 @@ MJB_HD void dual_state_ptr(const Env& d, const double* force, const double* flos
 //   MODE 1: vectors on chip; AR rows streamed from L2 through a 4-slot ring of row buffers (each row is
 //           requested four rows ahead of its use, its position in the sweep being known from the shuffle)
 //   MODE 0: everything in global memory (host emulation, lane-per-env mapping, oversized problems)
-template <int MODE>
-MJB_HD int pgs_sweeps(const Env& d, int nefc, int nf, const double* gAR, const double* AR, double* ring,
+// generic sweeps (any lane count, everything in global memory): host emulation, lane-per-env and
+// sub-warp mappings, oversized problems.  rows/nrow: the island's rows in island order (NULL = all rows).
+MJB_HD int pgs_sweeps(const Env& d, int nefc, int nf, const int* rows, int nrow, const double* gAR,
                       double* force, const double* b, const double* floss, const double* ARinv, double* fprev,
                       double* fmom, const double* Adiag, double* shared, int* order) {
   const DModel& m = d.m;
   const int nv = m.sz.nv;
   const int n4 = nefc & ~3, tail = nefc - n4;
   const double scale = 1 / (m.opt.meaninertia * (nv > 1 ? nv : 1));
+  auto row_of = [&](int c) { return rows ? rows[c] : c; };
+  MJB_PFOR(c, nrow) { const int i = row_of(c); order[c] = i; fprev[i] = force[i]; }
+  MJB_PSYNC();
   Pcg32 rng{0, 1};
   pcg32_next(rng);
   int iter = 0, nk = 0;
@@ -537,7 +629,8 @@ MJB_HD int pgs_sweeps(const Env& d, int nefc, int nf, const double* gAR, const d
     double beta = 0;
     if (iter > 0) beta = (double)(nk - 1) / (double)(nk + 2);
     if (beta > 0) {
-      MJB_PFOR(i, nefc) {
+      MJB_PFOR(c, nrow) {
+        const int i = row_of(c);
         const double fs = force[i];
         double f = fs + beta * (fs - fprev[i]);
         fprev[i] = fs;
@@ -547,53 +640,28 @@ MJB_HD int pgs_sweeps(const Env& d, int nefc, int nf, const double* gAR, const d
         fmom[i] = f;
       }
     } else {
-      MJB_PFOR(i, nefc) { fprev[i] = force[i]; fmom[i] = force[i]; }
+      MJB_PFOR(c, nrow) { const int i = row_of(c); fprev[i] = force[i]; fmom[i] = force[i]; }
     }
     MJB_LANE0 {
-      for (int i = nefc - 1; i > 0; i--) {   // Fisher-Yates, same draws as the reference
-        const uint32_t j = pcg32_next(rng) % (uint32_t)(i + 1);
-        const int t = order[i]; order[i] = order[j]; order[j] = t;
+      for (int c = nrow - 1; c > 0; c--) {   // Fisher-Yates, same draws as the reference
+        const uint32_t j = pcg32_next(rng) % (uint32_t)(c + 1);
+        const int t = order[c]; order[c] = order[j]; order[j] = t;
       }
     }
     MJB_PSYNC();
-    double p0 = 0, p1 = 0;   // MODE 1: row in flight from L2 (requested one iteration before it is parked)
-    if (MODE == 1) {   // prime the ring with the first three rows of this sweep, request the fourth
-      for (int q = 0; q < 3 && q < nefc; q++) {
-        const double* g = gAR + order[q] * nefc;
-        MJB_PFOR(c, nefc) ring[q * nefc + c] = g[c];
-      }
-      if (3 < nefc) {
-        const double* g = gAR + order[3] * nefc;
-        if (d.lane < nefc) p0 = g[d.lane];
-        if (d.lane + 32 < nefc) p1 = g[d.lane + 32];
+    double impr = 0;   // meaningful on lane 0
+    for (int bi = 0; bi < nrow; bi++) {
+      const int i = order[bi];
+      const double* row = gAR + (long)i * nefc;
+      // mju_dot structure: four stride-4 partial sums, combined as (r0+r2)+(r1+r3)
+      for (int k = d.lane; k < 4; k += d.nlane) {
+        double r = 0;
+        for (int c = k; c < n4; c += 4) r += row[c] * force[c];
+        shared[1 + k] = r;
       }
       MJB_PSYNC();
-    }
-    double impr = 0;   // meaningful on lane 0
-    for (int bi = 0; bi < nefc; bi++) {
-      const int i = order[bi];
-      const double* row = (MODE == 2) ? AR + i * nefc : (MODE == 1) ? ring + (bi & 3) * nefc : gAR + (long)i * nefc;
-      // mju_dot structure: four stride-4 partial sums, one per lane, combined as (r0+r2)+(r1+r3)
-      double dotv;
-#if defined(__CUDA_ARCH__)
-      if (d.nlane == 32) {
-        double r = 0;
-        if (d.lane < 4) for (int c = d.lane; c < n4; c += 4) r += row[c] * force[c];
-        const double v = r + __shfl_down_sync(0xffffffffu, r, 2);    // lane 0: r0+r2   lane 1: r1+r3
-        dotv = v + __shfl_down_sync(0xffffffffu, v, 1);              // lane 0: (r0+r2)+(r1+r3)
-      } else
-#endif
-      {
-        for (int k = d.lane; k < 4; k += d.nlane) {
-          double r = 0;
-          for (int c = k; c < n4; c += 4) r += row[c] * force[c];
-          shared[1 + k] = r;
-        }
-        MJB_PSYNC();
-        dotv = (shared[1] + shared[3]) + (shared[2] + shared[4]);
-      }
       MJB_LANE0 {
-        double res = dotv;
+        double res = (shared[1] + shared[3]) + (shared[2] + shared[4]);
         if (tail == 3) res += row[n4] * force[n4] + row[n4 + 1] * force[n4 + 1] + row[n4 + 2] * force[n4 + 2];
         else if (tail == 2) res += row[n4] * force[n4] + row[n4 + 1] * force[n4 + 1];
         else if (tail == 1) res += row[n4] * force[n4];
@@ -610,30 +678,18 @@ MJB_HD int pgs_sweeps(const Env& d, int nefc, int nf, const double* gAR, const d
         force[i] = f;
         impr -= change;
       }
-      if (MODE == 1 && bi + 3 < nefc) {
-        // park row bi+3 (requested during the previous iteration) in the slot freed by row bi-1, then
-        // request row bi+4: every row has a full iteration in flight before it is parked
-        double* dst = ring + ((bi + 3) & 3) * nefc;
-        if (d.lane < nefc) dst[d.lane] = p0;
-        if (d.lane + 32 < nefc) dst[d.lane + 32] = p1;
-        if (bi + 4 < nefc) {
-          const double* g = gAR + order[bi + 4] * nefc;
-          if (d.lane < nefc) p0 = g[d.lane];
-          if (d.lane + 32 < nefc) p1 = g[d.lane + 32];
-        }
-      }
       MJB_PSYNC();
     }
     MJB_LANE0 shared[0] = impr * scale;
     MJB_PSYNC();
     const double improvement = shared[0];
-    dual_state_ptr(d, force, floss, nefc, nf);
     bool restart = false;
     if (iter > 0) {   // every lane evaluates the same serial sum: uniform restart decision
       double dce = 0;
-      for (int i = 0; i < nefc; i++) dce += (force[i] - fmom[i]) * (fmom[i] - fprev[i]);
+      for (int c = 0; c < nrow; c++) { const int i = row_of(c); dce += (force[i] - fmom[i]) * (fmom[i] - fprev[i]); }
       restart = dce < 0;
     }
+    MJB_PSYNC();
     if (restart) nk = 0; else nk++;
     iter++;
     if (improvement < m.opt.tolerance) break;
@@ -663,7 +719,7 @@ __device__ inline uint64_t pcg32_skip(uint64_t state, uint32_t delta) {
 // evaluates the projected update redundantly — which removes all divergence/reconvergence from the
 // serial chain.  lo/hi are the projection bounds (-floss/floss for friction rows, 0/inf otherwise).
 template <int MODE>
-__device__ int pgs_sweeps_warp(const Env& d, int nefc, int nf, const double* __restrict__ gAR, const double* AR,
+__device__ int pgs_sweeps_warp(const Env& d, int nefc, int nf, const int* rows, int nrow, const double* __restrict__ gAR, const double* AR,
                                double* ring, double* force, const double* b, const double* lo, const double* hi,
                                const double* ARinv, double* fprev, double* fmom, const double* Adiag,
                                int* order, int* jdraw) {
@@ -672,6 +728,9 @@ __device__ int pgs_sweeps_warp(const Env& d, int nefc, int nf, const double* __r
   const int nv = m.sz.nv, lane = d.lane, k = lane & 3;
   const int n4 = nefc & ~3, tail = nefc - n4, nq = n4 >> 2;
   const double scale = 1 / (m.opt.meaninertia * (nv > 1 ? nv : 1));
+  auto row_of = [&](int c) { return rows ? rows[c] : c; };
+  for (int c = lane; c < nrow; c += 32) { const int i = row_of(c); order[c] = i; fprev[i] = force[i]; }
+  __syncwarp();
   Pcg32 rng{0, 1};
   pcg32_next(rng);
   uint64_t s0 = rng.state;
@@ -681,7 +740,8 @@ __device__ int pgs_sweeps_warp(const Env& d, int nefc, int nf, const double* __r
     double beta = 0;
     if (iter > 0) beta = (double)(nk - 1) / (double)(nk + 2);
     if (beta > 0) {
-      for (int i = lane; i < nefc; i += 32) {
+      for (int c = lane; c < nrow; c += 32) {
+        const int i = row_of(c);
         const double fs = force[i];
         double f = fs + beta * (fs - fprev[i]);
         fprev[i] = fs;
@@ -690,20 +750,20 @@ __device__ int pgs_sweeps_warp(const Env& d, int nefc, int nf, const double* __r
         fmom[i] = f;
       }
     } else {
-      for (int i = lane; i < nefc; i += 32) { fprev[i] = force[i]; fmom[i] = force[i]; }
+      for (int c = lane; c < nrow; c += 32) { const int i = row_of(c); fprev[i] = force[i]; fmom[i] = force[i]; }
     }
     // Fisher-Yates draws of this sweep (draw t serves position i = nefc-1-t), one per lane
-    for (int t = lane; t < nefc - 1; t += 32) {
+    for (int t = lane; t < nrow - 1; t += 32) {
       const uint64_t old = pcg32_skip(s0, (uint32_t)t);
       const uint32_t xs = (uint32_t)(((old >> 18u) ^ old) >> 27u), rot = (uint32_t)(old >> 59u);
       const uint32_t out = (xs >> rot) | (xs << ((0u - rot) & 31));
-      const int i = nefc - 1 - t;
+      const int i = nrow - 1 - t;
       jdraw[i] = (int)(out % (uint32_t)(i + 1));
     }
-    s0 = pcg32_skip(s0, (uint32_t)(nefc - 1));
+    s0 = pcg32_skip(s0, (uint32_t)(nrow - 1));
     __syncwarp();
     if (lane == 0) {
-      for (int i = nefc - 1; i > 0; i--) {
+      for (int i = nrow - 1; i > 0; i--) {
         const int j = jdraw[i];
         const int t = order[i]; order[i] = order[j]; order[j] = t;
       }
@@ -711,11 +771,11 @@ __device__ int pgs_sweeps_warp(const Env& d, int nefc, int nf, const double* __r
     __syncwarp();
     double p0 = 0, p1 = 0;
     if (MODE == 1) {
-      for (int q = 0; q < 3 && q < nefc; q++) {
+      for (int q = 0; q < 3 && q < nrow; q++) {
         const double* g = gAR + order[q] * nefc;
         for (int c = lane; c < nefc; c += 32) ring[q * nefc + c] = g[c];
       }
-      if (3 < nefc) {
+      if (3 < nrow) {
         const double* g = gAR + order[3] * nefc;
         if (lane < nefc) p0 = g[lane];
         if (lane + 32 < nefc) p1 = g[lane + 32];
@@ -726,9 +786,9 @@ __device__ int pgs_sweeps_warp(const Env& d, int nefc, int nf, const double* __r
     int inext = order[0];
     const double* glane = gAR + lane;
     asm volatile("" : "+l"(glane));   // keep the lane's AR base in registers (no per-row re-derivation)
-    for (int bi = 0; bi < nefc; bi++) {
+    for (int bi = 0; bi < nrow; bi++) {
       const int i = inext;
-      inext = order[bi + 1 < nefc ? bi + 1 : bi];
+      inext = order[bi + 1 < nrow ? bi + 1 : bi];
       const double* row = (MODE == 2) ? AR + i * nefc : ring + (bi & 3) * nefc;
       const double bi_ = b[i], ainv = ARinv[i], ad = Adiag[i], l = lo[i], h = hi[i], old = force[i];
       double r = 0;
@@ -754,11 +814,11 @@ __device__ int pgs_sweeps_warp(const Env& d, int nefc, int nf, const double* __r
       if (change > 1e-10) { f = old; change = 0; }
       if (lane == 0) force[i] = f;
       impr -= change;
-      if (MODE == 1 && bi + 3 < nefc) {
+      if (MODE == 1 && bi + 3 < nrow) {
         double* dst = ring + ((bi + 3) & 3) * nefc;
         if (lane < nefc) dst[lane] = p0;
         if (lane + 32 < nefc) dst[lane + 32] = p1;
-        if (bi + 4 < nefc) {
+        if (bi + 4 < nrow) {
           const double* g = glane + order[bi + 4] * nefc;
           if (lane < nefc) p0 = g[0];
           if (lane + 32 < nefc) p1 = g[32];
@@ -773,9 +833,10 @@ __device__ int pgs_sweeps_warp(const Env& d, int nefc, int nf, const double* __r
       if (lane < nefc) q0 = (force[lane] - fmom[lane]) * (fmom[lane] - fprev[lane]);
       if (lane + 32 < nefc) q1 = (force[lane + 32] - fmom[lane + 32]) * (fmom[lane + 32] - fprev[lane + 32]);
       double dce = 0;
-      const int nlo = nefc < 32 ? nefc : 32;
-      for (int i = 0; i < nlo; i++) dce += __shfl_sync(full, q0, i);
-      for (int i = 32; i < nefc; i++) dce += __shfl_sync(full, q1, i - 32);
+      for (int c = 0; c < nrow; c++) {
+        const int i = row_of(c);
+        dce += __shfl_sync(full, i < 32 ? q0 : q1, i & 31);
+      }
       restart = dce < 0;
     }
     if (restart) nk = 0; else nk++;
@@ -791,7 +852,14 @@ MJB_HD void solve_pgs(const Env& d) {
   const int nefc = d.nefc()[0], nf = d.nf()[0], njmax = m.sz.njmax;
   if (!nefc) return;
   const double* gAR = d.efc_AR().p;
-  int iter;
+  // islands (mj_fwdConstraint, engine_forward.c:1187-1194): one independent PGS solve per island over the
+  // island's rows, each with its own shuffle stream, momentum state, iteration count and termination; the
+  // residual of a row is still the dot with the FULL force vector (entries of other islands meet exact zeros)
+  const bool isl = use_islands(d);
+  const int nsolve = isl ? d.nisland()[0] : 1;
+  const int* iadr = d.island_iefcadr().p;
+  const int* imap = d.map_iefc2efc().p;
+  FI niter = d.solver_niter();
 #if defined(__CUDA_ARCH__)
   int mode = 0;
   const int nord = (nefc + 1) / 2;   // doubles that hold nefc ints
@@ -810,19 +878,24 @@ MJB_HD void solve_pgs(const Env& d) {
     const double* gf = d.efc_force().p; const double* gb = d.efc_b().p; const double* gfl = d.efc_frictionloss().p;
     if (mode == 2) { MJB_PFOR(i, nefc * nefc) AR[i] = gAR[i]; }
     MJB_PFOR(i, nefc) {
-      const double f0 = gf[i];
-      force[i] = f0; fprev[i] = f0; b[i] = gb[i];
+      force[i] = gf[i]; b[i] = gb[i];
       const double fl = gfl[i];
       lo[i] = (i < nf) ? -fl : 0.0;
       hi[i] = (i < nf) ? fl : HUGE_VAL;
       const double ai = 1 / gAR[(long)i * (nefc + 1)];
       ARinv[i] = ai;
       Adiag[i] = 1 / ai;    // the reference's Athis[0] = 1/ARinv
-      order[i] = i;
     }
     MJB_PSYNC();
-    if (mode == 2) iter = pgs_sweeps_warp<2>(d, nefc, nf, gAR, AR, ring, force, b, lo, hi, ARinv, fprev, fmom, Adiag, order, jdraw);
-    else iter = pgs_sweeps_warp<1>(d, nefc, nf, gAR, AR, ring, force, b, lo, hi, ARinv, fprev, fmom, Adiag, order, jdraw);
+    for (int k = 0; k < nsolve; k++) {
+      const int* rows = isl ? imap + iadr[k] : nullptr;
+      const int nrow = isl ? iadr[k + 1] - iadr[k] : nefc;
+      int iter;
+      if (mode == 2) iter = pgs_sweeps_warp<2>(d, nefc, nf, rows, nrow, gAR, AR, ring, force, b, lo, hi, ARinv, fprev, fmom, Adiag, order, jdraw);
+      else iter = pgs_sweeps_warp<1>(d, nefc, nf, rows, nrow, gAR, AR, ring, force, b, lo, hi, ARinv, fprev, fmom, Adiag, order, jdraw);
+      MJB_PSYNC();
+      MJB_LANE0 if (k < NISLAND) niter[k] += iter;
+    }
     MJB_PSYNC();
     double* gfo = d.efc_force().p;
     MJB_PFOR(i, nefc) gfo[i] = force[i];
@@ -837,18 +910,21 @@ MJB_HD void solve_pgs(const Env& d) {
     double* shared = scr + 4 * (long)njmax;
     int* order = d.scr_int().p + njmax;
     MJB_PFOR(i, nefc) {
-      fprev[i] = force[i];
       const double ai = 1 / gAR[(long)i * (nefc + 1)];
       ARinv[i] = ai;
       Adiag[i] = 1 / ai;
-      order[i] = i;
+    }
+    MJB_PSYNC();
+    for (int k = 0; k < nsolve; k++) {
+      const int* rows = isl ? imap + iadr[k] : nullptr;
+      const int nrow = isl ? iadr[k + 1] - iadr[k] : nefc;
+      const int iter = pgs_sweeps(d, nefc, nf, rows, nrow, gAR, force, b, floss, ARinv, fprev, fmom, Adiag, shared, order);
+      MJB_PSYNC();
+      MJB_LANE0 if (k < NISLAND) niter[k] += iter;
     }
     MJB_PSYNC();
     dual_state_ptr(d, force, floss, nefc, nf);
-    iter = pgs_sweeps<0>(d, nefc, nf, gAR, nullptr, nullptr, force, b, floss, ARinv, fprev, fmom, Adiag, shared, order);
   }
-  MJB_PSYNC();
-  MJB_LANE0 d.solver_niter()[0] += iter;
   MJB_PSYNC();
 }
 

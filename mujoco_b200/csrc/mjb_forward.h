@@ -29,7 +29,7 @@ MJB_HD void reset_env(const Env& d, bool clear_warnings) {
   for (int i = 0; i < m.sz.nv; i++) { qvel[i] = 0; ws[i] = 0; qa[i] = 0; d.qacc()[i] = 0; }
   for (int i = 0; i < m.sz.nu; i++) ctrl[i] = 0;
   d.time()[0] = 0;
-  d.ncon()[0] = 0; d.nefc()[0] = 0; d.ne()[0] = 0; d.nf()[0] = 0; d.nl()[0] = 0; d.solver_niter()[0] = 0;
+  d.ncon()[0] = 0; d.nefc()[0] = 0; d.ne()[0] = 0; d.nf()[0] = 0; d.nl()[0] = 0; for (int k = 0; k < NISLAND; k++) d.solver_niter()[k] = 0;
   if (clear_warnings) for (int i = 0; i < NWARNING; i++) d.warning()[i] = 0;
 }
 
@@ -64,6 +64,7 @@ MJB_HD void fwd_position(const Env& d) {
   }
   collision(d);
   make_constraint(d);
+  make_islands(d);
   project_constraint(d);
   transmission(d);
 }

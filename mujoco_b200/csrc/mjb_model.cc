@@ -358,6 +358,7 @@ int build_host_model(const mjModel* m, int nconmax, int njmax, HostModel* out) {
   B.addI(&D.dof_parentid, m->dof_parentid, m->nv);
   B.addI(&D.dof_simplenum, m->dof_simplenum, m->nv);
   B.addI(&D.dof_treeid, m->dof_treeid, m->nv);
+  B.addI(&D.body_treeid, m->body_treeid, m->nbody);
   B.addI(&D.M_rownnz, m->M_rownnz, m->nv);
   B.addI(&D.M_rowadr, m->M_rowadr, m->nv);
   B.addI(&D.M_colind, m->M_colind, m->nC);
@@ -674,7 +675,10 @@ int build_host_model(const mjModel* m, int nconmax, int njmax, HostModel* out) {
   S.njmax = njmax;
   if (O.solver == mjSOL_PGS && !O.dense) { set_error("unsupported: PGS with sparse Jacobian (nv >= 60)"); return -2; }
   if (!O.dense) { set_error("unsupported: sparse-Jacobian models (nv >= 60) are a 'next' row"); return -2; }
-  if (S.ntree != 1) { set_error("unsupported: multi-tree models (constraint islands) are a 'next' row"); return -2; }
+  if (S.ntree != 1 && !(O.disableflags & mjDSBL_ISLAND) && O.solver != mjSOL_PGS) {
+    set_error("unsupported: Newton/CG on multi-tree models with constraint islands (use PGS, or disable islands)");
+    return -2;
+  }
   if (O.solver != mjSOL_PGS && O.solver != mjSOL_NEWTON && O.solver != mjSOL_CG) { set_error("unsupported: unknown solver"); return -2; }
 
   B.fix();

@@ -31,7 +31,8 @@ enum { CNSTR_EQUALITY = 0, CNSTR_FRICTION_DOF = 1, CNSTR_FRICTION_TENDON = 2, CN
 enum { STATE_SATISFIED = 0, STATE_QUADRATIC = 1, STATE_LINEARNEG = 2, STATE_LINEARPOS = 3,
        STATE_CONE = 4 };                                                                // :544-548
 enum { WARN_INERTIA = 0, WARN_CONTACTFULL = 1, WARN_CNSTRFULL = 2, WARN_BADQPOS = 3,
-       WARN_BADQVEL = 4, WARN_BADQACC = 5, WARN_BADCTRL = 6, WARN_VGEOMFULL = 7, NWARNING = 8 };  // :553-561
+       WARN_BADQVEL = 4, WARN_BADQACC = 5, WARN_BADCTRL = 6, WARN_VGEOMFULL = 7, NWARNING = 8 };
+enum { NISLAND = 20 };   // mjNISLAND: islands with solver statistics (mjdata.h)  // :553-561
 enum { SOL_PGS = 0, SOL_CG = 1, SOL_NEWTON = 2 };                                        // :202-204
 enum { INT_EULER = 0, INT_RK4 = 1, INT_IMPLICIT = 2, INT_IMPLICITFAST = 3 };             // :181-184
 enum { SAMEFRAME_NONE = 0, SAMEFRAME_BODY = 1, SAMEFRAME_INERTIA = 2, SAMEFRAME_BODYROT = 3,
@@ -79,7 +80,7 @@ struct Options {
   X(jnt_type) X(jnt_qposadr) X(jnt_dofadr) X(jnt_bodyid) X(jnt_limited) X(jnt_actfrclimited) \
   X(dof_bodyid) X(dof_jntid) X(dof_parentid) X(dof_simplenum) X(dof_treeid)                  \
   X(M_rownnz) X(M_rowadr) X(M_colind)                                                       \
-  X(geom_type) X(geom_bodyid) X(geom_sameframe)                                              \
+  X(geom_type) X(geom_bodyid) X(geom_sameframe) X(body_treeid)                                              \
   X(tendon_adr) X(tendon_num) X(tendon_limited) X(wrap_type) X(wrap_objid)                   \
   X(ten_J_rownnz) X(ten_J_rowadr) X(ten_J_colind)                                            \
   X(actuator_trnjnt) X(actuator_gaintype) X(actuator_biastype) X(actuator_ctrllimited)       \
@@ -149,7 +150,8 @@ struct DModel {
 
 // ints (all hot)
 #define MJB_DATA_INT_FIELDS(X, S)                                                            \
-  X(ncon, 1) X(nefc, 1) X(ne, 1) X(nf, 1) X(nl, 1) X(solver_niter, 1) X(step_skip, 1) X(warning, NWARNING)     \
+  X(ncon, 1) X(nefc, 1) X(ne, 1) X(nf, 1) X(nl, 1) X(solver_niter, NISLAND) X(step_skip, 1) X(warning, NWARNING)  \
+  X(nisland, 1) X(efc_island, S.njmax) X(map_iefc2efc, S.njmax) X(island_iefcadr, S.ntree + 2) X(tree_island, 2 * S.ntree + 2)     \
   X(con_geom1, S.nconmax) X(con_geom2, S.nconmax) X(con_dim, S.nconmax)                       \
   X(con_exclude, S.nconmax) X(con_efcadr, S.nconmax) X(con_pair, S.nconmax)                    \
   X(efc_type, S.njmax) X(efc_id, S.njmax) X(efc_state, S.njmax) X(nwt_state, S.njmax) X(scr_int, 4 * S.njmax)        \

@@ -63,6 +63,7 @@ def compare_forward(b, o, states, ctrl, rtol, exact=False, check_dual=True):
     """run mj_forward per env on the oracle and compare every hot-path field; returns worst rel err"""
     b.set_state(states)
     b.set_field("ctrl", ctrl)
+    b.set_field("qacc_warmstart", 0.0)     # the oracle side starts from mj_resetData
     b.forward()
     got = {f: b.field(f) for f in FIELDS_POS + FIELDS_VEL + FIELDS_EFC +
            ["efc_J", "efc_KBIP", "efc_AR", "efc_Y", "qacc", "qfrc_constraint", "con_dist", "con_pos", "con_frame"]}
@@ -79,6 +80,8 @@ def compare_forward(b, o, states, ctrl, rtol, exact=False, check_dual=True):
         assert gi["nefc"][e, 0] == nefc, (e, gi["nefc"][e, 0], nefc)
         assert np.array_equal(gi["efc_type"][e, :nefc], np.array(o.dfield("efc_type"))[:nefc])
         assert np.array_equal(gi["efc_id"][e, :nefc], np.array(o.dfield("efc_id"))[:nefc])
+        nit = np.array(o.dfield("solver_niter"))
+        assert np.array_equal(gi["solver_niter"][e, :len(nit)], nit), (e, gi["solver_niter"][e], nit)   # per island
 
         def chk(name, ref, n=None):
             nonlocal worst
