@@ -126,7 +126,7 @@ mjbBatch* mjb_make_batch(const struct mjModel_* m, int nenv, int nconmax, int nj
   // small models (<= 16 bodies and dofs) with a primal solver: two environments per warp.  PGS keeps a
   // whole warp per environment (its on-chip sweep uses warp-wide shuffles).  MJB_LANES=32|16 overrides.
   b.nlane = (H.sz.nbody <= 16 && H.sz.nv <= 16 && H.opt.solver != SOL_PGS) ? 16 : 32;
-  if (const char* ls = getenv("MJB_LANES")) { const int v = atoi(ls); if (v == 8 || v == 16 || v == 32) b.nlane = v; }
+  if (const char* ls = getenv("MJB_LANES")) { const int v = atoi(ls); if (v == 16 || v == 32) b.nlane = v; }
   b.dpitch = ((size_t)b.L.ndbl + 15) / 16 * 16;   // env-major blocks, 128-byte aligned
   b.ipitch = ((size_t)b.L.nint + 31) / 32 * 32;
   size_t nd = b.dpitch * b.stride;

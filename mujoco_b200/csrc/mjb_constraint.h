@@ -443,6 +443,8 @@ MJB_HD void mul_M(const Env& d, FD res, FD vec) {
   }
   MJB_PSYNC();
 }
+MJB_HD bool use_islands(const Env& d);
+
 MJB_HD void constraint_begin(const Env& d) {
   const DModel& m = d.m;
   const int nv = m.sz.nv, nefc = d.nefc()[0];
@@ -483,6 +485,11 @@ MJB_HD void constraint_begin(const Env& d) {
       MJB_PSYNC();
       const double cost_smooth = constraint_update(d, b, true);
       if (cost_ws > cost_smooth) { MJB_PFOR(i, nv) qacc[i] = qas[i]; }
+      MJB_PSYNC();
+    }
+    if (use_islands(d)) {   // dofs outside every island are unconstrained: qacc = qacc_smooth
+      const int* tisl = d.tree_island().p;
+      MJB_PFOR(j, nv) { if (tisl[m.dof_treeid[j]] < 0) qacc[j] = qas[j]; }
       MJB_PSYNC();
     }
   } else {
@@ -589,6 +596,20 @@ MJB_HD void make_islands(const Env& d) {
     int* fill = parent;   // reuse as per-island fill counters
     for (int k = 0; k < nisland; k++) fill[k] = 0;
     for (int i = 0; i < nefc; i++) { const int k = eisl[i]; map[adr[k] + fill[k]++] = i; }
+    // dofs: island order = global order inside each island; unconstrained dofs go last
+    int* dadr = d.island_idofadr().p;
+    int* i2d = d.map_idof2dof().p;
+    int* d2i = d.map_dof2idof().p;
+    for (int k = 0; k <= nisland + 1; k++) dadr[k] = 0;
+    for (int j = 0; j < nv; j++) { const int k = tisl[m.dof_treeid[j]]; dadr[(k >= 0 ? k : nisland) + 1]++; }
+    for (int k = 0; k <= nisland; k++) dadr[k + 1] += dadr[k];
+    for (int k = 0; k <= nisland; k++) fill[k] = 0;
+    for (int j = 0; j < nv; j++) {
+      int k = tisl[m.dof_treeid[j]];
+      if (k < 0) k = nisland;
+      const int idof = dadr[k] + fill[k]++;
+      i2d[idof] = j; d2i[j] = idof;
+    }
   }
   MJB_PSYNC();
 }

@@ -17,6 +17,7 @@
 #include "mjb_backend.h"
 #include "mjb_model.h"
 #include "mjb_stage.h"
+#include "mjb_kstep.h"   // kWarpsPerCta + launchers of the fused step kernel (one translation unit per instantiation)
 
 namespace mjb {
 
@@ -25,39 +26,6 @@ __global__ void __launch_bounds__(32) k_step_lane(DModel m, Batch b, int mask, i
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= b.nenv) return;
   run_env(m, b, e, mask, flags, 0, 1, nullptr, 0);
-}
-
-// FUSED STEP KERNEL: one warp per environment, all pipeline stages of mj_step in one launch.
-// The environment's block lives in global memory (env-major: the 32 lanes touch consecutive
-// elements, one 256-byte line per 32 doubles) and is kept hot by L1/L2; occupancy, not staging, hides
-// the latency of the short dependent chains (measured: 3.7x faster than staging the whole block in
-// shared memory, which capped residency at 3 warps/SM).  Each warp owns kSmemPerWarp doubles of
-// shared memory used by the one truly serial loop, the PGS sweep (AR + sweep vectors on chip).
-constexpr int kWarpsPerCta = 4;
-#ifndef MJB_CTAS_PER_SM
-#define MJB_CTAS_PER_SM 7   // 28 warps/SM: a 4096-env batch is resident in ONE wave on 148 SMs (needs <= 72 regs)
-#endif
-#ifndef MJB_SMEM_PER_WARP
-#define MJB_SMEM_PER_WARP 832
-#endif
-constexpr int kSmemPerWarp = MJB_SMEM_PER_WARP;    // doubles = 6.5 KB: eight sweep vectors, order + draws, and a 4-row ring for nefc <= 64 (or all of AR for nefc <= 24)
-// Specialised per constraint solver (template constant propagated through Env::solver) so that each
-// instantiation carries only its own solver's code and register pressure.
-// NLANE = 16 maps TWO small environments onto each warp (models with <= 16 bodies and dofs leave half
-// of a warp idle in every cooperative loop); the two halves synchronise with their own lane masks.
-template <int SOLVER, int NLANE>
-__global__ void __launch_bounds__(32 * kWarpsPerCta, MJB_CTAS_PER_SM) k_step_warp(DModel m, Batch b, int mask, int flags) {
-  constexpr int kPerWarp = 32 / NLANE;
-  __shared__ double smem[NLANE == 32 ? kWarpsPerCta * kSmemPerWarp : 1];
-  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-  const int e = (blockIdx.x * kWarpsPerCta + w) * kPerWarp + l / NLANE;
-  if (e >= b.nenv) return;
-  if (NLANE == 32) {
-    run_env(m, b, e, mask, flags, l, 32, smem + w * kSmemPerWarp, kSmemPerWarp, SOLVER);
-  } else {
-    const unsigned lanes = ((1u << NLANE) - 1u) << ((l / NLANE) * NLANE);
-    run_env(m, b, e, mask, flags, l % NLANE, NLANE, nullptr, 0, SOLVER, lanes);
-  }
 }
 
 // Runge-Kutta phase between forward launches: one warp per environment (coalesced env-major access)
@@ -197,18 +165,12 @@ int launch_fill_zero(const Batch& b, int is_int, long off, long cnt, void* s) {
 
 int launch_stages(const DModel& dm, const Batch& b, int mask, int flags, void* s) {
   if (b.warp_per_env) {
-    const int per_cta = kWarpsPerCta * (32 / b.nlane);
-    const int grid = (b.nenv + per_cta - 1) / per_cta;
-    cudaStream_t st = (cudaStream_t)s;
     if (b.nlane == 16) {
-      if (dm.opt.solver == SOL_NEWTON) k_step_warp<SOL_NEWTON, 16><<<grid, 32 * kWarpsPerCta, 0, st>>>(dm, b, mask, flags);
-      else k_step_warp<-1, 16><<<grid, 32 * kWarpsPerCta, 0, st>>>(dm, b, mask, flags);
-    } else if (b.nlane == 8) {
-      if (dm.opt.solver == SOL_NEWTON) k_step_warp<SOL_NEWTON, 8><<<grid, 32 * kWarpsPerCta, 0, st>>>(dm, b, mask, flags);
-      else k_step_warp<-1, 8><<<grid, 32 * kWarpsPerCta, 0, st>>>(dm, b, mask, flags);
-    } else if (dm.opt.solver == SOL_PGS) k_step_warp<SOL_PGS, 32><<<grid, 32 * kWarpsPerCta, 0, st>>>(dm, b, mask, flags);
-    else if (dm.opt.solver == SOL_NEWTON) k_step_warp<SOL_NEWTON, 32><<<grid, 32 * kWarpsPerCta, 0, st>>>(dm, b, mask, flags);
-    else k_step_warp<SOL_CG, 32><<<grid, 32 * kWarpsPerCta, 0, st>>>(dm, b, mask, flags);
+      if (dm.opt.solver == SOL_NEWTON) launch_kstep_newton16(dm, b, mask, flags, s);
+      else launch_kstep_any16(dm, b, mask, flags, s);
+    } else if (dm.opt.solver == SOL_PGS) launch_kstep_pgs32(dm, b, mask, flags, s);
+    else if (dm.opt.solver == SOL_NEWTON) launch_kstep_newton32(dm, b, mask, flags, s);
+    else launch_kstep_cg32(dm, b, mask, flags, s);
   } else {
     k_step_lane<<<nblocks(b, 32), 32, 0, (cudaStream_t)s>>>(dm, b, mask, flags);
   }

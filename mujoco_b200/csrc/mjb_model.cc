@@ -675,10 +675,6 @@ int build_host_model(const mjModel* m, int nconmax, int njmax, HostModel* out) {
   S.njmax = njmax;
   if (O.solver == mjSOL_PGS && !O.dense) { set_error("unsupported: PGS with sparse Jacobian (nv >= 60)"); return -2; }
   if (!O.dense) { set_error("unsupported: sparse-Jacobian models (nv >= 60) are a 'next' row"); return -2; }
-  if (S.ntree != 1 && !(O.disableflags & mjDSBL_ISLAND) && O.solver != mjSOL_PGS) {
-    set_error("unsupported: Newton/CG on multi-tree models with constraint islands (use PGS, or disable islands)");
-    return -2;
-  }
   if (O.solver != mjSOL_PGS && O.solver != mjSOL_NEWTON && O.solver != mjSOL_CG) { set_error("unsupported: unknown solver"); return -2; }
 
   B.fix();

@@ -26,9 +26,23 @@ namespace mjb {
 
 struct LsPoint { double alpha, cost, d0, d1; };
 
+// the sub-problem one primal solve works on: all rows and dofs (monolithic), or the rows and dofs of one
+// constraint island in island order (engine_solver.c PrimalPointers/PrimalAllocate :1095-1366: the
+// reference gathers island-local copies iacc, ifrc_*, iM, iefc_J; here the global arrays are indexed
+// through the island maps, which performs the same arithmetic on the same operands in the same order)
+struct IslView {
+  const int* rows; int nrow;      // island row c -> global efc row (NULL: identity)
+  const int* dofs; int ndof;      // island dof k -> global dof (NULL: identity)
+  const int* dof2idof; int base;  // global dof -> island dof = dof2idof[dof] - base
+  MJB_HD int row(int c) const { return rows ? rows[c] : c; }
+  MJB_HD int dof(int k) const { return dofs ? dofs[k] : k; }
+  MJB_HD int loc(int dof_) const { return dofs ? dof2idof[dof_] - base : dof_; }
+};
+
 struct NewtonCtx {
-  int nv, nefc, nf;
-  FD J, Jaref, Jv, quad, Dq, Ma, Mv, grad, Mgrad, search, cholupd, L;
+  IslView v;
+  int nv, nefc, nf;               // nv: global dof count (row pitch of J); nefc/nf: global
+  FD J, Jaref, Jv, quad, Dq, Ma, Mv, grad, Mgrad, search, cholupd, L;   // Ma..cholupd, L: island-local
   FD efcD, efcR, floss, qfs, qas, qacc;
   FI state, oldstate;
   double quadGauss[3];
@@ -51,12 +65,87 @@ MJB_HD double friction_cost_dif(double start, double x, double f, double Rf, dou
   return friction_cost(x, f, Rf, D) - friction_cost(start, f, Rf, D);
 }
 
-// efc_force / efc_state / cost from Jaref, qfrc_constraint = J' force, plus the Gauss term
+// res = M * vec on the view's dofs (vectors island-local): mju_mulSymVecSparse order per output dof —
+// diagonal term, own-row off-diagonals from the last column to the first, descendant rows ascending
+MJB_HD void mul_M_view(const Env& d, const IslView& v, FD res, FD vec) {
+  const DModel& m = d.m;
+  FD M = d.M();
+  MJB_PFOR(k, v.ndof) {
+    const int i = v.dof(k);
+    const int adr = m.M_rowadr[i], nnz = m.M_rownnz[i];
+    double s = M[adr + nnz - 1] * vec[k];
+    for (int a = nnz - 2; a >= 0; a--) s += M[adr + a] * vec[v.loc(m.M_colind[adr + a])];
+    const int a0 = m.mt_adr[i], an = m.mt_adr[i + 1] - a0;
+    for (int c = an - 1; c >= 0; c--) s += M[m.mt_qadr[a0 + c]] * vec[v.loc(m.mt_dof[a0 + c])];
+    res[k] = s;
+  }
+  MJB_PSYNC();
+}
+
+// res[row] = J(row, view dofs) . vec   (mju_mulMatVec on the island block)
+MJB_HD void mul_jac_view(const Env& d, const NewtonCtx& c, FD res, FD vec) {
+  const IslView& v = c.v;
+  MJB_PFOR(cc, v.nrow) {
+    const int i = v.row(cc);
+    res[i] = dot_ref(v.ndof, [&](int k) { return c.J[(long)i * c.nv + v.dof(k)]; }, [&](int k) { return vec[k]; });
+  }
+  MJB_PSYNC();
+}
+
+// x = M^-1 x for an island-local vector: embedded in a global vector (zeros elsewhere; trees do not
+// couple in L'DL, so the island's dofs see exactly the operations of the block solve)
+MJB_HD void solve_M_view(const Env& d, const IslView& v, FD x) {
+  if (!v.dofs) { solve_LD(d, x, d.qLD(), d.qLDiagInv()); return; }
+  FD g = d.scr_nv() + 2 * d.m.sz.nv;
+  MJB_PFOR(i, d.m.sz.nv) g[i] = 0;
+  MJB_PSYNC();
+  MJB_PFOR(k, v.ndof) g[v.dof(k)] = x[k];
+  MJB_PSYNC();
+  solve_LD(d, g, d.qLD(), d.qLDiagInv());
+  MJB_PFOR(k, v.ndof) x[k] = g[v.dof(k)];
+  MJB_PSYNC();
+}
+
+// efc_force / efc_state / cost from Jaref (mj_constraintUpdate_impl on the view's rows),
+// qfrc_constraint = J' force on the view's dofs, plus the Gauss term
 MJB_HD void newton_update_constraint(const Env& d, NewtonCtx& c) {
-  double s = constraint_update(d, c.Jaref, true);
+  const IslView& v = c.v;
+  FD force = d.efc_force(), qfc = d.qfrc_constraint();
+  MJB_PFOR(cc, v.nrow) {
+    const int i = v.row(cc);
+    const double jar = c.Jaref[i];
+    double f = -c.efcD[i] * jar;
+    int st;
+    if (i < c.nf) {
+      if (jar <= -c.efcR[i] * c.floss[i]) { f = c.floss[i]; st = STATE_LINEARNEG; }
+      else if (jar >= c.efcR[i] * c.floss[i]) { f = -c.floss[i]; st = STATE_LINEARPOS; }
+      else st = STATE_QUADRATIC;
+    } else if (jar >= 0) { f = 0; st = STATE_SATISFIED; }
+    else st = STATE_QUADRATIC;
+    force[i] = f; c.state[i] = st;
+  }
+  MJB_PSYNC();
+  double s = 0;
+  for (int cc = 0; cc < v.nrow; cc++) {
+    const int i = v.row(cc), st = c.state[i];
+    const double jar = c.Jaref[i];
+    if (st == STATE_LINEARNEG) s += -0.5 * c.efcR[i] * c.floss[i] * c.floss[i] - c.floss[i] * jar;
+    else if (st == STATE_LINEARPOS) s += -0.5 * c.efcR[i] * c.floss[i] * c.floss[i] + c.floss[i] * jar;
+    else if (st == STATE_QUADRATIC) s += 0.5 * c.efcD[i] * jar * jar;
+  }
+  MJB_PFOR(k, v.ndof) {
+    const int dof = v.dof(k);
+    double q = 0;
+    for (int cc = 0; cc < v.nrow; cc++) {
+      const int i = v.row(cc);
+      const double f = force[i];
+      if (f != 0) q += c.J[(long)i * c.nv + dof] * f;
+    }
+    qfc[dof] = q;
+  }
   MJB_PSYNC();
   double gauss = 0;
-  for (int i = 0; i < c.nv; i++) gauss += 0.5 * (c.Ma[i] - c.qfs[i]) * (c.qacc[i] - c.qas[i]);
+  for (int k = 0; k < v.ndof; k++) { const int dof = v.dof(k); gauss += 0.5 * (c.Ma[k] - c.qfs[dof]) * (c.qacc[dof] - c.qas[dof]); }
   c.quadGauss[0] = gauss;
   s += gauss;
   c.cost = s;
@@ -64,7 +153,7 @@ MJB_HD void newton_update_constraint(const Env& d, NewtonCtx& c) {
 
 MJB_HD void newton_update_grad(const Env& d, NewtonCtx& c) {
   FD qfc = d.qfrc_constraint();
-  MJB_PFOR(i, c.nv) c.grad[i] = c.Ma[i] - c.qfs[i] - qfc[i];
+  MJB_PFOR(k, c.v.ndof) { const int dof = c.v.dof(k); c.grad[k] = c.Ma[k] - c.qfs[dof] - qfc[dof]; }
   MJB_PSYNC();
 }
 
@@ -139,22 +228,25 @@ MJB_HD int chol_update(const Env& d, FD mat, FD x, int n, bool plus) {
   return rank;
 }
 
-// L <- lower triangle of H = M + J' diag(Dq) J, then its Cholesky factor
+// L <- lower triangle of H = M + J' diag(Dq) J on the view (island-local n x n), then its Cholesky factor
 MJB_HD void newton_factorize(const Env& d, NewtonCtx& c, bool recompute) {
   const DModel& m = d.m;
-  const int nv = c.nv, nefc = c.nefc;
+  const IslView& v = c.v;
+  const int n = v.ndof, nv = c.nv;
   if (recompute) {
-    MJB_PFOR(i, nefc) c.Dq[i] = (c.state[i] == STATE_QUADRATIC) ? c.efcD[i] : 0.0;
+    MJB_PFOR(cc, v.nrow) { const int i = v.row(cc); c.Dq[i] = (c.state[i] == STATE_QUADRATIC) ? c.efcD[i] : 0.0; }
     MJB_PSYNC();
-    MJB_PFOR(e, nv * nv) {
-      const int i = e / nv, k = e - i * nv;
+    MJB_PFOR(e, n * n) {
+      const int a = e / n, b = e - a * n;
       double s = 0;
-      if (k <= i) {
-        for (int j = 0; j < nefc; j++) {
+      if (b <= a) {
+        const int da = v.dof(a), db = v.dof(b);
+        for (int cc = 0; cc < v.nrow; cc++) {
+          const int j = v.row(cc);
           const double dj = c.Dq[j];
           if (dj != 0) {
-            const double t = c.J[j * nv + i];
-            if (t != 0) s += c.J[j * nv + k] * (t * dj);
+            const double t = c.J[(long)j * nv + da];
+            if (t != 0) s += c.J[(long)j * nv + db] * (t * dj);
           }
         }
       }
@@ -162,28 +254,31 @@ MJB_HD void newton_factorize(const Env& d, NewtonCtx& c, bool recompute) {
     }
     MJB_PSYNC();
     FD M = d.M();
-    MJB_PFOR(i, nv) {
+    MJB_PFOR(a, n) {
+      const int i = v.dof(a);
       const int adr = m.M_rowadr[i], nnz = m.M_rownnz[i];
-      for (int a = 0; a < nnz; a++) c.L[i * nv + m.M_colind[adr + a]] += M[adr + a];
+      for (int q = 0; q < nnz; q++) c.L[a * n + v.loc(m.M_colind[adr + q])] += M[adr + q];
     }
     MJB_PSYNC();
   }
-  chol_factor(d, c.L, nv, kMinVal);
+  chol_factor(d, c.L, n, kMinVal);
 }
 
-MJB_HD void newton_update_mgrad(const Env& d, NewtonCtx& c) { chol_solve(d, c.Mgrad, c.L, c.grad, c.nv); }
+MJB_HD void newton_update_mgrad(const Env& d, NewtonCtx& c) { chol_solve(d, c.Mgrad, c.L, c.grad, c.v.ndof); }
 
 // rank-one updates of the factor for the rows whose QUADRATIC membership changed
 MJB_HD void newton_hessian_incremental(const Env& d, NewtonCtx& c) {
-  const int nv = c.nv, nefc = c.nefc;
-  for (int i = 0; i < nefc; i++) {
+  const IslView& v = c.v;
+  const int n = v.ndof;
+  for (int cc = 0; cc < v.nrow; cc++) {
+    const int i = v.row(cc);
     const bool was = c.oldstate[i] == STATE_QUADRATIC, is = c.state[i] == STATE_QUADRATIC;
     if (was == is) continue;
     const double sq = sqrt(c.efcD[i]);
-    MJB_PFOR(k, nv) c.cholupd[k] = c.J[i * nv + k] * sq;
+    MJB_PFOR(k, n) c.cholupd[k] = c.J[(long)i * c.nv + v.dof(k)] * sq;
     MJB_PSYNC();
-    const int rank = chol_update(d, c.L, c.cholupd, nv, is);
-    if (rank < nv) {
+    const int rank = chol_update(d, c.L, c.cholupd, n, is);
+    if (rank < n) {
       newton_factorize(d, c, true);
       return;
     }
@@ -195,7 +290,8 @@ MJB_HD void newton_eval(NewtonCtx& c, LsPoint& p) {
   const double alpha = p.alpha;
   double cost = 0, d0 = 0, d1 = 0;
   double q0 = 0, q1 = c.quadGauss[1], q2 = c.quadGauss[2];
-  for (int i = 0; i < c.nefc; i++) {
+  for (int cc = 0; cc < c.v.nrow; cc++) {
+    const int i = c.v.row(cc);
     if (i < c.nf) {
       const double start = c.Jaref[i], dir = c.Jv[i];
       const double x = start + alpha * dir;
@@ -241,21 +337,23 @@ MJB_HD int newton_update_bracket(NewtonCtx& c, LsPoint& p, const LsPoint* cand, 
 
 // exact line search along `search`; returns the step and the cost improvement
 MJB_HD double newton_search(const Env& d, NewtonCtx& c, double tolerance, int ls_iterations, double& improvement) {
-  const int nv = c.nv, nefc = c.nefc;
+  const IslView& v = c.v;
+  const int n = v.ndof;
   c.lsiter = 0;
   improvement = 0;
-  const double snorm = sqrt(dot_ref(nv, [&](int i) { return c.search[i]; }, [&](int i) { return c.search[i]; }));
+  const double snorm = sqrt(dot_ref(n, [&](int k) { return c.search[k]; }, [&](int k) { return c.search[k]; }));
   if (snorm < kMinVal) return 0;
   const double gtol = tolerance * snorm / c.scale;
 
-  mul_M(d, c.Mv, c.search);
-  mul_jac_vec(d, c.Jv, c.search);
+  mul_M_view(d, v, c.Mv, c.search);
+  mul_jac_view(d, c, c.Jv, c.search);
 
   // quadratic polynomials (PrimalPrepare)
-  c.quadGauss[1] = dot_ref(nv, [&](int i) { return c.search[i]; }, [&](int i) { return c.Ma[i]; }) -
-                   dot_ref(nv, [&](int i) { return c.qfs[i]; }, [&](int i) { return c.search[i]; });
-  c.quadGauss[2] = 0.5 * dot_ref(nv, [&](int i) { return c.search[i]; }, [&](int i) { return c.Mv[i]; });
-  MJB_PFOR(i, nefc) {
+  c.quadGauss[1] = dot_ref(n, [&](int k) { return c.search[k]; }, [&](int k) { return c.Ma[k]; }) -
+                   dot_ref(n, [&](int k) { return c.qfs[v.dof(k)]; }, [&](int k) { return c.search[k]; });
+  c.quadGauss[2] = 0.5 * dot_ref(n, [&](int k) { return c.search[k]; }, [&](int k) { return c.Mv[k]; });
+  MJB_PFOR(cc, v.nrow) {
+    const int i = v.row(cc);
     const double D = c.efcD[i], ja = c.Jaref[i], jv = c.Jv[i];
     const double DJ0 = D * ja;
     c.quad[3 * i] = ja * DJ0 * 0.5;
@@ -324,13 +422,15 @@ MJB_HD double newton_search(const Env& d, NewtonCtx& c, double tolerance, int ls
 }
 
 // Newton (newton = true) or conjugate gradient (mj_solCG: M-preconditioned, Hager-Zhang direction
-// update, engine_solver.c:2489-2518) on the primal problem
-MJB_HD void solve_primal(const Env& d, bool newton) {
+// update, engine_solver.c:2489-2518) on the primal problem of one view; returns the iteration count
+MJB_HD int solve_primal_view(const Env& d, bool newton, const IslView& view, bool island_scale) {
   const DModel& m = d.m;
-  const int nv = m.sz.nv, nefc = d.nefc()[0], njmax = m.sz.njmax;
-  if (!nefc) return;
+  const int nv = m.sz.nv, njmax = m.sz.njmax;
   NewtonCtx c;
-  c.nv = nv; c.nefc = nefc; c.nf = d.nf()[0];
+  c.v = view;
+  const IslView& v = c.v;
+  const int n = v.ndof;
+  c.nv = nv; c.nefc = d.nefc()[0]; c.nf = d.nf()[0];
   c.J = d.efc_J();
   FD se = d.nwt_efc(), sv = d.nwt_nv();
   c.Jaref = se; c.Jv = se + njmax; c.quad = se + 2 * (long)njmax; c.Dq = se + 5 * (long)njmax;
@@ -342,21 +442,25 @@ MJB_HD void solve_primal(const Env& d, bool newton) {
   c.state = d.efc_state(); c.oldstate = d.nwt_state();
   const double tol = m.opt.tolerance;
 
-  mul_M(d, c.Ma, c.qacc);
-  mul_jac_vec(d, c.Jaref, c.qacc);
+  // Ma = M qacc (island-local), Jaref = J qacc - aref
   {
+    FD qa = c.search;   // island-local copy of qacc (search is free until the first direction)
+    MJB_PFOR(k, n) qa[k] = c.qacc[v.dof(k)];
+    MJB_PSYNC();
+    mul_M_view(d, v, c.Ma, qa);
+    mul_jac_view(d, c, c.Jaref, qa);
     FD aref = d.efc_aref();
-    MJB_PFOR(i, nefc) c.Jaref[i] -= aref[i];
+    MJB_PFOR(cc, v.nrow) { const int i = v.row(cc); c.Jaref[i] -= aref[i]; }
     MJB_PSYNC();
   }
   newton_update_constraint(d, c);
   newton_update_grad(d, c);
 
-  // cost scale: the island's (trace of M) when islands are enabled, the global one otherwise
-  if (!(m.opt.disableflags & DSBL_ISLAND)) {
+  // cost scale: the island's (trace of its M block), the global one when islands are not in use
+  if (island_scale) {
     FD M = d.M();
     double tr = 0;
-    for (int i = 0; i < nv; i++) tr += M[m.M_rowadr[i] + m.M_rownnz[i] - 1];
+    for (int k = 0; k < n; k++) { const int i = v.dof(k); tr += M[m.M_rowadr[i] + m.M_rownnz[i] - 1]; }
     c.scale = 1 / tr;
   } else {
     c.scale = 1 / (m.opt.meaninertia * (nv > 1 ? nv : 1));
@@ -364,11 +468,11 @@ MJB_HD void solve_primal(const Env& d, bool newton) {
   const double scale = c.scale;
 
   // convergence certificate with the M-preconditioned gradient
-  MJB_PFOR(i, nv) c.Mgrad[i] = c.grad[i];
+  MJB_PFOR(k, n) c.Mgrad[k] = c.grad[k];
   MJB_PSYNC();
-  solve_LD(d, c.Mgrad, d.qLD(), d.qLDiagInv());
-  auto grad_dot_mgrad = [&]() { return dot_ref(nv, [&](int i) { return c.grad[i]; }, [&](int i) { return c.Mgrad[i]; }); };
-  auto grad_norm = [&]() { return sqrt(dot_ref(nv, [&](int i) { return c.grad[i]; }, [&](int i) { return c.grad[i]; })); };
+  solve_M_view(d, v, c.Mgrad);
+  auto grad_dot_mgrad = [&]() { return dot_ref(n, [&](int k) { return c.grad[k]; }, [&](int k) { return c.Mgrad[k]; }); };
+  auto grad_norm = [&]() { return sqrt(dot_ref(n, [&](int k) { return c.grad[k]; }, [&](int k) { return c.grad[k]; })); };
   const bool flg_gap = dmax(0.0, 0.5 * scale * grad_dot_mgrad()) < tol;
   const bool flg_gradient = scale * grad_norm() < tol;
   bool done = flg_gap && (!newton || flg_gradient);
@@ -380,7 +484,7 @@ MJB_HD void solve_primal(const Env& d, bool newton) {
     done = flg_gradient && dmax(0.0, 0.5 * scale * grad_dot_mgrad()) < tol;
   }
   if (!done) {
-    MJB_PFOR(i, nv) c.search[i] = c.Mgrad[i] * -1;
+    MJB_PFOR(k, n) c.search[k] = c.Mgrad[k] * -1;
     MJB_PSYNC();
   }
 
@@ -391,9 +495,9 @@ MJB_HD void solve_primal(const Env& d, bool newton) {
     const double alpha = newton_search(d, c, tol * m.opt.ls_tolerance, m.opt.ls_iterations, ls_improvement);
     if (alpha == 0) break;
     MJB_PSYNC();
-    MJB_PFOR(i, nv) { c.qacc[i] += c.search[i] * alpha; c.Ma[i] += c.Mv[i] * alpha; }
-    MJB_PFOR(i, nefc) { c.Jaref[i] += c.Jv[i] * alpha; c.oldstate[i] = c.state[i]; }
-    if (!newton) { MJB_PFOR(i, nv) { gradold[i] = c.grad[i]; Mgradold[i] = c.Mgrad[i]; } }
+    MJB_PFOR(k, n) { c.qacc[v.dof(k)] += c.search[k] * alpha; c.Ma[k] += c.Mv[k] * alpha; }
+    MJB_PFOR(cc, v.nrow) { const int i = v.row(cc); c.Jaref[i] += c.Jv[i] * alpha; c.oldstate[i] = c.state[i]; }
+    if (!newton) { MJB_PFOR(k, n) { gradold[k] = c.grad[k]; Mgradold[k] = c.Mgrad[k]; } }
     MJB_PSYNC();
     newton_update_constraint(d, c);
     if (newton) newton_hessian_incremental(d, c);
@@ -401,9 +505,9 @@ MJB_HD void solve_primal(const Env& d, bool newton) {
     if (newton) {
       newton_update_mgrad(d, c);
     } else {
-      MJB_PFOR(i, nv) c.Mgrad[i] = c.grad[i];
+      MJB_PFOR(k, n) c.Mgrad[k] = c.grad[k];
       MJB_PSYNC();
-      solve_LD(d, c.Mgrad, d.qLD(), d.qLDiagInv());
+      solve_M_view(d, v, c.Mgrad);
     }
     const double improvement = scale * ls_improvement;
     const double gradient = scale * grad_norm();
@@ -412,15 +516,15 @@ MJB_HD void solve_primal(const Env& d, bool newton) {
     if ((improvement > 0 && improvement < tol) || gradient < tol || (newton && decrement < tol)) break;
     MJB_PSYNC();
     if (newton) {
-      MJB_PFOR(i, nv) c.search[i] = c.Mgrad[i] * -1;
+      MJB_PFOR(k, n) c.search[k] = c.Mgrad[k] * -1;
     } else {
       // Hager-Zhang: every lane evaluates the same dot products (uniform beta)
-      auto dotf = [&](auto a, auto b) { return dot_ref(nv, a, b); };
-      auto S = [&](int i) { return c.search[i]; };
-      auto Y = [&](int i) { return c.grad[i] - gradold[i]; };
-      auto MY = [&](int i) { return c.Mgrad[i] - Mgradold[i]; };
-      auto G = [&](int i) { return c.grad[i]; };
-      auto MG = [&](int i) { return c.Mgrad[i]; };
+      auto dotf = [&](auto a, auto b) { return dot_ref(n, a, b); };
+      auto S = [&](int k) { return c.search[k]; };
+      auto Y = [&](int k) { return c.grad[k] - gradold[k]; };
+      auto MY = [&](int k) { return c.Mgrad[k] - Mgradold[k]; };
+      auto G = [&](int k) { return c.grad[k]; };
+      auto MG = [&](int k) { return c.Mgrad[k]; };
       double beta;
       const double d_dot_y = dotf(S, Y);
       if (d_dot_y < kMinVal) {
@@ -433,13 +537,40 @@ MJB_HD void solve_primal(const Env& d, bool newton) {
         beta = dmax(eta_k, beta_hz);
       }
       MJB_PSYNC();
-      MJB_PFOR(i, nv) c.search[i] = -c.Mgrad[i] + beta * c.search[i];
+      MJB_PFOR(k, n) c.search[k] = -c.Mgrad[k] + beta * c.search[k];
     }
     MJB_PSYNC();
   }
   MJB_PSYNC();
-  MJB_LANE0 d.solver_niter()[0] += iter;
-  MJB_PSYNC();
+  return iter;
+}
+
+// mj_fwdConstraint's dispatch (engine_forward.c:1187-1226): one solve per constraint island when islands
+// are in use, the monolithic problem otherwise.  Dofs outside every island keep qacc = qacc_smooth
+// (warmstart, engine_forward.c:1121-1128).
+MJB_HD void solve_primal(const Env& d, bool newton) {
+  const DModel& m = d.m;
+  const int nv = m.sz.nv, nefc = d.nefc()[0];
+  if (!nefc) return;
+  FI niter = d.solver_niter();
+  if (use_islands(d)) {
+    const int nisland = d.nisland()[0];
+    const int* eadr = d.island_iefcadr().p;
+    const int* dadr = d.island_idofadr().p;
+    for (int k = 0; k < nisland; k++) {
+      IslView v{d.map_iefc2efc().p + eadr[k], eadr[k + 1] - eadr[k], d.map_idof2dof().p + dadr[k], dadr[k + 1] - dadr[k],
+                d.map_dof2idof().p, dadr[k]};
+      const int iter = solve_primal_view(d, newton, v, true);
+      MJB_LANE0 if (k < NISLAND) niter[k] += iter;
+      MJB_PSYNC();
+    }
+  } else {
+    IslView v{nullptr, nefc, nullptr, nv, nullptr, 0};
+    // a single tree with islands enabled is one island: same problem, island cost scale
+    const int iter = solve_primal_view(d, newton, v, !(m.opt.disableflags & DSBL_ISLAND));
+    MJB_LANE0 niter[0] += iter;
+    MJB_PSYNC();
+  }
 }
 
 }  // namespace mjb

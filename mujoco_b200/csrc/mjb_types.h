@@ -151,7 +151,8 @@ struct DModel {
 // ints (all hot)
 #define MJB_DATA_INT_FIELDS(X, S)                                                            \
   X(ncon, 1) X(nefc, 1) X(ne, 1) X(nf, 1) X(nl, 1) X(solver_niter, NISLAND) X(step_skip, 1) X(warning, NWARNING)  \
-  X(nisland, 1) X(efc_island, S.njmax) X(map_iefc2efc, S.njmax) X(island_iefcadr, S.ntree + 2) X(tree_island, 2 * S.ntree + 2)     \
+  X(nisland, 1) X(efc_island, S.njmax) X(map_iefc2efc, S.njmax) X(island_iefcadr, S.ntree + 2) X(tree_island, 2 * S.ntree + 2)            \
+  X(island_idofadr, S.ntree + 2) X(map_idof2dof, S.nv) X(map_dof2idof, S.nv)     \
   X(con_geom1, S.nconmax) X(con_geom2, S.nconmax) X(con_dim, S.nconmax)                       \
   X(con_exclude, S.nconmax) X(con_efcadr, S.nconmax) X(con_pair, S.nconmax)                    \
   X(efc_type, S.njmax) X(efc_id, S.njmax) X(efc_state, S.njmax) X(nwt_state, S.njmax) X(scr_int, 4 * S.njmax)        \

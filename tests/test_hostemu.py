@@ -84,12 +84,14 @@ def test_frictionloss_rows_bit_exact(solver):
     assert np.array_equal(out, ref)
 
 
-def test_constraint_islands_pgs_bit_exact():
+@pytest.mark.parametrize("solver", [mb.SOLVER_PGS, mb.SOLVER_NEWTON, mb.SOLVER_CG])
+def test_constraint_islands_bit_exact(solver):
     """several kinematic trees (models/ant_balls.xml: the ant + two balls + a stick): mj_island partitions
-    the rows, PGS runs once per island (own shuffle stream, momentum, termination and iteration count)"""
+    rows and dofs, and every solver runs once per island (PGS: own shuffle stream, momentum, termination;
+    Newton/CG: island-local M, J, Hessian and cost scale), with per-island iteration counts"""
     path = os.path.join(ROOT, "models", "ant_balls.mjb")
     nenv, nstep = 6, 150
-    m, b, o = make_pair(path, mb.SOLVER_PGS, library=hostemu_lib(), nenv=nenv)
+    m, b, o = make_pair(path, solver, library=hostemu_lib(), nenv=nenv)
     s0 = perturbed_states(o, nenv, seed=14, height=[0.35, 0.5, 0.75], qvel_std=0.3, qpos_std=0.05)
     ctrl = np.random.default_rng(15).uniform(-1, 1, (nenv, nstep, o.size("nu")))
     out = b.rollout(s0, ctrl)
@@ -98,15 +100,14 @@ def test_constraint_islands_pgs_bit_exact():
     assert np.array_equal(out, ref)
     seen = set()
     for t in (40, 80, 149):     # states with 3-4 islands: every field and the per-island iteration counts
-        compare_forward(b, o, out[:, t, :], ctrl[:, t, :], rtol=0, exact=True, check_dual=True)
+        compare_forward(b, o, out[:, t, :], ctrl[:, t, :], rtol=0, exact=True, check_dual=(solver == mb.SOLVER_PGS))
         seen |= set(b.field("nisland")[:, 0].tolist())
     assert max(seen) >= 3
-    # islands disabled: the monolithic solvers handle the same forest
-    for solver in (mb.SOLVER_PGS, mb.SOLVER_NEWTON, mb.SOLVER_CG):
-        m, b, o = make_pair(path, solver, library=hostemu_lib(), nenv=nenv, disableflags=1 << 18)
-        out = b.rollout(s0, ctrl[:, :60])
-        ref, _, _ = o.rollout(s0, ctrl[:, :60], nthread=4)
-        assert np.array_equal(out, ref), solver
+    # islands disabled: the monolithic solver handles the same forest
+    m, b, o = make_pair(path, solver, library=hostemu_lib(), nenv=nenv, disableflags=1 << 18)
+    out = b.rollout(s0, ctrl[:, :60])
+    ref, _, _ = o.rollout(s0, ctrl[:, :60], nthread=4)
+    assert np.array_equal(out, ref)
 
 
 @pytest.mark.parametrize("model", [HUMANOID, ANT])
