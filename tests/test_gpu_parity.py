@@ -142,3 +142,23 @@ def test_rk4_rollout_vs_oracle(model, solver):
     rel = (np.abs(out - ref) / np.maximum(1.0, np.abs(ref).max(axis=(0, 1)))).max()
     print("rk4 rollout rel err %.3e" % rel)
     assert rel < RTOL_TIGHT
+
+
+@pytest.mark.parametrize("solver", [pytest.param(mb.SOLVER_PGS, id="pgs"), pytest.param(mb.SOLVER_NEWTON, id="newton"),
+                                    pytest.param(mb.SOLVER_CG, id="cg")])
+def test_constraint_islands_vs_oracle(solver):
+    """four kinematic trees (models/ant_balls.xml): 3-4 constraint islands, one solve per island"""
+    assert available()
+    path = os.path.join(ROOT, "models", "ant_balls.mjb")
+    nenv, nstep = 24, 150
+    m, b, o = make_pair(path, solver, nenv=nenv)
+    s0 = perturbed_states(o, nenv, seed=14, height=[0.35, 0.5, 0.75], qvel_std=0.3, qpos_std=0.05)
+    ctrl = np.random.default_rng(15).uniform(-1, 1, (nenv, nstep, o.size("nu")))
+    out = b.rollout(s0, ctrl)
+    ref, stats, _ = o.rollout(s0, ctrl, nthread=os.cpu_count() or 1)
+    assert stats[:, 3].sum() == 0 and (b.warnings() == 0).all()
+    rel = (np.abs(out - ref) / np.maximum(1.0, np.abs(ref).max(axis=(0, 1)))).max()
+    print("islands rollout rel err %.3e" % rel)
+    assert rel < RTOL_TIGHT
+    compare_forward(b, o, ref[:, 100, :], ctrl[:, 100, :], rtol=RTOL_TIGHT, check_dual=(solver == mb.SOLVER_PGS))
+    assert b.field("nisland")[:, 0].max() >= 3
