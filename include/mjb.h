@@ -108,6 +108,14 @@ MJB_API int mjb_rollout(mjbBatch* b, int nstep, unsigned int control_spec,
  * mjSTATE_FULLPHYSICS state [nenv][nstate] is copied back; returns after the copy completed. */
 MJB_API int mjb_step_host(mjbBatch* b, const double* ctrl, double* state_out);
 
+/* mj_step for the reference's own mjData objects, one per environment (replaces the per-thread loop
+ * `for k: mj_step(m, d[k])`, sample/testspeed.cc:123 / python/mujoco/rollout.cc:85-177): reads time, qpos,
+ * qvel, ctrl, qfrc_applied, qacc_warmstart from every d[e], steps the batch once, and writes the new state
+ * and every fixed-size mjData array the path computes back under the same member names (plus ncon, nefc and
+ * the warning counters; arena members - contact, efc_* - stay on the device: use mjb_get_field). */
+struct mjData_;
+MJB_API int mjb_step_mjdata(mjbBatch* b, struct mjData_* const* d, int nd);
+
 /* Same, with DEVICE-resident control / state buffers in the library's native layout
  * ([nstep][ncontrol][nenv_stride] and [nstep][nstate][nenv_stride]); used by bench.py's
  * HBM-resident throughput measurement.  Either pointer may be NULL. */

@@ -59,6 +59,7 @@ def _bind(cdll):
     L.mjb_forward.argtypes = [vp]
     L.mjb_step.argtypes = [vp, i]
     L.mjb_rollout.argtypes = [vp, i, u, vp, vp, vp, vp, vp]
+    L.mjb_step_mjdata.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
     L.mjb_step_host.argtypes = [vp, vp, vp]
     L.mjb_rollout_device.argtypes = [vp, i, vp, vp]
     L.mjb_env_stride.restype = l
@@ -208,6 +209,12 @@ class Batch:
 
     def step(self, nstep=1):
         self._chk(self.L.mjb_step(self.ptr, int(nstep)))
+
+    def step_mjdata(self, addresses):
+        """mj_step for the reference's own mjData objects (one address per environment, e.g.
+        mujoco.MjData._address): inputs read from / results written to the mjData members"""
+        arr = (C.c_void_p * len(addresses))(*[int(a) for a in addresses])
+        self._chk(self.L.mjb_step_mjdata(self.ptr, arr, len(addresses)))
 
     def step_host(self, ctrl, state_out):
         """one step with host I/O: ctrl [nenv,nu] in, FULLPHYSICS state [nenv,nstate] out (numpy or

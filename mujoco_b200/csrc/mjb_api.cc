@@ -10,6 +10,8 @@
 #include <string>
 #include <vector>
 
+#include <mujoco/mjdata.h>   // the reference's own mjData (public header), for the mjData bridge
+
 #include "mjb_backend.h"
 #include "mjb_model.h"
 
@@ -433,6 +435,73 @@ int mjb_set_field(mjbBatch* B, const char* name, const double* in) {
   long off, cnt; bool is_int;
   if (!B || !in || !find_field(B, name, &off, &cnt, &is_int) || is_int) return fail(MJB_ERR_ARG, std::string("mjb_set_field: unknown double field ") + (name ? name : ""));
   return field_from_host(B, false, off, cnt, in);
+}
+
+// ---- mjData bridge: mj_step for a set of the reference's own mjData objects ---------------------------
+// The reference steps one mjData per environment (`for k: mj_step(m, d[k])`, sample/testspeed.cc:123,
+// rollout.cc:85-177).  mjb_step_mjdata is that loop as one call: inputs are read from every d[e]
+// (time, qpos, qvel, ctrl, qfrc_applied, qacc_warmstart), the batch takes one mj_step, and the state plus
+// every fixed-size mjData array the path computes is written back under the same member name, so code
+// that reads mjData after mj_step keeps working.  Arena-allocated members (contact, efc_*) are not
+// materialised on the host; ncon / nefc and the warning counters are.
+#define MJB_MJDATA_IN(X) X(qpos, nq) X(qvel, nv) X(ctrl, nu) X(qfrc_applied, nv) X(qacc_warmstart, nv)
+#define MJB_MJDATA_OUT(X)                                                                                   \
+  X(qpos, nq) X(qvel, nv) X(qacc_warmstart, nv) X(qacc, nv)                                                 \
+  X(xpos, 3 * nbody) X(xquat, 4 * nbody) X(xmat, 9 * nbody) X(xipos, 3 * nbody) X(ximat, 9 * nbody)         \
+  X(xanchor, 3 * njnt) X(xaxis, 3 * njnt) X(geom_xpos, 3 * ngeom) X(geom_xmat, 9 * ngeom)                   \
+  X(subtree_com, 3 * nbody) X(cinert, 10 * nbody) X(cdof, 6 * nv) X(crb, 10 * nbody) X(M, nC) X(qLD, nC)    \
+  X(qLDiagInv, nv) X(ten_length, ntendon) X(actuator_length, nu) X(ten_velocity, ntendon)                   \
+  X(actuator_velocity, nu) X(cvel, 6 * nbody) X(cdof_dot, 6 * nv) X(qfrc_spring, nv) X(qfrc_damper, nv)     \
+  X(qfrc_passive, nv) X(qfrc_bias, nv) X(actuator_force, nu) X(qfrc_actuator, nv) X(qfrc_smooth, nv)        \
+  X(qacc_smooth, nv) X(qfrc_constraint, nv)
+
+int mjb_step_mjdata(mjbBatch* B, struct mjData_* const* dd, int nd) {
+  if (!B || !dd || nd != B->b.nenv) return fail(MJB_ERR_ARG, "mjb_step_mjdata: need one mjData per environment");
+  const Sizes& S = B->hm.dm.sz;
+  const int nenv = B->b.nenv;
+  mjData* const* d = (mjData* const*)dd;
+  const int nq = S.nq, nv = S.nv, nu = S.nu, nbody = S.nbody, njnt = S.njnt, ngeom = S.ngeom, ntendon = S.ntendon, nC = S.nC;
+  (void)nbody; (void)njnt; (void)ngeom; (void)ntendon; (void)nC;
+  std::vector<double> tmp;
+  {
+    tmp.resize(nenv);
+    for (int e = 0; e < nenv; e++) tmp[e] = d[e]->time;
+    if (int rc = field_from_host(B, false, B->b.L.time, 1, tmp.data())) return rc;
+  }
+#define X(name, cnt)                                                                             \
+  if ((cnt) > 0) {                                                                               \
+    tmp.resize((size_t)nenv * (cnt));                                                            \
+    for (int e = 0; e < nenv; e++) memcpy(tmp.data() + (size_t)e * (cnt), d[e]->name, sizeof(double) * (cnt)); \
+    if (int rc = field_from_host(B, false, B->b.L.name, (cnt), tmp.data())) return rc;            \
+  }
+  MJB_MJDATA_IN(X)
+#undef X
+  if (int rc = run_step(B, false)) return rc;
+  {
+    tmp.resize(nenv);
+    if (int rc = field_to_host(B, false, B->b.L.time, 1, tmp.data())) return rc;
+    for (int e = 0; e < nenv; e++) d[e]->time = tmp[e];
+  }
+#define X(name, cnt)                                                                             \
+  if ((cnt) > 0) {                                                                               \
+    tmp.resize((size_t)nenv * (cnt));                                                            \
+    if (int rc = field_to_host(B, false, B->b.L.name, (cnt), tmp.data())) return rc;              \
+    for (int e = 0; e < nenv; e++) memcpy(d[e]->name, tmp.data() + (size_t)e * (cnt), sizeof(double) * (cnt)); \
+  }
+  MJB_MJDATA_OUT(X)
+#undef X
+  std::vector<int> it((size_t)nenv * NWARNING);
+  if (int rc = field_to_host(B, true, B->b.L.ncon, 1, it.data())) return rc;
+  for (int e = 0; e < nenv; e++) d[e]->ncon = it[e];
+  if (int rc = field_to_host(B, true, B->b.L.nefc, 1, it.data())) return rc;
+  for (int e = 0; e < nenv; e++) d[e]->nefc = it[e];
+  if (int rc = field_to_host(B, true, B->b.L.warning, NWARNING, it.data())) return rc;
+  for (int e = 0; e < nenv; e++)
+    for (int w = 0; w < NWARNING; w++) {
+      // the batch counts warnings since its last reset; mjData accumulates: add what this step raised
+      d[e]->warning[w].number += it[(size_t)e * NWARNING + w];
+    }
+  return field_zero(B, true, B->b.L.warning, NWARNING) || backend::sync(B->stream);
 }
 
 int mjb_set_thread_mapping(int warp_per_env) {
