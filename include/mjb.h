@@ -96,7 +96,7 @@ MJB_API int mjb_step(mjbBatch* b, int nstep);
  *   warmstart0 [nenv][nv] or NULL      initial qacc_warmstart (NULL -> zeros)
  *   control    [nenv][nstep][ncontrol] or NULL, ncontrol = mjb_state_size(control_spec)
  *   state      [nenv][nstep][nstate] or NULL  (output)
- *   sensordata must be NULL (nsensordata == 0 on the supported models)
+ *   sensordata [nenv][nstep][nsensordata] or NULL  (output; supported sensor types: mjb_check_model)
  * Environments that raise a warning stop stepping and pad their outputs with the current state,
  * as the reference does (rollout.cc:127-155). */
 MJB_API int mjb_rollout(mjbBatch* b, int nstep, unsigned int control_spec,

@@ -262,9 +262,10 @@ class Batch:
         return int(self.L.mjb_kernel_launches(self.ptr))
 
     def rollout(self, initial_state, control=None, nstep=None, control_spec=STATE_CTRL,
-                initial_warmstart=None, return_state=True):
+                initial_warmstart=None, return_state=True, return_sensordata=False):
         """mirror of mujoco.rollout.rollout: initial_state [nenv,nstate], control [nenv,nstep,ncontrol]
-        -> state [nenv,nstep,nstate] (mjSTATE_FULLPHYSICS)"""
+        -> state [nenv,nstep,nstate] (mjSTATE_FULLPHYSICS); with return_sensordata also
+        sensordata [nenv,nstep,nsensordata] (returned as a pair, like the reference)"""
         s0 = np.ascontiguousarray(initial_state, dtype=np.float64)
         nstate = self.state_size()
         if s0.shape != (self.nenv, nstate):
@@ -290,6 +291,8 @@ class Batch:
                 raise ValueError(f"initial_warmstart must have shape {(self.nenv, nv)}")
             wptr = w.ctypes.data
         out = np.zeros((self.nenv, nstep, nstate)) if return_state else None
+        sens = np.zeros((self.nenv, nstep, self.model.size("nsensordata"))) if return_sensordata else None
         self._chk(self.L.mjb_rollout(self.ptr, int(nstep), control_spec, s0.ctypes.data, wptr, cptr,
-                                     out.ctypes.data if return_state else None, None))
-        return out
+                                     out.ctypes.data if return_state else None,
+                                     sens.ctypes.data if return_sensordata else None))
+        return (out, sens) if return_sensordata else out

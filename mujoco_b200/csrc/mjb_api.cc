@@ -234,11 +234,12 @@ int mjb_get_state(mjbBatch* B, double* state, unsigned int sig) {
 // check, then three (phase, forward) pairs and the final combination = 8 launches.
 static int run_step_on(mjbBatch* B, const Batch& b, void* stream, bool skip_warned) {
   const int first = 1 | (skip_warned ? 2 : 0), later = skip_warned ? 4 : 0;
+  const int sub = later | 8;   // RK4 sub-steps: mj_forwardSkip(.., skipsensor = 1)
   if (B->hm.dm.opt.integrator == INT_RK4) {
     int rc = backend::launch_stages(B->dm, b, 0x7 | 32, first, stream);
     for (int phase = 1; phase <= 3 && !rc; phase++) {
       rc = backend::launch_rk4(B->dm, b, phase, later, stream);
-      if (!rc) rc = backend::launch_stages(B->dm, b, 0x17, later, stream);
+      if (!rc) rc = backend::launch_stages(B->dm, b, 0x17, sub, stream);
     }
     if (!rc) rc = backend::launch_rk4(B->dm, b, 4, later, stream);
     return rc;
@@ -312,7 +313,8 @@ int mjb_run_stages(mjbBatch* B, int first, int last) {
 int mjb_rollout(mjbBatch* B, int nstep, unsigned int control_spec, const double* state0,
                 const double* warmstart0, const double* control, double* state, double* sensordata) {
   if (!B || nstep < 0 || !state0) return fail(MJB_ERR_ARG, "mjb_rollout: bad arguments");
-  if (sensordata) return fail(MJB_ERR_ARG, "mjb_rollout: sensordata must be NULL (nsensordata == 0)");
+  const int nsens = B->hm.dm.sz.nsensordata;
+  if (sensordata && !nsens) return fail(MJB_ERR_ARG, "mjb_rollout: the model has no sensors (nsensordata == 0)");
   const unsigned full = ST_TIME | ST_QPOS | ST_QVEL | ST_ACT | ST_HISTORY | ST_PLUGIN;
   std::vector<Seg> csegs;
   if (control && state_segments(B, control_spec, &csegs)) return fail(MJB_ERR_ARG, "mjb_rollout: unsupported control_spec");
@@ -345,6 +347,12 @@ int mjb_rollout(mjbBatch* B, int nstep, unsigned int control_spec, const double*
     d_state = (double*)backend::dev_alloc(sbytes);
     if (!d_state) { backend::dev_free(d_control); return fail(MJB_ERR_CUDA, "device allocation failed (state)"); }
   }
+  double* d_sens = nullptr;
+  const size_t nbytes = (size_t)nenv * nstep * nsens * sizeof(double);
+  if (sensordata && nstep) {
+    d_sens = (double*)backend::dev_alloc(nbytes);
+    if (!d_sens) { backend::dev_free(d_control); backend::dev_free(d_state); return fail(MJB_ERR_CUDA, "device allocation failed (sensordata)"); }
+  }
   std::vector<EnvGroup> gs = env_groups(B, nstep);
   int rc = groups_fork(B, gs);
   for (int t = 0; t < nstep && !rc; t++) {
@@ -352,13 +360,16 @@ int mjb_rollout(mjbBatch* B, int nstep, unsigned int control_spec, const double*
       if (d_control && !rc) rc = backend::launch_set_control(B->dm, g.b, d_control + (size_t)g.e0 * nstep * ncontrol, nstep, t, control_spec, ncontrol, g.stream);
       if (!rc) rc = run_step_on(B, g.b, g.stream, true);
       if (d_state && !rc) rc = backend::launch_get_state(B->dm, g.b, d_state + (size_t)g.e0 * nstep * nstate, nstep, t, nstate, g.stream);
+      if (d_sens && !rc) rc = backend::launch_get_sensor(B->dm, g.b, d_sens + (size_t)g.e0 * nstep * nsens, nstep, t, nsens, g.stream);
     }
   }
   if (!rc) rc = groups_join(B, gs);
   if (!rc && d_state) rc = backend::d2h(state, d_state, sbytes, B->stream);
+  if (!rc && d_sens) rc = backend::d2h(sensordata, d_sens, nbytes, B->stream);
   if (!rc) rc = backend::sync(B->stream);
   backend::dev_free(d_control);
   backend::dev_free(d_state);
+  backend::dev_free(d_sens);
   return rc;
 }
 

@@ -32,6 +32,7 @@ int launch_reset(const DModel& dm, const Batch& b, void* stream);
 int launch_set_control(const DModel& dm, const Batch& b, const double* control, int nstep, int t,
                        unsigned spec, int ncontrol, void* stream);
 int launch_get_state(const DModel& dm, const Batch& b, double* state, int nstep, int t, int nstate, void* stream);
+int launch_get_sensor(const DModel& dm, const Batch& b, double* sens, int nstep, int t, int nsens, void* stream);   // [nenv][nstep][nsens]
 // native-layout variants: ctrl [nstep][nu][stride], state [nstep][nstate][stride]
 int launch_set_control_native(const DModel& dm, const Batch& b, const double* ctrl, int t, void* stream);
 int launch_get_state_native(const DModel& dm, const Batch& b, double* state, int t, int nstate, void* stream);

@@ -242,6 +242,126 @@ MJB_HD void stage_solve(const Env& d) {
 MJB_HD void stage_finish_forward(const Env& d) {
   if (d.solver == SOL_PGS) dual_finish(d);
 }
+// ---- sensors (engine_sensor.c: mj_computeSensorPos :525-836, Vel :839-955, Acc :958-1385, apply_cutoff
+// :198-223, frame helpers :227-277; mj_objectVelocity engine_core_util.c:835-886, mju_transformSpatial
+// engine_util_spatial.c).  All supported sensors read quantities that stay valid until the end of the
+// forward pass, so the three stage-wise sweeps of the reference collapse into one, run after the solve.
+MJB_HD void sensor_frame(const Env& d, int kind, int id, V3& pos, M3& mat) {
+  if (kind == SOBJ_XBODY) { pos = ld3(d.xpos(), 3 * id); mat = ld9(d.xmat(), 9 * id); }
+  else if (kind == SOBJ_BODY) { pos = ld3(d.xipos(), 3 * id); mat = ld9(d.ximat(), 9 * id); }
+  else { pos = ld3(d.geom_xpos(), 3 * id); mat = ld9(d.geom_xmat(), 9 * id); }
+}
+MJB_HD Q4 sensor_quat(const Env& d, int kind, int id) {
+  const DModel& m = d.m;
+  if (kind == SOBJ_XBODY) return ld4(d.xquat(), 4 * id);
+  if (kind == SOBJ_BODY) return qmul(ld4(d.xquat(), 4 * id), ldc4(m.body_iquat, 4 * id));
+  return qmul(ld4(d.xquat(), 4 * m.geom_bodyid[id]), ldc4(m.geom_quat, 4 * id));
+}
+MJB_HD V3 mulmTv(const M3& a, V3 v) {   // mju_mulMatTVec3
+  return V3{a.m[0] * v.x + a.m[3] * v.y + a.m[6] * v.z, a.m[1] * v.x + a.m[4] * v.y + a.m[7] * v.z,
+            a.m[2] * v.x + a.m[5] * v.y + a.m[8] * v.z};
+}
+// 6D velocity of an object frame in the global frame (angular, linear)
+MJB_HD void object_velocity(const Env& d, int kind, int id, V3& ang, V3& lin) {
+  const DModel& m = d.m;
+  const int body = (kind == SOBJ_GEOM) ? m.geom_bodyid[id] : id;
+  if (m.body_dofnum[m.body_weldid[body]] == 0) { ang = V3{0, 0, 0}; lin = V3{0, 0, 0}; return; }
+  V3 pos; M3 mat;
+  sensor_frame(d, kind, id, pos, mat);
+  FD cvel = d.cvel();
+  ang = ld3(cvel, 6 * body);
+  const V3 vl = ld3(cvel, 6 * body + 3);
+  const V3 dif = pos - ld3(d.subtree_com(), 3 * m.body_rootid[body]);
+  lin = vl - cross(dif, ang);
+}
+
+MJB_HD void sensors(const Env& d) {
+  const DModel& m = d.m;
+  if (!m.sz.nsensor || (m.opt.disableflags & DSBL_SENSOR)) return;
+  const int nefc = d.nefc()[0], nf = d.nf()[0];
+  FD out = d.sensordata();
+  FI etype = d.efc_type(), eid = d.efc_id();
+  MJB_PFOR(i, m.sz.nsensor) {
+    const int type = m.sensor_type[i], id = m.sensor_objid[i], adr = m.sensor_adr[i], dim = m.sensor_dim[i];
+    const int okind = m.sensor_objtype[i], rkind = m.sensor_reftype[i], refid = m.sensor_refid[i];
+    double v[4] = {0, 0, 0, 0};
+    auto limit_row = [&](int ctype) {   // first limit row of this joint / tendon, -1 if inactive
+      for (int j = nf; j < nefc; j++) if (etype[j] == ctype && eid[j] == id) return j;
+      return -1;
+    };
+    switch (type) {
+      case SENS_JOINTPOS: v[0] = d.qpos()[m.jnt_qposadr[id]]; break;
+      case SENS_TENDONPOS: v[0] = d.ten_length()[id]; break;
+      case SENS_ACTUATORPOS: v[0] = d.actuator_length()[id]; break;
+      case SENS_BALLQUAT: { Q4 q = ld4(d.qpos(), m.jnt_qposadr[id]); normalize(q); v[0] = q.w; v[1] = q.x; v[2] = q.y; v[3] = q.z; break; }
+      case SENS_JOINTLIMITPOS: { const int j = limit_row(CNSTR_LIMIT_JOINT); if (j >= 0) v[0] = d.efc_pos()[j] - d.efc_margin()[j]; break; }
+      case SENS_TENDONLIMITPOS: { const int j = limit_row(CNSTR_LIMIT_TENDON); if (j >= 0) v[0] = d.efc_pos()[j] - d.efc_margin()[j]; break; }
+      case SENS_FRAMEPOS: case SENS_FRAMEXAXIS: case SENS_FRAMEYAXIS: case SENS_FRAMEZAXIS: {
+        V3 pos; M3 mat;
+        sensor_frame(d, okind, id, pos, mat);
+        const int off = type - SENS_FRAMEXAXIS;
+        V3 r = (type == SENS_FRAMEPOS) ? pos : V3{mat.m[off], mat.m[off + 3], mat.m[off + 6]};
+        if (refid >= 0) {
+          V3 rpos; M3 rmat;
+          sensor_frame(d, rkind, refid, rpos, rmat);
+          r = mulmTv(rmat, (type == SENS_FRAMEPOS) ? pos - rpos : r);
+        }
+        v[0] = r.x; v[1] = r.y; v[2] = r.z;
+        break;
+      }
+      case SENS_FRAMEQUAT: {
+        Q4 q = sensor_quat(d, okind, id);
+        if (refid >= 0) {
+          Q4 rq = sensor_quat(d, rkind, refid);
+          rq = Q4{rq.w, -rq.x, -rq.y, -rq.z};
+          q = qmul(rq, q);
+        }
+        v[0] = q.w; v[1] = q.x; v[2] = q.y; v[3] = q.z;
+        break;
+      }
+      case SENS_SUBTREECOM: { const V3 c = ld3(d.subtree_com(), 3 * id); v[0] = c.x; v[1] = c.y; v[2] = c.z; break; }
+      case SENS_CLOCK: v[0] = d.time()[0]; break;
+      case SENS_JOINTVEL: v[0] = d.qvel()[m.jnt_dofadr[id]]; break;
+      case SENS_TENDONVEL: v[0] = d.ten_velocity()[id]; break;
+      case SENS_ACTUATORVEL: v[0] = d.actuator_velocity()[id]; break;
+      case SENS_BALLANGVEL: { const V3 w = ld3(d.qvel(), m.jnt_dofadr[id]); v[0] = w.x; v[1] = w.y; v[2] = w.z; break; }
+      case SENS_JOINTLIMITVEL: { const int j = limit_row(CNSTR_LIMIT_JOINT); if (j >= 0) v[0] = d.efc_vel()[j]; break; }
+      case SENS_TENDONLIMITVEL: { const int j = limit_row(CNSTR_LIMIT_TENDON); if (j >= 0) v[0] = d.efc_vel()[j]; break; }
+      case SENS_FRAMELINVEL: case SENS_FRAMEANGVEL: {
+        V3 ang, lin;
+        object_velocity(d, okind, id, ang, lin);
+        if (refid >= 0) {
+          V3 pos, rpos, rang, rlin; M3 mat, rmat;
+          sensor_frame(d, okind, id, pos, mat);
+          sensor_frame(d, rkind, refid, rpos, rmat);
+          object_velocity(d, rkind, refid, rang, rlin);
+          V3 rel_ang = ang - rang, rel_lin = lin - rlin;
+          rel_lin = rel_lin + cross(pos - rpos, rang);
+          ang = mulmTv(rmat, rel_ang);
+          lin = mulmTv(rmat, rel_lin);
+        }
+        const V3 r = (type == SENS_FRAMELINVEL) ? lin : ang;
+        v[0] = r.x; v[1] = r.y; v[2] = r.z;
+        break;
+      }
+      case SENS_ACTUATORFRC: v[0] = d.actuator_force()[id]; break;
+      case SENS_JOINTACTFRC: v[0] = d.qfrc_actuator()[m.jnt_dofadr[id]]; break;
+      case SENS_JOINTLIMITFRC: { const int j = limit_row(CNSTR_LIMIT_JOINT); if (j >= 0) v[0] = d.efc_force()[j]; break; }
+      case SENS_TENDONLIMITFRC: { const int j = limit_row(CNSTR_LIMIT_TENDON); if (j >= 0) v[0] = d.efc_force()[j]; break; }
+      default: break;
+    }
+    const int cm = m.sensor_cutmode[i];
+    const double cut = m.sensor_cutoff[i];
+    for (int k = 0; k < dim && k < 4; k++) {
+      double x = v[k];
+      if (cm == 1) x = dclip(x, -cut, cut);
+      else if (cm == 2) x = dmin(cut, x);
+      out[adr + k] = x;
+    }
+  }
+  MJB_PSYNC();
+}
+
 // explicit Runge-Kutta 4 (mj_RungeKutta, engine_forward.c:1486-1591) split into phases around the
 // forward passes, which are separate launches of the fused kernel:
 //   phase 1..3 (after forward #phase-1): record F[phase-1] = qacc, form X[phase] = X[0] (+) h*dX with the

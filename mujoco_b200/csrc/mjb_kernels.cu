@@ -65,6 +65,12 @@ __global__ void k_get_state(DModel m, Batch b, double* state, int nstep, int t, 
   run_get_state(m, b, e, state, nstep, t, nstate);
 }
 
+__global__ void k_get_sensor(DModel m, Batch b, double* sens, int nstep, int t, int nsens) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= b.nenv) return;
+  run_get_sensor(m, b, e, sens, nstep, t, nsens);
+}
+
 __global__ void k_set_control_native(DModel m, Batch b, const double* ctrl, int t) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= b.nenv) return;
@@ -176,6 +182,12 @@ int launch_stages(const DModel& dm, const Batch& b, int mask, int flags, void* s
   }
   g_launches++;
   CK(cudaPeekAtLastError(), "step kernel launch");
+  return 0;
+}
+int launch_get_sensor(const DModel& dm, const Batch& b, double* sens, int nstep, int t, int nsens, void* s) {
+  k_get_sensor<<<nblocks(b, 128), 128, 0, (cudaStream_t)s>>>(dm, b, sens, nstep, t, nsens);
+  g_launches++;
+  CK(cudaPeekAtLastError(), "get_sensor launch");
   return 0;
 }
 int launch_rk4(const DModel& dm, const Batch& b, int phase, int flags, void* s) {

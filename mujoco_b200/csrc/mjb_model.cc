@@ -236,6 +236,51 @@ static void contact_param(const mjModel* m, int g1, int g2, int* condim, double*
   for (int i = 0; i < 5; i++) friction[i] = std::max((double)mjMINMU, friction[i]);  // mj_assignFriction
 }
 
+// sensors of the path: mjtSensor -> internal code, object kinds for the frame sensors; false = unsupported
+static bool sensor_code(const mjModel* m, int i, int* code, int* okind, int* rkind) {
+  auto kind = [](int objtype, int* k) {
+    if (objtype == mjOBJ_XBODY) { *k = SOBJ_XBODY; return true; }
+    if (objtype == mjOBJ_BODY) { *k = SOBJ_BODY; return true; }
+    if (objtype == mjOBJ_GEOM) { *k = SOBJ_GEOM; return true; }
+    return false;
+  };
+  *okind = 0; *rkind = 0;
+  bool frame = false;
+  switch (m->sensor_type[i]) {
+    case mjSENS_JOINTPOS: *code = SENS_JOINTPOS; break;
+    case mjSENS_TENDONPOS: *code = SENS_TENDONPOS; break;
+    case mjSENS_ACTUATORPOS: *code = SENS_ACTUATORPOS; break;
+    case mjSENS_BALLQUAT: *code = SENS_BALLQUAT; break;
+    case mjSENS_JOINTLIMITPOS: *code = SENS_JOINTLIMITPOS; break;
+    case mjSENS_TENDONLIMITPOS: *code = SENS_TENDONLIMITPOS; break;
+    case mjSENS_FRAMEPOS: *code = SENS_FRAMEPOS; frame = true; break;
+    case mjSENS_FRAMEXAXIS: *code = SENS_FRAMEXAXIS; frame = true; break;
+    case mjSENS_FRAMEYAXIS: *code = SENS_FRAMEYAXIS; frame = true; break;
+    case mjSENS_FRAMEZAXIS: *code = SENS_FRAMEZAXIS; frame = true; break;
+    case mjSENS_FRAMEQUAT: *code = SENS_FRAMEQUAT; frame = true; break;
+    case mjSENS_SUBTREECOM: *code = SENS_SUBTREECOM; break;
+    case mjSENS_CLOCK: *code = SENS_CLOCK; break;
+    case mjSENS_JOINTVEL: *code = SENS_JOINTVEL; break;
+    case mjSENS_TENDONVEL: *code = SENS_TENDONVEL; break;
+    case mjSENS_ACTUATORVEL: *code = SENS_ACTUATORVEL; break;
+    case mjSENS_BALLANGVEL: *code = SENS_BALLANGVEL; break;
+    case mjSENS_JOINTLIMITVEL: *code = SENS_JOINTLIMITVEL; break;
+    case mjSENS_TENDONLIMITVEL: *code = SENS_TENDONLIMITVEL; break;
+    case mjSENS_FRAMELINVEL: *code = SENS_FRAMELINVEL; frame = true; break;
+    case mjSENS_FRAMEANGVEL: *code = SENS_FRAMEANGVEL; frame = true; break;
+    case mjSENS_ACTUATORFRC: *code = SENS_ACTUATORFRC; break;
+    case mjSENS_JOINTACTFRC: *code = SENS_JOINTACTFRC; break;
+    case mjSENS_JOINTLIMITFRC: *code = SENS_JOINTLIMITFRC; break;
+    case mjSENS_TENDONLIMITFRC: *code = SENS_TENDONLIMITFRC; break;
+    default: return false;
+  }
+  if (frame) {
+    if (!kind(m->sensor_objtype[i], okind)) return false;
+    if (m->sensor_refid[i] >= 0 && !kind(m->sensor_reftype[i], rkind)) return false;
+  }
+  return true;
+}
+
 // ------------------------------------------------------------------------------------------------
 int check_model(const mjModel* m) {
   char msg[256];
@@ -244,7 +289,13 @@ int check_model(const mjModel* m) {
   if (m->nflex || m->nhfield || m->nmocap || m->nplugin) FAIL("flex / hfield / mocap / plugin present");
   if (m->neq) FAIL("equality constraints (neq=%d) are a 'next' row of the scope table", (int)m->neq);
   if (m->na) FAIL("stateful actuators (na=%d)", (int)m->na);
-  if (m->nsensor) FAIL("sensors (nsensor=%d)", (int)m->nsensor);
+  if (m->opt.disableflags & mjDSBL_SENSOR) { /* sensordata simply stays untouched */ }
+  for (int i = 0; i < m->nsensor; i++) {
+    int code, okind, rkind;
+    if (!sensor_code(m, i, &code, &okind, &rkind))
+      FAIL("sensor %d: type %d / object type %d is outside the supported set", i, (int)m->sensor_type[i], (int)m->sensor_objtype[i]);
+    if (m->sensor_history[2 * i] > 0 || m->sensor_delay[i] > 0 || m->sensor_interval[2 * i] > 0) FAIL("sensor %d: history / delay / interval", i);
+  }
   if (m->npair) FAIL("predefined contact pairs (npair=%d)", (int)m->npair);
   if (m->nhistory) FAIL("history buffers / delays");
   if (m->flg_gravcomp) FAIL("gravity compensation");
@@ -322,6 +373,7 @@ int build_host_model(const mjModel* m, int nconmax, int njmax, HostModel* out) {
   S.nq = m->nq; S.nv = m->nv; S.nu = m->nu; S.na = m->na; S.nbody = m->nbody; S.njnt = m->njnt;
   S.ngeom = m->ngeom; S.ntendon = m->ntendon; S.nwrap = m->nwrap; S.nJten = m->nJten; S.nC = m->nC;
   S.ntree = m->ntree;
+  S.nsensor = m->nsensor; S.nsensordata = m->nsensordata;
 
   Options& O = D.opt;
   O.timestep = m->opt.timestep; O.impratio = m->opt.impratio; O.tolerance = m->opt.tolerance;
@@ -359,6 +411,26 @@ int build_host_model(const mjModel* m, int nconmax, int njmax, HostModel* out) {
   B.addI(&D.dof_simplenum, m->dof_simplenum, m->nv);
   B.addI(&D.dof_treeid, m->dof_treeid, m->nv);
   B.addI(&D.body_treeid, m->body_treeid, m->nbody);
+  {   // sensors: internal type codes, cutoff mode (0 none, 1 real: both sides, 2 positive: upper side)
+    std::vector<int> st(m->nsensor), cm(m->nsensor), ok(m->nsensor), rk(m->nsensor), rid(m->nsensor);
+    for (int i = 0; i < m->nsensor; i++) {
+      sensor_code(m, i, &st[i], &ok[i], &rk[i]);
+      rid[i] = m->sensor_refid[i];
+      cm[i] = 0;
+      if (m->sensor_cutoff[i] > 0) {
+        if (m->sensor_datatype[i] == mjDATATYPE_REAL) cm[i] = 1;
+        else if (m->sensor_datatype[i] == mjDATATYPE_POSITIVE) cm[i] = 2;
+      }
+    }
+    B.addI(&D.sensor_type, st.data(), m->nsensor);
+    B.addI(&D.sensor_cutmode, cm.data(), m->nsensor);
+    B.addI(&D.sensor_objtype, ok.data(), m->nsensor);
+    B.addI(&D.sensor_objid, m->sensor_objid, m->nsensor);
+    B.addI(&D.sensor_reftype, rk.data(), m->nsensor);
+    B.addI(&D.sensor_refid, rid.data(), m->nsensor);
+    B.addI(&D.sensor_dim, m->sensor_dim, m->nsensor);
+    B.addI(&D.sensor_adr, m->sensor_adr, m->nsensor);
+  }
   B.addI(&D.M_rownnz, m->M_rownnz, m->nv);
   B.addI(&D.M_rowadr, m->M_rowadr, m->nv);
   B.addI(&D.M_colind, m->M_colind, m->nC);
@@ -468,6 +540,7 @@ int build_host_model(const mjModel* m, int nconmax, int njmax, HostModel* out) {
   }
   B.addD(&D.actuator_ctrlrange, m->actuator_ctrlrange, 2 * m->nu);
   B.addD(&D.actuator_forcerange, m->actuator_forcerange, 2 * m->nu);
+  B.addD(&D.sensor_cutoff, m->sensor_cutoff, m->nsensor);
 
   int has_lim = 0, has_fl = 0;
   for (int i = 0; i < m->njnt; i++) has_lim |= m->jnt_limited[i];

@@ -31,7 +31,7 @@ MJB_HD void run_stage_mask(const Env& d, int mask, int flags) {
     if ((mask & 1) || redo) stage_position(d, (flags & 1) != 0 && !redo);
     if ((mask & 2) || redo) stage_velocity(d);
     if ((mask & 4) || redo) stage_solve(d);
-    if (mask & (8 | 16 | 32)) stage_finish_forward(d);
+    if (mask & (8 | 16 | 32)) { stage_finish_forward(d); if (!(flags & 8)) sensors(d); }
     if (!(mask & (8 | 32))) return;
     if (!redo) {
       check_vec(d, d.qacc(), d.m.sz.nv, WARN_BADQACC);
@@ -100,6 +100,14 @@ MJB_HD void run_get_state(const DModel& m, const Batch& b, int e, double* state,
   FD qp = d.qpos(), qv = d.qvel();
   for (int i = 0; i < m.sz.nq; i++) dst[k++] = qp[i];
   for (int i = 0; i < m.sz.nv; i++) dst[k++] = qv[i];
+}
+
+// sensordata [nenv][nstep][nsensordata]; a warned env repeats its last values (the reference pads likewise)
+MJB_HD void run_get_sensor(const DModel& m, const Batch& b, int e, double* sens, int nstep, int t, int nsens) {
+  Env d(m, b, e);
+  double* dst = sens + ((size_t)e * nstep + t) * nsens;
+  FD sd = d.sensordata();
+  for (int i = 0; i < nsens; i++) dst[i] = sd[i];
 }
 
 // native layouts: ctrl [nstep][nu][stride], state [nstep][nstate][stride] — coalesced across envs

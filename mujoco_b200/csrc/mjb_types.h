@@ -32,7 +32,14 @@ enum { STATE_SATISFIED = 0, STATE_QUADRATIC = 1, STATE_LINEARNEG = 2, STATE_LINE
        STATE_CONE = 4 };                                                                // :544-548
 enum { WARN_INERTIA = 0, WARN_CONTACTFULL = 1, WARN_CNSTRFULL = 2, WARN_BADQPOS = 3,
        WARN_BADQVEL = 4, WARN_BADQACC = 5, WARN_BADCTRL = 6, WARN_VGEOMFULL = 7, NWARNING = 8 };
-enum { NISLAND = 20 };   // mjNISLAND: islands with solver statistics (mjdata.h)  // :553-561
+enum { NISLAND = 20 };
+// sensors of the path (engine_sensor.c); internal codes, translated from mjtSensor by the host
+enum { SENS_JOINTPOS, SENS_TENDONPOS, SENS_ACTUATORPOS, SENS_BALLQUAT, SENS_JOINTLIMITPOS, SENS_TENDONLIMITPOS,
+       SENS_FRAMEPOS, SENS_FRAMEXAXIS, SENS_FRAMEYAXIS, SENS_FRAMEZAXIS, SENS_FRAMEQUAT, SENS_SUBTREECOM, SENS_CLOCK,
+       SENS_JOINTVEL, SENS_TENDONVEL, SENS_ACTUATORVEL, SENS_BALLANGVEL, SENS_JOINTLIMITVEL, SENS_TENDONLIMITVEL,
+       SENS_FRAMELINVEL, SENS_FRAMEANGVEL, SENS_ACTUATORFRC, SENS_JOINTACTFRC, SENS_JOINTLIMITFRC,
+       SENS_TENDONLIMITFRC };
+enum { SOBJ_XBODY = 0, SOBJ_BODY = 1, SOBJ_GEOM = 2 };   // frame sensor object kinds (mjOBJ_XBODY/BODY/GEOM)   // mjNISLAND: islands with solver statistics (mjdata.h)  // :553-561
 enum { SOL_PGS = 0, SOL_CG = 1, SOL_NEWTON = 2 };                                        // :202-204
 enum { INT_EULER = 0, INT_RK4 = 1, INT_IMPLICIT = 2, INT_IMPLICITFAST = 3 };             // :181-184
 enum { SAMEFRAME_NONE = 0, SAMEFRAME_BODY = 1, SAMEFRAME_INERTIA = 2, SAMEFRAME_BODYROT = 3,
@@ -43,7 +50,7 @@ enum { DSBL_CONSTRAINT = 1 << 0, DSBL_EQUALITY = 1 << 1, DSBL_FRICTIONLOSS = 1 <
        DSBL_CONTACT = 1 << 4, DSBL_SPRING = 1 << 5, DSBL_DAMPER = 1 << 6, DSBL_GRAVITY = 1 << 7,
        DSBL_CLAMPCTRL = 1 << 8, DSBL_WARMSTART = 1 << 9, DSBL_FILTERPARENT = 1 << 10,
        DSBL_ACTUATION = 1 << 11, DSBL_REFSAFE = 1 << 12, DSBL_EULERDAMP = 1 << 15,
-       DSBL_AUTORESET = 1 << 16, DSBL_ISLAND = 1 << 18 };                                // :54-73
+       DSBL_AUTORESET = 1 << 16, DSBL_ISLAND = 1 << 18, DSBL_SENSOR = 1 << 13 };                                // :54-73
 enum { LIM_HINGE = 0, LIM_BALL = 1, LIM_TENDON = 2 };   // kinds of limit candidates (host-built table)
 constexpr int kNPoly = 2;   // mjNPOLY (include/mujoco/mjmodel.h:44)
 constexpr int kNGain = 3;   // leading gain/bias parameters used by the supported actuator family
@@ -51,6 +58,7 @@ constexpr int kNGain = 3;   // leading gain/bias parameters used by the supporte
 // ---- model sizes and options --------------------------------------------------------------------
 struct Sizes {
   int nq, nv, nu, na, nbody, njnt, ngeom, ntendon, nwrap, nJten, nC, ntree;
+  int nsensor, nsensordata;
   int npair;     // static candidate geom pairs (host-built, reference order)
   int nconmax;   // per-env contact cap
   int njmax;     // per-env constraint-row cap
@@ -89,7 +97,9 @@ struct Options {
   X(lvl_adr) X(lvl_body) X(child_adr) X(child_id)                                             \
   X(dlvl_adr) X(dlvl_dof) X(mt_adr) X(mt_dof) X(mt_qadr)                                      \
   X(fac_adr) X(fac_dst) X(fac_src) X(fac_cf)                                                  \
-  X(lim_kind) X(lim_id) X(lim_side) X(fl_dof) X(body_dofanc)
+  X(lim_kind) X(lim_id) X(lim_side) X(fl_dof) X(body_dofanc)                                 \
+  X(sensor_type) X(sensor_cutmode) X(sensor_objtype) X(sensor_objid) X(sensor_reftype) X(sensor_refid)   \
+  X(sensor_dim) X(sensor_adr)
 
 #define MJB_MODEL_DBL_FIELDS(X)                                                             \
   X(qpos0) X(qpos_spring) X(body_pos) X(body_quat) X(body_ipos) X(body_iquat) X(body_mass)   \
@@ -104,7 +114,7 @@ struct Options {
   X(tendon_dampingpoly_eff) X(tendon_lengthspring) X(tendon_armature_eff)                    \
   X(actuator_gear0) X(actuator_gainprm) X(actuator_biasprm) X(actuator_ctrlrange)            \
   X(actuator_forcerange)                                                                     \
-  X(pair_margin) X(pair_includemargin) X(pair_solref) X(pair_solimp) X(pair_friction)
+  X(pair_margin) X(pair_includemargin) X(pair_solref) X(pair_solimp) X(pair_friction) X(sensor_cutoff)
 
 struct DModel {
   Sizes sz;
@@ -141,7 +151,7 @@ struct DModel {
   X(efc_D, S.njmax) X(efc_R, S.njmax) X(efc_vel, S.njmax) X(efc_aref, S.njmax)               \
   X(efc_b, S.njmax) X(efc_force, S.njmax)                                                    \
   X(scr_body, 12 * S.nbody) X(scr_nv, 8 * S.nv) X(scr_efc, 6 * S.njmax)                         \
-  X(nwt_nv, 6 * S.nv) X(nwt_efc, 6 * S.njmax) X(rk_scr, S.nq + 8 * S.nv + 4)
+  X(nwt_nv, 6 * S.nv) X(nwt_efc, 6 * S.njmax) X(rk_scr, S.nq + 8 * S.nv + 4) X(sensordata, S.nsensordata)
 
 // COLD doubles: stay in global memory / L2 in every mapping
 #define MJB_DATA_COLD_FIELDS(X, S)                                                           \

@@ -20,6 +20,10 @@ REF = os.environ.get("MJB_REFERENCE", "/root/reference")
 MODELS = {
     "humanoid": os.path.join(REF, "model/humanoid/humanoid.xml"),
     "ant": os.path.join(ROOT, "models", "ant.xml"),          # authored here (BASELINE config 3)
+    # test models derived from the ant: dry friction rows, several trees (islands), sensors
+    "ant_frictionloss": os.path.join(ROOT, "models", "ant_frictionloss.xml"),
+    "ant_balls": os.path.join(ROOT, "models", "ant_balls.xml"),
+    "ant_sensors": os.path.join(ROOT, "models", "ant_sensors.xml"),
 }
 
 

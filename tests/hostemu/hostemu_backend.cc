@@ -33,6 +33,11 @@ int launch_stages(const DModel& dm, const Batch& b, int mask, int flags, void*) 
   for (int e = 0; e < b.nenv; e++) run_env(dm, b, e, mask, flags, 0, 1, nullptr, 0);
   return 0;
 }
+int launch_get_sensor(const DModel& dm, const Batch& b, double* sens, int nstep, int t, int nsens, void*) {
+  g_launches++;
+  for (int e = 0; e < b.nenv; e++) run_get_sensor(dm, b, e, sens, nstep, t, nsens);
+  return 0;
+}
 int launch_rk4(const DModel& dm, const Batch& b, int phase, int flags, void*) {
   g_launches++;
   for (int e = 0; e < b.nenv; e++) run_rk4(dm, b, e, phase, flags, 0, 1);

@@ -238,3 +238,40 @@ def test_mjdata_bridge_matches_mj_step():
             assert ref[e].scalar("ncon") == ours[e].scalar("ncon") and ref[e].scalar("nefc") == ours[e].scalar("nefc")
             for f in fields:
                 assert np.array_equal(np.array(ref[e].dfield(f)), np.array(ours[e].dfield(f))), (t, e, f)
+
+
+@pytest.mark.parametrize("solver,integrator", [(mb.SOLVER_NEWTON, mb.INT_EULER), (mb.SOLVER_PGS, mb.INT_EULER),
+                                               (mb.SOLVER_NEWTON, mb.INT_RK4)])
+def test_sensors_bit_exact(solver, integrator):
+    """sensordata (engine_sensor.c): one sensor of every supported type — joint / tendon / actuator
+    position, velocity and force, limit distance / velocity / force, ball-joint quaternion and rate, frame
+    position / axes / quaternion / linear and angular velocity (absolute and relative to a reference
+    frame, objects xbody / body / geom), subtree com, clock, with and without cutoff — recorded by
+    rollout() like python/mujoco/rollout.cc:160-170; RK4 evaluates sensors in the first forward only"""
+    from oracle_util import Oracle
+    path = os.path.join(ROOT, "models", "ant_sensors.mjb")
+    nenv, nstep = 4, 60
+    m = mb.Model(path, library=hostemu_lib())
+    m.set_option("solver", solver)
+    m.set_option("integrator", integrator)
+    b = mb.Batch(m, nenv, nconmax=48, njmax=128)
+    oracles = [Oracle(path) for _ in range(nenv)]
+    rough = integrator == mb.INT_EULER     # explicit RK4 at dt = 0.01 diverges from the rougher states
+    s0 = perturbed_states(oracles[0], nenv, seed=91, height=[0.35, 0.5, 0.75], qvel_std=0.5 if rough else 0.1,
+                          qpos_std=0.15 if rough else 0.03)
+    ctrl = np.random.default_rng(92).uniform(-1, 1, (nenv, nstep, oracles[0].size("nu")))
+    out, sens = b.rollout(s0, ctrl, return_sensordata=True)
+    ns = oracles[0].size("nsensordata")
+    assert sens.shape == (nenv, nstep, ns) and ns == 70
+    for e, o in enumerate(oracles):
+        o.set_opt("solver", solver)
+        o.set_opt("integrator", integrator)
+        o.reset()
+        o.set_state(s0[e])
+        for t in range(nstep):
+            o.dfield("ctrl")[:] = ctrl[e, t]
+            o.step()
+            ref = np.array(o.dfield("sensordata"))
+            assert np.array_equal(sens[e, t], ref), (e, t, np.argwhere(sens[e, t] != ref).ravel()[:8])
+            assert np.array_equal(out[e, t], o.get_state())
+    assert np.abs(sens).max() > 0 and (b.warnings() == 0).all()
