@@ -162,3 +162,40 @@ def test_constraint_islands_vs_oracle(solver):
     assert rel < RTOL_TIGHT
     compare_forward(b, o, ref[:, 100, :], ctrl[:, 100, :], rtol=RTOL_TIGHT, check_dual=(solver == mb.SOLVER_PGS))
     assert b.field("nisland")[:, 0].max() >= 3
+
+
+def test_sensors_and_mjdata_bridge_vs_oracle():
+    """sensordata through rollout() (32 sensors of every supported type, models/ant_sensors.xml) and the
+    mjData bridge (mjb_step_mjdata on the reference's own mjData objects), both against mj_step"""
+    assert available()
+    path = os.path.join(ROOT, "models", "ant_sensors.mjb")
+    nenv, nstep = 6, 50
+    m = mb.Model(path)
+    m.set_option("solver", mb.SOLVER_NEWTON)
+    b = mb.Batch(m, nenv, nconmax=48, njmax=128)
+    ref = [Oracle(path) for _ in range(nenv)]
+    ours = [Oracle(path) for _ in range(nenv)]
+    s0 = perturbed_states(ref[0], nenv, seed=91, height=[0.35, 0.5, 0.75], qvel_std=0.5, qpos_std=0.15)
+    ctrl = np.random.default_rng(92).uniform(-1, 1, (nenv, nstep, ref[0].size("nu")))
+    out, sens = b.rollout(s0, ctrl, return_sensordata=True)
+    b2 = mb.Batch(m, nenv, nconmax=48, njmax=128)
+    for e in range(nenv):
+        for o in (ref[e], ours[e]):
+            o.set_opt("solver", mb.SOLVER_NEWTON)
+            o.reset()
+            o.set_state(s0[e])
+    worst = 0.0
+    for t in range(nstep):
+        for e in range(nenv):
+            ref[e].dfield("ctrl")[:] = ctrl[e, t]
+            ours[e].dfield("ctrl")[:] = ctrl[e, t]
+            ref[e].step()
+        b2.step_mjdata([o.d for o in ours])
+        for e in range(nenv):
+            r = np.array(ref[e].dfield("sensordata"))
+            worst = max(worst, np.abs(sens[e, t] - r).max() / max(1.0, np.abs(r).max()))
+            for f in ("qpos", "qvel", "qacc", "xpos", "cvel", "qfrc_constraint"):
+                a, c = np.array(ours[e].dfield(f)), np.array(ref[e].dfield(f))
+                worst = max(worst, np.abs(a - c).max() / max(1.0, np.abs(c).max()))
+    print("sensors / bridge worst rel err %.3e" % worst)
+    assert worst < RTOL_TIGHT
