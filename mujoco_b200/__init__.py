@@ -25,7 +25,7 @@ STATE_WARMSTART, STATE_CTRL, STATE_QFRC_APPLIED, STATE_PLUGIN = 32, 64, 128, 1 <
 STATE_FULLPHYSICS = STATE_TIME | STATE_QPOS | STATE_QVEL | STATE_ACT | STATE_HISTORY | STATE_PLUGIN
 
 SOLVER_PGS, SOLVER_CG, SOLVER_NEWTON = 0, 1, 2
-INT_EULER, INT_RK4 = 0, 1
+INT_EULER, INT_RK4, INT_IMPLICIT, INT_IMPLICITFAST = 0, 1, 2, 3
 
 
 class MjbError(RuntimeError):

@@ -220,6 +220,83 @@ MJB_HD void euler_advance(const Env& d) {
   MJB_PSYNC();
 }
 
+// implicitfast integrator (mj_implicitSkip, engine_forward.c:1649-1771, without standalone free bodies):
+// qH = M - h * d(qfrc_actuator + qfrc_passive)/d(qvel) on M's sparsity (mjd_smooth_vel with flg_bias = 0,
+// engine_derivative.c:3145-3170: actuator velocity gains mjd_actuator_vel :2350-2500, then dof and tendon
+// damping mjd_passive_vel :3040-3140; entries outside the tree sparsity are dropped as in the reference),
+// L'DL, qacc_int = qH^-1 (qfrc_smooth + qfrc_constraint), mj_advance
+MJB_HDN void implicitfast_advance(const Env& d) {
+  const DModel& m = d.m;
+  const int nv = m.sz.nv, nu = m.sz.nu, ntendon = m.sz.ntendon;
+  const double h = m.opt.timestep;
+  FD qacc = d.qacc(), qvel = d.qvel(), qH = d.qH(), M = d.M();
+  FD acc = d.scr_nv();
+  FD tB = d.scr_nv() + nv;          // per tendon: B = -d(damping force)/d(velocity)
+  FD aB = d.scr_nv() + 2 * nv;      // per actuator: d(force)/d(velocity) (0 when clamped)   [nu <= 4 nv]
+  const bool act_on = !(m.opt.disableflags & DSBL_ACTUATION);
+  const bool spring_off = (m.opt.disableflags & DSBL_SPRING) != 0, damper_off = (m.opt.disableflags & DSBL_DAMPER) != 0;
+  const bool passive_on = !(spring_off && damper_off) && !damper_off;
+  FD tv = d.ten_velocity(), tJ = d.ten_J(), mom = d.actuator_moment(), force = d.actuator_force(), ctrl = d.ctrl();
+  MJB_PFOR(t, ntendon) {
+    tB[t] = passive_on ? -d_xpoly_force(m.tendon_damping_eff[t], m.tendon_dampingpoly_eff + kNPoly * t, kNPoly, tv[t], true) : 0.0;
+  }
+  MJB_PFOR(u, nu) {
+    double bv = 0;
+    bool live = act_on;
+    if (live && m.actuator_forcelimited[u]) {
+      const double f = force[u];
+      if (f <= m.actuator_forcerange[2 * u] || f >= m.actuator_forcerange[2 * u + 1]) live = false;
+    }
+    if (live) {
+      if (m.actuator_biastype[u] == BIAS_AFFINE) bv = m.actuator_biasprm[kNGain * u + 2];
+      const double gv = (m.actuator_gaintype[u] == GAIN_AFFINE) ? m.actuator_gainprm[kNGain * u + 2] : 0.0;
+      if (gv != 0) bv += gv * ctrl[u];
+    }
+    aB[u] = bv;
+  }
+  MJB_PSYNC();
+  MJB_PFOR(i, nv) {
+    const int adr = m.M_rowadr[i], nnz = m.M_rownnz[i];
+    for (int a = 0; a < nnz; a++) {
+      const int j = m.M_colind[adr + a];
+      double q = 0;
+      if (i == j) {
+        for (int u = 0; u < nu; u++) {
+          if (aB[u] != 0 && m.jnt_dofadr[m.actuator_trnjnt[u]] == i) q += mom[u] * (mom[u] * aB[u]);
+        }
+        if (passive_on) q -= d_xpoly_force(m.dof_damping_eff[i], m.dof_dampingpoly_eff + kNPoly * i, kNPoly, qvel[i], true);
+      }
+      for (int t = 0; t < ntendon; t++) {
+        const double B = tB[t];
+        if (B == 0) continue;
+        const int ta = m.ten_J_rowadr[t], tn = m.ten_J_rownnz[t];
+        double Ji = 0, Jj = 0;
+        bool hi = false, hj = false;
+        for (int c = 0; c < tn; c++) {
+          const int col = m.ten_J_colind[ta + c];
+          if (col == i) { Ji = tJ[ta + c]; hi = true; }
+          if (col == j) { Jj = tJ[ta + c]; hj = true; }
+        }
+        if (hi && hj) q += Jj * (Ji * B);
+      }
+      qH[adr + a] = M[adr + a] + q * (-h);
+    }
+  }
+  MJB_PSYNC();
+  factor_I(d, qH, d.qHDiagInv());
+  FD qfs = d.qfrc_smooth(), qfc = d.qfrc_constraint();
+  MJB_PFOR(i, nv) acc[i] = qfs[i] + qfc[i];
+  MJB_PSYNC();
+  solve_LD(d, acc, qH, d.qHDiagInv());
+  MJB_PFOR(i, nv) qvel[i] += acc[i] * h;
+  MJB_PSYNC();
+  integrate_pos(d, d.qpos(), d.qvel(), h);
+  FD ws = d.qacc_warmstart();
+  MJB_PFOR(i, nv) ws[i] = qacc[i];
+  MJB_LANE0 d.time()[0] += h;
+  MJB_PSYNC();
+}
+
 // ---- stages ---------------------------------------------------------------------------------------
 // Every stage is entered by ALL lanes that share the environment.
 MJB_HD void stage_position(const Env& d, bool is_step) {

@@ -301,7 +301,17 @@ int check_model(const mjModel* m) {
   if (m->flg_gravcomp) FAIL("gravity compensation");
   if (m->flg_surfacevel) FAIL("geom surface velocity");
   if (m->opt.cone != mjCONE_PYRAMIDAL) FAIL("elliptic friction cones");
-  if (m->opt.integrator != mjINT_EULER && m->opt.integrator != mjINT_RK4) FAIL("implicit integrators");
+  if (m->opt.integrator == mjINT_IMPLICIT) FAIL("the fully implicit integrator (RNE velocity derivatives, sparse LU)");
+  if (m->opt.integrator == mjINT_IMPLICITFAST) {
+    if (m->ntendon > m->nv) FAIL("implicitfast with more tendons than dofs");
+    // standalone free bodies take a separate unsymmetric 6x6 solve (mjd_freeMhat): not built
+    for (int j = 0; j < m->njnt; j++) {
+      const int b = m->jnt_bodyid[j];
+      if (m->jnt_type[j] == mjJNT_FREE && m->body_jntnum[b] == 1 && m->tree_dofnum[m->dof_treeid[m->jnt_dofadr[j]]] == 6 &&
+          m->body_subtreemass[b] == m->body_mass[b])
+        FAIL("implicitfast with a standalone free body (body %d)", b);
+    }
+  }
   if (m->opt.noslip_iterations > 0) FAIL("noslip solver");
   if (m->opt.enableflags & (mjENBL_OVERRIDE | mjENBL_SLEEP | mjENBL_DIAGEXACT | mjENBL_ENERGY))
     FAIL("enable flags override/sleep/diagexact/energy");

@@ -39,7 +39,7 @@ MJB_HD void run_stage_mask(const Env& d, int mask, int flags) {
       MJB_PSYNC();
       if (bad && !(d.m.opt.disableflags & DSBL_AUTORESET)) continue;
     }
-    if (mask & 8) euler_advance(d);
+    if (mask & 8) { if (d.m.opt.integrator == INT_IMPLICITFAST) implicitfast_advance(d); else euler_advance(d); }
     return;
   }
 }

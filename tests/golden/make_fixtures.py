@@ -24,6 +24,7 @@ MODELS = {
     "ant_frictionloss": os.path.join(ROOT, "models", "ant_frictionloss.xml"),
     "ant_balls": os.path.join(ROOT, "models", "ant_balls.xml"),
     "ant_sensors": os.path.join(ROOT, "models", "ant_sensors.xml"),
+    "ant_servo": os.path.join(ROOT, "models", "ant_servo.xml"),
 }
 
 

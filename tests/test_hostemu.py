@@ -200,7 +200,7 @@ def test_unsupported_models_are_refused():
     with pytest.raises(mb.MjbError, match="elliptic"):
         mb.Batch(m, 1)
     m.set_option("cone", 0)
-    m.set_option("integrator", 3)
+    m.set_option("integrator", 2)
     with pytest.raises(mb.MjbError, match="implicit"):
         mb.Batch(m, 1)
 
@@ -275,3 +275,28 @@ def test_sensors_bit_exact(solver, integrator):
             assert np.array_equal(sens[e, t], ref), (e, t, np.argwhere(sens[e, t] != ref).ravel()[:8])
             assert np.array_equal(out[e, t], o.get_state())
     assert np.abs(sens).max() > 0 and (b.warnings() == 0).all()
+
+
+@pytest.mark.parametrize("model", ["humanoid", "ant", "ant_servo"])
+@pytest.mark.parametrize("solver", [mb.SOLVER_NEWTON, mb.SOLVER_PGS])
+def test_implicitfast_bit_exact(model, solver):
+    """integrator = implicitfast (mj_implicitSkip): qH = M - h d(qfrc_actuator + qfrc_passive)/d(qvel).
+    ant_servo has velocity-dependent actuators (position / velocity servos, an affine general actuator,
+    two of them force-limited so the clamp test matters) and damped tendons, one along a kinematic chain
+    and one across unrelated legs (whose cross terms fall outside the tree sparsity and are dropped)"""
+    path = os.path.join(ROOT, "models", model + ".mjb")
+    nenv, nstep = 6, 150
+    m, b, o = make_pair(path, solver, library=hostemu_lib(), nenv=nenv, integrator=mb.INT_IMPLICITFAST)
+    s0 = perturbed_states(o, nenv, seed=14, height=[0.35, 0.5, 0.75], qvel_std=0.3, qpos_std=0.05)
+    ctrl = np.random.default_rng(15).uniform(-1, 1, (nenv, nstep, o.size("nu")))
+    out = b.rollout(s0, ctrl)
+    ref, stats, _ = o.rollout(s0, ctrl, nthread=4)
+    assert stats[:, 3].sum() == 0
+    assert np.array_equal(out, ref)
+
+
+def test_implicitfast_refuses_standalone_free_bodies():
+    m = mb.Model(os.path.join(ROOT, "models", "ant_balls.mjb"), library=hostemu_lib())
+    m.set_option("integrator", mb.INT_IMPLICITFAST)
+    with pytest.raises(mb.MjbError, match="standalone free body"):
+        mb.Batch(m, 1)
