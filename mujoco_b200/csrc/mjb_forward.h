@@ -225,7 +225,7 @@ MJB_HD void euler_advance(const Env& d) {
 // engine_derivative.c:3145-3170: actuator velocity gains mjd_actuator_vel :2350-2500, then dof and tendon
 // damping mjd_passive_vel :3040-3140; entries outside the tree sparsity are dropped as in the reference),
 // L'DL, qacc_int = qH^-1 (qfrc_smooth + qfrc_constraint), mj_advance
-MJB_HDN void implicitfast_advance(const Env& d) {
+MJB_HD void implicitfast_advance(const Env& d) {
   const DModel& m = d.m;
   const int nv = m.sz.nv, nu = m.sz.nu, ntendon = m.sz.ntendon;
   const double h = m.opt.timestep;
