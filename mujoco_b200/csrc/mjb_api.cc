@@ -508,7 +508,7 @@ int mjb_step_mjdata(mjbBatch* B, struct mjData_* const* dd, int nd) {
   for (int e = 0; e < nenv; e++) d[e]->nefc = it[e];
   if (int rc = field_to_host(B, true, B->b.L.warning, NWARNING, it.data())) return rc;
   for (int e = 0; e < nenv; e++)
-    for (int w = 0; w < NWARNING; w++) {
+    for (int w = 0; w < NWARNING && w < (int)mjNWARNING; w++) {
       // the batch counts warnings since its last reset; mjData accumulates: add what this step raised
       d[e]->warning[w].number += it[(size_t)e * NWARNING + w];
     }
