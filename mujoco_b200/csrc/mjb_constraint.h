@@ -410,23 +410,6 @@ MJB_HD double constraint_update(const Env& d, FD jar, bool want_cost) {
   return s;
 }
 
-// dual state from forces (engine_solver.c dualState, scalar rows)
-MJB_HD void dual_state(const Env& d) {
-  const int nefc = d.nefc()[0], nf = d.nf()[0];
-  FD force = d.efc_force(), floss = d.efc_frictionloss();
-  FI state = d.efc_state();
-  MJB_PFOR(i, nefc) {
-    if (i < nf) {
-      if (force[i] <= -floss[i]) state[i] = STATE_LINEARPOS;
-      else if (force[i] >= floss[i]) state[i] = STATE_LINEARNEG;
-      else state[i] = STATE_QUADRATIC;
-    } else state[i] = (force[i] <= 0) ? STATE_SATISFIED : STATE_QUADRATIC;
-  }
-  MJB_PSYNC();
-}
-
-// M * vec over the tree-sparse symmetric M (mju_mulSymVecSparse): one lane per output dof
-// res[i] = dotSparse(row i incl. diagonal) + sum over descendants k (ascending k) M(k,i)*vec[k]
 // res = M * vec (mj_mulM -> mju_mulSymVecSparse, engine_util_sparse.c): per output dof the order is
 // the diagonal term, the own-row off-diagonals from the last column to the first, then the rows of
 // the descendants in ascending order

@@ -1,12 +1,9 @@
 // CUDA backend of libmjb200 for sm_100a (B200): kernels + the mjb_backend.h implementation.
 //
-// Thread mapping, first generation: one environment per lane.  Every mjData field is stored
-// field[elem][env] (mjb_types.h), so the 32 lanes of a warp touch 32 consecutive doubles = one
-// 256-byte line per element: every global access of every stage is perfectly coalesced, model
-// constants are warp-uniform broadcasts, and all lanes of a warp execute the same body/dof/pair
-// loops (same model), diverging only on contact hit/miss and solver iteration counts.
-// Kernels are launched with 32-thread blocks so that a 4096-env batch spreads its 128 warps over
-// 128 of the 148 SMs; larger batches fill the machine (multiple of 148 x resident CTAs).
+// This translation unit holds the backend glue (allocation, copies, streams, the small I/O kernels, the
+// Runge-Kutta phase kernel, the validation mapping k_step_lane) and dispatches the fused step kernel,
+// whose instantiations (solver x lanes-per-environment) are compiled in their own translation units
+// (mjb_kstep.h, mjb_kstep_*.cu).  Mapping and occupancy rationale: mjb_kstep.h and DESIGN.md section 4.
 // Compiled with -fmad=false: contact in/out decisions must round like the reference's C build.
 #include <cuda_runtime.h>
 

@@ -1,15 +1,13 @@
 // Device-side model (flattened, read-only, replicated per GPU) and the batch data layout for the
 // batched mj_step path.
 //
-// Thread mappings and storage (both address a field element as  e*pitch + (offset+i)*step):
-//   warp-per-env (default): one warp owns one environment.  Storage is env-major: every
-//       environment has one contiguous block, so the 32 lanes of the warp read/write 32 consecutive
-//       elements = one 256-byte line.  The fused step kernel stages the block's HOT part (state and
-//       every smooth-dynamics / contact / constraint-vector field, MJB_DATA_DBL_FIELDS below) into
-//       shared memory, runs all pipeline stages there, and writes it back once; the COLD part
-//       (efc_J, efc_Y, efc_AR: njmax*nv / njmax^2 doubles) stays in global memory / L2.
-//   lane-per-env (mapping 0): one lane owns one environment, storage is field[elem][env]
-//       (SoA across environments): a warp of 32 environments reads one line per element.
+// Storage is env-major: every environment owns one contiguous block of doubles (hot fields first,
+// the cold constraint matrices efc_J / efc_Y / efc_AR and the Newton factor last) and one of ints, so
+// the cooperative lanes of an environment read/write consecutive elements (one 256-byte line per 32
+// doubles) and the block stays hot in L1/L2.  Thread mappings over that storage (Env::lane/nlane):
+//   cooperative (default): 32 lanes (one warp) per environment, or 16 lanes (two small environments
+//       per warp) - MJB_PFOR / MJB_PSYNC / MJB_LANE0 below;
+//   lane-per-env (validation): one lane runs the whole pipeline of one environment.
 // Every mjData field the hot path touches (reference include/mujoco/mjxmacro.h:842-1030) exists
 // per environment.  The per-env arena of the reference (contacts, efc_*) is replaced by fixed caps
 // nconmax / njmax; overflow raises the same warning ids (mjWARN_CONTACTFULL / mjWARN_CNSTRFULL).
