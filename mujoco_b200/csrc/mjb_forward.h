@@ -326,13 +326,15 @@ MJB_HD void stage_finish_forward(const Env& d) {
 MJB_HD void sensor_frame(const Env& d, int kind, int id, V3& pos, M3& mat) {
   if (kind == SOBJ_XBODY) { pos = ld3(d.xpos(), 3 * id); mat = ld9(d.xmat(), 9 * id); }
   else if (kind == SOBJ_BODY) { pos = ld3(d.xipos(), 3 * id); mat = ld9(d.ximat(), 9 * id); }
-  else { pos = ld3(d.geom_xpos(), 3 * id); mat = ld9(d.geom_xmat(), 9 * id); }
+  else if (kind == SOBJ_GEOM) { pos = ld3(d.geom_xpos(), 3 * id); mat = ld9(d.geom_xmat(), 9 * id); }
+  else { pos = ld3(d.site_xpos(), 3 * id); mat = ld9(d.site_xmat(), 9 * id); }
 }
 MJB_HD Q4 sensor_quat(const Env& d, int kind, int id) {
   const DModel& m = d.m;
   if (kind == SOBJ_XBODY) return ld4(d.xquat(), 4 * id);
   if (kind == SOBJ_BODY) return qmul(ld4(d.xquat(), 4 * id), ldc4(m.body_iquat, 4 * id));
-  return qmul(ld4(d.xquat(), 4 * m.geom_bodyid[id]), ldc4(m.geom_quat, 4 * id));
+  if (kind == SOBJ_GEOM) return qmul(ld4(d.xquat(), 4 * m.geom_bodyid[id]), ldc4(m.geom_quat, 4 * id));
+  return qmul(ld4(d.xquat(), 4 * m.site_bodyid[id]), ldc4(m.site_quat, 4 * id));
 }
 MJB_HD V3 mulmTv(const M3& a, V3 v) {   // mju_mulMatTVec3
   return V3{a.m[0] * v.x + a.m[3] * v.y + a.m[6] * v.z, a.m[1] * v.x + a.m[4] * v.y + a.m[7] * v.z,
@@ -341,7 +343,7 @@ MJB_HD V3 mulmTv(const M3& a, V3 v) {   // mju_mulMatTVec3
 // 6D velocity of an object frame in the global frame (angular, linear)
 MJB_HD void object_velocity(const Env& d, int kind, int id, V3& ang, V3& lin) {
   const DModel& m = d.m;
-  const int body = (kind == SOBJ_GEOM) ? m.geom_bodyid[id] : id;
+  const int body = (kind == SOBJ_GEOM) ? m.geom_bodyid[id] : (kind == SOBJ_SITE) ? m.site_bodyid[id] : id;
   if (m.body_dofnum[m.body_weldid[body]] == 0) { ang = V3{0, 0, 0}; lin = V3{0, 0, 0}; return; }
   V3 pos; M3 mat;
   sensor_frame(d, kind, id, pos, mat);
@@ -418,6 +420,14 @@ MJB_HD void sensors(const Env& d) {
           lin = mulmTv(rmat, rel_lin);
         }
         const V3 r = (type == SENS_FRAMELINVEL) ? lin : ang;
+        v[0] = r.x; v[1] = r.y; v[2] = r.z;
+        break;
+      }
+      case SENS_VELOCIMETER: case SENS_GYRO: {   // site velocity expressed in the site frame
+        V3 ang, lin, pos; M3 mat;
+        object_velocity(d, SOBJ_SITE, id, ang, lin);
+        sensor_frame(d, SOBJ_SITE, id, pos, mat);
+        const V3 r = mulmTv(mat, (type == SENS_GYRO) ? ang : lin);
         v[0] = r.x; v[1] = r.y; v[2] = r.z;
         break;
       }

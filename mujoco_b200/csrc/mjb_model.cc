@@ -242,6 +242,7 @@ static bool sensor_code(const mjModel* m, int i, int* code, int* okind, int* rki
     if (objtype == mjOBJ_XBODY) { *k = SOBJ_XBODY; return true; }
     if (objtype == mjOBJ_BODY) { *k = SOBJ_BODY; return true; }
     if (objtype == mjOBJ_GEOM) { *k = SOBJ_GEOM; return true; }
+    if (objtype == mjOBJ_SITE) { *k = SOBJ_SITE; return true; }
     return false;
   };
   *okind = 0; *rkind = 0;
@@ -272,6 +273,8 @@ static bool sensor_code(const mjModel* m, int i, int* code, int* okind, int* rki
     case mjSENS_JOINTACTFRC: *code = SENS_JOINTACTFRC; break;
     case mjSENS_JOINTLIMITFRC: *code = SENS_JOINTLIMITFRC; break;
     case mjSENS_TENDONLIMITFRC: *code = SENS_TENDONLIMITFRC; break;
+    case mjSENS_VELOCIMETER: *code = SENS_VELOCIMETER; *okind = SOBJ_SITE; return m->sensor_objtype[i] == mjOBJ_SITE;
+    case mjSENS_GYRO: *code = SENS_GYRO; *okind = SOBJ_SITE; return m->sensor_objtype[i] == mjOBJ_SITE;
     default: return false;
   }
   if (frame) {
@@ -383,7 +386,7 @@ int build_host_model(const mjModel* m, int nconmax, int njmax, HostModel* out) {
   S.nq = m->nq; S.nv = m->nv; S.nu = m->nu; S.na = m->na; S.nbody = m->nbody; S.njnt = m->njnt;
   S.ngeom = m->ngeom; S.ntendon = m->ntendon; S.nwrap = m->nwrap; S.nJten = m->nJten; S.nC = m->nC;
   S.ntree = m->ntree;
-  S.nsensor = m->nsensor; S.nsensordata = m->nsensordata;
+  S.nsensor = m->nsensor; S.nsensordata = m->nsensordata; S.nsite = m->nsite;
 
   Options& O = D.opt;
   O.timestep = m->opt.timestep; O.impratio = m->opt.impratio; O.tolerance = m->opt.tolerance;
@@ -440,6 +443,8 @@ int build_host_model(const mjModel* m, int nconmax, int njmax, HostModel* out) {
     B.addI(&D.sensor_refid, rid.data(), m->nsensor);
     B.addI(&D.sensor_dim, m->sensor_dim, m->nsensor);
     B.addI(&D.sensor_adr, m->sensor_adr, m->nsensor);
+    B.addI(&D.site_bodyid, m->site_bodyid, m->nsite);
+    B.addI(&D.site_sameframe, m->site_sameframe, m->nsite);
   }
   B.addI(&D.M_rownnz, m->M_rownnz, m->nv);
   B.addI(&D.M_rowadr, m->M_rowadr, m->nv);
@@ -551,6 +556,8 @@ int build_host_model(const mjModel* m, int nconmax, int njmax, HostModel* out) {
   B.addD(&D.actuator_ctrlrange, m->actuator_ctrlrange, 2 * m->nu);
   B.addD(&D.actuator_forcerange, m->actuator_forcerange, 2 * m->nu);
   B.addD(&D.sensor_cutoff, m->sensor_cutoff, m->nsensor);
+  B.addD(&D.site_pos, m->site_pos, 3 * m->nsite);
+  B.addD(&D.site_quat, m->site_quat, 4 * m->nsite);
 
   int has_lim = 0, has_fl = 0;
   for (int i = 0; i < m->njnt; i++) has_lim |= m->jnt_limited[i];

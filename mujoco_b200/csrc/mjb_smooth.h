@@ -113,6 +113,18 @@ MJB_HD void kinematics(const Env& d) {
     else if (sf == SAMEFRAME_BODY || sf == SAMEFRAME_BODYROT) st9(gmat, 9 * g, ld9(xmat, 9 * b));
     else st9(gmat, 9 * g, ld9(ximat, 9 * b));
   }
+  // sites: same local-to-global rule (mj_kinematics, engine_core_smooth.c:222-233)
+  FD spos = d.site_xpos(), smat = d.site_xmat();
+  MJB_PFOR(s_, m.sz.nsite) {
+    const int b = m.site_bodyid[s_], sf = m.site_sameframe[s_];
+    V3 bp = ld3(xpos, 3 * b);
+    if (sf == SAMEFRAME_BODY) st3(spos, 3 * s_, bp);
+    else if (sf == SAMEFRAME_INERTIA) st3(spos, 3 * s_, ld3(xipos, 3 * b));
+    else st3(spos, 3 * s_, mulmv(ld9(xmat, 9 * b), ldc3(m.site_pos, 3 * s_)) + bp);
+    if (sf == SAMEFRAME_NONE) st9(smat, 9 * s_, quat2mat(qmul(ld4(xquat, 4 * b), ldc4(m.site_quat, 4 * s_))));
+    else if (sf == SAMEFRAME_BODY || sf == SAMEFRAME_BODYROT) st9(smat, 9 * s_, ld9(xmat, 9 * b));
+    else st9(smat, 9 * s_, ld9(ximat, 9 * b));
+  }
   MJB_PSYNC();
 }
 

@@ -36,8 +36,8 @@ enum { SENS_JOINTPOS, SENS_TENDONPOS, SENS_ACTUATORPOS, SENS_BALLQUAT, SENS_JOIN
        SENS_FRAMEPOS, SENS_FRAMEXAXIS, SENS_FRAMEYAXIS, SENS_FRAMEZAXIS, SENS_FRAMEQUAT, SENS_SUBTREECOM, SENS_CLOCK,
        SENS_JOINTVEL, SENS_TENDONVEL, SENS_ACTUATORVEL, SENS_BALLANGVEL, SENS_JOINTLIMITVEL, SENS_TENDONLIMITVEL,
        SENS_FRAMELINVEL, SENS_FRAMEANGVEL, SENS_ACTUATORFRC, SENS_JOINTACTFRC, SENS_JOINTLIMITFRC,
-       SENS_TENDONLIMITFRC };
-enum { SOBJ_XBODY = 0, SOBJ_BODY = 1, SOBJ_GEOM = 2 };   // frame sensor object kinds (mjOBJ_XBODY/BODY/GEOM)   // mjNISLAND: islands with solver statistics (mjdata.h)  // :553-561
+       SENS_TENDONLIMITFRC, SENS_VELOCIMETER, SENS_GYRO };
+enum { SOBJ_XBODY = 0, SOBJ_BODY = 1, SOBJ_GEOM = 2, SOBJ_SITE = 3 };   // frame sensor object kinds (mjOBJ_*)   // mjNISLAND: islands with solver statistics (mjdata.h)  // :553-561
 enum { SOL_PGS = 0, SOL_CG = 1, SOL_NEWTON = 2 };                                        // :202-204
 enum { INT_EULER = 0, INT_RK4 = 1, INT_IMPLICIT = 2, INT_IMPLICITFAST = 3 };             // :181-184
 enum { SAMEFRAME_NONE = 0, SAMEFRAME_BODY = 1, SAMEFRAME_INERTIA = 2, SAMEFRAME_BODYROT = 3,
@@ -56,7 +56,7 @@ constexpr int kNGain = 3;   // leading gain/bias parameters used by the supporte
 // ---- model sizes and options --------------------------------------------------------------------
 struct Sizes {
   int nq, nv, nu, na, nbody, njnt, ngeom, ntendon, nwrap, nJten, nC, ntree;
-  int nsensor, nsensordata;
+  int nsensor, nsensordata, nsite;
   int npair;     // static candidate geom pairs (host-built, reference order)
   int nconmax;   // per-env contact cap
   int njmax;     // per-env constraint-row cap
@@ -97,7 +97,7 @@ struct Options {
   X(fac_adr) X(fac_dst) X(fac_src) X(fac_cf)                                                  \
   X(lim_kind) X(lim_id) X(lim_side) X(fl_dof) X(body_dofanc)                                 \
   X(sensor_type) X(sensor_cutmode) X(sensor_objtype) X(sensor_objid) X(sensor_reftype) X(sensor_refid)   \
-  X(sensor_dim) X(sensor_adr)
+  X(sensor_dim) X(sensor_adr) X(site_bodyid) X(site_sameframe)
 
 #define MJB_MODEL_DBL_FIELDS(X)                                                             \
   X(qpos0) X(qpos_spring) X(body_pos) X(body_quat) X(body_ipos) X(body_iquat) X(body_mass)   \
@@ -112,7 +112,7 @@ struct Options {
   X(tendon_dampingpoly_eff) X(tendon_lengthspring) X(tendon_armature_eff)                    \
   X(actuator_gear0) X(actuator_gainprm) X(actuator_biasprm) X(actuator_ctrlrange)            \
   X(actuator_forcerange)                                                                     \
-  X(pair_margin) X(pair_includemargin) X(pair_solref) X(pair_solimp) X(pair_friction) X(sensor_cutoff)
+  X(pair_margin) X(pair_includemargin) X(pair_solref) X(pair_solimp) X(pair_friction) X(sensor_cutoff) X(site_pos) X(site_quat)
 
 struct DModel {
   Sizes sz;
@@ -149,7 +149,8 @@ struct DModel {
   X(efc_D, S.njmax) X(efc_R, S.njmax) X(efc_vel, S.njmax) X(efc_aref, S.njmax)               \
   X(efc_b, S.njmax) X(efc_force, S.njmax)                                                    \
   X(scr_body, 12 * S.nbody) X(scr_nv, 8 * S.nv) X(scr_efc, 6 * S.njmax)                         \
-  X(nwt_nv, 6 * S.nv) X(nwt_efc, 6 * S.njmax) X(rk_scr, S.nq + 8 * S.nv + 4) X(sensordata, S.nsensordata)
+  X(nwt_nv, 6 * S.nv) X(nwt_efc, 6 * S.njmax) X(rk_scr, S.nq + 8 * S.nv + 4) X(sensordata, S.nsensordata)  \
+  X(site_xpos, 3 * S.nsite) X(site_xmat, 9 * S.nsite)
 
 // COLD doubles: stay in global memory / L2 in every mapping
 #define MJB_DATA_COLD_FIELDS(X, S)                                                           \
