@@ -69,6 +69,8 @@ MJB_HD void make_constraint(const Env& d) {
     MJB_PSYNC();
     return;
   }
+  const bool do_eq = m.sz.neq > 0 && !(m.opt.disableflags & DSBL_EQUALITY);
+  FI ieq = d.scr_ieq();   // row of every equality, -1 if inactive
   const bool do_fl = m.opt.has_frictionloss && !(m.opt.disableflags & DSBL_FRICTIONLOSS);
   const bool do_lim = m.opt.has_limits && !(m.opt.disableflags & DSBL_LIMIT);
   const bool do_con = !(m.opt.disableflags & DSBL_CONTACT);
@@ -101,9 +103,19 @@ MJB_HD void make_constraint(const Env& d) {
 
   // ---- serial scan: row index of every friction dof, active limit and included contact
   MJB_LANE0 {
-    int nefc = 0, nf = 0, nl = 0;
+    int nefc = 0, ne = 0, nf = 0, nl = 0;
     bool full = false;
-    if (do_fl) { nf = m.sz.nfl; nefc = nf; if (nefc > njmax) { nefc = nf = njmax; full = true; } }
+    // equality rows first (mj_instantiateEquality: joint / tendon couplings, one row each)
+    if (do_eq) {
+      for (int i = 0; i < m.sz.neq; i++) {
+        ieq[i] = -1;
+        if (!m.eq_active0[i]) continue;
+        if (nefc + 1 > njmax) { full = true; continue; }
+        ieq[i] = nefc++;
+        ne++;
+      }
+    }
+    if (do_fl) { nf = m.sz.nfl; if (nefc + nf > njmax) { nf = njmax - nefc; full = true; } nefc += nf; }
     for (int c = 0; c < nlim; c++) {
       if (!ilim[c]) { ilim[c] = -1; continue; }
       if (m.lim_kind[c] == LIM_TENDON) {
@@ -126,18 +138,64 @@ MJB_HD void make_constraint(const Env& d) {
       nefc += rows;
     }
     if (full) d.warning()[WARN_CNSTRFULL] += 1;
-    ne_f[0] = 0; nf_f[0] = nf; nl_f[0] = nl; nefc_f[0] = nefc;
+    ne_f[0] = ne; nf_f[0] = nf; nl_f[0] = nl; nefc_f[0] = nefc;
   }
   MJB_PSYNC();
-  const int nefc = nefc_f[0], nf = nf_f[0];
+  const int nefc = nefc_f[0], nf = nf_f[0], ne = ne_f[0];
   if (!nefc) return;
 
   FD J = d.efc_J(), epos = d.efc_pos(), emargin = d.efc_margin(), efl = d.efc_frictionloss();
   FI type = d.efc_type(), id = d.efc_id();
 
+  // ---- equality rows: scalar joint / tendon couplings  q1 - q1_0 = data0 + poly(q2 - q2_0)
+  if (ne) {
+    FD tJ = d.ten_J(), tlen = d.ten_length();
+    MJB_PFOR(i, m.sz.neq) {
+      const int r = ieq[i];
+      if (r < 0) continue;
+      const int o1 = m.eq_obj1id[i], o2 = m.eq_obj2id[i];
+      const bool jnt = m.eq_kind[i] == EQ_JOINT;
+      const double* data = m.eq_data + 5 * i;
+      FD row = J + (long)r * nv;
+      for (int k = 0; k < nv; k++) row[k] = 0;
+      auto value = [&](int o) { return jnt ? qpos[m.jnt_qposadr[o]] : tlen[o]; };
+      auto ref0 = [&](int o) { return jnt ? m.qpos0[m.jnt_qposadr[o]] : m.tendon_length0[o]; };
+      auto add_jac = [&](int o, double scl, bool first) {   // row (+)= jac(o) * scl   (mju_addToScl on the dense row)
+        if (jnt) {
+          const int dof = m.jnt_dofadr[o];
+          if (first) row[dof] = 1;
+          else for (int k = 0; k < nv; k++) row[k] += ((k == dof) ? 1.0 : 0.0) * scl;
+        } else {
+          const int adr = m.ten_J_rowadr[o], nnz = m.ten_J_rownnz[o];
+          if (first) { for (int a = 0; a < nnz; a++) row[m.ten_J_colind[adr + a]] = tJ[adr + a]; }
+          else {
+            for (int k = 0; k < nv; k++) {
+              double j2 = 0;
+              for (int a = 0; a < nnz; a++) if (m.ten_J_colind[adr + a] == k) j2 = tJ[adr + a];
+              row[k] += j2 * scl;
+            }
+          }
+        }
+      };
+      add_jac(o1, 1, true);
+      double cpos;
+      if (o2 >= 0) {
+        const double dif = value(o2) - ref0(o2);
+        cpos = value(o1) - ref0(o1) - data[0] -
+               (data[1] * dif + data[2] * dif * dif + data[3] * dif * dif * dif + data[4] * dif * dif * dif * dif);
+        const double deriv = data[1] + 2 * data[2] * dif + 3 * data[3] * dif * dif + 4 * data[4] * dif * dif * dif;
+        add_jac(o2, -deriv, false);
+      } else {
+        cpos = value(o1) - ref0(o1) - data[0];
+      }
+      epos[r] = cpos; emargin[r] = 0; efl[r] = 0; type[r] = CNSTR_EQUALITY; id[r] = i;
+    }
+  }
+
   // ---- friction-loss and limit rows (one lane per row)
-  MJB_PFOR(r, nf) {
-    const int i = m.fl_dof[r];
+  MJB_PFOR(r_, nf) {
+    const int r = ne + r_;
+    const int i = m.fl_dof[r_];
     FD row = J + (long)r * nv;
     for (int c = 0; c < nv; c++) row[c] = 0;
     row[i] = 1;
@@ -185,7 +243,7 @@ MJB_HD void make_constraint(const Env& d) {
     }
   }
   MJB_PSYNC();
-  const int first_con_row = nf + nl_f[0];
+  const int first_con_row = ne + nf + nl_f[0];
   MJB_PFOR(it, (nefc - first_con_row) * nv) {
     const int r = first_con_row + it / nv, c = it % nv;
     const int i = id[r];
@@ -212,7 +270,14 @@ MJB_HD void make_constraint(const Env& d) {
   FD dA = d.efc_diagA();
   MJB_PFOR(r, nefc) {
     const int t = type[r], k = id[r];
-    if (t == CNSTR_FRICTION_DOF) dA[r] = m.dof_invweight0[k];
+    if (t == CNSTR_EQUALITY) {
+      const bool jnt = m.eq_kind[k] == EQ_JOINT;
+      const int o1 = m.eq_obj1id[k], o2 = m.eq_obj2id[k];
+      double a = jnt ? m.dof_invweight0[m.jnt_dofadr[o1]] : m.tendon_invweight0[o1];
+      if (o2 >= 0) a += jnt ? m.dof_invweight0[m.jnt_dofadr[o2]] : m.tendon_invweight0[o2];
+      dA[r] = a;
+    }
+    else if (t == CNSTR_FRICTION_DOF) dA[r] = m.dof_invweight0[k];
     else if (t == CNSTR_LIMIT_JOINT) dA[r] = m.dof_invweight0[m.jnt_dofadr[k]];
     else if (t == CNSTR_LIMIT_TENDON) dA[r] = m.tendon_invweight0[k];
     else {
@@ -235,7 +300,8 @@ MJB_HD void make_constraint(const Env& d) {
   MJB_PFOR(r, nefc) {
     const int t = type[r], k = id[r];
     double solref[2], solimp[5];
-    if (t == CNSTR_FRICTION_DOF) { for (int j = 0; j < 2; j++) solref[j] = m.dof_solref[2 * k + j]; for (int j = 0; j < 5; j++) solimp[j] = m.dof_solimp[5 * k + j]; }
+    if (t == CNSTR_EQUALITY) { for (int j = 0; j < 2; j++) solref[j] = m.eq_solref[2 * k + j]; for (int j = 0; j < 5; j++) solimp[j] = m.eq_solimp[5 * k + j]; }
+    else if (t == CNSTR_FRICTION_DOF) { for (int j = 0; j < 2; j++) solref[j] = m.dof_solref[2 * k + j]; for (int j = 0; j < 5; j++) solimp[j] = m.dof_solimp[5 * k + j]; }
     else if (t == CNSTR_LIMIT_JOINT) { for (int j = 0; j < 2; j++) solref[j] = m.jnt_solref[2 * k + j]; for (int j = 0; j < 5; j++) solimp[j] = m.jnt_solimp[5 * k + j]; }
     else if (t == CNSTR_LIMIT_TENDON) { for (int j = 0; j < 2; j++) solref[j] = m.tendon_solref_lim[2 * k + j]; for (int j = 0; j < 5; j++) solimp[j] = m.tendon_solimp_lim[5 * k + j]; }
     else {
@@ -382,13 +448,14 @@ MJB_HD void reference_constraint(const Env& d) {
 
 // ---- primal constraint update (pyramidal / scalar rows): force, state; optional cost (serial sum)
 MJB_HD double constraint_update(const Env& d, FD jar, bool want_cost) {
-  const int nefc = d.nefc()[0], nf = d.nf()[0];
+  const int nefc = d.nefc()[0], ne = d.ne()[0], nf = ne + d.nf()[0];   // nf: end of the friction rows
   FD D = d.efc_D(), R = d.efc_R(), floss = d.efc_frictionloss(), force = d.efc_force();
   FI state = d.efc_state();
   MJB_PFOR(i, nefc) {
     double f = -D[i] * jar[i];
     int st;
-    if (i < nf) {
+    if (i < ne) st = STATE_QUADRATIC;
+    else if (i < nf) {
       if (jar[i] <= -R[i] * floss[i]) { f = floss[i]; st = STATE_LINEARNEG; }
       else if (jar[i] >= R[i] * floss[i]) { f = -floss[i]; st = STATE_LINEARPOS; }
       else st = STATE_QUADRATIC;
@@ -483,10 +550,11 @@ MJB_HD void constraint_begin(const Env& d) {
 }
 
 // dual state from forces on raw pointers (engine_solver.c dualState, scalar rows)
-MJB_HD void dual_state_ptr(const Env& d, const double* force, const double* floss, int nefc, int nf) {
+MJB_HD void dual_state_ptr(const Env& d, const double* force, const double* floss, int nefc, int ne, int nf) {
   FI state = d.efc_state();
   MJB_PFOR(i, nefc) {
-    if (i < nf) {
+    if (i < ne) state[i] = STATE_QUADRATIC;
+    else if (i < ne + nf) {
       if (force[i] <= -floss[i]) state[i] = STATE_LINEARPOS;
       else if (force[i] >= floss[i]) state[i] = STATE_LINEARNEG;
       else state[i] = STATE_QUADRATIC;
@@ -615,7 +683,7 @@ MJB_HD void make_islands(const Env& d) {
 //   MODE 0: everything in global memory (host emulation, lane-per-env mapping, oversized problems)
 // generic sweeps (any lane count, everything in global memory): host emulation, lane-per-env and
 // sub-warp mappings, oversized problems.  rows/nrow: the island's rows in island order (NULL = all rows).
-MJB_HD int pgs_sweeps(const Env& d, int nefc, int nf, const int* rows, int nrow, const double* gAR,
+MJB_HD int pgs_sweeps(const Env& d, int nefc, int ne, int nf, const int* rows, int nrow, const double* gAR,
                       double* force, const double* b, const double* floss, const double* ARinv, double* fprev,
                       double* fmom, const double* Adiag, double* shared, int* order) {
   const DModel& m = d.m;
@@ -638,7 +706,8 @@ MJB_HD int pgs_sweeps(const Env& d, int nefc, int nf, const int* rows, int nrow,
         const double fs = force[i];
         double f = fs + beta * (fs - fprev[i]);
         fprev[i] = fs;
-        if (i < nf) f = dclip(f, -floss[i], floss[i]);
+        if (i < ne) {}
+        else if (i < ne + nf) f = dclip(f, -floss[i], floss[i]);
         else if (f < 0) f = 0;
         force[i] = f;
         fmom[i] = f;
@@ -672,7 +741,8 @@ MJB_HD int pgs_sweeps(const Env& d, int nefc, int nf, const int* rows, int nrow,
         res = b[i] + res;
         const double old = force[i];
         double f = old - res * ARinv[i];
-        if (i < nf) {
+        if (i < ne) {}
+        else if (i < ne + nf) {
           if (f < -floss[i]) f = -floss[i];
           else if (f > floss[i]) f = floss[i];
         } else if (f < 0) f = 0;
@@ -853,7 +923,7 @@ __device__ int pgs_sweeps_warp(const Env& d, int nefc, int nf, const int* rows, 
 
 MJB_HD void solve_pgs(const Env& d) {
   const DModel& m = d.m;
-  const int nefc = d.nefc()[0], nf = d.nf()[0], njmax = m.sz.njmax;
+  const int nefc = d.nefc()[0], ne = d.ne()[0], nf = d.nf()[0], njmax = m.sz.njmax;
   if (!nefc) return;
   const double* gAR = d.efc_AR().p;
   // islands (mj_fwdConstraint, engine_forward.c:1187-1194): one independent PGS solve per island over the
@@ -884,8 +954,8 @@ MJB_HD void solve_pgs(const Env& d) {
     MJB_PFOR(i, nefc) {
       force[i] = gf[i]; b[i] = gb[i];
       const double fl = gfl[i];
-      lo[i] = (i < nf) ? -fl : 0.0;
-      hi[i] = (i < nf) ? fl : HUGE_VAL;
+      lo[i] = (i < ne) ? -HUGE_VAL : (i < ne + nf) ? -fl : 0.0;     // equality rows are unbounded
+      hi[i] = (i >= ne && i < ne + nf) ? fl : HUGE_VAL;
       const double ai = 1 / gAR[(long)i * (nefc + 1)];
       ARinv[i] = ai;
       Adiag[i] = 1 / ai;    // the reference's Athis[0] = 1/ARinv
@@ -904,7 +974,7 @@ MJB_HD void solve_pgs(const Env& d) {
     double* gfo = d.efc_force().p;
     MJB_PFOR(i, nefc) gfo[i] = force[i];
     MJB_PSYNC();
-    dual_state_ptr(d, gfo, gfl, nefc, nf);
+    dual_state_ptr(d, gfo, gfl, nefc, ne, nf);
   } else
 #endif
   {
@@ -922,12 +992,12 @@ MJB_HD void solve_pgs(const Env& d) {
     for (int k = 0; k < nsolve; k++) {
       const int* rows = isl ? imap + iadr[k] : nullptr;
       const int nrow = isl ? iadr[k + 1] - iadr[k] : nefc;
-      const int iter = pgs_sweeps(d, nefc, nf, rows, nrow, gAR, force, b, floss, ARinv, fprev, fmom, Adiag, shared, order);
+      const int iter = pgs_sweeps(d, nefc, ne, nf, rows, nrow, gAR, force, b, floss, ARinv, fprev, fmom, Adiag, shared, order);
       MJB_PSYNC();
       MJB_LANE0 if (k < NISLAND) niter[k] += iter;
     }
     MJB_PSYNC();
-    dual_state_ptr(d, force, floss, nefc, nf);
+    dual_state_ptr(d, force, floss, nefc, ne, nf);
   }
   MJB_PSYNC();
 }

@@ -357,7 +357,7 @@ MJB_HD void object_velocity(const Env& d, int kind, int id, V3& ang, V3& lin) {
 MJB_HD void sensors(const Env& d) {
   const DModel& m = d.m;
   if (!m.sz.nsensor || (m.opt.disableflags & DSBL_SENSOR)) return;
-  const int nefc = d.nefc()[0], nf = d.nf()[0];
+  const int nefc = d.nefc()[0], nf = d.ne()[0] + d.nf()[0];   // first row after the equality and friction rows
   FD out = d.sensordata();
   FI etype = d.efc_type(), eid = d.efc_id();
   MJB_PFOR(i, m.sz.nsensor) {

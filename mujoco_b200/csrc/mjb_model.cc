@@ -290,7 +290,16 @@ int check_model(const mjModel* m) {
 #define FAIL(...) do { snprintf(msg, sizeof(msg), __VA_ARGS__); set_error(std::string("unsupported: ") + msg); return -2; } while (0)
   if (m->nv <= 0 || m->nbody < 2) FAIL("model without degrees of freedom");
   if (m->nflex || m->nhfield || m->nmocap || m->nplugin) FAIL("flex / hfield / mocap / plugin present");
-  if (m->neq) FAIL("equality constraints (neq=%d) are a 'next' row of the scope table", (int)m->neq);
+  for (int i = 0; i < m->neq; i++) {
+    if (m->eq_type[i] != mjEQ_JOINT && m->eq_type[i] != mjEQ_TENDON)
+      FAIL("equality %d: only joint and tendon couplings are built (connect / weld need Jacobian time-derivatives)", i);
+    if (m->eq_type[i] == mjEQ_JOINT) {
+      for (int k = 0; k < 2; k++) {
+        const int j = k ? m->eq_obj2id[i] : m->eq_obj1id[i];
+        if (j >= 0 && m->jnt_type[j] != mjJNT_HINGE && m->jnt_type[j] != mjJNT_SLIDE) FAIL("equality %d couples a non-scalar joint", i);
+      }
+    }
+  }
   if (m->na) FAIL("stateful actuators (na=%d)", (int)m->na);
   if (m->opt.disableflags & mjDSBL_SENSOR) { /* sensordata simply stays untouched */ }
   for (int i = 0; i < m->nsensor; i++) {
@@ -386,7 +395,7 @@ int build_host_model(const mjModel* m, int nconmax, int njmax, HostModel* out) {
   S.nq = m->nq; S.nv = m->nv; S.nu = m->nu; S.na = m->na; S.nbody = m->nbody; S.njnt = m->njnt;
   S.ngeom = m->ngeom; S.ntendon = m->ntendon; S.nwrap = m->nwrap; S.nJten = m->nJten; S.nC = m->nC;
   S.ntree = m->ntree;
-  S.nsensor = m->nsensor; S.nsensordata = m->nsensordata; S.nsite = m->nsite;
+  S.nsensor = m->nsensor; S.nsensordata = m->nsensordata; S.nsite = m->nsite; S.neq = m->neq;
 
   Options& O = D.opt;
   O.timestep = m->opt.timestep; O.impratio = m->opt.impratio; O.tolerance = m->opt.tolerance;
@@ -443,6 +452,14 @@ int build_host_model(const mjModel* m, int nconmax, int njmax, HostModel* out) {
     B.addI(&D.sensor_refid, rid.data(), m->nsensor);
     B.addI(&D.sensor_dim, m->sensor_dim, m->nsensor);
     B.addI(&D.sensor_adr, m->sensor_adr, m->nsensor);
+    {
+      std::vector<int> kind(m->neq), act(m->neq);
+      for (int i = 0; i < m->neq; i++) { kind[i] = (m->eq_type[i] == mjEQ_JOINT) ? EQ_JOINT : EQ_TENDON; act[i] = m->eq_active0[i] ? 1 : 0; }
+      B.addI(&D.eq_kind, kind.data(), m->neq);
+      B.addI(&D.eq_obj1id, m->eq_obj1id, m->neq);
+      B.addI(&D.eq_obj2id, m->eq_obj2id, m->neq);
+      B.addI(&D.eq_active0, act.data(), m->neq);
+    }
     B.addI(&D.site_bodyid, m->site_bodyid, m->nsite);
     B.addI(&D.site_sameframe, m->site_sameframe, m->nsite);
   }
@@ -556,6 +573,14 @@ int build_host_model(const mjModel* m, int nconmax, int njmax, HostModel* out) {
   B.addD(&D.actuator_ctrlrange, m->actuator_ctrlrange, 2 * m->nu);
   B.addD(&D.actuator_forcerange, m->actuator_forcerange, 2 * m->nu);
   B.addD(&D.sensor_cutoff, m->sensor_cutoff, m->nsensor);
+  {
+    std::vector<double> ed(5 * (size_t)m->neq);
+    for (int i = 0; i < m->neq; i++) for (int k = 0; k < 5; k++) ed[5 * i + k] = m->eq_data[mjNEQDATA * i + k];
+    B.addD(&D.eq_data, ed.data(), ed.size());
+    B.addD(&D.eq_solref, m->eq_solref, 2 * (size_t)m->neq);
+    B.addD(&D.eq_solimp, m->eq_solimp, 5 * (size_t)m->neq);
+    B.addD(&D.tendon_length0, m->tendon_length0, m->ntendon);
+  }
   B.addD(&D.site_pos, m->site_pos, 3 * m->nsite);
   B.addD(&D.site_quat, m->site_quat, 4 * m->nsite);
 
@@ -760,7 +785,7 @@ int build_host_model(const mjModel* m, int nconmax, int njmax, HostModel* out) {
 
   // caps replacing the reference arena
   if (nconmax <= 0) nconmax = std::min(std::max(S.npair / 2, 16), 32);
-  if (njmax <= 0) njmax = S.nfl + 64;
+  if (njmax <= 0) njmax = S.nfl + S.neq + 64;
   S.nconmax = nconmax;
   S.njmax = njmax;
   if (O.solver == mjSOL_PGS && !O.dense) { set_error("unsupported: PGS with sparse Jacobian (nv >= 60)"); return -2; }

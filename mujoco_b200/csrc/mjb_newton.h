@@ -41,7 +41,8 @@ struct IslView {
 
 struct NewtonCtx {
   IslView v;
-  int nv, nefc, nf;               // nv: global dof count (row pitch of J); nefc/nf: global
+  int nv, nefc, ne, nf;           // nv: global dof count (row pitch of J); nefc: global; rows [0,ne) equality,
+                                  // [ne,nf) friction (nf = END of the friction rows)
   FD J, Jaref, Jv, quad, Dq, Ma, Mv, grad, Mgrad, search, cholupd, L;   // Ma..cholupd, L: island-local
   FD efcD, efcR, floss, qfs, qas, qacc;
   FI state, oldstate;
@@ -116,7 +117,8 @@ MJB_HD void newton_update_constraint(const Env& d, NewtonCtx& c) {
     const double jar = c.Jaref[i];
     double f = -c.efcD[i] * jar;
     int st;
-    if (i < c.nf) {
+    if (i < c.ne) st = STATE_QUADRATIC;
+    else if (i < c.nf) {
       if (jar <= -c.efcR[i] * c.floss[i]) { f = c.floss[i]; st = STATE_LINEARNEG; }
       else if (jar >= c.efcR[i] * c.floss[i]) { f = -c.floss[i]; st = STATE_LINEARPOS; }
       else st = STATE_QUADRATIC;
@@ -292,6 +294,11 @@ MJB_HD void newton_eval(NewtonCtx& c, LsPoint& p) {
   double q0 = 0, q1 = c.quadGauss[1], q2 = c.quadGauss[2];
   for (int cc = 0; cc < c.v.nrow; cc++) {
     const int i = c.v.row(cc);
+    if (i < c.ne) {   // equality: shifted quadratic (quad[0] dropped)
+      q1 += c.quad[3 * i + 1];
+      q2 += c.quad[3 * i + 2];
+      continue;
+    }
     if (i < c.nf) {
       const double start = c.Jaref[i], dir = c.Jv[i];
       const double x = start + alpha * dir;
@@ -430,7 +437,7 @@ MJB_HD int solve_primal_view(const Env& d, bool newton, const IslView& view, boo
   c.v = view;
   const IslView& v = c.v;
   const int n = v.ndof;
-  c.nv = nv; c.nefc = d.nefc()[0]; c.nf = d.nf()[0];
+  c.nv = nv; c.nefc = d.nefc()[0]; c.ne = d.ne()[0]; c.nf = c.ne + d.nf()[0];
   c.J = d.efc_J();
   FD se = d.nwt_efc(), sv = d.nwt_nv();
   c.Jaref = se; c.Jv = se + njmax; c.quad = se + 2 * (long)njmax; c.Dq = se + 5 * (long)njmax;

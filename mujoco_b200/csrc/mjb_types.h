@@ -31,6 +31,7 @@ enum { STATE_SATISFIED = 0, STATE_QUADRATIC = 1, STATE_LINEARNEG = 2, STATE_LINE
 enum { WARN_INERTIA = 0, WARN_CONTACTFULL = 1, WARN_CNSTRFULL = 2, WARN_BADQPOS = 3,
        WARN_BADQVEL = 4, WARN_BADQACC = 5, WARN_BADCTRL = 6, WARN_VGEOMFULL = 7, NWARNING = 8 };
 enum { NISLAND = 20 };
+enum { EQ_JOINT = 0, EQ_TENDON = 1 };   // supported equality kinds (mjEQ_JOINT / mjEQ_TENDON): scalar couplings
 // sensors of the path (engine_sensor.c); internal codes, translated from mjtSensor by the host
 enum { SENS_JOINTPOS, SENS_TENDONPOS, SENS_ACTUATORPOS, SENS_BALLQUAT, SENS_JOINTLIMITPOS, SENS_TENDONLIMITPOS,
        SENS_FRAMEPOS, SENS_FRAMEXAXIS, SENS_FRAMEYAXIS, SENS_FRAMEZAXIS, SENS_FRAMEQUAT, SENS_SUBTREECOM, SENS_CLOCK,
@@ -56,7 +57,7 @@ constexpr int kNGain = 3;   // leading gain/bias parameters used by the supporte
 // ---- model sizes and options --------------------------------------------------------------------
 struct Sizes {
   int nq, nv, nu, na, nbody, njnt, ngeom, ntendon, nwrap, nJten, nC, ntree;
-  int nsensor, nsensordata, nsite;
+  int nsensor, nsensordata, nsite, neq;
   int npair;     // static candidate geom pairs (host-built, reference order)
   int nconmax;   // per-env contact cap
   int njmax;     // per-env constraint-row cap
@@ -97,7 +98,8 @@ struct Options {
   X(fac_adr) X(fac_dst) X(fac_src) X(fac_cf)                                                  \
   X(lim_kind) X(lim_id) X(lim_side) X(fl_dof) X(body_dofanc)                                 \
   X(sensor_type) X(sensor_cutmode) X(sensor_objtype) X(sensor_objid) X(sensor_reftype) X(sensor_refid)   \
-  X(sensor_dim) X(sensor_adr) X(site_bodyid) X(site_sameframe)
+  X(sensor_dim) X(sensor_adr) X(site_bodyid) X(site_sameframe)                               \
+  X(eq_kind) X(eq_obj1id) X(eq_obj2id) X(eq_active0)
 
 #define MJB_MODEL_DBL_FIELDS(X)                                                             \
   X(qpos0) X(qpos_spring) X(body_pos) X(body_quat) X(body_ipos) X(body_iquat) X(body_mass)   \
@@ -112,7 +114,8 @@ struct Options {
   X(tendon_dampingpoly_eff) X(tendon_lengthspring) X(tendon_armature_eff)                    \
   X(actuator_gear0) X(actuator_gainprm) X(actuator_biasprm) X(actuator_ctrlrange)            \
   X(actuator_forcerange)                                                                     \
-  X(pair_margin) X(pair_includemargin) X(pair_solref) X(pair_solimp) X(pair_friction) X(sensor_cutoff) X(site_pos) X(site_quat)
+  X(pair_margin) X(pair_includemargin) X(pair_solref) X(pair_solimp) X(pair_friction) X(sensor_cutoff) X(site_pos) X(site_quat)            \
+  X(eq_data) X(eq_solref) X(eq_solimp) X(tendon_length0)
 
 struct DModel {
   Sizes sz;
@@ -165,7 +168,7 @@ struct DModel {
   X(con_geom1, S.nconmax) X(con_geom2, S.nconmax) X(con_dim, S.nconmax)                       \
   X(con_exclude, S.nconmax) X(con_efcadr, S.nconmax) X(con_pair, S.nconmax)                    \
   X(efc_type, S.njmax) X(efc_id, S.njmax) X(efc_state, S.njmax) X(nwt_state, S.njmax) X(scr_int, 4 * S.njmax)        \
-  X(scr_ipair, S.npair + 4) X(scr_ilim, 2 * S.nlim + 4)
+  X(scr_ipair, S.npair + 4) X(scr_ilim, 2 * S.nlim + 4) X(scr_ieq, S.neq + 1)
 
 struct Layout {
 #define X(name, cnt) long name;

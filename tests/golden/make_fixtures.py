@@ -25,6 +25,7 @@ MODELS = {
     "ant_balls": os.path.join(ROOT, "models", "ant_balls.xml"),
     "ant_sensors": os.path.join(ROOT, "models", "ant_sensors.xml"),
     "ant_servo": os.path.join(ROOT, "models", "ant_servo.xml"),
+    "ant_equality": os.path.join(ROOT, "models", "ant_equality.xml"),
 }
 
 

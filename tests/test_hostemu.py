@@ -300,3 +300,28 @@ def test_implicitfast_refuses_standalone_free_bodies():
     m.set_option("integrator", mb.INT_IMPLICITFAST)
     with pytest.raises(mb.MjbError, match="standalone free body"):
         mb.Batch(m, 1)
+
+
+@pytest.mark.parametrize("solver", [mb.SOLVER_PGS, mb.SOLVER_NEWTON, mb.SOLVER_CG])
+def test_equality_couplings_bit_exact(solver):
+    """joint / tendon equality constraints (mj_instantiateEquality, scalar couplings with the quartic
+    polynomial): equality, frictionloss, limit and contact rows in one problem (models/ant_equality.xml:
+    5 equalities, one of them inactive)"""
+    path = os.path.join(ROOT, "models", "ant_equality.mjb")
+    nenv, nstep = 6, 150
+    m, b, o = make_pair(path, solver, library=hostemu_lib(), nenv=nenv)
+    states = perturbed_states(o, nenv, seed=4, height=[0.3, 0.45, 0.6], qpos_std=0.1)
+    ctrl1 = np.random.default_rng(6).uniform(-1, 1, (nenv, o.size("nu")))
+    compare_forward(b, o, states, ctrl1, rtol=0, exact=True, check_dual=(solver == mb.SOLVER_PGS))
+    assert (b.field("ne")[:, 0] == 4).all()
+    s0 = perturbed_states(o, nenv, seed=14, height=[0.35, 0.5, 0.75], qvel_std=0.3, qpos_std=0.05)
+    ctrl = np.random.default_rng(15).uniform(-1, 1, (nenv, nstep, o.size("nu")))
+    out = b.rollout(s0, ctrl)
+    ref, stats, _ = o.rollout(s0, ctrl, nthread=4)
+    assert stats[:, 3].sum() == 0
+    assert np.array_equal(out, ref)
+    # mjDSBL_EQUALITY drops the rows
+    m, b, o = make_pair(path, solver, library=hostemu_lib(), nenv=nenv, disableflags=1 << 1)
+    out = b.rollout(s0, ctrl[:, :40])
+    ref, _, _ = o.rollout(s0, ctrl[:, :40], nthread=4)
+    assert np.array_equal(out, ref) and (b.field("ne")[:, 0] == 0).all()
