@@ -354,12 +354,103 @@ MJB_HD void object_velocity(const Env& d, int kind, int id, V3& ang, V3& lin) {
   lin = vl - cross(dif, ang);
 }
 
+// mj_rnePostConstraint (engine_core_smooth.c:2394-2600): external contact forces per body (cfrc_ext), body
+// accelerations (cacc) and interaction forces with the parent (cfrc_int), all in the com-based frame.
+// Only run when a sensor needs it.  xfrc_applied and connect / weld rows are not part of the supported set.
+MJB_HD S6 transform_force(S6 v, V3 newpos, V3 oldpos) {   // mju_transformSpatial, flg_force = 1, no rotation
+  const V3 dif = newpos - oldpos;
+  const V3 tq{v.v[0], v.v[1], v.v[2]}, f{v.v[3], v.v[4], v.v[5]};
+  const V3 t = tq - cross(dif, f);
+  return S6{{t.x, t.y, t.z, f.x, f.y, f.z}};
+}
+MJB_HD void rne_post(const Env& d) {
+  const DModel& m = d.m;
+  const int nbody = m.sz.nbody, ncon = d.ncon()[0];
+  FD cacc = d.cacc(), cint = d.cfrc_int(), cext = d.cfrc_ext();
+  FD cinert = d.cinert(), cvel = d.cvel(), cdof = d.cdof(), cdd = d.cdof_dot(), qvel = d.qvel(), qacc = d.qacc();
+  FD force = d.efc_force(), cfri = d.con_friction(), cframe = d.con_frame(), cpos = d.con_pos(), sc = d.subtree_com();
+  FI cadr = d.con_efcadr(), cdim = d.con_dim(), cg1 = d.con_geom1(), cg2 = d.con_geom2();
+  // cfrc_ext: one lane per body, contacts in order, body 1 (subtract) before body 2 (add)
+  MJB_PFOR(k, nbody) {
+    S6 acc{{0, 0, 0, 0, 0, 0}};
+    if (k) {
+      for (int i = 0; i < ncon; i++) {
+        const int a = cadr[i];
+        if (a < 0) continue;
+        const int b1 = m.geom_bodyid[cg1[i]], b2 = m.geom_bodyid[cg2[i]];
+        if (b1 != k && b2 != k) continue;
+        const int dim = cdim[i];
+        double lf[6] = {0, 0, 0, 0, 0, 0};   // mj_contactForce: contact-frame force:torque (mju_decodePyramid)
+        if (dim == 1) lf[0] = force[a];
+        else {
+          double n = 0;
+          for (int q = 0; q < 2 * (dim - 1); q++) n += force[a + q];
+          lf[0] = n;
+          for (int q = 0; q < dim - 1; q++) lf[q + 1] = (force[a + 2 * q] - force[a + 2 * q + 1]) * cfri[5 * i + q];
+        }
+        lf[0] -= 0.0;   // adhesion (unsupported, zero)
+        const M3 fr = ld9(cframe, 9 * i);
+        const V3 tq = mulmTv(fr, V3{lf[3], lf[4], lf[5]}), ff = mulmTv(fr, V3{lf[0], lf[1], lf[2]});
+        const S6 cc = transform_force(S6{{tq.x, tq.y, tq.z, ff.x, ff.y, ff.z}}, ld3(sc, 3 * m.body_rootid[k]), ld3(cpos, 3 * i));
+        if (b1 == k) for (int q = 0; q < 6; q++) acc.v[q] -= cc.v[q];
+        if (b2 == k) for (int q = 0; q < 6; q++) acc.v[q] += cc.v[q];
+      }
+    }
+    st6(cext, 6 * k, acc);
+  }
+  MJB_LANE0 {
+    for (int k = 0; k < 6; k++) { cacc[k] = 0; cint[k] = 0; }
+    if (!(m.opt.disableflags & DSBL_GRAVITY)) {
+      cacc[3] = m.opt.gravity[0] * -1; cacc[4] = m.opt.gravity[1] * -1; cacc[5] = m.opt.gravity[2] * -1;
+    }
+  }
+  MJB_PSYNC();
+  for (int l = 1; l < m.sz.nlevel; l++) {
+    const int ladr = m.lvl_adr[l], cnt = m.lvl_adr[l + 1] - ladr;
+    MJB_PFOR(k_, cnt) {
+      const int j = m.lvl_body[ladr + k_];
+      const int bda = m.body_dofadr[j], dn = m.body_dofnum[j];
+      S6 t = mul_dof_vec(cdd + 6 * bda, qvel + bda, dn);
+      S6 a = ld6(cacc, 6 * m.body_parentid[j]);
+      for (int k = 0; k < 6; k++) a.v[k] = a.v[k] + t.v[k];
+      t = mul_dof_vec(cdof + 6 * bda, qacc + bda, dn);
+      for (int k = 0; k < 6; k++) a.v[k] += t.v[k];
+      st6(cacc, 6 * j, a);
+      const I10 I = ld10(cinert, 10 * j);
+      S6 f = mul_inert(I, a);
+      const S6 v = ld6(cvel, 6 * j);
+      const S6 c = cross_force(v, mul_inert(I, v));
+      for (int k = 0; k < 6; k++) f.v[k] += c.v[k];
+      const S6 e = ld6(cext, 6 * j);
+      for (int k = 0; k < 6; k++) f.v[k] = f.v[k] - e.v[k];
+      st6(cint, 6 * j, f);
+    }
+    MJB_PSYNC();
+  }
+  tree_accumulate(d, cint, 6, false);
+}
+// 6D acceleration of an object frame (mj_objectAcceleration): global frame, or the object's own frame
+MJB_HD void object_acceleration(const Env& d, int kind, int id, bool local, V3& ang, V3& lin) {
+  const DModel& m = d.m;
+  const int body = (kind == SOBJ_GEOM) ? m.geom_bodyid[id] : (kind == SOBJ_SITE) ? m.site_bodyid[id] : id;
+  if (m.body_dofnum[m.body_weldid[body]] == 0) { ang = V3{0, 0, 0}; lin = V3{0, 0, 0}; return; }
+  V3 pos; M3 mat;
+  sensor_frame(d, kind, id, pos, mat);
+  const V3 dif = pos - ld3(d.subtree_com(), 3 * m.body_rootid[body]);
+  V3 aa = ld3(d.cacc(), 6 * body), al = ld3(d.cacc(), 6 * body + 3) - cross(dif, aa);
+  V3 va = ld3(d.cvel(), 6 * body), vl = ld3(d.cvel(), 6 * body + 3) - cross(dif, va);
+  if (local) { aa = mulmTv(mat, aa); al = mulmTv(mat, al); va = mulmTv(mat, va); vl = mulmTv(mat, vl); }
+  ang = aa;
+  lin = al + cross(va, vl);
+}
+
 MJB_HD void sensors(const Env& d) {
   const DModel& m = d.m;
   if (!m.sz.nsensor || (m.opt.disableflags & DSBL_SENSOR)) return;
   const int nefc = d.nefc()[0], nf = d.ne()[0] + d.nf()[0];   // first row after the equality and friction rows
   FD out = d.sensordata();
   FI etype = d.efc_type(), eid = d.efc_id();
+  if (m.sz.rnepost) rne_post(d);
   MJB_PFOR(i, m.sz.nsensor) {
     const int type = m.sensor_type[i], id = m.sensor_objid[i], adr = m.sensor_adr[i], dim = m.sensor_dim[i];
     const int okind = m.sensor_objtype[i], rkind = m.sensor_reftype[i], refid = m.sensor_refid[i];
@@ -428,6 +519,28 @@ MJB_HD void sensors(const Env& d) {
         object_velocity(d, SOBJ_SITE, id, ang, lin);
         sensor_frame(d, SOBJ_SITE, id, pos, mat);
         const V3 r = mulmTv(mat, (type == SENS_GYRO) ? ang : lin);
+        v[0] = r.x; v[1] = r.y; v[2] = r.z;
+        break;
+      }
+      case SENS_ACCELEROMETER: {
+        V3 ang, lin;
+        object_acceleration(d, SOBJ_SITE, id, true, ang, lin);
+        v[0] = lin.x; v[1] = lin.y; v[2] = lin.z;
+        break;
+      }
+      case SENS_FORCE: case SENS_TORQUE: {   // interaction force with the parent at the site, in the site frame
+        V3 pos; M3 mat;
+        sensor_frame(d, SOBJ_SITE, id, pos, mat);
+        const int body = m.site_bodyid[id];
+        const S6 t = transform_force(ld6(d.cfrc_int(), 6 * body), pos, ld3(d.subtree_com(), 3 * m.body_rootid[body]));
+        const V3 r = (type == SENS_FORCE) ? mulmTv(mat, V3{t.v[3], t.v[4], t.v[5]}) : mulmTv(mat, V3{t.v[0], t.v[1], t.v[2]});
+        v[0] = r.x; v[1] = r.y; v[2] = r.z;
+        break;
+      }
+      case SENS_FRAMELINACC: case SENS_FRAMEANGACC: {
+        V3 ang, lin;
+        object_acceleration(d, okind, id, false, ang, lin);
+        const V3 r = (type == SENS_FRAMELINACC) ? lin : ang;
         v[0] = r.x; v[1] = r.y; v[2] = r.z;
         break;
       }

@@ -275,6 +275,11 @@ static bool sensor_code(const mjModel* m, int i, int* code, int* okind, int* rki
     case mjSENS_TENDONLIMITFRC: *code = SENS_TENDONLIMITFRC; break;
     case mjSENS_VELOCIMETER: *code = SENS_VELOCIMETER; *okind = SOBJ_SITE; return m->sensor_objtype[i] == mjOBJ_SITE;
     case mjSENS_GYRO: *code = SENS_GYRO; *okind = SOBJ_SITE; return m->sensor_objtype[i] == mjOBJ_SITE;
+    case mjSENS_ACCELEROMETER: *code = SENS_ACCELEROMETER; *okind = SOBJ_SITE; return m->sensor_objtype[i] == mjOBJ_SITE;
+    case mjSENS_FORCE: *code = SENS_FORCE; *okind = SOBJ_SITE; return m->sensor_objtype[i] == mjOBJ_SITE;
+    case mjSENS_TORQUE: *code = SENS_TORQUE; *okind = SOBJ_SITE; return m->sensor_objtype[i] == mjOBJ_SITE;
+    case mjSENS_FRAMELINACC: *code = SENS_FRAMELINACC; frame = true; break;
+    case mjSENS_FRAMEANGACC: *code = SENS_FRAMEANGACC; frame = true; break;
     default: return false;
   }
   if (frame) {
@@ -396,6 +401,11 @@ int build_host_model(const mjModel* m, int nconmax, int njmax, HostModel* out) {
   S.ngeom = m->ngeom; S.ntendon = m->ntendon; S.nwrap = m->nwrap; S.nJten = m->nJten; S.nC = m->nC;
   S.ntree = m->ntree;
   S.nsensor = m->nsensor; S.nsensordata = m->nsensordata; S.nsite = m->nsite; S.neq = m->neq;
+  S.rnepost = 0;
+  for (int i = 0; i < m->nsensor; i++) {
+    const int t = m->sensor_type[i];
+    if (t == mjSENS_ACCELEROMETER || t == mjSENS_FORCE || t == mjSENS_TORQUE || t == mjSENS_FRAMELINACC || t == mjSENS_FRAMEANGACC) S.rnepost = 1;
+  }
 
   Options& O = D.opt;
   O.timestep = m->opt.timestep; O.impratio = m->opt.impratio; O.tolerance = m->opt.tolerance;

@@ -37,7 +37,8 @@ enum { SENS_JOINTPOS, SENS_TENDONPOS, SENS_ACTUATORPOS, SENS_BALLQUAT, SENS_JOIN
        SENS_FRAMEPOS, SENS_FRAMEXAXIS, SENS_FRAMEYAXIS, SENS_FRAMEZAXIS, SENS_FRAMEQUAT, SENS_SUBTREECOM, SENS_CLOCK,
        SENS_JOINTVEL, SENS_TENDONVEL, SENS_ACTUATORVEL, SENS_BALLANGVEL, SENS_JOINTLIMITVEL, SENS_TENDONLIMITVEL,
        SENS_FRAMELINVEL, SENS_FRAMEANGVEL, SENS_ACTUATORFRC, SENS_JOINTACTFRC, SENS_JOINTLIMITFRC,
-       SENS_TENDONLIMITFRC, SENS_VELOCIMETER, SENS_GYRO };
+       SENS_TENDONLIMITFRC, SENS_VELOCIMETER, SENS_GYRO, SENS_ACCELEROMETER, SENS_FORCE, SENS_TORQUE,
+       SENS_FRAMELINACC, SENS_FRAMEANGACC };
 enum { SOBJ_XBODY = 0, SOBJ_BODY = 1, SOBJ_GEOM = 2, SOBJ_SITE = 3 };   // frame sensor object kinds (mjOBJ_*)   // mjNISLAND: islands with solver statistics (mjdata.h)  // :553-561
 enum { SOL_PGS = 0, SOL_CG = 1, SOL_NEWTON = 2 };                                        // :202-204
 enum { INT_EULER = 0, INT_RK4 = 1, INT_IMPLICIT = 2, INT_IMPLICITFAST = 3 };             // :181-184
@@ -58,6 +59,7 @@ constexpr int kNGain = 3;   // leading gain/bias parameters used by the supporte
 struct Sizes {
   int nq, nv, nu, na, nbody, njnt, ngeom, ntendon, nwrap, nJten, nC, ntree;
   int nsensor, nsensordata, nsite, neq;
+  int rnepost;   // 1 when a sensor needs mj_rnePostConstraint (cacc / cfrc_int / cfrc_ext are allocated then)
   int npair;     // static candidate geom pairs (host-built, reference order)
   int nconmax;   // per-env contact cap
   int njmax;     // per-env constraint-row cap
@@ -153,7 +155,8 @@ struct DModel {
   X(efc_b, S.njmax) X(efc_force, S.njmax)                                                    \
   X(scr_body, 12 * S.nbody) X(scr_nv, 8 * S.nv) X(scr_efc, 6 * S.njmax)                         \
   X(nwt_nv, 6 * S.nv) X(nwt_efc, 6 * S.njmax) X(rk_scr, S.nq + 8 * S.nv + 4) X(sensordata, S.nsensordata)  \
-  X(site_xpos, 3 * S.nsite) X(site_xmat, 9 * S.nsite)
+  X(site_xpos, 3 * S.nsite) X(site_xmat, 9 * S.nsite)                                        \
+  X(cacc, 6 * S.nbody * S.rnepost) X(cfrc_int, 6 * S.nbody * S.rnepost) X(cfrc_ext, 6 * S.nbody * S.rnepost)
 
 // COLD doubles: stay in global memory / L2 in every mapping
 #define MJB_DATA_COLD_FIELDS(X, S)                                                           \

@@ -165,7 +165,7 @@ def test_constraint_islands_vs_oracle(solver):
 
 
 def test_sensors_and_mjdata_bridge_vs_oracle():
-    """sensordata through rollout() (42 sensors of every supported type, models/ant_sensors.xml) and the
+    """sensordata through rollout() (52 sensors of every supported type, models/ant_sensors.xml) and the
     mjData bridge (mjb_step_mjdata on the reference's own mjData objects), both against mj_step"""
     assert available()
     path = os.path.join(ROOT, "models", "ant_sensors.mjb")
