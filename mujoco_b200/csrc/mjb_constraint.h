@@ -56,6 +56,33 @@ MJB_HD double jac_elem(const Env& d, V3 pt, int body, int k, int c) {
   return cdof[6 * c + 3 + k] + get(t, k);
 }
 
+// global anchor points of a body-semantic connect (mj_equalityAnchors, engine_core_constraint.c:561-590)
+MJB_HD void connect_anchors(const Env& d, int eq, V3& p0, V3& p1) {
+  const DModel& m = d.m;
+  const int o1 = m.eq_obj1id[eq], o2 = m.eq_obj2id[eq];
+  const double* data = m.eq_data + kNEqData * eq;
+  p0 = mulmv(ld9(d.xmat(), 9 * o1), V3{data[0], data[1], data[2]}) + ld3(d.xpos(), 3 * o1);
+  p1 = mulmv(ld9(d.xmat(), 9 * o2), V3{data[3], data[4], data[5]}) + ld3(d.xpos(), 3 * o2);
+}
+
+// one element of the time derivative of the translational point Jacobian (mj_jacDot, engine_core_util.c
+// :605-675): component k, dof c; zero off the body's dof chain
+MJB_HD double jacdot_elem(const Env& d, V3 pt, int body, int k, int c) {
+  const DModel& m = d.m;
+  if (!m.body_dofanc[(long)body * m.sz.nv + c]) return 0;
+  FD cdof = d.cdof(), cvel = d.cvel();
+  const V3 com = ld3(d.subtree_com(), 3 * m.body_rootid[body]);
+  const V3 off = pt - com;
+  const V3 pang = ld3(cvel, 6 * body);
+  const V3 plin = ld3(cvel, 6 * body + 3) - cross(off, pang);     // point velocity (mju_transformSpatial)
+  S6 cd = ld6(d.cdof_dot(), 6 * c);
+  const int j = m.dof_jntid[c], jt = m.jnt_type[j];
+  if (jt == JNT_BALL || (jt == JNT_FREE && c >= m.jnt_dofadr[j] + 3)) cd = cross_motion(ld6(cvel, 6 * m.dof_bodyid[c]), ld6(cdof, 6 * c));
+  const V3 t1 = cross(V3{cd.v[0], cd.v[1], cd.v[2]}, off);
+  const V3 t2 = cross(ld3(cdof, 6 * c), plin);
+  return cd.v[3 + k] + get(t1, k) + get(t2, k);
+}
+
 MJB_HD void make_constraint(const Env& d) {
   const DModel& m = d.m;
   const int nv = m.sz.nv, njmax = m.sz.njmax;
@@ -110,9 +137,10 @@ MJB_HD void make_constraint(const Env& d) {
       for (int i = 0; i < m.sz.neq; i++) {
         ieq[i] = -1;
         if (!m.eq_active0[i]) continue;
-        if (nefc + 1 > njmax) { full = true; continue; }
-        ieq[i] = nefc++;
-        ne++;
+        const int rows = (m.eq_kind[i] == EQ_CONNECT) ? 3 : 1;
+        if (nefc + rows > njmax) { full = true; continue; }
+        ieq[i] = nefc;
+        nefc += rows; ne += rows;
       }
     }
     if (do_fl) { nf = m.sz.nfl; if (nefc + nf > njmax) { nf = njmax - nefc; full = true; } nefc += nf; }
@@ -154,8 +182,19 @@ MJB_HD void make_constraint(const Env& d) {
       const int r = ieq[i];
       if (r < 0) continue;
       const int o1 = m.eq_obj1id[i], o2 = m.eq_obj2id[i];
+      if (m.eq_kind[i] == EQ_CONNECT) {   // ball-joint connect of two body anchors: 3 rows, J = jac(0) - jac(1)
+        V3 p0, p1;
+        connect_anchors(d, i, p0, p1);
+        const V3 cp = p0 - p1;
+        for (int k = 0; k < 3; k++) {
+          FD row = J + (long)(r + k) * nv;
+          for (int c = 0; c < nv; c++) row[c] = jac_elem(d, p0, o1, k, c) - jac_elem(d, p1, o2, k, c);
+          epos[r + k] = get(cp, k); emargin[r + k] = 0; efl[r + k] = 0; type[r + k] = CNSTR_EQUALITY; id[r + k] = i;
+        }
+        continue;
+      }
       const bool jnt = m.eq_kind[i] == EQ_JOINT;
-      const double* data = m.eq_data + 5 * i;
+      const double* data = m.eq_data + kNEqData * i;
       FD row = J + (long)r * nv;
       for (int k = 0; k < nv; k++) row[k] = 0;
       auto value = [&](int o) { return jnt ? qpos[m.jnt_qposadr[o]] : tlen[o]; };
@@ -270,7 +309,10 @@ MJB_HD void make_constraint(const Env& d) {
   FD dA = d.efc_diagA();
   MJB_PFOR(r, nefc) {
     const int t = type[r], k = id[r];
-    if (t == CNSTR_EQUALITY) {
+    if (t == CNSTR_EQUALITY && m.eq_kind[k] == EQ_CONNECT) {
+      dA[r] = m.body_invweight0[2 * m.eq_obj1id[k]] + m.body_invweight0[2 * m.eq_obj2id[k]];
+    }
+    else if (t == CNSTR_EQUALITY) {
       const bool jnt = m.eq_kind[k] == EQ_JOINT;
       const int o1 = m.eq_obj1id[k], o2 = m.eq_obj2id[k];
       double a = jnt ? m.dof_invweight0[m.jnt_dofadr[o1]] : m.tendon_invweight0[o1];
@@ -316,7 +358,13 @@ MJB_HD void make_constraint(const Env& d) {
     solimp[3] = dmin(kMaxImp, dmax(kMinImp, solimp[3]));
     solimp[4] = dmax(1, solimp[4]);
     double imp, impP;
-    impedance(solimp, epos[r], emargin[r], imp, impP);
+    double ipos = epos[r], imargin = emargin[r];
+    if (t == CNSTR_EQUALITY && m.eq_kind[k] == EQ_CONNECT) {   // getposdim: the 3 rows share |pos| (mju_norm)
+      const int base = ieq[k];
+      ipos = sqrt(dot_ref(3, [&](int q) { return epos[base + q]; }, [&](int q) { return epos[base + q]; }));
+      imargin = emargin[base];
+    }
+    impedance(solimp, ipos, imargin, imp, impP);
     R[r] = dmax(kMinVal, (1 - imp) * dA[r] / imp);
     double K, Bv;
     if (t == CNSTR_FRICTION_DOF) K = 0;
@@ -444,6 +492,25 @@ MJB_HD void reference_constraint(const Env& d) {
   MJB_PFOR(i, nefc)
     aref[i] = -KBIP[4 * i + 1] * vel[i] - KBIP[4 * i] * KBIP[4 * i + 2] * (pos[i] - margin[i]);
   MJB_PSYNC();
+  // mj_Jdotv (engine_core_constraint.c:1056-1200): connect rows get aref -= (Jdot1 - Jdot2) * qvel
+  const DModel& m = d.m;
+  if (d.ne()[0] && m.sz.neq) {
+    FI ieq = d.scr_ieq();
+    FD qvel = d.qvel();
+    const int nv = m.sz.nv;
+    MJB_PFOR(it, m.sz.neq * 3) {
+      const int eq = it / 3, k = it - eq * 3;
+      const int r = ieq[eq];
+      if (r < 0 || m.eq_kind[eq] != EQ_CONNECT) continue;
+      V3 p0, p1;
+      connect_anchors(d, eq, p0, p1);
+      const int o1 = m.eq_obj1id[eq], o2 = m.eq_obj2id[eq];
+      const double j1 = dot_ref(nv, [&](int c) { return jacdot_elem(d, p0, o1, k, c); }, [&](int c) { return qvel[c]; });
+      const double j2 = dot_ref(nv, [&](int c) { return jacdot_elem(d, p1, o2, k, c); }, [&](int c) { return qvel[c]; });
+      aref[r + k] -= j1 - j2;
+    }
+    MJB_PSYNC();
+  }
 }
 
 // ---- primal constraint update (pyramidal / scalar rows): force, state; optional cost (serial sum)
@@ -608,7 +675,11 @@ MJB_HD void make_islands(const Env& d) {
       ptype = type[i]; pid = id[i];
       int t1 = -2, t2 = -2;
       bool scan = false;
-      if (ptype == CNSTR_FRICTION_DOF) t1 = m.dof_treeid[pid];
+      if (ptype == CNSTR_EQUALITY && m.eq_kind[pid] == EQ_CONNECT) {
+        t1 = m.body_treeid[m.eq_obj1id[pid]];
+        t2 = m.body_treeid[m.eq_obj2id[pid]];
+      }
+      else if (ptype == CNSTR_FRICTION_DOF) t1 = m.dof_treeid[pid];
       else if (ptype == CNSTR_LIMIT_JOINT) t1 = m.dof_treeid[m.jnt_dofadr[pid]];
       else if (ptype == CNSTR_CONTACT_PYRAMIDAL || ptype == CNSTR_CONTACT_FRICTIONLESS) {
         t1 = m.body_treeid[m.geom_bodyid[cg1[pid]]];

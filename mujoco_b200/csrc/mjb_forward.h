@@ -396,6 +396,20 @@ MJB_HD void rne_post(const Env& d) {
         if (b2 == k) for (int q = 0; q < 6; q++) acc.v[q] += cc.v[q];
       }
     }
+    if (k && d.ne()[0]) {   // connect rows: force on body 1 (+) and body 2 (-), applied at the anchors
+      FI ieq = d.scr_ieq();
+      for (int eq = 0; eq < m.sz.neq; eq++) {
+        const int r = ieq[eq];
+        if (r < 0 || m.eq_kind[eq] != EQ_CONNECT) continue;
+        const int o1 = m.eq_obj1id[eq], o2 = m.eq_obj2id[eq];
+        if (o1 != k && o2 != k) continue;
+        V3 p0, p1;
+        connect_anchors(d, eq, p0, p1);
+        const S6 cf{{0, 0, 0, force[r], force[r + 1], force[r + 2]}};
+        if (o1 == k) { const S6 cc = transform_force(cf, ld3(sc, 3 * m.body_rootid[k]), p0); for (int q = 0; q < 6; q++) acc.v[q] += cc.v[q]; }
+        if (o2 == k) { const S6 cc = transform_force(cf, ld3(sc, 3 * m.body_rootid[k]), p1); for (int q = 0; q < 6; q++) acc.v[q] -= cc.v[q]; }
+      }
+    }
     st6(cext, 6 * k, acc);
   }
   MJB_LANE0 {

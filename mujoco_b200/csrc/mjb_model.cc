@@ -296,8 +296,9 @@ int check_model(const mjModel* m) {
   if (m->nv <= 0 || m->nbody < 2) FAIL("model without degrees of freedom");
   if (m->nflex || m->nhfield || m->nmocap || m->nplugin) FAIL("flex / hfield / mocap / plugin present");
   for (int i = 0; i < m->neq; i++) {
-    if (m->eq_type[i] != mjEQ_JOINT && m->eq_type[i] != mjEQ_TENDON)
-      FAIL("equality %d: only joint and tendon couplings are built (connect / weld need Jacobian time-derivatives)", i);
+    if (m->eq_type[i] != mjEQ_JOINT && m->eq_type[i] != mjEQ_TENDON && m->eq_type[i] != mjEQ_CONNECT)
+      FAIL("equality %d: joint, tendon and connect equalities are built; weld and flex equalities are not", i);
+    if (m->eq_type[i] == mjEQ_CONNECT && m->eq_objtype[i] != mjOBJ_BODY) FAIL("equality %d: connect with site semantics", i);
     if (m->eq_type[i] == mjEQ_JOINT) {
       for (int k = 0; k < 2; k++) {
         const int j = k ? m->eq_obj2id[i] : m->eq_obj1id[i];
@@ -464,7 +465,7 @@ int build_host_model(const mjModel* m, int nconmax, int njmax, HostModel* out) {
     B.addI(&D.sensor_adr, m->sensor_adr, m->nsensor);
     {
       std::vector<int> kind(m->neq), act(m->neq);
-      for (int i = 0; i < m->neq; i++) { kind[i] = (m->eq_type[i] == mjEQ_JOINT) ? EQ_JOINT : EQ_TENDON; act[i] = m->eq_active0[i] ? 1 : 0; }
+      for (int i = 0; i < m->neq; i++) { kind[i] = (m->eq_type[i] == mjEQ_JOINT) ? EQ_JOINT : (m->eq_type[i] == mjEQ_TENDON) ? EQ_TENDON : EQ_CONNECT; act[i] = m->eq_active0[i] ? 1 : 0; }
       B.addI(&D.eq_kind, kind.data(), m->neq);
       B.addI(&D.eq_obj1id, m->eq_obj1id, m->neq);
       B.addI(&D.eq_obj2id, m->eq_obj2id, m->neq);
@@ -584,8 +585,8 @@ int build_host_model(const mjModel* m, int nconmax, int njmax, HostModel* out) {
   B.addD(&D.actuator_forcerange, m->actuator_forcerange, 2 * m->nu);
   B.addD(&D.sensor_cutoff, m->sensor_cutoff, m->nsensor);
   {
-    std::vector<double> ed(5 * (size_t)m->neq);
-    for (int i = 0; i < m->neq; i++) for (int k = 0; k < 5; k++) ed[5 * i + k] = m->eq_data[mjNEQDATA * i + k];
+    std::vector<double> ed(kNEqData * (size_t)m->neq);
+    for (int i = 0; i < m->neq; i++) for (int k = 0; k < kNEqData; k++) ed[kNEqData * i + k] = m->eq_data[mjNEQDATA * i + k];
     B.addD(&D.eq_data, ed.data(), ed.size());
     B.addD(&D.eq_solref, m->eq_solref, 2 * (size_t)m->neq);
     B.addD(&D.eq_solimp, m->eq_solimp, 5 * (size_t)m->neq);
@@ -795,7 +796,7 @@ int build_host_model(const mjModel* m, int nconmax, int njmax, HostModel* out) {
 
   // caps replacing the reference arena
   if (nconmax <= 0) nconmax = std::min(std::max(S.npair / 2, 16), 32);
-  if (njmax <= 0) njmax = S.nfl + S.neq + 64;
+  if (njmax <= 0) njmax = S.nfl + 3 * S.neq + 64;
   S.nconmax = nconmax;
   S.njmax = njmax;
   if (O.solver == mjSOL_PGS && !O.dense) { set_error("unsupported: PGS with sparse Jacobian (nv >= 60)"); return -2; }

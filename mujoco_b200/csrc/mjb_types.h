@@ -31,7 +31,8 @@ enum { STATE_SATISFIED = 0, STATE_QUADRATIC = 1, STATE_LINEARNEG = 2, STATE_LINE
 enum { WARN_INERTIA = 0, WARN_CONTACTFULL = 1, WARN_CNSTRFULL = 2, WARN_BADQPOS = 3,
        WARN_BADQVEL = 4, WARN_BADQACC = 5, WARN_BADCTRL = 6, WARN_VGEOMFULL = 7, NWARNING = 8 };
 enum { NISLAND = 20 };
-enum { EQ_JOINT = 0, EQ_TENDON = 1 };   // supported equality kinds (mjEQ_JOINT / mjEQ_TENDON): scalar couplings
+enum { EQ_JOINT = 0, EQ_TENDON = 1, EQ_CONNECT = 2 };   // supported equality kinds (scalar couplings; ball-joint connect)
+constexpr int kNEqData = 6;             // leading eq_data values kept per equality (polycoef[5] / two anchors)
 // sensors of the path (engine_sensor.c); internal codes, translated from mjtSensor by the host
 enum { SENS_JOINTPOS, SENS_TENDONPOS, SENS_ACTUATORPOS, SENS_BALLQUAT, SENS_JOINTLIMITPOS, SENS_TENDONLIMITPOS,
        SENS_FRAMEPOS, SENS_FRAMEXAXIS, SENS_FRAMEYAXIS, SENS_FRAMEZAXIS, SENS_FRAMEQUAT, SENS_SUBTREECOM, SENS_CLOCK,

@@ -26,6 +26,7 @@ MODELS = {
     "ant_sensors": os.path.join(ROOT, "models", "ant_sensors.xml"),
     "ant_servo": os.path.join(ROOT, "models", "ant_servo.xml"),
     "ant_equality": os.path.join(ROOT, "models", "ant_equality.xml"),
+    "ant_connect": os.path.join(ROOT, "models", "ant_connect.xml"),
 }
 
 

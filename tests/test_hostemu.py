@@ -325,3 +325,32 @@ def test_equality_couplings_bit_exact(solver):
     out = b.rollout(s0, ctrl[:, :40])
     ref, _, _ = o.rollout(s0, ctrl[:, :40], nthread=4)
     assert np.array_equal(out, ref) and (b.field("ne")[:, 0] == 0).all()
+
+
+@pytest.mark.parametrize("solver", [mb.SOLVER_PGS, mb.SOLVER_NEWTON, mb.SOLVER_CG])
+def test_connect_equality_bit_exact(solver):
+    """connect (ball-joint) equalities: 3 rows with J = jac(anchor 0) - jac(anchor 1), common impedance from
+    |pos|, the Jdot*v correction of aref (mj_Jdotv / mj_jacDot), an equality row joining two kinematic
+    trees into one island, a closed loop inside a tree, and the connect forces entering
+    mj_rnePostConstraint (accelerometer / force / frame acceleration sensors) - models/ant_connect.xml"""
+    from oracle_util import Oracle
+    path = os.path.join(ROOT, "models", "ant_connect.mjb")
+    nenv, nstep = 4, 100
+    m, b, o = make_pair(path, solver, library=hostemu_lib(), nenv=nenv)
+    states = perturbed_states(o, nenv, seed=4, height=[0.3, 0.45, 0.6], qpos_std=0.1)
+    ctrl1 = np.random.default_rng(6).uniform(-1, 1, (nenv, o.size("nu")))
+    compare_forward(b, o, states, ctrl1, rtol=0, exact=True, check_dual=(solver == mb.SOLVER_PGS))
+    assert (b.field("ne")[:, 0] == 6).all() and (b.field("nisland")[:, 0] == 1).all()
+    s0 = perturbed_states(o, nenv, seed=14, height=[0.35, 0.5, 0.75], qvel_std=0.3, qpos_std=0.05)
+    ctrl = np.random.default_rng(15).uniform(-1, 1, (nenv, nstep, o.size("nu")))
+    out, sens = b.rollout(s0, ctrl, return_sensordata=True)
+    for e in range(nenv):
+        oe = Oracle(path)
+        oe.set_opt("solver", solver)
+        oe.reset()
+        oe.set_state(s0[e])
+        for t in range(nstep):
+            oe.dfield("ctrl")[:] = ctrl[e, t]
+            oe.step()
+            assert np.array_equal(out[e, t], oe.get_state()), (e, t)
+            assert np.array_equal(sens[e, t], np.array(oe.dfield("sensordata"))), (e, t)
