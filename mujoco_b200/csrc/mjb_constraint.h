@@ -863,7 +863,7 @@ __device__ inline uint64_t pcg32_skip(uint64_t state, uint32_t delta) {
 // butterfly gives every lane the identical (r0+r2)+(r1+r3) (IEEE addition commutes), and every lane
 // evaluates the projected update redundantly — which removes all divergence/reconvergence from the
 // serial chain.  lo/hi are the projection bounds (-floss/floss for friction rows, 0/inf otherwise).
-template <int MODE>
+template <int MODE, bool ISL>
 __device__ int pgs_sweeps_warp(const Env& d, int nefc, int nf, const int* rows, int nrow, const double* __restrict__ gAR, const double* AR,
                                double* ring, double* force, const double* b, const double* lo, const double* hi,
                                const double* ARinv, double* fprev, double* fmom, const double* Adiag,
@@ -873,7 +873,7 @@ __device__ int pgs_sweeps_warp(const Env& d, int nefc, int nf, const int* rows, 
   const int nv = m.sz.nv, lane = d.lane, k = lane & 3;
   const int n4 = nefc & ~3, tail = nefc - n4, nq = n4 >> 2;
   const double scale = 1 / (m.opt.meaninertia * (nv > 1 ? nv : 1));
-  auto row_of = [&](int c) { return rows ? rows[c] : c; };
+  auto row_of = [&](int c) { return ISL ? rows[c] : c; };
   for (int c = lane; c < nrow; c += 32) { const int i = row_of(c); order[c] = i; fprev[i] = force[i]; }
   __syncwarp();
   Pcg32 rng{0, 1};
@@ -978,9 +978,15 @@ __device__ int pgs_sweeps_warp(const Env& d, int nefc, int nf, const int* rows, 
       if (lane < nefc) q0 = (force[lane] - fmom[lane]) * (fmom[lane] - fprev[lane]);
       if (lane + 32 < nefc) q1 = (force[lane + 32] - fmom[lane + 32]) * (fmom[lane + 32] - fprev[lane + 32]);
       double dce = 0;
-      for (int c = 0; c < nrow; c++) {
-        const int i = row_of(c);
-        dce += __shfl_sync(full, i < 32 ? q0 : q1, i & 31);
+      if (ISL) {
+        for (int c = 0; c < nrow; c++) {
+          const int i = row_of(c);
+          dce += __shfl_sync(full, i < 32 ? q0 : q1, i & 31);
+        }
+      } else {
+        const int nlo = nefc < 32 ? nefc : 32;
+        for (int i = 0; i < nlo; i++) dce += __shfl_sync(full, q0, i);
+        for (int i = 32; i < nefc; i++) dce += __shfl_sync(full, q1, i - 32);
       }
       restart = dce < 0;
     }
@@ -1036,8 +1042,13 @@ MJB_HD void solve_pgs(const Env& d) {
       const int* rows = isl ? imap + iadr[k] : nullptr;
       const int nrow = isl ? iadr[k + 1] - iadr[k] : nefc;
       int iter;
-      if (mode == 2) iter = pgs_sweeps_warp<2>(d, nefc, nf, rows, nrow, gAR, AR, ring, force, b, lo, hi, ARinv, fprev, fmom, Adiag, order, jdraw);
-      else iter = pgs_sweeps_warp<1>(d, nefc, nf, rows, nrow, gAR, AR, ring, force, b, lo, hi, ARinv, fprev, fmom, Adiag, order, jdraw);
+      if (isl) {
+        if (mode == 2) iter = pgs_sweeps_warp<2, true>(d, nefc, nf, rows, nrow, gAR, AR, ring, force, b, lo, hi, ARinv, fprev, fmom, Adiag, order, jdraw);
+        else iter = pgs_sweeps_warp<1, true>(d, nefc, nf, rows, nrow, gAR, AR, ring, force, b, lo, hi, ARinv, fprev, fmom, Adiag, order, jdraw);
+      } else {
+        if (mode == 2) iter = pgs_sweeps_warp<2, false>(d, nefc, nf, rows, nrow, gAR, AR, ring, force, b, lo, hi, ARinv, fprev, fmom, Adiag, order, jdraw);
+        else iter = pgs_sweeps_warp<1, false>(d, nefc, nf, rows, nrow, gAR, AR, ring, force, b, lo, hi, ARinv, fprev, fmom, Adiag, order, jdraw);
+      }
       MJB_PSYNC();
       MJB_LANE0 if (k < NISLAND) niter[k] += iter;
     }

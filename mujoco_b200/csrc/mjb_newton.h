@@ -30,17 +30,20 @@ struct LsPoint { double alpha, cost, d0, d1; };
 // constraint island in island order (engine_solver.c PrimalPointers/PrimalAllocate :1095-1366: the
 // reference gathers island-local copies iacc, ifrc_*, iM, iefc_J; here the global arrays are indexed
 // through the island maps, which performs the same arithmetic on the same operands in the same order)
+// ISL = false is the identity view (monolithic problem): the maps fold away at compile time
+template <bool ISL>
 struct IslView {
-  const int* rows; int nrow;      // island row c -> global efc row (NULL: identity)
-  const int* dofs; int ndof;      // island dof k -> global dof (NULL: identity)
+  const int* rows; int nrow;      // island row c -> global efc row
+  const int* dofs; int ndof;      // island dof k -> global dof
   const int* dof2idof; int base;  // global dof -> island dof = dof2idof[dof] - base
-  MJB_HD int row(int c) const { return rows ? rows[c] : c; }
-  MJB_HD int dof(int k) const { return dofs ? dofs[k] : k; }
-  MJB_HD int loc(int dof_) const { return dofs ? dof2idof[dof_] - base : dof_; }
+  MJB_HD int row(int c) const { return ISL ? rows[c] : c; }
+  MJB_HD int dof(int k) const { return ISL ? dofs[k] : k; }
+  MJB_HD int loc(int dof_) const { return ISL ? dof2idof[dof_] - base : dof_; }
 };
 
+template <bool ISL>
 struct NewtonCtx {
-  IslView v;
+  IslView<ISL> v;
   int nv, nefc, ne, nf;           // nv: global dof count (row pitch of J); nefc: global; rows [0,ne) equality,
                                   // [ne,nf) friction (nf = END of the friction rows)
   FD J, Jaref, Jv, quad, Dq, Ma, Mv, grad, Mgrad, search, cholupd, L;   // Ma..cholupd, L: island-local
@@ -68,7 +71,8 @@ MJB_HD double friction_cost_dif(double start, double x, double f, double Rf, dou
 
 // res = M * vec on the view's dofs (vectors island-local): mju_mulSymVecSparse order per output dof —
 // diagonal term, own-row off-diagonals from the last column to the first, descendant rows ascending
-MJB_HD void mul_M_view(const Env& d, const IslView& v, FD res, FD vec) {
+template <bool ISL>
+MJB_HD void mul_M_view(const Env& d, const IslView<ISL>& v, FD res, FD vec) {
   const DModel& m = d.m;
   FD M = d.M();
   MJB_PFOR(k, v.ndof) {
@@ -84,8 +88,9 @@ MJB_HD void mul_M_view(const Env& d, const IslView& v, FD res, FD vec) {
 }
 
 // res[row] = J(row, view dofs) . vec   (mju_mulMatVec on the island block)
-MJB_HD void mul_jac_view(const Env& d, const NewtonCtx& c, FD res, FD vec) {
-  const IslView& v = c.v;
+template <bool ISL>
+MJB_HD void mul_jac_view(const Env& d, const NewtonCtx<ISL>& c, FD res, FD vec) {
+  const IslView<ISL>& v = c.v;
   MJB_PFOR(cc, v.nrow) {
     const int i = v.row(cc);
     res[i] = dot_ref(v.ndof, [&](int k) { return c.J[(long)i * c.nv + v.dof(k)]; }, [&](int k) { return vec[k]; });
@@ -95,8 +100,9 @@ MJB_HD void mul_jac_view(const Env& d, const NewtonCtx& c, FD res, FD vec) {
 
 // x = M^-1 x for an island-local vector: embedded in a global vector (zeros elsewhere; trees do not
 // couple in L'DL, so the island's dofs see exactly the operations of the block solve)
-MJB_HD void solve_M_view(const Env& d, const IslView& v, FD x) {
-  if (!v.dofs) { solve_LD(d, x, d.qLD(), d.qLDiagInv()); return; }
+template <bool ISL>
+MJB_HD void solve_M_view(const Env& d, const IslView<ISL>& v, FD x) {
+  if (!ISL) { solve_LD(d, x, d.qLD(), d.qLDiagInv()); return; }
   FD g = d.scr_nv() + 2 * d.m.sz.nv;
   MJB_PFOR(i, d.m.sz.nv) g[i] = 0;
   MJB_PSYNC();
@@ -109,8 +115,9 @@ MJB_HD void solve_M_view(const Env& d, const IslView& v, FD x) {
 
 // efc_force / efc_state / cost from Jaref (mj_constraintUpdate_impl on the view's rows),
 // qfrc_constraint = J' force on the view's dofs, plus the Gauss term
-MJB_HD void newton_update_constraint(const Env& d, NewtonCtx& c) {
-  const IslView& v = c.v;
+template <bool ISL>
+MJB_HD void newton_update_constraint(const Env& d, NewtonCtx<ISL>& c) {
+  const IslView<ISL>& v = c.v;
   FD force = d.efc_force(), qfc = d.qfrc_constraint();
   MJB_PFOR(cc, v.nrow) {
     const int i = v.row(cc);
@@ -153,7 +160,8 @@ MJB_HD void newton_update_constraint(const Env& d, NewtonCtx& c) {
   c.cost = s;
 }
 
-MJB_HD void newton_update_grad(const Env& d, NewtonCtx& c) {
+template <bool ISL>
+MJB_HD void newton_update_grad(const Env& d, NewtonCtx<ISL>& c) {
   FD qfc = d.qfrc_constraint();
   MJB_PFOR(k, c.v.ndof) { const int dof = c.v.dof(k); c.grad[k] = c.Ma[k] - c.qfs[dof] - qfc[dof]; }
   MJB_PSYNC();
@@ -231,9 +239,10 @@ MJB_HD int chol_update(const Env& d, FD mat, FD x, int n, bool plus) {
 }
 
 // L <- lower triangle of H = M + J' diag(Dq) J on the view (island-local n x n), then its Cholesky factor
-MJB_HD void newton_factorize(const Env& d, NewtonCtx& c, bool recompute) {
+template <bool ISL>
+MJB_HD void newton_factorize(const Env& d, NewtonCtx<ISL>& c, bool recompute) {
   const DModel& m = d.m;
-  const IslView& v = c.v;
+  const IslView<ISL>& v = c.v;
   const int n = v.ndof, nv = c.nv;
   if (recompute) {
     MJB_PFOR(cc, v.nrow) { const int i = v.row(cc); c.Dq[i] = (c.state[i] == STATE_QUADRATIC) ? c.efcD[i] : 0.0; }
@@ -266,11 +275,13 @@ MJB_HD void newton_factorize(const Env& d, NewtonCtx& c, bool recompute) {
   chol_factor(d, c.L, n, kMinVal);
 }
 
-MJB_HD void newton_update_mgrad(const Env& d, NewtonCtx& c) { chol_solve(d, c.Mgrad, c.L, c.grad, c.v.ndof); }
+template <bool ISL>
+MJB_HD void newton_update_mgrad(const Env& d, NewtonCtx<ISL>& c) { chol_solve(d, c.Mgrad, c.L, c.grad, c.v.ndof); }
 
 // rank-one updates of the factor for the rows whose QUADRATIC membership changed
-MJB_HD void newton_hessian_incremental(const Env& d, NewtonCtx& c) {
-  const IslView& v = c.v;
+template <bool ISL>
+MJB_HD void newton_hessian_incremental(const Env& d, NewtonCtx<ISL>& c) {
+  const IslView<ISL>& v = c.v;
   const int n = v.ndof;
   for (int cc = 0; cc < v.nrow; cc++) {
     const int i = v.row(cc);
@@ -288,7 +299,8 @@ MJB_HD void newton_hessian_incremental(const Env& d, NewtonCtx& c) {
 }
 
 // line-search objective and its first two derivatives at p.alpha (cost relative to alpha = 0)
-MJB_HD void newton_eval(NewtonCtx& c, LsPoint& p) {
+template <bool ISL>
+MJB_HD void newton_eval(NewtonCtx<ISL>& c, LsPoint& p) {
   const double alpha = p.alpha;
   double cost = 0, d0 = 0, d1 = 0;
   double q0 = 0, q1 = c.quadGauss[1], q2 = c.quadGauss[2];
@@ -329,7 +341,8 @@ MJB_HD void newton_eval(NewtonCtx& c, LsPoint& p) {
   c.lsiter++;
 }
 
-MJB_HD int newton_update_bracket(NewtonCtx& c, LsPoint& p, const LsPoint* cand, LsPoint& pnext) {
+template <bool ISL>
+MJB_HD int newton_update_bracket(NewtonCtx<ISL>& c, LsPoint& p, const LsPoint* cand, LsPoint& pnext) {
   int flag = 0;
   for (int i = 0; i < 3; i++) {
     if (p.d0 < 0 && cand[i].d0 < 0 && p.d0 < cand[i].d0) { p = cand[i]; flag = 1; }
@@ -343,8 +356,9 @@ MJB_HD int newton_update_bracket(NewtonCtx& c, LsPoint& p, const LsPoint* cand, 
 }
 
 // exact line search along `search`; returns the step and the cost improvement
-MJB_HD double newton_search(const Env& d, NewtonCtx& c, double tolerance, int ls_iterations, double& improvement) {
-  const IslView& v = c.v;
+template <bool ISL>
+MJB_HD double newton_search(const Env& d, NewtonCtx<ISL>& c, double tolerance, int ls_iterations, double& improvement) {
+  const IslView<ISL>& v = c.v;
   const int n = v.ndof;
   c.lsiter = 0;
   improvement = 0;
@@ -430,12 +444,13 @@ MJB_HD double newton_search(const Env& d, NewtonCtx& c, double tolerance, int ls
 
 // Newton (newton = true) or conjugate gradient (mj_solCG: M-preconditioned, Hager-Zhang direction
 // update, engine_solver.c:2489-2518) on the primal problem of one view; returns the iteration count
-MJB_HD int solve_primal_view(const Env& d, bool newton, const IslView& view, bool island_scale) {
+template <bool ISL>
+MJB_HD int solve_primal_view(const Env& d, bool newton, const IslView<ISL>& view, bool island_scale) {
   const DModel& m = d.m;
   const int nv = m.sz.nv, njmax = m.sz.njmax;
-  NewtonCtx c;
+  NewtonCtx<ISL> c;
   c.v = view;
-  const IslView& v = c.v;
+  const IslView<ISL>& v = c.v;
   const int n = v.ndof;
   c.nv = nv; c.nefc = d.nefc()[0]; c.ne = d.ne()[0]; c.nf = c.ne + d.nf()[0];
   c.J = d.efc_J();
@@ -565,16 +580,16 @@ MJB_HD void solve_primal(const Env& d, bool newton) {
     const int* eadr = d.island_iefcadr().p;
     const int* dadr = d.island_idofadr().p;
     for (int k = 0; k < nisland; k++) {
-      IslView v{d.map_iefc2efc().p + eadr[k], eadr[k + 1] - eadr[k], d.map_idof2dof().p + dadr[k], dadr[k + 1] - dadr[k],
-                d.map_dof2idof().p, dadr[k]};
-      const int iter = solve_primal_view(d, newton, v, true);
+      IslView<true> v{d.map_iefc2efc().p + eadr[k], eadr[k + 1] - eadr[k], d.map_idof2dof().p + dadr[k], dadr[k + 1] - dadr[k],
+                      d.map_dof2idof().p, dadr[k]};
+      const int iter = solve_primal_view<true>(d, newton, v, true);
       MJB_LANE0 if (k < NISLAND) niter[k] += iter;
       MJB_PSYNC();
     }
   } else {
-    IslView v{nullptr, nefc, nullptr, nv, nullptr, 0};
+    IslView<false> v{nullptr, nefc, nullptr, nv, nullptr, 0};
     // a single tree with islands enabled is one island: same problem, island cost scale
-    const int iter = solve_primal_view(d, newton, v, !(m.opt.disableflags & DSBL_ISLAND));
+    const int iter = solve_primal_view<false>(d, newton, v, !(m.opt.disableflags & DSBL_ISLAND));
     MJB_LANE0 niter[0] += iter;
     MJB_PSYNC();
   }
