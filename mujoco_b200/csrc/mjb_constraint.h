@@ -96,7 +96,7 @@ MJB_HD void make_constraint(const Env& d) {
     MJB_PSYNC();
     return;
   }
-  const bool do_eq = m.sz.neq > 0 && !(m.opt.disableflags & DSBL_EQUALITY);
+  const bool do_eq = (d.feat & FEAT_EQUALITY) && m.sz.neq > 0 && !(m.opt.disableflags & DSBL_EQUALITY);
   FI ieq = d.scr_ieq();   // row of every equality, -1 if inactive
   const bool do_fl = m.opt.has_frictionloss && !(m.opt.disableflags & DSBL_FRICTIONLOSS);
   const bool do_lim = m.opt.has_limits && !(m.opt.disableflags & DSBL_LIMIT);
@@ -176,7 +176,7 @@ MJB_HD void make_constraint(const Env& d) {
   FI type = d.efc_type(), id = d.efc_id();
 
   // ---- equality rows: scalar joint / tendon couplings  q1 - q1_0 = data0 + poly(q2 - q2_0)
-  if (ne) {
+  if ((d.feat & FEAT_EQUALITY) && ne) {
     FD tJ = d.ten_J(), tlen = d.ten_length();
     MJB_PFOR(i, m.sz.neq) {
       const int r = ieq[i];
@@ -494,7 +494,7 @@ MJB_HD void reference_constraint(const Env& d) {
   MJB_PSYNC();
   // mj_Jdotv (engine_core_constraint.c:1056-1200): connect rows get aref -= (Jdot1 - Jdot2) * qvel
   const DModel& m = d.m;
-  if (d.ne()[0] && m.sz.neq) {
+  if ((d.feat & FEAT_EQUALITY) && d.ne()[0] && m.sz.neq) {
     FI ieq = d.scr_ieq();
     FD qvel = d.qvel();
     const int nv = m.sz.nv;
@@ -656,7 +656,7 @@ MJB_HD void dsu_merge(int* parent, int t1, int t2) {
 
 // islands are used when the model has several trees and mjDSBL_ISLAND is not set (a single tree is one
 // island that coincides with the monolithic problem)
-MJB_HD bool use_islands(const Env& d) { return d.m.sz.ntree > 1 && !(d.m.opt.disableflags & DSBL_ISLAND); }
+MJB_HD bool use_islands(const Env& d) { return (d.feat & FEAT_ISLAND) && d.m.sz.ntree > 1 && !(d.m.opt.disableflags & DSBL_ISLAND); }
 
 MJB_HD void make_islands(const Env& d) {
   const DModel& m = d.m;

@@ -396,7 +396,7 @@ MJB_HD void rne_post(const Env& d) {
         if (b2 == k) for (int q = 0; q < 6; q++) acc.v[q] += cc.v[q];
       }
     }
-    if (k && d.ne()[0]) {   // connect rows: force on body 1 (+) and body 2 (-), applied at the anchors
+    if ((d.feat & FEAT_EQUALITY) && k && d.ne()[0]) {   // connect rows: force on body 1 (+) and body 2 (-), applied at the anchors
       FI ieq = d.scr_ieq();
       for (int eq = 0; eq < m.sz.neq; eq++) {
         const int r = ieq[eq];

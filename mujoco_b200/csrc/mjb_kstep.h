@@ -14,6 +14,10 @@ void launch_kstep_newton32(const DModel& dm, const Batch& b, int mask, int flags
 void launch_kstep_cg32(const DModel& dm, const Batch& b, int mask, int flags, void* stream);
 void launch_kstep_newton16(const DModel& dm, const Batch& b, int mask, int flags, void* stream);
 void launch_kstep_any16(const DModel& dm, const Batch& b, int mask, int flags, void* stream);
+// lean instantiations (FEAT = 0): models without sensors, equalities, several trees or implicitfast
+void launch_kstep_pgs32_lean(const DModel& dm, const Batch& b, int mask, int flags, void* stream);
+void launch_kstep_newton32_lean(const DModel& dm, const Batch& b, int mask, int flags, void* stream);
+void launch_kstep_newton16_lean(const DModel& dm, const Batch& b, int mask, int flags, void* stream);
 }  // namespace backend
 
 #if defined(MJB_KSTEP_INSTANCE) && defined(__CUDACC__)
@@ -34,7 +38,7 @@ constexpr int kSmemPerWarp = MJB_SMEM_PER_WARP;    // doubles = 6.5 KB: eight sw
 // instantiation carries only its own solver's code and register pressure.
 // NLANE = 16 maps TWO small environments onto each warp (models with <= 16 bodies and dofs leave half
 // of a warp idle in every cooperative loop); the two halves synchronise with their own lane masks.
-template <int SOLVER, int NLANE>
+template <int SOLVER, int NLANE, int FEAT>
 __global__ void __launch_bounds__(32 * kWarpsPerCta, MJB_CTAS_PER_SM) k_step_warp(DModel m, Batch b, int mask, int flags) {
   constexpr int kPerWarp = 32 / NLANE;
   __shared__ double smem[NLANE == 32 ? kWarpsPerCta * kSmemPerWarp : 1];
@@ -42,20 +46,20 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta, MJB_CTAS_PER_SM) k_step_war
   const int e = (blockIdx.x * kWarpsPerCta + w) * kPerWarp + l / NLANE;
   if (e >= b.nenv) return;
   if (NLANE == 32) {
-    run_env(m, b, e, mask, flags, l, 32, smem + w * kSmemPerWarp, kSmemPerWarp, SOLVER);
+    run_env(m, b, e, mask, flags, l, 32, smem + w * kSmemPerWarp, kSmemPerWarp, SOLVER, 0xffffffffu, FEAT);
   } else {
     const unsigned lanes = ((1u << NLANE) - 1u) << ((l / NLANE) * NLANE);
-    run_env(m, b, e, mask, flags, l % NLANE, NLANE, nullptr, 0, SOLVER, lanes);
+    run_env(m, b, e, mask, flags, l % NLANE, NLANE, nullptr, 0, SOLVER, lanes, FEAT);
   }
 }
 
 
-#define MJB_KSTEP_LAUNCHER(NAME, SOLVER, NLANE)                                                              \
+#define MJB_KSTEP_LAUNCHER(NAME, SOLVER, NLANE, FEAT)                                                             \
   namespace backend {                                                                                        \
   void NAME(const DModel& dm, const Batch& b, int mask, int flags, void* stream) {                            \
     const int per_cta = kWarpsPerCta * (32 / NLANE);                                                         \
     const int grid = (b.nenv + per_cta - 1) / per_cta;                                                       \
-    k_step_warp<SOLVER, NLANE><<<grid, 32 * kWarpsPerCta, 0, (cudaStream_t)stream>>>(dm, b, mask, flags);     \
+    k_step_warp<SOLVER, NLANE, FEAT><<<grid, 32 * kWarpsPerCta, 0, (cudaStream_t)stream>>>(dm, b, mask, flags);     \
   }                                                                                                          \
   }
 #endif

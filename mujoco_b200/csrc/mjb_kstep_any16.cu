@@ -2,5 +2,5 @@
 #define MJB_KSTEP_INSTANCE
 #include "mjb_kstep.h"
 namespace mjb {
-MJB_KSTEP_LAUNCHER(launch_kstep_any16, -1, 16)
+MJB_KSTEP_LAUNCHER(launch_kstep_any16, -1, 16, FEAT_ALL)
 }  // namespace mjb

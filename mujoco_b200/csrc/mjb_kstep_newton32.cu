@@ -2,5 +2,5 @@
 #define MJB_KSTEP_INSTANCE
 #include "mjb_kstep.h"
 namespace mjb {
-MJB_KSTEP_LAUNCHER(launch_kstep_newton32, SOL_NEWTON, 32)
+MJB_KSTEP_LAUNCHER(launch_kstep_newton32, SOL_NEWTON, 32, FEAT_ALL)
 }  // namespace mjb

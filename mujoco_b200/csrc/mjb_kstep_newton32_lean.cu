@@ -2,5 +2,5 @@
 #define MJB_KSTEP_INSTANCE
 #include "mjb_kstep.h"
 namespace mjb {
-MJB_KSTEP_LAUNCHER(launch_kstep_newton16, SOL_NEWTON, 16, FEAT_ALL)
+MJB_KSTEP_LAUNCHER(launch_kstep_newton32_lean, SOL_NEWTON, 32, 0)
 }  // namespace mjb

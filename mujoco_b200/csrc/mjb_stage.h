@@ -31,7 +31,7 @@ MJB_HD void run_stage_mask(const Env& d, int mask, int flags) {
     if ((mask & 1) || redo) stage_position(d, (flags & 1) != 0 && !redo);
     if ((mask & 2) || redo) stage_velocity(d);
     if ((mask & 4) || redo) stage_solve(d);
-    if (mask & (8 | 16 | 32)) { stage_finish_forward(d); if (!(flags & 8)) sensors(d); }
+    if (mask & (8 | 16 | 32)) { stage_finish_forward(d); if ((d.feat & FEAT_SENSOR) && !(flags & 8)) sensors(d); }
     if (!(mask & (8 | 32))) return;
     if (!redo) {
       check_vec(d, d.qacc(), d.m.sz.nv, WARN_BADQACC);
@@ -39,7 +39,7 @@ MJB_HD void run_stage_mask(const Env& d, int mask, int flags) {
       MJB_PSYNC();
       if (bad && !(d.m.opt.disableflags & DSBL_AUTORESET)) continue;
     }
-    if (mask & 8) { if (d.m.opt.integrator == INT_IMPLICITFAST) implicitfast_advance(d); else euler_advance(d); }
+    if (mask & 8) { if ((d.feat & FEAT_IMPLICITFAST) && d.m.opt.integrator == INT_IMPLICITFAST) implicitfast_advance(d); else euler_advance(d); }
     return;
   }
 }
@@ -64,9 +64,9 @@ MJB_HD bool step_enabled(const Env& d, int flags) {
 // flags: bit0 = part of mj_step (qpos/qvel checks), bit1/bit2 = rollout skip rule (step_enabled).
 // sm/smcap: optional per-warp shared-memory scratch (doubles) used by the latency-critical loops.
 MJB_HD void run_env(const DModel& m, const Batch& b, int e, int mask, int flags, int lane, int nlane,
-                    double* sm, int smcap, int solver = -1, unsigned lanes = 0xffffffffu) {
+                    double* sm, int smcap, int solver = -1, unsigned lanes = 0xffffffffu, int feat = FEAT_ALL) {
   Env d(m, b, e, lane, nlane);
-  d.sm = sm; d.smcap = smcap; d.mask = lanes;
+  d.sm = sm; d.smcap = smcap; d.mask = lanes; d.feat = feat;
   d.solver = solver < 0 ? m.opt.solver : solver;
   if (!step_enabled(d, flags)) return;
   run_stage_mask(d, mask, flags);

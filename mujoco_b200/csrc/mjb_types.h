@@ -31,6 +31,7 @@ enum { STATE_SATISFIED = 0, STATE_QUADRATIC = 1, STATE_LINEARNEG = 2, STATE_LINE
 enum { WARN_INERTIA = 0, WARN_CONTACTFULL = 1, WARN_CNSTRFULL = 2, WARN_BADQPOS = 3,
        WARN_BADQVEL = 4, WARN_BADQACC = 5, WARN_BADCTRL = 6, WARN_VGEOMFULL = 7, NWARNING = 8 };
 enum { NISLAND = 20 };
+enum { FEAT_SENSOR = 1, FEAT_EQUALITY = 2, FEAT_ISLAND = 4, FEAT_IMPLICITFAST = 8, FEAT_ALL = 15 };
 enum { EQ_JOINT = 0, EQ_TENDON = 1, EQ_CONNECT = 2 };   // supported equality kinds (scalar couplings; ball-joint connect)
 constexpr int kNEqData = 6;             // leading eq_data values kept per equality (polycoef[5] / two anchors)
 // sensors of the path (engine_sensor.c); internal codes, translated from mjtSensor by the host
@@ -235,6 +236,10 @@ struct Env {
   int smcap = 0;
   int solver = -1;   // constraint solver; a compile-time constant in the specialised fused kernels
   unsigned mask = 0xffffffffu;   // lanes of the warp that share this environment (sub-warp mapping)
+  // optional parts of the pipeline this environment's model needs (FEAT_*); a compile-time constant in the
+  // specialised fused kernels, so a model without sensors / equalities / several trees / implicitfast runs a
+  // kernel that does not carry (or pay registers for) that code
+  int feat = FEAT_ALL;
   MJB_HD Env(const DModel& m_, const Batch& b_, int e_, int lane_ = 0, int nlane_ = 1)
       : m(m_), b(b_), e(e_), lane(lane_), nlane(nlane_) {
     hd = b.dbl + (size_t)e * b.dpitch;
