@@ -61,8 +61,9 @@ MJB_HD void connect_anchors(const Env& d, int eq, V3& p0, V3& p1) {
   const DModel& m = d.m;
   const int o1 = m.eq_obj1id[eq], o2 = m.eq_obj2id[eq];
   const double* data = m.eq_data + kNEqData * eq;
-  p0 = mulmv(ld9(d.xmat(), 9 * o1), V3{data[0], data[1], data[2]}) + ld3(d.xpos(), 3 * o1);
-  p1 = mulmv(ld9(d.xmat(), 9 * o2), V3{data[3], data[4], data[5]}) + ld3(d.xpos(), 3 * o2);
+  const int a0 = (m.eq_kind[eq] == EQ_WELD) ? 3 : 0, a1 = 3 - a0;   // weld keeps its anchors the other way round
+  p0 = mulmv(ld9(d.xmat(), 9 * o1), V3{data[a0], data[a0 + 1], data[a0 + 2]}) + ld3(d.xpos(), 3 * o1);
+  p1 = mulmv(ld9(d.xmat(), 9 * o2), V3{data[a1], data[a1 + 1], data[a1 + 2]}) + ld3(d.xpos(), 3 * o2);
 }
 
 // one element of the time derivative of the translational point Jacobian (mj_jacDot, engine_core_util.c
@@ -81,6 +82,16 @@ MJB_HD double jacdot_elem(const Env& d, V3 pt, int body, int k, int c) {
   const V3 t1 = cross(V3{cd.v[0], cd.v[1], cd.v[2]}, off);
   const V3 t2 = cross(ld3(cdof, 6 * c), plin);
   return cd.v[3 + k] + get(t1, k) + get(t2, k);
+}
+
+// element of the time derivative of the rotational Jacobian (mj_jacDot, jacr): component k, dof c
+MJB_HD double jacrdot_elem(const Env& d, int body, int k, int c) {
+  const DModel& m = d.m;
+  if (!m.body_dofanc[(long)body * m.sz.nv + c]) return 0;
+  const int j = m.dof_jntid[c], jt = m.jnt_type[j];
+  if (jt == JNT_BALL || (jt == JNT_FREE && c >= m.jnt_dofadr[j] + 3))
+    return cross_motion(ld6(d.cvel(), 6 * m.dof_bodyid[c]), ld6(d.cdof(), 6 * c)).v[k];
+  return d.cdof_dot()[6 * c + k];
 }
 
 MJB_HD void make_constraint(const Env& d) {
@@ -137,7 +148,7 @@ MJB_HD void make_constraint(const Env& d) {
       for (int i = 0; i < m.sz.neq; i++) {
         ieq[i] = -1;
         if (!m.eq_active0[i]) continue;
-        const int rows = (m.eq_kind[i] == EQ_CONNECT) ? 3 : 1;
+        const int rows = (m.eq_kind[i] == EQ_WELD) ? 6 : (m.eq_kind[i] == EQ_CONNECT) ? 3 : 1;
         if (nefc + rows > njmax) { full = true; continue; }
         ieq[i] = nefc;
         nefc += rows; ne += rows;
@@ -182,7 +193,7 @@ MJB_HD void make_constraint(const Env& d) {
       const int r = ieq[i];
       if (r < 0) continue;
       const int o1 = m.eq_obj1id[i], o2 = m.eq_obj2id[i];
-      if (m.eq_kind[i] == EQ_CONNECT) {   // ball-joint connect of two body anchors: 3 rows, J = jac(0) - jac(1)
+      if (m.eq_kind[i] >= EQ_CONNECT) {   // connect: 3 rows, J = jac(0) - jac(1) at the anchors; weld: + 3 rotational rows
         V3 p0, p1;
         connect_anchors(d, i, p0, p1);
         const V3 cp = p0 - p1;
@@ -190,6 +201,30 @@ MJB_HD void make_constraint(const Env& d) {
           FD row = J + (long)(r + k) * nv;
           for (int c = 0; c < nv; c++) row[c] = jac_elem(d, p0, o1, k, c) - jac_elem(d, p1, o2, k, c);
           epos[r + k] = get(cp, k); emargin[r + k] = 0; efl[r + k] = 0; type[r + k] = CNSTR_EQUALITY; id[r + k] = i;
+        }
+        if (m.eq_kind[i] == EQ_WELD) {
+          const double* data = m.eq_data + kNEqData * i;
+          const double ts = data[10];
+          const Q4 quat = qmul(ld4(d.xquat(), 4 * o1), Q4{data[6], data[7], data[8], data[9]});   // q0 * relpose
+          Q4 q1n = ld4(d.xquat(), 4 * o2);
+          q1n = Q4{q1n.w, -q1n.x, -q1n.y, -q1n.z};                                                   // neg(q1)
+          const Q4 qe = qmul(q1n, quat);
+          const double ce[3] = {qe.x * ts, qe.y * ts, qe.z * ts};
+          FD cdof = d.cdof();
+          for (int c = 0; c < nv; c++) {   // 0.5 * neg(q1) * (jacr0 - jacr1)_col * q0*relpose, scaled
+            const bool in1 = m.body_dofanc[(long)o1 * nv + c], in2 = m.body_dofanc[(long)o2 * nv + c];
+            V3 ax;
+            ax.x = (in1 ? cdof[6 * c] : 0.0) - (in2 ? cdof[6 * c] : 0.0);
+            ax.y = (in1 ? cdof[6 * c + 1] : 0.0) - (in2 ? cdof[6 * c + 1] : 0.0);
+            ax.z = (in1 ? cdof[6 * c + 2] : 0.0) - (in2 ? cdof[6 * c + 2] : 0.0);
+            const Q4 q3 = qmul(qmul_axis(q1n, ax), quat);
+            J[(long)(r + 3) * nv + c] = 0.5 * q3.x * ts;
+            J[(long)(r + 4) * nv + c] = 0.5 * q3.y * ts;
+            J[(long)(r + 5) * nv + c] = 0.5 * q3.z * ts;
+          }
+          for (int k = 0; k < 3; k++) {
+            epos[r + 3 + k] = ce[k]; emargin[r + 3 + k] = 0; efl[r + 3 + k] = 0; type[r + 3 + k] = CNSTR_EQUALITY; id[r + 3 + k] = i;
+          }
         }
         continue;
       }
@@ -309,8 +344,9 @@ MJB_HD void make_constraint(const Env& d) {
   FD dA = d.efc_diagA();
   MJB_PFOR(r, nefc) {
     const int t = type[r], k = id[r];
-    if (t == CNSTR_EQUALITY && m.eq_kind[k] == EQ_CONNECT) {
-      dA[r] = m.body_invweight0[2 * m.eq_obj1id[k]] + m.body_invweight0[2 * m.eq_obj2id[k]];
+    if (t == CNSTR_EQUALITY && m.eq_kind[k] >= EQ_CONNECT) {   // translation rows, then (weld) rotation rows
+      const int rot = (r - ieq[k] > 2) ? 1 : 0;
+      dA[r] = m.body_invweight0[2 * m.eq_obj1id[k] + rot] + m.body_invweight0[2 * m.eq_obj2id[k] + rot];
     }
     else if (t == CNSTR_EQUALITY) {
       const bool jnt = m.eq_kind[k] == EQ_JOINT;
@@ -359,9 +395,9 @@ MJB_HD void make_constraint(const Env& d) {
     solimp[4] = dmax(1, solimp[4]);
     double imp, impP;
     double ipos = epos[r], imargin = emargin[r];
-    if (t == CNSTR_EQUALITY && m.eq_kind[k] == EQ_CONNECT) {   // getposdim: the 3 rows share |pos| (mju_norm)
-      const int base = ieq[k];
-      ipos = sqrt(dot_ref(3, [&](int q) { return epos[base + q]; }, [&](int q) { return epos[base + q]; }));
+    if (t == CNSTR_EQUALITY && m.eq_kind[k] >= EQ_CONNECT) {   // getposdim: the 3 (6) rows share |pos| (mju_norm)
+      const int base = ieq[k], dimp = (m.eq_kind[k] == EQ_WELD) ? 6 : 3;
+      ipos = sqrt(dot_ref(dimp, [&](int q) { return epos[base + q]; }, [&](int q) { return epos[base + q]; }));
       imargin = emargin[base];
     }
     impedance(solimp, ipos, imargin, imp, impP);
@@ -501,13 +537,44 @@ MJB_HD void reference_constraint(const Env& d) {
     MJB_PFOR(it, m.sz.neq * 3) {
       const int eq = it / 3, k = it - eq * 3;
       const int r = ieq[eq];
-      if (r < 0 || m.eq_kind[eq] != EQ_CONNECT) continue;
+      if (r < 0 || m.eq_kind[eq] < EQ_CONNECT) continue;
       V3 p0, p1;
       connect_anchors(d, eq, p0, p1);
       const int o1 = m.eq_obj1id[eq], o2 = m.eq_obj2id[eq];
       const double j1 = dot_ref(nv, [&](int c) { return jacdot_elem(d, p0, o1, k, c); }, [&](int c) { return qvel[c]; });
       const double j2 = dot_ref(nv, [&](int c) { return jacdot_elem(d, p1, o2, k, c); }, [&](int c) { return qvel[c]; });
       aref[r + k] -= j1 - j2;
+    }
+    MJB_PSYNC();
+    // welds: rotational part, three product-rule terms of d/dt [0.5 neg(q1) (J0-J1) v q0 relpose]
+    MJB_PFOR(eq, m.sz.neq) {
+      const int r = ieq[eq];
+      if (r < 0 || m.eq_kind[eq] != EQ_WELD) continue;
+      const int o1 = m.eq_obj1id[eq], o2 = m.eq_obj2id[eq];
+      const double* data = m.eq_data + kNEqData * eq;
+      const double ts = data[10];
+      const Q4 rel{data[6], data[7], data[8], data[9]};
+      const Q4 q0 = ld4(d.xquat(), 4 * o1), q1 = ld4(d.xquat(), 4 * o2);
+      const Q4 q0r = qmul(q0, rel);
+      const Q4 negq1{q1.w, -q1.x, -q1.y, -q1.z};
+      const V3 w1 = ld3(d.cvel(), 6 * o1), w2 = ld3(d.cvel(), 6 * o2);
+      const V3 dom = w1 - w2;
+      const Q4 qdot0r = qmul(deriv_quat(q0, w1), rel);
+      const Q4 qd1 = deriv_quat(q1, w2);
+      const Q4 negqdot1{qd1.w, -qd1.x, -qd1.y, -qd1.z};
+      V3 jr1, jr2;   // rotational jacDot * qvel of the two bodies
+      for (int k = 0; k < 3; k++) {
+        const double a = dot_ref(nv, [&](int c) { return jacrdot_elem(d, o1, k, c); }, [&](int c) { return qvel[c]; });
+        const double b = dot_ref(nv, [&](int c) { return jacrdot_elem(d, o2, k, c); }, [&](int c) { return qvel[c]; });
+        if (k == 0) { jr1.x = a; jr2.x = b; } else if (k == 1) { jr1.y = a; jr2.y = b; } else { jr1.z = a; jr2.z = b; }
+      }
+      const V3 djr = jr1 - jr2;
+      const Q4 t1 = qmul(qmul_axis(negqdot1, dom), q0r);
+      const Q4 t2 = qmul(qmul_axis(negq1, djr), q0r);
+      const Q4 t3 = qmul(qmul_axis(negq1, dom), qdot0r);
+      aref[r + 3] -= 0.5 * (t1.x + t2.x + t3.x) * ts;
+      aref[r + 4] -= 0.5 * (t1.y + t2.y + t3.y) * ts;
+      aref[r + 5] -= 0.5 * (t1.z + t2.z + t3.z) * ts;
     }
     MJB_PSYNC();
   }
@@ -675,7 +742,7 @@ MJB_HD void make_islands(const Env& d) {
       ptype = type[i]; pid = id[i];
       int t1 = -2, t2 = -2;
       bool scan = false;
-      if (ptype == CNSTR_EQUALITY && m.eq_kind[pid] == EQ_CONNECT) {
+      if (ptype == CNSTR_EQUALITY && m.eq_kind[pid] >= EQ_CONNECT) {
         t1 = m.body_treeid[m.eq_obj1id[pid]];
         t2 = m.body_treeid[m.eq_obj2id[pid]];
       }

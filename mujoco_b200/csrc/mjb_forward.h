@@ -400,12 +400,13 @@ MJB_HD void rne_post(const Env& d) {
       FI ieq = d.scr_ieq();
       for (int eq = 0; eq < m.sz.neq; eq++) {
         const int r = ieq[eq];
-        if (r < 0 || m.eq_kind[eq] != EQ_CONNECT) continue;
+        if (r < 0 || m.eq_kind[eq] < EQ_CONNECT) continue;
         const int o1 = m.eq_obj1id[eq], o2 = m.eq_obj2id[eq];
         if (o1 != k && o2 != k) continue;
         V3 p0, p1;
         connect_anchors(d, eq, p0, p1);
-        const S6 cf{{0, 0, 0, force[r], force[r + 1], force[r + 2]}};
+        const bool weld = m.eq_kind[eq] == EQ_WELD;   // welds also transmit a torque
+        const S6 cf{{weld ? force[r + 3] : 0.0, weld ? force[r + 4] : 0.0, weld ? force[r + 5] : 0.0, force[r], force[r + 1], force[r + 2]}};
         if (o1 == k) { const S6 cc = transform_force(cf, ld3(sc, 3 * m.body_rootid[k]), p0); for (int q = 0; q < 6; q++) acc.v[q] += cc.v[q]; }
         if (o2 == k) { const S6 cc = transform_force(cf, ld3(sc, 3 * m.body_rootid[k]), p1); for (int q = 0; q < 6; q++) acc.v[q] -= cc.v[q]; }
       }

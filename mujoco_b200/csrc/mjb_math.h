@@ -277,6 +277,16 @@ MJB_HD double d_xpoly_force(double linear, const double* poly, int n, double x, 
   return res;
 }
 
+// mju_mulQuatAxis / mju_derivQuat (engine_util_spatial.c:81-92, :225-230)
+MJB_HD Q4 qmul_axis(Q4 q, V3 a) {
+  return Q4{-q.x * a.x - q.y * a.y - q.z * a.z, q.w * a.x + q.y * a.z - q.z * a.y,
+            q.w * a.y + q.z * a.x - q.x * a.z, q.w * a.z + q.x * a.y - q.y * a.x};
+}
+MJB_HD Q4 deriv_quat(Q4 q, V3 v) {
+  return Q4{0.5 * (-v.x * q.x - v.y * q.y - v.z * q.z), 0.5 * (v.x * q.w + v.y * q.z - v.z * q.y),
+            0.5 * (-v.x * q.z + v.y * q.w + v.z * q.x), 0.5 * (v.x * q.y - v.y * q.x + v.z * q.w)};
+}
+
 // PCG32 (engine_solver.c:240-255): the PGS sweep order must match the reference draw for draw
 struct Pcg32 { uint64_t state, inc; };
 MJB_HD uint32_t pcg32_next(Pcg32& r) {

@@ -296,9 +296,9 @@ int check_model(const mjModel* m) {
   if (m->nv <= 0 || m->nbody < 2) FAIL("model without degrees of freedom");
   if (m->nflex || m->nhfield || m->nmocap || m->nplugin) FAIL("flex / hfield / mocap / plugin present");
   for (int i = 0; i < m->neq; i++) {
-    if (m->eq_type[i] != mjEQ_JOINT && m->eq_type[i] != mjEQ_TENDON && m->eq_type[i] != mjEQ_CONNECT)
-      FAIL("equality %d: joint, tendon and connect equalities are built; weld and flex equalities are not", i);
-    if (m->eq_type[i] == mjEQ_CONNECT && m->eq_objtype[i] != mjOBJ_BODY) FAIL("equality %d: connect with site semantics", i);
+    if (m->eq_type[i] != mjEQ_JOINT && m->eq_type[i] != mjEQ_TENDON && m->eq_type[i] != mjEQ_CONNECT && m->eq_type[i] != mjEQ_WELD)
+      FAIL("equality %d: joint, tendon, connect and weld equalities are built; flex equalities are not", i);
+    if ((m->eq_type[i] == mjEQ_CONNECT || m->eq_type[i] == mjEQ_WELD) && m->eq_objtype[i] != mjOBJ_BODY) FAIL("equality %d: connect / weld with site semantics", i);
     if (m->eq_type[i] == mjEQ_JOINT) {
       for (int k = 0; k < 2; k++) {
         const int j = k ? m->eq_obj2id[i] : m->eq_obj1id[i];
@@ -465,7 +465,7 @@ int build_host_model(const mjModel* m, int nconmax, int njmax, HostModel* out) {
     B.addI(&D.sensor_adr, m->sensor_adr, m->nsensor);
     {
       std::vector<int> kind(m->neq), act(m->neq);
-      for (int i = 0; i < m->neq; i++) { kind[i] = (m->eq_type[i] == mjEQ_JOINT) ? EQ_JOINT : (m->eq_type[i] == mjEQ_TENDON) ? EQ_TENDON : EQ_CONNECT; act[i] = m->eq_active0[i] ? 1 : 0; }
+      for (int i = 0; i < m->neq; i++) { kind[i] = (m->eq_type[i] == mjEQ_JOINT) ? EQ_JOINT : (m->eq_type[i] == mjEQ_TENDON) ? EQ_TENDON : (m->eq_type[i] == mjEQ_CONNECT) ? EQ_CONNECT : EQ_WELD; act[i] = m->eq_active0[i] ? 1 : 0; }
       B.addI(&D.eq_kind, kind.data(), m->neq);
       B.addI(&D.eq_obj1id, m->eq_obj1id, m->neq);
       B.addI(&D.eq_obj2id, m->eq_obj2id, m->neq);
@@ -796,7 +796,7 @@ int build_host_model(const mjModel* m, int nconmax, int njmax, HostModel* out) {
 
   // caps replacing the reference arena
   if (nconmax <= 0) nconmax = std::min(std::max(S.npair / 2, 16), 32);
-  if (njmax <= 0) njmax = S.nfl + 3 * S.neq + 64;
+  if (njmax <= 0) njmax = S.nfl + 6 * S.neq + 64;
   S.nconmax = nconmax;
   S.njmax = njmax;
   if (O.solver == mjSOL_PGS && !O.dense) { set_error("unsupported: PGS with sparse Jacobian (nv >= 60)"); return -2; }

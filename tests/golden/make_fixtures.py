@@ -27,6 +27,7 @@ MODELS = {
     "ant_servo": os.path.join(ROOT, "models", "ant_servo.xml"),
     "ant_equality": os.path.join(ROOT, "models", "ant_equality.xml"),
     "ant_connect": os.path.join(ROOT, "models", "ant_connect.xml"),
+    "ant_weld": os.path.join(ROOT, "models", "ant_weld.xml"),
 }
 
 

@@ -205,3 +205,35 @@ def test_sensors_and_mjdata_bridge_vs_oracle():
                 worst = max(worst, np.abs(a - c).max() / max(1.0, np.abs(c).max()))
     print("sensors / bridge worst rel err %.3e" % worst)
     assert worst < RTOL_TIGHT
+
+
+@pytest.mark.parametrize("solver", SOLVERS)
+@pytest.mark.parametrize("model", ["ant_equality", "ant_connect", "ant_weld"])
+def test_equality_constraints_vs_oracle(model, solver):
+    """equality rows on the device: joint / tendon couplings, connects and welds (models/ant_equality,
+    ant_connect, ant_weld) incl. the Jdot*v corrections and the equality forces in the sensors"""
+    assert available()
+    path = os.path.join(ROOT, "models", model + ".mjb")
+    nenv, nstep = 12, 100
+    m, b, o = make_pair(path, solver, nenv=nenv)
+    s0 = perturbed_states(o, nenv, seed=14, height=[0.35, 0.5, 0.75], qvel_std=0.3, qpos_std=0.05)
+    ctrl = np.random.default_rng(15).uniform(-1, 1, (nenv, nstep, o.size("nu")))
+    out, sens = b.rollout(s0, ctrl, return_sensordata=True)
+    ref, stats, _ = o.rollout(s0, ctrl, nthread=os.cpu_count() or 1)
+    assert stats[:, 3].sum() == 0 and (b.warnings() == 0).all()
+    err = (np.abs(out - ref) / np.maximum(1.0, np.abs(ref).max(axis=(0, 1)))).max(axis=(0, 2))
+    print("%s rollout rel err: step 30 %.3e, step 100 %.3e" % (model, err[:30].max(), err.max()))
+    assert err[:30].max() < RTOL_TIGHT and err.max() < RTOL_TRAJ
+    if o.size("nsensordata"):      # equality forces reach the accelerometer / force / torque sensors
+        oe = Oracle(path)
+        oe.set_opt("solver", solver)
+        oe.reset()
+        oe.set_state(s0[0])
+        for t in range(30):
+            oe.dfield("ctrl")[:] = ctrl[0, t]
+            oe.step()
+            r = np.array(oe.dfield("sensordata"))
+            assert np.abs(sens[0, t] - r).max() <= 1e-7 * max(1.0, np.abs(r).max()), t
+    for t in (0, 40, 99):
+        compare_forward(b, o, ref[:, t, :], ctrl[:, t, :], rtol=RTOL_TIGHT, check_dual=(solver == mb.SOLVER_PGS))
+    assert (b.field("ne")[:, 0] > 0).all()

@@ -354,3 +354,32 @@ def test_connect_equality_bit_exact(solver):
             oe.step()
             assert np.array_equal(out[e, t], oe.get_state()), (e, t)
             assert np.array_equal(sens[e, t], np.array(oe.dfield("sensordata"))), (e, t)
+
+
+@pytest.mark.parametrize("solver", [mb.SOLVER_PGS, mb.SOLVER_NEWTON, mb.SOLVER_CG])
+def test_weld_equality_bit_exact(solver):
+    """weld equalities: 3 translational rows (connect at the weld anchors) + 3 rotational rows
+    0.5*neg(q1)*(jacr0-jacr1)*q0*relpose*torquescale, impedance from the 6-row |pos|, translational and
+    rotational Jdot*v corrections, a weld to the world body, weld forces and torques in
+    mj_rnePostConstraint (force / torque sensors) - models/ant_weld.xml"""
+    from oracle_util import Oracle
+    path = os.path.join(ROOT, "models", "ant_weld.mjb")
+    nenv, nstep = 4, 100
+    m, b, o = make_pair(path, solver, library=hostemu_lib(), nenv=nenv)
+    states = perturbed_states(o, nenv, seed=4, height=[0.3, 0.45, 0.6], qpos_std=0.1)
+    ctrl1 = np.random.default_rng(6).uniform(-1, 1, (nenv, o.size("nu")))
+    compare_forward(b, o, states, ctrl1, rtol=0, exact=True, check_dual=(solver == mb.SOLVER_PGS))
+    assert (b.field("ne")[:, 0] == 15).all() and (b.field("nisland")[:, 0] == 2).all()
+    s0 = perturbed_states(o, nenv, seed=14, height=[0.35, 0.5, 0.75], qvel_std=0.3, qpos_std=0.05)
+    ctrl = np.random.default_rng(15).uniform(-1, 1, (nenv, nstep, o.size("nu")))
+    out, sens = b.rollout(s0, ctrl, return_sensordata=True)
+    for e in range(nenv):
+        oe = Oracle(path)
+        oe.set_opt("solver", solver)
+        oe.reset()
+        oe.set_state(s0[e])
+        for t in range(nstep):
+            oe.dfield("ctrl")[:] = ctrl[e, t]
+            oe.step()
+            assert np.array_equal(out[e, t], oe.get_state()), (e, t)
+            assert np.array_equal(sens[e, t], np.array(oe.dfield("sensordata"))), (e, t)
