@@ -178,7 +178,8 @@ static int state_segments(const mjbBatch* B, unsigned sig, std::vector<Seg>* seg
   if (sig & ST_TIME) segs->push_back({L.time, 1});
   if (sig & ST_QPOS) segs->push_back({L.qpos, S.nq});
   if (sig & ST_QVEL) segs->push_back({L.qvel, S.nv});
-  // ACT, HISTORY: zero-sized on supported models (na == 0, nhistory == 0)
+  if ((sig & ST_ACT) && S.na) segs->push_back({L.act, S.na});
+  // HISTORY: zero-sized on supported models (nhistory == 0)
   if (sig & ST_WARMSTART) segs->push_back({L.qacc_warmstart, S.nv});
   if (sig & ST_CTRL) segs->push_back({L.ctrl, S.nu});
   if (sig & ST_QFRC_APPLIED) segs->push_back({L.qfrc_applied, S.nv});
@@ -376,7 +377,7 @@ int mjb_rollout(mjbBatch* B, int nstep, unsigned int control_spec, const double*
 int mjb_step_host(mjbBatch* B, const double* ctrl, double* state_out) {
   if (!B || !ctrl || !state_out) return fail(MJB_ERR_ARG, "mjb_step_host: bad arguments");
   const int nenv = B->b.nenv, nu = B->hm.dm.sz.nu;
-  const int nstate = 1 + B->hm.dm.sz.nq + B->hm.dm.sz.nv;
+  const int nstate = 1 + B->hm.dm.sz.nq + B->hm.dm.sz.nv + B->hm.dm.sz.na;
   if (!B->io_ctrl) {
     B->io_ctrl = (double*)backend::dev_alloc((size_t)nenv * nu * sizeof(double));
     B->io_state = (double*)backend::dev_alloc((size_t)nenv * nstate * sizeof(double));
@@ -393,7 +394,7 @@ int mjb_step_host(mjbBatch* B, const double* ctrl, double* state_out) {
 
 int mjb_rollout_device(mjbBatch* B, int nstep, const double* d_ctrl, double* d_state) {
   if (!B || nstep < 0) return fail(MJB_ERR_ARG, "mjb_rollout_device: bad arguments");
-  const int nstate = 1 + B->hm.dm.sz.nq + B->hm.dm.sz.nv;
+  const int nstate = 1 + B->hm.dm.sz.nq + B->hm.dm.sz.nv + B->hm.dm.sz.na;
   // one fused launch per step: a persistent multi-step kernel measured ~2x slower (warps drift apart and
   // the instruction working set no longer fits the instruction caches; per-step launches re-converge them)
   std::vector<EnvGroup> gs = env_groups(B, nstep);
@@ -455,9 +456,9 @@ int mjb_set_field(mjbBatch* B, const char* name, const double* in) {
 // every fixed-size mjData array the path computes is written back under the same member name, so code
 // that reads mjData after mj_step keeps working.  Arena-allocated members (contact, efc_*) are not
 // materialised on the host; ncon / nefc and the warning counters are.
-#define MJB_MJDATA_IN(X) X(qpos, nq) X(qvel, nv) X(ctrl, nu) X(qfrc_applied, nv) X(qacc_warmstart, nv)
+#define MJB_MJDATA_IN(X) X(qpos, nq) X(qvel, nv) X(act, na) X(ctrl, nu) X(qfrc_applied, nv) X(qacc_warmstart, nv)
 #define MJB_MJDATA_OUT(X)                                                                                   \
-  X(qpos, nq) X(qvel, nv) X(qacc_warmstart, nv) X(qacc, nv)                                                 \
+  X(qpos, nq) X(qvel, nv) X(act, na) X(act_dot, na) X(qacc_warmstart, nv) X(qacc, nv)                       \
   X(xpos, 3 * nbody) X(xquat, 4 * nbody) X(xmat, 9 * nbody) X(xipos, 3 * nbody) X(ximat, 9 * nbody)         \
   X(xanchor, 3 * njnt) X(xaxis, 3 * njnt) X(geom_xpos, 3 * ngeom) X(geom_xmat, 9 * ngeom)                   \
   X(subtree_com, 3 * nbody) X(cinert, 10 * nbody) X(cdof, 6 * nv) X(crb, 10 * nbody) X(M, nC) X(qLD, nC)    \
@@ -471,8 +472,8 @@ int mjb_step_mjdata(mjbBatch* B, struct mjData_* const* dd, int nd) {
   const Sizes& S = B->hm.dm.sz;
   const int nenv = B->b.nenv;
   mjData* const* d = (mjData* const*)dd;
-  const int nq = S.nq, nv = S.nv, nu = S.nu, nbody = S.nbody, njnt = S.njnt, ngeom = S.ngeom, ntendon = S.ntendon, nC = S.nC;
-  (void)nbody; (void)njnt; (void)ngeom; (void)ntendon; (void)nC;
+  const int nq = S.nq, nv = S.nv, nu = S.nu, na = S.na, nbody = S.nbody, njnt = S.njnt, ngeom = S.ngeom, ntendon = S.ntendon, nC = S.nC;
+  (void)na; (void)nbody; (void)njnt; (void)ngeom; (void)ntendon; (void)nC;
   std::vector<double> tmp;
   {
     tmp.resize(nenv);

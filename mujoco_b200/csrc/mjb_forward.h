@@ -28,6 +28,7 @@ MJB_HD void reset_env(const Env& d, bool clear_warnings) {
   for (int i = 0; i < m.sz.nq; i++) qpos[i] = m.qpos0[i];
   for (int i = 0; i < m.sz.nv; i++) { qvel[i] = 0; ws[i] = 0; qa[i] = 0; d.qacc()[i] = 0; }
   for (int i = 0; i < m.sz.nu; i++) ctrl[i] = 0;
+  for (int i = 0; i < m.sz.na; i++) { d.act()[i] = 0; d.act_dot()[i] = 0; }
   d.time()[0] = 0;
   d.ncon()[0] = 0; d.nefc()[0] = 0; d.ne()[0] = 0; d.nf()[0] = 0; d.nl()[0] = 0; for (int k = 0; k < NISLAND; k++) d.solver_niter()[k] = 0;
   if (clear_warnings) for (int i = 0; i < NWARNING; i++) d.warning()[i] = 0;
@@ -80,12 +81,17 @@ MJB_HD void fwd_velocity(const Env& d) {
   FD av = d.actuator_velocity(), mom = d.actuator_moment();
   const bool act = !(m.opt.disableflags & DSBL_ACTUATION);
   MJB_PFOR(i, m.sz.nu) {
-    if (act) {
+    if (!act) av[i] = 0;
+    else if ((d.feat & FEAT_ACT) && m.actuator_trntype[i] == TRN_TENDON) {
+      const int t = m.actuator_trnjnt[i], adr = m.ten_J_rowadr[t], nnz = m.ten_J_rownnz[t];
+      const double g = mom[i];
+      av[i] = dot_sparse_ref(nnz, [&](int c) { return tJ[adr + c] * g; }, [&](int c) { return qvel[m.ten_J_colind[adr + c]]; });
+    } else {
       const int dof = m.jnt_dofadr[m.actuator_trnjnt[i]];
       double r = 0;
       r += mom[i] * qvel[dof];
       av[i] = r;
-    } else av[i] = 0;
+    }
   }
   MJB_PSYNC();
   com_vel(d);
@@ -93,6 +99,83 @@ MJB_HD void fwd_velocity(const Env& d) {
   reference_constraint(d);
   rne_bias(d);
   // tendon-armature bias: needs d/dt(ten_J), identically zero for fixed tendons -> no contribution
+}
+
+// muscle model (engine_util_misc.c:1049-1190): FLV gain, passive bias, activation dynamics
+MJB_HD double muscle_gain_length(double length, double lmin, double lmax) {
+  if (lmin <= length && length <= lmax) {
+    const double a = 0.5 * (lmin + 1), b = 0.5 * (1 + lmax);
+    if (length <= a) { const double x = (length - lmin) / dmax(kMinVal, a - lmin); return 0.5 * x * x; }
+    else if (length <= 1) { const double x = (1 - length) / dmax(kMinVal, 1 - a); return 1 - 0.5 * x * x; }
+    else if (length <= b) { const double x = (length - 1) / dmax(kMinVal, b - 1); return 1 - 0.5 * x * x; }
+    else { const double x = (lmax - length) / dmax(kMinVal, lmax - b); return 0.5 * x * x; }
+  }
+  return 0.0;
+}
+MJB_HD double muscle_gain(double len, double vel, const double* lengthrange, double acc0, const double* prm) {
+  double force = prm[2];
+  const double scale = prm[3], lmin = prm[4], lmax = prm[5], vmax = prm[6], fvmax = prm[8];
+  if (force < 0) force = scale / dmax(kMinVal, acc0);
+  const double L0 = (lengthrange[1] - lengthrange[0]) / dmax(kMinVal, prm[1] - prm[0]);
+  const double L = prm[0] + (len - lengthrange[0]) / dmax(kMinVal, L0);
+  const double V = vel / dmax(kMinVal, L0 * vmax);
+  const double FL = muscle_gain_length(L, lmin, lmax);
+  double FV;
+  const double y = fvmax - 1;
+  if (V <= -1) FV = 0;
+  else if (V <= 0) FV = (V + 1) * (V + 1);
+  else if (V <= y) FV = fvmax - (y - V) * (y - V) / dmax(kMinVal, y);
+  else FV = fvmax;
+  return -force * FL * FV;
+}
+MJB_HD double muscle_bias(double len, const double* lengthrange, double acc0, const double* prm) {
+  double force = prm[2];
+  const double scale = prm[3], lmax = prm[5], fpmax = prm[7];
+  if (force < 0) force = scale / dmax(kMinVal, acc0);
+  const double L0 = (lengthrange[1] - lengthrange[0]) / dmax(kMinVal, prm[1] - prm[0]);
+  const double L = prm[0] + (len - lengthrange[0]) / dmax(kMinVal, L0);
+  const double b = 0.5 * (1 + lmax);
+  if (L <= 1) return 0;
+  else if (L <= b) { const double x = (L - 1) / dmax(kMinVal, b - 1); return -force * fpmax * 0.5 * x * x; }
+  else { const double x = (L - b) / dmax(kMinVal, b - 1); return -force * fpmax * (0.5 + x); }
+}
+MJB_HD double muscle_dynamics(double ctrl, double act, const double* prm) {
+  const double ctrlclamp = dclip(ctrl, 0, 1), actclamp = dclip(act, 0, 1);
+  const double tau_act = prm[0] * (0.5 + 1.5 * actclamp), tau_deact = prm[1] / (0.5 + 1.5 * actclamp);
+  const double width = prm[2], dctrl = ctrlclamp - act;
+  double tau;
+  if (width < kMinVal) tau = dctrl > 0 ? tau_act : tau_deact;
+  else {
+    const double x = dctrl / width + 0.5;   // mju_sigmoid
+    const double sg = (x <= 0) ? 0.0 : (x >= 1) ? 1.0 : x * x * x * (3 * x * (2 * x - 5) + 10);
+    tau = tau_deact + (tau_act - tau_deact) * sg;
+  }
+  return dctrl / dmax(kMinVal, tau);
+}
+
+// mj_nextActivation (engine_support.c:706-775): activation after one timestep, clamped to actrange
+MJB_HD double next_activation(const Env& d, int u, double act, double act_dot) {
+  const DModel& m = d.m;
+  if (m.actuator_dyntype[u] == DYN_FILTEREXACT) {
+    const double tau = dmax(kMinVal, m.actuator_dynprm[kNDyn * u]);
+    act = act + act_dot * tau * (1 - exp(-m.opt.timestep / tau));
+  } else {
+    act = act + act_dot * m.opt.timestep;
+  }
+  if (m.actuator_actlimited[u]) act = dclip(act, m.actuator_actrange[2 * u], m.actuator_actrange[2 * u + 1]);
+  return act;
+}
+
+// advance activations (mj_advance, engine_forward.c:1316-1326) with the given act_dot
+MJB_HD void advance_act(const Env& d, FD act_dot) {
+  const DModel& m = d.m;
+  if (!(d.feat & FEAT_ACT) || m.sz.na == 0 || (m.opt.disableflags & DSBL_ACTUATION)) return;
+  FD act = d.act();
+  MJB_PFOR(u, m.sz.nu) {
+    const int a = m.actuator_actadr[u];
+    if (a >= 0) act[a] = next_activation(d, u, act[a], act_dot[a]);
+  }
+  MJB_PSYNC();
 }
 
 MJB_HD void fwd_actuation(const Env& d) {
@@ -124,12 +207,38 @@ MJB_HD void fwd_actuation(const Env& d) {
   }
   MJB_PSYNC();
   FD len = d.actuator_length(), vel = d.actuator_velocity(), mom = d.actuator_moment();
+  const bool stateful = (d.feat & FEAT_ACT) != 0;
+  if (stateful && m.sz.na) {   // act_dot of the stateful actuators
+    FD act = d.act(), act_dot = d.act_dot();
+    MJB_PFOR(i, nu) {
+      const int a = m.actuator_actadr[i];
+      if (a < 0) continue;
+      const double* dp = m.actuator_dynprm + kNDyn * i;
+      const int dt = m.actuator_dyntype[i];
+      if (dt == DYN_INTEGRATOR) act_dot[a] = ctrl[i];
+      else if (dt == DYN_MUSCLE) act_dot[a] = muscle_dynamics(ctrl[i], act[a], dp);
+      else act_dot[a] = (ctrl[i] - act[a]) / dmax(kMinVal, dp[0]);
+    }
+    MJB_PSYNC();
+  }
   MJB_PFOR(i, nu) {
     const double* gp = m.actuator_gainprm + kNGain * i;
     const double* bp = m.actuator_biasprm + kNGain * i;
-    double gain = (m.actuator_gaintype[i] == GAIN_FIXED) ? gp[0] : gp[0] + gp[1] * len[i] + gp[2] * vel[i];
-    double f = gain * ctrl[i];
-    double bias = (m.actuator_biastype[i] == BIAS_NONE) ? 0.0 : bp[0] + bp[1] * len[i] + bp[2] * vel[i];
+    const int gt = m.actuator_gaintype[i], bt = m.actuator_biastype[i];
+    double gain;
+    if (gt == GAIN_FIXED) gain = gp[0];
+    else if (stateful && gt == GAIN_MUSCLE) gain = muscle_gain(len[i], vel[i], m.actuator_lengthrange + 2 * i, m.actuator_acc0[i], gp);
+    else gain = gp[0] + gp[1] * len[i] + gp[2] * vel[i];
+    double in = ctrl[i];
+    if (stateful && m.actuator_actadr[i] >= 0) {
+      const int a = m.actuator_actadr[i];
+      in = m.actuator_actearly[i] ? next_activation(d, i, d.act()[a], d.act_dot()[a]) : d.act()[a];
+    }
+    double f = gain * in;
+    double bias;
+    if (bt == BIAS_NONE) bias = 0.0;
+    else if (stateful && bt == BIAS_MUSCLE) bias = muscle_bias(len[i], m.actuator_lengthrange + 2 * i, m.actuator_acc0[i], bp);
+    else bias = bp[0] + bp[1] * len[i] + bp[2] * vel[i];
     f += bias;
     if (m.actuator_forcelimited[i]) f = dclip(f, m.actuator_forcerange[2 * i], m.actuator_forcerange[2 * i + 1]);
     force[i] = f;
@@ -140,6 +249,12 @@ MJB_HD void fwd_actuation(const Env& d) {
     for (int i = 0; i < nu; i++) {
       const double s = force[i];
       if (s == 0) continue;
+      if (stateful && m.actuator_trntype[i] == TRN_TENDON) {
+        const int t = m.actuator_trnjnt[i], adr = m.ten_J_rowadr[t], nnz = m.ten_J_rownnz[t];
+        FD tJ = d.ten_J();
+        for (int c = 0; c < nnz; c++) qfa[m.ten_J_colind[adr + c]] += (tJ[adr + c] * mom[i]) * s;
+        continue;
+      }
       qfa[m.jnt_dofadr[m.actuator_trnjnt[i]]] += mom[i] * s;
     }
     for (int j = 0; j < m.sz.njnt; j++) {
@@ -211,6 +326,7 @@ MJB_HD void euler_advance(const Env& d) {
     MJB_PSYNC();
     solve_LD(d, acc, qH, d.qHDiagInv());
   }
+  advance_act(d, d.act_dot());
   MJB_PFOR(i, nv) qvel[i] += acc[i] * h;
   MJB_PSYNC();
   integrate_pos(d, d.qpos(), d.qvel(), h);
@@ -250,7 +366,11 @@ MJB_HD void implicitfast_advance(const Env& d) {
     if (live) {
       if (m.actuator_biastype[u] == BIAS_AFFINE) bv = m.actuator_biasprm[kNGain * u + 2];
       const double gv = (m.actuator_gaintype[u] == GAIN_AFFINE) ? m.actuator_gainprm[kNGain * u + 2] : 0.0;
-      if (gv != 0) bv += gv * ctrl[u];
+      if (gv != 0) {
+        const int a = (d.feat & FEAT_ACT) ? m.actuator_actadr[u] : -1;
+        if (a < 0) bv += gv * ctrl[u];
+        else bv += gv * (m.actuator_actearly[u] ? next_activation(d, u, d.act()[a], d.act_dot()[a]) : d.act()[a]);
+      }
     }
     aB[u] = bv;
   }
@@ -260,10 +380,23 @@ MJB_HD void implicitfast_advance(const Env& d) {
     for (int a = 0; a < nnz; a++) {
       const int j = m.M_colind[adr + a];
       double q = 0;
-      if (i == j) {
-        for (int u = 0; u < nu; u++) {
-          if (aB[u] != 0 && m.jnt_dofadr[m.actuator_trnjnt[u]] == i) q += mom[u] * (mom[u] * aB[u]);
+      for (int u = 0; u < nu; u++) {   // actuators in index order (mjd_actuator_vel): J'BJ of each moment row
+        if (aB[u] == 0) continue;
+        if ((d.feat & FEAT_ACT) && m.actuator_trntype[u] == TRN_TENDON) {   // moment row = ten_J row * gear
+          const int t = m.actuator_trnjnt[u], ta = m.ten_J_rowadr[t], tn = m.ten_J_rownnz[t];
+          double Ji = 0, Jj = 0;
+          bool hi = false, hj = false;
+          for (int c = 0; c < tn; c++) {
+            const int col = m.ten_J_colind[ta + c];
+            if (col == i) { Ji = tJ[ta + c] * mom[u]; hi = true; }
+            if (col == j) { Jj = tJ[ta + c] * mom[u]; hj = true; }
+          }
+          if (hi && hj) q += Jj * (Ji * aB[u]);
+        } else if (i == j && m.jnt_dofadr[m.actuator_trnjnt[u]] == i) {
+          q += mom[u] * (mom[u] * aB[u]);
         }
+      }
+      if (i == j) {
         if (passive_on) q -= d_xpoly_force(m.dof_damping_eff[i], m.dof_dampingpoly_eff + kNPoly * i, kNPoly, qvel[i], true);
       }
       for (int t = 0; t < ntendon; t++) {
@@ -288,6 +421,7 @@ MJB_HD void implicitfast_advance(const Env& d) {
   MJB_PFOR(i, nv) acc[i] = qfs[i] + qfc[i];
   MJB_PSYNC();
   solve_LD(d, acc, qH, d.qHDiagInv());
+  advance_act(d, d.act_dot());
   MJB_PFOR(i, nv) qvel[i] += acc[i] * h;
   MJB_PSYNC();
   integrate_pos(d, d.qpos(), d.qvel(), h);
@@ -589,16 +723,22 @@ MJB_HD void rk4_phase(const Env& d, int phase) {
   const double h = m.opt.timestep;
   FD scr = d.rk_scr();
   FD x0q = scr, x0v = scr + nq, xv = scr + nq + nv, F = scr + nq + 4 * nv, t0 = scr + nq + 8 * nv;
-  FD dXv = d.scr_nv(), dXa = d.scr_nv() + nv;
+  FD dXv = d.scr_nv(), dXa = d.scr_nv() + nv, dXact = d.scr_nv() + 2 * nv;
   FD qpos = d.qpos(), qvel = d.qvel(), qacc = d.qacc();
+  // activations ride along as extra state (X) with act_dot as their derivative (F)
+  const int na = (d.feat & FEAT_ACT) ? m.sz.na : 0;
+  FD x0a = scr + nq + 8 * nv + 4, Fa = x0a + na;   // Fa[4][na]
+  FD act = d.act(), act_dot = d.act_dot();
   const double A[9] = {0.5, 0, 0, 0, 0.5, 0, 0, 0, 1};
   const double B[4] = {1.0 / 6.0, 1.0 / 3.0, 1.0 / 3.0, 1.0 / 6.0};
   if (phase == 1) {
     MJB_PFOR(i, nq) x0q[i] = qpos[i];
     MJB_PFOR(i, nv) x0v[i] = qvel[i];
+    MJB_PFOR(i, na) x0a[i] = act[i];
     MJB_LANE0 t0[0] = d.time()[0];
   }
   MJB_PFOR(i, nv) F[(phase - 1) * nv + i] = qacc[i];
+  MJB_PFOR(i, na) Fa[(phase - 1) * na + i] = act_dot[i];
   MJB_PSYNC();
   auto Xv = [&](int j, int i) { return j == 0 ? x0v[i] : xv[(j - 1) * nv + i]; };
   if (phase < 4) {
@@ -610,6 +750,11 @@ MJB_HD void rk4_phase(const Env& d, int phase) {
         sa += F[j * nv + i] * a;
       }
       dXv[i] = sv; dXa[i] = sa;
+    }
+    MJB_PFOR(i, na) {
+      double sa = 0;
+      for (int j = 0; j < phase; j++) sa += Fa[j * na + i] * A[(phase - 1) * 3 + j];
+      act[i] = x0a[i] + sa * h;
     }
     MJB_PFOR(i, nq) qpos[i] = x0q[i];
     MJB_PSYNC();
@@ -631,8 +776,15 @@ MJB_HD void rk4_phase(const Env& d, int phase) {
       for (int j = 0; j < 4; j++) { sv += Xv(j, i) * B[j]; sa += F[j * nv + i] * B[j]; }
       dXv[i] = sv; dXa[i] = sa;
     }
+    MJB_PFOR(i, na) {
+      double sa = 0;
+      for (int j = 0; j < 4; j++) sa += Fa[j * na + i] * B[j];
+      dXact[i] = sa;
+      act[i] = x0a[i];
+    }
     MJB_PFOR(i, nq) qpos[i] = x0q[i];
     MJB_PSYNC();
+    if (na) advance_act(d, dXact);
     MJB_PFOR(i, nv) qvel[i] = x0v[i] + dXa[i] * h;
     integrate_pos(d, qpos, dXv, h);
     FD ws = d.qacc_warmstart();

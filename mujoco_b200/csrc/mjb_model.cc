@@ -306,7 +306,6 @@ int check_model(const mjModel* m) {
       }
     }
   }
-  if (m->na) FAIL("stateful actuators (na=%d)", (int)m->na);
   if (m->opt.disableflags & mjDSBL_SENSOR) { /* sensordata simply stays untouched */ }
   for (int i = 0; i < m->nsensor; i++) {
     int code, okind, rkind;
@@ -346,12 +345,18 @@ int check_model(const mjModel* m) {
   if (m->nout != m->nu || m->nactuator != m->nu) FAIL("multi-input/multi-output actuators");
   for (int i = 0; i < m->nactuator; i++) {
     int tt = m->actuator_trntype[i];
-    if (tt != mjTRN_JOINT && tt != mjTRN_JOINTINPARENT) FAIL("actuator %d: non-joint transmission", i);
-    int jt = m->jnt_type[m->actuator_trnid[2 * i]];
-    if (jt != mjJNT_HINGE && jt != mjJNT_SLIDE) FAIL("actuator %d on ball/free joint", i);
-    if (m->actuator_dyntype[i] != mjDYN_NONE) FAIL("actuator %d: activation dynamics", i);
-    if (m->actuator_gaintype[i] != mjGAIN_FIXED && m->actuator_gaintype[i] != mjGAIN_AFFINE) FAIL("actuator %d: gain type", i);
-    if (m->actuator_biastype[i] != mjBIAS_NONE && m->actuator_biastype[i] != mjBIAS_AFFINE) FAIL("actuator %d: bias type", i);
+    if (tt != mjTRN_JOINT && tt != mjTRN_JOINTINPARENT && tt != mjTRN_TENDON) FAIL("actuator %d: transmission other than joint / tendon", i);
+    if (tt != mjTRN_TENDON) {
+      int jt = m->jnt_type[m->actuator_trnid[2 * i]];
+      if (jt != mjJNT_HINGE && jt != mjJNT_SLIDE) FAIL("actuator %d on ball/free joint", i);
+    }
+    int dt = m->actuator_dyntype[i], gt = m->actuator_gaintype[i], bt = m->actuator_biastype[i];
+    if (dt != mjDYN_NONE && dt != mjDYN_INTEGRATOR && dt != mjDYN_FILTER && dt != mjDYN_FILTEREXACT && dt != mjDYN_MUSCLE)
+      FAIL("actuator %d: dynamics type (none, integrator, filter, filterexact and muscle are built)", i);
+    if (m->actuator_actnum[i] != (dt == mjDYN_NONE ? 0 : 1)) FAIL("actuator %d: activation block of %d states", i, (int)m->actuator_actnum[i]);
+    if (gt != mjGAIN_FIXED && gt != mjGAIN_AFFINE && gt != mjGAIN_MUSCLE) FAIL("actuator %d: gain type", i);
+    if (bt != mjBIAS_NONE && bt != mjBIAS_AFFINE && bt != mjBIAS_MUSCLE) FAIL("actuator %d: bias type", i);
+    if (gt == mjGAIN_MUSCLE && m->opt.integrator == mjINT_IMPLICITFAST) FAIL("actuator %d: muscle gain with implicitfast (velocity derivative of the FLV curve)", i);
     if (m->actuator_ctrlnum[i] != 1 || m->actuator_outnum[i] != 1 || m->actuator_ctrladr[i] != i || m->actuator_outadr[i] != i)
       FAIL("actuator %d: non-scalar control block", i);
     if (m->actuator_delay[i] != 0) FAIL("actuator %d: delay", i);
@@ -398,6 +403,10 @@ int build_host_model(const mjModel* m, int nconmax, int njmax, HostModel* out) {
   DModel& D = out->dm;
   memset(&D, 0, sizeof(D));
   Sizes& S = D.sz;
+  S.actfeat = 0;
+  for (int i = 0; i < m->nu; i++)
+    if (m->actuator_dyntype[i] != mjDYN_NONE || m->actuator_trntype[i] == mjTRN_TENDON || m->actuator_gaintype[i] == mjGAIN_MUSCLE ||
+        m->actuator_biastype[i] == mjBIAS_MUSCLE) S.actfeat = 1;
   S.nq = m->nq; S.nv = m->nv; S.nu = m->nu; S.na = m->na; S.nbody = m->nbody; S.njnt = m->njnt;
   S.ngeom = m->ngeom; S.ntendon = m->ntendon; S.nwrap = m->nwrap; S.nJten = m->nJten; S.nC = m->nC;
   S.ntree = m->ntree;
@@ -497,6 +506,19 @@ int build_host_model(const mjModel* m, int nconmax, int njmax, HostModel* out) {
   B.addI(&D.actuator_biastype, m->actuator_biastype, m->nu);
   B.addI(&D.actuator_ctrllimited, m->actuator_ctrllimited, m->nu);
   B.addI(&D.actuator_forcelimited, m->actuator_forcelimited, m->nu);
+  {
+    std::vector<int> tt(m->nu), al(m->nu), ae(m->nu);
+    for (int i = 0; i < m->nu; i++) {
+      tt[i] = (m->actuator_trntype[i] == mjTRN_TENDON) ? TRN_TENDON : TRN_JOINT;
+      al[i] = m->actuator_actlimited[i];
+      ae[i] = m->actuator_actearly[i];
+    }
+    B.addI(&D.actuator_trntype, tt.data(), m->nu);
+    B.addI(&D.actuator_dyntype, m->actuator_dyntype, m->nu);
+    B.addI(&D.actuator_actadr, m->actuator_actadr, m->nu);
+    B.addI(&D.actuator_actlimited, al.data(), m->nu);
+    B.addI(&D.actuator_actearly, ae.data(), m->nu);
+  }
 
   B.addD(&D.qpos0, m->qpos0, m->nq);
   B.addD(&D.qpos_spring, m->qpos_spring, m->nq);
@@ -583,6 +605,14 @@ int build_host_model(const mjModel* m, int nconmax, int njmax, HostModel* out) {
   }
   B.addD(&D.actuator_ctrlrange, m->actuator_ctrlrange, 2 * m->nu);
   B.addD(&D.actuator_forcerange, m->actuator_forcerange, 2 * m->nu);
+  {
+    std::vector<double> dp(kNDyn * (size_t)m->nu);
+    for (int i = 0; i < m->nu; i++) for (int k = 0; k < kNDyn; k++) dp[kNDyn * i + k] = m->actuator_dynprm[mjNDYN * i + k];
+    B.addD(&D.actuator_dynprm, dp.data(), dp.size());
+  }
+  B.addD(&D.actuator_actrange, m->actuator_actrange, 2 * m->nu);
+  B.addD(&D.actuator_lengthrange, m->actuator_lengthrange, 2 * m->nu);
+  B.addD(&D.actuator_acc0, m->actuator_acc0, m->nu);
   B.addD(&D.sensor_cutoff, m->sensor_cutoff, m->nsensor);
   {
     std::vector<double> ed(kNEqData * (size_t)m->neq);

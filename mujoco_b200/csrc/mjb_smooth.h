@@ -229,14 +229,17 @@ MJB_HD void tendon(const Env& d) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// joint transmissions (hinge / slide): actuator_length and the single moment entry per actuator
+// transmissions (mj_transmission, engine_core_smooth.c:1380-1480): scalar joints — actuator_length and the
+// single moment entry; fixed tendons — length = ten_length * gear, moment row = ten_J row * gear (the row
+// values are re-formed as ten_J * gear where they are used, actuator_moment keeps the gear)
 MJB_HD void transmission(const Env& d) {
   const DModel& m = d.m;
   FD len = d.actuator_length(), mom = d.actuator_moment(), qpos = d.qpos();
   MJB_PFOR(i, m.sz.nu) {
     const int j = m.actuator_trnjnt[i];
     const double g = m.actuator_gear0[i];
-    len[i] = qpos[m.jnt_qposadr[j]] * g;
+    if ((d.feat & FEAT_ACT) && m.actuator_trntype[i] == TRN_TENDON) len[i] = d.ten_length()[j] * g;
+    else len[i] = qpos[m.jnt_qposadr[j]] * g;
     mom[i] = g;
   }
   MJB_PSYNC();

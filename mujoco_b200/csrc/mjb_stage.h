@@ -91,7 +91,7 @@ MJB_HD void run_set_control(const DModel& m, const Batch& b, int e, const double
   if (spec & (1u << 7)) { FD q = d.qfrc_applied(); for (int i = 0; i < m.sz.nv; i++) q[i] = src[k++]; }
 }
 
-// state [nenv][nstep][nstate] = (time, qpos, qvel)  (mjSTATE_FULLPHYSICS with na == 0)
+// state [nenv][nstep][nstate] = (time, qpos, qvel, act)  (mjSTATE_FULLPHYSICS)
 MJB_HD void run_get_state(const DModel& m, const Batch& b, int e, double* state, int nstep, int t, int nstate) {
   Env d(m, b, e);
   double* dst = state + ((size_t)e * nstep + t) * nstate;
@@ -100,6 +100,7 @@ MJB_HD void run_get_state(const DModel& m, const Batch& b, int e, double* state,
   FD qp = d.qpos(), qv = d.qvel();
   for (int i = 0; i < m.sz.nq; i++) dst[k++] = qp[i];
   for (int i = 0; i < m.sz.nv; i++) dst[k++] = qv[i];
+  for (int i = 0; i < m.sz.na; i++) dst[k++] = d.act()[i];
 }
 
 // sensordata [nenv][nstep][nsensordata]; a warned env repeats its last values (the reference pads likewise)
@@ -125,6 +126,7 @@ MJB_HD void run_get_state_native(const DModel& m, const Batch& b, int e, double*
   FD qp = d.qpos(), qv = d.qvel();
   for (int i = 0; i < m.sz.nq; i++) dst[(size_t)(k++) * b.stride] = qp[i];
   for (int i = 0; i < m.sz.nv; i++) dst[(size_t)(k++) * b.stride] = qv[i];
+  for (int i = 0; i < m.sz.na; i++) dst[(size_t)(k++) * b.stride] = d.act()[i];
 }
 
 // dense [nenv][cnt] <-> field of either layout; idx enumerates (env, elem)

@@ -31,7 +31,7 @@ enum { STATE_SATISFIED = 0, STATE_QUADRATIC = 1, STATE_LINEARNEG = 2, STATE_LINE
 enum { WARN_INERTIA = 0, WARN_CONTACTFULL = 1, WARN_CNSTRFULL = 2, WARN_BADQPOS = 3,
        WARN_BADQVEL = 4, WARN_BADQACC = 5, WARN_BADCTRL = 6, WARN_VGEOMFULL = 7, NWARNING = 8 };
 enum { NISLAND = 20 };
-enum { FEAT_SENSOR = 1, FEAT_EQUALITY = 2, FEAT_ISLAND = 4, FEAT_IMPLICITFAST = 8, FEAT_ALL = 15 };
+enum { FEAT_SENSOR = 1, FEAT_EQUALITY = 2, FEAT_ISLAND = 4, FEAT_IMPLICITFAST = 8, FEAT_ACT = 16, FEAT_ALL = 31 };   // FEAT_ACT: stateful actuators (act), tendon transmissions, muscles
 enum { EQ_JOINT = 0, EQ_TENDON = 1, EQ_CONNECT = 2, EQ_WELD = 3 };   // supported equality kinds (body semantics)
 constexpr int kNEqData = 11;            // eq_data values per equality (mjNEQDATA): polycoef / anchors, relpose, torquescale
 // sensors of the path (engine_sensor.c); internal codes, translated from mjtSensor by the host
@@ -46,8 +46,10 @@ enum { SOL_PGS = 0, SOL_CG = 1, SOL_NEWTON = 2 };                               
 enum { INT_EULER = 0, INT_RK4 = 1, INT_IMPLICIT = 2, INT_IMPLICITFAST = 3 };             // :181-184
 enum { SAMEFRAME_NONE = 0, SAMEFRAME_BODY = 1, SAMEFRAME_INERTIA = 2, SAMEFRAME_BODYROT = 3,
        SAMEFRAME_INERTIAROT = 4 };                                                      // :457-461
-enum { GAIN_FIXED = 0, GAIN_AFFINE = 1 };                                                // :256-257
-enum { BIAS_NONE = 0, BIAS_AFFINE = 1 };                                                 // :267-268
+enum { GAIN_FIXED = 0, GAIN_AFFINE = 1, GAIN_MUSCLE = 2 };                               // :256-258
+enum { BIAS_NONE = 0, BIAS_AFFINE = 1, BIAS_MUSCLE = 2 };                                // :267-269
+enum { DYN_NONE = 0, DYN_INTEGRATOR = 1, DYN_FILTER = 2, DYN_FILTEREXACT = 3, DYN_MUSCLE = 4 };   // :244-248
+enum { TRN_JOINT = 0, TRN_TENDON = 1 };   // transmissions built (mjTRN_JOINT / JOINTINPARENT on scalar joints, mjTRN_TENDON)
 enum { DSBL_CONSTRAINT = 1 << 0, DSBL_EQUALITY = 1 << 1, DSBL_FRICTIONLOSS = 1 << 2, DSBL_LIMIT = 1 << 3,
        DSBL_CONTACT = 1 << 4, DSBL_SPRING = 1 << 5, DSBL_DAMPER = 1 << 6, DSBL_GRAVITY = 1 << 7,
        DSBL_CLAMPCTRL = 1 << 8, DSBL_WARMSTART = 1 << 9, DSBL_FILTERPARENT = 1 << 10,
@@ -55,12 +57,14 @@ enum { DSBL_CONSTRAINT = 1 << 0, DSBL_EQUALITY = 1 << 1, DSBL_FRICTIONLOSS = 1 <
        DSBL_AUTORESET = 1 << 16, DSBL_ISLAND = 1 << 18, DSBL_SENSOR = 1 << 13 };                                // :54-73
 enum { LIM_HINGE = 0, LIM_BALL = 1, LIM_TENDON = 2 };   // kinds of limit candidates (host-built table)
 constexpr int kNPoly = 2;   // mjNPOLY (include/mujoco/mjmodel.h:44)
-constexpr int kNGain = 3;   // leading gain/bias parameters used by the supported actuator family
+constexpr int kNGain = 9;   // leading gain/bias parameters kept (affine: 3, muscle: 9)
+constexpr int kNDyn = 3;    // leading dynprm values kept (filter tau; muscle tau_act, tau_deact, smoothing width)
 
 // ---- model sizes and options --------------------------------------------------------------------
 struct Sizes {
   int nq, nv, nu, na, nbody, njnt, ngeom, ntendon, nwrap, nJten, nC, ntree;
   int nsensor, nsensordata, nsite, neq;
+  int actfeat;   // 1 when an actuator is stateful, drives a tendon or is a muscle (FEAT_ACT code paths)
   int rnepost;   // 1 when a sensor needs mj_rnePostConstraint (cacc / cfrc_int / cfrc_ext are allocated then)
   int npair;     // static candidate geom pairs (host-built, reference order)
   int nconmax;   // per-env contact cap
@@ -95,7 +99,8 @@ struct Options {
   X(tendon_adr) X(tendon_num) X(tendon_limited) X(wrap_type) X(wrap_objid)                   \
   X(ten_J_rownnz) X(ten_J_rowadr) X(ten_J_colind)                                            \
   X(actuator_trnjnt) X(actuator_gaintype) X(actuator_biastype) X(actuator_ctrllimited)       \
-  X(actuator_forcelimited)                                                                   \
+  X(actuator_forcelimited) X(actuator_trntype) X(actuator_dyntype) X(actuator_actadr)        \
+  X(actuator_actlimited) X(actuator_actearly)                                                \
   X(pair_geom1) X(pair_geom2) X(pair_dim)                                                     \
   X(lvl_adr) X(lvl_body) X(child_adr) X(child_id)                                             \
   X(dlvl_adr) X(dlvl_dof) X(mt_adr) X(mt_dof) X(mt_qadr)                                      \
@@ -117,7 +122,7 @@ struct Options {
   X(tendon_invweight0) X(tendon_stiffness) X(tendon_stiffnesspoly) X(tendon_damping_eff)     \
   X(tendon_dampingpoly_eff) X(tendon_lengthspring) X(tendon_armature_eff)                    \
   X(actuator_gear0) X(actuator_gainprm) X(actuator_biasprm) X(actuator_ctrlrange)            \
-  X(actuator_forcerange)                                                                     \
+  X(actuator_forcerange) X(actuator_dynprm) X(actuator_actrange) X(actuator_lengthrange) X(actuator_acc0) \
   X(pair_margin) X(pair_includemargin) X(pair_solref) X(pair_solimp) X(pair_friction) X(sensor_cutoff) X(site_pos) X(site_quat)            \
   X(eq_data) X(eq_solref) X(eq_solimp) X(tendon_length0)
 
@@ -135,7 +140,7 @@ struct DModel {
 // ---- batch data fields (per environment), sizes in elements -------------------------------------
 // HOT doubles: staged in shared memory by the fused warp-per-env kernel
 #define MJB_DATA_DBL_FIELDS(X, S)                                                            \
-  X(time, 1) X(qpos, S.nq) X(qvel, S.nv) X(ctrl, S.nu) X(qacc_warmstart, S.nv)                \
+  X(time, 1) X(qpos, S.nq) X(qvel, S.nv) X(act, S.na) X(act_dot, S.na) X(ctrl, S.nu) X(qacc_warmstart, S.nv)  \
   X(qfrc_applied, S.nv)                                                                      \
   X(xpos, 3 * S.nbody) X(xquat, 4 * S.nbody) X(xmat, 9 * S.nbody) X(xipos, 3 * S.nbody)      \
   X(ximat, 9 * S.nbody) X(xanchor, 3 * S.njnt) X(xaxis, 3 * S.njnt)                          \
@@ -156,7 +161,7 @@ struct DModel {
   X(efc_D, S.njmax) X(efc_R, S.njmax) X(efc_vel, S.njmax) X(efc_aref, S.njmax)               \
   X(efc_b, S.njmax) X(efc_force, S.njmax)                                                    \
   X(scr_body, 12 * S.nbody) X(scr_nv, 8 * S.nv) X(scr_efc, 6 * S.njmax)                         \
-  X(nwt_nv, 6 * S.nv) X(nwt_efc, 6 * S.njmax) X(rk_scr, S.nq + 8 * S.nv + 4) X(sensordata, S.nsensordata)  \
+  X(nwt_nv, 6 * S.nv) X(nwt_efc, 6 * S.njmax) X(rk_scr, S.nq + 8 * S.nv + 8 * S.na + 4) X(sensordata, S.nsensordata)  \
   X(site_xpos, 3 * S.nsite) X(site_xmat, 9 * S.nsite)                                        \
   X(cacc, 6 * S.nbody * S.rnepost) X(cfrc_int, 6 * S.nbody * S.rnepost) X(cfrc_ext, 6 * S.nbody * S.rnepost)
 

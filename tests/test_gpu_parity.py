@@ -240,3 +240,27 @@ def test_equality_constraints_vs_oracle(model, solver):
     for t in (0, 40, 99):
         compare_forward(b, o, ref[:, t, :], ctrl[:, t, :], rtol=RTOL_TIGHT, check_dual=(solver == mb.SOLVER_PGS))
     assert (b.field("ne")[:, 0] > 0).all()
+
+
+@pytest.mark.parametrize("model,integrator", [("ant_act", mb.INT_EULER), ("ant_act", mb.INT_RK4),
+                                              ("ant_act_nomuscle", mb.INT_IMPLICITFAST)])
+def test_stateful_actuators_vs_oracle(model, integrator):
+    """activation state (filter / filterexact / integrator / muscle dynamics), muscles and tendon transmissions
+    on the device (models/ant_act*.xml); the rollout state carries act"""
+    assert available()
+    path = os.path.join(ROOT, "models", model + ".mjb")
+    nenv, nstep = 12, 100
+    m, b, o = make_pair(path, mb.SOLVER_NEWTON, nenv=nenv, integrator=integrator)
+    na, nq, nv = o.size("na"), o.size("nq"), o.size("nv")
+    assert b.state_size() == 1 + nq + nv + na
+    s0 = perturbed_states(o, nenv, seed=14, height=[0.35, 0.5, 0.75], qvel_std=0.3, qpos_std=0.05)
+    s0[:, 1 + nq + nv:] = np.random.default_rng(3).uniform(-0.3, 0.8, (nenv, na))
+    ctrl = np.random.default_rng(15).uniform(-1, 1, (nenv, nstep, o.size("nu")))
+    out = b.rollout(s0, ctrl)
+    ref, stats, _ = o.rollout(s0, ctrl, nthread=os.cpu_count() or 1)
+    assert stats[:, 3].sum() == 0 and (b.warnings() == 0).all()
+    err = (np.abs(out - ref) / np.maximum(1.0, np.abs(ref).max(axis=(0, 1)))).max(axis=(0, 2))
+    print("%s rollout rel err: step 30 %.3e, step 100 %.3e" % (model, err[:30].max(), err.max()))
+    assert err[:30].max() < RTOL_TIGHT and err.max() < RTOL_TRAJ
+    for t in (0, 50, 99):
+        compare_forward(b, o, ref[:, t, :], ctrl[:, t, :], rtol=RTOL_TIGHT, check_dual=False)

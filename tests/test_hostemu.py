@@ -205,15 +205,17 @@ def test_unsupported_models_are_refused():
         mb.Batch(m, 1)
 
 
-def test_mjdata_bridge_matches_mj_step():
+@pytest.mark.parametrize("model", ["humanoid", "ant_act"])
+def test_mjdata_bridge_matches_mj_step(model):
     """mjb_step_mjdata: the reference's per-mjData loop `for k: mj_step(m, d[k])` as one call.  Two sets
     of the reference's own mjData objects start identical; one is stepped by the reference engine, the other
     through the bridge; every fixed-size member the path computes must then be identical"""
     from oracle_util import Oracle
     nenv, nstep = 3, 25
-    ref = [Oracle(HUMANOID) for _ in range(nenv)]
-    ours = [Oracle(HUMANOID) for _ in range(nenv)]
-    m = mb.Model(HUMANOID, library=hostemu_lib())
+    path = os.path.join(ROOT, "models", model + ".mjb")
+    ref = [Oracle(path) for _ in range(nenv)]
+    ours = [Oracle(path) for _ in range(nenv)]
+    m = mb.Model(path, library=hostemu_lib())
     m.set_option("solver", mb.SOLVER_NEWTON)
     b = mb.Batch(m, nenv, nconmax=64, njmax=200)
     states = perturbed_states(ref[0], nenv, seed=33, height=[0.3, 0.5, 0.9], qvel_std=0.4, qpos_std=0.1)
@@ -226,6 +228,8 @@ def test_mjdata_bridge_matches_mj_step():
     fields = ["qpos", "qvel", "qacc", "qacc_warmstart", "xpos", "xquat", "xmat", "xipos", "geom_xpos", "geom_xmat",
               "subtree_com", "cinert", "cdof", "crb", "M", "qLD", "qLDiagInv", "cvel", "cdof_dot", "qfrc_bias",
               "qfrc_passive", "actuator_force", "qfrc_actuator", "qfrc_smooth", "qacc_smooth", "qfrc_constraint"]
+    if ref[0].size("na"):      # stateful actuators: act goes in and comes back, act_dot comes back
+        fields += ["act", "act_dot", "actuator_length", "actuator_velocity"]
     for t in range(nstep):
         for e in range(nenv):
             c = rng.uniform(-1, 1, ref[e].size("nu"))
@@ -383,3 +387,28 @@ def test_weld_equality_bit_exact(solver):
             oe.step()
             assert np.array_equal(out[e, t], oe.get_state()), (e, t)
             assert np.array_equal(sens[e, t], np.array(oe.dfield("sensordata"))), (e, t)
+
+
+@pytest.mark.parametrize("model,integrator", [("ant_act", mb.INT_EULER), ("ant_act", mb.INT_RK4),
+                                              ("ant_act_nomuscle", mb.INT_EULER), ("ant_act_nomuscle", mb.INT_RK4),
+                                              ("ant_act_nomuscle", mb.INT_IMPLICITFAST)])
+@pytest.mark.parametrize("solver", [mb.SOLVER_NEWTON, mb.SOLVER_PGS])
+def test_stateful_actuators_bit_exact(model, integrator, solver):
+    """activation state `act` (part of mjSTATE_FULLPHYSICS): filter, filterexact (exact exponential update),
+    integrator with actrange clamp, actearly, muscles (FLV gain, passive bias, activation dynamics), and
+    tendon transmissions (moment row = ten_J row * gear) - models/ant_act*.xml; the state vector returned by
+    rollout carries act, RK4 integrates it with act_dot, implicitfast differentiates gain*act"""
+    path = os.path.join(ROOT, "models", model + ".mjb")
+    nenv, nstep = 6, 120
+    m, b, o = make_pair(path, solver, library=hostemu_lib(), nenv=nenv, integrator=integrator)
+    na, nq, nv = o.size("na"), o.size("nq"), o.size("nv")
+    assert na > 0 and b.state_size() == 1 + nq + nv + na
+    s0 = perturbed_states(o, nenv, seed=14, height=[0.35, 0.5, 0.75], qvel_std=0.3, qpos_std=0.05)
+    s0[:, 1 + nq + nv:] = np.random.default_rng(3).uniform(-0.3, 0.8, (nenv, na))
+    ctrl = np.random.default_rng(15).uniform(-1, 1, (nenv, nstep, o.size("nu")))
+    compare_forward(b, o, s0, ctrl[:, 0], rtol=0, exact=True, check_dual=(solver == mb.SOLVER_PGS))
+    out = b.rollout(s0, ctrl)
+    ref, stats, _ = o.rollout(s0, ctrl, nthread=4)
+    assert stats[:, 3].sum() == 0
+    assert np.array_equal(out, ref)
+    assert np.abs(out[:, -1, 1 + nq + nv:]).max() > 0
