@@ -272,6 +272,13 @@ MJB_HD void make_constraint(const Env& d) {
     const int i = m.fl_dof[r_];
     FD row = J + (long)r * nv;
     for (int c = 0; c < nv; c++) row[c] = 0;
+    if (i < 0) {   // tendon with dry friction: the tendon's Jacobian row
+      const int t = -i - 1, adr = m.ten_J_rowadr[t], nnz = m.ten_J_rownnz[t];
+      FD tJ = d.ten_J();
+      for (int a = 0; a < nnz; a++) row[m.ten_J_colind[adr + a]] = tJ[adr + a];
+      epos[r] = 0; emargin[r] = 0; efl[r] = m.tendon_frictionloss[t]; type[r] = CNSTR_FRICTION_TENDON; id[r] = t;
+      continue;
+    }
     row[i] = 1;
     epos[r] = 0; emargin[r] = 0; efl[r] = m.dof_frictionloss[i]; type[r] = CNSTR_FRICTION_DOF; id[r] = i;
   }
@@ -357,7 +364,7 @@ MJB_HD void make_constraint(const Env& d) {
     }
     else if (t == CNSTR_FRICTION_DOF) dA[r] = m.dof_invweight0[k];
     else if (t == CNSTR_LIMIT_JOINT) dA[r] = m.dof_invweight0[m.jnt_dofadr[k]];
-    else if (t == CNSTR_LIMIT_TENDON) dA[r] = m.tendon_invweight0[k];
+    else if (t == CNSTR_LIMIT_TENDON || t == CNSTR_FRICTION_TENDON) dA[r] = m.tendon_invweight0[k];
     else {
       const int b1 = m.geom_bodyid[cg1[k]], b2 = m.geom_bodyid[cg2[k]];
       double tran = 0, rot = 0;
@@ -381,6 +388,7 @@ MJB_HD void make_constraint(const Env& d) {
     if (t == CNSTR_EQUALITY) { for (int j = 0; j < 2; j++) solref[j] = m.eq_solref[2 * k + j]; for (int j = 0; j < 5; j++) solimp[j] = m.eq_solimp[5 * k + j]; }
     else if (t == CNSTR_FRICTION_DOF) { for (int j = 0; j < 2; j++) solref[j] = m.dof_solref[2 * k + j]; for (int j = 0; j < 5; j++) solimp[j] = m.dof_solimp[5 * k + j]; }
     else if (t == CNSTR_LIMIT_JOINT) { for (int j = 0; j < 2; j++) solref[j] = m.jnt_solref[2 * k + j]; for (int j = 0; j < 5; j++) solimp[j] = m.jnt_solimp[5 * k + j]; }
+    else if (t == CNSTR_FRICTION_TENDON) { for (int j = 0; j < 2; j++) solref[j] = m.tendon_solref_fri[2 * k + j]; for (int j = 0; j < 5; j++) solimp[j] = m.tendon_solimp_fri[5 * k + j]; }
     else if (t == CNSTR_LIMIT_TENDON) { for (int j = 0; j < 2; j++) solref[j] = m.tendon_solref_lim[2 * k + j]; for (int j = 0; j < 5; j++) solimp[j] = m.tendon_solimp_lim[5 * k + j]; }
     else {
       for (int j = 0; j < 2; j++) solref[j] = d.con_solref()[2 * k + j];
@@ -403,7 +411,7 @@ MJB_HD void make_constraint(const Env& d) {
     impedance(solimp, ipos, imargin, imp, impP);
     R[r] = dmax(kMinVal, (1 - imp) * dA[r] / imp);
     double K, Bv;
-    if (t == CNSTR_FRICTION_DOF) K = 0;
+    if (t == CNSTR_FRICTION_DOF || t == CNSTR_FRICTION_TENDON) K = 0;
     else if (solref[0] > 0) K = 1 / dmax(kMinVal, solimp[1] * solimp[1] * solref[0] * solref[0] * solref[1] * solref[1]);
     else K = -solref[0] / dmax(kMinVal, solimp[1] * solimp[1]);
     if (solref[1] > 0) Bv = 2 / dmax(kMinVal, solimp[1] * solref[0]);

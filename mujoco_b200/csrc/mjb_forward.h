@@ -240,8 +240,28 @@ MJB_HD void fwd_actuation(const Env& d) {
     else if (stateful && bt == BIAS_MUSCLE) bias = muscle_bias(len[i], m.actuator_lengthrange + 2 * i, m.actuator_acc0[i], bp);
     else bias = bp[0] + bp[1] * len[i] + bp[2] * vel[i];
     f += bias;
-    if (m.actuator_forcelimited[i]) f = dclip(f, m.actuator_forcerange[2 * i], m.actuator_forcerange[2 * i + 1]);
     force[i] = f;
+  }
+  if (stateful && m.sz.ntendon) {   // tendons with a limit on their total actuator force (engine_forward.c:955-985)
+    MJB_PSYNC();
+    MJB_LANE0 {
+      for (int t = 0; t < m.sz.ntendon; t++) {
+        if (!m.tendon_actfrclimited[t]) continue;
+        double total = 0;
+        for (int i = 0; i < nu; i++) if (m.actuator_trntype[i] == TRN_TENDON && m.actuator_trnjnt[i] == t) total += force[i];
+        if (!total) continue;
+        const double lo = m.tendon_actfrcrange[2 * t], hi = m.tendon_actfrcrange[2 * t + 1];
+        for (int i = 0; i < nu; i++) {
+          if (m.actuator_trntype[i] != TRN_TENDON || m.actuator_trnjnt[i] != t) continue;
+          if (total < lo) force[i] *= lo / total;
+          else if (total > hi) force[i] *= hi / total;
+        }
+      }
+    }
+    MJB_PSYNC();
+  }
+  MJB_PFOR(i, nu) {
+    if (m.actuator_forcelimited[i]) force[i] = dclip(force[i], m.actuator_forcerange[2 * i], m.actuator_forcerange[2 * i + 1]);
   }
   MJB_PFOR(i, nv) qfa[i] = 0;
   MJB_PSYNC();

@@ -339,8 +339,6 @@ int check_model(const mjModel* m) {
   }
   for (int i = 0; i < m->ntendon; i++) {
     if (m->wrap_type[m->tendon_adr[i]] != mjWRAP_JOINT) FAIL("spatial tendons");
-    if (m->tendon_frictionloss[i] != 0) FAIL("tendon frictionloss");
-    if (m->tendon_actfrclimited[i]) FAIL("tendon actuator force limits");
   }
   if (m->nout != m->nu || m->nactuator != m->nu) FAIL("multi-input/multi-output actuators");
   for (int i = 0; i < m->nactuator; i++) {
@@ -518,6 +516,9 @@ int build_host_model(const mjModel* m, int nconmax, int njmax, HostModel* out) {
     B.addI(&D.actuator_actadr, m->actuator_actadr, m->nu);
     B.addI(&D.actuator_actlimited, al.data(), m->nu);
     B.addI(&D.actuator_actearly, ae.data(), m->nu);
+    std::vector<int> tl(m->ntendon);
+    for (int i = 0; i < m->ntendon; i++) tl[i] = m->tendon_actfrclimited[i];
+    B.addI(&D.tendon_actfrclimited, tl.data(), m->ntendon);
   }
 
   B.addD(&D.qpos0, m->qpos0, m->nq);
@@ -613,6 +614,10 @@ int build_host_model(const mjModel* m, int nconmax, int njmax, HostModel* out) {
   B.addD(&D.actuator_actrange, m->actuator_actrange, 2 * m->nu);
   B.addD(&D.actuator_lengthrange, m->actuator_lengthrange, 2 * m->nu);
   B.addD(&D.actuator_acc0, m->actuator_acc0, m->nu);
+  B.addD(&D.tendon_frictionloss, m->tendon_frictionloss, m->ntendon);
+  B.addD(&D.tendon_solref_fri, m->tendon_solref_fri, mjNREF * m->ntendon);
+  B.addD(&D.tendon_solimp_fri, m->tendon_solimp_fri, mjNIMP * m->ntendon);
+  B.addD(&D.tendon_actfrcrange, m->tendon_actfrcrange, 2 * m->ntendon);
   B.addD(&D.sensor_cutoff, m->sensor_cutoff, m->nsensor);
   {
     std::vector<double> ed(kNEqData * (size_t)m->neq);
@@ -629,6 +634,7 @@ int build_host_model(const mjModel* m, int nconmax, int njmax, HostModel* out) {
   for (int i = 0; i < m->njnt; i++) has_lim |= m->jnt_limited[i];
   for (int i = 0; i < m->ntendon; i++) has_lim |= m->tendon_limited[i];
   for (int i = 0; i < m->nv; i++) has_fl |= (m->dof_frictionloss[i] != 0);
+  for (int i = 0; i < m->ntendon; i++) has_fl |= (m->tendon_frictionloss[i] > 0);
   O.has_limits = has_lim; O.has_frictionloss = has_fl;
 
   // ---- static candidate geom pairs, in the order the reference emits their contacts -----------
@@ -806,6 +812,7 @@ int build_host_model(const mjModel* m, int nconmax, int njmax, HostModel* out) {
       for (int side = -1; side <= 1; side += 2) { lk.push_back(LIM_TENDON); lid.push_back(i); ls.push_back(side); }
     }
     for (int i = 0; i < nv; i++) if (m->dof_frictionloss[i] != 0) fl.push_back(i);
+    for (int i = 0; i < m->ntendon; i++) if (m->tendon_frictionloss[i] > 0) fl.push_back(-(i + 1));   // engine_core_constraint.c:1323
     S.nlim = (int)lk.size();
     S.nfl = (int)fl.size();
     B.addI(&D.lim_kind, lk.data(), lk.size());

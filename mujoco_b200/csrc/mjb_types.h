@@ -72,7 +72,7 @@ struct Sizes {
   int nlevel;    // depth levels of the body tree (level 0 = world)
   int ndlevel;   // depth levels of the dof tree
   int nlim;      // limit candidates (joint sides, ball joints, tendon sides) in row order
-  int nfl;       // dofs with frictionloss, in row order
+  int nfl;       // dofs, then tendons, with frictionloss, in row order (fl_dof: dof index, or -(tendon+1))
 };
 
 struct Options {
@@ -100,7 +100,7 @@ struct Options {
   X(ten_J_rownnz) X(ten_J_rowadr) X(ten_J_colind)                                            \
   X(actuator_trnjnt) X(actuator_gaintype) X(actuator_biastype) X(actuator_ctrllimited)       \
   X(actuator_forcelimited) X(actuator_trntype) X(actuator_dyntype) X(actuator_actadr)        \
-  X(actuator_actlimited) X(actuator_actearly)                                                \
+  X(actuator_actlimited) X(actuator_actearly) X(tendon_actfrclimited)                        \
   X(pair_geom1) X(pair_geom2) X(pair_dim)                                                     \
   X(lvl_adr) X(lvl_body) X(child_adr) X(child_id)                                             \
   X(dlvl_adr) X(dlvl_dof) X(mt_adr) X(mt_dof) X(mt_qadr)                                      \
@@ -123,6 +123,7 @@ struct Options {
   X(tendon_dampingpoly_eff) X(tendon_lengthspring) X(tendon_armature_eff)                    \
   X(actuator_gear0) X(actuator_gainprm) X(actuator_biasprm) X(actuator_ctrlrange)            \
   X(actuator_forcerange) X(actuator_dynprm) X(actuator_actrange) X(actuator_lengthrange) X(actuator_acc0) \
+  X(tendon_frictionloss) X(tendon_solref_fri) X(tendon_solimp_fri) X(tendon_actfrcrange)      \
   X(pair_margin) X(pair_includemargin) X(pair_solref) X(pair_solimp) X(pair_friction) X(sensor_cutoff) X(site_pos) X(site_quat)            \
   X(eq_data) X(eq_solref) X(eq_solimp) X(tendon_length0)
 
