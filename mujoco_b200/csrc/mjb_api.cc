@@ -183,7 +183,10 @@ static int state_segments(const mjbBatch* B, unsigned sig, std::vector<Seg>* seg
   if (sig & ST_WARMSTART) segs->push_back({L.qacc_warmstart, S.nv});
   if (sig & ST_CTRL) segs->push_back({L.ctrl, S.nu});
   if (sig & ST_QFRC_APPLIED) segs->push_back({L.qfrc_applied, S.nv});
-  // EQ_ACTIVE, MOCAP_*, USERDATA, PLUGIN: zero-sized on supported models
+  if ((sig & ST_EQ_ACTIVE) && S.neq) return -1;   // eq_active is not a runtime input of this path (eq_active0 is used)
+  if ((sig & ST_MOCAP_POS) && S.nmocap) segs->push_back({L.mocap_pos, 3 * S.nmocap});
+  if ((sig & ST_MOCAP_QUAT) && S.nmocap) segs->push_back({L.mocap_quat, 4 * S.nmocap});
+  // USERDATA, PLUGIN: zero-sized on supported models
   return 0;
 }
 
@@ -327,6 +330,20 @@ int mjb_rollout(mjbBatch* B, int nstep, unsigned int control_spec, const double*
   {
     if (!(control_spec & ST_CTRL) || !control) field_zero(B, false, B->b.L.ctrl, B->hm.dm.sz.nu);
     if (!(control_spec & ST_QFRC_APPLIED) || !control) field_zero(B, false, B->b.L.qfrc_applied, nv);
+    const Sizes& S = B->hm.dm.sz;
+    if (S.nmocap) {   // unspecified mocap inputs come from the model (rollout.cc:98-109)
+      const DModel& hm = B->hm.dm;
+      std::vector<double> mp((size_t)nenv * 3 * S.nmocap), mq((size_t)nenv * 4 * S.nmocap);
+      for (int e = 0; e < nenv; e++)
+        for (int i = 0; i < S.nbody; i++) {
+          const int id = hm.body_mocapid[i];
+          if (id < 0) continue;
+          for (int k = 0; k < 3; k++) mp[((size_t)e * S.nmocap + id) * 3 + k] = hm.body_pos[3 * i + k];
+          for (int k = 0; k < 4; k++) mq[((size_t)e * S.nmocap + id) * 4 + k] = hm.body_quat[4 * i + k];
+        }
+      if (!(control_spec & ST_MOCAP_POS) || !control) field_from_host(B, false, B->b.L.mocap_pos, 3 * S.nmocap, mp.data());
+      if (!(control_spec & ST_MOCAP_QUAT) || !control) field_from_host(B, false, B->b.L.mocap_quat, 4 * S.nmocap, mq.data());
+    }
     field_zero(B, true, B->b.L.warning, NWARNING);
     if (int rc = mjb_set_state(B, state0, full)) return rc;
     if (warmstart0) {
@@ -456,7 +473,7 @@ int mjb_set_field(mjbBatch* B, const char* name, const double* in) {
 // every fixed-size mjData array the path computes is written back under the same member name, so code
 // that reads mjData after mj_step keeps working.  Arena-allocated members (contact, efc_*) are not
 // materialised on the host; ncon / nefc and the warning counters are.
-#define MJB_MJDATA_IN(X) X(qpos, nq) X(qvel, nv) X(act, na) X(ctrl, nu) X(qfrc_applied, nv) X(qacc_warmstart, nv)
+#define MJB_MJDATA_IN(X) X(qpos, nq) X(qvel, nv) X(act, na) X(mocap_pos, 3 * nmocap) X(mocap_quat, 4 * nmocap) X(ctrl, nu) X(qfrc_applied, nv) X(qacc_warmstart, nv)
 #define MJB_MJDATA_OUT(X)                                                                                   \
   X(qpos, nq) X(qvel, nv) X(act, na) X(act_dot, na) X(qacc_warmstart, nv) X(qacc, nv)                       \
   X(xpos, 3 * nbody) X(xquat, 4 * nbody) X(xmat, 9 * nbody) X(xipos, 3 * nbody) X(ximat, 9 * nbody)         \
@@ -472,8 +489,8 @@ int mjb_step_mjdata(mjbBatch* B, struct mjData_* const* dd, int nd) {
   const Sizes& S = B->hm.dm.sz;
   const int nenv = B->b.nenv;
   mjData* const* d = (mjData* const*)dd;
-  const int nq = S.nq, nv = S.nv, nu = S.nu, na = S.na, nbody = S.nbody, njnt = S.njnt, ngeom = S.ngeom, ntendon = S.ntendon, nC = S.nC;
-  (void)na; (void)nbody; (void)njnt; (void)ngeom; (void)ntendon; (void)nC;
+  const int nq = S.nq, nv = S.nv, nu = S.nu, na = S.na, nmocap = S.nmocap, nbody = S.nbody, njnt = S.njnt, ngeom = S.ngeom, ntendon = S.ntendon, nC = S.nC;
+  (void)na; (void)nmocap; (void)nbody; (void)njnt; (void)ngeom; (void)ntendon; (void)nC;
   std::vector<double> tmp;
   {
     tmp.resize(nenv);

@@ -29,6 +29,14 @@ MJB_HD void reset_env(const Env& d, bool clear_warnings) {
   for (int i = 0; i < m.sz.nv; i++) { qvel[i] = 0; ws[i] = 0; qa[i] = 0; d.qacc()[i] = 0; }
   for (int i = 0; i < m.sz.nu; i++) ctrl[i] = 0;
   for (int i = 0; i < m.sz.na; i++) { d.act()[i] = 0; d.act_dot()[i] = 0; }
+  if (m.sz.nmocap) {   // mj_resetData: mocap poses from the model (engine_io.c:1531-1540)
+    for (int i = 0; i < m.sz.nbody; i++) {
+      const int mid = m.body_mocapid[i];
+      if (mid < 0) continue;
+      for (int k = 0; k < 3; k++) d.mocap_pos()[3 * mid + k] = m.body_pos[3 * i + k];
+      for (int k = 0; k < 4; k++) d.mocap_quat()[4 * mid + k] = m.body_quat[4 * i + k];
+    }
+  }
   d.time()[0] = 0;
   d.ncon()[0] = 0; d.nefc()[0] = 0; d.ne()[0] = 0; d.nf()[0] = 0; d.nl()[0] = 0; for (int k = 0; k < NISLAND; k++) d.solver_niter()[k] = 0;
   if (clear_warnings) for (int i = 0; i < NWARNING; i++) d.warning()[i] = 0;

@@ -294,7 +294,7 @@ int check_model(const mjModel* m) {
   char msg[256];
 #define FAIL(...) do { snprintf(msg, sizeof(msg), __VA_ARGS__); set_error(std::string("unsupported: ") + msg); return -2; } while (0)
   if (m->nv <= 0 || m->nbody < 2) FAIL("model without degrees of freedom");
-  if (m->nflex || m->nhfield || m->nmocap || m->nplugin) FAIL("flex / hfield / mocap / plugin present");
+  if (m->nflex || m->nhfield || m->nplugin) FAIL("flex / hfield / plugin present");
   for (int i = 0; i < m->neq; i++) {
     if (m->eq_type[i] != mjEQ_JOINT && m->eq_type[i] != mjEQ_TENDON && m->eq_type[i] != mjEQ_CONNECT && m->eq_type[i] != mjEQ_WELD)
       FAIL("equality %d: joint, tendon, connect and weld equalities are built; flex equalities are not", i);
@@ -405,6 +405,7 @@ int build_host_model(const mjModel* m, int nconmax, int njmax, HostModel* out) {
   for (int i = 0; i < m->nu; i++)
     if (m->actuator_dyntype[i] != mjDYN_NONE || m->actuator_trntype[i] == mjTRN_TENDON || m->actuator_gaintype[i] == mjGAIN_MUSCLE ||
         m->actuator_biastype[i] == mjBIAS_MUSCLE) S.actfeat = 1;
+  S.nmocap = m->nmocap;
   S.nq = m->nq; S.nv = m->nv; S.nu = m->nu; S.na = m->na; S.nbody = m->nbody; S.njnt = m->njnt;
   S.ngeom = m->ngeom; S.ntendon = m->ntendon; S.nwrap = m->nwrap; S.nJten = m->nJten; S.nC = m->nC;
   S.ntree = m->ntree;
@@ -519,6 +520,7 @@ int build_host_model(const mjModel* m, int nconmax, int njmax, HostModel* out) {
     std::vector<int> tl(m->ntendon);
     for (int i = 0; i < m->ntendon; i++) tl[i] = m->tendon_actfrclimited[i];
     B.addI(&D.tendon_actfrclimited, tl.data(), m->ntendon);
+    B.addI(&D.body_mocapid, m->body_mocapid, m->nbody);
   }
 
   B.addD(&D.qpos0, m->qpos0, m->nq);

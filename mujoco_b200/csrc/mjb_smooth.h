@@ -49,6 +49,12 @@ MJB_HD void kinematics(const Env& d) {
         const int pid = m.body_parentid[i];
         V3 bpos = ldc3(m.body_pos, 3 * i);
         Q4 bquat = ldc4(m.body_quat, 4 * i);
+        if (m.sz.nmocap && m.body_mocapid[i] >= 0) {   // mocap body: pose from mjData (engine_core_smooth.c:84-90)
+          const int mid = m.body_mocapid[i];
+          bpos = ld3(d.mocap_pos(), 3 * mid);
+          bquat = ld4(d.mocap_quat(), 4 * mid);
+          normalize(bquat);
+        }
         if (pid) {
           p = mulmv(ld9(xmat, 9 * pid), bpos);
           p = p + ld3(xpos, 3 * pid);

@@ -63,7 +63,7 @@ constexpr int kNDyn = 3;    // leading dynprm values kept (filter tau; muscle ta
 // ---- model sizes and options --------------------------------------------------------------------
 struct Sizes {
   int nq, nv, nu, na, nbody, njnt, ngeom, ntendon, nwrap, nJten, nC, ntree;
-  int nsensor, nsensordata, nsite, neq;
+  int nsensor, nsensordata, nsite, neq, nmocap;
   int actfeat;   // 1 when an actuator is stateful, drives a tendon or is a muscle (FEAT_ACT code paths)
   int rnepost;   // 1 when a sensor needs mj_rnePostConstraint (cacc / cfrc_int / cfrc_ext are allocated then)
   int npair;     // static candidate geom pairs (host-built, reference order)
@@ -100,7 +100,7 @@ struct Options {
   X(ten_J_rownnz) X(ten_J_rowadr) X(ten_J_colind)                                            \
   X(actuator_trnjnt) X(actuator_gaintype) X(actuator_biastype) X(actuator_ctrllimited)       \
   X(actuator_forcelimited) X(actuator_trntype) X(actuator_dyntype) X(actuator_actadr)        \
-  X(actuator_actlimited) X(actuator_actearly) X(tendon_actfrclimited)                        \
+  X(actuator_actlimited) X(actuator_actearly) X(tendon_actfrclimited) X(body_mocapid)        \
   X(pair_geom1) X(pair_geom2) X(pair_dim)                                                     \
   X(lvl_adr) X(lvl_body) X(child_adr) X(child_id)                                             \
   X(dlvl_adr) X(dlvl_dof) X(mt_adr) X(mt_dof) X(mt_qadr)                                      \
@@ -141,7 +141,7 @@ struct DModel {
 // ---- batch data fields (per environment), sizes in elements -------------------------------------
 // HOT doubles: staged in shared memory by the fused warp-per-env kernel
 #define MJB_DATA_DBL_FIELDS(X, S)                                                            \
-  X(time, 1) X(qpos, S.nq) X(qvel, S.nv) X(act, S.na) X(act_dot, S.na) X(ctrl, S.nu) X(qacc_warmstart, S.nv)  \
+  X(time, 1) X(qpos, S.nq) X(qvel, S.nv) X(act, S.na) X(act_dot, S.na) X(mocap_pos, 3 * S.nmocap) X(mocap_quat, 4 * S.nmocap) X(ctrl, S.nu) X(qacc_warmstart, S.nv)  \
   X(qfrc_applied, S.nv)                                                                      \
   X(xpos, 3 * S.nbody) X(xquat, 4 * S.nbody) X(xmat, 9 * S.nbody) X(xipos, 3 * S.nbody)      \
   X(ximat, 9 * S.nbody) X(xanchor, 3 * S.njnt) X(xaxis, 3 * S.njnt)                          \

@@ -412,3 +412,40 @@ def test_stateful_actuators_bit_exact(model, integrator, solver):
     assert stats[:, 3].sum() == 0
     assert np.array_equal(out, ref)
     assert np.abs(out[:, -1, 1 + nq + nv:]).max() > 0
+
+
+@pytest.mark.parametrize("solver", [mb.SOLVER_NEWTON, mb.SOLVER_PGS])
+def test_mocap_body_bit_exact(solver):
+    """mocap body (pose read from mjData.mocap_pos / mocap_quat in mj_kinematics, unnormalised quaternions
+    included) dragging a free body through a soft weld - models/ant_mocap.xml.  The mocap trajectory enters
+    rollout() through control_spec = CTRL | MOCAP_POS | MOCAP_QUAT like in the reference; without those bits
+    the model's pose is used"""
+    from oracle_util import Oracle
+    path = os.path.join(ROOT, "models", "ant_mocap.mjb")
+    nenv, nstep = 3, 80
+    m, b, o = make_pair(path, solver, library=hostemu_lib(), nenv=nenv)
+    nu = o.size("nu")
+    s0 = perturbed_states(o, nenv, seed=14, height=[0.35, 0.5, 0.75], qvel_std=0.3, qpos_std=0.05)
+    rng = np.random.default_rng(5)
+    ctrl = rng.uniform(-1, 1, (nenv, nstep, nu))
+    t = np.arange(nstep)[None, :, None] * 0.01
+    mpos = np.array([1.5, 0.2, 0.7]) + 0.3 * np.sin(3 * t + rng.uniform(0, 6, (nenv, 1, 3)))
+    mquat = np.array([0.98, 0.1, 0.1, 0.12]) + 0.2 * np.cos(2 * t + rng.uniform(0, 6, (nenv, 1, 4)))
+    spec = mb.STATE_CTRL | mb.STATE_MOCAP_POS | mb.STATE_MOCAP_QUAT
+    assert b.state_size(spec) == nu + 7
+    out = b.rollout(s0, np.concatenate([ctrl, mpos, mquat], axis=2), control_spec=spec)
+    out_default = b.rollout(s0, ctrl)          # mocap pose falls back to the model's
+    for e in range(nenv):
+        for moving, got in ((True, out), (False, out_default)):
+            oe = Oracle(path)
+            oe.set_opt("solver", solver)
+            oe.reset()
+            oe.set_state(s0[e])
+            for k in range(nstep):
+                oe.dfield("ctrl")[:] = ctrl[e, k]
+                if moving:
+                    oe.dfield("mocap_pos")[:] = mpos[e, k]
+                    oe.dfield("mocap_quat")[:] = mquat[e, k]
+                oe.step()
+                assert np.array_equal(got[e, k], oe.get_state()), (e, k, moving)
+    assert not np.array_equal(out, out_default)
