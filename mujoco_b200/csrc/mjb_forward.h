@@ -621,6 +621,49 @@ MJB_HD void object_acceleration(const Env& d, int kind, int id, bool local, V3& 
   lin = al + cross(va, vl);
 }
 
+// mj_subtreeVel (engine_core_smooth.c:2249-2322): linear velocity and angular momentum of every subtree
+// about its own centre of mass; serial over bodies in the reference's order (sensor models only)
+MJB_HD void subtree_vel(const Env& d) {
+  const DModel& m = d.m;
+  const int nbody = m.sz.nbody;
+  FD lv = d.subtree_linvel(), am = d.subtree_angmom(), bv = d.subtree_bvel();
+  MJB_PFOR(i, nbody) {
+    V3 ang, lin;
+    object_velocity(d, SOBJ_BODY, i, ang, lin);
+    st3(bv, 6 * i, ang); st3(bv, 6 * i + 3, lin);
+    const double mass = m.body_mass[i];
+    st3(lv, 3 * i, V3{lin.x * mass, lin.y * mass, lin.z * mass});
+    const M3 xi = ld9(d.ximat(), 9 * i);
+    V3 dv = mulmTv(xi, ang);
+    dv.x *= m.body_inertia[3 * i]; dv.y *= m.body_inertia[3 * i + 1]; dv.z *= m.body_inertia[3 * i + 2];
+    st3(am, 3 * i, mulmv(xi, dv));
+  }
+  MJB_PSYNC();
+  MJB_LANE0 {
+    for (int i = nbody - 1; i >= 0; i--) {
+      if (i) { const int p = m.body_parentid[i]; st3(lv, 3 * p, ld3(lv, 3 * p) + ld3(lv, 3 * i)); }
+      const double s = 1 / dmax(kMinVal, m.body_subtreemass[i]);
+      const V3 l = ld3(lv, 3 * i);
+      st3(lv, 3 * i, V3{l.x * s, l.y * s, l.z * s});
+    }
+    for (int i = nbody - 1; i > 0; i--) {
+      const int p = m.body_parentid[i];
+      V3 dx = ld3(d.xipos(), 3 * i) - ld3(d.subtree_com(), 3 * i);
+      V3 dv = ld3(bv, 6 * i + 3) - ld3(lv, 3 * i);
+      const double mass = m.body_mass[i];
+      V3 dL = cross(dx, V3{dv.x * mass, dv.y * mass, dv.z * mass});
+      st3(am, 3 * i, ld3(am, 3 * i) + dL);
+      st3(am, 3 * p, ld3(am, 3 * p) + ld3(am, 3 * i));
+      dx = ld3(d.subtree_com(), 3 * i) - ld3(d.subtree_com(), 3 * p);
+      dv = ld3(lv, 3 * i) - ld3(lv, 3 * p);
+      const double sm = m.body_subtreemass[i];
+      dL = cross(dx, V3{dv.x * sm, dv.y * sm, dv.z * sm});
+      st3(am, 3 * p, ld3(am, 3 * p) + dL);
+    }
+  }
+  MJB_PSYNC();
+}
+
 MJB_HD void sensors(const Env& d) {
   const DModel& m = d.m;
   if (!m.sz.nsensor || (m.opt.disableflags & DSBL_SENSOR)) return;
@@ -628,6 +671,7 @@ MJB_HD void sensors(const Env& d) {
   FD out = d.sensordata();
   FI etype = d.efc_type(), eid = d.efc_id();
   if (m.sz.rnepost) rne_post(d);
+  if (m.sz.subtreevel) subtree_vel(d);
   MJB_PFOR(i, m.sz.nsensor) {
     const int type = m.sensor_type[i], id = m.sensor_objid[i], adr = m.sensor_adr[i], dim = m.sensor_dim[i];
     const int okind = m.sensor_objtype[i], rkind = m.sensor_reftype[i], refid = m.sensor_refid[i];
@@ -667,6 +711,8 @@ MJB_HD void sensors(const Env& d) {
         break;
       }
       case SENS_SUBTREECOM: { const V3 c = ld3(d.subtree_com(), 3 * id); v[0] = c.x; v[1] = c.y; v[2] = c.z; break; }
+      case SENS_SUBTREELINVEL: { const V3 c = ld3(d.subtree_linvel(), 3 * id); v[0] = c.x; v[1] = c.y; v[2] = c.z; break; }
+      case SENS_SUBTREEANGMOM: { const V3 c = ld3(d.subtree_angmom(), 3 * id); v[0] = c.x; v[1] = c.y; v[2] = c.z; break; }
       case SENS_CLOCK: v[0] = d.time()[0]; break;
       case SENS_JOINTVEL: v[0] = d.qvel()[m.jnt_dofadr[id]]; break;
       case SENS_TENDONVEL: v[0] = d.ten_velocity()[id]; break;

@@ -280,6 +280,8 @@ static bool sensor_code(const mjModel* m, int i, int* code, int* okind, int* rki
     case mjSENS_TORQUE: *code = SENS_TORQUE; *okind = SOBJ_SITE; return m->sensor_objtype[i] == mjOBJ_SITE;
     case mjSENS_FRAMELINACC: *code = SENS_FRAMELINACC; frame = true; break;
     case mjSENS_FRAMEANGACC: *code = SENS_FRAMEANGACC; frame = true; break;
+    case mjSENS_SUBTREELINVEL: *code = SENS_SUBTREELINVEL; break;
+    case mjSENS_SUBTREEANGMOM: *code = SENS_SUBTREEANGMOM; break;
     default: return false;
   }
   if (frame) {
@@ -411,6 +413,9 @@ int build_host_model(const mjModel* m, int nconmax, int njmax, HostModel* out) {
   S.ntree = m->ntree;
   S.nsensor = m->nsensor; S.nsensordata = m->nsensordata; S.nsite = m->nsite; S.neq = m->neq;
   S.rnepost = 0;
+  S.subtreevel = 0;
+  for (int i = 0; i < m->nsensor; i++)
+    if (m->sensor_type[i] == mjSENS_SUBTREELINVEL || m->sensor_type[i] == mjSENS_SUBTREEANGMOM) S.subtreevel = 1;
   for (int i = 0; i < m->nsensor; i++) {
     const int t = m->sensor_type[i];
     if (t == mjSENS_ACCELEROMETER || t == mjSENS_FORCE || t == mjSENS_TORQUE || t == mjSENS_FRAMELINACC || t == mjSENS_FRAMEANGACC) S.rnepost = 1;

@@ -40,7 +40,7 @@ enum { SENS_JOINTPOS, SENS_TENDONPOS, SENS_ACTUATORPOS, SENS_BALLQUAT, SENS_JOIN
        SENS_JOINTVEL, SENS_TENDONVEL, SENS_ACTUATORVEL, SENS_BALLANGVEL, SENS_JOINTLIMITVEL, SENS_TENDONLIMITVEL,
        SENS_FRAMELINVEL, SENS_FRAMEANGVEL, SENS_ACTUATORFRC, SENS_JOINTACTFRC, SENS_JOINTLIMITFRC,
        SENS_TENDONLIMITFRC, SENS_VELOCIMETER, SENS_GYRO, SENS_ACCELEROMETER, SENS_FORCE, SENS_TORQUE,
-       SENS_FRAMELINACC, SENS_FRAMEANGACC };
+       SENS_FRAMELINACC, SENS_FRAMEANGACC, SENS_SUBTREELINVEL, SENS_SUBTREEANGMOM };
 enum { SOBJ_XBODY = 0, SOBJ_BODY = 1, SOBJ_GEOM = 2, SOBJ_SITE = 3 };   // frame sensor object kinds (mjOBJ_*)   // mjNISLAND: islands with solver statistics (mjdata.h)  // :553-561
 enum { SOL_PGS = 0, SOL_CG = 1, SOL_NEWTON = 2 };                                        // :202-204
 enum { INT_EULER = 0, INT_RK4 = 1, INT_IMPLICIT = 2, INT_IMPLICITFAST = 3 };             // :181-184
@@ -65,6 +65,7 @@ struct Sizes {
   int nq, nv, nu, na, nbody, njnt, ngeom, ntendon, nwrap, nJten, nC, ntree;
   int nsensor, nsensordata, nsite, neq, nmocap;
   int actfeat;   // 1 when an actuator is stateful, drives a tendon or is a muscle (FEAT_ACT code paths)
+  int subtreevel;   // 1 when a sensor needs mj_subtreeVel (subtree_linvel / subtree_angmom are allocated then)
   int rnepost;   // 1 when a sensor needs mj_rnePostConstraint (cacc / cfrc_int / cfrc_ext are allocated then)
   int npair;     // static candidate geom pairs (host-built, reference order)
   int nconmax;   // per-env contact cap
@@ -164,6 +165,7 @@ struct DModel {
   X(scr_body, 12 * S.nbody) X(scr_nv, 8 * S.nv) X(scr_efc, 6 * S.njmax)                         \
   X(nwt_nv, 6 * S.nv) X(nwt_efc, 6 * S.njmax) X(rk_scr, S.nq + 8 * S.nv + 8 * S.na + 4) X(sensordata, S.nsensordata)  \
   X(site_xpos, 3 * S.nsite) X(site_xmat, 9 * S.nsite)                                        \
+  X(subtree_linvel, 3 * S.nbody * S.subtreevel) X(subtree_angmom, 3 * S.nbody * S.subtreevel) X(subtree_bvel, 6 * S.nbody * S.subtreevel) \
   X(cacc, 6 * S.nbody * S.rnepost) X(cfrc_int, 6 * S.nbody * S.rnepost) X(cfrc_ext, 6 * S.nbody * S.rnepost)
 
 // COLD doubles: stay in global memory / L2 in every mapping

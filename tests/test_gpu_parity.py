@@ -264,3 +264,35 @@ def test_stateful_actuators_vs_oracle(model, integrator):
     assert err[:30].max() < RTOL_TIGHT and err.max() < RTOL_TRAJ
     for t in (0, 50, 99):
         compare_forward(b, o, ref[:, t, :], ctrl[:, t, :], rtol=RTOL_TIGHT, check_dual=False)
+
+
+def test_mocap_and_tendon_friction_vs_oracle():
+    """mocap-driven weld (models/ant_mocap.xml, control_spec with the MOCAP bits) on the device"""
+    assert available()
+    path = os.path.join(ROOT, "models", "ant_mocap.mjb")
+    nenv, nstep = 4, 60
+    m, b, o = make_pair(path, mb.SOLVER_NEWTON, nenv=nenv)
+    nu = o.size("nu")
+    s0 = perturbed_states(o, nenv, seed=14, height=[0.35, 0.5, 0.75], qvel_std=0.3, qpos_std=0.05)
+    rng = np.random.default_rng(5)
+    ctrl = rng.uniform(-1, 1, (nenv, nstep, nu))
+    t = np.arange(nstep)[None, :, None] * 0.01
+    mpos = np.array([1.5, 0.2, 0.7]) + 0.3 * np.sin(3 * t + rng.uniform(0, 6, (nenv, 1, 3)))
+    mquat = np.array([0.98, 0.1, 0.1, 0.12]) + 0.2 * np.cos(2 * t + rng.uniform(0, 6, (nenv, 1, 4)))
+    spec = mb.STATE_CTRL | mb.STATE_MOCAP_POS | mb.STATE_MOCAP_QUAT
+    out = b.rollout(s0, np.concatenate([ctrl, mpos, mquat], axis=2), control_spec=spec)
+    worst = 0.0
+    for e in range(nenv):
+        oe = Oracle(path)
+        oe.set_opt("solver", mb.SOLVER_NEWTON)
+        oe.reset()
+        oe.set_state(s0[e])
+        for k in range(nstep):
+            oe.dfield("ctrl")[:] = ctrl[e, k]
+            oe.dfield("mocap_pos")[:] = mpos[e, k]
+            oe.dfield("mocap_quat")[:] = mquat[e, k]
+            oe.step()
+            r = oe.get_state()
+            worst = max(worst, np.abs(out[e, k] - r).max() / max(1.0, np.abs(r).max()))
+    print("mocap rollout worst rel err %.3e" % worst)
+    assert worst < RTOL_TRAJ

@@ -433,10 +433,10 @@ def test_mocap_body_bit_exact(solver):
     mquat = np.array([0.98, 0.1, 0.1, 0.12]) + 0.2 * np.cos(2 * t + rng.uniform(0, 6, (nenv, 1, 4)))
     spec = mb.STATE_CTRL | mb.STATE_MOCAP_POS | mb.STATE_MOCAP_QUAT
     assert b.state_size(spec) == nu + 7
-    out = b.rollout(s0, np.concatenate([ctrl, mpos, mquat], axis=2), control_spec=spec)
-    out_default = b.rollout(s0, ctrl)          # mocap pose falls back to the model's
+    out, sens = b.rollout(s0, np.concatenate([ctrl, mpos, mquat], axis=2), control_spec=spec, return_sensordata=True)
+    out_default, sens_default = b.rollout(s0, ctrl, return_sensordata=True)          # mocap pose falls back to the model's
     for e in range(nenv):
-        for moving, got in ((True, out), (False, out_default)):
+        for moving, got, gsens in ((True, out, sens), (False, out_default, sens_default)):
             oe = Oracle(path)
             oe.set_opt("solver", solver)
             oe.reset()
@@ -448,4 +448,6 @@ def test_mocap_body_bit_exact(solver):
                     oe.dfield("mocap_quat")[:] = mquat[e, k]
                 oe.step()
                 assert np.array_equal(got[e, k], oe.get_state()), (e, k, moving)
+                # incl. subtreelinvel / subtreeangmom (mj_subtreeVel) of moving, static and leaf subtrees
+                assert np.array_equal(gsens[e, k], np.array(oe.dfield("sensordata"))), (e, k, moving)
     assert not np.array_equal(out, out_default)

@@ -14,7 +14,7 @@ variant = os.environ.get('MJB_VARIANT_LIB')   # development only: A/B a differen
 m = mb.Model(path, library=mb._bind(ctypes.CDLL(variant)) if variant else None); m.set_option('solver', solver)
 for kv in sys.argv[6:]:
     k, v = kv.split('='); m.set_option(k, float(v))
-b = mb.Batch(m, nenv)
+b = mb.Batch(m, nenv, nconmax=int(os.environ.get('MJB_NCONMAX', '0')), njmax=int(os.environ.get('MJB_NJMAX', '0')))   # 0 = library defaults
 nu, stride = m.size('nu'), b.env_stride()
 stream = torch.cuda.ExternalStream(b.stream())
 g = torch.Generator(device='cuda'); g.manual_seed(0)
