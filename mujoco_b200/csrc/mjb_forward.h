@@ -621,6 +621,46 @@ MJB_HD void object_acceleration(const Env& d, int kind, int id, bool local, V3& 
   lin = al + cross(va, vl);
 }
 
+// ray against a sphere / box zone (engine_ray.c: ray_quad :103, ray_sphere :242, ray_box :490); only the
+// distance is needed (>= 0: hit), normals are not
+MJB_HD double ray_quad(double a, double b, double c) {
+  double det = b * b - a * c;
+  if (det < 0 || a < kMinVal) return -1;
+  det = sqrt(det);
+  const double x0 = (-b - det) / a, x1 = (-b + det) / a;
+  if (x0 >= 0) return x0;
+  if (x1 >= 0) return x1;
+  return -1;
+}
+MJB_HD double ray_sphere(V3 pos, double dist_sqr, V3 pnt, V3 vec) {
+  const V3 dif = pnt - pos;
+  const double a = vec.x * vec.x + vec.y * vec.y + vec.z * vec.z;
+  const double b = vec.x * dif.x + vec.y * dif.y + vec.z * dif.z;
+  const double c = dif.x * dif.x + dif.y * dif.y + dif.z * dif.z - dist_sqr;
+  return ray_quad(a, b, c);
+}
+MJB_HD double ray_box(V3 pos, const M3& mat, const double* size, V3 pnt, V3 vec) {
+  const double ssz = size[0] * size[0] + size[1] * size[1] + size[2] * size[2];
+  if (ray_sphere(pos, ssz, pnt, vec) < 0) return -1;
+  const V3 dif = pnt - pos;
+  const double lp[3] = {mat.m[0] * dif.x + mat.m[3] * dif.y + mat.m[6] * dif.z, mat.m[1] * dif.x + mat.m[4] * dif.y + mat.m[7] * dif.z,
+                        mat.m[2] * dif.x + mat.m[5] * dif.y + mat.m[8] * dif.z};
+  const double lv[3] = {mat.m[0] * vec.x + mat.m[3] * vec.y + mat.m[6] * vec.z, mat.m[1] * vec.x + mat.m[4] * vec.y + mat.m[7] * vec.z,
+                        mat.m[2] * vec.x + mat.m[5] * vec.y + mat.m[8] * vec.z};
+  double x = -1;
+  for (int i = 0; i < 3; i++) {
+    if (fabs(lv[i]) <= kMinVal) continue;
+    const int f0 = (i == 0) ? 1 : 0, f1 = (i == 2) ? 1 : 2;
+    for (int side = -1; side <= 1; side += 2) {
+      const double sol = (side * size[i] - lp[i]) / lv[i];
+      if (sol < 0) continue;
+      const double p0 = lp[f0] + sol * lv[f0], p1 = lp[f1] + sol * lv[f1];
+      if (fabs(p0) <= size[f0] && fabs(p1) <= size[f1] && (x < 0 || sol < x)) x = sol;
+    }
+  }
+  return x;
+}
+
 // mj_subtreeVel (engine_core_smooth.c:2249-2322): linear velocity and angular momentum of every subtree
 // about its own centre of mass; serial over bodies in the reference's order (sensor models only)
 MJB_HD void subtree_vel(const Env& d) {
@@ -713,6 +753,30 @@ MJB_HD void sensors(const Env& d) {
       case SENS_SUBTREECOM: { const V3 c = ld3(d.subtree_com(), 3 * id); v[0] = c.x; v[1] = c.y; v[2] = c.z; break; }
       case SENS_SUBTREELINVEL: { const V3 c = ld3(d.subtree_linvel(), 3 * id); v[0] = c.x; v[1] = c.y; v[2] = c.z; break; }
       case SENS_SUBTREEANGMOM: { const V3 c = ld3(d.subtree_angmom(), 3 * id); v[0] = c.x; v[1] = c.y; v[2] = c.z; break; }
+      case SENS_TOUCH: {   // engine_sensor.c:980-1025: normal forces of the body's contacts whose ray meets the zone
+        const int bodyid = m.site_bodyid[id], ncon = d.ncon()[0];
+        FI cadr = d.con_efcadr(), cdim = d.con_dim(), g1 = d.con_geom1(), g2 = d.con_geom2();
+        FD ef = d.efc_force();
+        const V3 spos = ld3(d.site_xpos(), 3 * id);
+        const M3 smat = ld9(d.site_xmat(), 9 * id);
+        for (int j = 0; j < ncon; j++) {
+          const int b1 = m.geom_bodyid[g1[j]], b2 = m.geom_bodyid[g2[j]], a = cadr[j];
+          if (a < 0 || (bodyid != b1 && bodyid != b2)) continue;
+          double fn = 0;   // mju_decodePyramid: normal force = sum of the pyramid forces
+          if (cdim[j] == 1) fn = ef[a];
+          else for (int k = 0; k < 2 * (cdim[j] - 1); k++) fn += ef[a + k];
+          if (fn <= 0) continue;
+          const V3 fr = ld3(d.con_frame(), 9 * j);
+          V3 ray{fr.x * fn, fr.y * fn, fr.z * fn};
+          normalize(ray);
+          if (bodyid == b2) ray = V3{ray.x * -1, ray.y * -1, ray.z * -1};
+          const V3 cp = ld3(d.con_pos(), 3 * j);
+          const double hit = (m.site_type[id] == GEOM_SPHERE) ? ray_sphere(spos, m.site_size[3 * id] * m.site_size[3 * id], cp, ray)
+                                                            : ray_box(spos, smat, m.site_size + 3 * id, cp, ray);
+          if (hit >= 0) v[0] += fn;
+        }
+        break;
+      }
       case SENS_CLOCK: v[0] = d.time()[0]; break;
       case SENS_JOINTVEL: v[0] = d.qvel()[m.jnt_dofadr[id]]; break;
       case SENS_TENDONVEL: v[0] = d.ten_velocity()[id]; break;

@@ -281,6 +281,9 @@ static bool sensor_code(const mjModel* m, int i, int* code, int* okind, int* rki
     case mjSENS_FRAMELINACC: *code = SENS_FRAMELINACC; frame = true; break;
     case mjSENS_FRAMEANGACC: *code = SENS_FRAMEANGACC; frame = true; break;
     case mjSENS_SUBTREELINVEL: *code = SENS_SUBTREELINVEL; break;
+    case mjSENS_TOUCH:   // contact normal forces inside a site volume: sphere and box zones are built
+      *code = SENS_TOUCH; *okind = SOBJ_SITE;
+      return m->sensor_objtype[i] == mjOBJ_SITE && (m->site_type[m->sensor_objid[i]] == mjGEOM_SPHERE || m->site_type[m->sensor_objid[i]] == mjGEOM_BOX);
     case mjSENS_SUBTREEANGMOM: *code = SENS_SUBTREEANGMOM; break;
     default: return false;
   }
@@ -635,6 +638,8 @@ int build_host_model(const mjModel* m, int nconmax, int njmax, HostModel* out) {
     B.addD(&D.tendon_length0, m->tendon_length0, m->ntendon);
   }
   B.addD(&D.site_pos, m->site_pos, 3 * m->nsite);
+  B.addD(&D.site_size, m->site_size, 3 * m->nsite);
+  B.addI(&D.site_type, m->site_type, m->nsite);
   B.addD(&D.site_quat, m->site_quat, 4 * m->nsite);
 
   int has_lim = 0, has_fl = 0;

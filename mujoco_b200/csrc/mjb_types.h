@@ -40,7 +40,7 @@ enum { SENS_JOINTPOS, SENS_TENDONPOS, SENS_ACTUATORPOS, SENS_BALLQUAT, SENS_JOIN
        SENS_JOINTVEL, SENS_TENDONVEL, SENS_ACTUATORVEL, SENS_BALLANGVEL, SENS_JOINTLIMITVEL, SENS_TENDONLIMITVEL,
        SENS_FRAMELINVEL, SENS_FRAMEANGVEL, SENS_ACTUATORFRC, SENS_JOINTACTFRC, SENS_JOINTLIMITFRC,
        SENS_TENDONLIMITFRC, SENS_VELOCIMETER, SENS_GYRO, SENS_ACCELEROMETER, SENS_FORCE, SENS_TORQUE,
-       SENS_FRAMELINACC, SENS_FRAMEANGACC, SENS_SUBTREELINVEL, SENS_SUBTREEANGMOM };
+       SENS_FRAMELINACC, SENS_FRAMEANGACC, SENS_SUBTREELINVEL, SENS_SUBTREEANGMOM, SENS_TOUCH };
 enum { SOBJ_XBODY = 0, SOBJ_BODY = 1, SOBJ_GEOM = 2, SOBJ_SITE = 3 };   // frame sensor object kinds (mjOBJ_*)   // mjNISLAND: islands with solver statistics (mjdata.h)  // :553-561
 enum { SOL_PGS = 0, SOL_CG = 1, SOL_NEWTON = 2 };                                        // :202-204
 enum { INT_EULER = 0, INT_RK4 = 1, INT_IMPLICIT = 2, INT_IMPLICITFAST = 3 };             // :181-184
@@ -101,7 +101,7 @@ struct Options {
   X(ten_J_rownnz) X(ten_J_rowadr) X(ten_J_colind)                                            \
   X(actuator_trnjnt) X(actuator_gaintype) X(actuator_biastype) X(actuator_ctrllimited)       \
   X(actuator_forcelimited) X(actuator_trntype) X(actuator_dyntype) X(actuator_actadr)        \
-  X(actuator_actlimited) X(actuator_actearly) X(tendon_actfrclimited) X(body_mocapid)        \
+  X(actuator_actlimited) X(actuator_actearly) X(tendon_actfrclimited) X(body_mocapid) X(site_type)        \
   X(pair_geom1) X(pair_geom2) X(pair_dim)                                                     \
   X(lvl_adr) X(lvl_body) X(child_adr) X(child_id)                                             \
   X(dlvl_adr) X(dlvl_dof) X(mt_adr) X(mt_dof) X(mt_qadr)                                      \
@@ -124,7 +124,7 @@ struct Options {
   X(tendon_dampingpoly_eff) X(tendon_lengthspring) X(tendon_armature_eff)                    \
   X(actuator_gear0) X(actuator_gainprm) X(actuator_biasprm) X(actuator_ctrlrange)            \
   X(actuator_forcerange) X(actuator_dynprm) X(actuator_actrange) X(actuator_lengthrange) X(actuator_acc0) \
-  X(tendon_frictionloss) X(tendon_solref_fri) X(tendon_solimp_fri) X(tendon_actfrcrange)      \
+  X(site_size) X(tendon_frictionloss) X(tendon_solref_fri) X(tendon_solimp_fri) X(tendon_actfrcrange)      \
   X(pair_margin) X(pair_includemargin) X(pair_solref) X(pair_solimp) X(pair_friction) X(sensor_cutoff) X(site_pos) X(site_quat)            \
   X(eq_data) X(eq_solref) X(eq_solimp) X(tendon_length0)
 
