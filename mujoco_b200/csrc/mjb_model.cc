@@ -844,8 +844,10 @@ int build_host_model(const mjModel* m, int nconmax, int njmax, HostModel* out) {
   }
 
   // caps replacing the reference arena
-  if (nconmax <= 0) nconmax = std::min(std::max(S.npair / 2, 16), 32);
-  if (njmax <= 0) njmax = S.nfl + 6 * S.neq + 64;
+  // (measured on B200, humanoid x4096: 2.216 ms/step at 32 / 64, 2.225 at 64 / 160, 2.227 at 100 / 300 — the
+  // caps cost memory, not time, so the defaults lean generous)
+  if (nconmax <= 0) nconmax = std::min(std::max(S.npair / 2, 16), 48);
+  if (njmax <= 0) njmax = S.nfl + 6 * S.neq + 128;
   S.nconmax = nconmax;
   S.njmax = njmax;
   if (O.solver == mjSOL_PGS && !O.dense) { set_error("unsupported: PGS with sparse Jacobian (nv >= 60)"); return -2; }
