@@ -252,7 +252,7 @@ def main():
             "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
             "traffic_source": traffic_src, "algorithmic_bytes_per_launch": NENV * b_mjdata,
             "algorithmic_bytes_per_env_step": b_mjdata, "launch_ms": launch_ms,
-            "note": "latency-bound (serial PGS dependency chain of the slowest env), not bandwidth-bound: see DESIGN.md",
+            "note": "not bandwidth-bound: instruction issue / fetch of the branchy PGS sweeps of a heavy-tailed batch (DESIGN.md section 5)",
             "stage_ms": dict(zip(["position", "velocity", "solve", "integrate"], [float(x) for x in stage_ms])),
             "stage_bytes_per_env": dict(zip(["position", "velocity", "solve", "integrate"], [float(x) for x in bytes_per_env]))}
 
