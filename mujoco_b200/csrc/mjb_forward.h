@@ -78,6 +78,36 @@ MJB_HD void fwd_position(const Env& d) {
   transmission(d);
 }
 
+// gravity compensation (mj_gravcomp, engine_passive.c:846-866; mj_applyFT with a zero torque): per body an
+// upward force -gravity*mass*gravcomp at the body's com, mapped through the point Jacobian; bodies in order
+MJB_HD void gravcomp(const Env& d) {
+  const DModel& m = d.m;
+  if (!(d.feat & FEAT_ACT) || !m.sz.gravcomp) return;
+  const int nv = m.sz.nv;
+  FD gc = d.qfrc_gravcomp(), fp = d.qfrc_passive();
+  const double* g = m.opt.gravity;
+  const bool off = (m.opt.disableflags & DSBL_GRAVITY) || sqrt(g[0] * g[0] + g[1] * g[1] + g[2] * g[2]) == 0 ||
+                   ((m.opt.disableflags & DSBL_SPRING) && (m.opt.disableflags & DSBL_DAMPER));
+  MJB_PFOR(j, nv) {
+    double acc = 0;
+    if (!off) {
+      for (int i = 1; i < m.sz.nbody; i++) {
+        if (!m.body_gravcomp[i]) continue;
+        const double s = -(m.body_mass[i] * m.body_gravcomp[i]);
+        const double f[3] = {g[0] * s, g[1] * s, g[2] * s};
+        const V3 pt = ld3(d.xipos(), 3 * i);
+        double q = 0;   // mju_mulMatTVec: rows with a zero force component are skipped
+        for (int r = 0; r < 3; r++) if (f[r]) q += jac_elem(d, pt, i, r, j) * f[r];
+        acc += q;
+        acc += 0.0;     // the (zero) torque part of mj_applyFT
+      }
+    }
+    gc[j] = acc;
+    if (!off && !m.jnt_actgravcomp[m.dof_jntid[j]]) fp[j] += acc;
+  }
+  MJB_PSYNC();
+}
+
 MJB_HD void fwd_velocity(const Env& d) {
   const DModel& m = d.m;
   FD qvel = d.qvel();
@@ -104,6 +134,7 @@ MJB_HD void fwd_velocity(const Env& d) {
   MJB_PSYNC();
   com_vel(d);
   passive(d);
+  gravcomp(d);
   reference_constraint(d);
   rne_bias(d);
   // tendon-armature bias: needs d/dt(ten_J), identically zero for fixed tendons -> no contribution
@@ -284,6 +315,14 @@ MJB_HD void fwd_actuation(const Env& d) {
         continue;
       }
       qfa[m.jnt_dofadr[m.actuator_trnjnt[i]]] += mom[i] * s;
+    }
+    if (stateful && m.sz.gravcomp && !(m.opt.disableflags & DSBL_GRAVITY)) {   // actuator-level gravity compensation
+      FD gcf = d.qfrc_gravcomp();
+      for (int j = 0; j < m.sz.njnt; j++) {
+        if (!m.jnt_actgravcomp[j]) continue;
+        const int da = m.jnt_dofadr[j], nd = (m.jnt_type[j] == JNT_FREE) ? 6 : (m.jnt_type[j] == JNT_BALL) ? 3 : 1;
+        for (int k = 0; k < nd; k++) qfa[da + k] += gcf[da + k];
+      }
     }
     for (int j = 0; j < m.sz.njnt; j++) {
       if (!m.jnt_actfrclimited[j]) continue;

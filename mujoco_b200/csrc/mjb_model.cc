@@ -320,7 +320,6 @@ int check_model(const mjModel* m) {
   }
   if (m->npair) FAIL("predefined contact pairs (npair=%d)", (int)m->npair);
   if (m->nhistory) FAIL("history buffers / delays");
-  if (m->flg_gravcomp) FAIL("gravity compensation");
   if (m->flg_surfacevel) FAIL("geom surface velocity");
   if (m->opt.cone != mjCONE_PYRAMIDAL) FAIL("elliptic friction cones");
   if (m->opt.integrator == mjINT_IMPLICIT) FAIL("the fully implicit integrator (RNE velocity derivatives, sparse LU)");
@@ -411,6 +410,8 @@ int build_host_model(const mjModel* m, int nconmax, int njmax, HostModel* out) {
     if (m->actuator_dyntype[i] != mjDYN_NONE || m->actuator_trntype[i] == mjTRN_TENDON || m->actuator_gaintype[i] == mjGAIN_MUSCLE ||
         m->actuator_biastype[i] == mjBIAS_MUSCLE) S.actfeat = 1;
   S.nmocap = m->nmocap;
+  S.gravcomp = m->flg_gravcomp ? 1 : 0;
+  if (S.gravcomp) S.actfeat = 1;
   S.nq = m->nq; S.nv = m->nv; S.nu = m->nu; S.na = m->na; S.nbody = m->nbody; S.njnt = m->njnt;
   S.ngeom = m->ngeom; S.ntendon = m->ntendon; S.nwrap = m->nwrap; S.nJten = m->nJten; S.nC = m->nC;
   S.ntree = m->ntree;
@@ -529,6 +530,9 @@ int build_host_model(const mjModel* m, int nconmax, int njmax, HostModel* out) {
     for (int i = 0; i < m->ntendon; i++) tl[i] = m->tendon_actfrclimited[i];
     B.addI(&D.tendon_actfrclimited, tl.data(), m->ntendon);
     B.addI(&D.body_mocapid, m->body_mocapid, m->nbody);
+    std::vector<int> ag(m->njnt);
+    for (int i = 0; i < m->njnt; i++) ag[i] = m->jnt_actgravcomp[i];
+    B.addI(&D.jnt_actgravcomp, ag.data(), m->njnt);
   }
 
   B.addD(&D.qpos0, m->qpos0, m->nq);
@@ -639,6 +643,7 @@ int build_host_model(const mjModel* m, int nconmax, int njmax, HostModel* out) {
   }
   B.addD(&D.site_pos, m->site_pos, 3 * m->nsite);
   B.addD(&D.site_size, m->site_size, 3 * m->nsite);
+  B.addD(&D.body_gravcomp, m->body_gravcomp, m->nbody);
   B.addI(&D.site_type, m->site_type, m->nsite);
   B.addD(&D.site_quat, m->site_quat, 4 * m->nsite);
 
