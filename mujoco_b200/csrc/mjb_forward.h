@@ -124,6 +124,10 @@ MJB_HD void fwd_velocity(const Env& d) {
       const int t = m.actuator_trnjnt[i], adr = m.ten_J_rowadr[t], nnz = m.ten_J_rownnz[t];
       const double g = mom[i];
       av[i] = dot_sparse_ref(nnz, [&](int c) { return tJ[adr + c] * g; }, [&](int c) { return qvel[m.ten_J_colind[adr + c]]; });
+    } else if ((d.feat & FEAT_ACT) && m.actuator_trntype[i] >= TRN_BALL) {
+      const int da = m.jnt_dofadr[m.actuator_trnjnt[i]], nd = (m.actuator_trntype[i] == TRN_FREE) ? 6 : 3;
+      FD m6 = d.actuator_mom6();
+      av[i] = dot_sparse_ref(nd, [&](int c) { return m6[6 * i + c]; }, [&](int c) { return qvel[da + c]; });
     } else {
       const int dof = m.jnt_dofadr[m.actuator_trnjnt[i]];
       double r = 0;
@@ -213,6 +217,10 @@ MJB_HD void advance_act(const Env& d, FD act_dot) {
   MJB_PFOR(u, m.sz.nu) {
     const int a = m.actuator_actadr[u];
     if (a >= 0) act[a] = next_activation(d, u, act[a], act_dot[a]);
+    if (a >= 0 && m.actuator_dyntype[u] == DYN_INTEGRATOR && m.actuator_wrapperiod[u] > 0) {   // engine_forward.c:1328-1340
+      const double period = m.actuator_wrapperiod[u], err = act[a] - d.actuator_length()[u];
+      act[a] = act[a] - period * round_int(err / period);
+    }
   }
   MJB_PSYNC();
 }
@@ -273,6 +281,10 @@ MJB_HD void fwd_actuation(const Env& d) {
       const int a = m.actuator_actadr[i];
       in = m.actuator_actearly[i] ? next_activation(d, i, d.act()[a], d.act_dot()[a]) : d.act()[a];
     }
+    if (stateful && m.actuator_wrapperiod[i] > 0) {   // rotational setpoint: representative nearest the length (wrapSetpoint)
+      const double period = m.actuator_wrapperiod[i], err = in - len[i];
+      in = in - period * round_int(err / period);
+    }
     double f = gain * in;
     double bias;
     if (bt == BIAS_NONE) bias = 0.0;
@@ -312,6 +324,12 @@ MJB_HD void fwd_actuation(const Env& d) {
         const int t = m.actuator_trnjnt[i], adr = m.ten_J_rowadr[t], nnz = m.ten_J_rownnz[t];
         FD tJ = d.ten_J();
         for (int c = 0; c < nnz; c++) qfa[m.ten_J_colind[adr + c]] += (tJ[adr + c] * mom[i]) * s;
+        continue;
+      }
+      if (stateful && m.actuator_trntype[i] >= TRN_BALL) {
+        const int da = m.jnt_dofadr[m.actuator_trnjnt[i]], nd = (m.actuator_trntype[i] == TRN_FREE) ? 6 : 3;
+        FD m6 = d.actuator_mom6();
+        for (int c = 0; c < nd; c++) qfa[da + c] += m6[6 * i + c] * s;
         continue;
       }
       qfa[m.jnt_dofadr[m.actuator_trnjnt[i]]] += mom[i] * s;
@@ -459,6 +477,12 @@ MJB_HD void implicitfast_advance(const Env& d) {
             if (col == j) { Jj = tJ[ta + c] * mom[u]; hj = true; }
           }
           if (hi && hj) q += Jj * (Ji * aB[u]);
+        } else if ((d.feat & FEAT_ACT) && m.actuator_trntype[u] >= TRN_BALL) {   // moment row on the joint's 3 / 6 dofs
+          const int da = m.jnt_dofadr[m.actuator_trnjnt[u]], nd = (m.actuator_trntype[u] == TRN_FREE) ? 6 : 3;
+          if (i >= da && i < da + nd && j >= da && j < da + nd) {
+            FD m6 = d.actuator_mom6();
+            q += m6[6 * u + (j - da)] * (m6[6 * u + (i - da)] * aB[u]);
+          }
         } else if (i == j && m.jnt_dofadr[m.actuator_trnjnt[u]] == i) {
           q += mom[u] * (mom[u] * aB[u]);
         }

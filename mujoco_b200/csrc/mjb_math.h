@@ -277,6 +277,13 @@ MJB_HD double d_xpoly_force(double linear, const double* poly, int n, double x, 
   return res;
 }
 
+// mju_round (engine_util_misc.c:1752): nearest integer, halves away from zero, saturating at the int range
+MJB_HD int round_int(double x) {
+  if (x > 2147483647.0) return 2147483647;
+  if (x < -2147483648.0) return (-2147483647 - 1);
+  return (int)round(x);
+}
+
 // mju_mulQuatAxis / mju_derivQuat (engine_util_spatial.c:81-92, :225-230)
 MJB_HD Q4 qmul_axis(Q4 q, V3 a) {
   return Q4{-q.x * a.x - q.y * a.y - q.z * a.z, q.w * a.x + q.y * a.z - q.z * a.y,

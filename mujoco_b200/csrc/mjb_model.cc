@@ -350,7 +350,8 @@ int check_model(const mjModel* m) {
     if (tt != mjTRN_JOINT && tt != mjTRN_JOINTINPARENT && tt != mjTRN_TENDON) FAIL("actuator %d: transmission other than joint / tendon", i);
     if (tt != mjTRN_TENDON) {
       int jt = m->jnt_type[m->actuator_trnid[2 * i]];
-      if (jt != mjJNT_HINGE && jt != mjJNT_SLIDE) FAIL("actuator %d on ball/free joint", i);
+      if ((jt == mjJNT_BALL || jt == mjJNT_FREE) && (m->actuator_damping[i] != 0 || m->actuator_armature[i] != 0))
+        FAIL("actuator %d: actuator damping / armature on a ball or free joint", i);
     }
     int dt = m->actuator_dyntype[i], gt = m->actuator_gaintype[i], bt = m->actuator_biastype[i];
     if (dt != mjDYN_NONE && dt != mjDYN_INTEGRATOR && dt != mjDYN_FILTER && dt != mjDYN_FILTEREXACT && dt != mjDYN_MUSCLE)
@@ -407,7 +408,9 @@ int build_host_model(const mjModel* m, int nconmax, int njmax, HostModel* out) {
   Sizes& S = D.sz;
   S.actfeat = 0;
   for (int i = 0; i < m->nu; i++)
-    if (m->actuator_dyntype[i] != mjDYN_NONE || m->actuator_trntype[i] == mjTRN_TENDON || m->actuator_gaintype[i] == mjGAIN_MUSCLE ||
+    if (m->actuator_dyntype[i] != mjDYN_NONE || m->actuator_trntype[i] == mjTRN_TENDON ||
+        ((m->actuator_trntype[i] == mjTRN_JOINT || m->actuator_trntype[i] == mjTRN_JOINTINPARENT) &&
+         (m->jnt_type[m->actuator_trnid[2 * i]] == mjJNT_BALL || m->jnt_type[m->actuator_trnid[2 * i]] == mjJNT_FREE)) || m->actuator_gaintype[i] == mjGAIN_MUSCLE ||
         m->actuator_biastype[i] == mjBIAS_MUSCLE) S.actfeat = 1;
   S.nmocap = m->nmocap;
   S.gravcomp = m->flg_gravcomp ? 1 : 0;
@@ -518,6 +521,8 @@ int build_host_model(const mjModel* m, int nconmax, int njmax, HostModel* out) {
     std::vector<int> tt(m->nu), al(m->nu), ae(m->nu);
     for (int i = 0; i < m->nu; i++) {
       tt[i] = (m->actuator_trntype[i] == mjTRN_TENDON) ? TRN_TENDON : TRN_JOINT;
+      if (tt[i] == TRN_JOINT && m->jnt_type[m->actuator_trnid[2 * i]] == mjJNT_BALL) tt[i] = TRN_BALL;
+      if (tt[i] == TRN_JOINT && m->jnt_type[m->actuator_trnid[2 * i]] == mjJNT_FREE) tt[i] = TRN_FREE;
       al[i] = m->actuator_actlimited[i];
       ae[i] = m->actuator_actearly[i];
     }
@@ -526,6 +531,9 @@ int build_host_model(const mjModel* m, int nconmax, int njmax, HostModel* out) {
     B.addI(&D.actuator_actadr, m->actuator_actadr, m->nu);
     B.addI(&D.actuator_actlimited, al.data(), m->nu);
     B.addI(&D.actuator_actearly, ae.data(), m->nu);
+    std::vector<int> ip(m->nu);
+    for (int i = 0; i < m->nu; i++) ip[i] = (m->actuator_trntype[i] == mjTRN_JOINTINPARENT);
+    B.addI(&D.actuator_inparent, ip.data(), m->nu);
     std::vector<int> tl(m->ntendon);
     for (int i = 0; i < m->ntendon; i++) tl[i] = m->tendon_actfrclimited[i];
     B.addI(&D.tendon_actfrclimited, tl.data(), m->ntendon);
@@ -628,6 +636,22 @@ int build_host_model(const mjModel* m, int nconmax, int njmax, HostModel* out) {
   B.addD(&D.actuator_actrange, m->actuator_actrange, 2 * m->nu);
   B.addD(&D.actuator_lengthrange, m->actuator_lengthrange, 2 * m->nu);
   B.addD(&D.actuator_acc0, m->actuator_acc0, m->nu);
+  B.addD(&D.actuator_gear6, m->actuator_gear, 6 * m->nu);
+  {   // wrapPeriod (engine_forward.c:296-328): servo-shaped actuators on a ball joint take the setpoint nearest the length
+    std::vector<double> wp(m->nu, 0.0);
+    for (int i = 0; i < m->nu; i++) {
+      const int dt = m->actuator_dyntype[i], tt = m->actuator_trntype[i];
+      const bool servo = m->actuator_gaintype[i] == mjGAIN_FIXED && m->actuator_biastype[i] == mjBIAS_AFFINE &&
+                         m->actuator_gainprm[mjNGAIN * i] == -m->actuator_biasprm[mjNBIAS * i + 1] &&
+                         (dt == mjDYN_NONE || dt == mjDYN_INTEGRATOR);
+      if (servo && (tt == mjTRN_JOINT || tt == mjTRN_JOINTINPARENT) && m->jnt_type[m->actuator_trnid[2 * i]] == mjJNT_BALL)
+      {
+        const mjtNum* g = m->actuator_gear + 6 * i;
+        wp[i] = 2 * mjPI * std::sqrt(g[0] * g[0] + g[1] * g[1] + g[2] * g[2]);   // 2*mjPI * mju_norm3(gear)
+      }
+    }
+    B.addD(&D.actuator_wrapperiod, wp.data(), m->nu);
+  }
   B.addD(&D.tendon_frictionloss, m->tendon_frictionloss, m->ntendon);
   B.addD(&D.tendon_solref_fri, m->tendon_solref_fri, mjNREF * m->ntendon);
   B.addD(&D.tendon_solimp_fri, m->tendon_solimp_fri, mjNIMP * m->ntendon);

@@ -244,7 +244,25 @@ MJB_HD void transmission(const Env& d) {
   MJB_PFOR(i, m.sz.nu) {
     const int j = m.actuator_trnjnt[i];
     const double g = m.actuator_gear0[i];
-    if ((d.feat & FEAT_ACT) && m.actuator_trntype[i] == TRN_TENDON) len[i] = d.ten_length()[j] * g;
+    const int tt = (d.feat & FEAT_ACT) ? m.actuator_trntype[i] : TRN_JOINT;
+    if (tt == TRN_TENDON) len[i] = d.ten_length()[j] * g;
+    else if (tt == TRN_BALL || tt == TRN_FREE) {   // 3D / 6D gear (engine_core_smooth.c:1331-1393)
+      const double* gear = m.actuator_gear6 + 6 * i;
+      FD m6 = d.actuator_mom6();
+      Q4 q = ld4(qpos, m.jnt_qposadr[j] + (tt == TRN_FREE ? 3 : 0));
+      normalize(q);
+      V3 ga{gear[tt == TRN_FREE ? 3 : 0], gear[tt == TRN_FREE ? 4 : 1], gear[tt == TRN_FREE ? 5 : 2]};
+      if (m.actuator_inparent[i]) ga = rotate(ga, Q4{q.w, -q.x, -q.y, -q.z});
+      if (tt == TRN_BALL) {
+        const V3 axis = quat2vel(q, 1);
+        len[i] = axis.x * ga.x + axis.y * ga.y + axis.z * ga.z;
+        m6[6 * i] = ga.x; m6[6 * i + 1] = ga.y; m6[6 * i + 2] = ga.z;
+      } else {
+        len[i] = 0;
+        m6[6 * i] = gear[0]; m6[6 * i + 1] = gear[1]; m6[6 * i + 2] = gear[2];
+        m6[6 * i + 3] = ga.x; m6[6 * i + 4] = ga.y; m6[6 * i + 5] = ga.z;
+      }
+    }
     else len[i] = qpos[m.jnt_qposadr[j]] * g;
     mom[i] = g;
   }

@@ -49,7 +49,7 @@ enum { SAMEFRAME_NONE = 0, SAMEFRAME_BODY = 1, SAMEFRAME_INERTIA = 2, SAMEFRAME_
 enum { GAIN_FIXED = 0, GAIN_AFFINE = 1, GAIN_MUSCLE = 2 };                               // :256-258
 enum { BIAS_NONE = 0, BIAS_AFFINE = 1, BIAS_MUSCLE = 2 };                                // :267-269
 enum { DYN_NONE = 0, DYN_INTEGRATOR = 1, DYN_FILTER = 2, DYN_FILTEREXACT = 3, DYN_MUSCLE = 4 };   // :244-248
-enum { TRN_JOINT = 0, TRN_TENDON = 1 };   // transmissions built (mjTRN_JOINT / JOINTINPARENT on scalar joints, mjTRN_TENDON)
+enum { TRN_JOINT = 0, TRN_TENDON = 1, TRN_BALL = 2, TRN_FREE = 3 };   // TRN_BALL / TRN_FREE: 3D / 6D gear on a ball / free joint;   // transmissions built (mjTRN_JOINT / JOINTINPARENT on scalar joints, mjTRN_TENDON)
 enum { DSBL_CONSTRAINT = 1 << 0, DSBL_EQUALITY = 1 << 1, DSBL_FRICTIONLOSS = 1 << 2, DSBL_LIMIT = 1 << 3,
        DSBL_CONTACT = 1 << 4, DSBL_SPRING = 1 << 5, DSBL_DAMPER = 1 << 6, DSBL_GRAVITY = 1 << 7,
        DSBL_CLAMPCTRL = 1 << 8, DSBL_WARMSTART = 1 << 9, DSBL_FILTERPARENT = 1 << 10,
@@ -102,7 +102,7 @@ struct Options {
   X(ten_J_rownnz) X(ten_J_rowadr) X(ten_J_colind)                                            \
   X(actuator_trnjnt) X(actuator_gaintype) X(actuator_biastype) X(actuator_ctrllimited)       \
   X(actuator_forcelimited) X(actuator_trntype) X(actuator_dyntype) X(actuator_actadr)        \
-  X(actuator_actlimited) X(actuator_actearly) X(tendon_actfrclimited) X(body_mocapid) X(site_type) X(jnt_actgravcomp)        \
+  X(actuator_actlimited) X(actuator_actearly) X(tendon_actfrclimited) X(body_mocapid) X(site_type) X(jnt_actgravcomp) X(actuator_inparent)        \
   X(pair_geom1) X(pair_geom2) X(pair_dim)                                                     \
   X(lvl_adr) X(lvl_body) X(child_adr) X(child_id)                                             \
   X(dlvl_adr) X(dlvl_dof) X(mt_adr) X(mt_dof) X(mt_qadr)                                      \
@@ -125,7 +125,7 @@ struct Options {
   X(tendon_dampingpoly_eff) X(tendon_lengthspring) X(tendon_armature_eff)                    \
   X(actuator_gear0) X(actuator_gainprm) X(actuator_biasprm) X(actuator_ctrlrange)            \
   X(actuator_forcerange) X(actuator_dynprm) X(actuator_actrange) X(actuator_lengthrange) X(actuator_acc0) \
-  X(site_size) X(body_gravcomp) X(tendon_frictionloss) X(tendon_solref_fri) X(tendon_solimp_fri) X(tendon_actfrcrange)      \
+  X(site_size) X(body_gravcomp) X(actuator_gear6) X(actuator_wrapperiod) X(tendon_frictionloss) X(tendon_solref_fri) X(tendon_solimp_fri) X(tendon_actfrcrange)      \
   X(pair_margin) X(pair_includemargin) X(pair_solref) X(pair_solimp) X(pair_friction) X(sensor_cutoff) X(site_pos) X(site_quat)            \
   X(eq_data) X(eq_solref) X(eq_solimp) X(tendon_length0)
 
@@ -150,7 +150,7 @@ struct DModel {
   X(geom_xpos, 3 * S.ngeom) X(geom_xmat, 9 * S.ngeom) X(subtree_com, 3 * S.nbody)            \
   X(cinert, 10 * S.nbody) X(cdof, 6 * S.nv) X(crb, 10 * S.nbody) X(M, S.nC) X(qLD, S.nC)      \
   X(qLDiagInv, S.nv) X(ten_length, S.ntendon) X(ten_J, S.nJten)                              \
-  X(actuator_length, S.nu) X(actuator_moment, S.nu)                                          \
+  X(actuator_length, S.nu) X(actuator_moment, S.nu) X(actuator_mom6, 6 * S.nu * S.actfeat)    \
   X(ten_velocity, S.ntendon) X(actuator_velocity, S.nu) X(cvel, 6 * S.nbody)                 \
   X(cdof_dot, 6 * S.nv) X(qfrc_gravcomp, S.nv * S.gravcomp) X(qfrc_spring, S.nv) X(qfrc_damper, S.nv) X(qfrc_passive, S.nv)      \
   X(qfrc_bias, S.nv) X(actuator_force, S.nu) X(qfrc_actuator, S.nv) X(qfrc_smooth, S.nv)     \
