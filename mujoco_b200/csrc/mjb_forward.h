@@ -60,6 +60,32 @@ MJB_HD void check_vec(const Env& d, FD v, int n, int warn) {
   MJB_PSYNC();
 }
 
+// site transmissions without a reference site (engine_core_smooth.c:1573-1593): the 6D gear, expressed in
+// the world through the site frame, projected on the site's translational and rotational Jacobians
+MJB_HD void site_moment(const Env& d) {
+  const DModel& m = d.m;
+  if (!(d.feat & FEAT_ACT) || !m.sz.sitetrn) return;
+  const int nv = m.sz.nv;
+  FD row = d.actuator_momrow(), cdof = d.cdof();
+  for (int u = 0; u < m.sz.nu; u++) {
+    if (m.actuator_trntype[u] != TRN_SITE) continue;
+    const int sid = m.actuator_trnjnt[u], body = m.site_bodyid[sid];
+    const double* gear = m.actuator_gear6 + 6 * u;
+    const M3 sm = ld9(d.site_xmat(), 9 * sid);
+    const V3 sp = ld3(d.site_xpos(), 3 * sid);
+    const V3 wt = mulmv(sm, V3{gear[0], gear[1], gear[2]}), wr = mulmv(sm, V3{gear[3], gear[4], gear[5]});
+    const double w[6] = {wt.x, wt.y, wt.z, wr.x, wr.y, wr.z};
+    MJB_PFOR(j, nv) {
+      double m1 = 0, m2 = 0;   // mju_mulMatTVec skips rows whose wrench component is zero
+      const bool in = m.body_dofanc[(long)body * nv + j];
+      for (int r = 0; r < 3; r++) if (w[r]) m1 += jac_elem(d, sp, body, r, j) * w[r];
+      for (int r = 0; r < 3; r++) if (w[3 + r]) m2 += (in ? cdof[6 * j + r] : 0.0) * w[3 + r];
+      row[(long)u * nv + j] = m1 + m2;
+    }
+  }
+  MJB_PSYNC();
+}
+
 MJB_HD void fwd_position(const Env& d) {
   kinematics(d);
   com_pos(d);
@@ -76,6 +102,7 @@ MJB_HD void fwd_position(const Env& d) {
   make_islands(d);
   project_constraint(d);
   transmission(d);
+  site_moment(d);
 }
 
 // gravity compensation (mj_gravcomp, engine_passive.c:846-866; mj_applyFT with a zero torque): per body an
@@ -124,6 +151,11 @@ MJB_HD void fwd_velocity(const Env& d) {
       const int t = m.actuator_trnjnt[i], adr = m.ten_J_rowadr[t], nnz = m.ten_J_rownnz[t];
       const double g = mom[i];
       av[i] = dot_sparse_ref(nnz, [&](int c) { return tJ[adr + c] * g; }, [&](int c) { return qvel[m.ten_J_colind[adr + c]]; });
+    } else if ((d.feat & FEAT_ACT) && m.actuator_trntype[i] == TRN_SITE) {   // sparse dot over the nonzero moments
+      FD row = d.actuator_momrow() + (long)i * m.sz.nv;
+      int idx[64], nnz = 0;
+      for (int c = 0; c < m.sz.nv; c++) if (row[c]) idx[nnz++] = c;
+      av[i] = dot_sparse_ref(nnz, [&](int c) { return row[idx[c]]; }, [&](int c) { return qvel[idx[c]]; });
     } else if ((d.feat & FEAT_ACT) && m.actuator_trntype[i] >= TRN_BALL) {
       const int da = m.jnt_dofadr[m.actuator_trnjnt[i]], nd = (m.actuator_trntype[i] == TRN_FREE) ? 6 : 3;
       FD m6 = d.actuator_mom6();
@@ -326,6 +358,11 @@ MJB_HD void fwd_actuation(const Env& d) {
         for (int c = 0; c < nnz; c++) qfa[m.ten_J_colind[adr + c]] += (tJ[adr + c] * mom[i]) * s;
         continue;
       }
+      if (stateful && m.actuator_trntype[i] == TRN_SITE) {
+        FD row = d.actuator_momrow() + (long)i * nv;
+        for (int c = 0; c < nv; c++) if (row[c]) qfa[c] += row[c] * s;
+        continue;
+      }
       if (stateful && m.actuator_trntype[i] >= TRN_BALL) {
         const int da = m.jnt_dofadr[m.actuator_trnjnt[i]], nd = (m.actuator_trntype[i] == TRN_FREE) ? 6 : 3;
         FD m6 = d.actuator_mom6();
@@ -477,6 +514,9 @@ MJB_HD void implicitfast_advance(const Env& d) {
             if (col == j) { Jj = tJ[ta + c] * mom[u]; hj = true; }
           }
           if (hi && hj) q += Jj * (Ji * aB[u]);
+        } else if ((d.feat & FEAT_ACT) && m.actuator_trntype[u] == TRN_SITE) {
+          FD row = d.actuator_momrow() + (long)u * nv;
+          if (row[i] && row[j]) q += row[j] * (row[i] * aB[u]);
         } else if ((d.feat & FEAT_ACT) && m.actuator_trntype[u] >= TRN_BALL) {   // moment row on the joint's 3 / 6 dofs
           const int da = m.jnt_dofadr[m.actuator_trnjnt[u]], nd = (m.actuator_trntype[u] == TRN_FREE) ? 6 : 3;
           if (i >= da && i < da + nd && j >= da && j < da + nd) {

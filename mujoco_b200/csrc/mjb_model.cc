@@ -347,8 +347,10 @@ int check_model(const mjModel* m) {
   if (m->nout != m->nu || m->nactuator != m->nu) FAIL("multi-input/multi-output actuators");
   for (int i = 0; i < m->nactuator; i++) {
     int tt = m->actuator_trntype[i];
-    if (tt != mjTRN_JOINT && tt != mjTRN_JOINTINPARENT && tt != mjTRN_TENDON) FAIL("actuator %d: transmission other than joint / tendon", i);
-    if (tt != mjTRN_TENDON) {
+    if (tt != mjTRN_JOINT && tt != mjTRN_JOINTINPARENT && tt != mjTRN_TENDON && tt != mjTRN_SITE) FAIL("actuator %d: transmission other than joint / tendon / site", i);
+    if (tt == mjTRN_SITE && m->actuator_trnid[2 * i + 1] >= 0) FAIL("actuator %d: site transmission with a reference site", i);
+    if (tt == mjTRN_SITE && (m->actuator_damping[i] != 0 || m->actuator_armature[i] != 0)) FAIL("actuator %d: actuator damping / armature on a site transmission", i);
+    if (tt != mjTRN_TENDON && tt != mjTRN_SITE) {
       int jt = m->jnt_type[m->actuator_trnid[2 * i]];
       if ((jt == mjJNT_BALL || jt == mjJNT_FREE) && (m->actuator_damping[i] != 0 || m->actuator_armature[i] != 0))
         FAIL("actuator %d: actuator damping / armature on a ball or free joint", i);
@@ -408,11 +410,13 @@ int build_host_model(const mjModel* m, int nconmax, int njmax, HostModel* out) {
   Sizes& S = D.sz;
   S.actfeat = 0;
   for (int i = 0; i < m->nu; i++)
-    if (m->actuator_dyntype[i] != mjDYN_NONE || m->actuator_trntype[i] == mjTRN_TENDON ||
+    if (m->actuator_dyntype[i] != mjDYN_NONE || m->actuator_trntype[i] == mjTRN_TENDON || m->actuator_trntype[i] == mjTRN_SITE ||
         ((m->actuator_trntype[i] == mjTRN_JOINT || m->actuator_trntype[i] == mjTRN_JOINTINPARENT) &&
          (m->jnt_type[m->actuator_trnid[2 * i]] == mjJNT_BALL || m->jnt_type[m->actuator_trnid[2 * i]] == mjJNT_FREE)) || m->actuator_gaintype[i] == mjGAIN_MUSCLE ||
         m->actuator_biastype[i] == mjBIAS_MUSCLE) S.actfeat = 1;
   S.nmocap = m->nmocap;
+  S.sitetrn = 0;
+  for (int i = 0; i < m->nu; i++) if (m->actuator_trntype[i] == mjTRN_SITE) S.sitetrn = 1;
   S.gravcomp = m->flg_gravcomp ? 1 : 0;
   if (S.gravcomp) S.actfeat = 1;
   S.nq = m->nq; S.nv = m->nv; S.nu = m->nu; S.na = m->na; S.nbody = m->nbody; S.njnt = m->njnt;
@@ -520,7 +524,7 @@ int build_host_model(const mjModel* m, int nconmax, int njmax, HostModel* out) {
   {
     std::vector<int> tt(m->nu), al(m->nu), ae(m->nu);
     for (int i = 0; i < m->nu; i++) {
-      tt[i] = (m->actuator_trntype[i] == mjTRN_TENDON) ? TRN_TENDON : TRN_JOINT;
+      tt[i] = (m->actuator_trntype[i] == mjTRN_TENDON) ? TRN_TENDON : (m->actuator_trntype[i] == mjTRN_SITE) ? TRN_SITE : TRN_JOINT;
       if (tt[i] == TRN_JOINT && m->jnt_type[m->actuator_trnid[2 * i]] == mjJNT_BALL) tt[i] = TRN_BALL;
       if (tt[i] == TRN_JOINT && m->jnt_type[m->actuator_trnid[2 * i]] == mjJNT_FREE) tt[i] = TRN_FREE;
       al[i] = m->actuator_actlimited[i];

@@ -49,7 +49,7 @@ enum { SAMEFRAME_NONE = 0, SAMEFRAME_BODY = 1, SAMEFRAME_INERTIA = 2, SAMEFRAME_
 enum { GAIN_FIXED = 0, GAIN_AFFINE = 1, GAIN_MUSCLE = 2 };                               // :256-258
 enum { BIAS_NONE = 0, BIAS_AFFINE = 1, BIAS_MUSCLE = 2 };                                // :267-269
 enum { DYN_NONE = 0, DYN_INTEGRATOR = 1, DYN_FILTER = 2, DYN_FILTEREXACT = 3, DYN_MUSCLE = 4 };   // :244-248
-enum { TRN_JOINT = 0, TRN_TENDON = 1, TRN_BALL = 2, TRN_FREE = 3 };   // TRN_BALL / TRN_FREE: 3D / 6D gear on a ball / free joint;   // transmissions built (mjTRN_JOINT / JOINTINPARENT on scalar joints, mjTRN_TENDON)
+enum { TRN_JOINT = 0, TRN_TENDON = 1, TRN_BALL = 2, TRN_FREE = 3, TRN_SITE = 4 };   // TRN_SITE: 6D gear at a site (no refsite);   // TRN_BALL / TRN_FREE: 3D / 6D gear on a ball / free joint;   // transmissions built (mjTRN_JOINT / JOINTINPARENT on scalar joints, mjTRN_TENDON)
 enum { DSBL_CONSTRAINT = 1 << 0, DSBL_EQUALITY = 1 << 1, DSBL_FRICTIONLOSS = 1 << 2, DSBL_LIMIT = 1 << 3,
        DSBL_CONTACT = 1 << 4, DSBL_SPRING = 1 << 5, DSBL_DAMPER = 1 << 6, DSBL_GRAVITY = 1 << 7,
        DSBL_CLAMPCTRL = 1 << 8, DSBL_WARMSTART = 1 << 9, DSBL_FILTERPARENT = 1 << 10,
@@ -65,6 +65,7 @@ struct Sizes {
   int nq, nv, nu, na, nbody, njnt, ngeom, ntendon, nwrap, nJten, nC, ntree;
   int nsensor, nsensordata, nsite, neq, nmocap;
   int actfeat;   // 1 when an actuator is stateful, drives a tendon or is a muscle, or a body has gravcomp (FEAT_ACT code paths)
+  int sitetrn;   // 1 when an actuator acts at a site (dense moment rows are allocated then)
   int gravcomp;  // 1 when a body has gravity compensation (qfrc_gravcomp is allocated then)
   int subtreevel;   // 1 when a sensor needs mj_subtreeVel (subtree_linvel / subtree_angmom are allocated then)
   int rnepost;   // 1 when a sensor needs mj_rnePostConstraint (cacc / cfrc_int / cfrc_ext are allocated then)
@@ -150,7 +151,7 @@ struct DModel {
   X(geom_xpos, 3 * S.ngeom) X(geom_xmat, 9 * S.ngeom) X(subtree_com, 3 * S.nbody)            \
   X(cinert, 10 * S.nbody) X(cdof, 6 * S.nv) X(crb, 10 * S.nbody) X(M, S.nC) X(qLD, S.nC)      \
   X(qLDiagInv, S.nv) X(ten_length, S.ntendon) X(ten_J, S.nJten)                              \
-  X(actuator_length, S.nu) X(actuator_moment, S.nu) X(actuator_mom6, 6 * S.nu * S.actfeat)    \
+  X(actuator_length, S.nu) X(actuator_moment, S.nu) X(actuator_mom6, 6 * S.nu * S.actfeat) X(actuator_momrow, S.nu * S.nv * S.sitetrn)    \
   X(ten_velocity, S.ntendon) X(actuator_velocity, S.nu) X(cvel, 6 * S.nbody)                 \
   X(cdof_dot, 6 * S.nv) X(qfrc_gravcomp, S.nv * S.gravcomp) X(qfrc_spring, S.nv) X(qfrc_damper, S.nv) X(qfrc_passive, S.nv)      \
   X(qfrc_bias, S.nv) X(actuator_force, S.nu) X(qfrc_actuator, S.nv) X(qfrc_smooth, S.nv)     \
