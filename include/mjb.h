@@ -82,7 +82,8 @@ MJB_API int mjb_nenv(const mjbBatch* b);
 MJB_API int mjb_reset(mjbBatch* b);
 
 /* state I/O with the reference's signature semantics; supported bits: mjSTATE_TIME, QPOS, QVEL,
- * ACT(na==0), WARMSTART, CTRL, QFRC_APPLIED  (mjSTATE_FULLPHYSICS = TIME|QPOS|QVEL|ACT|...) */
+ * ACT, WARMSTART, CTRL, QFRC_APPLIED, MOCAP_POS, MOCAP_QUAT  (mjSTATE_FULLPHYSICS = TIME|QPOS|QVEL|ACT|...;
+ * XFRC_APPLIED, and EQ_ACTIVE on models with equalities, are refused) */
 MJB_API int mjb_state_size(const mjbBatch* b, unsigned int sig);
 MJB_API int mjb_set_state(mjbBatch* b, const double* state /* [nenv][size(sig)] */, unsigned int sig);
 MJB_API int mjb_get_state(mjbBatch* b, double* state /* [nenv][size(sig)] */, unsigned int sig);
