@@ -105,6 +105,73 @@ MJB_HD void fwd_position(const Env& d) {
   site_moment(d);
 }
 
+MJB_HD void object_velocity(const Env& d, int kind, int id, V3& ang, V3& lin);   // defined with the sensors below
+MJB_HD V3 mulmTv(const M3& a, V3 v);
+
+// fluid forces, inertia-box model (mj_fluid / mj_inertiaBoxFluidModel, engine_passive.c:868-903, :1154-1210):
+// per body a viscous and a quadratic drag wrench from the body-local velocity relative to the wind, applied
+// at the body's com through mj_applyFT; bodies in order, added to qfrc_passive before gravity compensation
+MJB_HD void fluid(const Env& d) {
+  const DModel& m = d.m;
+  if (!(d.feat & FEAT_ACT) || !m.sz.fluid) return;
+  const int nv = m.sz.nv, nbody = m.sz.nbody;
+  FD ff = d.qfrc_fluid(), fp = d.qfrc_passive(), wr = d.scr_body(), cdof = d.cdof();   // wr: 6 per body (torque, force), world frame
+  const bool off = (m.opt.disableflags & DSBL_SPRING) && (m.opt.disableflags & DSBL_DAMPER);
+  if (off) { MJB_PFOR(j, nv) ff[j] = 0; MJB_PSYNC(); return; }
+  const double visc = m.opt.viscosity, dens = m.opt.density;
+  MJB_PFOR(i, nbody) {
+    for (int k = 0; k < 6; k++) wr[6 * i + k] = 0;
+    if (m.body_mass[i] < kMinVal) continue;
+    const double* in = m.body_inertia + 3 * i;
+    const double mass = m.body_mass[i];
+    const double box[3] = {sqrt(dmax(kMinVal, (in[1] + in[2] - in[0])) / mass * 6.0), sqrt(dmax(kMinVal, (in[0] + in[2] - in[1])) / mass * 6.0),
+                           sqrt(dmax(kMinVal, (in[0] + in[1] - in[2])) / mass * 6.0)};
+    const M3 xi = ld9(d.ximat(), 9 * i);
+    V3 ang, lin;
+    object_velocity(d, SOBJ_BODY, i, ang, lin);
+    ang = mulmTv(xi, ang); lin = mulmTv(xi, lin);          // flg_local = 1
+    // wind in local coordinates (mju_transformSpatial of (0, wind): the translation leaves it unchanged)
+    const V3 w0{m.opt.wind[0], m.opt.wind[1], m.opt.wind[2]};
+    const V3 dif = ld3(d.xipos(), 3 * i) - ld3(d.subtree_com(), 3 * m.body_rootid[i]);
+    const V3 lw = mulmTv(xi, w0 - cross(dif, V3{0, 0, 0}));
+    lin = lin - lw;
+    double lf[6] = {0, 0, 0, 0, 0, 0};
+    const double lv[6] = {ang.x, ang.y, ang.z, lin.x, lin.y, lin.z};
+    if (visc > 0) {
+      const double diam = (box[0] + box[1] + box[2]) / 3.0;
+      const double sa = -kPi * diam * diam * diam * visc, sl = -3.0 * kPi * diam * visc;
+      for (int k = 0; k < 3; k++) { lf[k] = lv[k] * sa; lf[3 + k] = lv[3 + k] * sl; }
+    }
+    if (dens > 0) {
+      lf[3] -= 0.5 * dens * box[1] * box[2] * fabs(lv[3]) * lv[3];
+      lf[4] -= 0.5 * dens * box[0] * box[2] * fabs(lv[4]) * lv[4];
+      lf[5] -= 0.5 * dens * box[0] * box[1] * fabs(lv[5]) * lv[5];
+      lf[0] -= dens * box[0] * (box[1] * box[1] * box[1] * box[1] + box[2] * box[2] * box[2] * box[2]) * fabs(lv[0]) * lv[0] / 64.0;
+      lf[1] -= dens * box[1] * (box[0] * box[0] * box[0] * box[0] + box[2] * box[2] * box[2] * box[2]) * fabs(lv[1]) * lv[1] / 64.0;
+      lf[2] -= dens * box[2] * (box[0] * box[0] * box[0] * box[0] + box[1] * box[1] * box[1] * box[1]) * fabs(lv[2]) * lv[2] / 64.0;
+    }
+    const V3 bt = mulmv(xi, V3{lf[0], lf[1], lf[2]}), bf = mulmv(xi, V3{lf[3], lf[4], lf[5]});
+    st3(wr, 6 * i, bt); st3(wr, 6 * i + 3, bf);
+  }
+  MJB_PSYNC();
+  MJB_PFOR(j, nv) {
+    double acc = 0;
+    for (int i = 0; i < nbody; i++) {
+      if (m.body_mass[i] < kMinVal) continue;
+      const V3 pt = ld3(d.xipos(), 3 * i);
+      const bool in = m.body_dofanc[(long)i * nv + j];
+      double qf = 0, qt = 0;   // mj_applyFT: force part, then torque part; zero components are skipped
+      for (int r = 0; r < 3; r++) { const double f = wr[6 * i + 3 + r]; if (f) qf += jac_elem(d, pt, i, r, j) * f; }
+      acc += qf;
+      for (int r = 0; r < 3; r++) { const double t = wr[6 * i + r]; if (t) qt += (in ? cdof[6 * j + r] : 0.0) * t; }
+      acc += qt;
+    }
+    ff[j] = acc;
+    fp[j] += acc;
+  }
+  MJB_PSYNC();
+}
+
 // gravity compensation (mj_gravcomp, engine_passive.c:846-866; mj_applyFT with a zero torque): per body an
 // upward force -gravity*mass*gravcomp at the body's com, mapped through the point Jacobian; bodies in order
 MJB_HD void gravcomp(const Env& d) {
@@ -170,6 +237,7 @@ MJB_HD void fwd_velocity(const Env& d) {
   MJB_PSYNC();
   com_vel(d);
   passive(d);
+  fluid(d);
   gravcomp(d);
   reference_constraint(d);
   rne_bias(d);

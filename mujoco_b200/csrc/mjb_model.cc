@@ -336,7 +336,10 @@ int check_model(const mjModel* m) {
   if (m->opt.noslip_iterations > 0) FAIL("noslip solver");
   if (m->opt.enableflags & (mjENBL_OVERRIDE | mjENBL_SLEEP | mjENBL_DIAGEXACT | mjENBL_ENERGY))
     FAIL("enable flags override/sleep/diagexact/energy");
-  if (m->opt.density != 0 || m->opt.viscosity != 0) FAIL("fluid forces (density/viscosity)");
+  if (m->opt.density != 0 || m->opt.viscosity != 0) {   // inertia-box fluid model only
+    for (int i = 0; i < m->ngeom; i++) if (m->geom_fluid[mjNFLUID * i] > 0) FAIL("geom %d: ellipsoid fluid model", i);
+    if (m->opt.integrator == mjINT_IMPLICITFAST) FAIL("fluid forces with implicitfast (velocity derivatives of the fluid forces)");
+  }
   if (m->opt.disableflags & mjDSBL_ISLAND) { /* monolithic solve: fine for single-tree models */ }
   for (int i = 0; i < m->ngeom; i++) {
     if (m->geom_adhesion[i] != 0) FAIL("geom adhesion");
@@ -415,6 +418,8 @@ int build_host_model(const mjModel* m, int nconmax, int njmax, HostModel* out) {
          (m->jnt_type[m->actuator_trnid[2 * i]] == mjJNT_BALL || m->jnt_type[m->actuator_trnid[2 * i]] == mjJNT_FREE)) || m->actuator_gaintype[i] == mjGAIN_MUSCLE ||
         m->actuator_biastype[i] == mjBIAS_MUSCLE) S.actfeat = 1;
   S.nmocap = m->nmocap;
+  S.fluid = (m->opt.density != 0 || m->opt.viscosity != 0) ? 1 : 0;
+  if (S.fluid) S.actfeat = 1;
   S.sitetrn = 0;
   for (int i = 0; i < m->nu; i++) if (m->actuator_trntype[i] == mjTRN_SITE) S.sitetrn = 1;
   S.gravcomp = m->flg_gravcomp ? 1 : 0;
@@ -436,6 +441,8 @@ int build_host_model(const mjModel* m, int nconmax, int njmax, HostModel* out) {
   O.timestep = m->opt.timestep; O.impratio = m->opt.impratio; O.tolerance = m->opt.tolerance;
   O.ls_tolerance = m->opt.ls_tolerance;
   for (int i = 0; i < 3; i++) O.gravity[i] = m->opt.gravity[i];
+  O.density = m->opt.density; O.viscosity = m->opt.viscosity;
+  for (int i = 0; i < 3; i++) O.wind[i] = m->opt.wind[i];
   O.meaninertia = m->stat.meaninertia;
   O.integrator = m->opt.integrator; O.cone = m->opt.cone; O.solver = m->opt.solver;
   O.iterations = m->opt.iterations; O.ls_iterations = m->opt.ls_iterations;

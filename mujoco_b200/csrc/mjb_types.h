@@ -66,6 +66,7 @@ struct Sizes {
   int nsensor, nsensordata, nsite, neq, nmocap;
   int actfeat;   // 1 when an actuator is stateful, drives a tendon or is a muscle, or a body has gravcomp (FEAT_ACT code paths)
   int sitetrn;   // 1 when an actuator acts at a site (dense moment rows are allocated then)
+  int fluid;     // 1 when the medium has density or viscosity (qfrc_fluid is allocated then)
   int gravcomp;  // 1 when a body has gravity compensation (qfrc_gravcomp is allocated then)
   int subtreevel;   // 1 when a sensor needs mj_subtreeVel (subtree_linvel / subtree_angmom are allocated then)
   int rnepost;   // 1 when a sensor needs mj_rnePostConstraint (cacc / cfrc_int / cfrc_ext are allocated then)
@@ -81,6 +82,7 @@ struct Sizes {
 struct Options {
   double timestep, impratio, tolerance, ls_tolerance;
   double gravity[3];
+  double density, viscosity, wind[3];   // medium (inertia-box fluid model)
   double meaninertia;   // m->stat.meaninertia
   int integrator, cone, solver, iterations, ls_iterations, disableflags, enableflags;
   int dense;            // mj_isSparse(m) == 0
@@ -153,7 +155,7 @@ struct DModel {
   X(qLDiagInv, S.nv) X(ten_length, S.ntendon) X(ten_J, S.nJten)                              \
   X(actuator_length, S.nu) X(actuator_moment, S.nu) X(actuator_mom6, 6 * S.nu * S.actfeat) X(actuator_momrow, S.nu * S.nv * S.sitetrn)    \
   X(ten_velocity, S.ntendon) X(actuator_velocity, S.nu) X(cvel, 6 * S.nbody)                 \
-  X(cdof_dot, 6 * S.nv) X(qfrc_gravcomp, S.nv * S.gravcomp) X(qfrc_spring, S.nv) X(qfrc_damper, S.nv) X(qfrc_passive, S.nv)      \
+  X(cdof_dot, 6 * S.nv) X(qfrc_gravcomp, S.nv * S.gravcomp) X(qfrc_fluid, S.nv * S.fluid) X(qfrc_spring, S.nv) X(qfrc_damper, S.nv) X(qfrc_passive, S.nv)      \
   X(qfrc_bias, S.nv) X(actuator_force, S.nu) X(qfrc_actuator, S.nv) X(qfrc_smooth, S.nv)     \
   X(qacc_smooth, S.nv) X(qfrc_constraint, S.nv) X(qacc, S.nv) X(qH, S.nC)                    \
   X(qHDiagInv, S.nv)                                                                         \

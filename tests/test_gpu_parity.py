@@ -296,3 +296,20 @@ def test_mocap_and_tendon_friction_vs_oracle():
             worst = max(worst, np.abs(out[e, k] - r).max() / max(1.0, np.abs(r).max()))
     print("mocap rollout worst rel err %.3e" % worst)
     assert worst < RTOL_TRAJ
+
+
+def test_fluid_forces_vs_oracle():
+    """inertia-box fluid forces (density, viscosity, wind) on the device - models/ant_fluid.xml"""
+    assert available()
+    path = os.path.join(ROOT, "models", "ant_fluid.mjb")
+    nenv, nstep = 12, 100
+    m, b, o = make_pair(path, mb.SOLVER_NEWTON, nenv=nenv)
+    s0 = perturbed_states(o, nenv, seed=14, height=[0.35, 0.5, 0.75], qvel_std=1.5, qpos_std=0.05)
+    ctrl = np.random.default_rng(15).uniform(-1, 1, (nenv, nstep, o.size("nu")))
+    out = b.rollout(s0, ctrl)
+    ref, stats, _ = o.rollout(s0, ctrl, nthread=os.cpu_count() or 1)
+    assert stats[:, 3].sum() == 0 and (b.warnings() == 0).all()
+    err = (np.abs(out - ref) / np.maximum(1.0, np.abs(ref).max(axis=(0, 1)))).max(axis=(0, 2))
+    print("fluid rollout rel err: step 30 %.3e, step 100 %.3e" % (err[:30].max(), err.max()))
+    assert err[:30].max() < RTOL_TIGHT and err.max() < RTOL_TRAJ
+    compare_forward(b, o, ref[:, 50, :], ctrl[:, 50, :], rtol=RTOL_TIGHT, check_dual=False)

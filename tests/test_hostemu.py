@@ -451,3 +451,21 @@ def test_mocap_body_bit_exact(solver):
                 # incl. subtreelinvel / subtreeangmom (mj_subtreeVel) of moving, static and leaf subtrees
                 assert np.array_equal(gsens[e, k], np.array(oe.dfield("sensordata"))), (e, k, moving)
     assert not np.array_equal(out, out_default)
+
+
+@pytest.mark.parametrize("solver,integrator", [(mb.SOLVER_NEWTON, mb.INT_EULER), (mb.SOLVER_PGS, mb.INT_EULER),
+                                               (mb.SOLVER_NEWTON, mb.INT_RK4)])
+def test_fluid_forces_bit_exact(solver, integrator):
+    """medium with density, viscosity and wind (inertia-box fluid model, mj_inertiaBoxFluidModel): per-body
+    viscous + quadratic drag wrench from the body-local velocity, mapped by mj_applyFT - models/ant_fluid.xml"""
+    path = os.path.join(ROOT, "models", "ant_fluid.mjb")
+    nenv, nstep = 6, 120
+    m, b, o = make_pair(path, solver, library=hostemu_lib(), nenv=nenv, integrator=integrator)
+    s0 = perturbed_states(o, nenv, seed=14, height=[0.35, 0.5, 0.75], qvel_std=1.5, qpos_std=0.05)
+    ctrl = np.random.default_rng(15).uniform(-1, 1, (nenv, nstep, o.size("nu")))
+    compare_forward(b, o, s0, ctrl[:, 0], rtol=0, exact=True, check_dual=(solver == mb.SOLVER_PGS))
+    out = b.rollout(s0, ctrl)
+    ref, stats, _ = o.rollout(s0, ctrl, nthread=4)
+    assert stats[:, 3].sum() == 0
+    assert np.array_equal(out, ref)
+    assert np.abs(b.field("qfrc_fluid")).max() > 0
