@@ -25,7 +25,7 @@ enum {  // mjtState bits (include/mujoco/mjtype.h:503-517)
   ST_PLUGIN = 1 << 13
 };
 const unsigned kSupportedState = ST_TIME | ST_QPOS | ST_QVEL | ST_ACT | ST_HISTORY | ST_WARMSTART | ST_CTRL |
-                                 ST_QFRC_APPLIED | ST_EQ_ACTIVE | ST_MOCAP_POS | ST_MOCAP_QUAT | ST_USERDATA | ST_PLUGIN;
+                                 ST_QFRC_APPLIED | ST_XFRC_APPLIED | ST_EQ_ACTIVE | ST_MOCAP_POS | ST_MOCAP_QUAT | ST_USERDATA | ST_PLUGIN;
 }  // namespace
 
 struct mjbBatch_ {
@@ -128,6 +128,7 @@ mjbBatch* mjb_make_batch(const struct mjModel_* m, int nenv, int nconmax, int nj
   // small models (<= 16 bodies and dofs) with a primal solver: two environments per warp.  PGS keeps a
   // whole warp per environment (its on-chip sweep uses warp-wide shuffles).  MJB_LANES=32|16 overrides.
   b.nlane = (H.sz.nbody <= 16 && H.sz.nv <= 16 && H.opt.solver != SOL_PGS) ? 16 : 32;
+  b.xfrc = 0;
   if (const char* ls = getenv("MJB_LANES")) { const int v = atoi(ls); if (v == 16 || v == 32) b.nlane = v; }
   b.dpitch = ((size_t)b.L.ndbl + 15) / 16 * 16;   // env-major blocks, 128-byte aligned
   b.ipitch = ((size_t)b.L.nint + 31) / 32 * 32;
@@ -173,7 +174,6 @@ static int state_segments(const mjbBatch* B, unsigned sig, std::vector<Seg>* seg
   const Sizes& S = B->hm.dm.sz;
   const Layout& L = B->b.L;
   if (sig & ~kSupportedState) return -1;
-  if (sig & ST_XFRC_APPLIED) return -1;
   segs->clear();
   if (sig & ST_TIME) segs->push_back({L.time, 1});
   if (sig & ST_QPOS) segs->push_back({L.qpos, S.nq});
@@ -183,6 +183,7 @@ static int state_segments(const mjbBatch* B, unsigned sig, std::vector<Seg>* seg
   if (sig & ST_WARMSTART) segs->push_back({L.qacc_warmstart, S.nv});
   if (sig & ST_CTRL) segs->push_back({L.ctrl, S.nu});
   if (sig & ST_QFRC_APPLIED) segs->push_back({L.qfrc_applied, S.nv});
+  if (sig & ST_XFRC_APPLIED) segs->push_back({L.xfrc_applied, 6 * S.nbody});
   if ((sig & ST_EQ_ACTIVE) && S.neq) return -1;   // eq_active is not a runtime input of this path (eq_active0 is used)
   if ((sig & ST_MOCAP_POS) && S.nmocap) segs->push_back({L.mocap_pos, 3 * S.nmocap});
   if ((sig & ST_MOCAP_QUAT) && S.nmocap) segs->push_back({L.mocap_quat, 4 * S.nmocap});
@@ -201,6 +202,7 @@ int mjb_state_size(const mjbBatch* B, unsigned int sig) {
 int mjb_set_state(mjbBatch* B, const double* state, unsigned int sig) {
   std::vector<Seg> segs;
   if (!B || !state || state_segments(B, sig, &segs)) return fail(MJB_ERR_ARG, "mjb_set_state: bad arguments / unsupported signature");
+  if (sig & ST_XFRC_APPLIED) B->b.xfrc = 1;
   int ns = 0;
   for (auto& s : segs) ns += s.n;
   std::vector<double> tmp;
@@ -330,6 +332,8 @@ int mjb_rollout(mjbBatch* B, int nstep, unsigned int control_spec, const double*
   {
     if (!(control_spec & ST_CTRL) || !control) field_zero(B, false, B->b.L.ctrl, B->hm.dm.sz.nu);
     if (!(control_spec & ST_QFRC_APPLIED) || !control) field_zero(B, false, B->b.L.qfrc_applied, nv);
+    if ((control_spec & ST_XFRC_APPLIED) && control) B->b.xfrc = 1;
+    else if (B->b.xfrc) field_zero(B, false, B->b.L.xfrc_applied, 6 * B->hm.dm.sz.nbody);
     const Sizes& S = B->hm.dm.sz;
     if (S.nmocap) {   // unspecified mocap inputs come from the model (rollout.cc:98-109)
       const DModel& hm = B->hm.dm;
@@ -463,6 +467,7 @@ int mjb_get_field_int(mjbBatch* B, const char* name, int* out) {
 int mjb_set_field(mjbBatch* B, const char* name, const double* in) {
   long off, cnt; bool is_int;
   if (!B || !in || !find_field(B, name, &off, &cnt, &is_int) || is_int) return fail(MJB_ERR_ARG, std::string("mjb_set_field: unknown double field ") + (name ? name : ""));
+  if (!strcmp(name, "xfrc_applied")) B->b.xfrc = 1;
   return field_from_host(B, false, off, cnt, in);
 }
 
@@ -473,7 +478,7 @@ int mjb_set_field(mjbBatch* B, const char* name, const double* in) {
 // every fixed-size mjData array the path computes is written back under the same member name, so code
 // that reads mjData after mj_step keeps working.  Arena-allocated members (contact, efc_*) are not
 // materialised on the host; ncon / nefc and the warning counters are.
-#define MJB_MJDATA_IN(X) X(qpos, nq) X(qvel, nv) X(act, na) X(mocap_pos, 3 * nmocap) X(mocap_quat, 4 * nmocap) X(ctrl, nu) X(qfrc_applied, nv) X(qacc_warmstart, nv)
+#define MJB_MJDATA_IN(X) X(qpos, nq) X(qvel, nv) X(act, na) X(mocap_pos, 3 * nmocap) X(mocap_quat, 4 * nmocap) X(xfrc_applied, 6 * nbody) X(ctrl, nu) X(qfrc_applied, nv) X(qacc_warmstart, nv)
 #define MJB_MJDATA_OUT(X)                                                                                   \
   X(qpos, nq) X(qvel, nv) X(act, na) X(act_dot, na) X(qacc_warmstart, nv) X(qacc, nv)                       \
   X(xpos, 3 * nbody) X(xquat, 4 * nbody) X(xmat, 9 * nbody) X(xipos, 3 * nbody) X(ximat, 9 * nbody)         \
@@ -492,6 +497,8 @@ int mjb_step_mjdata(mjbBatch* B, struct mjData_* const* dd, int nd) {
   const int nq = S.nq, nv = S.nv, nu = S.nu, na = S.na, nmocap = S.nmocap, nbody = S.nbody, njnt = S.njnt, ngeom = S.ngeom, ntendon = S.ntendon, nC = S.nC;
   (void)na; (void)nmocap; (void)nbody; (void)njnt; (void)ngeom; (void)ntendon; (void)nC;
   std::vector<double> tmp;
+  for (int e = 0; e < nenv && !B->b.xfrc; e++)
+    for (int k = 0; k < 6 * nbody; k++) if (d[e]->xfrc_applied[k] != 0) { B->b.xfrc = 1; break; }
   {
     tmp.resize(nenv);
     for (int e = 0; e < nenv; e++) tmp[e] = d[e]->time;

@@ -29,6 +29,7 @@ MJB_HD void reset_env(const Env& d, bool clear_warnings) {
   for (int i = 0; i < m.sz.nv; i++) { qvel[i] = 0; ws[i] = 0; qa[i] = 0; d.qacc()[i] = 0; }
   for (int i = 0; i < m.sz.nu; i++) ctrl[i] = 0;
   for (int i = 0; i < m.sz.na; i++) { d.act()[i] = 0; d.act_dot()[i] = 0; }
+  for (int i = 0; i < 6 * m.sz.nbody; i++) d.xfrc_applied()[i] = 0;
   if (m.sz.nmocap) {   // mj_resetData: mocap poses from the model (engine_io.c:1531-1540)
     for (int i = 0; i < m.sz.nbody; i++) {
       const int mid = m.body_mocapid[i];
@@ -467,6 +468,26 @@ MJB_HD void fwd_acceleration(const Env& d) {
     qfs[i] = s;
     qas[i] = s;
   }
+  if (d.feat & FEAT_ACT) {   // Cartesian perturbations (mj_xfrcAccumulate, engine_support.c:497-512): mj_applyFT per body
+    FD xf = d.xfrc_applied(), cdof = d.cdof();
+    MJB_PFOR(j, nv) {
+      double acc = qfs[j];
+      bool any = false;
+      for (int i = 1; i < d.m.sz.nbody; i++) {
+        const double* w = &xf[6 * i];
+        if (w[0] == 0 && w[1] == 0 && w[2] == 0 && w[3] == 0 && w[4] == 0 && w[5] == 0) continue;
+        any = true;
+        const V3 pt = ld3(d.xipos(), 3 * i);
+        const bool in = d.m.body_dofanc[(long)i * nv + j];
+        double qf = 0, qt = 0;
+        for (int r = 0; r < 3; r++) if (w[r]) qf += jac_elem(d, pt, i, r, j) * w[r];
+        acc += qf;
+        for (int r = 0; r < 3; r++) if (w[3 + r]) qt += (in ? cdof[6 * j + r] : 0.0) * w[3 + r];
+        acc += qt;
+      }
+      if (any) { qfs[j] = acc; qas[j] = acc; }
+    }
+  }
   MJB_PSYNC();
   solve_LD(d, qas, d.qLD(), d.qLDiagInv());
 }
@@ -706,6 +727,13 @@ MJB_HD void rne_post(const Env& d) {
   // cfrc_ext: one lane per body, contacts in order, body 1 (subtract) before body 2 (add)
   MJB_PFOR(k, nbody) {
     S6 acc{{0, 0, 0, 0, 0, 0}};
+    if (k && (d.feat & FEAT_ACT)) {   // cfrc_ext = perturbation wrench (engine_core_smooth.c:2406-2420), moved to the subtree com
+      const double* w = &d.xfrc_applied()[6 * k];
+      if (!(w[0] == 0 && w[1] == 0 && w[2] == 0 && w[3] == 0 && w[4] == 0 && w[5] == 0)) {
+        const S6 c = transform_force(S6{{w[3], w[4], w[5], w[0], w[1], w[2]}}, ld3(sc, 3 * m.body_rootid[k]), ld3(d.xipos(), 3 * k));
+        for (int q = 0; q < 6; q++) acc.v[q] += c.v[q];
+      }
+    }
     if (k) {
       for (int i = 0; i < ncon; i++) {
         const int a = cadr[i];

@@ -169,7 +169,7 @@ int launch_fill_zero(const Batch& b, int is_int, long off, long cnt, void* s) {
 int launch_stages(const DModel& dm, const Batch& b, int mask, int flags, void* s) {
   if (b.warp_per_env) {
     // lean kernels when the model needs none of the optional pipeline parts (FEAT_*)
-    const bool lean = dm.sz.nsensor == 0 && dm.sz.neq == 0 && dm.sz.ntree == 1 && dm.opt.integrator != INT_IMPLICITFAST && !dm.sz.actfeat;
+    const bool lean = dm.sz.nsensor == 0 && dm.sz.neq == 0 && dm.sz.ntree == 1 && dm.opt.integrator != INT_IMPLICITFAST && !dm.sz.actfeat && !b.xfrc;
     if (b.nlane == 16) {
       if (dm.opt.solver == SOL_NEWTON) { if (lean) launch_kstep_newton16_lean(dm, b, mask, flags, s); else launch_kstep_newton16(dm, b, mask, flags, s); }
       else launch_kstep_any16(dm, b, mask, flags, s);

@@ -313,3 +313,37 @@ def test_fluid_forces_vs_oracle():
     print("fluid rollout rel err: step 30 %.3e, step 100 %.3e" % (err[:30].max(), err.max()))
     assert err[:30].max() < RTOL_TIGHT and err.max() < RTOL_TRAJ
     compare_forward(b, o, ref[:, 50, :], ctrl[:, 50, :], rtol=RTOL_TIGHT, check_dual=False)
+
+
+def test_xfrc_applied_vs_oracle():
+    """Cartesian perturbations through rollout(control_spec = CTRL | XFRC_APPLIED): the batch switches from the lean
+    to the full step kernel once xfrc_applied has been written; humanoid, PGS"""
+    assert available()
+    nenv, nstep = 6, 60
+    m, b, o = make_pair(HUMANOID, mb.SOLVER_PGS, nenv=nenv, njmax=160)
+    nu, nbody = o.size("nu"), o.size("nbody")
+    s0 = perturbed_states(o, nenv, seed=14, height=[0.5, 0.9, 1.3], qvel_std=0.3, qpos_std=0.05)
+    rng = np.random.default_rng(5)
+    ctrl = rng.uniform(-1, 1, (nenv, nstep, nu))
+    plain = b.rollout(s0, ctrl)                      # lean kernel
+    xfrc = np.zeros((nenv, nstep, nbody, 6))
+    xfrc[:, :, 1, :] = rng.normal(0, 4, (nenv, nstep, 6))
+    xfrc[:, 20:40, nbody - 1, :3] = rng.normal(0, 2, (nenv, 20, 3))
+    out = b.rollout(s0, np.concatenate([ctrl, xfrc.reshape(nenv, nstep, -1)], axis=2),
+                    control_spec=mb.STATE_CTRL | mb.STATE_XFRC_APPLIED)
+    again = b.rollout(s0, ctrl)                      # full kernel, perturbations cleared: same physics as the lean one
+    assert np.array_equal(plain, again)
+    worst = 0.0
+    for e in range(nenv):
+        oe = Oracle(HUMANOID)
+        oe.set_opt("solver", mb.SOLVER_PGS)
+        oe.reset()
+        oe.set_state(s0[e])
+        for k in range(nstep):
+            oe.dfield("ctrl")[:] = ctrl[e, k]
+            oe.dfield("xfrc_applied")[:] = xfrc[e, k]
+            oe.step()
+            r = oe.get_state()
+            worst = max(worst, np.abs(out[e, k] - r).max() / max(1.0, np.abs(r).max()))
+    print("xfrc rollout worst rel err %.3e" % worst)
+    assert worst < RTOL_TRAJ

@@ -190,8 +190,9 @@ def test_state_io_and_argument_errors():
         b.set_state(s[:, :-1])
     with pytest.raises(ValueError):
         b.rollout(s, np.zeros((5, 3, 7)))
+    assert b.state_size(1 << 8) == 6 * m.size("nbody")   # xfrc_applied
     with pytest.raises(mb.MjbError):
-        b.state_size(1 << 8)        # xfrc_applied unsupported
+        b.state_size(1 << 20)       # not an mjtState bit
 
 
 def test_unsupported_models_are_refused():
@@ -469,3 +470,61 @@ def test_fluid_forces_bit_exact(solver, integrator):
     assert stats[:, 3].sum() == 0
     assert np.array_equal(out, ref)
     assert np.abs(b.field("qfrc_fluid")).max() > 0
+
+
+@pytest.mark.parametrize("model,solver", [("ant_weld", mb.SOLVER_NEWTON), ("humanoid", mb.SOLVER_PGS)])
+def test_xfrc_applied_bit_exact(model, solver):
+    """Cartesian perturbation wrenches mjData.xfrc_applied (mj_xfrcAccumulate -> qfrc_smooth; cfrc_ext in
+    mj_rnePostConstraint, seen by the force / torque / accelerometer sensors of ant_weld) as a rollout input
+    (control_spec = CTRL | XFRC_APPLIED) and through the mjData bridge"""
+    from oracle_util import Oracle
+    path = os.path.join(ROOT, "models", model + ".mjb")
+    nenv, nstep = 3, 60
+    m, b, o = make_pair(path, solver, library=hostemu_lib(), nenv=nenv)
+    nu, nbody, nsens = o.size("nu"), o.size("nbody"), o.size("nsensordata")
+    s0 = perturbed_states(o, nenv, seed=14, height=[0.5, 0.9, 1.3] if model == "humanoid" else [0.35, 0.5, 0.75], qvel_std=0.3, qpos_std=0.05)
+    rng = np.random.default_rng(5)
+    ctrl = rng.uniform(-1, 1, (nenv, nstep, nu))
+    xfrc = np.zeros((nenv, nstep, nbody, 6))
+    xfrc[:, :, 1, :] = rng.normal(0, 4, (nenv, nstep, 6))            # torso: force and torque every step
+    xfrc[:, 20:40, nbody - 1, :3] = rng.normal(0, 2, (nenv, 20, 3))  # last body: a force pulse
+    xfrc[:, :, 3, 2] = 1.5                                            # constant lift on body 3 (zero components skipped)
+    spec = mb.STATE_CTRL | mb.STATE_XFRC_APPLIED
+    control = np.concatenate([ctrl, xfrc.reshape(nenv, nstep, -1)], axis=2)
+    if nsens:
+        out, sens = b.rollout(s0, control, control_spec=spec, return_sensordata=True)
+    else:
+        out = b.rollout(s0, control, control_spec=spec)
+    for e in range(nenv):
+        oe = Oracle(path)
+        oe.set_opt("solver", solver)
+        oe.reset()
+        oe.set_state(s0[e])
+        for k in range(nstep):
+            oe.dfield("ctrl")[:] = ctrl[e, k]
+            oe.dfield("xfrc_applied")[:] = xfrc[e, k]
+            oe.step()
+            assert np.array_equal(out[e, k], oe.get_state()), (e, k)
+            if nsens:
+                assert np.array_equal(sens[e, k], np.array(oe.dfield("sensordata"))), (e, k)
+    # without the bit the perturbations are cleared again (rollout.cc:92-94)
+    out0 = b.rollout(s0, ctrl)
+    ref0, _, _ = o.rollout(s0, ctrl, nthread=2)
+    assert np.array_equal(out0, ref0) and not np.array_equal(out0, out)
+    # bridge: xfrc_applied is read from the caller's mjData
+    ours = [Oracle(path) for _ in range(nenv)]
+    refs = [Oracle(path) for _ in range(nenv)]
+    b2 = mb.Batch(m, nenv, nconmax=48, njmax=160)
+    for e in range(nenv):
+        for x in (ours[e], refs[e]):
+            x.set_opt("solver", solver); x.reset(); x.set_state(s0[e])
+    for k in range(10):
+        for e in range(nenv):
+            for x in (ours[e], refs[e]):
+                x.dfield("ctrl")[:] = ctrl[e, k]
+                x.dfield("xfrc_applied")[:] = xfrc[e, k]
+            refs[e].step()
+        b2.step_mjdata([x.d for x in ours])
+        for e in range(nenv):
+            assert np.array_equal(np.array(ours[e].dfield("qpos")), np.array(refs[e].dfield("qpos"))), (e, k)
+            assert np.array_equal(np.array(ours[e].dfield("qacc")), np.array(refs[e].dfield("qacc"))), (e, k)
