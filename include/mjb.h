@@ -82,8 +82,8 @@ MJB_API int mjb_nenv(const mjbBatch* b);
 MJB_API int mjb_reset(mjbBatch* b);
 
 /* state I/O with the reference's signature semantics; supported bits: mjSTATE_TIME, QPOS, QVEL,
- * ACT, WARMSTART, CTRL, QFRC_APPLIED, XFRC_APPLIED, MOCAP_POS, MOCAP_QUAT  (mjSTATE_FULLPHYSICS =
- * TIME|QPOS|QVEL|ACT|...; EQ_ACTIVE on models with equalities is refused).  Once xfrc_applied has been written the
+ * ACT, WARMSTART, CTRL, QFRC_APPLIED, XFRC_APPLIED, MOCAP_POS, MOCAP_QUAT,  (mjSTATE_FULLPHYSICS =
+ * TIME|QPOS|QVEL|ACT|...), EQ_ACTIVE (0 / 1 as doubles, like mj_setState).  Once xfrc_applied has been written the
  * batch steps with the full kernels instead of the lean ones (a model without optional features otherwise). */
 MJB_API int mjb_state_size(const mjbBatch* b, unsigned int sig);
 MJB_API int mjb_set_state(mjbBatch* b, const double* state /* [nenv][size(sig)] */, unsigned int sig);

@@ -22,7 +22,7 @@ LIB_PATH = os.path.join(_HERE, "libmjb200.so")
 # mjtState bits (reference include/mujoco/mjtype.h:503-527)
 STATE_TIME, STATE_QPOS, STATE_QVEL, STATE_ACT, STATE_HISTORY = 1, 2, 4, 8, 16
 STATE_WARMSTART, STATE_CTRL, STATE_QFRC_APPLIED, STATE_PLUGIN = 32, 64, 128, 1 << 13
-STATE_XFRC_APPLIED, STATE_MOCAP_POS, STATE_MOCAP_QUAT = 1 << 8, 1 << 10, 1 << 11
+STATE_XFRC_APPLIED, STATE_EQ_ACTIVE, STATE_MOCAP_POS, STATE_MOCAP_QUAT = 1 << 8, 1 << 9, 1 << 10, 1 << 11
 STATE_FULLPHYSICS = STATE_TIME | STATE_QPOS | STATE_QVEL | STATE_ACT | STATE_HISTORY | STATE_PLUGIN
 
 SOLVER_PGS, SOLVER_CG, SOLVER_NEWTON = 0, 1, 2

@@ -184,7 +184,7 @@ static int state_segments(const mjbBatch* B, unsigned sig, std::vector<Seg>* seg
   if (sig & ST_CTRL) segs->push_back({L.ctrl, S.nu});
   if (sig & ST_QFRC_APPLIED) segs->push_back({L.qfrc_applied, S.nv});
   if (sig & ST_XFRC_APPLIED) segs->push_back({L.xfrc_applied, 6 * S.nbody});
-  if ((sig & ST_EQ_ACTIVE) && S.neq) return -1;   // eq_active is not a runtime input of this path (eq_active0 is used)
+  if ((sig & ST_EQ_ACTIVE) && S.neq) segs->push_back({L.eq_active, S.neq});   // values 0 / 1 as doubles, like mj_getState
   if ((sig & ST_MOCAP_POS) && S.nmocap) segs->push_back({L.mocap_pos, 3 * S.nmocap});
   if ((sig & ST_MOCAP_QUAT) && S.nmocap) segs->push_back({L.mocap_quat, 4 * S.nmocap});
   // USERDATA, PLUGIN: zero-sized on supported models
@@ -334,6 +334,12 @@ int mjb_rollout(mjbBatch* B, int nstep, unsigned int control_spec, const double*
     if (!(control_spec & ST_QFRC_APPLIED) || !control) field_zero(B, false, B->b.L.qfrc_applied, nv);
     if ((control_spec & ST_XFRC_APPLIED) && control) B->b.xfrc = 1;
     else if (B->b.xfrc) field_zero(B, false, B->b.L.xfrc_applied, 6 * B->hm.dm.sz.nbody);
+    if (B->hm.dm.sz.neq && (!(control_spec & ST_EQ_ACTIVE) || !control)) {   // rollout.cc:110-114
+      const int neq = B->hm.dm.sz.neq;
+      std::vector<double> ea((size_t)nenv * neq);
+      for (int e = 0; e < nenv; e++) for (int i = 0; i < neq; i++) ea[(size_t)e * neq + i] = B->hm.dm.eq_active0[i];
+      field_from_host(B, false, B->b.L.eq_active, neq, ea.data());
+    }
     const Sizes& S = B->hm.dm.sz;
     if (S.nmocap) {   // unspecified mocap inputs come from the model (rollout.cc:98-109)
       const DModel& hm = B->hm.dm;
@@ -512,6 +518,11 @@ int mjb_step_mjdata(mjbBatch* B, struct mjData_* const* dd, int nd) {
   }
   MJB_MJDATA_IN(X)
 #undef X
+  if (S.neq) {   // mjData.eq_active is a byte array
+    tmp.resize((size_t)nenv * S.neq);
+    for (int e = 0; e < nenv; e++) for (int i = 0; i < S.neq; i++) tmp[(size_t)e * S.neq + i] = d[e]->eq_active[i];
+    if (int rc = field_from_host(B, false, B->b.L.eq_active, S.neq, tmp.data())) return rc;
+  }
   if (int rc = run_step(B, false)) return rc;
   {
     tmp.resize(nenv);

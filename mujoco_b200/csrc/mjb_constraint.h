@@ -147,7 +147,7 @@ MJB_HD void make_constraint(const Env& d) {
     if (do_eq) {
       for (int i = 0; i < m.sz.neq; i++) {
         ieq[i] = -1;
-        if (!m.eq_active0[i]) continue;
+        if ((int)d.eq_active()[i] == 0) continue;   // runtime switch (mjData.eq_active), reset to eq_active0
         const int rows = (m.eq_kind[i] == EQ_WELD) ? 6 : (m.eq_kind[i] == EQ_CONNECT) ? 3 : 1;
         if (nefc + rows > njmax) { full = true; continue; }
         ieq[i] = nefc;

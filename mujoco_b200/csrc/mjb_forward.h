@@ -30,6 +30,7 @@ MJB_HD void reset_env(const Env& d, bool clear_warnings) {
   for (int i = 0; i < m.sz.nu; i++) ctrl[i] = 0;
   for (int i = 0; i < m.sz.na; i++) { d.act()[i] = 0; d.act_dot()[i] = 0; }
   for (int i = 0; i < 6 * m.sz.nbody; i++) d.xfrc_applied()[i] = 0;
+  for (int i = 0; i < m.sz.neq; i++) d.eq_active()[i] = m.eq_active0[i];
   if (m.sz.nmocap) {   // mj_resetData: mocap poses from the model (engine_io.c:1531-1540)
     for (int i = 0; i < m.sz.nbody; i++) {
       const int mid = m.body_mocapid[i];

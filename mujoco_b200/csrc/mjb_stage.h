@@ -90,6 +90,7 @@ MJB_HD void run_set_control(const DModel& m, const Batch& b, int e, const double
   if (spec & (1u << 6)) { FD c = d.ctrl(); for (int i = 0; i < m.sz.nu; i++) c[i] = src[k++]; }
   if (spec & (1u << 7)) { FD q = d.qfrc_applied(); for (int i = 0; i < m.sz.nv; i++) q[i] = src[k++]; }
   if (spec & (1u << 8)) { FD q = d.xfrc_applied(); for (int i = 0; i < 6 * m.sz.nbody; i++) q[i] = src[k++]; }
+  if (spec & (1u << 9)) { FD q = d.eq_active(); for (int i = 0; i < m.sz.neq; i++) q[i] = src[k++]; }
   if (spec & (1u << 10)) { FD q = d.mocap_pos(); for (int i = 0; i < 3 * m.sz.nmocap; i++) q[i] = src[k++]; }
   if (spec & (1u << 11)) { FD q = d.mocap_quat(); for (int i = 0; i < 4 * m.sz.nmocap; i++) q[i] = src[k++]; }
 }

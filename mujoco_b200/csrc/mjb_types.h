@@ -147,7 +147,7 @@ struct DModel {
 // HOT doubles: staged in shared memory by the fused warp-per-env kernel
 #define MJB_DATA_DBL_FIELDS(X, S)                                                            \
   X(time, 1) X(qpos, S.nq) X(qvel, S.nv) X(act, S.na) X(act_dot, S.na) X(mocap_pos, 3 * S.nmocap) X(mocap_quat, 4 * S.nmocap) X(ctrl, S.nu) X(qacc_warmstart, S.nv)  \
-  X(qfrc_applied, S.nv) X(xfrc_applied, 6 * S.nbody)                                         \
+  X(qfrc_applied, S.nv) X(xfrc_applied, 6 * S.nbody) X(eq_active, S.neq)                                         \
   X(xpos, 3 * S.nbody) X(xquat, 4 * S.nbody) X(xmat, 9 * S.nbody) X(xipos, 3 * S.nbody)      \
   X(ximat, 9 * S.nbody) X(xanchor, 3 * S.njnt) X(xaxis, 3 * S.njnt)                          \
   X(geom_xpos, 3 * S.ngeom) X(geom_xmat, 9 * S.ngeom) X(subtree_com, 3 * S.nbody)            \

@@ -528,3 +528,32 @@ def test_xfrc_applied_bit_exact(model, solver):
         for e in range(nenv):
             assert np.array_equal(np.array(ours[e].dfield("qpos")), np.array(refs[e].dfield("qpos"))), (e, k)
             assert np.array_equal(np.array(ours[e].dfield("qacc")), np.array(refs[e].dfield("qacc"))), (e, k)
+
+
+def test_eq_active_runtime_switch_bit_exact():
+    """mjData.eq_active as a runtime input: equalities switched off and on during a rollout through
+    control_spec = CTRL | EQ_ACTIVE (values 0 / 1 as doubles, like mj_setState), default = eq_active0"""
+    from oracle_util import Oracle
+    path = os.path.join(ROOT, "models", "ant_weld.mjb")
+    nenv, nstep = 3, 60
+    m, b, o = make_pair(path, mb.SOLVER_NEWTON, library=hostemu_lib(), nenv=nenv)
+    nu, neq = o.size("nu"), o.size("neq")
+    s0 = perturbed_states(o, nenv, seed=14, height=[0.35, 0.5, 0.75], qvel_std=0.3, qpos_std=0.05)
+    rng = np.random.default_rng(5)
+    ctrl = rng.uniform(-1, 1, (nenv, nstep, nu))
+    act = (rng.uniform(0, 1, (nenv, nstep // 10, neq)) > 0.4).astype(np.float64).repeat(10, axis=1)   # switches every 10 steps
+    spec = mb.STATE_CTRL | mb.STATE_EQ_ACTIVE
+    assert b.state_size(spec) == nu + neq
+    out = b.rollout(s0, np.concatenate([ctrl, act], axis=2), control_spec=spec)
+    for e in range(nenv):
+        oe = Oracle(path)
+        oe.set_opt("solver", mb.SOLVER_NEWTON)
+        oe.reset()
+        oe.set_state(s0[e])
+        for k in range(nstep):
+            oe.dfield("ctrl")[:] = ctrl[e, k]
+            oe.dfield("eq_active")[:] = act[e, k].astype(np.uint8)
+            oe.step()
+            assert np.array_equal(out[e, k], oe.get_state()), (e, k)
+    ref0, _, _ = o.rollout(s0, ctrl, nthread=2)          # default: every equality as in the model
+    assert np.array_equal(b.rollout(s0, ctrl), ref0) and not np.array_equal(ref0, out)
