@@ -340,7 +340,17 @@ MJB_HD void make_constraint(const Env& d) {
     else {
       const int q = (r - a) / 2 + 1;                    // friction direction 1..dim-1
       double jq = 0;
-      for (int k = 0; k < 3; k++) { const double f = cframe[9 * i + 3 * q + k]; if (f != 0) jq += jd[k] * f; }
+      if (q < 3) {
+        for (int k = 0; k < 3; k++) { const double f = cframe[9 * i + 3 * q + k]; if (f != 0) jq += jd[k] * f; }
+      } else {   // condim 4 / 6: torsional (about the normal) and rolling (about the tangents) rows use the rotational Jacobian
+        FD cdof = d.cdof();
+        const bool in1 = m.body_dofanc[(long)b1 * nv + c], in2 = m.body_dofanc[(long)b2 * nv + c];
+        for (int k = 0; k < 3; k++) {
+          const double jr = (in2 ? cdof[6 * c + k] : 0.0) - (in1 ? cdof[6 * c + k] : 0.0);
+          const double f = cframe[9 * i + 3 * (q - 3) + k];
+          if (f != 0) jq += jr * f;
+        }
+      }
       const double mu = cfri[5 * i + q - 1];
       J[(long)r * nv + c] = ((r - a) % 2 == 0) ? j0 + jq * mu : j0 + jq * (-mu);
     }

@@ -28,6 +28,7 @@ MODELS = {
     "ant_equality": os.path.join(ROOT, "models", "ant_equality.xml"),
     "ant_connect": os.path.join(ROOT, "models", "ant_connect.xml"),
     "ant_weld": os.path.join(ROOT, "models", "ant_weld.xml"),
+    "ant_condim": os.path.join(ROOT, "models", "ant_condim.xml"),
     "ant_fluid": os.path.join(ROOT, "models", "ant_fluid.xml"),
     "ant_mocap": os.path.join(ROOT, "models", "ant_mocap.xml"),
     "ant_act": os.path.join(ROOT, "models", "ant_act.xml"),

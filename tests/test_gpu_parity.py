@@ -347,3 +347,22 @@ def test_xfrc_applied_vs_oracle():
             worst = max(worst, np.abs(out[e, k] - r).max() / max(1.0, np.abs(r).max()))
     print("xfrc rollout worst rel err %.3e" % worst)
     assert worst < RTOL_TRAJ
+
+
+def test_condim_4_and_6_vs_oracle():
+    """torsional / rolling friction pyramids (condim 4 / 6) on the device - models/ant_condim.xml"""
+    assert available()
+    path = os.path.join(ROOT, "models", "ant_condim.mjb")
+    nenv, nstep = 12, 100
+    m, b, o = make_pair(path, mb.SOLVER_PGS, nenv=nenv, nconmax=48, njmax=220)
+    s0 = perturbed_states(o, nenv, seed=14, height=[0.35, 0.5, 0.75], qvel_std=0.8, qpos_std=0.05)
+    ctrl = np.random.default_rng(15).uniform(-1, 1, (nenv, nstep, o.size("nu")))
+    out = b.rollout(s0, ctrl)
+    ref, stats, _ = o.rollout(s0, ctrl, nthread=os.cpu_count() or 1)
+    assert stats[:, 3].sum() == 0 and (b.warnings() == 0).all()
+    err = (np.abs(out - ref) / np.maximum(1.0, np.abs(ref).max(axis=(0, 1)))).max(axis=(0, 2))
+    print("condim rollout rel err: step 30 %.3e, step 100 %.3e" % (err[:30].max(), err.max()))
+    assert err[:30].max() < RTOL_TIGHT and err.max() < RTOL_TRAJ
+    for t in (10, 60):
+        compare_forward(b, o, ref[:, t, :], ctrl[:, t, :], rtol=RTOL_TIGHT, check_dual=True)
+    assert b.field("con_dim").max() >= 4

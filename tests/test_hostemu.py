@@ -557,3 +557,21 @@ def test_eq_active_runtime_switch_bit_exact():
             assert np.array_equal(out[e, k], oe.get_state()), (e, k)
     ref0, _, _ = o.rollout(s0, ctrl, nthread=2)          # default: every equality as in the model
     assert np.array_equal(b.rollout(s0, ctrl), ref0) and not np.array_equal(ref0, out)
+
+
+@pytest.mark.parametrize("solver", [mb.SOLVER_PGS, mb.SOLVER_NEWTON, mb.SOLVER_CG])
+def test_condim_4_and_6_bit_exact(solver):
+    """torsional and rolling friction (condim 4 / 6): pyramids with 6 / 10 edges whose extra rows use the
+    rotational contact Jacobian (mj_contactJacobian), diagApprox with the rotational weights, contact torques in
+    the decoded contact force - models/ant_condim.xml"""
+    path = os.path.join(ROOT, "models", "ant_condim.mjb")
+    nenv, nstep = 6, 120
+    m, b, o = make_pair(path, solver, library=hostemu_lib(), nenv=nenv, nconmax=48, njmax=220)
+    s0 = perturbed_states(o, nenv, seed=14, height=[0.35, 0.5, 0.75], qvel_std=0.8, qpos_std=0.05)
+    ctrl = np.random.default_rng(15).uniform(-1, 1, (nenv, nstep, o.size("nu")))
+    compare_forward(b, o, s0, ctrl[:, 0], rtol=0, exact=True, check_dual=(solver == mb.SOLVER_PGS))
+    out = b.rollout(s0, ctrl)
+    ref, stats, _ = o.rollout(s0, ctrl, nthread=4)
+    assert stats[:, 3].sum() == 0
+    assert np.array_equal(out, ref)
+    assert b.field("con_dim").max() >= 4
