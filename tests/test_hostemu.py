@@ -570,8 +570,17 @@ def test_condim_4_and_6_bit_exact(solver):
     s0 = perturbed_states(o, nenv, seed=14, height=[0.35, 0.5, 0.75], qvel_std=0.8, qpos_std=0.05)
     ctrl = np.random.default_rng(15).uniform(-1, 1, (nenv, nstep, o.size("nu")))
     compare_forward(b, o, s0, ctrl[:, 0], rtol=0, exact=True, check_dual=(solver == mb.SOLVER_PGS))
-    out = b.rollout(s0, ctrl)
+    out, sens = b.rollout(s0, ctrl, return_sensordata=True)
     ref, stats, _ = o.rollout(s0, ctrl, nthread=4)
     assert stats[:, 3].sum() == 0
     assert np.array_equal(out, ref)
     assert b.field("con_dim").max() >= 4
+    from oracle_util import Oracle      # contact torques of the 4 / 6-dim contacts reach cfrc_ext (force / torque sensors)
+    oe = Oracle(path)
+    oe.set_opt("solver", solver)
+    oe.reset()
+    oe.set_state(s0[0])
+    for t in range(nstep):
+        oe.dfield("ctrl")[:] = ctrl[0, t]
+        oe.step()
+        assert np.array_equal(sens[0, t], np.array(oe.dfield("sensordata"))), t
