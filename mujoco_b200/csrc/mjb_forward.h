@@ -823,11 +823,12 @@ MJB_HD void object_acceleration(const Env& d, int kind, int id, bool local, V3& 
 
 // ray against a sphere / box zone (engine_ray.c: ray_quad :103, ray_sphere :242, ray_box :490); only the
 // distance is needed (>= 0: hit), normals are not
-MJB_HD double ray_quad(double a, double b, double c) {
+MJB_HD double ray_quad(double a, double b, double c, double* xx = nullptr) {
   double det = b * b - a * c;
-  if (det < 0 || a < kMinVal) return -1;
+  if (det < 0 || a < kMinVal) { if (xx) { xx[0] = -1; xx[1] = -1; } return -1; }
   det = sqrt(det);
   const double x0 = (-b - det) / a, x1 = (-b + det) / a;
+  if (xx) { xx[0] = x0; xx[1] = x1; }
   if (x0 >= 0) return x0;
   if (x1 >= 0) return x1;
   return -1;
@@ -858,6 +859,71 @@ MJB_HD double ray_box(V3 pos, const M3& mat, const double* size, V3 pnt, V3 vec)
       if (fabs(p0) <= size[f0] && fabs(p1) <= size[f1] && (x < 0 || sol < x)) x = sol;
     }
   }
+  return x;
+}
+
+// local ray (ray_map, engine_ray.c:38): point and direction in the zone's frame
+MJB_HD void ray_local(V3 pos, const M3& mat, V3 pnt, V3 vec, double* lp, double* lv) {
+  const V3 dif = pnt - pos;
+  lp[0] = mat.m[0] * dif.x + mat.m[3] * dif.y + mat.m[6] * dif.z;
+  lp[1] = mat.m[1] * dif.x + mat.m[4] * dif.y + mat.m[7] * dif.z;
+  lp[2] = mat.m[2] * dif.x + mat.m[5] * dif.y + mat.m[8] * dif.z;
+  lv[0] = mat.m[0] * vec.x + mat.m[3] * vec.y + mat.m[6] * vec.z;
+  lv[1] = mat.m[1] * vec.x + mat.m[4] * vec.y + mat.m[7] * vec.z;
+  lv[2] = mat.m[2] * vec.x + mat.m[5] * vec.y + mat.m[8] * vec.z;
+}
+MJB_HD double ray_capsule(V3 pos, const M3& mat, const double* size, V3 pnt, V3 vec) {   // engine_ray.c:272-355
+  const double ssz = size[0] + size[1];
+  if (ray_sphere(pos, ssz * ssz, pnt, vec) < 0) return -1;
+  double lp[3], lv[3], xx[2];
+  ray_local(pos, mat, pnt, vec, lp, lv);
+  double x = -1;
+  double a = lv[0] * lv[0] + lv[1] * lv[1];
+  double b = lv[0] * lp[0] + lv[1] * lp[1];
+  double c = lp[0] * lp[0] + lp[1] * lp[1] - size[0] * size[0];
+  const double sol = ray_quad(a, b, c, xx);
+  if (sol >= 0 && fabs(lp[2] + sol * lv[2]) <= size[1]) { if (x < 0 || sol < x) x = sol; }
+  double ld[3] = {lp[0], lp[1], lp[2] - size[1]};   // top cap
+  a = lv[0] * lv[0] + lv[1] * lv[1] + lv[2] * lv[2];
+  b = lv[0] * ld[0] + lv[1] * ld[1] + lv[2] * ld[2];
+  c = ld[0] * ld[0] + ld[1] * ld[1] + ld[2] * ld[2] - size[0] * size[0];
+  ray_quad(a, b, c, xx);
+  for (int i = 0; i < 2; i++) if (xx[i] >= 0 && lp[2] + xx[i] * lv[2] >= size[1]) { if (x < 0 || xx[i] < x) x = xx[i]; }
+  ld[2] = lp[2] + size[1];                          // bottom cap
+  b = lv[0] * ld[0] + lv[1] * ld[1] + lv[2] * ld[2];
+  c = ld[0] * ld[0] + ld[1] * ld[1] + ld[2] * ld[2] - size[0] * size[0];
+  ray_quad(a, b, c, xx);
+  for (int i = 0; i < 2; i++) if (xx[i] >= 0 && lp[2] + xx[i] * lv[2] <= -size[1]) { if (x < 0 || xx[i] < x) x = xx[i]; }
+  return x;
+}
+MJB_HD double ray_ellipsoid(V3 pos, const M3& mat, const double* size, V3 pnt, V3 vec) {   // engine_ray.c:358-398
+  double lp[3], lv[3];
+  ray_local(pos, mat, pnt, vec, lp, lv);
+  const double s[3] = {1 / (size[0] * size[0]), 1 / (size[1] * size[1]), 1 / (size[2] * size[2])};
+  const double a = s[0] * lv[0] * lv[0] + s[1] * lv[1] * lv[1] + s[2] * lv[2] * lv[2];
+  const double b = s[0] * lv[0] * lp[0] + s[1] * lv[1] * lp[1] + s[2] * lv[2] * lp[2];
+  const double c = s[0] * lp[0] * lp[0] + s[1] * lp[1] * lp[1] + s[2] * lp[2] * lp[2] - 1;
+  return ray_quad(a, b, c);
+}
+MJB_HD double ray_cylinder(V3 pos, const M3& mat, const double* size, V3 pnt, V3 vec) {   // engine_ray.c:401-486
+  const double ssz = size[0] * size[0] + size[1] * size[1];
+  if (ray_sphere(pos, ssz, pnt, vec) < 0) return -1;
+  double lp[3], lv[3];
+  ray_local(pos, mat, pnt, vec, lp, lv);
+  double x = -1;
+  if (fabs(lv[2]) > kMinVal) {
+    for (int side = -1; side <= 1; side += 2) {
+      const double sol = (side * size[1] - lp[2]) / lv[2];
+      if (sol < 0) continue;
+      const double p0 = lp[0] + sol * lv[0], p1 = lp[1] + sol * lv[1];
+      if (p0 * p0 + p1 * p1 <= size[0] * size[0] && (x < 0 || sol < x)) x = sol;
+    }
+  }
+  const double a = lv[0] * lv[0] + lv[1] * lv[1];
+  const double b = lv[0] * lp[0] + lv[1] * lp[1];
+  const double c = lp[0] * lp[0] + lp[1] * lp[1] - size[0] * size[0];
+  const double sol = ray_quad(a, b, c);
+  if (sol >= 0 && fabs(lp[2] + sol * lv[2]) <= size[1] && (x < 0 || sol < x)) x = sol;
   return x;
 }
 
@@ -971,8 +1037,11 @@ MJB_HD void sensors(const Env& d) {
           normalize(ray);
           if (bodyid == b2) ray = V3{ray.x * -1, ray.y * -1, ray.z * -1};
           const V3 cp = ld3(d.con_pos(), 3 * j);
-          const double hit = (m.site_type[id] == GEOM_SPHERE) ? ray_sphere(spos, m.site_size[3 * id] * m.site_size[3 * id], cp, ray)
-                                                            : ray_box(spos, smat, m.site_size + 3 * id, cp, ray);
+          const int st = m.site_type[id];
+          const double* ssz = m.site_size + 3 * id;
+          const double hit = (st == GEOM_SPHERE) ? ray_sphere(spos, ssz[0] * ssz[0], cp, ray) : (st == GEOM_BOX) ? ray_box(spos, smat, ssz, cp, ray)
+                           : (st == GEOM_CAPSULE) ? ray_capsule(spos, smat, ssz, cp, ray) : (st == GEOM_ELLIPSOID) ? ray_ellipsoid(spos, smat, ssz, cp, ray)
+                           : ray_cylinder(spos, smat, ssz, cp, ray);
           if (hit >= 0) v[0] += fn;
         }
         break;

@@ -281,9 +281,12 @@ static bool sensor_code(const mjModel* m, int i, int* code, int* okind, int* rki
     case mjSENS_FRAMELINACC: *code = SENS_FRAMELINACC; frame = true; break;
     case mjSENS_FRAMEANGACC: *code = SENS_FRAMEANGACC; frame = true; break;
     case mjSENS_SUBTREELINVEL: *code = SENS_SUBTREELINVEL; break;
-    case mjSENS_TOUCH:   // contact normal forces inside a site volume: sphere and box zones are built
+    case mjSENS_TOUCH: {   // contact normal forces inside a site volume (sphere, capsule, ellipsoid, cylinder, box zones)
       *code = SENS_TOUCH; *okind = SOBJ_SITE;
-      return m->sensor_objtype[i] == mjOBJ_SITE && (m->site_type[m->sensor_objid[i]] == mjGEOM_SPHERE || m->site_type[m->sensor_objid[i]] == mjGEOM_BOX);
+      if (m->sensor_objtype[i] != mjOBJ_SITE) return false;
+      const int st = m->site_type[m->sensor_objid[i]];
+      return st == mjGEOM_SPHERE || st == mjGEOM_CAPSULE || st == mjGEOM_ELLIPSOID || st == mjGEOM_CYLINDER || st == mjGEOM_BOX;
+    }
     case mjSENS_SUBTREEANGMOM: *code = SENS_SUBTREEANGMOM; break;
     default: return false;
   }
