@@ -30,6 +30,7 @@ MODELS = {
     "ant_weld": os.path.join(ROOT, "models", "ant_weld.xml"),
     "ant_condim": os.path.join(ROOT, "models", "ant_condim.xml"),
     "ant_fluid": os.path.join(ROOT, "models", "ant_fluid.xml"),
+    "ant_touch": os.path.join(ROOT, "models", "ant_touch.xml"),
     "ant_mocap": os.path.join(ROOT, "models", "ant_mocap.xml"),
     "ant_act": os.path.join(ROOT, "models", "ant_act.xml"),
     "ant_act_nomuscle": os.path.join(ROOT, "models", "ant_act_nomuscle.xml"),

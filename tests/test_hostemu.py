@@ -584,3 +584,29 @@ def test_condim_4_and_6_bit_exact(solver):
         oe.dfield("ctrl")[:] = ctrl[0, t]
         oe.step()
         assert np.array_equal(sens[0, t], np.array(oe.dfield("sensordata"))), t
+
+
+@pytest.mark.parametrize("solver", [mb.SOLVER_NEWTON, mb.SOLVER_PGS])
+def test_touch_zones_bit_exact(solver):
+    """touch sensors with every zone shape (sphere, box, capsule, ellipsoid, cylinder: mju_rayGeom against the
+    site volume) - models/ant_touch.xml (the mocap model plus the extra zones)"""
+    from oracle_util import Oracle
+    path = os.path.join(ROOT, "models", "ant_touch.mjb")
+    nenv, nstep = 3, 80
+    m, b, o = make_pair(path, solver, library=hostemu_lib(), nenv=nenv)
+    s0 = perturbed_states(o, nenv, seed=14, height=[0.35, 0.5, 0.75], qvel_std=0.3, qpos_std=0.05)
+    ctrl = np.random.default_rng(5).uniform(-1, 1, (nenv, nstep, o.size("nu")))
+    out, sens = b.rollout(s0, ctrl, return_sensordata=True)
+    hits = np.zeros(6, dtype=int)
+    for e in range(nenv):
+        oe = Oracle(path)
+        oe.set_opt("solver", solver)
+        oe.reset()
+        oe.set_state(s0[e])
+        for k in range(nstep):
+            oe.dfield("ctrl")[:] = ctrl[e, k]
+            oe.step()
+            r = np.array(oe.dfield("sensordata"))
+            assert np.array_equal(out[e, k], oe.get_state()) and np.array_equal(sens[e, k], r), (e, k)
+            hits += (r[12:18] != 0)
+    assert (hits > 0).all(), hits      # every zone shape saw a contact
