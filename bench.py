@@ -30,11 +30,37 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
-NENV = int(os.environ.get("MJB_BENCH_NENV", 4096))
 SETTLE = int(os.environ.get("MJB_BENCH_SETTLE", 300))
-MODEL = os.path.join(ROOT, "models", "humanoid.mjb")
-METRIC = "env-steps/sec (whole box) humanoid.xml batch 4096/GPU, PGS, Euler, random ctrl"
-WORKLOAD = "humanoid.xml x%d envs/GPU, solver=PGS, integrator=Euler, ctrl~U[-1,1] (configs[1])" % NENV
+# BASELINE.json configs: [1] is the configuration the metric is quoted on (the default); [2] is the other
+# configuration this build runs at full size.  configs[3] (humanoid100) and [4] (cube) need colliders / the
+# sparse Jacobian that mjb_check_model still refuses - `--config 3|4` says so instead of printing a number.
+CONFIGS = {
+    1: dict(model="humanoid.mjb", nenv=4096, solver=0, integrator=0, name="humanoid.xml", sname="PGS", iname="Euler"),
+    2: dict(model="ant.mjb", nenv=65536, solver=2, integrator=0, name="ant.xml", sname="Newton", iname="Euler"),
+}
+NENV = 4096
+MODEL = METRIC = WORKLOAD = None
+CFG = None
+
+
+def select_config(idx):
+    global NENV, MODEL, METRIC, WORKLOAD, CFG
+    CFG = CONFIGS[idx]
+    NENV = int(os.environ.get("MJB_BENCH_NENV", CFG["nenv"]))
+    MODEL = os.path.join(ROOT, "models", CFG["model"])
+    METRIC = "env-steps/sec (whole box) %s batch %d/GPU, %s, %s, random ctrl" % (CFG["name"], NENV, CFG["sname"], CFG["iname"])
+    WORKLOAD = "%s x%d envs/GPU, solver=%s, integrator=%s, ctrl~U[-1,1] (configs[%d])" % (
+        CFG["name"], NENV, CFG["sname"], CFG["iname"], idx)
+
+
+def config_dict(l2_note):
+    """identical keys (and values) in both arms, so that the driver can compare the two lines' `config`"""
+    return {"workload": WORKLOAD, "nenv_per_gpu": NENV, "settle_steps": SETTLE, "l2": l2_note}
+
+
+def l2_note(nq, nv, nu):
+    # every step touches the hot block of every environment; the batch is far larger than the 126 MB L2
+    return "no flush: inputs larger than L2 (per-env blocks of the whole batch are touched every step)"
 
 
 def peaks():
@@ -85,7 +111,8 @@ def reference_arm(args, rank, world):
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libmujoco_ref.so not built on this box"}))
         return
     o = Oracle(MODEL)
-    o.set_opt("solver", 0)
+    o.set_opt("solver", CFG["solver"])
+    o.set_opt("integrator", CFG["integrator"])
     nu, cores = o.size("nu"), os.cpu_count() or 1
     nthread = cores
     # each "step" = one mj_step of a bounded sample of the batch, sized to ~0.25 s per step
@@ -108,11 +135,13 @@ def reference_arm(args, rank, world):
         "metric": METRIC, "value": value, "unit": "env-steps/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * sec / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "reference",
-        "config": {"workload": WORKLOAD, "sample": "%d of %d envs per step (bounded CPU sample)" % (sample, NENV)},
+        "config": config_dict(l2_note(0, 0, 0)),
         "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": nthread, "kind": "reference",
-                         "sample": "%d envs x %d steps, mjo_rollout threads=%d" % (sample, args.steps, nthread)},
+                         "sample": "%d of %d envs x %d steps, mjo_rollout (rollout.cc loop), %d worker threads created "
+                                   "before the clock starts" % (sample, NENV, args.steps, nthread)},
         "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "mean_ncon": float(stats[:, 0].mean() / args.steps), "mean_nefc": float(stats[:, 1].mean() / args.steps),
+        "workload_stats": {"mean_ncon": float(stats[:, 0].mean() / args.steps),
+                           "mean_nefc": float(stats[:, 1].mean() / args.steps)},
     }
     print(json.dumps(line))
 
@@ -123,7 +152,13 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", type=int, default=1, help="BASELINE.json configs index (1 = the metric's configuration)")
     args = ap.parse_args()
+    if args.config not in CONFIGS:
+        print(json.dumps({"impl": args.impl, "config": {"workload": "BASELINE configs[%d]" % args.config},
+                          "unavailable": "mjb_check_model refuses this model (colliders / sparse Jacobian not built)"}))
+        return
+    select_config(args.config)
     rank = int(os.environ.get("RANK", 0))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
@@ -142,8 +177,8 @@ def main():
     K, W = args.steps, max(args.warmup, 3)
 
     model = mb.Model(MODEL)
-    model.set_option("solver", mb.SOLVER_PGS)
-    model.set_option("integrator", mb.INT_EULER)
+    model.set_option("solver", CFG["solver"])
+    model.set_option("integrator", CFG["integrator"])
     nu, nq, nv = model.size("nu"), model.size("nq"), model.size("nv")
     batch = mb.Batch(model, NENV, device=local_rank)
     stride = batch.env_stride()
@@ -178,16 +213,18 @@ def main():
         dist.barrier()
     torch.cuda.synchronize()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record(stream)
     d_last = torch.empty((1, nstate, stride), device="cuda", dtype=torch.float64)
+    c_last = c[K - 1:].contiguous()
+    gathered = torch.empty((world, NENV), device="cuda", dtype=torch.float64) if world > 1 else None
+    torch.cuda.synchronize()
+    ev0.record(stream)   # nothing but the launches of the K steps (and the boundary collective) is enqueued after this
     batch.rollout_device(K - 1, c.data_ptr(), 0)
-    batch.rollout_device(1, c[K - 1:].data_ptr(), d_last.data_ptr())
+    batch.rollout_device(1, c_last.data_ptr(), d_last.data_ptr())
     if world > 1:
         # boundary collective: ONE all-gather of per-env episode returns (final torso height),
         # enqueued on the batch stream right behind the last step
         with torch.cuda.stream(stream):
             ret = d_last[0, 3, :NENV].contiguous()
-            gathered = torch.empty((world, NENV), device="cuda", dtype=torch.float64)
             dist.all_gather_into_tensor(gathered, ret)
     ev1.record(stream)
     stream.synchronize()
@@ -282,9 +319,10 @@ def main():
             from oracle_util import Oracle, available
             if available():
                 o = Oracle(MODEL)
-                o.set_opt("solver", 0)
+                o.set_opt("solver", CFG["solver"])
+                o.set_opt("integrator", CFG["integrator"])
                 cores = os.cpu_count() or 1
-                sample, csteps = NENV, 100
+                sample, csteps = min(NENV, 8192), 100
                 s_now = batch.get_state()[:sample]
                 rng = np.random.default_rng(1)
                 cctrl = rng.uniform(-1, 1, (sample, csteps, nu))
@@ -299,10 +337,9 @@ def main():
             "metric": METRIC, "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": WORKLOAD, "nenv_per_gpu": NENV, "settle_steps": SETTLE,
-                       "l2": "no flush: bytes touched per step %.0f MB/GPU > 126 MB L2 (inputs larger than L2)" %
-                             (b_mjdata * NENV / 1e6),
-                       "mean_ncon": m_ncon, "mean_nefc": m_nefc, "mean_pgs_iter": m_iter, "warnings": warn},
+            "config": config_dict(l2_note(nq, nv, nu)),
+            "workload_stats": {"mean_ncon": m_ncon, "mean_nefc": m_nefc, "mean_solver_iter": m_iter, "warnings": warn,
+                               "bytes_touched_per_step_mb": b_mjdata * NENV / 1e6},
             "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
             "clocks": sampler.summary(),
         }

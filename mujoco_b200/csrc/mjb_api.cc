@@ -250,6 +250,7 @@ static int run_step_on(mjbBatch* B, const Batch& b, void* stream, bool skip_warn
     if (!rc) rc = backend::launch_rk4(B->dm, b, 4, later, stream);
     return rc;
   }
+  if (backend::split_step_available(B->dm, b)) return backend::launch_split_step(B->dm, b, first, later, stream);
   return backend::launch_stages(B->dm, b, 0xF, first, stream);
 }
 static int run_step(mjbBatch* B, bool skip_warned) { return run_step_on(B, B->b, B->stream, skip_warned); }

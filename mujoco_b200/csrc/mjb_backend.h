@@ -26,6 +26,10 @@ int stream_order(void* signaller, void* waiter);
 // environment in ONE launch.  flags: bit0 = part of mj_step (run the qpos/qvel checks), bit1 = skip
 // environments whose warning counters are non-zero
 int launch_stages(const DModel& dm, const Batch& b, int mask, int flags, void* stream);
+// one full Euler / implicitfast step as a split sequence of launches (PGS in its own kernel); `first` / `later`
+// are the flags of the first and the following launches of the step (rollout skip rule)
+bool split_step_available(const DModel& dm, const Batch& b);
+int launch_split_step(const DModel& dm, const Batch& b, int first, int later, void* stream);
 int launch_rk4(const DModel& dm, const Batch& b, int phase, int flags, void* stream);   // rk4_phase of every env
 int launch_reset(const DModel& dm, const Batch& b, void* stream);
 // rollout helpers; control/state are DEVICE buffers laid out [nenv][nstep][n] (reference layout)

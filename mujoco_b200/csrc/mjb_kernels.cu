@@ -166,6 +166,30 @@ int launch_fill_zero(const Batch& b, int is_int, long off, long cnt, void* s) {
   return 0;
 }
 
+// split step: position + velocity | PGS (4 lanes per environment, mjb_pgs4.cu) | finish + integrate | redo
+// launch for environments whose acceleration check failed (exits at once everywhere else).
+bool split_step_available(const DModel& dm, const Batch& b) {
+  static int want = -1;
+  if (want < 0) { const char* s = getenv("MJB_SPLIT"); want = s ? atoi(s) : 1; }
+  const bool islands = dm.sz.ntree > 1 && !(dm.opt.disableflags & DSBL_ISLAND);
+  return want && b.warp_per_env && b.nlane == 32 && dm.opt.solver == SOL_PGS && !islands &&
+         (dm.opt.integrator == INT_EULER || dm.opt.integrator == INT_IMPLICITFAST);
+}
+int launch_split_step(const DModel& dm, const Batch& b, int first, int later, void* s) {
+  const bool lean = dm.sz.nsensor == 0 && dm.sz.neq == 0 && dm.sz.ntree == 1 && dm.opt.integrator != INT_IMPLICITFAST && !dm.sz.actfeat && !b.xfrc;
+  if (lean) launch_kpart1_lean(dm, b, 0, first, s); else launch_kpart1(dm, b, 0, first, s);
+  launch_pgs4(dm, b, later, s);
+  if (lean) launch_kpart2_lean(dm, b, 0, later, s); else launch_kpart2(dm, b, 0, later, s);
+  g_launches += 3;
+  CK(cudaPeekAtLastError(), "split step launch");
+  if (!(dm.opt.disableflags & DSBL_AUTORESET)) {
+    if (lean) launch_kstep_pgs32_lean(dm, b, kMaskStep, later | 16, s); else launch_kstep_pgs32(dm, b, kMaskStep, later | 16, s);
+    g_launches++;
+    CK(cudaPeekAtLastError(), "redo launch");
+  }
+  return 0;
+}
+
 int launch_stages(const DModel& dm, const Batch& b, int mask, int flags, void* s) {
   if (b.warp_per_env) {
     // lean kernels when the model needs none of the optional pipeline parts (FEAT_*)

@@ -18,6 +18,13 @@ void launch_kstep_any16(const DModel& dm, const Batch& b, int mask, int flags, v
 void launch_kstep_pgs32_lean(const DModel& dm, const Batch& b, int mask, int flags, void* stream);
 void launch_kstep_newton32_lean(const DModel& dm, const Batch& b, int mask, int flags, void* stream);
 void launch_kstep_newton16_lean(const DModel& dm, const Batch& b, int mask, int flags, void* stream);
+// split step (PGS as its own launch): part 1 = position + velocity, part 2 = finish + check + integrate
+// (mjb_stage.h run_part); the mask argument is ignored.  mjb_pgs4.cu: the solve, 4 lanes per environment.
+void launch_kpart1_lean(const DModel& dm, const Batch& b, int mask, int flags, void* stream);
+void launch_kpart1(const DModel& dm, const Batch& b, int mask, int flags, void* stream);
+void launch_kpart2_lean(const DModel& dm, const Batch& b, int mask, int flags, void* stream);
+void launch_kpart2(const DModel& dm, const Batch& b, int mask, int flags, void* stream);
+void launch_pgs4(const DModel& dm, const Batch& b, int flags, void* stream);
 }  // namespace backend
 
 #if defined(MJB_KSTEP_INSTANCE) && defined(__CUDACC__)
@@ -38,30 +45,34 @@ constexpr int kSmemPerWarp = MJB_SMEM_PER_WARP;    // doubles = 6.5 KB: eight sw
 // instantiation carries only its own solver's code and register pressure.
 // NLANE = 16 maps TWO small environments onto each warp (models with <= 16 bodies and dofs leave half
 // of a warp idle in every cooperative loop); the two halves synchronise with their own lane masks.
-template <int SOLVER, int NLANE, int FEAT>
+// PART = 0: stages by mask (fused step).  PART = 1 / 2: the two halves of a split step, compiled without the
+// solver (no shared-memory scratch, their own register budget and a fraction of the fused kernel's code).
+template <int SOLVER, int NLANE, int FEAT, int PART>
 __global__ void __launch_bounds__(32 * kWarpsPerCta, MJB_CTAS_PER_SM) k_step_warp(DModel m, Batch b, int mask, int flags) {
   constexpr int kPerWarp = 32 / NLANE;
-  __shared__ double smem[NLANE == 32 ? kWarpsPerCta * kSmemPerWarp : 1];
+  __shared__ double smem[(NLANE == 32 && PART == 0) ? kWarpsPerCta * kSmemPerWarp : 1];
   const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
   const int e = (blockIdx.x * kWarpsPerCta + w) * kPerWarp + l / NLANE;
   if (e >= b.nenv) return;
   if (NLANE == 32) {
-    run_env(m, b, e, mask, flags, l, 32, smem + w * kSmemPerWarp, kSmemPerWarp, SOLVER, 0xffffffffu, FEAT);
+    if (PART == 0) run_env(m, b, e, mask, flags, l, 32, smem + w * kSmemPerWarp, kSmemPerWarp, SOLVER, 0xffffffffu, FEAT);
+    else run_env(m, b, e, 0, flags & ~16, l, 32, nullptr, 0, SOLVER, 0xffffffffu, FEAT, PART);
   } else {
     const unsigned lanes = ((1u << NLANE) - 1u) << ((l / NLANE) * NLANE);
-    run_env(m, b, e, mask, flags, l % NLANE, NLANE, nullptr, 0, SOLVER, lanes, FEAT);
+    run_env(m, b, e, mask, flags, l % NLANE, NLANE, nullptr, 0, SOLVER, lanes, FEAT, PART);
   }
 }
 
 
-#define MJB_KSTEP_LAUNCHER(NAME, SOLVER, NLANE, FEAT)                                                             \
+#define MJB_KSTEP_LAUNCHER_PART(NAME, SOLVER, NLANE, FEAT, PART)                                                  \
   namespace backend {                                                                                        \
   void NAME(const DModel& dm, const Batch& b, int mask, int flags, void* stream) {                            \
     const int per_cta = kWarpsPerCta * (32 / NLANE);                                                         \
     const int grid = (b.nenv + per_cta - 1) / per_cta;                                                       \
-    k_step_warp<SOLVER, NLANE, FEAT><<<grid, 32 * kWarpsPerCta, 0, (cudaStream_t)stream>>>(dm, b, mask, flags);     \
+    k_step_warp<SOLVER, NLANE, FEAT, PART><<<grid, 32 * kWarpsPerCta, 0, (cudaStream_t)stream>>>(dm, b, mask, flags);     \
   }                                                                                                          \
   }
+#define MJB_KSTEP_LAUNCHER(NAME, SOLVER, NLANE, FEAT) MJB_KSTEP_LAUNCHER_PART(NAME, SOLVER, NLANE, FEAT, 0)
 #endif
 
 }  // namespace mjb

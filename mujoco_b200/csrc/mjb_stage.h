@@ -22,11 +22,11 @@ constexpr int kMaskStep = 0xF, kMaskForward = 0x17;
 // mj_checkAcc (engine_forward.c:99-113): a bad acceleration resets the environment and the forward
 // pass is run again before integrating; that second pass is the SAME code (one loop iteration more),
 // not a second inlined copy of the pipeline.
-MJB_HD void run_stage_mask(const Env& d, int mask, int flags) {
+MJB_HD void run_stage_mask(const Env& d, int mask, int flags, int first_pass = 0) {
 #if defined(__CUDA_ARCH__)
 #pragma unroll 1
 #endif
-  for (int pass = 0; pass < 2; pass++) {
+  for (int pass = first_pass; pass < 2; pass++) {
     const bool redo = pass == 1;
     if ((mask & 1) || redo) stage_position(d, (flags & 1) != 0 && !redo);
     if ((mask & 2) || redo) stage_velocity(d);
@@ -60,16 +60,55 @@ MJB_HD bool step_enabled(const Env& d, int flags) {
   return true;
 }
 
+// SPLIT step (the PGS solve runs as its own launch between the two parts, mjb_pgs4.cu):
+//   part 1: position + velocity stages (constraint_begin included);
+//   part 2: dual finish + acceleration check + integration.  A bad acceleration only MARKS the environment
+//           (step_skip = 2); the redo launch of the fused kernel (flags bit4, below) then repeats the forward
+//           pass on the reset state and integrates - mj_checkAcc + mj_forward, engine_forward.c:99-113 - so
+//           that neither part has to carry the whole pipeline.
+MJB_HD void run_part(const Env& d, int part, int flags) {
+  if (part == 1) {
+    stage_position(d, (flags & 1) != 0);
+    stage_velocity(d);
+    return;
+  }
+  stage_finish_forward(d);
+  if ((d.feat & FEAT_SENSOR) && !(flags & 8)) sensors(d);
+  check_vec(d, d.qacc(), d.m.sz.nv, WARN_BADQACC);
+  const int bad = d.scr_int()[0];
+  MJB_PSYNC();
+  if (bad && !(d.m.opt.disableflags & DSBL_AUTORESET)) {
+    MJB_LANE0 d.step_skip()[0] = 2;
+    MJB_PSYNC();
+    return;
+  }
+  if ((d.feat & FEAT_IMPLICITFAST) && d.m.opt.integrator == INT_IMPLICITFAST) implicitfast_advance(d); else euler_advance(d);
+}
+
 // run the selected stages of one environment with its cooperative lanes.
-// flags: bit0 = part of mj_step (qpos/qvel checks), bit1/bit2 = rollout skip rule (step_enabled).
+// flags: bit0 = part of mj_step (qpos/qvel checks), bit1/bit2 = rollout skip rule (step_enabled),
+// bit4 = redo launch of a split step: only environments marked by part 2 (step_skip == 2) run, from the
+// second pass of run_stage_mask (forward on the reset state, then integration).
+// part: 0 = stages by mask (fused), 1 / 2 = parts of the split step.
 // sm/smcap: optional per-warp shared-memory scratch (doubles) used by the latency-critical loops.
 MJB_HD void run_env(const DModel& m, const Batch& b, int e, int mask, int flags, int lane, int nlane,
-                    double* sm, int smcap, int solver = -1, unsigned lanes = 0xffffffffu, int feat = FEAT_ALL) {
+                    double* sm, int smcap, int solver = -1, unsigned lanes = 0xffffffffu, int feat = FEAT_ALL,
+                    int part = 0) {
   Env d(m, b, e, lane, nlane);
   d.sm = sm; d.smcap = smcap; d.mask = lanes; d.feat = feat;
   d.solver = solver < 0 ? m.opt.solver : solver;
+  if (flags & 16) {
+    const bool marked = d.step_skip()[0] == 2;
+    MJB_PSYNC();
+    if (!marked) return;
+    MJB_LANE0 d.step_skip()[0] = 0;
+    MJB_PSYNC();
+    run_stage_mask(d, kMaskStep, flags, 1);
+    return;
+  }
   if (!step_enabled(d, flags)) return;
-  run_stage_mask(d, mask, flags);
+  if (part) run_part(d, part, flags);
+  else run_stage_mask(d, mask, flags);
 }
 
 // one phase of the Runge-Kutta step (between forward launches)

@@ -134,12 +134,22 @@ typedef struct {
   int nbatch, nstep, nstate, nu;
   const double* state0; const double* ctrl; double* state; int* stats; /* per env: [sum ncon, sum nefc, sum niter, nwarn] */
   volatile int* next; int chunk;
+  pthread_barrier_t* start;
 } RollJob;
 
 static void roll_range(RollJob* j, int lo, int hi) {
   const mjModel* m = j->m; mjData* d = j->d;
   for (int r = lo; r < hi; r++) {
-    mj_resetData(m, d);
+    /* rollout.cc:85-125: defaults for the user inputs the caller does not specify, then the initial state
+     * (no mj_resetData per environment - the reference's rollout does not reset either) */
+    mju_zero(d->ctrl, m->nu);
+    mju_zero(d->qfrc_applied, m->nv);
+    mju_zero(d->xfrc_applied, 6*m->nbody);
+    for (int i = 0; i < m->neq; i++) d->eq_active[i] = m->eq_active0[i];
+    for (int i = 0; i < m->nbody; i++) {
+      int id = m->body_mocapid[i];
+      if (id >= 0) { mju_copy3(d->mocap_pos + 3*id, m->body_pos + 3*i); mju_copy4(d->mocap_quat + 4*id, m->body_quat + 4*i); }
+    }
     mj_setState(m, d, j->state0 + (size_t)r*j->nstate, mjSTATE_FULLPHYSICS);
     mju_zero(d->qacc_warmstart, m->nv);
     for (int i = 0; i < mjNWARNING; i++) d->warning[i].number = 0;
@@ -168,6 +178,7 @@ static void roll_range(RollJob* j, int lo, int hi) {
 
 static void* roll_worker(void* arg) {
   RollJob* j = (RollJob*)arg;
+  pthread_barrier_wait(j->start);   /* the clock starts once every worker exists (the reference keeps a persistent ThreadPool) */
   for (;;) {
     int lo = __sync_fetch_and_add(j->next, j->chunk);
     if (lo >= j->nbatch) break;
@@ -187,14 +198,18 @@ EXPORT double mjo_rollout(const mjModel* m, int nbatch, int nstep, const double*
   int chunk = nbatch / (10*nthread); if (chunk < 1) chunk = 1;
   RollJob* jobs = (RollJob*)calloc(nthread, sizeof(RollJob));
   pthread_t* th = (pthread_t*)calloc(nthread, sizeof(pthread_t));
+  pthread_barrier_t start;
+  pthread_barrier_init(&start, NULL, (unsigned)nthread + 1);
   for (int i = 0; i < nthread; i++) {
-    jobs[i] = (RollJob){m, mj_makeData(m), nbatch, nstep, nstate, m->nu, state0, ctrl, state, stats, &next, chunk};
+    jobs[i] = (RollJob){m, mj_makeData(m), nbatch, nstep, nstate, m->nu, state0, ctrl, state, stats, &next, chunk, &start};
   }
   struct timespec t0, t1;
-  clock_gettime(CLOCK_MONOTONIC, &t0);
   for (int i = 0; i < nthread; i++) pthread_create(&th[i], NULL, roll_worker, &jobs[i]);
+  clock_gettime(CLOCK_MONOTONIC, &t0);
+  pthread_barrier_wait(&start);
   for (int i = 0; i < nthread; i++) pthread_join(th[i], NULL);
   clock_gettime(CLOCK_MONOTONIC, &t1);
+  pthread_barrier_destroy(&start);
   for (int i = 0; i < nthread; i++) mj_deleteData(jobs[i].d);
   free(jobs); free(th);
   return (t1.tv_sec - t0.tv_sec) + 1e-9*(t1.tv_nsec - t0.tv_nsec);

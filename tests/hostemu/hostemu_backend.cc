@@ -33,6 +33,23 @@ int launch_stages(const DModel& dm, const Batch& b, int mask, int flags, void*) 
   for (int e = 0; e < b.nenv; e++) run_env(dm, b, e, mask, flags, 0, 1, nullptr, 0);
   return 0;
 }
+// split step, emulated part by part (the CUDA build runs the solve with mjb_pgs4.cu; here the generic sweeps
+// stand in for it, so the CPU suite covers run_part and the redo launch)
+bool split_step_available(const DModel& dm, const Batch& b) {
+  const char* s = getenv("MJB_SPLIT");
+  const bool islands = dm.sz.ntree > 1 && !(dm.opt.disableflags & DSBL_ISLAND);
+  return (s ? atoi(s) : 1) && b.warp_per_env && dm.opt.solver == SOL_PGS && !islands &&
+         (dm.opt.integrator == INT_EULER || dm.opt.integrator == INT_IMPLICITFAST);
+}
+int launch_split_step(const DModel& dm, const Batch& b, int first, int later, void*) {
+  g_launches += 4;
+  for (int e = 0; e < b.nenv; e++) run_env(dm, b, e, 0, first, 0, 1, nullptr, 0, -1, 0xffffffffu, FEAT_ALL, 1);
+  for (int e = 0; e < b.nenv; e++) run_env(dm, b, e, 4, later, 0, 1, nullptr, 0);
+  for (int e = 0; e < b.nenv; e++) run_env(dm, b, e, 0, later, 0, 1, nullptr, 0, -1, 0xffffffffu, FEAT_ALL, 2);
+  if (!(dm.opt.disableflags & DSBL_AUTORESET))
+    for (int e = 0; e < b.nenv; e++) run_env(dm, b, e, kMaskStep, later | 16, 0, 1, nullptr, 0);
+  return 0;
+}
 int launch_get_sensor(const DModel& dm, const Batch& b, double* sens, int nstep, int t, int nsens, void*) {
   g_launches++;
   for (int e = 0; e < b.nenv; e++) run_get_sensor(dm, b, e, sens, nstep, t, nsens);

@@ -66,8 +66,10 @@ def compare_forward(b, o, states, ctrl, rtol, exact=False, check_dual=True):
     b.set_field("qacc_warmstart", 0.0)     # the oracle side starts from mj_resetData
     b.forward()
     got = {f: b.field(f) for f in FIELDS_POS + FIELDS_VEL + FIELDS_EFC +
-           ["efc_J", "efc_KBIP", "efc_AR", "efc_Y", "qacc", "qfrc_constraint", "con_dist", "con_pos", "con_frame"]}
-    gi = {f: b.field(f) for f in ["ncon", "nefc", "efc_type", "efc_id", "con_geom1", "con_geom2", "con_dim", "solver_niter"]}
+           ["efc_J", "efc_KBIP", "efc_AR", "efc_Y", "qacc", "qfrc_constraint", "con_dist", "con_pos", "con_frame",
+            "con_includemargin", "con_friction", "con_solref", "con_solimp"]}
+    gi = {f: b.field(f) for f in ["ncon", "nefc", "efc_type", "efc_id", "con_geom1", "con_geom2", "con_dim", "con_exclude",
+                                  "con_efcadr", "solver_niter"]}
     worst = 0.0
     nv = o.size("nv")
     for e in range(states.shape[0]):
@@ -98,6 +100,21 @@ def compare_forward(b, o, states, ctrl, rtol, exact=False, check_dual=True):
                 worst = max(worst, err)
                 assert err <= rtol, (name, e, err)
 
+        # the contact list (north_star: bit-exact contact counts / INDICES): geom pair, dimension, exclude flag and
+        # constraint address of every contact are exact; distance / position / frame / mixed parameters at 1e-12
+        con = o.contacts(max(ncon, 1))
+        assert np.array_equal(gi["con_geom1"][e, :ncon], con["geom"][:, 0]), (e, gi["con_geom1"][e, :ncon], con["geom"][:, 0])
+        assert np.array_equal(gi["con_geom2"][e, :ncon], con["geom"][:, 1]), (e, gi["con_geom2"][e, :ncon], con["geom"][:, 1])
+        assert np.array_equal(gi["con_dim"][e, :ncon], con["dim"])
+        assert np.array_equal(gi["con_exclude"][e, :ncon], con["exclude"])
+        assert np.array_equal(gi["con_efcadr"][e, :ncon], con["efc_address"]), (e, gi["con_efcadr"][e, :ncon], con["efc_address"])
+        for name, key, w in [("con_dist", "dist", 1), ("con_pos", "pos", 3), ("con_frame", "frame", 9),
+                             ("con_includemargin", "includemargin", 1), ("con_friction", "friction", 5),
+                             ("con_solref", "solref", 2), ("con_solimp", "solimp", 5)]:
+            a, r = got[name][e][:ncon * w], con[key].reshape(-1)
+            if a.size:
+                err = np.abs(a - r).max() / max(1.0, np.abs(r).max())
+                assert err <= 1e-12, (name, e, err)
         for f in FIELDS_POS + FIELDS_VEL:
             chk(f, o.dfield(f))
         for f in FIELDS_EFC:

@@ -41,6 +41,8 @@ class Oracle:
             H.mjo_data_field.argtypes = [C.c_void_p, C.c_void_p, C.c_char_p, C.POINTER(C.c_void_p), C.c_char_p, C.POINTER(C.c_long), C.POINTER(C.c_long)]
             H.mjo_opt_get.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_double), C.c_int]
             H.mjo_opt_set.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_double), C.c_int]
+            H.mjo_contacts.restype = C.c_int
+            H.mjo_contacts.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 11
             H.mjo_rollout.restype = C.c_double
             H.mjo_rollout.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
             L.mj_makeData.restype = C.c_void_p
@@ -133,6 +135,18 @@ class Oracle:
     def set_state(self, state, sig=mjSTATE_FULLPHYSICS):
         s = np.ascontiguousarray(state, dtype=np.float64)
         self.L.mj_setState(self.m, self.d, s.ctypes.data, sig)
+
+    def contacts(self, nmax=256):
+        """the mjContact list of the current mjData, flattened (oracle_helper.c mjo_contacts): dict of arrays"""
+        f = {"dist": np.zeros(nmax), "pos": np.zeros((nmax, 3)), "frame": np.zeros((nmax, 9)),
+             "geom": np.zeros((nmax, 2), dtype=np.int32), "dim": np.zeros(nmax, dtype=np.int32),
+             "efc_address": np.zeros(nmax, dtype=np.int32), "includemargin": np.zeros(nmax),
+             "friction": np.zeros((nmax, 5)), "solref": np.zeros((nmax, 2)), "solimp": np.zeros((nmax, 5)),
+             "exclude": np.zeros(nmax, dtype=np.int32)}
+        order = ["dist", "pos", "frame", "geom", "dim", "efc_address", "includemargin", "friction", "solref", "solimp", "exclude"]
+        n = self.H.mjo_contacts(self.d, nmax, *[f[k].ctypes.data for k in order])
+        assert n <= nmax
+        return {k: v[:n] for k, v in f.items()}
 
     def save_mjb(self, path):
         self.L.mj_saveModel(self.m, path.encode(), None, 0)
