@@ -178,7 +178,7 @@ bool split_step_available(const DModel& dm, const Batch& b) {
 int launch_split_step(const DModel& dm, const Batch& b, int first, int later, void* s) {
   const bool lean = dm.sz.nsensor == 0 && dm.sz.neq == 0 && dm.sz.ntree == 1 && dm.opt.integrator != INT_IMPLICITFAST && !dm.sz.actfeat && !b.xfrc;
   if (lean) launch_kpart1_lean(dm, b, 0, first, s); else launch_kpart1(dm, b, 0, first, s);
-  launch_pgs4(dm, b, later, s);
+  if (launch_pgs4(dm, b, later, s)) return cuda_fail(cudaGetLastError(), "PGS order table");
   if (lean) launch_kpart2_lean(dm, b, 0, later, s); else launch_kpart2(dm, b, 0, later, s);
   g_launches += 3;
   CK(cudaPeekAtLastError(), "split step launch");

@@ -24,7 +24,7 @@ void launch_kpart1_lean(const DModel& dm, const Batch& b, int mask, int flags, v
 void launch_kpart1(const DModel& dm, const Batch& b, int mask, int flags, void* stream);
 void launch_kpart2_lean(const DModel& dm, const Batch& b, int mask, int flags, void* stream);
 void launch_kpart2(const DModel& dm, const Batch& b, int mask, int flags, void* stream);
-void launch_pgs4(const DModel& dm, const Batch& b, int flags, void* stream);
+int launch_pgs4(const DModel& dm, const Batch& b, int flags, void* stream);
 }  // namespace backend
 
 #if defined(MJB_KSTEP_INSTANCE) && defined(__CUDACC__)

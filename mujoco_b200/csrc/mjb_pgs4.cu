@@ -17,9 +17,9 @@
 //   * the AR row, the row's constants (b, 1/AR_ii, AR_ii, lo, hi) and the old force of the NEXT row
 //     are fetched one row ahead (AR through L1: read-only during the solve, 1.2 KB per environment on
 //     average, so every sweep after the first hits L1) - no load sits between two updates;
-//   * the Fisher-Yates shuffle of the NEXT sweep (LCG step, output permutation, modulo, swap) is
-//     software-pipelined into the row loop, one swap per row: it fills issue slots the fp64 chain
-//     leaves empty instead of running serially between sweeps;
+//   * the visiting order of sweep s of a problem with n rows is a constant of (n, s) - one PCG32 stream per
+//     solve, Fisher-Yates from the identity - so all orders come from a table built once per device
+//     (pgs4_order_table): no generator, modulo or swap is left in the row loop;
 //   * zero padding is exact: a chain sum is never -0 (it starts from +0), so adding a +-0 product of
 //     the padded positions returns the same bits; the same holds for the padded tail terms.
 // Results are bit-identical to the serial reference arithmetic (tests/test_gpu_parity.py compares
@@ -29,6 +29,9 @@
 // mjb_constraint.h (global memory, any lane count) on their four lanes.
 #include <cuda_runtime.h>
 
+#include <mutex>
+#include <vector>
+
 #include "mjb_backend.h"
 #include "mjb_stage.h"
 #include "mjb_kstep.h"
@@ -36,38 +39,22 @@
 namespace mjb {
 
 constexpr int kPgs4Rows = 68;                 // row capacity of the largest register class (4 * 16 + 3, padded)
-constexpr int kPgs4EnvDbl = 9 * kPgs4Rows;    // doubles per environment slot: force fprev fmom prod b ainv ad lo hi
-constexpr int kPgs4EnvInt = 2 * kPgs4Rows + 4;    // ints: current order, next order, one dummy word per lane
+constexpr int kPgs4EnvDbl = 10 * kPgs4Rows;   // doubles per environment slot: force fprev fmom prod + 6 per row (b ainv ad lo hi -)
 // slot stride in 4-byte words == 8 (mod 32): the eight environments of a warp start on different bank groups
-constexpr int kPgs4SlotWords = ((2 * kPgs4EnvDbl + kPgs4EnvInt + 31) / 32) * 32 + 8;
+constexpr int kPgs4SlotWords = ((2 * kPgs4EnvDbl + 31) / 32) * 32 + 8;
+static_assert(kPgs4SlotWords % 32 == 8 && kPgs4SlotWords % 4 == 0, "slot stride: bank spread and 16-byte alignment");
 constexpr int kPgs4SmemBytes = 8 * kPgs4SlotWords * 4;
 
 struct Pgs4Env {
   int nefc, ne, nf;
   const double* gAR;
-  double* slot;   // shared-memory slot of this environment
+  double* slot;               // shared-memory slot of this environment
+  const unsigned char* ord;   // visiting orders of a problem with nefc rows: [sweep][position] (pgs4_order_table)
 };
 
-// one LCG step + output permutation of PCG32 (engine_solver.c:240-255), then the Fisher-Yates swap of
-// position idx (engine_solver.c:258-265) in `ord`.  Branch-free, so that the scheduler can interleave it with
-// the fp64 chain of the row: every lane of the group tracks the generator; lane 0 swaps in `ord`, the other
-// lanes (and disabled steps) "swap" their private dummy word at ord[dummy] with itself.
-__device__ __forceinline__ void pgs4_fy_step(uint64_t& st, int* ord, int idx, bool pred, bool writer, int dummy) {
-  const uint64_t old = st;
-  const uint32_t xs = (uint32_t)(((old >> 18u) ^ old) >> 27u), rot = (uint32_t)(old >> 59u);
-  const uint32_t out = (xs >> rot) | (xs << ((0u - rot) & 31));
-  const uint32_t n = (uint32_t)(idx > 0 ? idx + 1 : 1);
-  const int j = (int)(out % n);
-  const bool doit = pred && writer;
-  const int ia = doit ? idx : dummy, ib = doit ? j : dummy;
-  const int t = ord[ia], u = ord[ib];
-  ord[ia] = u;
-  ord[ib] = t;
-  st = pred ? old * 6364136223846793005ULL + 1ULL : old;
-}
-
-// all sweeps of the (up to) eight environments of this warp; returns the iteration count of the lane's environment
-template <int NQ>
+// all sweeps of the (up to) eight environments of this warp; returns the iteration count of the lane's environment.
+// DEPTH: rows whose AR operands are in flight ahead of the row being updated (2 where the registers allow it).
+template <int NQ, int DEPTH>
 __device__ __forceinline__ int pgs4_sweeps(const Options& opt, int nv, bool act, const Pgs4Env& E, int k) {
   constexpr int R = kPgs4Rows;
   const unsigned full = 0xffffffffu;
@@ -75,20 +62,14 @@ __device__ __forceinline__ int pgs4_sweeps(const Options& opt, int nv, bool act,
   double* s_fprev = s_force + R;
   double* s_fmom = s_fprev + R;
   double* s_prod = s_fmom + R;
-  const double* s_b = s_prod + R;
-  const double* s_ainv = s_b + R;
-  const double* s_ad = s_ainv + R;
-  const double* s_lo = s_ad + R;
-  const double* s_hi = s_lo + R;
-  int* ordA = (int*)(E.slot + 9 * R);
-  int* ordB = ordA + R;
-  const int dummyA = 2 * R + k, dummyB = R + k;   // the lane's dummy word, as an index relative to ordA / ordB
+  const double* s_rc = s_prod + R;   // [row][6]: b, 1/AR_ii, AR_ii, lo, hi, (pad)
   const int nefc = E.nefc;
   const int n4 = nefc & ~3, nq = n4 >> 2, tail = nefc - n4;
   const double scale = 1 / (opt.meaninertia * (nv > 1 ? nv : 1));
   const double tolerance = opt.tolerance;
   const int maxiter = opt.iterations;
   const double* __restrict__ gAR = E.gAR + k;
+  const int last = nefc > 0 ? nefc - 1 : 0;
 
   // chain forces in registers; the (up to three) tail forces are kept by every lane
   // (with their previous / extrapolated values: no lane ever reads a tail value another lane writes)
@@ -97,20 +78,18 @@ __device__ __forceinline__ int pgs4_sweeps(const Options& opt, int nv, bool act,
   for (int q = 0; q < NQ; q++) F[q] = (act && q < nq) ? s_force[4 * q + k] : 0.0;
 #pragma unroll
   for (int t = 0; t < 3; t++) { T[t] = (act && t < tail) ? s_force[n4 + t] : 0.0; TP[t] = T[t]; TM[t] = T[t]; }
-  if (act) for (int c = k; c < nefc; c += 4) { ordA[c] = c; s_fprev[c] = s_force[c]; }
-  else if (k == 0) { ordA[0] = 0; ordB[0] = 0; }   // idle lanes index row 0 of their (unused) slot
+  if (act) for (int c = k; c < nefc; c += 4) s_fprev[c] = s_force[c];
   __syncwarp();
 
-  // generator after the reference's warm-up draw (state 0, inc 1); the order of sweep 0 is shuffled up front
-  uint64_t rng = 1ULL;
-  {
-    const int top = __reduce_max_sync(full, act ? nefc : 0);
-    for (int idx = top - 1; idx >= 1; idx--) pgs4_fy_step(rng, ordA, idx, act && idx < nefc, k == 0, dummyA);
-  }
-  __syncwarp();
+  auto load_row = [&](int i, double (&A)[NQ], double (&AT)[3]) {
+    const double* row = gAR + (long)i * nefc;
+#pragma unroll
+    for (int q = 0; q < NQ; q++) A[q] = (q < nq) ? __ldg(row + 4 * q) : 0.0;
+#pragma unroll
+    for (int t = 0; t < 3; t++) AT[t] = (t < tail) ? __ldg(row - k + n4 + t) : 0.0;
+  };
 
   int iter = 0, nk = 0;
-  int fy_dummy = dummyB;   // dummy word relative to the buffer that currently plays ordB
   bool done = !act;
   while (!__all_sync(full, done)) {
     // ---- Nesterov extrapolation + projection (engine_solver.c:520-556), element-wise on the lane's own forces
@@ -125,7 +104,7 @@ __device__ __forceinline__ int pgs4_sweeps(const Options& opt, int nv, bool act,
             const double fs = F[q];
             double f = fs + beta * (fs - s_fprev[c]);
             s_fprev[c] = fs;
-            f = dclip(f, s_lo[c], s_hi[c]);
+            f = dclip(f, s_rc[6 * c + 3], s_rc[6 * c + 4]);
             F[q] = f; s_fmom[c] = f; s_force[c] = f;
           }
         }
@@ -136,7 +115,7 @@ __device__ __forceinline__ int pgs4_sweeps(const Options& opt, int nv, bool act,
             const double fs = T[t];
             double f = fs + beta * (fs - TP[t]);
             TP[t] = fs;
-            f = dclip(f, s_lo[c], s_hi[c]);
+            f = dclip(f, s_rc[6 * c + 3], s_rc[6 * c + 4]);
             T[t] = f; TM[t] = f;
             if (k == 0) s_force[c] = f;
           }
@@ -147,72 +126,72 @@ __device__ __forceinline__ int pgs4_sweeps(const Options& opt, int nv, bool act,
 #pragma unroll
         for (int t = 0; t < 3; t++) { TP[t] = T[t]; TM[t] = T[t]; }
       }
-      for (int c = k; c < nefc; c += 4) ordB[c] = ordA[c];   // the next sweep's shuffle starts from this sweep's order
     }
     __syncwarp();
 
-    // ---- the sweep: rows in shuffled order, the next row's operands in flight while this row updates
+    // ---- the sweep: rows in the reference's shuffled order; the operands of the next row(s) are in flight while
+    // this row updates, so that no load sits between two updates of the recurrence
     const int maxrow = __reduce_max_sync(full, done ? 0 : nefc);
-    const int last = nefc > 0 ? nefc - 1 : 0;
-    int i = ordA[0];
-    double A[NQ], AT[3];
-    {
-      const double* row = gAR + (long)i * nefc;
-#pragma unroll
-      for (int q = 0; q < NQ; q++) A[q] = (q < nq) ? __ldg(row + 4 * q) : 0.0;
-#pragma unroll
-      for (int t = 0; t < 3; t++) AT[t] = (t < tail) ? __ldg(row - k + n4 + t) : 0.0;
-    }
-    double cb = s_b[i], cainv = s_ainv[i], cad = s_ad[i], clo = s_lo[i], chi = s_hi[i], old = s_force[i];
+    const unsigned char* __restrict__ os = E.ord + (done ? 0 : iter) * nefc;
+    int i0 = __ldg(os), i1 = __ldg(os + (1 < nefc ? 1 : last)), i2 = __ldg(os + (2 < nefc ? 2 : last));
+    double Ab[3][NQ], ATb[3][3];   // operand buffers, rotated by renaming (the loop body is unrolled three times)
+    load_row(i0, Ab[0], ATb[0]);
+    if (DEPTH == 2) load_row(i1, Ab[1], ATb[1]);
+    double2 c01 = *(const double2*)(s_rc + 6 * i0), c23 = *(const double2*)(s_rc + 6 * i0 + 2);
+    double c4 = s_rc[6 * i0 + 4], old = s_force[i0];
     double impr = 0;
-    for (int bi = 0; bi < maxrow; bi++) {
+    // one row: `cur` holds this row's AR operands, `nxt` / `far` receive the operands in flight
+    auto row_step = [&](int bi, double (&cur)[NQ], double (&curT)[3], double (&nxt)[NQ], double (&nxtT)[3],
+                        double (&far)[NQ], double (&farT)[3]) {
       const bool on = !done && bi < nefc;
-      // operands of the next row
-      const int in = ordA[bi + 1 < nefc ? bi + 1 : last];
-      double An[NQ], ATn[3];
-      {
-        const double* row = gAR + (long)in * nefc;
-#pragma unroll
-        for (int q = 0; q < NQ; q++) An[q] = (q < nq) ? __ldg(row + 4 * q) : 0.0;
-#pragma unroll
-        for (int t = 0; t < 3; t++) ATn[t] = (t < tail) ? __ldg(row - k + n4 + t) : 0.0;
-      }
-      const double nb = s_b[in], nainv = s_ainv[in], nad = s_ad[in], nlo = s_lo[in], nhi = s_hi[in], nold = s_force[in];
-      // one Fisher-Yates step of the next sweep's order
-      {
-        const int idx = nefc - 1 - bi;
-        pgs4_fy_step(rng, ordB, idx, on && idx >= 1, k == 0, fy_dummy);
-      }
+      // operands in flight: the row after next (DEPTH 2) or the next row (DEPTH 1); constants of the next row
+      const int i3 = __ldg(os + (bi + 3 < nefc ? bi + 3 : last));
+      if (DEPTH == 2) load_row(i2, far, farT); else load_row(i1, nxt, nxtT);
+      const double2 n01 = *(const double2*)(s_rc + 6 * i1), n23 = *(const double2*)(s_rc + 6 * i1 + 2);
+      const double n4_ = s_rc[6 * i1 + 4], nold = s_force[i1];
       // residual: chain k of the mju_dot structure, then the butterfly (r0+r2)+(r1+r3), then the tail
       double r = 0;
 #pragma unroll
-      for (int q = 0; q < NQ; q++) r += A[q] * F[q];
+      for (int q = 0; q < NQ; q++) r += cur[q] * F[q];
       const double v = r + __shfl_xor_sync(full, r, 2);
       double res = v + __shfl_xor_sync(full, v, 1);
-      res += (AT[0] * T[0] + AT[1] * T[1]) + AT[2] * T[2];
-      res = cb + res;
+      res += (curT[0] * T[0] + curT[1] * T[1]) + curT[2] * T[2];
+      res = c01.x + res;
       // projected update with the cost-change guard (engine_solver.c:216-237,600-660)
-      double f = old - res * cainv;
-      f = f < clo ? clo : (f > chi ? chi : f);
+      double f = old - res * c01.y;
+      f = f < c23.y ? c23.y : (f > c4 ? c4 : f);
       const double delta = f - old;
-      double change = 0.5 * delta * delta * cad + delta * res;
+      double change = 0.5 * delta * delta * c23.x + delta * res;
       if (change > 1e-10) { f = old; change = 0; }
       {   // commit (selects, no branch: rows past an environment's end and finished environments change nothing)
-        const int sel = (on && i < n4 && (i & 3) == k) ? (i >> 2) : -1;
-        const int tsel = on ? i - n4 : -1;
+        // position of the updated force in this lane's registers as ONE integer (-1: not in this lane / row disabled)
+        const int mine = (int)on & (int)(i0 < n4) & (int)((i0 & 3) == k);
+        const int sel = (i0 >> 2) | (mine - 1);
+        const int tsel = (i0 - n4) | ((int)on - 1);
 #pragma unroll
         for (int q = 0; q < NQ; q++) F[q] = (q == sel) ? f : F[q];
 #pragma unroll
         for (int t = 0; t < 3; t++) T[t] = (t == tsel) ? f : T[t];
-        if (on && k == 0) s_force[i] = f;
+        if (on && k == 0) s_force[i0] = f;
         impr -= on ? change : 0.0;
       }
-      i = in;
+      i0 = i1; i1 = i2; i2 = i3;
+      c01 = n01; c23 = n23; c4 = n4_; old = nold;
+    };
+#pragma unroll 1
+    for (int bi = 0; bi < maxrow; bi += 3) {
+      row_step(bi, Ab[0], ATb[0], Ab[1], ATb[1], Ab[2], ATb[2]);
+      if (DEPTH == 2) {
+        row_step(bi + 1, Ab[1], ATb[1], Ab[2], ATb[2], Ab[0], ATb[0]);
+        row_step(bi + 2, Ab[2], ATb[2], Ab[0], ATb[0], Ab[1], ATb[1]);
+      } else {   // two buffers alternate; the third call restores the pairing for the next trip
+        row_step(bi + 1, Ab[1], ATb[1], Ab[0], ATb[0], Ab[2], ATb[2]);
+        row_step(bi + 2, Ab[0], ATb[0], Ab[1], ATb[1], Ab[2], ATb[2]);
 #pragma unroll
-      for (int q = 0; q < NQ; q++) A[q] = An[q];
+        for (int q = 0; q < NQ; q++) Ab[0][q] = Ab[1][q];
 #pragma unroll
-      for (int t = 0; t < 3; t++) AT[t] = ATn[t];
-      cb = nb; cainv = nainv; cad = nad; clo = nlo; chi = nhi; old = nold;
+        for (int t = 0; t < 3; t++) ATb[0][t] = ATb[1][t];
+      }
     }
 
     // ---- gradient restart test (engine_solver.c:690-712): serial-order sum of the per-row products
@@ -242,15 +221,37 @@ __device__ __forceinline__ int pgs4_sweeps(const Options& opt, int nv, bool act,
       iter++;
       if (impr * scale < tolerance || iter >= maxiter) done = true;
     }
-    { int* t = ordA; ordA = ordB; ordB = t; fy_dummy = (fy_dummy == dummyB) ? dummyA : dummyB; }
     __syncwarp();
   }
   return iter;
 }
 
+// Visiting orders of every sweep, for every problem size of the register classes: the reference reshuffles the
+// row order before each sweep with Fisher-Yates draws of ONE PCG32 stream seeded (0, 1) per solve
+// (engine_solver.c:240-265,498-502,560), so the order of sweep s of a problem with n rows is a constant of
+// (n, s).  Table: for n = 1..67, `iters` sweeps of n bytes; problem n starts at iters * n(n-1)/2.
+static std::vector<unsigned char> pgs4_order_table(int iters) {
+  std::vector<unsigned char> tab((size_t)iters * (67 * 68 / 2));
+  for (int n = 1; n <= 67; n++) {
+    unsigned char* dst = tab.data() + (size_t)iters * (n * (n - 1) / 2);
+    int order[68];
+    for (int c = 0; c < n; c++) order[c] = c;
+    Pcg32 rng{0, 1};
+    pcg32_next(rng);
+    for (int s = 0; s < iters; s++) {
+      for (int i = n - 1; i > 0; i--) {
+        const uint32_t j = pcg32_next(rng) % (uint32_t)(i + 1);
+        const int t = order[i]; order[i] = order[j]; order[j] = t;
+      }
+      for (int c = 0; c < n; c++) dst[(size_t)s * n + c] = (unsigned char)order[c];
+    }
+  }
+  return tab;
+}
+
 // grid: one warp per eight environments.  flags bit1/bit2: rollout skip rule (step_skip written by the
 // position launch of this step).
-__global__ void __launch_bounds__(32) k_pgs4(DModel m, Batch b, int flags) {
+__global__ void __launch_bounds__(32) k_pgs4(DModel m, Batch b, int flags, const unsigned char* __restrict__ order_tab, int order_iters) {
   extern __shared__ double pgs4_smem[];
   const unsigned full = 0xffffffffu;
   const int l = threadIdx.x, g = l >> 2, k = l & 3;
@@ -265,7 +266,7 @@ __global__ void __launch_bounds__(32) k_pgs4(DModel m, Batch b, int flags) {
   act = act && nefc > 0;
   const int top = __reduce_max_sync(full, nefc);
   if (top == 0) return;
-  if (top > 4 * 16 + 3) {   // oversized problem in this warp: generic sweeps, each environment on its four lanes
+  if (top > 4 * 16 + 3 || m.opt.iterations > order_iters) {   // oversized problem in this warp: generic sweeps, each environment on its four lanes
     if (act) solve_pgs(d);
     return;
   }
@@ -273,26 +274,28 @@ __global__ void __launch_bounds__(32) k_pgs4(DModel m, Batch b, int flags) {
   E.nefc = nefc; E.ne = act ? d.ne()[0] : 0; E.nf = act ? d.nf()[0] : 0;
   E.gAR = d.efc_AR().p;
   E.slot = (double*)((int*)pgs4_smem + (size_t)g * kPgs4SlotWords);
+  E.ord = order_tab + (size_t)order_iters * (nefc > 0 ? nefc * (nefc - 1) / 2 : 0);
   constexpr int R = kPgs4Rows;
   if (act) {   // stage the vectors; projection bounds and diagonal terms per row (engine_solver.c:91-124 ARdiaginv)
     const double* gf = d.efc_force().p; const double* gb = d.efc_b().p; const double* gfl = d.efc_frictionloss().p;
     double* S = E.slot;
     for (int c = k; c < nefc; c += 4) {
       S[c] = gf[c];
-      S[4 * R + c] = gb[c];
+      double* rc = S + 4 * R + 6 * c;
+      rc[0] = gb[c];
       const double fl = gfl[c];
       const double ai = 1 / E.gAR[(long)c * (nefc + 1)];
-      S[5 * R + c] = ai;
-      S[6 * R + c] = 1 / ai;     // the reference's Athis[0] = 1 / ARinv
-      S[7 * R + c] = (c < E.ne) ? -HUGE_VAL : (c < E.ne + E.nf) ? -fl : 0.0;   // equality rows are unbounded
-      S[8 * R + c] = (c >= E.ne && c < E.ne + E.nf) ? fl : HUGE_VAL;
+      rc[1] = ai;
+      rc[2] = 1 / ai;     // the reference's Athis[0] = 1 / ARinv
+      rc[3] = (c < E.ne) ? -HUGE_VAL : (c < E.ne + E.nf) ? -fl : 0.0;   // equality rows are unbounded
+      rc[4] = (c >= E.ne && c < E.ne + E.nf) ? fl : HUGE_VAL;
     }
   }
   __syncwarp();
   int iter;
-  if (top <= 4 * 4 + 3) iter = pgs4_sweeps<4>(m.opt, m.sz.nv, act, E, k);
-  else if (top <= 4 * 8 + 3) iter = pgs4_sweeps<8>(m.opt, m.sz.nv, act, E, k);
-  else iter = pgs4_sweeps<16>(m.opt, m.sz.nv, act, E, k);
+  if (top <= 4 * 4 + 3) iter = pgs4_sweeps<4, 2>(m.opt, m.sz.nv, act, E, k);
+  else if (top <= 4 * 8 + 3) iter = pgs4_sweeps<8, 2>(m.opt, m.sz.nv, act, E, k);
+  else iter = pgs4_sweeps<16, 1>(m.opt, m.sz.nv, act, E, k);
   __syncwarp();
   if (act) {
     double* gfo = d.efc_force().p;
@@ -304,12 +307,32 @@ __global__ void __launch_bounds__(32) k_pgs4(DModel m, Batch b, int flags) {
 }
 
 namespace backend {
-int pgs4_smem_bytes() { return kPgs4SmemBytes; }
-void launch_pgs4(const DModel& dm, const Batch& b, int flags, void* stream) {
-  static bool once = false;
-  if (!once) { cudaFuncSetAttribute(k_pgs4, cudaFuncAttributeMaxDynamicSharedMemorySize, kPgs4SmemBytes); once = true; }
+// the order table lives once per device (built on first use for the model's iteration cap; 235 KB at 100 sweeps)
+struct Pgs4Table { unsigned char* dev = nullptr; int iters = 0; };
+static Pgs4Table g_pgs4_tab[64];
+static std::mutex g_pgs4_mutex;
+int launch_pgs4(const DModel& dm, const Batch& b, int flags, void* stream) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  Pgs4Table* T;
+  {
+    std::lock_guard<std::mutex> lock(g_pgs4_mutex);
+    T = &g_pgs4_tab[dev & 63];
+    const int want = dm.opt.iterations < 4096 ? dm.opt.iterations : 0;   // beyond: the kernel takes the generic sweeps
+    if (want > T->iters) {
+      const int iters = want < 100 ? 100 : want;
+      std::vector<unsigned char> tab = pgs4_order_table(iters);
+      unsigned char* p = nullptr;
+      if (cudaMalloc(&p, tab.size()) != cudaSuccess) return -3;
+      if (cudaMemcpy(p, tab.data(), tab.size(), cudaMemcpyHostToDevice) != cudaSuccess) { cudaFree(p); return -3; }
+      // an older, shorter table may still be read by launches in flight: it is small, leave it allocated
+      T->dev = p; T->iters = iters;
+      cudaFuncSetAttribute(k_pgs4, cudaFuncAttributeMaxDynamicSharedMemorySize, kPgs4SmemBytes);
+    }
+  }
   const int grid = (b.nenv + 7) / 8;
-  k_pgs4<<<grid, 32, kPgs4SmemBytes, (cudaStream_t)stream>>>(dm, b, flags);
+  k_pgs4<<<grid, 32, kPgs4SmemBytes, (cudaStream_t)stream>>>(dm, b, flags, T->dev, T->iters);
+  return 0;
 }
 }  // namespace backend
 
