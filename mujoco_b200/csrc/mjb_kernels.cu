@@ -177,9 +177,14 @@ bool split_step_available(const DModel& dm, const Batch& b) {
 }
 int launch_split_step(const DModel& dm, const Batch& b, int first, int later, void* s) {
   const bool lean = dm.sz.nsensor == 0 && dm.sz.neq == 0 && dm.sz.ntree == 1 && dm.opt.integrator != INT_IMPLICITFAST && !dm.sz.actfeat && !b.xfrc;
-  if (lean) launch_kpart1_lean(dm, b, 0, first, s); else launch_kpart1(dm, b, 0, first, s);
+  static const int part_lanes = [] { const char* e = getenv("MJB_PART_LANES"); return e ? atoi(e) : 16; }();   // measured (humanoid x4096): 16 lanes 1.357 ms/step, 32 lanes 1.385, 8 lanes 1.533
+  if (lean && part_lanes == 16) launch_kpart1_lean16(dm, b, 0, first, s);
+  else if (lean && part_lanes == 8) launch_kpart1_lean8(dm, b, 0, first, s);
+  else if (lean) launch_kpart1_lean(dm, b, 0, first, s); else launch_kpart1(dm, b, 0, first, s);
   if (launch_pgs4(dm, b, later, s)) return cuda_fail(cudaGetLastError(), "PGS order table");
-  if (lean) launch_kpart2_lean(dm, b, 0, later, s); else launch_kpart2(dm, b, 0, later, s);
+  if (lean && part_lanes == 16) launch_kpart2_lean16(dm, b, 0, later, s);
+  else if (lean && part_lanes == 8) launch_kpart2_lean8(dm, b, 0, later, s);
+  else if (lean) launch_kpart2_lean(dm, b, 0, later, s); else launch_kpart2(dm, b, 0, later, s);
   g_launches += 3;
   CK(cudaPeekAtLastError(), "split step launch");
   if (!(dm.opt.disableflags & DSBL_AUTORESET)) {

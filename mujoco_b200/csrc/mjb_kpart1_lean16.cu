@@ -1,0 +1,6 @@
+// one half of the split step, 16 lanes per environment (see mjb_kstep.h, mjb_stage.h run_part)
+#define MJB_KSTEP_INSTANCE
+#include "mjb_kstep.h"
+namespace mjb {
+MJB_KSTEP_LAUNCHER_PART(launch_kpart1_lean16, SOL_PGS, 16, 0, 1)
+}  // namespace mjb

@@ -24,6 +24,11 @@ void launch_kpart1_lean(const DModel& dm, const Batch& b, int mask, int flags, v
 void launch_kpart1(const DModel& dm, const Batch& b, int mask, int flags, void* stream);
 void launch_kpart2_lean(const DModel& dm, const Batch& b, int mask, int flags, void* stream);
 void launch_kpart2(const DModel& dm, const Batch& b, int mask, int flags, void* stream);
+// the same halves with 16 / 8 lanes per environment (2 / 4 environments per warp)
+void launch_kpart1_lean16(const DModel& dm, const Batch& b, int mask, int flags, void* stream);
+void launch_kpart2_lean16(const DModel& dm, const Batch& b, int mask, int flags, void* stream);
+void launch_kpart1_lean8(const DModel& dm, const Batch& b, int mask, int flags, void* stream);
+void launch_kpart2_lean8(const DModel& dm, const Batch& b, int mask, int flags, void* stream);
 int launch_pgs4(const DModel& dm, const Batch& b, int flags, void* stream);
 }  // namespace backend
 
@@ -47,8 +52,10 @@ constexpr int kSmemPerWarp = MJB_SMEM_PER_WARP;    // doubles = 6.5 KB: eight sw
 // of a warp idle in every cooperative loop); the two halves synchronise with their own lane masks.
 // PART = 0: stages by mask (fused step).  PART = 1 / 2: the two halves of a split step, compiled without the
 // solver (no shared-memory scratch, their own register budget and a fraction of the fused kernel's code).
+// Sub-warp halves (PART != 0, NLANE < 32) run few warps per SM (4096 environments = 1024 warps at 8 lanes): they
+// trade the register cap that buys occupancy for a spill-free, latency-oriented allocation.
 template <int SOLVER, int NLANE, int FEAT, int PART>
-__global__ void __launch_bounds__(32 * kWarpsPerCta, MJB_CTAS_PER_SM) k_step_warp(DModel m, Batch b, int mask, int flags) {
+__global__ void __launch_bounds__(32 * kWarpsPerCta, (PART != 0 && NLANE < 32) ? (NLANE == 16 ? 4 : 2) : MJB_CTAS_PER_SM) k_step_warp(DModel m, Batch b, int mask, int flags) {
   constexpr int kPerWarp = 32 / NLANE;
   __shared__ double smem[(NLANE == 32 && PART == 0) ? kWarpsPerCta * kSmemPerWarp : 1];
   const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
@@ -59,7 +66,7 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta, MJB_CTAS_PER_SM) k_step_war
     else run_env(m, b, e, 0, flags & ~16, l, 32, nullptr, 0, SOLVER, 0xffffffffu, FEAT, PART);
   } else {
     const unsigned lanes = ((1u << NLANE) - 1u) << ((l / NLANE) * NLANE);
-    run_env(m, b, e, mask, flags, l % NLANE, NLANE, nullptr, 0, SOLVER, lanes, FEAT, PART);
+    run_env(m, b, e, mask, PART ? (flags & ~16) : flags, l % NLANE, NLANE, nullptr, 0, SOLVER, lanes, FEAT, PART);
   }
 }
 
