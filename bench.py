@@ -244,54 +244,68 @@ def main():
     niter = batch.field("solver_niter")[:, 0].astype(np.float64)
     warn = int(batch.warnings().sum())
 
-    # ---- per-stage timing pass (CUDA events on the launching stream), 20 steps
-    stage_ms = np.zeros(4)
+    # ---- per-launch timing pass: CUDA events on the launching stream around each launch of the step (mjb_step_profile)
     nprobe = 20
+    names = ["position+velocity", "solve", "finish+integrate", "redo"]
+    launch_ms = np.zeros(4)
+    split = True
     torch.cuda.synchronize()
-    for t_ in range(nprobe):
-        evs = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
-        for s in range(4):
-            evs[s].record(stream)
-            batch.run_stages(s, s)
-        evs[4].record(stream)
-        stream.synchronize()
-        for s in range(4):
-            stage_ms[s] += evs[s].elapsed_time(evs[s + 1])
-    stage_ms /= nprobe
+    try:
+        for t_ in range(nprobe):
+            launch_ms += batch.step_profile()
+        launch_ms /= nprobe
+    except RuntimeError:       # this configuration steps with one fused launch
+        split = False
     # ---- roofline of the dominant kernel
     peak, peak_src = peaks()
     m_nefc, m_nefc2, m_ncon = float(nefc.mean()), float((nefc ** 2).mean()), float(ncon.mean())
     m_iter = float(niter.mean())
     # ALGORITHMIC bytes per env-step, SURVEY.md section 8(d) convention "B_mjdata" (DESIGN.md section 5):
     #   B_state + 8 * (hot-path mjData fields written once) + ncon*584 + nefc*(8*(nv+14)+12)
-    #   + PGS: 8*nefc*nv (efc_Y... the A = J M^-1 J^T factor) + 8*nefc^2 (efc_AR)
-    # with the batch's own mean ncon / nefc / nefc^2 at the end of the timed window.  Split per stage for
-    # the stage table only (position: kinematic fields + contacts + rows + Y + AR; velocity; solve: AR re-read;
-    # integrate: state out).
+    #   + PGS: 8*nefc*nv (efc_Y) + 8*nefc^2 (efc_AR)
+    # with the batch's own mean ncon / nefc / nefc^2 at the end of the timed window; the per-field counts come from
+    # the batch layout (mjb_field_size), so the formula follows the model.
+    fs = batch.field_size
+    pos_fields = ["xpos", "xquat", "xmat", "xipos", "ximat", "xanchor", "xaxis", "geom_xpos", "geom_xmat", "subtree_com",
+                  "cdof", "cinert", "ten_J", "ten_length", "actuator_length", "actuator_moment", "crb", "M", "qLD", "qLDiagInv"]
+    vel_fields = ["ten_velocity", "actuator_velocity", "cvel", "cdof_dot", "qfrc_bias", "qfrc_spring", "qfrc_damper",
+                  "qfrc_passive", "qH", "qHDiagInv"]
+    acc_fields = ["actuator_force", "qfrc_actuator", "qfrc_smooth", "qfrc_constraint", "qacc_smooth", "qacc"]
+    n_pos, n_vel, n_acc = (sum(fs(f) for f in grp) for grp in (pos_fields, vel_fields, acc_fields))
     b_state = 8 * ((1 + nq + nv + nu + nv) + (1 + nq + nv + nv))
-    b_pos = 8 * 2010 + m_ncon * 584 + m_nefc * (8 * (nv + 14) + 12) + 8 * m_nefc * nv + 8 * m_nefc2
-    b_vel = 8 * 746
-    b_sol = 8 * 156
-    b_int = b_state
-    bytes_per_env = [b_pos, b_vel, b_sol, b_int]
-    b_mjdata = sum(bytes_per_env)
-    # dominant kernel = the fused per-step launch k_step_warp (stages 0-3 of every env, one launch per
-    # step); its average duration over the timed region = ms / K (launches are back to back on the
-    # stream; the tiny k_set_control launch in between is included, which only lowers `achieved`)
-    launch_ms = ms / K
-    achieved = NENV * b_mjdata / (launch_ms * 1e-3) / 1e9
-    traffic, traffic_src = None, None
-    tp = os.path.join(ROOT, "profiles", "r01_traffic.json")
-    if os.path.exists(tp):
-        tj = json.load(open(tp))
-        traffic, traffic_src = tj.get("dram_bytes_per_launch"), tj.get("source")
-    roof = {"bound": "hbm", "kernel": "k_step_warp<PGS,32> (fused mj_step, 1 launch/step)", "achieved": achieved, "peak": peak,
-            "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-            "traffic_source": traffic_src, "algorithmic_bytes_per_launch": NENV * b_mjdata,
-            "algorithmic_bytes_per_env_step": b_mjdata, "launch_ms": launch_ms,
-            "note": "not bandwidth-bound: instruction issue / fetch of the branchy PGS sweeps of a heavy-tailed batch (DESIGN.md section 5)",
-            "stage_ms": dict(zip(["position", "velocity", "solve", "integrate"], [float(x) for x in stage_ms])),
-            "stage_bytes_per_env": dict(zip(["position", "velocity", "solve", "integrate"], [float(x) for x in bytes_per_env]))}
+    pgs = CFG["solver"] == 0
+    b_pos = 8 * n_pos + m_ncon * 584 + m_nefc * (8 * (nv + 14) + 12) + (8 * m_nefc * nv + 8 * m_nefc2 if pgs else 0)
+    b_mjdata = b_state + b_pos + 8 * n_vel + 8 * n_acc
+    step_gbs = NENV * b_mjdata / (ms / K * 1e-3) / 1e9
+    prof = {}
+    pp = os.path.join(ROOT, "profiles", "r02_kernels.json")
+    if os.path.exists(pp):
+        prof = json.load(open(pp))
+    if split:
+        dom = int(np.argmax(launch_ms[:3]))
+        # algorithmic bytes of each launch: the fields it reads once and writes once
+        b_k = [b_state / 2 + b_pos + 8 * n_vel + 8 * (n_acc - 2 * nv) + 8 * 2 * m_nefc,           # first half (+ efc_b, warm-start force)
+               8 * m_nefc2 + 8 * 3 * m_nefc + 12 * m_nefc,                                        # solve: AR, b / force / frictionloss in, force + state out
+               b_state / 2 + 8 * 2 * nv + 8 * m_nefc * nv + 8 * m_nefc]                           # second half: J' f, qacc, state out
+        kname = ["k_step_warp<PGS,16,lean,part 1> (position + velocity)", "k_pgs4 (PGS, 4 lanes per environment)",
+                 "k_step_warp<PGS,16,lean,part 2> (finish + integrate)"][dom]
+        kkey = ["part1", "pgs4", "part2"][dom]
+        achieved = NENV * b_k[dom] / (launch_ms[dom] * 1e-3) / 1e9
+        traffic = prof.get(kkey, {}).get("dram_bytes_per_launch")
+        roof = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": traffic, "traffic_source": prof.get("source"),
+                "algorithmic_bytes_per_launch": NENV * b_k[dom], "launch_ms": float(launch_ms[dom]),
+                "fp64_pipe_frac": prof.get(kkey, {}).get("fp64_pipe_frac"), "issue_active": prof.get(kkey, {}).get("issue_active"),
+                "note": "not bandwidth-bound: the solve is ONE dependent chain per environment (Gauss-Seidel recurrence) and the launch "
+                        "lasts as long as the batch's longest chain; see DESIGN.md section 5",
+                "launches_ms": dict(zip(names, [float(x) for x in launch_ms])),
+                "launches_bytes_per_env": dict(zip(names[:3], [float(x) for x in b_k])),
+                "step": {"algorithmic_bytes_per_env_step": b_mjdata, "achieved": step_gbs, "frac": step_gbs / peak}}
+    else:
+        roof = {"bound": "hbm", "kernel": "k_step_warp (fused mj_step, 1 launch/step)", "achieved": step_gbs, "peak": peak,
+                "peak_source": peak_src, "unit": "GB/s", "frac": step_gbs / peak, "traffic": None,
+                "algorithmic_bytes_per_launch": NENV * b_mjdata, "launch_ms": ms / K,
+                "note": "not bandwidth-bound: dependent chains of the constraint solver and the tree passes (DESIGN.md section 5)"}
 
     # ---- e2e: per step H2D ctrl from pinned host, step, D2H state
     ke = min(K, 100)
@@ -310,7 +324,22 @@ def main():
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e2e_s = float(tt.item())
     e2e = {"value": NENV * world * ke / e2e_s, "unit": "env-steps/s", "h2d_bytes_per_step": NENV * nu * 8,
-           "d2h_bytes_per_step": NENV * nstate * 8, "steps": ke}
+           "d2h_bytes_per_step": NENV * nstate * 8, "steps": ke,
+           "call": "mjb_step_host per step: ctrl [nenv,nu] host -> device, one mj_step, FULLPHYSICS state device -> host, synchronised"}
+    # the reference's own batched call shape (rollout.cc): nstep steps per call, controls for all steps in, states
+    # of all steps out, host buffers
+    kr = min(K, 20)
+    h_c = np.random.default_rng(3).uniform(-1, 1, (NENV, kr, nu))
+    s_now = batch.get_state()
+    batch.rollout(s_now, h_c)
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    batch.rollout(s_now, h_c)
+    r_s = time.perf_counter() - t0
+    e2e["rollout_call"] = {"value": NENV * world * kr / r_s, "unit": "env-steps/s", "steps_per_call": kr,
+                           "h2d_bytes_per_step": NENV * nu * 8, "d2h_bytes_per_step": NENV * nstate * 8,
+                           "call": "mjb_rollout (the rollout.cc contract): pageable host arrays in / out, initial state set per call"}
 
     # ---- CPU baseline (rank 0, N=1 only): reference engine on a bounded sample, all host cores
     cpu = None

@@ -132,6 +132,30 @@ MJB_API int mjb_get_field(mjbBatch* b, const char* name, double* out);
 MJB_API int mjb_get_field_int(mjbBatch* b, const char* name, int* out);
 MJB_API int mjb_set_field(mjbBatch* b, const char* name, const double* in);
 
+/* mj_forward on the reference's own mjData objects (as mjb_step_mjdata, without integration) */
+MJB_API int mjb_forward_mjdata(mjbBatch* b, struct mjData_* const* d, int nd);
+
+/* _unsafe_rollout's own argument list (python/mujoco/rollout.cc:67-78): one mjModel pointer per environment.  All
+ * pointers must name the same model (this path shares one flattened model per batch; MJB_ERR_UNSUPPORTED
+ * otherwise).  The batch lives for the call.  Arrays as in mjb_rollout. */
+MJB_API int mjb_rollout_models(const struct mjModel_* const* m, int nbatch, int nstep, unsigned int control_spec,
+                               const double* state0, const double* warmstart0, const double* control, double* state,
+                               double* sensordata, int device);
+
+/* The reference's single-environment entry points, include/mujoco/mujoco.h:189-204, with the reference's
+ * signatures and semantics: a host linked (or dlopen-ed) against libmjb200.so instead of libmujoco for these five
+ * symbols steps its mjData on the GPU, one environment per call (a batch of 1 on the mjData bridge; one cached
+ * batch per mjModel pointer - mjb_forget_model() after editing or before freeing a model).  mjData.ncon / nefc
+ * read 0 afterwards (arena members are not materialised).  Fatal conditions are reported
+ * through the process's mju_error when the reference library is loaded, else stderr + abort (mju_error's default);
+ * first occurrences of a warning through mju_warning. */
+MJB_API void mj_step(const struct mjModel_* m, struct mjData_* d);
+MJB_API void mj_forward(const struct mjModel_* m, struct mjData_* d);
+MJB_API void mj_forwardSkip(const struct mjModel_* m, struct mjData_* d, int skipstage, int skipsensor);
+MJB_API void mj_step1(const struct mjModel_* m, struct mjData_* d);
+MJB_API void mj_step2(const struct mjModel_* m, struct mjData_* d);
+MJB_API void mjb_forget_model(const struct mjModel_* m);
+
 /* statistics of the last mjb_step/mjb_rollout call */
 MJB_API long mjb_kernel_launches(const mjbBatch* b);   /* cumulative number of kernels launched */
 MJB_API int mjb_warning_counts(mjbBatch* b, int* out /* [nenv][8] */);
@@ -139,6 +163,14 @@ MJB_API int mjb_warning_counts(mjbBatch* b, int* out /* [nenv][8] */);
 /* staged execution for tests/profiling: run only pipeline stages [first,last] of one step
  * (0 position, 1 velocity+actuation+acceleration, 2 constraint solve, 3 integrate) */
 MJB_API int mjb_run_stages(mjbBatch* b, int first, int last);
+
+/* one mj_step of every environment (as mjb_step(b, 1)) that also reports the duration in ms of the launches the
+ * step is made of, timed with CUDA events on the batch's stream: ms4 = {position + velocity half, constraint
+ * solve, finish + integrate half, redo launch}.  MJB_ERR_UNSUPPORTED when the batch steps with one fused launch. */
+MJB_API int mjb_step_profile(mjbBatch* b, float* ms4);
+
+/* test switches (process-wide).  "pgs4_slots" = 1: the PGS kernel takes its fallback shared-memory layout. */
+MJB_API int mjb_set_debug(const char* key, int value);
 
 /* CUDA stream used by the batch (cudaStream_t as void*), e.g. for event timing by the caller */
 MJB_API void* mjb_stream(mjbBatch* b);

@@ -74,6 +74,8 @@ def _bind(cdll):
     L.mjb_kernel_launches.argtypes = [vp]
     L.mjb_warning_counts.argtypes = [vp, vp]
     L.mjb_run_stages.argtypes = [vp, i, i]
+    L.mjb_step_profile.argtypes = [vp, vp]
+    L.mjb_set_debug.argtypes = [cp, i]
     L.mjb_stream.restype = vp
     L.mjb_stream.argtypes = [vp]
     return L
@@ -236,6 +238,22 @@ class Batch:
 
     def run_stages(self, first, last):
         self._chk(self.L.mjb_run_stages(self.ptr, first, last))
+
+    def set_debug(self, key, value):
+        self._chk(self.L.mjb_set_debug(key.encode(), int(value)))
+
+    def step_profile(self):
+        """one step; returns ms of its launches [first half, solve, second half, redo] (CUDA events)"""
+        ms = np.zeros(4, dtype=np.float32)
+        self._chk(self.L.mjb_step_profile(self.ptr, ms.ctypes.data))
+        return ms
+
+    def field_size(self, name):
+        """elements per environment of a batch field (0 when the model has none; KeyError for unknown names)"""
+        n = self.L.mjb_field_size(self.ptr, name.encode())
+        if n < 0:
+            raise KeyError(name)
+        return int(n)
 
     def field(self, name):
         n = self.L.mjb_field_size(self.ptr, name.encode())

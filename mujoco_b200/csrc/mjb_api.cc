@@ -6,7 +6,10 @@
 
 #include <cstdio>
 #include <cstdlib>
+#include <dlfcn.h>
 #include <cstring>
+#include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -44,6 +47,28 @@ struct mjbBatch_ {
 };
 
 static int fail(int code, const std::string& msg) { set_error(msg); return code; }
+
+// mju_error / mju_warning of the reference library when it is loaded in this process (looked up once, never
+// linked): the Python bindings install their handlers there (python/mujoco/errors.h:140-226)
+static void route_error(const std::string& msg) {
+  typedef void (*fn_t)(const char*, ...);
+  static fn_t fn = (fn_t)dlsym(RTLD_DEFAULT, "mju_error");
+  set_error(msg);
+  if (fn) { fn("%s", msg.c_str()); return; }   // normally does not return
+  fprintf(stderr, "ERROR: %s\n", msg.c_str());
+  abort();
+}
+static void route_warning(int type, double time) {
+  typedef void (*fn_t)(const char*, ...);
+  static fn_t fn = (fn_t)dlsym(RTLD_DEFAULT, "mju_warning");
+  static const char* text[NWARNING] = {
+      "Inertia matrix is too close to singular. Check model.", "Pre-allocated contact buffer is full (nconmax of the batch).",
+      "Pre-allocated constraint buffer is full (njmax of the batch).", "Nan, Inf or huge value in QPOS. The simulation is unstable.",
+      "Nan, Inf or huge value in QVEL. The simulation is unstable.", "Nan, Inf or huge value in QACC. The simulation is unstable.",
+      "Nan, Inf or huge value in CTRL.", "Pre-allocated visual geom buffer is full."};
+  if (fn) fn("%s Time = %.4f.", text[type], time);
+  else fprintf(stderr, "WARNING: %s Time = %.4f.\n", text[type], time);
+}
 
 // thread mapping for new batches: 1 = one warp per environment (default), 0 = one lane per environment
 static int g_warp_per_env = 1;
@@ -93,7 +118,7 @@ mjbBatch* mjb_make_batch(const struct mjModel_* m, int nenv, int nconmax, int nj
   if (!m || nenv <= 0) { set_error("mjb_make_batch: bad arguments"); return nullptr; }
   if (int rc = backend::init(device)) { (void)rc; return nullptr; }
   mjbBatch* B = new mjbBatch_();
-  if (build_host_model((const mjModel*)m, nconmax, njmax, &B->hm)) { delete B; return nullptr; }
+  if (build_host_model((const mjModel*)m, nconmax, njmax, &B->hm)) { delete B; return nullptr; }   // nothing on the device yet
   const DModel& H = B->hm.dm;
   if (H.opt.solver == SOL_NEWTON) {
 #ifndef MJB_HAVE_NEWTON
@@ -109,7 +134,7 @@ mjbBatch* mjb_make_batch(const struct mjModel_* m, int nenv, int nconmax, int nj
   // device copy of the model blobs, pointers rebased
   B->d_ib = (int*)backend::dev_alloc(B->hm.ib.size() * sizeof(int));
   B->d_db = (double*)backend::dev_alloc(B->hm.db.size() * sizeof(double));
-  if (!B->d_ib || !B->d_db) { set_error("device allocation failed (model)"); delete B; return nullptr; }
+  if (!B->d_ib || !B->d_db) { set_error("device allocation failed (model)"); mjb_free_batch(B); return nullptr; }
   backend::h2d(B->d_ib, B->hm.ib.data(), B->hm.ib.size() * sizeof(int), B->stream);
   backend::h2d(B->d_db, B->hm.db.data(), B->hm.db.size() * sizeof(double), B->stream);
   B->dm = H;
@@ -238,7 +263,7 @@ int mjb_get_state(mjbBatch* B, double* state, unsigned int sig) {
 // one mj_step of every environment.  skip_warned: rollout rule (environments carrying a warning do
 // not step).  Euler: all four stages in ONE fused launch.  RK4 (mj_RungeKutta): forward + acceleration
 // check, then three (phase, forward) pairs and the final combination = 8 launches.
-static int run_step_on(mjbBatch* B, const Batch& b, void* stream, bool skip_warned) {
+static int run_step_on(mjbBatch* B, const Batch& b, void* stream, bool skip_warned, void* stagger = nullptr) {
   const int first = 1 | (skip_warned ? 2 : 0), later = skip_warned ? 4 : 0;
   const int sub = later | 8;   // RK4 sub-steps: mj_forwardSkip(.., skipsensor = 1)
   if (B->hm.dm.opt.integrator == INT_RK4) {
@@ -250,7 +275,7 @@ static int run_step_on(mjbBatch* B, const Batch& b, void* stream, bool skip_warn
     if (!rc) rc = backend::launch_rk4(B->dm, b, 4, later, stream);
     return rc;
   }
-  if (backend::split_step_available(B->dm, b)) return backend::launch_split_step(B->dm, b, first, later, stream);
+  if (backend::split_step_available(B->dm, b)) return backend::launch_split_step(B->dm, b, first, later, stream, stagger);
   return backend::launch_stages(B->dm, b, 0xF, first, stream);
 }
 static int run_step(mjbBatch* B, bool skip_warned) { return run_step_on(B, B->b, B->stream, skip_warned); }
@@ -303,8 +328,8 @@ int mjb_step(mjbBatch* B, int nstep) {
   std::vector<EnvGroup> gs = env_groups(B, nstep);
   if (int rc = groups_fork(B, gs)) return rc;
   for (int t = 0; t < nstep; t++)
-    for (auto& g : gs)
-      if (int rc = run_step_on(B, g.b, g.stream, false)) return rc;
+    for (size_t g = 0; g < gs.size(); g++)
+      if (int rc = run_step_on(B, gs[g].b, gs[g].stream, false, (t == 0 && g + 1 < gs.size()) ? gs[g + 1].stream : nullptr)) return rc;
   if (int rc = groups_join(B, gs)) return rc;
   return backend::sync(B->stream);
 }
@@ -317,6 +342,17 @@ int mjb_run_stages(mjbBatch* B, int first, int last) {
   return backend::sync(B->stream);
 }
 
+int mjb_set_debug(const char* key, int value) {
+  if (!key || backend::set_debug(key, value)) return fail(MJB_ERR_ARG, "mjb_set_debug: unknown key");
+  return 0;
+}
+
+int mjb_step_profile(mjbBatch* B, float* ms4) {
+  if (!B || !ms4) return fail(MJB_ERR_ARG, "mjb_step_profile: bad arguments");
+  if (!backend::split_step_available(B->dm, B->b)) return fail(MJB_ERR_UNSUPPORTED, "mjb_step_profile: this batch steps with the fused kernel (one launch)");
+  return backend::profile_split_step(B->dm, B->b, B->stream, ms4);
+}
+
 int mjb_rollout(mjbBatch* B, int nstep, unsigned int control_spec, const double* state0,
                 const double* warmstart0, const double* control, double* state, double* sensordata) {
   if (!B || nstep < 0 || !state0) return fail(MJB_ERR_ARG, "mjb_rollout: bad arguments");
@@ -324,7 +360,9 @@ int mjb_rollout(mjbBatch* B, int nstep, unsigned int control_spec, const double*
   if (sensordata && !nsens) return fail(MJB_ERR_ARG, "mjb_rollout: the model has no sensors (nsensordata == 0)");
   const unsigned full = ST_TIME | ST_QPOS | ST_QVEL | ST_ACT | ST_HISTORY | ST_PLUGIN;
   std::vector<Seg> csegs;
-  if (control && state_segments(B, control_spec, &csegs)) return fail(MJB_ERR_ARG, "mjb_rollout: unsupported control_spec");
+  const unsigned user_inputs = ST_CTRL | ST_QFRC_APPLIED | ST_XFRC_APPLIED | ST_EQ_ACTIVE | ST_MOCAP_POS | ST_MOCAP_QUAT;
+  if (control && ((control_spec & ~user_inputs) || state_segments(B, control_spec, &csegs)))
+    return fail(MJB_ERR_ARG, "mjb_rollout: control_spec may hold CTRL, QFRC_APPLIED, XFRC_APPLIED, EQ_ACTIVE, MOCAP_POS, MOCAP_QUAT only");
   const int nenv = B->b.nenv, nv = B->hm.dm.sz.nv;
   const int nstate = mjb_state_size(B, full);
   int ncontrol = 0;
@@ -385,9 +423,10 @@ int mjb_rollout(mjbBatch* B, int nstep, unsigned int control_spec, const double*
   std::vector<EnvGroup> gs = env_groups(B, nstep);
   int rc = groups_fork(B, gs);
   for (int t = 0; t < nstep && !rc; t++) {
-    for (auto& g : gs) {
+    for (size_t gi = 0; gi < gs.size(); gi++) {
+      auto& g = gs[gi];
       if (d_control && !rc) rc = backend::launch_set_control(B->dm, g.b, d_control + (size_t)g.e0 * nstep * ncontrol, nstep, t, control_spec, ncontrol, g.stream);
-      if (!rc) rc = run_step_on(B, g.b, g.stream, true);
+      if (!rc) rc = run_step_on(B, g.b, g.stream, true, (t == 0 && gi + 1 < gs.size()) ? gs[gi + 1].stream : nullptr);
       if (d_state && !rc) rc = backend::launch_get_state(B->dm, g.b, d_state + (size_t)g.e0 * nstep * nstate, nstep, t, nstate, g.stream);
       if (d_sens && !rc) rc = backend::launch_get_sensor(B->dm, g.b, d_sens + (size_t)g.e0 * nstep * nsens, nstep, t, nsens, g.stream);
     }
@@ -412,7 +451,7 @@ int mjb_step_host(mjbBatch* B, const double* ctrl, double* state_out) {
     if (!B->io_ctrl || !B->io_state) return fail(MJB_ERR_CUDA, "device allocation failed (io staging)");
   }
   int rc = backend::h2d(B->io_ctrl, ctrl, (size_t)nenv * nu * sizeof(double), B->stream);
-  if (!rc) rc = backend::launch_set_control(B->dm, B->b, B->io_ctrl, 1, 0, ST_CTRL, nu, B->stream);
+  if (!rc) rc = backend::launch_set_control(B->dm, B->b, B->io_ctrl, 1, 0, ST_CTRL, nu, B->stream, /*skip_warned=*/false);
   if (!rc) rc = run_step(B, false);
   if (!rc) rc = backend::launch_get_state(B->dm, B->b, B->io_state, 1, 0, nstate, B->stream);
   if (!rc) rc = backend::d2h(state_out, B->io_state, (size_t)nenv * nstate * sizeof(double), B->stream);
@@ -428,9 +467,10 @@ int mjb_rollout_device(mjbBatch* B, int nstep, const double* d_ctrl, double* d_s
   std::vector<EnvGroup> gs = env_groups(B, nstep);
   int rc = groups_fork(B, gs);
   for (int t = 0; t < nstep && !rc; t++) {
-    for (auto& g : gs) {   // native layouts are [..][elem][env]: a group starts e0 elements further
+    for (size_t gi = 0; gi < gs.size(); gi++) {   // native layouts are [..][elem][env]: a group starts e0 elements further
+      auto& g = gs[gi];
       if (d_ctrl && !rc) rc = backend::launch_set_control_native(B->dm, g.b, d_ctrl + g.e0, t, g.stream);
-      if (!rc) rc = run_step_on(B, g.b, g.stream, false);
+      if (!rc) rc = run_step_on(B, g.b, g.stream, false, (t == 0 && gi + 1 < gs.size()) ? gs[gi + 1].stream : nullptr);
       if (d_state && !rc) rc = backend::launch_get_state_native(B->dm, g.b, d_state + g.e0, t, nstate, g.stream);
     }
   }
@@ -484,25 +524,33 @@ int mjb_set_field(mjbBatch* B, const char* name, const double* in) {
 // (time, qpos, qvel, ctrl, qfrc_applied, qacc_warmstart), the batch takes one mj_step, and the state plus
 // every fixed-size mjData array the path computes is written back under the same member name, so code
 // that reads mjData after mj_step keeps working.  Arena-allocated members (contact, efc_*) are not
-// materialised on the host; ncon / nefc and the warning counters are.
+// materialised on the host and ncon / nefc are published as ZERO (see bridge_mjdata); warning counters are added.
 #define MJB_MJDATA_IN(X) X(qpos, nq) X(qvel, nv) X(act, na) X(mocap_pos, 3 * nmocap) X(mocap_quat, 4 * nmocap) X(xfrc_applied, 6 * nbody) X(ctrl, nu) X(qfrc_applied, nv) X(qacc_warmstart, nv)
+// every fixed-size mjData array the path computes (position, velocity, acceleration stage; sensors and the
+// rnePostConstraint / subtreeVel outputs where the model's sensors make the batch compute them)
 #define MJB_MJDATA_OUT(X)                                                                                   \
   X(qpos, nq) X(qvel, nv) X(act, na) X(act_dot, na) X(qacc_warmstart, nv) X(qacc, nv)                       \
   X(xpos, 3 * nbody) X(xquat, 4 * nbody) X(xmat, 9 * nbody) X(xipos, 3 * nbody) X(ximat, 9 * nbody)         \
   X(xanchor, 3 * njnt) X(xaxis, 3 * njnt) X(geom_xpos, 3 * ngeom) X(geom_xmat, 9 * ngeom)                   \
+  X(site_xpos, 3 * nsite) X(site_xmat, 9 * nsite)                                                           \
   X(subtree_com, 3 * nbody) X(cinert, 10 * nbody) X(cdof, 6 * nv) X(crb, 10 * nbody) X(M, nC) X(qLD, nC)    \
   X(qLDiagInv, nv) X(ten_length, ntendon) X(actuator_length, nu) X(ten_velocity, ntendon)                   \
   X(actuator_velocity, nu) X(cvel, 6 * nbody) X(cdof_dot, 6 * nv) X(qfrc_spring, nv) X(qfrc_damper, nv)     \
   X(qfrc_passive, nv) X(qfrc_bias, nv) X(actuator_force, nu) X(qfrc_actuator, nv) X(qfrc_smooth, nv)        \
-  X(qacc_smooth, nv) X(qfrc_constraint, nv)
+  X(qacc_smooth, nv) X(qfrc_constraint, nv) X(sensordata, nsensordata)                                     \
+  X(subtree_linvel, 3 * nbody * subtreevel) X(subtree_angmom, 3 * nbody * subtreevel)                       \
+  X(cacc, 6 * nbody * rnepost) X(cfrc_int, 6 * nbody * rnepost) X(cfrc_ext, 6 * nbody * rnepost)
 
-int mjb_step_mjdata(mjbBatch* B, struct mjData_* const* dd, int nd) {
-  if (!B || !dd || nd != B->b.nenv) return fail(MJB_ERR_ARG, "mjb_step_mjdata: need one mjData per environment");
+// what the bridge runs between copying the inputs in and the results out
+enum BridgeOp { BR_STEP, BR_FORWARD, BR_FORWARD_NOSENSOR, BR_STEP1, BR_STEP2 };
+
+static int bridge_mjdata(mjbBatch* B, mjData* const* d, int nd, BridgeOp op) {
+  if (!B || !d || nd != B->b.nenv) return fail(MJB_ERR_ARG, "mjData bridge: need one mjData per environment");
   const Sizes& S = B->hm.dm.sz;
   const int nenv = B->b.nenv;
-  mjData* const* d = (mjData* const*)dd;
-  const int nq = S.nq, nv = S.nv, nu = S.nu, na = S.na, nmocap = S.nmocap, nbody = S.nbody, njnt = S.njnt, ngeom = S.ngeom, ntendon = S.ntendon, nC = S.nC;
-  (void)na; (void)nmocap; (void)nbody; (void)njnt; (void)ngeom; (void)ntendon; (void)nC;
+  const int nq = S.nq, nv = S.nv, nu = S.nu, na = S.na, nmocap = S.nmocap, nbody = S.nbody, njnt = S.njnt, ngeom = S.ngeom,
+            ntendon = S.ntendon, nC = S.nC, nsite = S.nsite, nsensordata = S.nsensordata, subtreevel = S.subtreevel, rnepost = S.rnepost;
+  (void)na; (void)nmocap; (void)nbody; (void)njnt; (void)ngeom; (void)ntendon; (void)nC; (void)nsite; (void)nsensordata; (void)subtreevel; (void)rnepost;
   std::vector<double> tmp;
   for (int e = 0; e < nenv && !B->b.xfrc; e++)
     for (int k = 0; k < 6 * nbody; k++) if (d[e]->xfrc_applied[k] != 0) { B->b.xfrc = 1; break; }
@@ -524,32 +572,109 @@ int mjb_step_mjdata(mjbBatch* B, struct mjData_* const* dd, int nd) {
     for (int e = 0; e < nenv; e++) for (int i = 0; i < S.neq; i++) tmp[(size_t)e * S.neq + i] = d[e]->eq_active[i];
     if (int rc = field_from_host(B, false, B->b.L.eq_active, S.neq, tmp.data())) return rc;
   }
-  if (int rc = run_step(B, false)) return rc;
+  int rc = 0;
+  switch (op) {
+    case BR_STEP: rc = run_step(B, false); break;
+    case BR_FORWARD: rc = backend::launch_stages(B->dm, B->b, 0x17, 0, B->stream); break;
+    case BR_FORWARD_NOSENSOR: rc = backend::launch_stages(B->dm, B->b, 0x17, 8, B->stream); break;
+    // mj_step1 (engine_forward.c:1884-1905): checks, position and velocity stages.  The velocity launch of this
+    // path also evaluates actuation / acceleration; mj_step2 recomputes those from the controls it is given.
+    case BR_STEP1: rc = backend::launch_stages(B->dm, B->b, 1 | 2, 1, B->stream); break;
+    // mj_step2 (:1909-1940): actuation, acceleration, constraint, acceleration check, integration (Euler family)
+    case BR_STEP2: rc = backend::launch_stages(B->dm, B->b, 2 | 4 | 8, 0, B->stream); break;
+  }
+  if (rc) return rc;
   {
     tmp.resize(nenv);
-    if (int rc = field_to_host(B, false, B->b.L.time, 1, tmp.data())) return rc;
+    if (int rc2 = field_to_host(B, false, B->b.L.time, 1, tmp.data())) return rc2;
     for (int e = 0; e < nenv; e++) d[e]->time = tmp[e];
   }
 #define X(name, cnt)                                                                             \
   if ((cnt) > 0) {                                                                               \
     tmp.resize((size_t)nenv * (cnt));                                                            \
-    if (int rc = field_to_host(B, false, B->b.L.name, (cnt), tmp.data())) return rc;              \
+    if (int rc2 = field_to_host(B, false, B->b.L.name, (cnt), tmp.data())) return rc2;            \
     for (int e = 0; e < nenv; e++) memcpy(d[e]->name, tmp.data() + (size_t)e * (cnt), sizeof(double) * (cnt)); \
   }
   MJB_MJDATA_OUT(X)
 #undef X
+  // Arena members (contact, efc_*) are NOT materialised in the reference's mjData: the arena allocator is private
+  // to the reference library.  The counts are therefore published as zero - an mjData that claims ncon contacts
+  // without holding them would make mj_contactForce / the visualiser / `d.contact` read stale memory.  The batch's
+  // own counts and lists are available by name (mjb_get_field_int(b, "ncon") ..., "con_*", "efc_*").
+  for (int e = 0; e < nenv; e++) { d[e]->ncon = 0; d[e]->nefc = 0; d[e]->ne = 0; d[e]->nf = 0; d[e]->nl = 0; }
   std::vector<int> it((size_t)nenv * NWARNING);
-  if (int rc = field_to_host(B, true, B->b.L.ncon, 1, it.data())) return rc;
-  for (int e = 0; e < nenv; e++) d[e]->ncon = it[e];
-  if (int rc = field_to_host(B, true, B->b.L.nefc, 1, it.data())) return rc;
-  for (int e = 0; e < nenv; e++) d[e]->nefc = it[e];
-  if (int rc = field_to_host(B, true, B->b.L.warning, NWARNING, it.data())) return rc;
+  if (int rc2 = field_to_host(B, true, B->b.L.warning, NWARNING, it.data())) return rc2;
   for (int e = 0; e < nenv; e++)
     for (int w = 0; w < NWARNING && w < (int)mjNWARNING; w++) {
       // the batch counts warnings since its last reset; mjData accumulates: add what this step raised
-      d[e]->warning[w].number += it[(size_t)e * NWARNING + w];
+      const int n = it[(size_t)e * NWARNING + w];
+      if (n && !d[e]->warning[w].number) route_warning(w, d[e]->time);   // first occurrence: mju_warning, like mj_warning
+      d[e]->warning[w].number += n;
     }
   return field_zero(B, true, B->b.L.warning, NWARNING) || backend::sync(B->stream);
+}
+
+int mjb_step_mjdata(mjbBatch* B, struct mjData_* const* dd, int nd) { return bridge_mjdata(B, (mjData* const*)dd, nd, BR_STEP); }
+int mjb_forward_mjdata(mjbBatch* B, struct mjData_* const* dd, int nd) { return bridge_mjdata(B, (mjData* const*)dd, nd, BR_FORWARD); }
+
+// _unsafe_rollout's own argument list (rollout.cc:67-78): one mjModel pointer per environment.  This path shares
+// one flattened model among the environments of a batch, so the pointers must all name the same model; the
+// batch is created for the call and released after it.
+int mjb_rollout_models(const struct mjModel_* const* m, int nbatch, int nstep, unsigned int control_spec, const double* state0,
+                       const double* warmstart0, const double* control, double* state, double* sensordata, int device) {
+  if (!m || nbatch <= 0) return fail(MJB_ERR_ARG, "mjb_rollout_models: bad arguments");
+  for (int e = 1; e < nbatch; e++)
+    if (m[e] != m[0]) return fail(MJB_ERR_UNSUPPORTED, "unsupported: a different mjModel per environment (share one model, or make one batch per model)");
+  mjbBatch* B = mjb_make_batch(m[0], nbatch, 0, 0, device);
+  if (!B) return MJB_ERR_UNSUPPORTED;
+  const int rc = mjb_rollout(B, nstep, control_spec, state0, warmstart0, control, state, sensordata);
+  const std::string msg = rc ? get_error() : "";
+  mjb_free_batch(B);
+  if (rc) set_error(msg);
+  return rc;
+}
+
+// ---- the reference's single-environment entry points (include/mujoco/mujoco.h:189-204) ------------------------
+// Exported under their own names so that a host written against the reference (sample/testspeed.cc's loop, the
+// Python bindings' functions.cc) can resolve them in libmjb200.so: each call is a batch of ONE environment on the
+// mjData bridge above.  One batch is cached per mjModel pointer; call mjb_forget_model(m) after editing the model
+// (options, parameters) or before freeing it.  Fatal conditions go to mju_error when the reference library is
+// loaded in the process (the Python bindings intercept it, python/mujoco/errors.h:140-226), else to stderr + abort,
+// which is what mju_error does by default.
+namespace {
+std::mutex g_shim_mutex;
+std::map<const mjModel*, mjbBatch*> g_shim_batches;
+
+void shim_call(const mjModel* m, mjData* d, BridgeOp op, const char* what) {
+  std::lock_guard<std::mutex> lock(g_shim_mutex);
+  mjbBatch*& B = g_shim_batches[m];
+  if (!B) B = mjb_make_batch((const struct mjModel_*)m, 1, 0, 0, -1);
+  if (!B) { g_shim_batches.erase(m); route_error(std::string(what) + ": " + get_error()); return; }
+  mjData* one[1] = {d};
+  if (bridge_mjdata(B, one, 1, op)) route_error(std::string(what) + ": " + get_error());
+}
+}  // namespace
+
+void mjb_forget_model(const struct mjModel_* m) {
+  std::lock_guard<std::mutex> lock(g_shim_mutex);
+  auto it = g_shim_batches.find((const mjModel*)m);
+  if (it == g_shim_batches.end()) return;
+  mjb_free_batch(it->second);
+  g_shim_batches.erase(it);
+}
+
+MJB_API void mj_step(const mjModel* m, mjData* d) { shim_call(m, d, BR_STEP, "mj_step"); }
+MJB_API void mj_forward(const mjModel* m, mjData* d) { shim_call(m, d, BR_FORWARD, "mj_forward"); }
+// skipstage only skips recomputation of stages whose inputs did not change (engine_forward.c:1783-1842): running
+// them again gives the same values, so the shim honours skipsensor and recomputes the stages
+MJB_API void mj_forwardSkip(const mjModel* m, mjData* d, int skipstage, int skipsensor) {
+  (void)skipstage;
+  shim_call(m, d, skipsensor ? BR_FORWARD_NOSENSOR : BR_FORWARD, "mj_forwardSkip");
+}
+MJB_API void mj_step1(const mjModel* m, mjData* d) { shim_call(m, d, BR_STEP1, "mj_step1"); }
+MJB_API void mj_step2(const mjModel* m, mjData* d) {
+  if (m->opt.integrator == mjINT_RK4) { route_error("mj_step2: the Runge-Kutta integrator cannot be split (engine_forward.c:1909), call mj_step"); return; }
+  shim_call(m, d, BR_STEP2, "mj_step2");
 }
 
 int mjb_set_thread_mapping(int warp_per_env) {

@@ -29,12 +29,17 @@ int launch_stages(const DModel& dm, const Batch& b, int mask, int flags, void* s
 // one full Euler / implicitfast step as a split sequence of launches (PGS in its own kernel); `first` / `later`
 // are the flags of the first and the following launches of the step (rollout skip rule)
 bool split_step_available(const DModel& dm, const Batch& b);
-int launch_split_step(const DModel& dm, const Batch& b, int first, int later, void* stream);
+// stagger: optional stream that is made to wait for this step's first half (position + velocity) - the env groups
+// of a multi-step call start one first-half apart, so that one group's solve (a dependent chain that leaves the
+// SMs mostly idle) overlaps the other groups' throughput-bound halves
+int launch_split_step(const DModel& dm, const Batch& b, int first, int later, void* stream, void* stagger = nullptr);
+// one split step, synchronous, with the duration (ms) of its four launches: first half, solve, second half, redo
+int profile_split_step(const DModel& dm, const Batch& b, void* stream, float* ms);
 int launch_rk4(const DModel& dm, const Batch& b, int phase, int flags, void* stream);   // rk4_phase of every env
 int launch_reset(const DModel& dm, const Batch& b, void* stream);
 // rollout helpers; control/state are DEVICE buffers laid out [nenv][nstep][n] (reference layout)
 int launch_set_control(const DModel& dm, const Batch& b, const double* control, int nstep, int t,
-                       unsigned spec, int ncontrol, void* stream);
+                       unsigned spec, int ncontrol, void* stream, bool skip_warned = true);
 int launch_get_state(const DModel& dm, const Batch& b, double* state, int nstep, int t, int nstate, void* stream);
 int launch_get_sensor(const DModel& dm, const Batch& b, double* sens, int nstep, int t, int nsens, void* stream);   // [nenv][nstep][nsens]
 // native-layout variants: ctrl [nstep][nu][stride], state [nstep][nstate][stride]
@@ -44,6 +49,8 @@ int launch_get_state_native(const DModel& dm, const Batch& b, double* state, int
 int launch_pack(const Batch& b, int is_int, long off, long cnt, void* dense, int to_dense, void* stream);
 int launch_fill_zero(const Batch& b, int is_int, long off, long cnt, void* stream);
 long launches();
+// development / test switches of the backend ("pgs4_slots": force the slot layout of the PGS kernel); -1 = unknown key
+int set_debug(const char* key, int value);
 
 }  // namespace backend
 }  // namespace mjb

@@ -88,10 +88,24 @@ MJB_HD void site_moment(const Env& d) {
   MJB_PSYNC();
 }
 
+// development aid (-DMJB_STAGE_PROF, device only): cycles per sub-stage, summed and maximised over environments
+#if defined(MJB_STAGE_PROF) && defined(__CUDACC__)
+static __device__ unsigned long long g_stage_prof[64];
+#endif
+#if defined(MJB_STAGE_PROF) && defined(__CUDA_ARCH__)
+#define MJB_PROF_BEGIN long long pt_ = clock64();
+#define MJB_PROF_MARK(id) { const long long t_ = clock64(); if (d.lane == 0) { atomicAdd(&g_stage_prof[2 * (id)], (unsigned long long)(t_ - pt_)); atomicMax(&g_stage_prof[2 * (id) + 1], (unsigned long long)(t_ - pt_)); } pt_ = clock64(); }
+#else
+#define MJB_PROF_BEGIN
+#define MJB_PROF_MARK(id)
+#endif
+
 MJB_HD void fwd_position(const Env& d) {
+  MJB_PROF_BEGIN
   kinematics(d);
   com_pos(d);
   tendon(d);
+  MJB_PROF_MARK(0)
   make_M(d);
   {
     FD M = d.M(), qLD = d.qLD();
@@ -99,12 +113,17 @@ MJB_HD void fwd_position(const Env& d) {
     MJB_PSYNC();
     factor_I(d, qLD, d.qLDiagInv());
   }
+  MJB_PROF_MARK(1)
   collision(d);
+  MJB_PROF_MARK(2)
   make_constraint(d);
   make_islands(d);
+  MJB_PROF_MARK(3)
   project_constraint(d);
+  MJB_PROF_MARK(4)
   transmission(d);
   site_moment(d);
+  MJB_PROF_MARK(5)
 }
 
 MJB_HD void object_velocity(const Env& d, int kind, int id, V3& ang, V3& lin);   // defined with the sensors below
@@ -662,17 +681,23 @@ MJB_HD void stage_position(const Env& d, bool is_step) {
   fwd_position(d);
 }
 MJB_HD void stage_velocity(const Env& d) {
+  MJB_PROF_BEGIN
   fwd_velocity(d);
+  MJB_PROF_MARK(6)
   fwd_actuation(d);
   fwd_acceleration(d);
+  MJB_PROF_MARK(7)
   constraint_begin(d);
+  MJB_PROF_MARK(8)
 }
 MJB_HD void stage_solve(const Env& d) {
   if (d.solver == SOL_PGS) solve_pgs(d);
   else solve_primal(d, d.solver == SOL_NEWTON);
 }
 MJB_HD void stage_finish_forward(const Env& d) {
+  MJB_PROF_BEGIN
   if (d.solver == SOL_PGS) dual_finish(d);
+  MJB_PROF_MARK(9)
 }
 // ---- sensors (engine_sensor.c: mj_computeSensorPos :525-836, Vel :839-955, Acc :958-1385, apply_cutoff
 // :198-223, frame helpers :227-277; mj_objectVelocity engine_core_util.c:835-886, mju_transformSpatial

@@ -50,10 +50,10 @@ __global__ void k_reset(DModel m, Batch b) {
   reset_env(d, true);
 }
 
-__global__ void k_set_control(DModel m, Batch b, const double* control, int nstep, int t, unsigned spec, int ncontrol) {
+__global__ void k_set_control(DModel m, Batch b, const double* control, int nstep, int t, unsigned spec, int ncontrol, int skip_warned) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= b.nenv) return;
-  run_set_control(m, b, e, control, nstep, t, spec, ncontrol);
+  run_set_control(m, b, e, control, nstep, t, spec, ncontrol, skip_warned != 0);
 }
 
 __global__ void k_get_state(DModel m, Batch b, double* state, int nstep, int t, int nstate) {
@@ -175,12 +175,13 @@ bool split_step_available(const DModel& dm, const Batch& b) {
   return want && b.warp_per_env && b.nlane == 32 && dm.opt.solver == SOL_PGS && !islands &&
          (dm.opt.integrator == INT_EULER || dm.opt.integrator == INT_IMPLICITFAST);
 }
-int launch_split_step(const DModel& dm, const Batch& b, int first, int later, void* s) {
+int launch_split_step(const DModel& dm, const Batch& b, int first, int later, void* s, void* stagger) {
   const bool lean = dm.sz.nsensor == 0 && dm.sz.neq == 0 && dm.sz.ntree == 1 && dm.opt.integrator != INT_IMPLICITFAST && !dm.sz.actfeat && !b.xfrc;
   static const int part_lanes = [] { const char* e = getenv("MJB_PART_LANES"); return e ? atoi(e) : 16; }();   // measured (humanoid x4096): 16 lanes 1.357 ms/step, 32 lanes 1.385, 8 lanes 1.533
   if (lean && part_lanes == 16) launch_kpart1_lean16(dm, b, 0, first, s);
   else if (lean && part_lanes == 8) launch_kpart1_lean8(dm, b, 0, first, s);
   else if (lean) launch_kpart1_lean(dm, b, 0, first, s); else launch_kpart1(dm, b, 0, first, s);
+  if (stagger) { if (int rc = stream_order(s, stagger)) return rc; }   // the next group starts once this group's first half is done
   if (launch_pgs4(dm, b, later, s)) return cuda_fail(cudaGetLastError(), "PGS order table");
   if (lean && part_lanes == 16) launch_kpart2_lean16(dm, b, 0, later, s);
   else if (lean && part_lanes == 8) launch_kpart2_lean8(dm, b, 0, later, s);
@@ -192,6 +193,35 @@ int launch_split_step(const DModel& dm, const Batch& b, int first, int later, vo
     g_launches++;
     CK(cudaPeekAtLastError(), "redo launch");
   }
+  return 0;
+}
+
+// one split step with CUDA events around each launch (bench.py: per-kernel durations on the launching stream)
+int profile_split_step(const DModel& dm, const Batch& b, void* s, float* ms) {
+  cudaStream_t st = (cudaStream_t)s;
+  cudaEvent_t ev[5];
+  for (auto& e : ev) CK(cudaEventCreate(&e), "event create");
+  const bool lean = dm.sz.nsensor == 0 && dm.sz.neq == 0 && dm.sz.ntree == 1 && dm.opt.integrator != INT_IMPLICITFAST && !dm.sz.actfeat && !b.xfrc;
+  static const int part_lanes = [] { const char* e = getenv("MJB_PART_LANES"); return e ? atoi(e) : 16; }();
+  cudaEventRecord(ev[0], st);
+  if (lean && part_lanes == 16) launch_kpart1_lean16(dm, b, 0, 1, s);
+  else if (lean && part_lanes == 8) launch_kpart1_lean8(dm, b, 0, 1, s);
+  else if (lean) launch_kpart1_lean(dm, b, 0, 1, s); else launch_kpart1(dm, b, 0, 1, s);
+  cudaEventRecord(ev[1], st);
+  if (launch_pgs4(dm, b, 0, s)) return cuda_fail(cudaGetLastError(), "PGS order table");
+  cudaEventRecord(ev[2], st);
+  if (lean && part_lanes == 16) launch_kpart2_lean16(dm, b, 0, 0, s);
+  else if (lean && part_lanes == 8) launch_kpart2_lean8(dm, b, 0, 0, s);
+  else if (lean) launch_kpart2_lean(dm, b, 0, 0, s); else launch_kpart2(dm, b, 0, 0, s);
+  cudaEventRecord(ev[3], st);
+  if (!(dm.opt.disableflags & DSBL_AUTORESET)) {
+    if (lean) launch_kstep_pgs32_lean(dm, b, kMaskStep, 16, s); else launch_kstep_pgs32(dm, b, kMaskStep, 16, s);
+  }
+  cudaEventRecord(ev[4], st);
+  g_launches += 4;
+  CK(cudaStreamSynchronize(st), "profile step");
+  for (int i = 0; i < 4; i++) cudaEventElapsedTime(&ms[i], ev[i], ev[i + 1]);
+  for (auto& e : ev) cudaEventDestroy(e);
   return 0;
 }
 
@@ -231,8 +261,8 @@ int launch_reset(const DModel& dm, const Batch& b, void* s) {
   return 0;
 }
 int launch_set_control(const DModel& dm, const Batch& b, const double* control, int nstep, int t, unsigned spec,
-                       int ncontrol, void* s) {
-  k_set_control<<<nblocks(b, 128), 128, 0, (cudaStream_t)s>>>(dm, b, control, nstep, t, spec, ncontrol);
+                       int ncontrol, void* s, bool skip_warned) {
+  k_set_control<<<nblocks(b, 128), 128, 0, (cudaStream_t)s>>>(dm, b, control, nstep, t, spec, ncontrol, skip_warned ? 1 : 0);
   g_launches++;
   CK(cudaPeekAtLastError(), "k_set_control launch");
   return 0;

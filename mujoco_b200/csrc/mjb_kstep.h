@@ -80,6 +80,14 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta, (PART != 0 && NLANE < 32) ?
   }                                                                                                          \
   }
 #define MJB_KSTEP_LAUNCHER(NAME, SOLVER, NLANE, FEAT) MJB_KSTEP_LAUNCHER_PART(NAME, SOLVER, NLANE, FEAT, 0)
+#if defined(MJB_STAGE_PROF) && defined(MJB_STAGE_PROF_FN)   // development aid: read (and clear) this unit's sub-stage counters
+extern "C" __attribute__((visibility("default"))) int MJB_STAGE_PROF_FN(unsigned long long* out) {
+  int rc = (int)cudaMemcpyFromSymbol(out, g_stage_prof, sizeof(unsigned long long) * 64);
+  unsigned long long zero[64] = {0};
+  cudaMemcpyToSymbol(g_stage_prof, zero, sizeof(zero));
+  return rc;
+}
+#endif
 #endif
 
 }  // namespace mjb

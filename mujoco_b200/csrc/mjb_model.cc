@@ -21,6 +21,7 @@
 #include <vector>
 
 #include <mujoco/mjmodel.h>
+#include <mujoco/mujoco.h>   // mjVERSION_HEADER (declarations only: the reference library is never linked)
 #include <mujoco/mjxmacro.h>
 
 namespace mjb {
@@ -39,7 +40,9 @@ mjModel* load_mjb(const char* path) {
   fseek(f, 0, SEEK_END);
   long sz = ftell(f);
   fseek(f, 0, SEEK_SET);
-  std::vector<unsigned char> buf(sz);
+  if (sz < 0 || sz > (1L << 34)) { fclose(f); set_error("cannot size the MJB file (or it is larger than 16 GB)"); return nullptr; }
+  std::vector<unsigned char> buf;
+  try { buf.resize((size_t)sz); } catch (...) { fclose(f); set_error("out of memory reading the MJB file"); return nullptr; }
   if (fread(buf.data(), 1, sz, f) != (size_t)sz) { fclose(f); set_error("short read"); return nullptr; }
   fclose(f);
   size_t p = 0;
@@ -58,13 +61,23 @@ mjModel* load_mjb(const char* path) {
 #define X(name) nsize_expected++;
   MJMODEL_SIZES
 #undef X
-  if (header[2] != nsize_expected) {
-    set_error("MJB was written by a different mjModel revision (size-field count differs)");
+  int nptr_expected = 0;
+  {
+#define X(type, name, nr, nc) nptr_expected++;
+    MJMODEL_POINTERS
+#undef X
+  }
+  // the reference compares all five header words (engine_io.c:568-580): id, precision, number of size fields,
+  // library version, number of pointers
+  if (header[2] != nsize_expected || header[3] != mjVERSION_HEADER || header[4] != nptr_expected) {
+    set_error("MJB was written by a different mjModel revision (version / size-field / pointer count differs)");
     return nullptr;
   }
   std::vector<mjtSize> sizes(nsize_expected);
   if (!rd(sizes.data(), sizeof(mjtSize) * nsize_expected)) { set_error("truncated MJB (sizes)"); return nullptr; }
+  for (mjtSize v : sizes) if (v < -1 || v > (mjtSize)1 << 40) { set_error("corrupt MJB (negative or absurd size field)"); return nullptr; }   // (nconmax / njmax are -1 by default)
   mjModel* m = (mjModel*)calloc(1, sizeof(mjModel));
+  if (!m) { set_error("out of memory (mjModel)"); return nullptr; }
   {
     int k = 0;
 #define X(name) m->name = sizes[k++];
@@ -82,7 +95,10 @@ mjModel* load_mjb(const char* path) {
     MJMODEL_POINTERS
 #undef X
   }
-  unsigned char* store = (unsigned char*)aligned_alloc(64, total + 64);
+  // the arrays of a well-formed file fit in the file: a larger total means corrupt size fields
+  if (total > (size_t)sz + 64 * (size_t)nptr_expected) { free(m); set_error("corrupt MJB (array sizes exceed the file)"); return nullptr; }
+  unsigned char* store = (unsigned char*)aligned_alloc(64, (total + 64 + 63) / 64 * 64);
+  if (!store) { free(m); set_error("out of memory (mjModel arrays)"); return nullptr; }
   memset(store, 0, total + 64);
   m->buffer = store;
   size_t off = 0;

@@ -29,6 +29,7 @@
 // mjb_constraint.h (global memory, any lane count) on their four lanes.
 #include <cuda_runtime.h>
 
+#include <cstring>
 #include <mutex>
 #include <vector>
 
@@ -41,13 +42,14 @@ namespace mjb {
 constexpr int kPgs4Rows = 68;                 // row capacity of the largest register class (4 * 16 + 3, padded)
 // shared memory of one warp (= one CTA): 48 KB.
 //   staged layout (the normal case): the eight environments are packed back to back, each with
-//     nefc records of RECD = 4 NQ + 8 doubles - one record per row of AR, re-laid so that every lane finds ITS
-//     chain elements contiguous and zero-padded to the class size: [lane 0: a_0 a_4 ..][lane 1: a_1 a_5 ..]
-//     [lane 2][lane 3][tail a_n4 a_n4+1 a_n4+2, b][1/AR_ii, AR_ii, lo, hi] - followed by four vectors of nefc
-//     doubles (force, fprev, fmom, restart products);
+//     nefc records of 4 nqp + 6 doubles (nqp = the environment's own chain length, rounded to even) - one record
+//     per row of AR, re-laid so that every lane finds ITS chain elements contiguous: [lane 0: a_0 a_4 ..]
+//     [lane 1: a_1 a_5 ..][lane 2][lane 3][tail a_n4 a_n4+1 a_n4+2, b][1/AR_ii, AR_ii] - then a zero pad; after the
+//     records of all eight environments, six vectors of nefc doubles each (force, fprev, fmom, restart products,
+//     lo, hi: the infinite bounds stay out of reach of the padded chain loads);
 //   slot layout (fallback when the packed records of a warp exceed the budget): fixed slots of kPgs4Rows rows with
 //     the vectors and six row constants; AR rows are then read from global memory two rows ahead.
-constexpr int kPgs4SmemBytes = 48 * 1024;
+constexpr int kPgs4SmemBytes = 56 * 1024;
 constexpr int kPgs4Beta = 128;                // entries of the momentum-coefficient table at the end of the shared memory
 constexpr int kPgs4EnvDbl = 10 * kPgs4Rows;   // slot layout: force fprev fmom prod + 6 per row (b ainv ad lo hi -)
 // slot stride in 4-byte words == 8 (mod 32): the eight environments of a warp start on different bank groups
@@ -68,6 +70,7 @@ struct Pgs4Env {
   double* slot;               // shared memory of this environment: its slot, or its packed records
   double* vec;                // the four vectors (force, fprev, fmom, prod), stride vstride
   int vstride;
+  int recd, nqp;              // packed layout: doubles per record (4 nqp + 6), chain elements per lane (own nq, rounded to even)
   const double* beta;         // (n - 1) / (n + 2) for n < kPgs4Beta (shared memory)
   const unsigned char* ord;   // visiting orders of a problem with nefc rows: [sweep][position] (pgs4_order_table)
 };
@@ -78,7 +81,7 @@ struct Pgs4Env {
 template <int NQ, int DEPTH, bool STAGED>
 __device__ __forceinline__ int pgs4_sweeps(const Options& opt, int nv, bool act, const Pgs4Env& E, int k) {
   constexpr int R = kPgs4Rows;
-  constexpr int RECD = 4 * NQ + 8;
+  const int RECD = E.recd;
   const unsigned full = 0xffffffffu;
   double* s_force = E.vec;
   double* s_fprev = s_force + E.vstride;
@@ -88,8 +91,8 @@ __device__ __forceinline__ int pgs4_sweeps(const Options& opt, int nv, bool act,
   const double* s_lo = s_prod + E.vstride;   // (staged layout only)
   const double* s_hi = s_lo + E.vstride;
   const double* s_rc = STAGED ? E.slot : E.slot + 4 * R;
-  const double* recA = E.slot + k * NQ;      // staged: this lane's chain elements of row 0
-  const double* recT = E.slot + 4 * NQ;      // staged: tail elements and constants of row 0
+  const double* recA = E.slot + k * E.nqp;   // staged: this lane's chain elements of row 0
+  const double* recT = E.slot + 4 * E.nqp;   // staged: tail elements and constants of row 0
   const int nefc = E.nefc;
   const int n4 = nefc & ~3, nq = n4 >> 2, tail = nefc - n4;
   const double scale = 1 / (opt.meaninertia * (nv > 1 ? nv : 1));
@@ -135,7 +138,7 @@ __device__ __forceinline__ int pgs4_sweeps(const Options& opt, int nv, bool act,
   auto load_consts = [&](int i, double2& c01, double2& c23) {
     if (STAGED) {
       const double2* pt = (const double2*)(recT + i * RECD);
-      c01 = pt[2]; c23 = pt[3];
+      c01 = pt[2]; c23 = make_double2(s_lo[i], s_hi[i]);
     } else {
       c01 = make_double2(s_rc[6 * i + 1], s_rc[6 * i + 2]);
       c23 = make_double2(s_rc[6 * i + 3], s_rc[6 * i + 4]);
@@ -357,24 +360,31 @@ __global__ void __launch_bounds__(32) k_pgs4(DModel m, Batch b, int flags, const
   E.gAR = d.efc_AR().p;
   E.ord = order_tab + (size_t)order_iters * (nefc > 0 ? nefc * (nefc - 1) / 2 : 0);
   // packed (staged) layout if the records of the eight environments fit the warp's shared memory
-  const int NQc = top <= 4 * 4 + 3 ? 4 : top <= 4 * 8 + 3 ? 8 : 16;
-  const int recd = 4 * NQc + 8;
-  const int mydbl = nefc * (recd + 6) + (nefc & 1) * 6;   // records + six vectors; keeps every base 16-byte aligned
-  int before = 0, total = 0;
+  const int NQc = top <= 4 * 4 + 3 ? 4 : top <= 4 * 8 + 3 ? 8 : top <= 4 * 12 + 3 ? 12 : 16;
+  // each environment's records are sized by its OWN row length (a small neighbour of a large problem stays small);
+  // the class code reads up to NQc chain elements per lane, so reads past an environment's own chain length land
+  // in finite data of the SAME environment (its next lane / record, or the zero pad after its last record) and meet
+  // forces that are exactly zero: + (+-0) leaves a chain sum unchanged
+  const int nqe_ = (nefc & ~3) >> 2;
+  E.nqp = (nqe_ + 1) & ~1;
+  E.recd = 4 * E.nqp + 6;
+  const int vstr = nefc + (nefc & 1);
+  const int myrec = nefc ? nefc * E.recd + 16 : 0, myvec = 6 * vstr;
+  int rec_before = 0, rec_total = 0, vec_before = 0, vec_total = 0;
 #pragma unroll
   for (int gg = 0; gg < 8; gg++) {
-    const int v = __shfl_sync(full, mydbl, 4 * gg);
-    if (gg < g) before += v;
-    total += v;
+    const int v = __shfl_sync(full, myrec, 4 * gg), w = __shfl_sync(full, myvec, 4 * gg);
+    if (gg < g) { rec_before += v; vec_before += w; }
+    rec_total += v; vec_total += w;
   }
-  const bool staged = total * 8 <= kPgs4SmemBytes - 8 * kPgs4Beta && !(flags & 256);   // flags bit8: force the slot layout (tests)
+  const bool staged = (rec_total + vec_total) * 8 <= kPgs4SmemBytes - 8 * kPgs4Beta && !(flags & 256);   // flags bit8: force the slot layout (tests)
   constexpr int R = kPgs4Rows;
   const double* gf = d.efc_force().p; const double* gb = d.efc_b().p; const double* gfl = d.efc_frictionloss().p;
   if (staged) {
-    E.slot = pgs4_smem + before;
-    E.vec = E.slot + nefc * recd;
-    E.vstride = nefc + (nefc & 1);
-    if (!act) { E.slot = pgs4_smem; E.vec = pgs4_smem; E.vstride = 0; }   // idle lanes read (never write) valid memory
+    E.slot = pgs4_smem + rec_before;
+    E.vec = pgs4_smem + rec_total + vec_before;
+    E.vstride = vstr;
+    if (!act) { E.slot = pgs4_smem; E.vec = pgs4_smem; E.vstride = 0; E.nqp = 0; E.recd = 6; }   // idle lanes read (never write) valid memory
     if (act) {   // build the records: AR rows re-laid per lane and zero-padded, tail, b, diagonal terms, bounds
       const int n4 = nefc & ~3, nqe = n4 >> 2, tail = nefc - n4;
       for (int i0 = 0; i0 < nefc; i0 += 4) {   // four rows per trip: their loads are in flight together
@@ -384,23 +394,23 @@ __global__ void __launch_bounds__(32) k_pgs4(DModel m, Batch b, int flags, const
           const int i = i0 + u < nefc ? i0 + u : nefc - 1;
           const double* row = E.gAR + (long)i * nefc;
 #pragma unroll
-          for (int q = 0; q < 16; q++) if (q < NQc) a[u][q] = (q < nqe) ? row[4 * q + k] : 0.0;
+          for (int q = 0; q < 16; q++) if (q < E.nqp) a[u][q] = (q < nqe) ? row[4 * q + k] : 0.0;
           tl[u] = (k < tail) ? row[n4 + k] : 0.0;
         }
 #pragma unroll
         for (int u = 0; u < 4; u++) {
           const int i = i0 + u;
           if (i < nefc) {
-            double* rec = E.slot + i * recd;
+            double* rec = E.slot + i * E.recd;
 #pragma unroll
-            for (int q = 0; q < 16; q++) if (q < NQc) rec[k * NQc + q] = a[u][q];
-            if (k < 3) rec[4 * NQc + k] = tl[u];
+            for (int q = 0; q < 16; q++) if (q < E.nqp) rec[k * E.nqp + q] = a[u][q];
+            if (k < 3) rec[4 * E.nqp + k] = tl[u];
           }
         }
       }
       // row constants, each lane its own rows (the two IEEE reciprocals per row are the expensive part)
       for (int c = k; c < nefc; c += 4) {
-        double* t = E.slot + c * recd + 4 * NQc;
+        double* t = E.slot + c * E.recd + 4 * E.nqp;
         const double fl = gfl[c];
         const double ai = __drcp_rn(E.gAR[(long)c * (nefc + 1)]);   // == 1 / x, correctly rounded
         const double lo = (c < E.ne) ? -HUGE_VAL : (c < E.ne + E.nf) ? -fl : 0.0;   // equality rows are unbounded
@@ -408,12 +418,12 @@ __global__ void __launch_bounds__(32) k_pgs4(DModel m, Batch b, int flags, const
         t[3] = gb[c];
         t[4] = ai;
         t[5] = __drcp_rn(ai);     // the reference's Athis[0] = 1 / ARinv
-        t[6] = lo;
-        t[7] = hi;
         E.vec[4 * E.vstride + c] = lo;
         E.vec[5 * E.vstride + c] = hi;
       }
       for (int c = k; c < nefc; c += 4) E.vec[c] = gf[c];
+#pragma unroll
+      for (int u = 0; u < 4; u++) E.slot[nefc * E.recd + 4 * u + k] = 0.0;   // the zero pad after the last record
     }
   } else {
     E.slot = (double*)((int*)pgs4_smem + (size_t)g * kPgs4SlotWords);
@@ -440,11 +450,12 @@ __global__ void __launch_bounds__(32) k_pgs4(DModel m, Batch b, int flags, const
   if (staged) {
     if (NQc == 4) iter = pgs4_sweeps<4, 1, true>(m.opt, m.sz.nv, act, E, k);
     else if (NQc == 8) iter = pgs4_sweeps<8, 1, true>(m.opt, m.sz.nv, act, E, k);
+    else if (NQc == 12) iter = pgs4_sweeps<12, 1, true>(m.opt, m.sz.nv, act, E, k);
     else iter = pgs4_sweeps<16, 1, true>(m.opt, m.sz.nv, act, E, k);
   } else {
     if (NQc == 4) iter = pgs4_sweeps<4, 2, false>(m.opt, m.sz.nv, act, E, k);
     else if (NQc == 8) iter = pgs4_sweeps<8, 2, false>(m.opt, m.sz.nv, act, E, k);
-    else iter = pgs4_sweeps<16, 1, false>(m.opt, m.sz.nv, act, E, k);
+    else iter = pgs4_sweeps<16, 1, false>(m.opt, m.sz.nv, act, E, k);   // (12 takes the 16 code here: the fallback is rare)
   }
   __syncwarp();
   if (act) {
@@ -467,6 +478,11 @@ namespace backend {
 // the order table lives once per device (built on first use for the model's iteration cap; 235 KB at 100 sweeps)
 struct Pgs4Table { unsigned char* dev = nullptr; int iters = 0; };
 static Pgs4Table g_pgs4_tab[64];
+static int g_pgs4_force_slots = 0;   // tests: take the slot layout even when the packed records fit (set_debug)
+int set_debug(const char* key, int value) {
+  if (!strcmp(key, "pgs4_slots")) { g_pgs4_force_slots = value; return 0; }
+  return -1;
+}
 static std::mutex g_pgs4_mutex;
 int launch_pgs4(const DModel& dm, const Batch& b, int flags, void* stream) {
   int dev = 0;
@@ -487,7 +503,8 @@ int launch_pgs4(const DModel& dm, const Batch& b, int flags, void* stream) {
       cudaFuncSetAttribute(k_pgs4, cudaFuncAttributeMaxDynamicSharedMemorySize, kPgs4SmemBytes);
     }
   }
-  static const int force_slots = [] { const char* e = getenv("MJB_PGS4_SLOTS"); return e && atoi(e) ? 256 : 0; }();
+  static const int env_slots = [] { const char* e = getenv("MJB_PGS4_SLOTS"); return e && atoi(e) ? 256 : 0; }();
+  const int force_slots = env_slots | (g_pgs4_force_slots ? 256 : 0);
   const int grid = (b.nenv + 7) / 8;
   k_pgs4<<<grid, 32, kPgs4SmemBytes, (cudaStream_t)stream>>>(dm, b, flags | force_slots, T->dev, T->iters);
   return 0;

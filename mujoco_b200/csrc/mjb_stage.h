@@ -82,7 +82,9 @@ MJB_HD void run_part(const Env& d, int part, int flags) {
     MJB_PSYNC();
     return;
   }
+  MJB_PROF_BEGIN
   if ((d.feat & FEAT_IMPLICITFAST) && d.m.opt.integrator == INT_IMPLICITFAST) implicitfast_advance(d); else euler_advance(d);
+  MJB_PROF_MARK(10)
 }
 
 // run the selected stages of one environment with its cooperative lanes.
@@ -120,10 +122,12 @@ MJB_HD void run_rk4(const DModel& m, const Batch& b, int e, int phase, int flags
 }
 
 // control [nenv][nstep][ncontrol] (reference layout): segments ctrl then qfrc_applied by spec bits
+// skip_warned: the rollout rule (rollout.cc:127-155) - an environment that carries a warning no longer steps, so
+// its controls are not written either.  Per-step callers (mjb_step_host) always write the controls.
 MJB_HD void run_set_control(const DModel& m, const Batch& b, int e, const double* control, int nstep, int t,
-                            unsigned spec, int ncontrol) {
+                            unsigned spec, int ncontrol, bool skip_warned = true) {
   Env d(m, b, e);
-  if (env_has_warning(d)) return;
+  if (skip_warned && env_has_warning(d)) return;
   const double* src = control + ((size_t)e * nstep + t) * ncontrol;
   int k = 0;
   if (spec & (1u << 6)) { FD c = d.ctrl(); for (int i = 0; i < m.sz.nu; i++) c[i] = src[k++]; }

@@ -27,6 +27,7 @@ void stream_destroy(void*) {}
 int sync(void*) { return 0; }
 int stream_order(void*, void*) { return 0; }
 long launches() { return g_launches; }
+int set_debug(const char*, int) { return 0; }
 
 int launch_stages(const DModel& dm, const Batch& b, int mask, int flags, void*) {
   g_launches++;
@@ -41,7 +42,7 @@ bool split_step_available(const DModel& dm, const Batch& b) {
   return (s ? atoi(s) : 1) && b.warp_per_env && dm.opt.solver == SOL_PGS && !islands &&
          (dm.opt.integrator == INT_EULER || dm.opt.integrator == INT_IMPLICITFAST);
 }
-int launch_split_step(const DModel& dm, const Batch& b, int first, int later, void*) {
+int launch_split_step(const DModel& dm, const Batch& b, int first, int later, void*, void*) {
   g_launches += 4;
   for (int e = 0; e < b.nenv; e++) run_env(dm, b, e, 0, first, 0, 1, nullptr, 0, -1, 0xffffffffu, FEAT_ALL, 1);
   for (int e = 0; e < b.nenv; e++) run_env(dm, b, e, 4, later, 0, 1, nullptr, 0);
@@ -49,6 +50,10 @@ int launch_split_step(const DModel& dm, const Batch& b, int first, int later, vo
   if (!(dm.opt.disableflags & DSBL_AUTORESET))
     for (int e = 0; e < b.nenv; e++) run_env(dm, b, e, kMaskStep, later | 16, 0, 1, nullptr, 0);
   return 0;
+}
+int profile_split_step(const DModel& dm, const Batch& b, void* s, float* ms) {
+  for (int i = 0; i < 4; i++) ms[i] = 0;
+  return launch_split_step(dm, b, 1, 0, s, nullptr);
 }
 int launch_get_sensor(const DModel& dm, const Batch& b, double* sens, int nstep, int t, int nsens, void*) {
   g_launches++;
@@ -74,9 +79,9 @@ int launch_reset(const DModel& dm, const Batch& b, void*) {
   return 0;
 }
 int launch_set_control(const DModel& dm, const Batch& b, const double* control, int nstep, int t, unsigned spec,
-                       int ncontrol, void*) {
+                       int ncontrol, void*, bool skip_warned) {
   g_launches++;
-  for (int e = 0; e < b.nenv; e++) run_set_control(dm, b, e, control, nstep, t, spec, ncontrol);
+  for (int e = 0; e < b.nenv; e++) run_set_control(dm, b, e, control, nstep, t, spec, ncontrol, skip_warned);
   return 0;
 }
 int launch_get_state(const DModel& dm, const Batch& b, double* state, int nstep, int t, int nstate, void*) {

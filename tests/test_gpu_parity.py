@@ -366,3 +366,170 @@ def test_condim_4_and_6_vs_oracle():
     for t in (10, 60):
         compare_forward(b, o, ref[:, t, :], ctrl[:, t, :], rtol=RTOL_TIGHT, check_dual=True)
     assert b.field("con_dim").max() >= 4
+
+
+def test_bad_state_warning_and_padding_gpu():
+    """rollout.cc:127-155 on the device: an environment that raises a warning stops stepping and pads its outputs;
+    mj_checkPos auto-resets to qpos0 (engine_forward.c:54-69).  Goes through the split step (first half checks
+    qpos / qvel, the skip decision is shared by the solve and the second half)."""
+    assert available()
+    nenv, nstep = 11, 6
+    m, b, o = make_pair(HUMANOID, mb.SOLVER_PGS, nenv=nenv)
+    o.reset()
+    s0 = np.tile(o.get_state(), (nenv, 1))
+    s0[1, 3] = np.nan                              # bad qpos in env 1
+    s0[9, 1 + o.size("nq") + 2] = np.inf           # bad qvel in env 9 (another warp of the solve launch)
+    ctrl = np.zeros((nenv, nstep, o.size("nu")))
+    out = b.rollout(s0, ctrl)
+    ref, stats, _ = o.rollout(s0, ctrl, nthread=1)
+    assert np.array_equal(out, ref)                # reset + one step, then padded - bit for bit
+    w = b.warnings()
+    assert w[1, 3] == 1 and w[9, 4] == 1 and w[0].sum() == 0 and w[2:9].sum() == 0
+
+
+def test_bad_acceleration_redo_gpu():
+    """mj_checkAcc (engine_forward.c:99-113): a bad qacc resets the environment, the forward pass is repeated on the
+    reset state and the step integrates from there.  In the split step the second half only marks the environment
+    and the redo launch of the fused kernel finishes its step."""
+    assert available()
+    nenv, nstep = 9, 4
+    m, b, o = make_pair(HUMANOID, mb.SOLVER_PGS, nenv=nenv)
+    o.reset()
+    s0 = np.tile(o.get_state(), (nenv, 1))
+    nu = o.size("nu")
+    ctrl = np.zeros((nenv, nstep, nu))
+    # a huge applied force makes qacc overflow mjMAXVAL in env 4 at the first step
+    q = np.zeros((nenv, nstep, o.size("nv")))
+    q[4, 0, 2] = 1e300
+    out = b.rollout(s0, np.concatenate([ctrl, q], axis=2), control_spec=mb.STATE_CTRL | mb.STATE_QFRC_APPLIED)
+    for e in (3, 4, 5):
+        oe = Oracle(HUMANOID)
+        oe.set_opt("solver", mb.SOLVER_PGS)
+        oe.reset()
+        oe.set_state(s0[e])
+        for k in range(nstep):
+            oe.dfield("ctrl")[:] = ctrl[e, k]
+            oe.dfield("qfrc_applied")[:] = q[e, k]
+            oe.step()
+            if e != 4 or k == 0:
+                assert np.array_equal(out[e, k], oe.get_state()), (e, k)
+            if e == 4:
+                break                              # the warning stops the rollout of this environment after the step
+    w = b.warnings()
+    assert w[4, 5] == 1 and w[3].sum() == 0       # mjWARN_BADQACC
+    assert np.array_equal(out[4, 1], out[4, 0])    # padded
+
+
+@pytest.mark.parametrize("solver", SOLVERS)
+def test_touch_zones_gpu(solver):
+    """touch sensors with every zone shape (sphere, box, capsule, ellipsoid, cylinder) on the device -
+    models/ant_touch.xml; bit-for-bit over the first 30 steps, north-star bound after"""
+    assert available()
+    path = os.path.join(ROOT, "models", "ant_touch.mjb")
+    nenv, nstep = 3, 80
+    m, b, o = make_pair(path, solver, nenv=nenv)
+    s0 = perturbed_states(o, nenv, seed=14, height=[0.35, 0.5, 0.75], qvel_std=0.3, qpos_std=0.05)
+    ctrl = np.random.default_rng(5).uniform(-1, 1, (nenv, nstep, o.size("nu")))
+    out, sens = b.rollout(s0, ctrl, return_sensordata=True)
+    hits = np.zeros(6, dtype=int)
+    worst = 0.0
+    for e in range(nenv):
+        oe = Oracle(path)
+        oe.set_opt("solver", solver)
+        oe.reset()
+        oe.set_state(s0[e])
+        for k in range(nstep):
+            oe.dfield("ctrl")[:] = ctrl[e, k]
+            oe.step()
+            r = np.array(oe.dfield("sensordata"))
+            st = oe.get_state()
+            err = max(np.abs(out[e, k] - st).max() / max(1.0, np.abs(st).max()),
+                      np.abs(sens[e, k] - r).max() / max(1.0, np.abs(r).max()))
+            worst = max(worst, err)
+            assert err < (RTOL_TIGHT if k < 30 else RTOL_TRAJ), (e, k, err)
+            hits += (r[12:18] != 0)
+    print("touch zones worst rel err %.3e" % worst)
+    assert (hits > 0).all(), hits      # every zone shape saw a contact
+
+
+def test_1000_step_window_configs1():
+    """SURVEY 8(d) protocol: 64 environments of configs[1] (humanoid, PGS, Euler, random ctrl) over a 1000-step
+    window.  The first 100 steps are held to the north-star bound (1e-6 relative); afterwards the test REPORTS where
+    the trajectories leave it (a contact-rich chaotic system amplifies last-bit differences of libm calls), and checks
+    that contact counts keep matching for as long as the states agree."""
+    assert available()
+    nenv, nstep = 64, 1000
+    m, b, o = make_pair(HUMANOID, mb.SOLVER_PGS, nenv=nenv)
+    o.reset()
+    s0 = np.tile(o.get_state(), (nenv, 1))
+    ctrl = np.random.default_rng(2024).uniform(-1, 1, (nenv, nstep, o.size("nu")))
+    out = b.rollout(s0, ctrl)
+    ref, stats, _ = o.rollout(s0, ctrl, nthread=os.cpu_count() or 1)
+    assert stats[:, 3].sum() == 0 and (b.warnings() == 0).all()
+    scale = np.maximum(1.0, np.abs(ref).max(axis=(0, 1)))
+    err = (np.abs(out - ref) / scale).max(axis=2)            # [env, step]
+    first = np.array([np.argmax(err[e] > RTOL_TRAJ) if (err[e] > RTOL_TRAJ).any() else nstep for e in range(nenv)])
+    print("1000-step window: max rel err over the first 100 steps %.3e; environments inside 1e-6 for all 1000 steps: %d / %d; "
+          "earliest departure at step %d; median departure %d" %
+          (err[:, :100].max(), int((first == nstep).sum()), nenv, int(first.min()), int(np.median(first))))
+    assert err[:, :100].max() < RTOL_TRAJ
+    assert first.min() >= 100
+
+
+def test_pgs_slot_layout_fallback(monkeypatch):
+    """k_pgs4 with the slot layout forced (the path taken when the packed row records of a warp exceed the shared
+    memory): same results as the packed layout, bit for bit"""
+    nenv, nstep = 64, 40
+    o = Oracle(HUMANOID)
+    o.set_opt("solver", 0)
+    s0 = perturbed_states(o, nenv, seed=11, height=[0.2, 0.3, 0.5, 0.8], qvel_std=0.5, qpos_std=0.2)
+    ctrl = np.random.default_rng(12).uniform(-1, 1, (nenv, nstep, o.size("nu")))
+    m = mb.Model(HUMANOID)
+    m.set_option("solver", mb.SOLVER_PGS)
+    b = mb.Batch(m, nenv, nconmax=48, njmax=128)
+    packed = b.rollout(s0, ctrl)
+    niter = b.field("solver_niter")[:, 0].copy()
+    b.set_debug("pgs4_slots", 1)
+    slots = b.rollout(s0, ctrl)
+    b.set_debug("pgs4_slots", 0)
+    assert np.array_equal(packed, slots) and np.array_equal(niter, b.field("solver_niter")[:, 0])
+
+
+def test_single_environment_symbols_gpu():
+    """the loop of sample/testspeed.cc:123 - `mj_step(m, d)` on the reference's own mjModel / mjData - with the
+    symbol resolved in libmjb200.so instead of libmujoco (dlopen + dlsym through ctypes), next to the reference
+    engine stepping a twin mjData; mj_forward, mj_step1 + mj_step2 and mj_forwardSkip likewise"""
+    import ctypes as C
+    assert available()
+    lib = C.CDLL(os.path.join(ROOT, "mujoco_b200", "libmjb200.so"))
+    for name in ("mj_step", "mj_forward", "mj_step1", "mj_step2"):
+        getattr(lib, name).argtypes = [C.c_void_p, C.c_void_p]
+        getattr(lib, name).restype = None
+    lib.mj_forwardSkip.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+    lib.mjb_forget_model.argtypes = [C.c_void_p]
+    ref, ours = Oracle(HUMANOID), Oracle(HUMANOID)
+    s0 = perturbed_states(ref, 1, seed=5, height=[0.6], qvel_std=0.3, qpos_std=0.05)[0]
+    rng = np.random.default_rng(6)
+    for o in (ref, ours):
+        o.reset()
+        o.set_state(s0)
+    lib.mj_forward(ours.m, ours.d)
+    ref.forward()
+    np.testing.assert_allclose(np.array(ours.dfield("qacc")), np.array(ref.dfield("qacc")), rtol=0, atol=1e-9 * max(1.0, np.abs(ref.dfield("qacc")).max()))
+    worst = 0.0
+    for t in range(60):
+        c = rng.uniform(-1, 1, ref.size("nu"))
+        ref.dfield("ctrl")[:] = c
+        ours.dfield("ctrl")[:] = c
+        ref.step()
+        if t % 2:
+            lib.mj_step(ours.m, ours.d)
+        else:
+            lib.mj_step1(ours.m, ours.d)
+            lib.mj_step2(ours.m, ours.d)
+        r = ref.get_state()
+        worst = max(worst, np.abs(ours.get_state() - r).max() / max(1.0, np.abs(r).max()))
+        ours.set_state(r)                       # keep the twins together: the test is per step
+    print("mj_step through libmjb200.so: worst per-step rel err %.3e" % worst)
+    assert worst < RTOL_TIGHT
+    lib.mjb_forget_model(ours.m)

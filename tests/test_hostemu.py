@@ -206,7 +206,7 @@ def test_unsupported_models_are_refused():
         mb.Batch(m, 1)
 
 
-@pytest.mark.parametrize("model", ["humanoid", "ant_act"])
+@pytest.mark.parametrize("model", ["humanoid", "ant_act", "ant_sensors"])
 def test_mjdata_bridge_matches_mj_step(model):
     """mjb_step_mjdata: the reference's per-mjData loop `for k: mj_step(m, d[k])` as one call.  Two sets
     of the reference's own mjData objects start identical; one is stepped by the reference engine, the other
@@ -231,6 +231,8 @@ def test_mjdata_bridge_matches_mj_step(model):
               "qfrc_passive", "actuator_force", "qfrc_actuator", "qfrc_smooth", "qacc_smooth", "qfrc_constraint"]
     if ref[0].size("na"):      # stateful actuators: act goes in and comes back, act_dot comes back
         fields += ["act", "act_dot", "actuator_length", "actuator_velocity"]
+    if ref[0].size("nsensordata"):   # sensors, sites and the rnePostConstraint / subtreeVel outputs the sensors need
+        fields += ["sensordata", "site_xpos", "site_xmat", "cacc", "cfrc_int", "cfrc_ext", "subtree_linvel", "subtree_angmom"]
     for t in range(nstep):
         for e in range(nenv):
             c = rng.uniform(-1, 1, ref[e].size("nu"))
@@ -240,7 +242,9 @@ def test_mjdata_bridge_matches_mj_step(model):
         b.step_mjdata([o.d for o in ours])
         for e in range(nenv):
             assert ref[e].scalar("time") == ours[e].scalar("time")
-            assert ref[e].scalar("ncon") == ours[e].scalar("ncon") and ref[e].scalar("nefc") == ours[e].scalar("nefc")
+            # arena members are not materialised in the bridged mjData: its counts read 0, the batch has the real ones
+            assert ours[e].scalar("ncon") == 0 and ours[e].scalar("nefc") == 0
+            assert ref[e].scalar("ncon") == b.field("ncon")[e, 0] and ref[e].scalar("nefc") == b.field("nefc")[e, 0]
             for f in fields:
                 assert np.array_equal(np.array(ref[e].dfield(f)), np.array(ours[e].dfield(f))), (t, e, f)
 
@@ -610,3 +614,89 @@ def test_touch_zones_bit_exact(solver):
             assert np.array_equal(out[e, k], oe.get_state()) and np.array_equal(sens[e, k], r), (e, k)
             hits += (r[12:18] != 0)
     assert (hits > 0).all(), hits      # every zone shape saw a contact
+
+
+def test_step_host_writes_controls_after_a_warning():
+    """a benign warning (contact buffer full) must not freeze the controls of the per-step API: only the rollout
+    path applies the stop-on-warning rule (rollout.cc:127-155)"""
+    m = mb.Model(ANT, library=hostemu_lib())
+    b = mb.Batch(m, 2, nconmax=1, njmax=64)
+    b.reset()
+    s = b.get_state()
+    s[:, 3] = 0.1                                   # low: several contacts, more than nconmax = 1
+    b.set_state(s)
+    nu, ns = m.size("nu"), b.state_size()
+    out = np.zeros((2, ns))
+    b.step_host(np.full((2, nu), 0.5), out)
+    assert b.warnings()[:, 1].min() >= 1            # mjWARN_CONTACTFULL raised
+    b.step_host(np.full((2, nu), 0.6), out)
+    assert np.array_equal(b.field("ctrl"), np.full((2, nu), 0.6))
+
+
+def test_rollout_rejects_non_input_control_bits():
+    m = mb.Model(ANT, library=hostemu_lib())
+    b = mb.Batch(m, 2)
+    s0 = b.get_state()
+    nu, nv = m.size("nu"), m.size("nv")
+    with pytest.raises(mb.MjbError, match="control_spec"):
+        b.rollout(s0, np.zeros((2, 3, nu + nv)), control_spec=mb.STATE_CTRL | mb.STATE_WARMSTART)
+
+
+def test_single_environment_symbols_match_the_reference():
+    """mj_step / mj_forward / mj_forwardSkip / mj_step1 + mj_step2 exported under the reference's names
+    (include/mujoco/mujoco.h:189-204): the loop of sample/testspeed.cc:123 run through them on the reference's own
+    mjData gives the reference's trajectory (host build of the same source; the GPU test repeats it on the device)"""
+    import ctypes as C
+    from oracle_util import Oracle
+    lib = C.CDLL(HOSTEMU)
+    for name in ("mj_step", "mj_forward", "mj_step1", "mj_step2"):
+        getattr(lib, name).argtypes = [C.c_void_p, C.c_void_p]
+        getattr(lib, name).restype = None
+    lib.mj_forwardSkip.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+    lib.mjb_forget_model.argtypes = [C.c_void_p]
+    ref, ours = Oracle(ANT), Oracle(ANT)
+    s0 = perturbed_states(ref, 1, seed=5, height=[0.5], qvel_std=0.3, qpos_std=0.05)[0]
+    rng = np.random.default_rng(6)
+    for o in (ref, ours):
+        o.reset()
+        o.set_state(s0)
+    lib.mj_forward(ours.m, ours.d)
+    ref.forward()
+    assert np.array_equal(np.array(ref.dfield("qacc")), np.array(ours.dfield("qacc")))
+    for t in range(40):
+        c = rng.uniform(-1, 1, ref.size("nu"))
+        ref.dfield("ctrl")[:] = c
+        ours.dfield("ctrl")[:] = c
+        ref.step()
+        if t % 2:
+            lib.mj_step(ours.m, ours.d)
+        else:                                   # the split form: controls may change between the halves
+            lib.mj_step1(ours.m, ours.d)
+            lib.mj_step2(ours.m, ours.d)
+        assert np.array_equal(ref.get_state(), ours.get_state()), t
+        assert np.array_equal(np.array(ref.dfield("qfrc_constraint")), np.array(ours.dfield("qfrc_constraint")))
+    lib.mj_forwardSkip(ours.m, ours.d, 1, 1)
+    ref.forward()
+    assert np.array_equal(np.array(ref.dfield("qacc")), np.array(ours.dfield("qacc")))
+    lib.mjb_forget_model(ours.m)
+
+
+def test_rollout_models_entry():
+    """mjb_rollout_models: _unsafe_rollout's argument list with one mjModel pointer per environment"""
+    import ctypes as C
+    L = hostemu_lib()
+    L.mjb_rollout_models.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_uint] + [C.c_void_p] * 5 + [C.c_int]
+    m = mb.Model(ANT, library=L)
+    nenv, nstep = 3, 5
+    b = mb.Batch(m, nenv)
+    s0 = b.get_state()
+    s0[:, 3] = [0.4, 0.6, 0.8]
+    ctrl = np.random.default_rng(1).uniform(-1, 1, (nenv, nstep, m.size("nu")))
+    want = b.rollout(s0, ctrl)
+    models = (C.c_void_p * nenv)(*([m.ptr] * nenv))
+    got = np.zeros_like(want)
+    rc = L.mjb_rollout_models(models, nenv, nstep, mb.STATE_CTRL, s0.ctypes.data, None, ctrl.ctypes.data, got.ctypes.data, None, -1)
+    assert rc == 0 and np.array_equal(got, want)
+    other = mb.Model(ANT, library=L)
+    models[1] = other.ptr
+    assert L.mjb_rollout_models(models, nenv, nstep, mb.STATE_CTRL, s0.ctypes.data, None, ctrl.ctypes.data, got.ctypes.data, None, -1) != 0
