@@ -43,6 +43,8 @@ struct mjbBatch_ {
   double* io_state = nullptr;
   void* stage = nullptr;        // dense staging for field I/O
   size_t stage_bytes = 0;
+  void* roll[3] = {nullptr, nullptr, nullptr};   // control / state / sensordata buffers of mjb_rollout, kept between calls
+  size_t roll_bytes[3] = {0, 0, 0};
   std::vector<void*> gstreams;  // extra streams of the grouped multi-step execution (see env_groups)
 };
 
@@ -178,6 +180,7 @@ void mjb_free_batch(mjbBatch* B) {
   backend::dev_free(B->io_ctrl);
   backend::dev_free(B->io_state);
   backend::dev_free(B->stage);
+  for (void* r : B->roll) backend::dev_free(r);
   backend::stream_destroy(B->stream);
   delete B;
 }
@@ -405,20 +408,31 @@ int mjb_rollout(mjbBatch* B, int nstep, unsigned int control_spec, const double*
   double* d_state = nullptr;
   const size_t cbytes = (size_t)nenv * nstep * ncontrol * sizeof(double);
   const size_t sbytes = (size_t)nenv * nstep * nstate * sizeof(double);
+  // device-side images of the caller's arrays: kept in the batch and grown on demand (an allocation per call costs
+  // more than the copies of a short rollout)
+  auto reserve = [&](int k, size_t bytes) -> double* {
+    if (B->roll_bytes[k] < bytes) {
+      backend::sync(B->stream);
+      backend::dev_free(B->roll[k]);
+      B->roll[k] = backend::dev_alloc(bytes);
+      B->roll_bytes[k] = B->roll[k] ? bytes : 0;
+    }
+    return (double*)B->roll[k];
+  };
   if (control && ncontrol && nstep) {
-    d_control = (double*)backend::dev_alloc(cbytes);
+    d_control = reserve(0, cbytes);
     if (!d_control) return fail(MJB_ERR_CUDA, "device allocation failed (control)");
     backend::h2d(d_control, control, cbytes, B->stream);
   }
   if (state && nstep) {
-    d_state = (double*)backend::dev_alloc(sbytes);
-    if (!d_state) { backend::dev_free(d_control); return fail(MJB_ERR_CUDA, "device allocation failed (state)"); }
+    d_state = reserve(1, sbytes);
+    if (!d_state) return fail(MJB_ERR_CUDA, "device allocation failed (state)");
   }
   double* d_sens = nullptr;
   const size_t nbytes = (size_t)nenv * nstep * nsens * sizeof(double);
   if (sensordata && nstep) {
-    d_sens = (double*)backend::dev_alloc(nbytes);
-    if (!d_sens) { backend::dev_free(d_control); backend::dev_free(d_state); return fail(MJB_ERR_CUDA, "device allocation failed (sensordata)"); }
+    d_sens = reserve(2, nbytes);
+    if (!d_sens) return fail(MJB_ERR_CUDA, "device allocation failed (sensordata)");
   }
   std::vector<EnvGroup> gs = env_groups(B, nstep);
   int rc = groups_fork(B, gs);
@@ -435,9 +449,6 @@ int mjb_rollout(mjbBatch* B, int nstep, unsigned int control_spec, const double*
   if (!rc && d_state) rc = backend::d2h(state, d_state, sbytes, B->stream);
   if (!rc && d_sens) rc = backend::d2h(sensordata, d_sens, nbytes, B->stream);
   if (!rc) rc = backend::sync(B->stream);
-  backend::dev_free(d_control);
-  backend::dev_free(d_state);
-  backend::dev_free(d_sens);
   return rc;
 }
 
