@@ -206,11 +206,17 @@ static double act_armature(const mjModel* m, bool tendon, int id) {
   return arm;
 }
 
+// cylinder / box colliders (mjb_collision.h, compiled into the FEAT_COLBOX kernels): up to 8 contacts per pair
+static bool collider_boxfamily(int t1, int t2) {  // t1 <= t2
+  auto is = [&](int a, int b) { return t1 == a && t2 == b; };
+  return is(mjGEOM_PLANE, mjGEOM_CYLINDER) || is(mjGEOM_PLANE, mjGEOM_BOX) || is(mjGEOM_SPHERE, mjGEOM_CYLINDER) ||
+         is(mjGEOM_SPHERE, mjGEOM_BOX);
+}
 static bool collider_supported(int t1, int t2) {  // t1 <= t2
   auto is = [&](int a, int b) { return t1 == a && t2 == b; };
   return is(mjGEOM_PLANE, mjGEOM_SPHERE) || is(mjGEOM_PLANE, mjGEOM_CAPSULE) ||
          is(mjGEOM_SPHERE, mjGEOM_SPHERE) || is(mjGEOM_SPHERE, mjGEOM_CAPSULE) ||
-         is(mjGEOM_CAPSULE, mjGEOM_CAPSULE);
+         is(mjGEOM_CAPSULE, mjGEOM_CAPSULE) || collider_boxfamily(t1, t2);
 }
 static bool collider_defined(int t1, int t2) {  // mjCOLLISIONFUNC != NULL, t1 <= t2
   if (t1 == mjGEOM_PLANE) return t2 != mjGEOM_PLANE && t2 != mjGEOM_HFIELD;
@@ -442,6 +448,7 @@ int build_host_model(const mjModel* m, int nconmax, int njmax, HostModel* out) {
   S.sitetrn = 0;
   for (int i = 0; i < m->nu; i++) if (m->actuator_trntype[i] == mjTRN_SITE) S.sitetrn = 1;
   S.gravcomp = m->flg_gravcomp ? 1 : 0;
+  S.colbox = 0;   // set while the candidate pairs are built
   if (S.gravcomp) S.actfeat = 1;
   S.nq = m->nq; S.nv = m->nv; S.nu = m->nu; S.na = m->na; S.nbody = m->nbody; S.njnt = m->njnt;
   S.ngeom = m->ngeom; S.ntendon = m->ntendon; S.nwrap = m->nwrap; S.nJten = m->nJten; S.nC = m->nC;
@@ -772,6 +779,7 @@ int build_host_model(const mjModel* m, int nconmax, int njmax, HostModel* out) {
           set_error(msg);
           return -2;
         }
+        if (collider_boxfamily(m->geom_type[c.g1], m->geom_type[c.g2])) S.colbox = 1;
         int condim; double solref[mjNREF], solimp[mjNIMP], fr[5];
         contact_param(m, c.g1, c.g2, &condim, solref, solimp, fr);
         double margin = m->geom_margin[c.g1] + m->geom_margin[c.g2];

@@ -31,7 +31,7 @@ enum { STATE_SATISFIED = 0, STATE_QUADRATIC = 1, STATE_LINEARNEG = 2, STATE_LINE
 enum { WARN_INERTIA = 0, WARN_CONTACTFULL = 1, WARN_CNSTRFULL = 2, WARN_BADQPOS = 3,
        WARN_BADQVEL = 4, WARN_BADQACC = 5, WARN_BADCTRL = 6, WARN_VGEOMFULL = 7, NWARNING = 8 };
 enum { NISLAND = 20 };
-enum { FEAT_SENSOR = 1, FEAT_EQUALITY = 2, FEAT_ISLAND = 4, FEAT_IMPLICITFAST = 8, FEAT_ACT = 16, FEAT_ALL = 31 };   // FEAT_ACT: stateful actuators (act), tendon transmissions, muscles
+enum { FEAT_SENSOR = 1, FEAT_EQUALITY = 2, FEAT_ISLAND = 4, FEAT_IMPLICITFAST = 8, FEAT_ACT = 16, FEAT_COLBOX = 32, FEAT_ALL = 63 };   // FEAT_COLBOX: cylinder / box colliders (up to 8 contacts per pair)   // FEAT_ACT: stateful actuators (act), tendon transmissions, muscles
 enum { EQ_JOINT = 0, EQ_TENDON = 1, EQ_CONNECT = 2, EQ_WELD = 3 };   // supported equality kinds (body semantics)
 constexpr int kNEqData = 11;            // eq_data values per equality (mjNEQDATA): polycoef / anchors, relpose, torquescale
 // sensors of the path (engine_sensor.c); internal codes, translated from mjtSensor by the host
@@ -70,6 +70,7 @@ struct Sizes {
   int gravcomp;  // 1 when a body has gravity compensation (qfrc_gravcomp is allocated then)
   int subtreevel;   // 1 when a sensor needs mj_subtreeVel (subtree_linvel / subtree_angmom are allocated then)
   int rnepost;   // 1 when a sensor needs mj_rnePostConstraint (cacc / cfrc_int / cfrc_ext are allocated then)
+  int colbox;    // 1 when a candidate pair needs a cylinder / box collider (FEAT_COLBOX code paths)
   int npair;     // static candidate geom pairs (host-built, reference order)
   int nconmax;   // per-env contact cap
   int njmax;     // per-env constraint-row cap

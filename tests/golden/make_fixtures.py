@@ -34,6 +34,7 @@ MODELS = {
     "ant_mocap": os.path.join(ROOT, "models", "ant_mocap.xml"),
     "ant_act": os.path.join(ROOT, "models", "ant_act.xml"),
     "ant_act_nomuscle": os.path.join(ROOT, "models", "ant_act_nomuscle.xml"),
+    "boxes": os.path.join(ROOT, "models", "boxes.xml"),      # cylinder / box colliders
 }
 
 

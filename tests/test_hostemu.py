@@ -700,3 +700,36 @@ def test_rollout_models_entry():
     other = mb.Model(ANT, library=L)
     models[1] = other.ptr
     assert L.mjb_rollout_models(models, nenv, nstep, mb.STATE_CTRL, s0.ctypes.data, None, ctrl.ctypes.data, got.ctypes.data, None, -1) != 0
+
+
+@pytest.mark.parametrize("solver", [mb.SOLVER_NEWTON, mb.SOLVER_PGS])
+def test_box_and_cylinder_colliders_bit_exact(solver):
+    """plane-box, plane-cylinder, sphere-box, sphere-cylinder (engine_collision_primitive.c:101-258,345-423,
+    engine_collision_box.c:35-95) on models/boxes.xml: seven free bodies tumbling on a plane, contact lists and every
+    field compared bit for bit at several instants, and the whole rollout"""
+    path = os.path.join(ROOT, "models", "boxes.mjb")
+    nenv, nstep = 6, 150
+    m, b, o = make_pair(path, solver, library=hostemu_lib(), nenv=nenv, nconmax=64, njmax=300)
+    rng = np.random.default_rng(3)
+    o.reset()
+    s0 = np.tile(o.get_state(), (nenv, 1))
+    nq = o.size("nq")
+    for e in range(nenv):
+        for k in range(7):                      # random heights, orientations and spins of the free bodies
+            s0[e, 1 + 7 * k + 2] += rng.uniform(-0.05, 0.3)
+            s0[e, 1 + 7 * k + 3:1 + 7 * k + 7] = rng.normal(size=4)
+        s0[e, 1 + nq:] = rng.normal(0, 1.5, o.size("nv"))
+    ctrl = np.zeros((nenv, nstep, 0))
+    out = b.rollout(s0, ctrl)
+    ref, stats, _ = o.rollout(s0, ctrl, nthread=4)
+    assert stats[:, 3].sum() == 0 and (b.warnings() == 0).all()
+    assert np.array_equal(out, ref)
+    types = set()
+    for t in range(4, 150, 5):
+        compare_forward(b, o, ref[:, t, :], np.zeros((nenv, 0)), rtol=0, exact=True, check_dual=(solver == mb.SOLVER_PGS))
+        g1, g2, nc = b.field("con_geom1"), b.field("con_geom2"), b.field("ncon")[:, 0]
+        gt = o.mfield("geom_type")
+        for e in range(nenv):
+            for c in range(nc[e]):
+                types.add((int(gt[g1[e, c]]), int(gt[g2[e, c]])))
+    assert {(0, 5), (0, 6), (2, 5), (2, 6)} <= types, types      # every new collider produced contacts
