@@ -274,6 +274,396 @@ MJB_HD int raw_sphere_box(PreCon& c, double margin, V3 p1, double r1, V3 p2, con
   return 1;
 }
 
+// capsule : box (engine_collision_box.c:110-590).  In the box frame: the point of the capsule's segment closest to
+// the box (against the faces, then against the twelve edges by segment-segment distance), a sphere-box contact
+// there, and - when the segment runs along a face or an edge - a second sphere-box contact at the far point of the
+// segment that is still above the box.
+MJB_HD int collide_capsule_box(PreCon* c, double margin, V3 p1, const M3& m1, const double* size1,
+                               V3 p2, const M3& m2, const double* size2) {
+  double tmp1[3], tmp2[3], tmp3[3], halfaxis[3], axis[3], dif[3], pos[3];
+  const double halflength = size1[1];
+  double secondpos = -4;   // no second contact (valid values are in [-1, 1])
+  double bestsegmentpos, bestboxpos = 0, bestdist, dist, mul = 0, e1, e2, dp = 0, de = 0;
+  int cltype = -4, clface = -1, clcorner = 0, cledge = 0, c1, c2, ax = 0, ax1 = 0, ax2 = 0;
+  {
+    const V3 t = mulmTv3(m2, p1 - p2);          // capsule centre in the box frame
+    pos[0] = t.x; pos[1] = t.y; pos[2] = t.z;
+    const V3 a = mulmTv3(m2, V3{m1.m[2], m1.m[5], m1.m[8]});
+    axis[0] = a.x; axis[1] = a.y; axis[2] = a.z;
+    for (int k = 0; k < 3; k++) halfaxis[k] = axis[k] * halflength;
+  }
+  int axisdir = 0;
+  if (halfaxis[0] > 0) axisdir += 1;
+  if (halfaxis[1] > 0) axisdir += 2;
+  if (halfaxis[2] > 0) axisdir += 4;
+  const double bestdistmax = margin + 2 * (size1[0] + halflength + size2[0] + size2[1] + size2[2]);
+  bestdist = bestdistmax;
+  bestsegmentpos = 0;
+  // is an end of the segment closest to a face of the box?
+  for (int i = -1; i <= 1; i += 2) {
+    for (int k = 0; k < 3; k++) { tmp1[k] = pos[k]; tmp1[k] += halfaxis[k] * i; tmp2[k] = tmp1[k]; }
+    c1 = 0; c2 = -1;
+    for (int j = 0; j < 3; j++) {
+      if (tmp1[j] < -size2[j]) { c1++; c2 = j; tmp1[j] = -size2[j]; }
+      else if (tmp1[j] > size2[j]) { c1++; c2 = j; tmp1[j] = size2[j]; }
+    }
+    if (c1 > 1) continue;
+    for (int k = 0; k < 3; k++) tmp1[k] -= tmp2[k];
+    dist = tmp1[0] * tmp1[0] + tmp1[1] * tmp1[1] + tmp1[2] * tmp1[2];
+    if (dist < bestdist) { bestdist = dist; bestsegmentpos = i; cltype = -2 + i; clface = c2; }
+  }
+  // the twelve edges: edge along axis j through the corner i (bit j of i clear)
+  for (int j = 0; j < 3; j++) {
+    for (int i = 0; i < 8; i++) {
+      if ((i & (1 << j)) != 0) continue;
+      tmp3[0] = ((i & 1) ? 1 : -1) * size2[0];
+      tmp3[1] = ((i & 2) ? 1 : -1) * size2[1];
+      tmp3[2] = ((i & 4) ? 1 : -1) * size2[2];
+      tmp3[j] = 0;
+      for (int k = 0; k < 3; k++) dif[k] = tmp3[k] - pos[k];
+      const double ma = size2[j] * size2[j];
+      const double mb = -size2[j] * halfaxis[j];
+      const double mc = size1[1] * size1[1];
+      const double u = -size2[j] * dif[j];
+      const double v = halfaxis[0] * dif[0] + halfaxis[1] * dif[1] + halfaxis[2] * dif[2];
+      const double det = ma * mc - mb * mb;
+      if (fabs(det) < kMinVal) continue;
+      const double idet = 1 / det;
+      double x1 = (mc * u - mb * v) * idet;
+      double x2 = (ma * v - mb * u) * idet;
+      int s1 = 1, s2 = 1;   // 1: inside the segment, 0 / 2: clamped to an end
+      if (x1 > 1) { x1 = 1; s1 = 2; x2 = (v - mb) * (1 / mc); }
+      else if (x1 < -1) { x1 = -1; s1 = 0; x2 = (v + mb) * (1 / mc); }
+      if (x2 > 1) {
+        x2 = 1; s2 = 2;
+        x1 = (u - mb) * (1 / ma);
+        if (x1 > 1) { x1 = 1; s1 = 2; } else if (x1 < -1) { x1 = -1; s1 = 0; }
+      } else if (x2 < -1) {
+        x2 = -1; s2 = 0;
+        x1 = (u + mb) * (1 / ma);
+        if (x1 > 1) { x1 = 1; s1 = 2; } else if (x1 < -1) { x1 = -1; s1 = 0; }
+      }
+      for (int k = 0; k < 3; k++) { dif[k] = tmp3[k] - pos[k]; dif[k] += halfaxis[k] * (-x2); }
+      dif[j] += size2[j] * x1;
+      const double d2 = dif[0] * dif[0] + dif[1] * dif[1] + dif[2] * dif[2];
+      c1 = s1 * 3 + s2;
+      if (d2 < bestdist - kMinVal) {
+        bestdist = d2;
+        bestsegmentpos = x2;
+        bestboxpos = x1;
+        c2 = c1 / 6;                       // the upper end of the edge is the closest
+        clcorner = i + (1 << j) * c2;
+        cledge = j;
+        cltype = c1;
+      }
+    }
+  }
+  if (cltype == -4) return 0;
+  bool skip = false;
+  if (cltype >= 0 && cltype / 3 != 1) {   // closest to a corner of the box
+    c1 = axisdir ^ clcorner;
+    if (c1 == 0 || c1 == 7) skip = true;   // pointing to or away from the corner: no second contact
+    else {
+      if (c1 == 1 || c1 == 2 || c1 == 4) { mul = 1; de = 1 - bestsegmentpos; dp = 1 + bestsegmentpos; }
+      if (c1 == 3 || c1 == 5 || c1 == 6) { mul = -1; c1 = 7 - c1; dp = 1 - bestsegmentpos; de = 1 + bestsegmentpos; }
+      if (c1 == 1) { ax = 0; ax1 = 1; ax2 = 2; }
+      if (c1 == 2) { ax = 1; ax1 = 2; ax2 = 0; }
+      if (c1 == 4) { ax = 2; ax1 = 0; ax2 = 1; }
+      if (axis[ax] * axis[ax] > 0.5) {     // second point along the edge of the box
+        secondpos = de;
+        e1 = 2 * size2[ax] / fabs(halfaxis[ax]);
+        if (e1 < secondpos) secondpos = e1;
+        secondpos *= mul;
+      } else {                             // second point along a face of the box
+        secondpos = dp;
+        e1 = 2 * size2[ax1] / fabs(halfaxis[ax1]);
+        if (e1 < secondpos) secondpos = e1;
+        e1 = 2 * size2[ax2] / fabs(halfaxis[ax2]);
+        if (e1 < secondpos) secondpos = e1;
+        secondpos *= -mul;
+      }
+    }
+  } else if (cltype >= 0 && cltype / 3 == 1) {   // closest to the inside of an edge
+    c1 = axisdir ^ clcorner;
+    c1 &= 7 - (1 << cledge);
+    if (c1 != 1 && c1 != 2 && c1 != 4) skip = true;   // T configuration: no second contact
+    else {
+      if (cledge == 0) { ax1 = 1; ax2 = 2; }
+      if (cledge == 1) { ax1 = 2; ax2 = 0; }
+      if (cledge == 2) { ax1 = 0; ax2 = 1; }
+      ax = cledge;
+      if (fabs(axis[ax1]) > fabs(axis[ax2])) ax1 = ax2;   // the face the capsule makes the lower angle with
+      ax2 = 3 - ax - ax1;
+      if (c1 & (1 << ax2)) { mul = 1; secondpos = 1 - bestsegmentpos; }
+      else { mul = -1; secondpos = 1 + bestsegmentpos; }
+      e1 = 2 * size2[ax2] / fabs(halfaxis[ax2]);
+      if (e1 < secondpos) secondpos = e1;
+      if (((axisdir & (1 << ax)) != 0) == ((c1 & (1 << ax2)) != 0)) e2 = 1 - bestboxpos;
+      else e2 = 1 + bestboxpos;
+      e1 = size2[ax] * e2 / fabs(halfaxis[ax]);
+      if (e1 < secondpos) secondpos = e1;
+      secondpos *= mul;
+    }
+  } else if (cltype < 0) {                 // an end of the capsule is closest to a face
+    if (clface == -1) skip = true;         // the closest point is inside the box
+    else {
+      mul = (cltype == -3) ? 1 : -1;
+      secondpos = 2;
+      for (int k = 0; k < 3; k++) { tmp1[k] = pos[k]; tmp1[k] += halfaxis[k] * (-mul); }
+      for (int i = 0; i < 3; i++) {
+        if (i == clface) continue;
+        e1 = (size2[i] - tmp1[i]) / halfaxis[i] * mul;
+        if (e1 > 0 && e1 < secondpos) secondpos = e1;
+        e1 = (-size2[i] - tmp1[i]) / halfaxis[i] * mul;
+        if (e1 > 0 && e1 < secondpos) secondpos = e1;
+      }
+      secondpos *= mul;
+    }
+  }
+  (void)skip;
+  // sphere at the first contact point, back in the world frame
+  for (int k = 0; k < 3; k++) { tmp1[k] = pos[k]; tmp1[k] += halfaxis[k] * bestsegmentpos; }
+  V3 w = mulmv(m2, V3{tmp1[0], tmp1[1], tmp1[2]});
+  w = w + p2;
+  int n = raw_sphere_box(c[0], margin, w, size1[0], p2, m2, size2);
+  if (secondpos > -3) {
+    for (int k = 0; k < 3; k++) { tmp1[k] = pos[k]; tmp1[k] += halfaxis[k] * (secondpos + bestsegmentpos); }
+    w = mulmv(m2, V3{tmp1[0], tmp1[1], tmp1[2]});
+    w = w + p2;
+    n += raw_sphere_box(c[n], margin, w, size1[0], p2, m2, size2);
+  }
+  return n;
+}
+
+// ---- box : box (engine_collision_box.c:592-1068): separating-axis test over the 15 candidate axes, then a face
+// manifold (the incident face clipped against the side planes of the reference face) or one edge-edge contact
+constexpr double kBoxSepEps = 1e-13, kBoxParEps = 1e-16, kBoxSgnEps = 1e-9, kBoxDupEps = 1e-14, kBoxEdgeBias = 1e-6;
+constexpr int kBoxMaxVert = 12;
+
+// clip polygon `cur` against sign * v[coord] <= limit (Sutherland-Hodgman, z interpolated); untouched when every
+// vertex is inside, otherwise written to `spare` and the buffers swap (engine_collision_box.c:655-697)
+MJB_HD int box_clip(int nin, double (*&cur)[3], double (*&spare)[3], int coord, double sign, double limit) {
+  double (*in)[3] = cur;
+  double dd[kBoxMaxVert];
+  bool all_inside = true;
+  for (int k = 0; k < nin; k++) { dd[k] = sign * in[k][coord] - limit; all_inside = all_inside && dd[k] <= 0; }
+  if (all_inside) return nin;
+  double (*out)[3] = spare;
+  int nout = 0;
+  for (int k = 0; k < nin; k++) {
+    const double* p = in[k];
+    const int k1 = (k + 1 == nin) ? 0 : k + 1;
+    const double dpv = dd[k], dq = dd[k1];
+    if (dpv <= 0 && nout < kBoxMaxVert) { out[nout][0] = p[0]; out[nout][1] = p[1]; out[nout][2] = p[2]; nout++; }
+    if (((dpv < 0 && dq > 0) || (dpv > 0 && dq < 0)) && nout < kBoxMaxVert) {
+      const double* q = in[k1];
+      const double t = dpv / (dpv - dq);
+      out[nout][0] = p[0] + t * (q[0] - p[0]);
+      out[nout][1] = p[1] + t * (q[1] - p[1]);
+      out[nout][2] = p[2] + t * (q[2] - p[2]);
+      nout++;
+    }
+  }
+  cur = out;
+  spare = in;
+  return nout;
+}
+
+MJB_HD int collide_box_box(PreCon* c, double margin, V3 p1, const M3& m1, const double* size1,
+                           V3 p2, const M3& m2, const double* size2) {
+  double rot[9], rotabs[9], pos21[3], pos12[3];
+  {
+    const V3 a = mulmTv3(m1, p2 - p1), b = mulmTv3(m2, p1 - p2);
+    pos21[0] = a.x; pos21[1] = a.y; pos21[2] = a.z;
+    pos12[0] = b.x; pos12[1] = b.y; pos12[2] = b.z;
+    for (int r = 0; r < 3; r++)        // rot = mat1' * mat2: the axes of box 2 in the frame of box 1
+      for (int q = 0; q < 3; q++) rot[3 * r + q] = m1.m[r] * m2.m[q] + m1.m[3 + r] * m2.m[3 + q] + m1.m[6 + r] * m2.m[6 + q];
+    for (int i = 0; i < 9; i++) rotabs[i] = fabs(rot[i]);
+  }
+  // ---- stage 1: separating-axis test
+  const double septol = margin + kBoxSepEps * (size1[0] + size1[1] + size1[2] + size2[0] + size2[1] + size2[2]);
+  double sep_best = -kMaxVal, sep_face;
+  int code = -1;
+  for (int i = 0; i < 3; i++) {
+    const double radius2 = rotabs[3 * i + 0] * size2[0] + rotabs[3 * i + 1] * size2[1] + rotabs[3 * i + 2] * size2[2];
+    const double sep = fabs(pos21[i]) - size1[i] - radius2;
+    if (sep > septol) return 0;
+    if (sep > sep_best) { sep_best = sep; code = i; }
+  }
+  for (int j = 0; j < 3; j++) {
+    const double radius1 = rotabs[0 + j] * size1[0] + rotabs[3 + j] * size1[1] + rotabs[6 + j] * size1[2];
+    const double sep = fabs(pos12[j]) - size2[j] - radius1;
+    if (sep > septol) return 0;
+    if (sep > sep_best) { sep_best = sep; code = 3 + j; }
+  }
+  sep_face = sep_best;
+  const int code_face = code;
+  for (int i = 0; i < 3; i++) {
+    for (int j = 0; j < 3; j++) {
+      const int i1 = (i + 1) % 3, i2 = (i + 2) % 3;
+      double ax1 = -rot[3 * i2 + j];
+      double ax2 = rot[3 * i1 + j];
+      const double norm2 = ax1 * ax1 + ax2 * ax2;
+      if (norm2 < kBoxParEps) continue;
+      const double inv = 1 / sqrt(norm2);
+      ax1 *= inv;
+      ax2 *= inv;
+      const double radius1 = size1[i1] * fabs(ax1) + size1[i2] * fabs(ax2);
+      const int j1 = (j + 1) % 3, j2 = (j + 2) % 3;
+      const double a2_1 = ax1 * rot[3 * i1 + j1] + ax2 * rot[3 * i2 + j1];
+      const double a2_2 = ax1 * rot[3 * i1 + j2] + ax2 * rot[3 * i2 + j2];
+      const double radius2 = size2[j1] * fabs(a2_1) + size2[j2] * fabs(a2_2);
+      const double sep = fabs(ax1 * pos21[i1] + ax2 * pos21[i2]) - radius1 - radius2;
+      if (sep > septol) return 0;
+      if (sep - kBoxEdgeBias * fabs(sep) > sep_best && sep > sep_face) { sep_best = sep; code = 6 + 3 * i + j; }
+    }
+  }
+  if (code < 0) return 0;
+  auto edge_axis = [&](int i, int j, double* axis) {   // unit cross product of e_i and column j of rot
+    const int i1 = (i + 1) % 3, i2 = (i + 2) % 3;
+    axis[i] = 0;
+    axis[i1] = -rot[3 * i2 + j];
+    axis[i2] = rot[3 * i1 + j];
+    V3 v{axis[0], axis[1], axis[2]};
+    normalize(v);
+    axis[0] = v.x; axis[1] = v.y; axis[2] = v.z;
+  };
+  if (code >= 6) {   // an edge axis nearly parallel to the best face axis gives way to the face
+    double axis[3];
+    edge_axis((code - 6) / 3, (code - 6) % 3, axis);
+    double face_dot;
+    if (code_face < 3) face_dot = fabs(axis[code_face]);
+    else {
+      const int f = code_face - 3;
+      face_dot = fabs(axis[0] * rot[0 + f] + axis[1] * rot[3 + f] + axis[2] * rot[6 + f]);
+    }
+    if (face_dot > 0.99 && sep_best < sep_face + 0.05 * fabs(sep_face) + kMinVal) { code = code_face; sep_best = sep_face; }
+  }
+  // ---- stage 2a: edge-edge contact
+  if (code >= 6) {
+    const int i = (code - 6) / 3, j = (code - 6) % 3;
+    const int i1 = (i + 1) % 3, i2 = (i + 2) % 3, j1 = (j + 1) % 3, j2 = (j + 2) % 3;
+    double axis[3];
+    edge_axis(i, j, axis);
+    if (axis[0] * pos21[0] + axis[1] * pos21[1] + axis[2] * pos21[2] < 0) { axis[0] = -axis[0]; axis[1] = -axis[1]; axis[2] = -axis[2]; }
+    const double a2[3] = {axis[0] * rot[0 + 0] + axis[1] * rot[3 + 0] + axis[2] * rot[6 + 0],
+                          axis[0] * rot[0 + 1] + axis[1] * rot[3 + 1] + axis[2] * rot[6 + 1],
+                          axis[0] * rot[0 + 2] + axis[1] * rot[3 + 2] + axis[2] * rot[6 + 2]};
+    int amb1 = -1, amb2 = -1;
+    if (fabs(axis[i1]) < kBoxSgnEps) amb1 = i1; else if (fabs(axis[i2]) < kBoxSgnEps) amb1 = i2;
+    if (fabs(a2[j1]) < kBoxSgnEps) amb2 = j1; else if (fabs(a2[j2]) < kBoxSgnEps) amb2 = j2;
+    const double d2[3] = {rot[0 + j], rot[3 + j], rot[6 + j]};
+    const double b = d2[i];
+    const double denom = 1 - b * b;
+    double w1[3] = {0, 0, 0}, w2[3] = {0, 0, 0};
+    double best_d2 = kMaxVal;
+    for (int v1 = 0; v1 < (amb1 >= 0 ? 2 : 1); v1++) {
+      for (int v2 = 0; v2 < (amb2 >= 0 ? 2 : 1); v2++) {
+        double c1[3], cc[3], c2[3], e[3];
+        c1[i] = 0;
+        c1[i1] = axis[i1] >= 0 ? size1[i1] : -size1[i1];
+        c1[i2] = axis[i2] >= 0 ? size1[i2] : -size1[i2];
+        if (amb1 >= 0 && v1) c1[amb1] = -c1[amb1];
+        cc[j] = 0;
+        cc[j1] = a2[j1] >= 0 ? -size2[j1] : size2[j1];
+        cc[j2] = a2[j2] >= 0 ? -size2[j2] : size2[j2];
+        if (amb2 >= 0 && v2) cc[amb2] = -cc[amb2];
+        for (int r = 0; r < 3; r++) c2[r] = rot[3 * r] * cc[0] + rot[3 * r + 1] * cc[1] + rot[3 * r + 2] * cc[2];
+        for (int r = 0; r < 3; r++) c2[r] += pos21[r];
+        for (int r = 0; r < 3; r++) e[r] = c2[r] - c1[r];
+        const double d1e = e[i];
+        const double d2e = d2[0] * e[0] + d2[1] * e[1] + d2[2] * e[2];
+        double sp = denom < kMinVal ? 0 : (d1e - b * d2e) / denom;
+        sp = dclip(sp, -size1[i], size1[i]);
+        const double t = dclip(b * sp - d2e, -size2[j], size2[j]);
+        sp = dclip(d1e + b * t, -size1[i], size1[i]);
+        double q1[3] = {c1[0], c1[1], c1[2]}, q2[3] = {c2[0], c2[1], c2[2]};
+        q1[i] += sp;
+        for (int r = 0; r < 3; r++) q2[r] += d2[r] * t;
+        const double g0 = q2[0] - q1[0], g1 = q2[1] - q1[1], g2 = q2[2] - q1[2];
+        const double gap2 = g0 * g0 + g1 * g1 + g2 * g2;
+        if (gap2 < best_d2) { best_d2 = gap2; for (int r = 0; r < 3; r++) { w1[r] = q1[r]; w2[r] = q2[r]; } }
+      }
+    }
+    const double dist = (w2[0] - w1[0]) * axis[0] + (w2[1] - w1[1]) * axis[1] + (w2[2] - w1[2]) * axis[2];
+    if (dist > septol) return 0;
+    const V3 mid{0.5 * (w1[0] + w2[0]), 0.5 * (w1[1] + w2[1]), 0.5 * (w1[2] + w2[2])};
+    c[0].dist = dist;
+    c[0].pos = mulmv(m1, mid) + p1;
+    c[0].normal = mulmv(m1, V3{axis[0], axis[1], axis[2]});
+    c[0].tangent = V3{0, 0, 0};
+    return 1;
+  }
+  // ---- stage 2b: face contact
+  const bool ref1 = code < 3;
+  const int a = ref1 ? code : code - 3;
+  const double* sizeref = ref1 ? size1 : size2;
+  const double* sizeinc = ref1 ? size2 : size1;
+  const V3 posref = ref1 ? p1 : p2;
+  const M3& matref = ref1 ? m1 : m2;
+  const double* posoi = ref1 ? pos21 : pos12;
+  double rinc[9];   // incident axes in the reference frame
+  if (ref1) { for (int k = 0; k < 9; k++) rinc[k] = rot[k]; }
+  else { for (int r = 0; r < 3; r++) for (int q = 0; q < 3; q++) rinc[3 * q + r] = rot[3 * r + q]; }
+  const double sgn = posoi[a] >= 0 ? 1 : -1;
+  int binc = 0;
+  for (int k = 1; k < 3; k++) if (fabs(rinc[3 * a + k]) > fabs(rinc[3 * a + binc])) binc = k;
+  const double tinc = sgn * rinc[3 * a + binc] > 0 ? -1 : 1;
+  const int ax = (a + 1) % 3, ay = (a + 2) % 3, bu = (binc + 1) % 3, bv = (binc + 2) % 3;
+  double poly[2][kBoxMaxVert][3];
+  double cx[3], du[3], dv[3];
+  for (int r = 0; r < 3; r++) {
+    const int cc = r == 0 ? ax : (r == 1 ? ay : a);
+    cx[r] = posoi[cc] + tinc * sizeinc[binc] * rinc[3 * cc + binc];
+    du[r] = sizeinc[bu] * rinc[3 * cc + bu];
+    dv[r] = sizeinc[bv] * rinc[3 * cc + bv];
+  }
+  cx[2] = sgn * cx[2] - sizeref[a];
+  du[2] *= sgn;
+  dv[2] *= sgn;
+  for (int k = 0; k < 4; k++) {
+    const double su = (k == 0 || k == 3) ? 1 : -1, sv = (k < 2) ? 1 : -1;
+    poly[0][k][0] = cx[0] + su * du[0] + sv * dv[0];
+    poly[0][k][1] = cx[1] + su * du[1] + sv * dv[1];
+    poly[0][k][2] = cx[2] + su * du[2] + sv * dv[2];
+  }
+  int nvert = 4;
+  double (*cur)[3] = poly[0];
+  double (*spare)[3] = poly[1];
+  nvert = box_clip(nvert, cur, spare, 0, 1, sizeref[ax]);
+  nvert = box_clip(nvert, cur, spare, 0, -1, sizeref[ax]);
+  nvert = box_clip(nvert, cur, spare, 1, 1, sizeref[ay]);
+  nvert = box_clip(nvert, cur, spare, 1, -1, sizeref[ay]);
+  double accepted[kBoxMaxVert][3];
+  int naccept = 0;
+  const double dupe2 = kBoxDupEps * (sizeref[ax] * sizeref[ax] + sizeref[ay] * sizeref[ay]);
+  for (int k = 0; k < nvert; k++) {
+    if (cur[k][2] > margin) continue;
+    bool dupe = false;
+    for (int q = 0; q < naccept; q++) {
+      const double dx = accepted[q][0] - cur[k][0], dy = accepted[q][1] - cur[k][1];
+      if (dx * dx + dy * dy < dupe2) { dupe = true; break; }
+    }
+    if (!dupe) { accepted[naccept][0] = cur[k][0]; accepted[naccept][1] = cur[k][1]; accepted[naccept][2] = cur[k][2]; naccept++; }
+  }
+  if (naccept == 0) return 0;
+  if (naccept > 8) naccept = 8;   // a quadrilateral clipped by four half-planes has at most eight vertices
+  const double nsign = ref1 ? sgn : -sgn;
+  const V3 normal{nsign * matref.m[3 * 0 + a], nsign * matref.m[3 * 1 + a], nsign * matref.m[3 * 2 + a]};
+  for (int k = 0; k < naccept; k++) {
+    const double* v = accepted[k];
+    double posc[3];
+    posc[ax] = v[0];
+    posc[ay] = v[1];
+    posc[a] = sgn * (sizeref[a] + 0.5 * v[2]);
+    c[k].dist = v[2];
+    c[k].pos = mulmv(matref, V3{posc[0], posc[1], posc[2]}) + posref;
+    c[k].normal = normal;
+    c[k].tangent = V3{0, 0, 0};
+  }
+  return naccept;
+}
+
 // filter + narrowphase of candidate pair p; returns the number of pre-contacts written to pc[]
 MJB_HD int pair_collide(const Env& d, int p, PreCon* pc) {
   const DModel& m = d.m;
@@ -307,6 +697,8 @@ MJB_HD int pair_collide(const Env& d, int p, PreCon* pc) {
     if (t1 == GEOM_PLANE && t2 == GEOM_BOX) return collide_plane_box(pc, margin, p1, m1, p2, m2, s2);
     if (t1 == GEOM_SPHERE && t2 == GEOM_CYLINDER) return collide_sphere_cylinder(pc, margin, p1, m1, s1, p2, m2, s2);
     if (t1 == GEOM_SPHERE && t2 == GEOM_BOX) return raw_sphere_box(pc[0], margin, p1, s1[0], p2, m2, s2);
+    if (t1 == GEOM_CAPSULE && t2 == GEOM_BOX) return collide_capsule_box(pc, margin, p1, m1, s1, p2, m2, s2);
+    if (t1 == GEOM_BOX && t2 == GEOM_BOX) return collide_box_box(pc, margin, p1, m1, s1, p2, m2, s2);
   }
   return 0;
 }

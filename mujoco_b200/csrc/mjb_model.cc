@@ -210,7 +210,7 @@ static double act_armature(const mjModel* m, bool tendon, int id) {
 static bool collider_boxfamily(int t1, int t2) {  // t1 <= t2
   auto is = [&](int a, int b) { return t1 == a && t2 == b; };
   return is(mjGEOM_PLANE, mjGEOM_CYLINDER) || is(mjGEOM_PLANE, mjGEOM_BOX) || is(mjGEOM_SPHERE, mjGEOM_CYLINDER) ||
-         is(mjGEOM_SPHERE, mjGEOM_BOX);
+         is(mjGEOM_SPHERE, mjGEOM_BOX) || is(mjGEOM_CAPSULE, mjGEOM_BOX) || is(mjGEOM_BOX, mjGEOM_BOX);
 }
 static bool collider_supported(int t1, int t2) {  // t1 <= t2
   auto is = [&](int a, int b) { return t1 == a && t2 == b; };

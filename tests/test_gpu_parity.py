@@ -533,3 +533,38 @@ def test_single_environment_symbols_gpu():
     print("mj_step through libmjb200.so: worst per-step rel err %.3e" % worst)
     assert worst < RTOL_TIGHT
     lib.mjb_forget_model(ours.m)
+
+
+@pytest.mark.parametrize("solver", SOLVERS)
+def test_box_and_cylinder_colliders_gpu(solver):
+    """plane-box, plane-cylinder, sphere-box, sphere-cylinder, capsule-box and box-box on the device
+    (models/boxes.xml: nine free bodies, constraint islands): contact lists exact, fields at 1e-9, rollout"""
+    assert available()
+    path = os.path.join(ROOT, "models", "boxes.mjb")
+    nenv, nstep = 16, 120
+    m, b, o = make_pair(path, solver, nenv=nenv, nconmax=96, njmax=400)
+    rng = np.random.default_rng(3)
+    o.reset()
+    s0 = np.tile(o.get_state(), (nenv, 1))
+    nq = o.size("nq")
+    for e in range(nenv):
+        for k in range(9):
+            s0[e, 1 + 7 * k + 2] += rng.uniform(-0.05, 0.3)
+            s0[e, 1 + 7 * k + 3:1 + 7 * k + 7] = rng.normal(size=4)
+        s0[e, 1 + nq:] = rng.normal(0, 1.5, o.size("nv"))
+    ctrl = np.zeros((nenv, nstep, 0))
+    out = b.rollout(s0, ctrl)
+    ref, stats, _ = o.rollout(s0, ctrl, nthread=os.cpu_count() or 1)
+    assert stats[:, 3].sum() == 0 and (b.warnings() == 0).all()
+    err = (np.abs(out - ref) / np.maximum(1.0, np.abs(ref).max(axis=(0, 1)))).max(axis=(0, 2))
+    print("boxes rollout rel err: step 30 %.3e, step %d %.3e" % (err[:30].max(), nstep, err.max()))
+    assert err[:30].max() < RTOL_TIGHT and err.max() < RTOL_TRAJ
+    types = set()
+    gt = o.mfield("geom_type")
+    for t in range(4, nstep, 12):
+        compare_forward(b, o, ref[:, t, :], np.zeros((nenv, 0)), rtol=RTOL_TIGHT, check_dual=(solver == mb.SOLVER_PGS))
+        g1, g2, nc = b.field("con_geom1"), b.field("con_geom2"), b.field("ncon")[:, 0]
+        for e in range(nenv):
+            for c in range(nc[e]):
+                types.add((int(gt[g1[e, c]]), int(gt[g2[e, c]])))
+    assert {(0, 5), (0, 6), (2, 6), (3, 6), (6, 6)} <= types, types

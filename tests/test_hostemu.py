@@ -704,9 +704,9 @@ def test_rollout_models_entry():
 
 @pytest.mark.parametrize("solver", [mb.SOLVER_NEWTON, mb.SOLVER_PGS])
 def test_box_and_cylinder_colliders_bit_exact(solver):
-    """plane-box, plane-cylinder, sphere-box, sphere-cylinder (engine_collision_primitive.c:101-258,345-423,
-    engine_collision_box.c:35-95) on models/boxes.xml: seven free bodies tumbling on a plane, contact lists and every
-    field compared bit for bit at several instants, and the whole rollout"""
+    """plane-box, plane-cylinder, sphere-box, sphere-cylinder, capsule-box, box-box (engine_collision_primitive.c:
+    101-258,345-423, engine_collision_box.c:35-1068) on models/boxes.xml: nine free bodies tumbling on a plane and on
+    each other, contact lists and every field compared bit for bit at several instants, and the whole rollout"""
     path = os.path.join(ROOT, "models", "boxes.mjb")
     nenv, nstep = 6, 150
     m, b, o = make_pair(path, solver, library=hostemu_lib(), nenv=nenv, nconmax=64, njmax=300)
@@ -715,7 +715,7 @@ def test_box_and_cylinder_colliders_bit_exact(solver):
     s0 = np.tile(o.get_state(), (nenv, 1))
     nq = o.size("nq")
     for e in range(nenv):
-        for k in range(7):                      # random heights, orientations and spins of the free bodies
+        for k in range(9):                      # random heights, orientations and spins of the free bodies
             s0[e, 1 + 7 * k + 2] += rng.uniform(-0.05, 0.3)
             s0[e, 1 + 7 * k + 3:1 + 7 * k + 7] = rng.normal(size=4)
         s0[e, 1 + nq:] = rng.normal(0, 1.5, o.size("nv"))
@@ -732,4 +732,4 @@ def test_box_and_cylinder_colliders_bit_exact(solver):
         for e in range(nenv):
             for c in range(nc[e]):
                 types.add((int(gt[g1[e, c]]), int(gt[g2[e, c]])))
-    assert {(0, 5), (0, 6), (2, 5), (2, 6)} <= types, types      # every new collider produced contacts
+    assert {(0, 5), (0, 6), (2, 5), (2, 6), (3, 6), (6, 6)} <= types, types      # every new collider produced contacts
