@@ -548,7 +548,7 @@ int mjb_set_field(mjbBatch* B, const char* name, const double* in) {
   X(qLDiagInv, nv) X(ten_length, ntendon) X(actuator_length, nu) X(ten_velocity, ntendon)                   \
   X(actuator_velocity, nu) X(cvel, 6 * nbody) X(cdof_dot, 6 * nv) X(qfrc_spring, nv) X(qfrc_damper, nv)     \
   X(qfrc_passive, nv) X(qfrc_bias, nv) X(actuator_force, nu) X(qfrc_actuator, nv) X(qfrc_smooth, nv)        \
-  X(qacc_smooth, nv) X(qfrc_constraint, nv) X(sensordata, nsensordata)                                     \
+  X(qacc_smooth, nv) X(qfrc_constraint, nv) X(sensordata, nsensordata) X(energy, 2)                                    \
   X(subtree_linvel, 3 * nbody * subtreevel) X(subtree_angmom, 3 * nbody * subtreevel)                       \
   X(cacc, 6 * nbody * rnepost) X(cfrc_int, 6 * nbody * rnepost) X(cfrc_ext, 6 * nbody * rnepost)
 

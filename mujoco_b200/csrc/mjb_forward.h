@@ -995,6 +995,74 @@ MJB_HD void subtree_vel(const Env& d) {
   MJB_PSYNC();
 }
 
+// potential and kinetic energy (mj_energyPos / mj_energyVel, engine_sensor.c:1659-1779): gravity and the joint /
+// tendon springs (serial sums in the reference's order, on lane 0), 0.5 qvel' M qvel.  Both depend on the position
+// and velocity stages only, so they are evaluated once, after the solve, whatever stage the reference uses.
+MJB_HD double poly_potential(double linear, const double* poly, double x) {   // mju_polyPotential, flg_odd = 0
+  double res = 0.5 * linear * (x * x);
+  double xpow = x;
+  for (int i = 0; i < kNPoly; i++) {
+    xpow *= x;
+    res += poly[i] / (i + 3) * (xpow * x);
+  }
+  return res;
+}
+MJB_HD void energy(const Env& d) {
+  const DModel& m = d.m;
+  if (!(d.feat & FEAT_SENSOR)) return;   // (models with energy flags or sensors run the full kernels)
+  FD en = d.energy();
+  if (!m.sz.epot) { MJB_LANE0 { en[0] = 0; if (!m.sz.ekin) en[1] = 0; } }
+  else {
+    MJB_LANE0 {
+      double e = 0;
+      if (!(m.opt.disableflags & DSBL_GRAVITY)) {
+        FD xi = d.xipos();
+        for (int i = 1; i < m.sz.nbody; i++)
+          e -= m.body_mass[i] * (m.opt.gravity[0] * xi[3 * i] + m.opt.gravity[1] * xi[3 * i + 1] + m.opt.gravity[2] * xi[3 * i + 2]);
+      }
+      if (!(m.opt.disableflags & DSBL_SPRING)) {
+        FD qpos = d.qpos();
+        for (int b = 1; b < m.sz.nbody; b++) {
+          for (int j = m.body_jntadr[b]; j < m.body_jntadr[b] + m.body_jntnum[b]; j++) {
+            const double k = m.jnt_stiffness[j];
+            const double* poly = m.jnt_stiffnesspoly + kNPoly * j;
+            bool zero = true;
+            for (int c = 0; c < kNPoly; c++) if (poly[c] != 0) zero = false;
+            if (k == 0 && zero) continue;
+            int padr = m.jnt_qposadr[j];
+            const int jt = m.jnt_type[j];
+            if (jt == JNT_FREE) {
+              const V3 dif = ld3(qpos, padr) - ldc3(m.qpos_spring, padr);
+              e += poly_potential(k, poly, sqrt(dif.x * dif.x + dif.y * dif.y + dif.z * dif.z));
+              padr += 3;
+            }
+            if (jt == JNT_FREE || jt == JNT_BALL) {
+              const V3 dif = qsub(ld4(qpos, padr), ldc4(m.qpos_spring, padr));
+              e += poly_potential(k, poly, sqrt(dif.x * dif.x + dif.y * dif.y + dif.z * dif.z));
+            } else {
+              e += poly_potential(k, poly, qpos[padr] - m.qpos_spring[padr]);
+            }
+          }
+        }
+        FD tl = d.ten_length();
+        for (int t = 0; t < m.sz.ntendon; t++) {
+          const double len = tl[t], lower = m.tendon_lengthspring[2 * t], upper = m.tendon_lengthspring[2 * t + 1];
+          const double x = (len > upper) ? len - upper : (len < lower) ? len - lower : 0;
+          e += poly_potential(m.tendon_stiffness[t], m.tendon_stiffnesspoly + kNPoly * t, x);
+        }
+      }
+      en[0] = e;
+    }
+  }
+  if (m.sz.ekin) {
+    FD vec = d.scr_nv(), qvel = d.qvel();
+    MJB_PSYNC();
+    mul_M(d, vec, qvel);
+    MJB_LANE0 en[1] = 0.5 * dot_ref(m.sz.nv, [&](int i) { return vec[i]; }, [&](int i) { return qvel[i]; });
+  }
+  MJB_PSYNC();
+}
+
 MJB_HD void sensors(const Env& d) {
   const DModel& m = d.m;
   if (!m.sz.nsensor || (m.opt.disableflags & DSBL_SENSOR)) return;
@@ -1072,6 +1140,8 @@ MJB_HD void sensors(const Env& d) {
         break;
       }
       case SENS_CLOCK: v[0] = d.time()[0]; break;
+      case SENS_E_POTENTIAL: v[0] = d.energy()[0]; break;
+      case SENS_E_KINETIC: v[0] = d.energy()[1]; break;
       case SENS_JOINTVEL: v[0] = d.qvel()[m.jnt_dofadr[id]]; break;
       case SENS_TENDONVEL: v[0] = d.ten_velocity()[id]; break;
       case SENS_ACTUATORVEL: v[0] = d.actuator_velocity()[id]; break;

@@ -176,7 +176,7 @@ bool split_step_available(const DModel& dm, const Batch& b) {
          (dm.opt.integrator == INT_EULER || dm.opt.integrator == INT_IMPLICITFAST);
 }
 int launch_split_step(const DModel& dm, const Batch& b, int first, int later, void* s, void* stagger) {
-  const bool lean = dm.sz.nsensor == 0 && dm.sz.neq == 0 && dm.sz.ntree == 1 && dm.opt.integrator != INT_IMPLICITFAST && !dm.sz.actfeat && !dm.sz.colbox && !b.xfrc;
+  const bool lean = dm.sz.nsensor == 0 && dm.sz.neq == 0 && dm.sz.ntree == 1 && dm.opt.integrator != INT_IMPLICITFAST && !dm.sz.actfeat && !dm.sz.colbox && !dm.sz.epot && !dm.sz.ekin && !b.xfrc;
   static const int part_lanes = [] { const char* e = getenv("MJB_PART_LANES"); return e ? atoi(e) : 16; }();   // measured (humanoid x4096): 16 lanes 1.357 ms/step, 32 lanes 1.385, 8 lanes 1.533
   if (lean && part_lanes == 16) launch_kpart1_lean16(dm, b, 0, first, s);
   else if (lean && part_lanes == 8) launch_kpart1_lean8(dm, b, 0, first, s);
@@ -201,7 +201,7 @@ int profile_split_step(const DModel& dm, const Batch& b, void* s, float* ms) {
   cudaStream_t st = (cudaStream_t)s;
   cudaEvent_t ev[5];
   for (auto& e : ev) CK(cudaEventCreate(&e), "event create");
-  const bool lean = dm.sz.nsensor == 0 && dm.sz.neq == 0 && dm.sz.ntree == 1 && dm.opt.integrator != INT_IMPLICITFAST && !dm.sz.actfeat && !dm.sz.colbox && !b.xfrc;
+  const bool lean = dm.sz.nsensor == 0 && dm.sz.neq == 0 && dm.sz.ntree == 1 && dm.opt.integrator != INT_IMPLICITFAST && !dm.sz.actfeat && !dm.sz.colbox && !dm.sz.epot && !dm.sz.ekin && !b.xfrc;
   static const int part_lanes = [] { const char* e = getenv("MJB_PART_LANES"); return e ? atoi(e) : 16; }();
   cudaEventRecord(ev[0], st);
   if (lean && part_lanes == 16) launch_kpart1_lean16(dm, b, 0, 1, s);
@@ -228,7 +228,7 @@ int profile_split_step(const DModel& dm, const Batch& b, void* s, float* ms) {
 int launch_stages(const DModel& dm, const Batch& b, int mask, int flags, void* s) {
   if (b.warp_per_env) {
     // lean kernels when the model needs none of the optional pipeline parts (FEAT_*)
-    const bool lean = dm.sz.nsensor == 0 && dm.sz.neq == 0 && dm.sz.ntree == 1 && dm.opt.integrator != INT_IMPLICITFAST && !dm.sz.actfeat && !dm.sz.colbox && !b.xfrc;
+    const bool lean = dm.sz.nsensor == 0 && dm.sz.neq == 0 && dm.sz.ntree == 1 && dm.opt.integrator != INT_IMPLICITFAST && !dm.sz.actfeat && !dm.sz.colbox && !dm.sz.epot && !dm.sz.ekin && !b.xfrc;
     if (b.nlane == 16) {
       if (dm.opt.solver == SOL_NEWTON) { if (lean) launch_kstep_newton16_lean(dm, b, mask, flags, s); else launch_kstep_newton16(dm, b, mask, flags, s); }
       else launch_kstep_any16(dm, b, mask, flags, s);

@@ -283,6 +283,8 @@ static bool sensor_code(const mjModel* m, int i, int* code, int* okind, int* rki
     case mjSENS_FRAMEQUAT: *code = SENS_FRAMEQUAT; frame = true; break;
     case mjSENS_SUBTREECOM: *code = SENS_SUBTREECOM; break;
     case mjSENS_CLOCK: *code = SENS_CLOCK; break;
+    case mjSENS_E_POTENTIAL: *code = SENS_E_POTENTIAL; break;
+    case mjSENS_E_KINETIC: *code = SENS_E_KINETIC; break;
     case mjSENS_JOINTVEL: *code = SENS_JOINTVEL; break;
     case mjSENS_TENDONVEL: *code = SENS_TENDONVEL; break;
     case mjSENS_ACTUATORVEL: *code = SENS_ACTUATORVEL; break;
@@ -359,8 +361,8 @@ int check_model(const mjModel* m) {
     }
   }
   if (m->opt.noslip_iterations > 0) FAIL("noslip solver");
-  if (m->opt.enableflags & (mjENBL_OVERRIDE | mjENBL_SLEEP | mjENBL_DIAGEXACT | mjENBL_ENERGY))
-    FAIL("enable flags override/sleep/diagexact/energy");
+  if (m->opt.enableflags & (mjENBL_OVERRIDE | mjENBL_SLEEP | mjENBL_DIAGEXACT))
+    FAIL("enable flags override/sleep/diagexact");
   if (m->opt.density != 0 || m->opt.viscosity != 0) {   // inertia-box fluid model only
     for (int i = 0; i < m->ngeom; i++) if (m->geom_fluid[mjNFLUID * i] > 0) FAIL("geom %d: ellipsoid fluid model", i);
     if (m->opt.integrator == mjINT_IMPLICITFAST) FAIL("fluid forces with implicitfast (velocity derivatives of the fluid forces)");
@@ -456,6 +458,11 @@ int build_host_model(const mjModel* m, int nconmax, int njmax, HostModel* out) {
   S.nsensor = m->nsensor; S.nsensordata = m->nsensordata; S.nsite = m->nsite; S.neq = m->neq;
   S.rnepost = 0;
   S.subtreevel = 0;
+  S.epot = S.ekin = (m->opt.enableflags & mjENBL_ENERGY) ? 1 : 0;
+  for (int i = 0; i < m->nsensor; i++) {
+    if (m->sensor_type[i] == mjSENS_E_POTENTIAL) S.epot = 1;
+    if (m->sensor_type[i] == mjSENS_E_KINETIC) S.ekin = 1;
+  }
   for (int i = 0; i < m->nsensor; i++)
     if (m->sensor_type[i] == mjSENS_SUBTREELINVEL || m->sensor_type[i] == mjSENS_SUBTREEANGMOM) S.subtreevel = 1;
   for (int i = 0; i < m->nsensor; i++) {

@@ -31,7 +31,7 @@ MJB_HD void run_stage_mask(const Env& d, int mask, int flags, int first_pass = 0
     if ((mask & 1) || redo) stage_position(d, (flags & 1) != 0 && !redo);
     if ((mask & 2) || redo) stage_velocity(d);
     if ((mask & 4) || redo) stage_solve(d);
-    if (mask & (8 | 16 | 32)) { stage_finish_forward(d); if ((d.feat & FEAT_SENSOR) && !(flags & 8)) sensors(d); }
+    if (mask & (8 | 16 | 32)) { stage_finish_forward(d); energy(d); if ((d.feat & FEAT_SENSOR) && !(flags & 8)) sensors(d); }
     if (!(mask & (8 | 32))) return;
     if (!redo) {
       check_vec(d, d.qacc(), d.m.sz.nv, WARN_BADQACC);
@@ -73,6 +73,7 @@ MJB_HD void run_part(const Env& d, int part, int flags) {
     return;
   }
   stage_finish_forward(d);
+  energy(d);
   if ((d.feat & FEAT_SENSOR) && !(flags & 8)) sensors(d);
   check_vec(d, d.qacc(), d.m.sz.nv, WARN_BADQACC);
   const int bad = d.scr_int()[0];

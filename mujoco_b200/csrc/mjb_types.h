@@ -40,7 +40,7 @@ enum { SENS_JOINTPOS, SENS_TENDONPOS, SENS_ACTUATORPOS, SENS_BALLQUAT, SENS_JOIN
        SENS_JOINTVEL, SENS_TENDONVEL, SENS_ACTUATORVEL, SENS_BALLANGVEL, SENS_JOINTLIMITVEL, SENS_TENDONLIMITVEL,
        SENS_FRAMELINVEL, SENS_FRAMEANGVEL, SENS_ACTUATORFRC, SENS_JOINTACTFRC, SENS_JOINTLIMITFRC,
        SENS_TENDONLIMITFRC, SENS_VELOCIMETER, SENS_GYRO, SENS_ACCELEROMETER, SENS_FORCE, SENS_TORQUE,
-       SENS_FRAMELINACC, SENS_FRAMEANGACC, SENS_SUBTREELINVEL, SENS_SUBTREEANGMOM, SENS_TOUCH };
+       SENS_FRAMELINACC, SENS_FRAMEANGACC, SENS_SUBTREELINVEL, SENS_SUBTREEANGMOM, SENS_TOUCH, SENS_E_POTENTIAL, SENS_E_KINETIC };
 enum { SOBJ_XBODY = 0, SOBJ_BODY = 1, SOBJ_GEOM = 2, SOBJ_SITE = 3 };   // frame sensor object kinds (mjOBJ_*)   // mjNISLAND: islands with solver statistics (mjdata.h)  // :553-561
 enum { SOL_PGS = 0, SOL_CG = 1, SOL_NEWTON = 2 };                                        // :202-204
 enum { INT_EULER = 0, INT_RK4 = 1, INT_IMPLICIT = 2, INT_IMPLICITFAST = 3 };             // :181-184
@@ -54,7 +54,8 @@ enum { DSBL_CONSTRAINT = 1 << 0, DSBL_EQUALITY = 1 << 1, DSBL_FRICTIONLOSS = 1 <
        DSBL_CONTACT = 1 << 4, DSBL_SPRING = 1 << 5, DSBL_DAMPER = 1 << 6, DSBL_GRAVITY = 1 << 7,
        DSBL_CLAMPCTRL = 1 << 8, DSBL_WARMSTART = 1 << 9, DSBL_FILTERPARENT = 1 << 10,
        DSBL_ACTUATION = 1 << 11, DSBL_REFSAFE = 1 << 12, DSBL_EULERDAMP = 1 << 15,
-       DSBL_AUTORESET = 1 << 16, DSBL_ISLAND = 1 << 18, DSBL_SENSOR = 1 << 13 };                                // :54-73
+       DSBL_AUTORESET = 1 << 16, DSBL_ISLAND = 1 << 18, DSBL_SENSOR = 1 << 13 };
+enum { ENBL_ENERGY = 1 << 1 };   // mjENBL_ENERGY (mjmodel.h mjtEnableBit)                                // :54-73
 enum { LIM_HINGE = 0, LIM_BALL = 1, LIM_TENDON = 2 };   // kinds of limit candidates (host-built table)
 constexpr int kNPoly = 2;   // mjNPOLY (include/mujoco/mjmodel.h:44)
 constexpr int kNGain = 9;   // leading gain/bias parameters kept (affine: 3, muscle: 9)
@@ -68,6 +69,7 @@ struct Sizes {
   int sitetrn;   // 1 when an actuator acts at a site (dense moment rows are allocated then)
   int fluid;     // 1 when the medium has density or viscosity (qfrc_fluid is allocated then)
   int gravcomp;  // 1 when a body has gravity compensation (qfrc_gravcomp is allocated then)
+  int epot, ekin;   // 1 when the potential / kinetic energy is computed (mjENBL_ENERGY or an energy sensor)
   int subtreevel;   // 1 when a sensor needs mj_subtreeVel (subtree_linvel / subtree_angmom are allocated then)
   int rnepost;   // 1 when a sensor needs mj_rnePostConstraint (cacc / cfrc_int / cfrc_ext are allocated then)
   int colbox;    // 1 when a candidate pair needs a cylinder / box collider (FEAT_COLBOX code paths)
@@ -147,7 +149,7 @@ struct DModel {
 // ---- batch data fields (per environment), sizes in elements -------------------------------------
 // HOT doubles: staged in shared memory by the fused warp-per-env kernel
 #define MJB_DATA_DBL_FIELDS(X, S)                                                            \
-  X(time, 1) X(qpos, S.nq) X(qvel, S.nv) X(act, S.na) X(act_dot, S.na) X(mocap_pos, 3 * S.nmocap) X(mocap_quat, 4 * S.nmocap) X(ctrl, S.nu) X(qacc_warmstart, S.nv)  \
+  X(time, 1) X(energy, 2) X(qpos, S.nq) X(qvel, S.nv) X(act, S.na) X(act_dot, S.na) X(mocap_pos, 3 * S.nmocap) X(mocap_quat, 4 * S.nmocap) X(ctrl, S.nu) X(qacc_warmstart, S.nv)  \
   X(qfrc_applied, S.nv) X(xfrc_applied, 6 * S.nbody) X(eq_active, S.neq)                                         \
   X(xpos, 3 * S.nbody) X(xquat, 4 * S.nbody) X(xmat, 9 * S.nbody) X(xipos, 3 * S.nbody)      \
   X(ximat, 9 * S.nbody) X(xanchor, 3 * S.njnt) X(xaxis, 3 * S.njnt)                          \

@@ -78,6 +78,7 @@ EXPORT int mjo_data_field(const mjModel* m, const mjData* d, const char* name, v
 #define X(T, n) if (!strcmp(name, #n)) { *ptr = (void*)&d->n; *type = TCODE(T); *nr = 1; *nc = 1; return 0; }
   MJDATA_SCALAR
 #undef X
+  if (!strcmp(name, "energy")) { *ptr = (void*)d->energy; *type = 'd'; *nr = 2; *nc = 1; return 0; }
   if (!strcmp(name, "solver_niter")) { *ptr = (void*)d->solver_niter; *type = 'i'; *nr = mjNISLAND; *nc = 1; return 0; }
   if (!strcmp(name, "warning_number")) {  /* gathered copy, valid until next call (not thread safe) */
     static int w[mjNWARNING];

@@ -206,18 +206,23 @@ def test_unsupported_models_are_refused():
         mb.Batch(m, 1)
 
 
-@pytest.mark.parametrize("model", ["humanoid", "ant_act", "ant_sensors"])
+@pytest.mark.parametrize("model", ["humanoid", "ant_act", "ant_sensors", "humanoid+energy"])
 def test_mjdata_bridge_matches_mj_step(model):
     """mjb_step_mjdata: the reference's per-mjData loop `for k: mj_step(m, d[k])` as one call.  Two sets
     of the reference's own mjData objects start identical; one is stepped by the reference engine, the other
     through the bridge; every fixed-size member the path computes must then be identical"""
     from oracle_util import Oracle
     nenv, nstep = 3, 25
-    path = os.path.join(ROOT, "models", model + ".mjb")
+    energy_flag = model.endswith("+energy")       # mjENBL_ENERGY: mj_energyPos / mj_energyVel every step
+    path = os.path.join(ROOT, "models", model.split("+")[0] + ".mjb")
     ref = [Oracle(path) for _ in range(nenv)]
     ours = [Oracle(path) for _ in range(nenv)]
     m = mb.Model(path, library=hostemu_lib())
     m.set_option("solver", mb.SOLVER_NEWTON)
+    if energy_flag:
+        m.set_option("enableflags", 2)
+        for o in ref + ours:
+            o.set_opt("enableflags", 2)
     b = mb.Batch(m, nenv, nconmax=64, njmax=200)
     states = perturbed_states(ref[0], nenv, seed=33, height=[0.3, 0.5, 0.9], qvel_std=0.4, qpos_std=0.1)
     rng = np.random.default_rng(34)
@@ -228,7 +233,7 @@ def test_mjdata_bridge_matches_mj_step(model):
             o.set_state(states[e])
     fields = ["qpos", "qvel", "qacc", "qacc_warmstart", "xpos", "xquat", "xmat", "xipos", "geom_xpos", "geom_xmat",
               "subtree_com", "cinert", "cdof", "crb", "M", "qLD", "qLDiagInv", "cvel", "cdof_dot", "qfrc_bias",
-              "qfrc_passive", "actuator_force", "qfrc_actuator", "qfrc_smooth", "qacc_smooth", "qfrc_constraint"]
+              "qfrc_passive", "actuator_force", "qfrc_actuator", "qfrc_smooth", "qacc_smooth", "qfrc_constraint", "energy"]
     if ref[0].size("na"):      # stateful actuators: act goes in and comes back, act_dot comes back
         fields += ["act", "act_dot", "actuator_length", "actuator_velocity"]
     if ref[0].size("nsensordata"):   # sensors, sites and the rnePostConstraint / subtreeVel outputs the sensors need
@@ -271,7 +276,7 @@ def test_sensors_bit_exact(solver, integrator):
     ctrl = np.random.default_rng(92).uniform(-1, 1, (nenv, nstep, oracles[0].size("nu")))
     out, sens = b.rollout(s0, ctrl, return_sensordata=True)
     ns = oracles[0].size("nsensordata")
-    assert sens.shape == (nenv, nstep, ns) and ns == 131
+    assert sens.shape == (nenv, nstep, ns) and ns == 133
     for e, o in enumerate(oracles):
         o.set_opt("solver", solver)
         o.set_opt("integrator", integrator)
