@@ -345,7 +345,10 @@ int check_model(const mjModel* m) {
       FAIL("sensor %d: type %d / object type %d is outside the supported set", i, (int)m->sensor_type[i], (int)m->sensor_objtype[i]);
     if (m->sensor_history[2 * i] > 0 || m->sensor_delay[i] > 0 || m->sensor_interval[2 * i] > 0) FAIL("sensor %d: history / delay / interval", i);
   }
-  if (m->npair) FAIL("predefined contact pairs (npair=%d)", (int)m->npair);
+  for (int i = 0; i < m->npair; i++) {
+    if (m->pair_solreffriction[mjNREF * i] || m->pair_solreffriction[mjNREF * i + 1]) FAIL("contact pair %d: solreffriction", i);
+    if (m->pair_adhesion[i] != 0) FAIL("contact pair %d: adhesion", i);
+  }
   if (m->nhistory) FAIL("history buffers / delays");
   if (m->flg_surfacevel) FAIL("geom surface velocity");
   if (m->opt.cone != mjCONE_PYRAMIDAL) FAIL("elliptic friction cones");
@@ -737,8 +740,37 @@ int build_host_model(const mjModel* m, int nconmax, int njmax, HostModel* out) {
   auto always = [&](int b) {
     return (b == 0 && m->body_geomnum[b] > 0) || (m->body_dofnum[m->body_weldid[b]] == 0 && has_plane(b));
   };
+  // predefined <pair>s (engine_collision_driver.c:651-662,820-826): merged into the body-pair walk by signature -
+  // a pair is tested before the first body pair whose signature is not smaller, the rest after the walk - with the
+  // pair's own parameters and none of the body / bitmask filters
+  int pairadr = 0;
+  auto push_predefined = [&](int k) -> int {
+    int x = m->pair_geom1[k], y = m->pair_geom2[k];
+    if (m->geom_type[x] > m->geom_type[y]) std::swap(x, y);
+    if (!collider_defined(m->geom_type[x], m->geom_type[y])) return 0;
+    if (!collider_supported(m->geom_type[x], m->geom_type[y])) {
+      char msg[160];
+      snprintf(msg, sizeof(msg), "unsupported: collider for geom types (%d,%d) (contact pair %d) is a 'next' row", m->geom_type[x], m->geom_type[y], k);
+      set_error(msg);
+      return -2;
+    }
+    if (collider_boxfamily(m->geom_type[x], m->geom_type[y])) S.colbox = 1;
+    pg1.push_back(x); pg2.push_back(y); pdim.push_back(m->pair_dim[k]);
+    pmargin.push_back(m->pair_margin[k] + m->pair_gap[k]); pinc.push_back(m->pair_margin[k]);
+    for (int c = 0; c < mjNREF; c++) psolref.push_back(m->pair_solref[mjNREF * k + c]);
+    for (int c = 0; c < mjNIMP; c++) psolimp.push_back(m->pair_solimp[mjNIMP * k + c]);
+    for (int c = 0; c < 5; c++) pfric.push_back(m->pair_friction[5 * k + c]);
+    return 0;
+  };
   for (int b1 = 0; contacts_on && b1 < m->nbody; b1++) {
     for (int b2 = b1 + 1; b2 < m->nbody; b2++) {
+      const unsigned sig0 = ((unsigned)b1 << 16) + (unsigned)b2;
+      const int startadr = pairadr;
+      bool merged = false;
+      for (; pairadr < m->npair && (unsigned)m->pair_signature[pairadr] <= sig0; pairadr++) {
+        merged = ((unsigned)m->pair_signature[pairadr] == sig0);
+        if (int rc = push_predefined(pairadr)) return rc;
+      }
       if (!can_collide(b1) || !can_collide(b2)) continue;
       // broadphase membership: SAP covers bodies >= 1; the world body only through always-collide
       if (b1 == 0 && !always(0)) continue;
@@ -764,6 +796,10 @@ int build_host_model(const mjModel* m, int nconmax, int njmax, HostModel* out) {
       for (int g1 = a1; g1 < a1 + n1; g1++)
         for (int g2 = a2; g2 < a2 + n2; g2++) {
           if (!(m->geom_contype[g1] & m->geom_conaffinity[g2]) && !(m->geom_contype[g2] & m->geom_conaffinity[g1])) continue;
+          bool predefined = false;   // the geom pair of a merged <pair> is not collided a second time
+          for (int k = startadr; merged && k < pairadr; k++)
+            if ((m->pair_geom1[k] == g1 && m->pair_geom2[k] == g2) || (m->pair_geom1[k] == g2 && m->pair_geom2[k] == g1)) predefined = true;
+          if (predefined) continue;
           int x = g1, y = g2;
           if (m->geom_type[x] > m->geom_type[y]) std::swap(x, y);
           if (!collider_defined(m->geom_type[x], m->geom_type[y])) continue;
@@ -799,6 +835,8 @@ int build_host_model(const mjModel* m, int nconmax, int njmax, HostModel* out) {
       }
     }
   }
+  for (; contacts_on && pairadr < m->npair; pairadr++)   // predefined pairs past the last body pair
+    if (int rc = push_predefined(pairadr)) return rc;
   S.npair = (int)pg1.size();
   B.addI(&D.pair_geom1, pg1.data(), pg1.size());
   B.addI(&D.pair_geom2, pg2.data(), pg2.size());

@@ -35,6 +35,7 @@ MODELS = {
     "ant_act": os.path.join(ROOT, "models", "ant_act.xml"),
     "ant_act_nomuscle": os.path.join(ROOT, "models", "ant_act_nomuscle.xml"),
     "boxes": os.path.join(ROOT, "models", "boxes.xml"),      # cylinder / box colliders
+    "ant_pairs": os.path.join(ROOT, "models", "ant_pairs.xml"),   # predefined contact pairs
 }
 
 

@@ -568,3 +568,27 @@ def test_box_and_cylinder_colliders_gpu(solver):
             for c in range(nc[e]):
                 types.add((int(gt[g1[e, c]]), int(gt[g2[e, c]])))
     assert {(0, 5), (0, 6), (2, 6), (3, 6), (6, 6)} <= types, types
+
+
+def test_predefined_pairs_and_energy_gpu():
+    """<contact><pair> overrides (models/ant_pairs.xml) and mjENBL_ENERGY on the device: contact lists exact, energy
+    and every field at 1e-9 against the reference engine"""
+    assert available()
+    path = os.path.join(ROOT, "models", "ant_pairs.mjb")
+    nenv, nstep = 12, 100
+    m, b, o = make_pair(path, mb.SOLVER_NEWTON, nenv=nenv, nconmax=48, njmax=200, enableflags=2)
+    s0 = perturbed_states(o, nenv, seed=14, height=[0.3, 0.45, 0.7], qvel_std=0.8, qpos_std=0.15)
+    ctrl = np.random.default_rng(15).uniform(-1, 1, (nenv, nstep, o.size("nu")))
+    out = b.rollout(s0, ctrl)
+    ref, stats, _ = o.rollout(s0, ctrl, nthread=os.cpu_count() or 1)
+    assert stats[:, 3].sum() == 0 and (b.warnings() == 0).all()
+    err = (np.abs(out - ref) / np.maximum(1.0, np.abs(ref).max(axis=(0, 1)))).max(axis=(0, 2))
+    print("pairs rollout rel err: step 30 %.3e, step 100 %.3e" % (err[:30].max(), err.max()))
+    assert err[:30].max() < RTOL_TIGHT and err.max() < RTOL_TRAJ
+    for t in (10, 50, 90):
+        compare_forward(b, o, ref[:, t, :], ctrl[:, t, :], rtol=RTOL_TIGHT, check_dual=False)
+        en = b.field("energy")
+        for e in range(nenv):
+            o.reset(); o.set_state(ref[e, t]); o.dfield("ctrl")[:] = ctrl[e, t]; o.forward()
+            r = np.array(o.dfield("energy"))
+            assert np.abs(en[e] - r).max() <= 1e-9 * max(1.0, np.abs(r).max()), (e, t, en[e], r)

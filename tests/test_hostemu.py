@@ -738,3 +738,26 @@ def test_box_and_cylinder_colliders_bit_exact(solver):
             for c in range(nc[e]):
                 types.add((int(gt[g1[e, c]]), int(gt[g2[e, c]])))
     assert {(0, 5), (0, 6), (2, 5), (2, 6), (3, 6), (6, 6)} <= types, types      # every new collider produced contacts
+
+
+@pytest.mark.parametrize("solver", [mb.SOLVER_NEWTON, mb.SOLVER_PGS])
+def test_predefined_contact_pairs_bit_exact(solver):
+    """<contact><pair> (engine_collision_driver.c:651-662,820-826,2046-2056): pairs merged by signature into the
+    body-pair walk, their own condim / friction / solref / solimp / margin, the duplicated dynamic pair dropped, a
+    pair the collision masks would not select - models/ant_pairs.xml"""
+    path = os.path.join(ROOT, "models", "ant_pairs.mjb")
+    nenv, nstep = 6, 120
+    m, b, o = make_pair(path, solver, library=hostemu_lib(), nenv=nenv, nconmax=48, njmax=200)
+    s0 = perturbed_states(o, nenv, seed=14, height=[0.3, 0.45, 0.7], qvel_std=0.8, qpos_std=0.15)
+    ctrl = np.random.default_rng(15).uniform(-1, 1, (nenv, nstep, o.size("nu")))
+    out = b.rollout(s0, ctrl)
+    ref, stats, _ = o.rollout(s0, ctrl, nthread=4)
+    assert stats[:, 3].sum() == 0 and (b.warnings() == 0).all()
+    assert np.array_equal(out, ref)
+    dims = set()
+    for t in range(4, nstep, 10):
+        compare_forward(b, o, ref[:, t, :], ctrl[:, t, :], rtol=0, exact=True, check_dual=(solver == mb.SOLVER_PGS))
+        nc, cd = b.field("ncon")[:, 0], b.field("con_dim")
+        for e in range(nenv):
+            dims |= set(int(x) for x in cd[e, :nc[e]])
+    assert {1, 3, 4} <= dims, dims      # the pairs' own condim values reached the contacts
