@@ -164,10 +164,30 @@ def test_constraint_islands_vs_oracle(solver):
     # bouncing bodies of this model then amplify.  Early steps are held tight, the 100-step window to the
     # north-star bound, and the solver itself is checked re-synchronised on oracle states below.
     assert err[:30].max() < RTOL_TIGHT
-    assert err[:100].max() < (RTOL_TIGHT if solver != mb.SOLVER_CG else 1e-4)
+    assert err[:100].max() < (RTOL_TIGHT if solver != mb.SOLVER_CG else RTOL_TRAJ)   # (CG measured: inside 1e-6 until step 126)
     for t in (40, 100, 149):
         compare_forward(b, o, ref[:, t, :], ctrl[:, t, :], rtol=RTOL_TIGHT, check_dual=(solver == mb.SOLVER_PGS))
     assert b.field("nisland")[:, 0].max() >= 3
+    # the free-running bound above is loose for CG only because of amplification: ONE step from the reference's own
+    # state (both sides re-synchronised, warm start cleared) stays at the tight bound at every sampled instant of the
+    # trajectory, so no single step - solver included - contributes more than 1e-9
+    worst = 0.0
+    for t in range(0, nstep - 1, 6):
+        b.set_state(ref[:, t, :])
+        b.set_field("qacc_warmstart", 0.0)
+        b.set_field("ctrl", ctrl[:, t + 1, :])
+        b.step(1)
+        got = b.get_state()
+        for e in range(nenv):
+            o.reset()
+            o.set_state(ref[e, t])
+            o.dfield("ctrl")[:] = ctrl[e, t + 1]
+            o.step()
+            r = o.get_state()
+            worst = max(worst, np.abs(got[e] - r).max() / max(1.0, np.abs(r).max()))
+    first = int(np.argmax(err > RTOL_TRAJ)) if (err > RTOL_TRAJ).any() else nstep
+    print("islands: worst single-step (re-synchronised) rel err %.3e; free-running trajectory inside 1e-6 until step %d" % (worst, first))
+    assert worst < RTOL_TIGHT
 
 
 def test_sensors_and_mjdata_bridge_vs_oracle():
