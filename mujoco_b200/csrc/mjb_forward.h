@@ -62,27 +62,111 @@ MJB_HD void check_vec(const Env& d, FD v, int n, int warn) {
   MJB_PSYNC();
 }
 
-// site transmissions without a reference site (engine_core_smooth.c:1573-1593): the 6D gear, expressed in
-// the world through the site frame, projected on the site's translational and rotational Jacobians
+// transmissions with a dense moment row (mj_transmission, engine_core_smooth.c):
+//   site without a reference site (:1573-1593): the 6D gear, expressed in the world through the site frame,
+//       projected on the site's translational and rotational Jacobians; length 0;
+//   site with a reference site (:1595-1700): gear in the reference site's frame, Jacobians relative to the
+//       reference site, the dofs of the common ancestral chain cleared; length = offset and orientation
+//       difference in the reference frame, dotted with the gear;
+//   slider-crank (:1396-1465): length a'v - sqrt((a'v)^2 + r^2 - v'v) of the rod between crank and slider sites,
+//       moment by the chain rule through the point and axis Jacobians.
 MJB_HD void site_moment(const Env& d) {
   const DModel& m = d.m;
   if (!(d.feat & FEAT_ACT) || !m.sz.sitetrn) return;
   const int nv = m.sz.nv;
-  FD row = d.actuator_momrow(), cdof = d.cdof();
+  FD row = d.actuator_momrow(), cdof = d.cdof(), len = d.actuator_length();
+  auto jacr = [&](int body, int r, int j) { return m.body_dofanc[(long)body * nv + j] ? cdof[6 * j + r] : 0.0; };
   for (int u = 0; u < m.sz.nu; u++) {
-    if (m.actuator_trntype[u] != TRN_SITE) continue;
+    const int tt = m.actuator_trntype[u];
+    if (tt < TRN_SITE) continue;
     const int sid = m.actuator_trnjnt[u], body = m.site_bodyid[sid];
     const double* gear = m.actuator_gear6 + 6 * u;
-    const M3 sm = ld9(d.site_xmat(), 9 * sid);
     const V3 sp = ld3(d.site_xpos(), 3 * sid);
-    const V3 wt = mulmv(sm, V3{gear[0], gear[1], gear[2]}), wr = mulmv(sm, V3{gear[3], gear[4], gear[5]});
-    const double w[6] = {wt.x, wt.y, wt.z, wr.x, wr.y, wr.z};
-    MJB_PFOR(j, nv) {
-      double m1 = 0, m2 = 0;   // mju_mulMatTVec skips rows whose wrench component is zero
-      const bool in = m.body_dofanc[(long)body * nv + j];
-      for (int r = 0; r < 3; r++) if (w[r]) m1 += jac_elem(d, sp, body, r, j) * w[r];
-      for (int r = 0; r < 3; r++) if (w[3 + r]) m2 += (in ? cdof[6 * j + r] : 0.0) * w[3 + r];
-      row[(long)u * nv + j] = m1 + m2;
+    if (tt == TRN_SITE) {
+      const M3 sm = ld9(d.site_xmat(), 9 * sid);
+      const V3 wt = mulmv(sm, V3{gear[0], gear[1], gear[2]}), wr = mulmv(sm, V3{gear[3], gear[4], gear[5]});
+      const double w[6] = {wt.x, wt.y, wt.z, wr.x, wr.y, wr.z};
+      MJB_PFOR(j, nv) {
+        double m1 = 0, m2 = 0;   // mju_mulMatTVec skips rows whose wrench component is zero
+        for (int r = 0; r < 3; r++) if (w[r]) m1 += jac_elem(d, sp, body, r, j) * w[r];
+        for (int r = 0; r < 3; r++) if (w[3 + r]) m2 += jacr(body, r, j) * w[3 + r];
+        row[(long)u * nv + j] = m1 + m2;
+      }
+    } else if (tt == TRN_SITEREF) {
+      const int rid = m.actuator_trnid2[u], rbody = m.site_bodyid[rid];
+      const M3 rm = ld9(d.site_xmat(), 9 * rid);
+      const V3 rp = ld3(d.site_xpos(), 3 * rid);
+      const bool tr = gear[0] != 0 || gear[1] != 0 || gear[2] != 0, ro = gear[3] != 0 || gear[4] != 0 || gear[5] != 0;
+      const V3 wt = mulmv(rm, V3{gear[0], gear[1], gear[2]}), wr = mulmv(rm, V3{gear[3], gear[4], gear[5]});
+      const double w[6] = {wt.x, wt.y, wt.z, wr.x, wr.y, wr.z};
+      MJB_LANE0 {
+        double l = 0;
+        if (tr) {
+          const V3 v = mulmTv3(rm, sp - rp);
+          l += v.x * gear[0] + v.y * gear[1] + v.z * gear[2];
+        }
+        if (ro) {   // site orientations from the parent bodies' quaternions, in the reference's (site, body) order
+          const Q4 q = qmul(ldc4(m.site_quat, 4 * sid), ld4(d.xquat(), 4 * body));
+          const Q4 rq = qmul(ldc4(m.site_quat, 4 * rid), ld4(d.xquat(), 4 * rbody));
+          const V3 v = qsub(q, rq);
+          l += v.x * gear[3] + v.y * gear[4] + v.z * gear[5];
+        }
+        len[u] = l;
+      }
+      const int* clr = m.actuator_refclear + (long)u * nv;
+      MJB_PFOR(j, nv) {
+        double mrow = 0;
+        if (tr) {
+          double m1 = 0;
+          for (int r = 0; r < 3; r++) {
+            const double jd = clr[j] ? 0.0 : jac_elem(d, sp, body, r, j) - jac_elem(d, rp, rbody, r, j);
+            if (w[r]) m1 += jd * w[r];
+          }
+          mrow = m1;
+        }
+        if (ro) {
+          double m2 = 0;
+          for (int r = 0; r < 3; r++) {
+            const double jd = clr[j] ? 0.0 : jacr(body, r, j) - jacr(rbody, r, j);
+            if (w[3 + r]) m2 += jd * w[3 + r];
+          }
+          mrow += m2;
+        }
+        row[(long)u * nv + j] = mrow;
+      }
+    } else {   // slider-crank
+      const int lid = m.actuator_trnid2[u], lbody = m.site_bodyid[lid];
+      const double rod = m.actuator_cranklength[u], g = gear[0];
+      const M3 lm = ld9(d.site_xmat(), 9 * lid);
+      const V3 lp = ld3(d.site_xpos(), 3 * lid);
+      const V3 axis{lm.m[2], lm.m[5], lm.m[8]};
+      const V3 vec = sp - lp;
+      const double av = dot(vec, axis);
+      const double det = av * av + rod * rod - dot(vec, vec);
+      double sdet = 0, l;
+      const bool ok = det > 0;
+      if (!ok) l = av; else { sdet = sqrt(det); l = av - sdet; }
+      V3 dlda, dldv;
+      if (ok) {
+        dldv = axis * (1 - av / sdet);
+        dlda = vec * (1 / sdet);
+        dldv = dldv + dlda;
+        dlda = vec * (1 - av / sdet);
+      } else { dlda = vec; dldv = axis; }
+      MJB_LANE0 len[u] = l * g;
+      const double da[3] = {dlda.x, dlda.y, dlda.z}, dv[3] = {dldv.x, dldv.y, dldv.z};
+      MJB_PFOR(j, nv) {
+        // axis Jacobian = rotational Jacobian of the slider's body crossed with the axis; point Jacobian of the crank
+        // site relative to the slider site
+        const double r0 = jacr(lbody, 0, j), r1 = jacr(lbody, 1, j), r2 = jacr(lbody, 2, j);
+        const double ja[3] = {r1 * axis.z - r2 * axis.y, r2 * axis.x - r0 * axis.z, r0 * axis.y - r1 * axis.x};
+        double mr = 0;
+        for (int k = 0; k < 3; k++) {
+          const double jk = jac_elem(d, sp, body, k, j) - jac_elem(d, lp, lbody, k, j);
+          mr += da[k] * ja[k] + dv[k] * jk;
+        }
+        row[(long)u * nv + j] = mr ? mr * g : 0.0;
+      }
     }
   }
   MJB_PSYNC();
@@ -239,7 +323,7 @@ MJB_HD void fwd_velocity(const Env& d) {
       const int t = m.actuator_trnjnt[i], adr = m.ten_J_rowadr[t], nnz = m.ten_J_rownnz[t];
       const double g = mom[i];
       av[i] = dot_sparse_ref(nnz, [&](int c) { return tJ[adr + c] * g; }, [&](int c) { return qvel[m.ten_J_colind[adr + c]]; });
-    } else if ((d.feat & FEAT_ACT) && m.actuator_trntype[i] == TRN_SITE) {   // sparse dot over the nonzero moments
+    } else if ((d.feat & FEAT_ACT) && m.actuator_trntype[i] >= TRN_SITE) {   // sparse dot over the nonzero moments
       FD row = d.actuator_momrow() + (long)i * m.sz.nv;
       int idx[64], nnz = 0;
       for (int c = 0; c < m.sz.nv; c++) if (row[c]) idx[nnz++] = c;
@@ -447,7 +531,7 @@ MJB_HD void fwd_actuation(const Env& d) {
         for (int c = 0; c < nnz; c++) qfa[m.ten_J_colind[adr + c]] += (tJ[adr + c] * mom[i]) * s;
         continue;
       }
-      if (stateful && m.actuator_trntype[i] == TRN_SITE) {
+      if (stateful && m.actuator_trntype[i] >= TRN_SITE) {
         FD row = d.actuator_momrow() + (long)i * nv;
         for (int c = 0; c < nv; c++) if (row[c]) qfa[c] += row[c] * s;
         continue;
@@ -623,7 +707,7 @@ MJB_HD void implicitfast_advance(const Env& d) {
             if (col == j) { Jj = tJ[ta + c] * mom[u]; hj = true; }
           }
           if (hi && hj) q += Jj * (Ji * aB[u]);
-        } else if ((d.feat & FEAT_ACT) && m.actuator_trntype[u] == TRN_SITE) {
+        } else if ((d.feat & FEAT_ACT) && m.actuator_trntype[u] >= TRN_SITE) {
           FD row = d.actuator_momrow() + (long)u * nv;
           if (row[i] && row[j]) q += row[j] * (row[i] * aB[u]);
         } else if ((d.feat & FEAT_ACT) && m.actuator_trntype[u] >= TRN_BALL) {   // moment row on the joint's 3 / 6 dofs

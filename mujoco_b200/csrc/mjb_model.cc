@@ -380,10 +380,9 @@ int check_model(const mjModel* m) {
   if (m->nout != m->nu || m->nactuator != m->nu) FAIL("multi-input/multi-output actuators");
   for (int i = 0; i < m->nactuator; i++) {
     int tt = m->actuator_trntype[i];
-    if (tt != mjTRN_JOINT && tt != mjTRN_JOINTINPARENT && tt != mjTRN_TENDON && tt != mjTRN_SITE) FAIL("actuator %d: transmission other than joint / tendon / site", i);
-    if (tt == mjTRN_SITE && m->actuator_trnid[2 * i + 1] >= 0) FAIL("actuator %d: site transmission with a reference site", i);
-    if (tt == mjTRN_SITE && (m->actuator_damping[i] != 0 || m->actuator_armature[i] != 0)) FAIL("actuator %d: actuator damping / armature on a site transmission", i);
-    if (tt != mjTRN_TENDON && tt != mjTRN_SITE) {
+    if (tt != mjTRN_JOINT && tt != mjTRN_JOINTINPARENT && tt != mjTRN_TENDON && tt != mjTRN_SITE && tt != mjTRN_SLIDERCRANK) FAIL("actuator %d: body (adhesion) transmission", i);
+    if ((tt == mjTRN_SITE || tt == mjTRN_SLIDERCRANK) && (m->actuator_damping[i] != 0 || m->actuator_armature[i] != 0)) FAIL("actuator %d: actuator damping / armature on a site / slider-crank transmission", i);
+    if (tt != mjTRN_TENDON && tt != mjTRN_SITE && tt != mjTRN_SLIDERCRANK) {
       int jt = m->jnt_type[m->actuator_trnid[2 * i]];
       if ((jt == mjJNT_BALL || jt == mjJNT_FREE) && (m->actuator_damping[i] != 0 || m->actuator_armature[i] != 0))
         FAIL("actuator %d: actuator damping / armature on a ball or free joint", i);
@@ -443,7 +442,7 @@ int build_host_model(const mjModel* m, int nconmax, int njmax, HostModel* out) {
   Sizes& S = D.sz;
   S.actfeat = 0;
   for (int i = 0; i < m->nu; i++)
-    if (m->actuator_dyntype[i] != mjDYN_NONE || m->actuator_trntype[i] == mjTRN_TENDON || m->actuator_trntype[i] == mjTRN_SITE ||
+    if (m->actuator_dyntype[i] != mjDYN_NONE || m->actuator_trntype[i] == mjTRN_TENDON || m->actuator_trntype[i] == mjTRN_SITE || m->actuator_trntype[i] == mjTRN_SLIDERCRANK ||
         ((m->actuator_trntype[i] == mjTRN_JOINT || m->actuator_trntype[i] == mjTRN_JOINTINPARENT) &&
          (m->jnt_type[m->actuator_trnid[2 * i]] == mjJNT_BALL || m->jnt_type[m->actuator_trnid[2 * i]] == mjJNT_FREE)) || m->actuator_gaintype[i] == mjGAIN_MUSCLE ||
         m->actuator_biastype[i] == mjBIAS_MUSCLE) S.actfeat = 1;
@@ -451,7 +450,7 @@ int build_host_model(const mjModel* m, int nconmax, int njmax, HostModel* out) {
   S.fluid = (m->opt.density != 0 || m->opt.viscosity != 0) ? 1 : 0;
   if (S.fluid) S.actfeat = 1;
   S.sitetrn = 0;
-  for (int i = 0; i < m->nu; i++) if (m->actuator_trntype[i] == mjTRN_SITE) S.sitetrn = 1;
+  for (int i = 0; i < m->nu; i++) if (m->actuator_trntype[i] == mjTRN_SITE || m->actuator_trntype[i] == mjTRN_SLIDERCRANK) S.sitetrn = 1;
   S.gravcomp = m->flg_gravcomp ? 1 : 0;
   S.colbox = 0;   // set while the candidate pairs are built
   if (S.gravcomp) S.actfeat = 1;
@@ -567,13 +566,36 @@ int build_host_model(const mjModel* m, int nconmax, int njmax, HostModel* out) {
   {
     std::vector<int> tt(m->nu), al(m->nu), ae(m->nu);
     for (int i = 0; i < m->nu; i++) {
-      tt[i] = (m->actuator_trntype[i] == mjTRN_TENDON) ? TRN_TENDON : (m->actuator_trntype[i] == mjTRN_SITE) ? TRN_SITE : TRN_JOINT;
+      tt[i] = (m->actuator_trntype[i] == mjTRN_TENDON) ? TRN_TENDON : (m->actuator_trntype[i] == mjTRN_SITE) ? (m->actuator_trnid[2 * i + 1] >= 0 ? TRN_SITEREF : TRN_SITE)
+              : (m->actuator_trntype[i] == mjTRN_SLIDERCRANK) ? TRN_SLIDERCRANK : TRN_JOINT;
       if (tt[i] == TRN_JOINT && m->jnt_type[m->actuator_trnid[2 * i]] == mjJNT_BALL) tt[i] = TRN_BALL;
       if (tt[i] == TRN_JOINT && m->jnt_type[m->actuator_trnid[2 * i]] == mjJNT_FREE) tt[i] = TRN_FREE;
       al[i] = m->actuator_actlimited[i];
       ae[i] = m->actuator_actearly[i];
     }
     B.addI(&D.actuator_trntype, tt.data(), m->nu);
+    {
+      // second transmission target (reference site / slider site) and, for reference-site transmissions, the dofs of
+      // the common ancestral chain of the two sites' bodies, whose Jacobian columns are cleared (:1606-1630)
+      std::vector<int> t2(m->nu), clr((size_t)m->nu * m->nv * (S.sitetrn ? 1 : 0) + 1, 0);
+      for (int i = 0; i < m->nu; i++) {
+        t2[i] = m->actuator_trnid[2 * i + 1];
+        if (tt[i] != TRN_SITEREF) continue;
+        const int b0 = m->body_weldid[m->site_bodyid[m->actuator_trnid[2 * i]]], b1 = m->body_weldid[m->site_bodyid[t2[i]]];
+        int d0 = m->body_dofadr[b0] + m->body_dofnum[b0] - 1, d1 = m->body_dofadr[b1] + m->body_dofnum[b1] - 1;
+        int common = -1;
+        if (d0 >= 0 && d1 >= 0) {
+          while (d0 != d1) {
+            if (d0 < d1) d1 = m->dof_parentid[d1]; else d0 = m->dof_parentid[d0];
+            if (d0 == -1 || d1 == -1) break;
+          }
+          if (d0 == d1) common = d0;
+        }
+        for (int da = common; da >= 0; da = m->dof_parentid[da]) clr[(size_t)i * m->nv + da] = 1;
+      }
+      B.addI(&D.actuator_trnid2, t2.data(), m->nu);
+      B.addI(&D.actuator_refclear, clr.data(), clr.size());
+    }
     B.addI(&D.actuator_dyntype, m->actuator_dyntype, m->nu);
     B.addI(&D.actuator_actadr, m->actuator_actadr, m->nu);
     B.addI(&D.actuator_actlimited, al.data(), m->nu);
@@ -684,6 +706,7 @@ int build_host_model(const mjModel* m, int nconmax, int njmax, HostModel* out) {
   B.addD(&D.actuator_lengthrange, m->actuator_lengthrange, 2 * m->nu);
   B.addD(&D.actuator_acc0, m->actuator_acc0, m->nu);
   B.addD(&D.actuator_gear6, m->actuator_gear, 6 * m->nu);
+  B.addD(&D.actuator_cranklength, m->actuator_cranklength, m->nu);
   {   // wrapPeriod (engine_forward.c:296-328): servo-shaped actuators on a ball joint take the setpoint nearest the length
     std::vector<double> wp(m->nu, 0.0);
     for (int i = 0; i < m->nu; i++) {

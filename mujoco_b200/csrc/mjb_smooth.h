@@ -263,7 +263,7 @@ MJB_HD void transmission(const Env& d) {
         m6[6 * i + 3] = ga.x; m6[6 * i + 4] = ga.y; m6[6 * i + 5] = ga.z;
       }
     }
-    else if (tt == TRN_SITE) len[i] = 0;   // moment row: site_moment(), after the site poses exist
+    else if (tt >= TRN_SITE) len[i] = 0;   // length and moment row: site_moment(), after the site poses exist
     else len[i] = qpos[m.jnt_qposadr[j]] * g;
     mom[i] = g;
   }

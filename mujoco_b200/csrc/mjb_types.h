@@ -49,7 +49,7 @@ enum { SAMEFRAME_NONE = 0, SAMEFRAME_BODY = 1, SAMEFRAME_INERTIA = 2, SAMEFRAME_
 enum { GAIN_FIXED = 0, GAIN_AFFINE = 1, GAIN_MUSCLE = 2 };                               // :256-258
 enum { BIAS_NONE = 0, BIAS_AFFINE = 1, BIAS_MUSCLE = 2 };                                // :267-269
 enum { DYN_NONE = 0, DYN_INTEGRATOR = 1, DYN_FILTER = 2, DYN_FILTEREXACT = 3, DYN_MUSCLE = 4 };   // :244-248
-enum { TRN_JOINT = 0, TRN_TENDON = 1, TRN_BALL = 2, TRN_FREE = 3, TRN_SITE = 4 };   // TRN_SITE: 6D gear at a site (no refsite);   // TRN_BALL / TRN_FREE: 3D / 6D gear on a ball / free joint;   // transmissions built (mjTRN_JOINT / JOINTINPARENT on scalar joints, mjTRN_TENDON)
+enum { TRN_JOINT = 0, TRN_TENDON = 1, TRN_BALL = 2, TRN_FREE = 3, TRN_SITE = 4, TRN_SITEREF = 5, TRN_SLIDERCRANK = 6 };   // >= TRN_SITE: dense moment row built by site_moment (site, site + reference site, slider-crank);   // TRN_SITE: 6D gear at a site (no refsite);   // TRN_BALL / TRN_FREE: 3D / 6D gear on a ball / free joint;   // transmissions built (mjTRN_JOINT / JOINTINPARENT on scalar joints, mjTRN_TENDON)
 enum { DSBL_CONSTRAINT = 1 << 0, DSBL_EQUALITY = 1 << 1, DSBL_FRICTIONLOSS = 1 << 2, DSBL_LIMIT = 1 << 3,
        DSBL_CONTACT = 1 << 4, DSBL_SPRING = 1 << 5, DSBL_DAMPER = 1 << 6, DSBL_GRAVITY = 1 << 7,
        DSBL_CLAMPCTRL = 1 << 8, DSBL_WARMSTART = 1 << 9, DSBL_FILTERPARENT = 1 << 10,
@@ -108,7 +108,7 @@ struct Options {
   X(ten_J_rownnz) X(ten_J_rowadr) X(ten_J_colind)                                            \
   X(actuator_trnjnt) X(actuator_gaintype) X(actuator_biastype) X(actuator_ctrllimited)       \
   X(actuator_forcelimited) X(actuator_trntype) X(actuator_dyntype) X(actuator_actadr)        \
-  X(actuator_actlimited) X(actuator_actearly) X(tendon_actfrclimited) X(body_mocapid) X(site_type) X(jnt_actgravcomp) X(actuator_inparent)        \
+  X(actuator_trnid2) X(actuator_refclear) X(actuator_actlimited) X(actuator_actearly) X(tendon_actfrclimited) X(body_mocapid) X(site_type) X(jnt_actgravcomp) X(actuator_inparent)        \
   X(pair_geom1) X(pair_geom2) X(pair_dim)                                                     \
   X(lvl_adr) X(lvl_body) X(child_adr) X(child_id)                                             \
   X(dlvl_adr) X(dlvl_dof) X(mt_adr) X(mt_dof) X(mt_qadr)                                      \
@@ -131,7 +131,7 @@ struct Options {
   X(tendon_dampingpoly_eff) X(tendon_lengthspring) X(tendon_armature_eff)                    \
   X(actuator_gear0) X(actuator_gainprm) X(actuator_biasprm) X(actuator_ctrlrange)            \
   X(actuator_forcerange) X(actuator_dynprm) X(actuator_actrange) X(actuator_lengthrange) X(actuator_acc0) \
-  X(site_size) X(body_gravcomp) X(actuator_gear6) X(actuator_wrapperiod) X(tendon_frictionloss) X(tendon_solref_fri) X(tendon_solimp_fri) X(tendon_actfrcrange)      \
+  X(site_size) X(body_gravcomp) X(actuator_gear6) X(actuator_cranklength) X(actuator_wrapperiod) X(tendon_frictionloss) X(tendon_solref_fri) X(tendon_solimp_fri) X(tendon_actfrcrange)      \
   X(pair_margin) X(pair_includemargin) X(pair_solref) X(pair_solimp) X(pair_friction) X(sensor_cutoff) X(site_pos) X(site_quat)            \
   X(eq_data) X(eq_solref) X(eq_solimp) X(tendon_length0)
 

@@ -36,6 +36,7 @@ MODELS = {
     "ant_act_nomuscle": os.path.join(ROOT, "models", "ant_act_nomuscle.xml"),
     "boxes": os.path.join(ROOT, "models", "boxes.xml"),      # cylinder / box colliders
     "ant_pairs": os.path.join(ROOT, "models", "ant_pairs.xml"),   # predefined contact pairs
+    "ant_trn": os.path.join(ROOT, "models", "ant_trn.xml"),       # site + reference site and slider-crank transmissions
 }
 
 

@@ -761,3 +761,25 @@ def test_predefined_contact_pairs_bit_exact(solver):
         for e in range(nenv):
             dims |= set(int(x) for x in cd[e, :nc[e]])
     assert {1, 3, 4} <= dims, dims      # the pairs' own condim values reached the contacts
+
+
+@pytest.mark.parametrize("solver", [mb.SOLVER_NEWTON, mb.SOLVER_PGS])
+def test_refsite_and_slidercrank_transmissions_bit_exact(solver):
+    """site transmissions with a reference site (translational / rotational gear, common ancestral dofs cleared) and
+    slider-crank transmissions (engine_core_smooth.c:1396-1465,1595-1700) - models/ant_trn.xml"""
+    path = os.path.join(ROOT, "models", "ant_trn.mjb")
+    nenv, nstep = 5, 100
+    m, b, o = make_pair(path, solver, library=hostemu_lib(), nenv=nenv)
+    s0 = perturbed_states(o, nenv, seed=14, height=[0.4, 0.55, 0.8], qvel_std=0.8, qpos_std=0.15)
+    ctrl = np.random.default_rng(15).uniform(-1, 1, (nenv, nstep, o.size("nu")))
+    compare_forward(b, o, s0, ctrl[:, 0], rtol=0, exact=True, check_dual=(solver == mb.SOLVER_PGS))
+    out = b.rollout(s0, ctrl)
+    ref, stats, _ = o.rollout(s0, ctrl, nthread=4)
+    assert stats[:, 3].sum() == 0 and (b.warnings() == 0).all()
+    assert np.array_equal(out, ref)
+    for t in (20, 60, 99):
+        compare_forward(b, o, ref[:, t, :], ctrl[:, t, :], rtol=0, exact=True, check_dual=(solver == mb.SOLVER_PGS))
+        for e in range(nenv):     # lengths of the new transmissions
+            o.reset(); o.set_state(ref[e, t]); o.dfield("ctrl")[:] = ctrl[e, t]; o.forward()
+            assert np.array_equal(b.field("actuator_length")[e], np.array(o.dfield("actuator_length")))
+            assert np.array_equal(b.field("actuator_velocity")[e], np.array(o.dfield("actuator_velocity")))
