@@ -949,6 +949,19 @@ MJB_HD double ray_sphere(V3 pos, double dist_sqr, V3 pnt, V3 vec) {
   const double c = dif.x * dif.x + dif.y * dif.y + dif.z * dif.z - dist_sqr;
   return ray_quad(a, b, c);
 }
+MJB_HD double ray_plane(V3 pos, const M3& mat, const double* size, V3 pnt, V3 vec) {   // engine_ray.c:204-238
+  const V3 dif = pnt - pos;
+  const double lp[3] = {mat.m[0] * dif.x + mat.m[3] * dif.y + mat.m[6] * dif.z, mat.m[1] * dif.x + mat.m[4] * dif.y + mat.m[7] * dif.z,
+                        mat.m[2] * dif.x + mat.m[5] * dif.y + mat.m[8] * dif.z};
+  const double lv[3] = {mat.m[0] * vec.x + mat.m[3] * vec.y + mat.m[6] * vec.z, mat.m[1] * vec.x + mat.m[4] * vec.y + mat.m[7] * vec.z,
+                        mat.m[2] * vec.x + mat.m[5] * vec.y + mat.m[8] * vec.z};
+  if (lv[2] > -kMinVal) return -1;          // not pointing at the front face
+  const double x = -lp[2] / lv[2];
+  if (x < 0) return -1;
+  const double p0 = lp[0] + x * lv[0], p1 = lp[1] + x * lv[1];
+  if ((size[0] <= 0 || fabs(p0) <= size[0]) && (size[1] <= 0 || fabs(p1) <= size[1])) return x;   // inside the rendered rectangle
+  return -1;
+}
 MJB_HD double ray_box(V3 pos, const M3& mat, const double* size, V3 pnt, V3 vec) {
   const double ssz = size[0] * size[0] + size[1] * size[1] + size[2] * size[2];
   if (ray_sphere(pos, ssz, pnt, vec) < 0) return -1;
@@ -1224,6 +1237,42 @@ MJB_HD void sensors(const Env& d) {
         break;
       }
       case SENS_CLOCK: v[0] = d.time()[0]; break;
+      case SENS_RANGEFINDER: {   // mj_ray (engine_ray.c:1308-1351) along the site's z axis, the site's own body excluded
+        const int spec = m.sensor_intprm0[i], bodyex = m.site_bodyid[id];
+        const M3 smat = ld9(d.site_xmat(), 9 * id);
+        const V3 org = ld3(d.site_xpos(), 3 * id), dir{smat.m[2], smat.m[5], smat.m[8]};
+        double dist = -1;
+        for (int g = 0; g < m.sz.ngeom; g++) {
+          if (m.geom_rayskip[g] || m.geom_bodyid[g] == bodyex) continue;
+          const V3 gp = ld3(d.geom_xpos(), 3 * g);
+          const M3 gm = ld9(d.geom_xmat(), 9 * g);
+          const double* gs = m.geom_size + 3 * g;
+          const int gt = m.geom_type[g];
+          const double nd = (gt == GEOM_PLANE) ? ray_plane(gp, gm, gs, org, dir) : (gt == GEOM_SPHERE) ? ray_sphere(gp, gs[0] * gs[0], org, dir)
+                          : (gt == GEOM_CAPSULE) ? ray_capsule(gp, gm, gs, org, dir) : (gt == GEOM_ELLIPSOID) ? ray_ellipsoid(gp, gm, gs, org, dir)
+                          : (gt == GEOM_CYLINDER) ? ray_cylinder(gp, gm, gs, org, dir) : ray_box(gp, gm, gs, org, dir);
+          if (nd >= 0 && (nd < dist || dist < 0)) dist = nd;
+        }
+        // fill_raydata (engine_sensor.c:470-520), then the cutoff of every field
+        double vv[11];
+        int n = 0;
+        const bool hit = dist >= 0;
+        if (spec & 1) vv[n++] = dist;
+        if (spec & 2) { vv[n++] = hit ? dir.x : 0; vv[n++] = hit ? dir.y : 0; vv[n++] = hit ? dir.z : 0; }
+        if (spec & 4) { vv[n++] = org.x; vv[n++] = org.y; vv[n++] = org.z; }
+        V3 pt{0, 0, 0};
+        if ((spec & (8 | 32)) && hit) pt = addscl(org, dir, dist);
+        if (spec & 8) { vv[n++] = pt.x; vv[n++] = pt.y; vv[n++] = pt.z; }
+        if (spec & 32) vv[n++] = hit ? dist : -1;
+        const int cmr = m.sensor_cutmode[i];
+        const double cutr = m.sensor_cutoff[i];
+        for (int k2 = 0; k2 < n && k2 < dim; k2++) {
+          double x = vv[k2];
+          if (cmr == 1) x = dclip(x, -cutr, cutr); else if (cmr == 2) x = dmin(cutr, x);
+          out[adr + k2] = x;
+        }
+        continue;
+      }
       case SENS_E_POTENTIAL: v[0] = d.energy()[0]; break;
       case SENS_E_KINETIC: v[0] = d.energy()[1]; break;
       case SENS_JOINTVEL: v[0] = d.qvel()[m.jnt_dofadr[id]]; break;

@@ -312,6 +312,18 @@ static bool sensor_code(const mjModel* m, int i, int* code, int* okind, int* rki
       return st == mjGEOM_SPHERE || st == mjGEOM_CAPSULE || st == mjGEOM_ELLIPSOID || st == mjGEOM_CYLINDER || st == mjGEOM_BOX;
     }
     case mjSENS_SUBTREEANGMOM: *code = SENS_SUBTREEANGMOM; break;
+    case mjSENS_RANGEFINDER: {   // site-attached ray along the site's z axis; every field of the data spec but the normal
+      *code = SENS_RANGEFINDER; *okind = SOBJ_SITE;
+      if (m->sensor_objtype[i] != mjOBJ_SITE) return false;            // (camera depth images are not built)
+      if (m->sensor_intprm[i * mjNSENS] & (1 << mjRAYDATA_NORMAL)) return false;
+      for (int g = 0; g < m->ngeom; g++) {   // every geom a ray can meet needs a closed-form ray test
+        const bool invisible = (m->geom_matid[g] < 0 && m->geom_rgba[4 * g + 3] == 0) ||
+                               (m->geom_matid[g] >= 0 && m->mat_rgba[4 * m->geom_matid[g] + 3] == 0);
+        const int t = m->geom_type[g];
+        if (!invisible && (t == mjGEOM_MESH || t == mjGEOM_HFIELD || t == mjGEOM_SDF)) return false;
+      }
+      return true;
+    }
     default: return false;
   }
   if (frame) {
@@ -528,6 +540,14 @@ int build_host_model(const mjModel* m, int nconmax, int njmax, HostModel* out) {
     B.addI(&D.sensor_reftype, rk.data(), m->nsensor);
     B.addI(&D.sensor_refid, rid.data(), m->nsensor);
     B.addI(&D.sensor_dim, m->sensor_dim, m->nsensor);
+    {
+      std::vector<int> ip(m->nsensor), skip(m->ngeom);
+      for (int i = 0; i < m->nsensor; i++) ip[i] = m->sensor_intprm[i * mjNSENS];
+      for (int g = 0; g < m->ngeom; g++)   // ray_eliminate (engine_ray.c:68-99) with flg_static = 1 and no geom groups
+        skip[g] = ((m->geom_matid[g] < 0 && m->geom_rgba[4 * g + 3] == 0) || (m->geom_matid[g] >= 0 && m->mat_rgba[4 * m->geom_matid[g] + 3] == 0)) ? 1 : 0;
+      B.addI(&D.sensor_intprm0, ip.data(), m->nsensor);
+      B.addI(&D.geom_rayskip, skip.data(), m->ngeom);
+    }
     B.addI(&D.sensor_adr, m->sensor_adr, m->nsensor);
     {
       std::vector<int> kind(m->neq), act(m->neq);
