@@ -1160,6 +1160,156 @@ MJB_HD void energy(const Env& d) {
   MJB_PSYNC();
 }
 
+// ---- contact sensor (engine_sensor.c:318-470,1027-1165) -------------------------------------------------------------
+// point inside a site volume (mju_insideGeom, engine_util_misc.c:452-496)
+MJB_HD bool inside_geom(V3 pos, const M3& mat, const double* size, int type, V3 point) {
+  const V3 vec = point - pos;
+  if (type == GEOM_SPHERE) return dot(vec, vec) < size[0] * size[0];
+  const V3 pl = mulmTv3(mat, vec);
+  if (type == GEOM_CAPSULE) {
+    const double zc = dclip(pl.z, -size[1], size[1]);
+    const double zd = (pl.z - zc) * (pl.z - zc);
+    return pl.x * pl.x + pl.y * pl.y + zd < size[0] * size[0];
+  }
+  if (type == GEOM_ELLIPSOID) return pl.x * pl.x / (size[0] * size[0]) + pl.y * pl.y / (size[1] * size[1]) + pl.z * pl.z / (size[2] * size[2]) < 1;
+  if (type == GEOM_CYLINDER) return fabs(pl.z) < size[1] && pl.x * pl.x + pl.y * pl.y < size[0] * size[0];
+  if (type == GEOM_BOX) return fabs(pl.x) < size[0] && fabs(pl.y) < size[1] && fabs(pl.z) < size[2];
+  return false;
+}
+// object kinds of a contact sensor: 0 none, 1 site, 2 geom, 3 body, 4 subtree (xbody)
+MJB_HD bool contact_check(const DModel& m, int body, int geom, int kind, int id) {
+  if (kind == 0 || kind == 1) return true;
+  if (kind == 2) return id == geom;
+  if (kind == 3) return id == body;
+  while (body > id) body = m.body_parentid[body];
+  return body == id;
+}
+// 0: no match, 1: match, -1: match with the contact frame flipped (matchContact)
+MJB_HD int contact_match(const Env& d, int con, int k1, int id1, int k2, int id2) {
+  const DModel& m = d.m;
+  if (k1 == 0 && k2 == 0) return 1;
+  if (k1 == 1 && !inside_geom(ld3(d.site_xpos(), 3 * id1), ld9(d.site_xmat(), 9 * id1), m.site_size + 3 * id1, m.site_type[id1], ld3(d.con_pos(), 3 * con))) return 0;
+  const int g1 = d.con_geom1()[con], g2 = d.con_geom2()[con], b1 = m.geom_bodyid[g1], b2 = m.geom_bodyid[g2];
+  const bool m11 = contact_check(m, b1, g1, k1, id1), m12 = contact_check(m, b2, g2, k1, id1);
+  const bool m21 = contact_check(m, b1, g1, k2, id2), m22 = contact_check(m, b2, g2, k2, id2);
+  if (!m11 && !m12) return 0;
+  if (!m21 && !m22) return 0;
+  if (k1 != 0 && k2 != 0) {
+    const bool regular = m11 && m22, reverse = m12 && m21;
+    if (regular && !reverse) return 1;
+    if (reverse && !regular) return -1;
+    if (regular && reverse) return 1;
+  } else if (k1 != 0) return m11 ? 1 : -1;
+  else if (k2 != 0) return m22 ? 1 : -1;
+  return 0;
+}
+// contact-frame force : torque of contact `con` (mj_contactForce, engine_core_util.c:1075-1095; pyramidal cones)
+MJB_HD void contact_wrench(const Env& d, int con, double* lf) {
+  for (int q = 0; q < 6; q++) lf[q] = 0;
+  const int a = d.con_efcadr()[con];
+  if (a < 0) return;
+  FD force = d.efc_force(), cfri = d.con_friction();
+  const int dim = d.con_dim()[con];
+  if (dim == 1) lf[0] = force[a];
+  else {
+    double n = 0;
+    for (int q = 0; q < 2 * (dim - 1); q++) n += force[a + q];
+    lf[0] = n;
+    for (int q = 0; q < dim - 1; q++) lf[q + 1] = (force[a + 2 * q] - force[a + 2 * q + 1]) * cfri[5 * con + q];
+  }
+  lf[0] -= 0.0;   // adhesion (refused by the model check: zero)
+}
+MJB_HD void contact_sensor(const Env& d, int i, FD out) {
+  const DModel& m = d.m;
+  const int spec = m.sensor_intprm0[i], reduce = m.sensor_intprm1[i], dim = m.sensor_dim[i], adr = m.sensor_adr[i];
+  const int k1 = m.sensor_objraw[i], id1 = m.sensor_objid[i], k2 = m.sensor_refraw[i], id2 = m.sensor_refid[i];
+  const int fsz[7] = {1, 3, 3, 1, 3, 3, 3};   // found, force, torque, dist, pos, normal, tangent
+  int off[7], size = 0;
+  for (int f = 0; f < 7; f++) { off[f] = (spec & (1 << f)) ? size : -1; if (spec & (1 << f)) size += fsz[f]; }
+  const int num = size ? dim / size : 0, ncon = d.ncon()[0];
+  for (int c = 0; c < dim; c++) out[adr + c] = 0;
+  int nmatch = 0;
+  for (int j = 0; j < ncon; j++) if (contact_match(d, j, k1, id1, k2, id2)) nmatch++;
+  auto criterion = [&](int j) {
+    if (reduce == 1) return d.con_dist()[j];
+    double lf[6];
+    contact_wrench(d, j, lf);
+    return -(lf[0] * lf[0] + lf[1] * lf[1] + lf[2] * lf[2]);
+  };
+  auto fill = [&](int slot, int j, bool flip) {   // copySensorData
+    const long base = adr + (long)slot * size;
+    if (off[0] >= 0) out[base + off[0]] = nmatch;
+    if (off[1] >= 0 || off[2] >= 0) {
+      double lf[6];
+      contact_wrench(d, j, lf);
+      if (off[1] >= 0) { out[base + off[1]] = lf[0]; out[base + off[1] + 1] = lf[1]; out[base + off[1] + 2] = flip ? lf[2] * -1 : lf[2]; }
+      if (off[2] >= 0) { out[base + off[2]] = lf[3]; out[base + off[2] + 1] = lf[4]; out[base + off[2] + 2] = flip ? lf[5] * -1 : lf[5]; }
+    }
+    if (off[3] >= 0) out[base + off[3]] = d.con_dist()[j];
+    if (off[4] >= 0) for (int c = 0; c < 3; c++) out[base + off[4] + c] = d.con_pos()[3 * j + c];
+    if (off[5] >= 0) for (int c = 0; c < 3; c++) out[base + off[5] + c] = flip ? d.con_frame()[9 * j + c] * -1 : d.con_frame()[9 * j + c];
+    if (off[6] >= 0) for (int c = 0; c < 3; c++) out[base + off[6] + c] = flip ? d.con_frame()[9 * j + 3 + c] * -1 : d.con_frame()[9 * j + 3 + c];
+  };
+  const int nslot = num < nmatch ? num : nmatch;
+  if (reduce == 0) {          // first matches in contact order
+    int slot = 0;
+    for (int j = 0; j < ncon && slot < nslot; j++) {
+      const int mj = contact_match(d, j, k1, id1, k2, id2);
+      if (mj) fill(slot++, j, mj < 0);
+    }
+  } else if (reduce == 1 || reduce == 2) {   // the nslot smallest by (criterion, contact id), ascending (ContactSelect)
+    double lastc = 0;
+    int lastj = -1;
+    for (int slot = 0; slot < nslot; slot++) {
+      int best = -1;
+      double bestc = 0;
+      for (int j = 0; j < ncon; j++) {
+        if (!contact_match(d, j, k1, id1, k2, id2)) continue;
+        const double cj = criterion(j);
+        if (lastj >= 0 && (cj < lastc || (cj == lastc && j <= lastj))) continue;   // already emitted
+        if (best < 0 || cj < bestc || (cj == bestc && j < best)) { best = j; bestc = cj; }
+      }
+      if (best < 0) break;
+      fill(slot, best, contact_match(d, best, k1, id1, k2, id2) < 0);
+      lastc = bestc; lastj = best;
+    }
+  } else {                    // net force about the force-weighted centroid, global frame
+    V3 point{0, 0, 0};
+    double total = 0;
+    for (int j = 0; j < ncon; j++) {
+      const int mj = contact_match(d, j, k1, id1, k2, id2);
+      if (!mj) continue;
+      double lf[6];
+      contact_wrench(d, j, lf);
+      if (mj < 0) for (int q = 0; q < 6; q++) lf[q] = lf[q] * -1;
+      const double w = sqrt(lf[0] * lf[0] + lf[1] * lf[1] + lf[2] * lf[2]);
+      point.x += d.con_pos()[3 * j] * w; point.y += d.con_pos()[3 * j + 1] * w; point.z += d.con_pos()[3 * j + 2] * w;
+      total += w;
+    }
+    point = point * (1.0 / (total > kMinVal ? total : kMinVal));
+    V3 force{0, 0, 0}, torque{0, 0, 0};
+    for (int j = 0; j < ncon; j++) {
+      const int mj = contact_match(d, j, k1, id1, k2, id2);
+      if (!mj) continue;
+      double lf[6];
+      contact_wrench(d, j, lf);
+      if (mj < 0) for (int q = 0; q < 6; q++) lf[q] = lf[q] * -1;
+      const M3 fr = ld9(d.con_frame(), 9 * j);
+      const V3 fj = mulmTv3(fr, V3{lf[0], lf[1], lf[2]}), tj = mulmTv3(fr, V3{lf[3], lf[4], lf[5]});
+      force = force + fj;
+      torque = torque + tj;
+      torque = torque + cross(ld3(d.con_pos(), 3 * j) - point, fj);
+    }
+    if (off[0] >= 0) out[adr + off[0]] = nmatch;
+    if (off[1] >= 0) { out[adr + off[1]] = force.x; out[adr + off[1] + 1] = force.y; out[adr + off[1] + 2] = force.z; }
+    if (off[2] >= 0) { out[adr + off[2]] = torque.x; out[adr + off[2] + 1] = torque.y; out[adr + off[2] + 2] = torque.z; }
+    if (off[3] >= 0) out[adr + off[3]] = 0;
+    if (off[4] >= 0) { out[adr + off[4]] = point.x; out[adr + off[4] + 1] = point.y; out[adr + off[4] + 2] = point.z; }
+    if (off[5] >= 0) out[adr + off[5]] = 1;
+    if (off[6] >= 0) out[adr + off[6] + 1] = 1;
+  }
+}
+
 MJB_HD void sensors(const Env& d) {
   const DModel& m = d.m;
   if (!m.sz.nsensor || (m.opt.disableflags & DSBL_SENSOR)) return;
@@ -1237,6 +1387,7 @@ MJB_HD void sensors(const Env& d) {
         break;
       }
       case SENS_CLOCK: v[0] = d.time()[0]; break;
+      case SENS_CONTACT: contact_sensor(d, i, out); continue;
       case SENS_RANGEFINDER: {   // mj_ray (engine_ray.c:1308-1351) along the site's z axis, the site's own body excluded
         const int spec = m.sensor_intprm0[i], bodyex = m.site_bodyid[id];
         const M3 smat = ld9(d.site_xmat(), 9 * id);

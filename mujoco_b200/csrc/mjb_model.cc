@@ -312,6 +312,15 @@ static bool sensor_code(const mjModel* m, int i, int* code, int* okind, int* rki
       return st == mjGEOM_SPHERE || st == mjGEOM_CAPSULE || st == mjGEOM_ELLIPSOID || st == mjGEOM_CYLINDER || st == mjGEOM_BOX;
     }
     case mjSENS_SUBTREEANGMOM: *code = SENS_SUBTREEANGMOM; break;
+    case mjSENS_CONTACT: {   // contacts selected by object / reference criteria (site volume, geom, body, subtree), reduced
+      *code = SENS_CONTACT;
+      auto okc = [&](int t, int id) {
+        if (t == mjOBJ_UNKNOWN || t == mjOBJ_GEOM || t == mjOBJ_BODY || t == mjOBJ_XBODY) return true;
+        if (t == mjOBJ_SITE) { const int st = m->site_type[id]; return st == mjGEOM_SPHERE || st == mjGEOM_CAPSULE || st == mjGEOM_ELLIPSOID || st == mjGEOM_CYLINDER || st == mjGEOM_BOX; }
+        return false;
+      };
+      return okc(m->sensor_objtype[i], m->sensor_objid[i]) && okc(m->sensor_reftype[i], m->sensor_refid[i]) && m->sensor_reftype[i] != mjOBJ_SITE;
+    }
     case mjSENS_RANGEFINDER: {   // site-attached ray along the site's z axis; every field of the data spec but the normal
       *code = SENS_RANGEFINDER; *okind = SOBJ_SITE;
       if (m->sensor_objtype[i] != mjOBJ_SITE) return false;            // (camera depth images are not built)
@@ -541,8 +550,16 @@ int build_host_model(const mjModel* m, int nconmax, int njmax, HostModel* out) {
     B.addI(&D.sensor_refid, rid.data(), m->nsensor);
     B.addI(&D.sensor_dim, m->sensor_dim, m->nsensor);
     {
-      std::vector<int> ip(m->nsensor), skip(m->ngeom);
-      for (int i = 0; i < m->nsensor; i++) ip[i] = m->sensor_intprm[i * mjNSENS];
+      std::vector<int> ip(m->nsensor), ip1(m->nsensor), skip(m->ngeom), oraw(m->nsensor), rraw(m->nsensor);
+      for (int i = 0; i < m->nsensor; i++) {
+        ip[i] = m->sensor_intprm[i * mjNSENS]; ip1[i] = m->sensor_intprm[i * mjNSENS + 1];
+        // contact sensors match on the reference's own object kinds: 0 none, 1 site, 2 geom, 3 body, 4 xbody (subtree)
+        auto raw = [](int t) { return t == mjOBJ_SITE ? 1 : t == mjOBJ_GEOM ? 2 : t == mjOBJ_BODY ? 3 : t == mjOBJ_XBODY ? 4 : 0; };
+        oraw[i] = raw(m->sensor_objtype[i]); rraw[i] = raw(m->sensor_reftype[i]);
+      }
+      B.addI(&D.sensor_intprm1, ip1.data(), m->nsensor);
+      B.addI(&D.sensor_objraw, oraw.data(), m->nsensor);
+      B.addI(&D.sensor_refraw, rraw.data(), m->nsensor);
       for (int g = 0; g < m->ngeom; g++)   // ray_eliminate (engine_ray.c:68-99) with flg_static = 1 and no geom groups
         skip[g] = ((m->geom_matid[g] < 0 && m->geom_rgba[4 * g + 3] == 0) || (m->geom_matid[g] >= 0 && m->mat_rgba[4 * m->geom_matid[g] + 3] == 0)) ? 1 : 0;
       B.addI(&D.sensor_intprm0, ip.data(), m->nsensor);

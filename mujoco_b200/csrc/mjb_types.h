@@ -40,7 +40,7 @@ enum { SENS_JOINTPOS, SENS_TENDONPOS, SENS_ACTUATORPOS, SENS_BALLQUAT, SENS_JOIN
        SENS_JOINTVEL, SENS_TENDONVEL, SENS_ACTUATORVEL, SENS_BALLANGVEL, SENS_JOINTLIMITVEL, SENS_TENDONLIMITVEL,
        SENS_FRAMELINVEL, SENS_FRAMEANGVEL, SENS_ACTUATORFRC, SENS_JOINTACTFRC, SENS_JOINTLIMITFRC,
        SENS_TENDONLIMITFRC, SENS_VELOCIMETER, SENS_GYRO, SENS_ACCELEROMETER, SENS_FORCE, SENS_TORQUE,
-       SENS_FRAMELINACC, SENS_FRAMEANGACC, SENS_SUBTREELINVEL, SENS_SUBTREEANGMOM, SENS_TOUCH, SENS_E_POTENTIAL, SENS_E_KINETIC, SENS_RANGEFINDER };
+       SENS_FRAMELINACC, SENS_FRAMEANGACC, SENS_SUBTREELINVEL, SENS_SUBTREEANGMOM, SENS_TOUCH, SENS_E_POTENTIAL, SENS_E_KINETIC, SENS_RANGEFINDER, SENS_CONTACT };
 enum { SOBJ_XBODY = 0, SOBJ_BODY = 1, SOBJ_GEOM = 2, SOBJ_SITE = 3 };   // frame sensor object kinds (mjOBJ_*)   // mjNISLAND: islands with solver statistics (mjdata.h)  // :553-561
 enum { SOL_PGS = 0, SOL_CG = 1, SOL_NEWTON = 2 };                                        // :202-204
 enum { INT_EULER = 0, INT_RK4 = 1, INT_IMPLICIT = 2, INT_IMPLICITFAST = 3 };             // :181-184
@@ -115,7 +115,7 @@ struct Options {
   X(fac_adr) X(fac_dst) X(fac_src) X(fac_cf)                                                  \
   X(lim_kind) X(lim_id) X(lim_side) X(fl_dof) X(body_dofanc)                                 \
   X(sensor_type) X(sensor_cutmode) X(sensor_objtype) X(sensor_objid) X(sensor_reftype) X(sensor_refid)   \
-  X(sensor_dim) X(sensor_adr) X(sensor_intprm0) X(geom_rayskip) X(site_bodyid) X(site_sameframe)                               \
+  X(sensor_dim) X(sensor_adr) X(sensor_intprm0) X(sensor_intprm1) X(sensor_objraw) X(sensor_refraw) X(geom_rayskip) X(site_bodyid) X(site_sameframe)                               \
   X(eq_kind) X(eq_obj1id) X(eq_obj2id) X(eq_active0)
 
 #define MJB_MODEL_DBL_FIELDS(X)                                                             \

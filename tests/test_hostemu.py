@@ -276,7 +276,7 @@ def test_sensors_bit_exact(solver, integrator):
     ctrl = np.random.default_rng(92).uniform(-1, 1, (nenv, nstep, oracles[0].size("nu")))
     out, sens = b.rollout(s0, ctrl, return_sensordata=True)
     ns = oracles[0].size("nsensordata")
-    assert sens.shape == (nenv, nstep, ns) and ns == 146
+    assert sens.shape == (nenv, nstep, ns) and ns == 271
     for e, o in enumerate(oracles):
         o.set_opt("solver", solver)
         o.set_opt("integrator", integrator)
