@@ -612,3 +612,25 @@ def test_predefined_pairs_and_energy_gpu():
             o.reset(); o.set_state(ref[e, t]); o.dfield("ctrl")[:] = ctrl[e, t]; o.forward()
             r = np.array(o.dfield("energy"))
             assert np.abs(en[e] - r).max() <= 1e-9 * max(1.0, np.abs(r).max()), (e, t, en[e], r)
+
+
+def test_transmissions_gpu():
+    """site + reference-site and slider-crank transmissions on the device (models/ant_trn.xml)"""
+    assert available()
+    path = os.path.join(ROOT, "models", "ant_trn.mjb")
+    nenv, nstep = 8, 80
+    m, b, o = make_pair(path, mb.SOLVER_NEWTON, nenv=nenv)
+    s0 = perturbed_states(o, nenv, seed=14, height=[0.4, 0.55, 0.8], qvel_std=0.8, qpos_std=0.15)
+    ctrl = np.random.default_rng(15).uniform(-1, 1, (nenv, nstep, o.size("nu")))
+    out = b.rollout(s0, ctrl)
+    ref, stats, _ = o.rollout(s0, ctrl, nthread=os.cpu_count() or 1)
+    assert stats[:, 3].sum() == 0 and (b.warnings() == 0).all()
+    err = (np.abs(out - ref) / np.maximum(1.0, np.abs(ref).max(axis=(0, 1)))).max(axis=(0, 2))
+    print("transmissions rollout rel err: step 30 %.3e, step 80 %.3e" % (err[:30].max(), err.max()))
+    assert err[:30].max() < RTOL_TIGHT and err.max() < RTOL_TRAJ
+    for t in (10, 60):
+        compare_forward(b, o, ref[:, t, :], ctrl[:, t, :], rtol=RTOL_TIGHT, check_dual=False)
+        for e in range(nenv):
+            o.reset(); o.set_state(ref[e, t]); o.dfield("ctrl")[:] = ctrl[e, t]; o.forward()
+            r = np.array(o.dfield("actuator_length"))
+            assert np.abs(b.field("actuator_length")[e] - r).max() <= 1e-9 * max(1.0, np.abs(r).max())
