@@ -43,6 +43,7 @@ struct mjbBatch_ {
   double* io_state = nullptr;
   void* stage = nullptr;        // dense staging for field I/O
   size_t stage_bytes = 0;
+  void* copy_stream = nullptr;  // device -> host copies of finished rollout chunks, overlapped with the steps that follow
   void* roll[3] = {nullptr, nullptr, nullptr};   // control / state / sensordata buffers of mjb_rollout, kept between calls
   size_t roll_bytes[3] = {0, 0, 0};
   std::vector<void*> gstreams;  // extra streams of the grouped multi-step execution (see env_groups)
@@ -181,6 +182,7 @@ void mjb_free_batch(mjbBatch* B) {
   backend::dev_free(B->io_state);
   backend::dev_free(B->stage);
   for (void* r : B->roll) backend::dev_free(r);
+  if (B->copy_stream) { backend::sync(B->copy_stream); backend::stream_destroy(B->copy_stream); }
   backend::stream_destroy(B->stream);
   delete B;
 }
@@ -436,6 +438,12 @@ int mjb_rollout(mjbBatch* B, int nstep, unsigned int control_spec, const double*
   }
   std::vector<EnvGroup> gs = env_groups(B, nstep);
   int rc = groups_fork(B, gs);
+  // the states of a finished chunk of steps travel to the host while the next chunks are stepped: every launch is
+  // enqueued first, an event marks the end of each chunk, and the (strided: [env][step][state]) copies follow on a
+  // second stream.  Single group only; with several groups the copy follows the join.
+  const int nchunk = (gs.size() == 1 && d_state && nstep >= 8) ? 4 : 1;
+  std::vector<void*> chunk_ev;
+  std::vector<int> chunk_end;
   for (int t = 0; t < nstep && !rc; t++) {
     for (size_t gi = 0; gi < gs.size(); gi++) {
       auto& g = gs[gi];
@@ -444,9 +452,29 @@ int mjb_rollout(mjbBatch* B, int nstep, unsigned int control_spec, const double*
       if (d_state && !rc) rc = backend::launch_get_state(B->dm, g.b, d_state + (size_t)g.e0 * nstep * nstate, nstep, t, nstate, g.stream);
       if (d_sens && !rc) rc = backend::launch_get_sensor(B->dm, g.b, d_sens + (size_t)g.e0 * nstep * nsens, nstep, t, nsens, g.stream);
     }
+    if (nchunk > 1 && !rc && ((t + 1) % ((nstep + nchunk - 1) / nchunk) == 0 || t + 1 == nstep)) {
+      void* ev = backend::event_record(B->stream);
+      if (ev) { chunk_ev.push_back(ev); chunk_end.push_back(t + 1); }
+    }
   }
   if (!rc) rc = groups_join(B, gs);
-  if (!rc && d_state) rc = backend::d2h(state, d_state, sbytes, B->stream);
+  if (!rc && d_state) {
+    if (nchunk > 1 && !chunk_end.empty() && chunk_end.back() == nstep) {
+      if (!B->copy_stream) B->copy_stream = backend::stream_create();
+      const size_t pitch = (size_t)nstep * nstate * sizeof(double);
+      int t0 = 0;
+      for (size_t c = 0; c < chunk_ev.size() && !rc; c++) {
+        rc = backend::stream_wait_event(B->copy_stream, chunk_ev[c]);
+        if (!rc) rc = backend::d2h_2d(state + (size_t)t0 * nstate, pitch, d_state + (size_t)t0 * nstate, pitch,
+                                      (size_t)(chunk_end[c] - t0) * nstate * sizeof(double), (size_t)nenv, B->copy_stream);
+        t0 = chunk_end[c];
+      }
+      if (!rc) rc = backend::sync(B->copy_stream);
+    } else {
+      for (void* ev : chunk_ev) backend::stream_wait_event(B->stream, ev);   // (releases the events)
+      rc = backend::d2h(state, d_state, sbytes, B->stream);
+    }
+  }
   if (!rc && d_sens) rc = backend::d2h(sensordata, d_sens, nbytes, B->stream);
   if (!rc) rc = backend::sync(B->stream);
   return rc;

@@ -21,6 +21,10 @@ void stream_destroy(void* s);
 int sync(void* stream);
 // order `waiter` after everything enqueued on `signaller` so far (event record + stream wait)
 int stream_order(void* signaller, void* waiter);
+// events for overlapping copies with the work of another stream, and a strided device -> host copy
+void* event_record(void* stream);                    // new event recorded on `stream` (NULL on failure)
+int stream_wait_event(void* stream, void* event);    // `stream` waits for the event; the event is released afterwards
+int d2h_2d(void* dst, size_t dpitch, const void* src, size_t spitch, size_t width, size_t height, void* stream);
 
 // run the pipeline stages selected by `mask` (bit s = stage s, see mjb_forward.h) for every
 // environment in ONE launch.  flags: bit0 = part of mj_step (run the qpos/qvel checks), bit1 = skip

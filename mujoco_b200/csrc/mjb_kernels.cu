@@ -147,6 +147,21 @@ int stream_order(void* signaller, void* waiter) {
   CK(cudaEventDestroy(ev), "event destroy");   // released once the wait has been satisfied
   return 0;
 }
+void* event_record(void* stream) {
+  cudaEvent_t ev;
+  if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+  if (cudaEventRecord(ev, (cudaStream_t)stream) != cudaSuccess) { cudaEventDestroy(ev); return nullptr; }
+  return (void*)ev;
+}
+int stream_wait_event(void* stream, void* event) {
+  CK(cudaStreamWaitEvent((cudaStream_t)stream, (cudaEvent_t)event, 0), "stream wait");
+  CK(cudaEventDestroy((cudaEvent_t)event), "event destroy");
+  return 0;
+}
+int d2h_2d(void* dst, size_t dpitch, const void* src, size_t spitch, size_t width, size_t height, void* s) {
+  CK(cudaMemcpy2DAsync(dst, dpitch, src, spitch, width, height, cudaMemcpyDeviceToHost, (cudaStream_t)s), "d2h 2d");
+  return 0;
+}
 long launches() { return g_launches; }
 
 static inline int nblocks(const Batch& b, int threads) { return (b.nenv + threads - 1) / threads; }

@@ -26,6 +26,12 @@ void* stream_create() { return nullptr; }
 void stream_destroy(void*) {}
 int sync(void*) { return 0; }
 int stream_order(void*, void*) { return 0; }
+void* event_record(void*) { return (void*)1; }
+int stream_wait_event(void*, void*) { return 0; }
+int d2h_2d(void* dst, size_t dpitch, const void* src, size_t spitch, size_t width, size_t height, void*) {
+  for (size_t r = 0; r < height; r++) memcpy((char*)dst + r * dpitch, (const char*)src + r * spitch, width);
+  return 0;
+}
 long launches() { return g_launches; }
 int set_debug(const char*, int) { return 0; }
 
