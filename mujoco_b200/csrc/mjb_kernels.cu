@@ -56,10 +56,27 @@ __global__ void k_set_control(DModel m, Batch b, const double* control, int nste
   run_set_control(m, b, e, control, nstep, t, spec, ncontrol, skip_warned != 0);
 }
 
+// control_spec == CTRL (the common case): one thread per (environment, actuator)
+__global__ void k_set_ctrl_only(DModel m, Batch b, const double* control, int nstep, int t, int skip_warned) {
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int nu = m.sz.nu;
+  if (idx >= (long)b.nenv * nu) return;
+  const int e = (int)(idx / nu), k = (int)(idx - (long)e * nu);
+  Env d(m, b, e);
+  if (skip_warned && env_has_warning(d)) return;
+  d.ctrl()[k] = control[((size_t)e * nstep + t) * nu + k];
+}
+
+// one thread per (environment, state element): consecutive threads write consecutive elements of an environment's
+// state row (FULLPHYSICS = time, qpos, qvel, act)
 __global__ void k_get_state(DModel m, Batch b, double* state, int nstep, int t, int nstate) {
-  const int e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= b.nenv) return;
-  run_get_state(m, b, e, state, nstep, t, nstate);
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long)b.nenv * nstate) return;
+  const int e = (int)(idx / nstate), k = (int)(idx - (long)e * nstate);
+  Env d(m, b, e);
+  const int nq = m.sz.nq, nv = m.sz.nv;
+  const double v = (k == 0) ? d.time()[0] : (k <= nq) ? d.qpos()[k - 1] : (k <= nq + nv) ? d.qvel()[k - 1 - nq] : d.act()[k - 1 - nq - nv];
+  state[((size_t)e * nstep + t) * nstate + k] = v;
 }
 
 __global__ void k_get_sensor(DModel m, Batch b, double* sens, int nstep, int t, int nsens) {
@@ -68,10 +85,14 @@ __global__ void k_get_sensor(DModel m, Batch b, double* sens, int nstep, int t, 
   run_get_sensor(m, b, e, sens, nstep, t, nsens);
 }
 
+// one thread per (actuator, environment): consecutive threads read consecutive environments of one actuator's row
 __global__ void k_set_control_native(DModel m, Batch b, const double* ctrl, int t) {
-  const int e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= b.nenv) return;
-  run_set_control_native(m, b, e, ctrl, t);
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int nu = m.sz.nu;
+  if (idx >= (long)b.nenv * nu) return;
+  const int i = (int)(idx / b.nenv), e = (int)(idx - (long)i * b.nenv);
+  Env d(m, b, e);
+  d.ctrl()[i] = ctrl[((size_t)t * nu + i) * b.stride + e];
 }
 
 __global__ void k_get_state_native(DModel m, Batch b, double* state, int t, int nstate) {
@@ -277,19 +298,24 @@ int launch_reset(const DModel& dm, const Batch& b, void* s) {
 }
 int launch_set_control(const DModel& dm, const Batch& b, const double* control, int nstep, int t, unsigned spec,
                        int ncontrol, void* s, bool skip_warned) {
-  k_set_control<<<nblocks(b, 128), 128, 0, (cudaStream_t)s>>>(dm, b, control, nstep, t, spec, ncontrol, skip_warned ? 1 : 0);
+  if (ncontrol == 0) return 0;
+  if (spec == (1u << 6) && ncontrol == dm.sz.nu)
+    k_set_ctrl_only<<<(unsigned)(((long)b.nenv * dm.sz.nu + 255) / 256), 256, 0, (cudaStream_t)s>>>(dm, b, control, nstep, t, skip_warned ? 1 : 0);
+  else
+    k_set_control<<<nblocks(b, 128), 128, 0, (cudaStream_t)s>>>(dm, b, control, nstep, t, spec, ncontrol, skip_warned ? 1 : 0);
   g_launches++;
   CK(cudaPeekAtLastError(), "k_set_control launch");
   return 0;
 }
 int launch_get_state(const DModel& dm, const Batch& b, double* state, int nstep, int t, int nstate, void* s) {
-  k_get_state<<<nblocks(b, 128), 128, 0, (cudaStream_t)s>>>(dm, b, state, nstep, t, nstate);
+  k_get_state<<<(unsigned)(((long)b.nenv * nstate + 255) / 256), 256, 0, (cudaStream_t)s>>>(dm, b, state, nstep, t, nstate);
   g_launches++;
   CK(cudaPeekAtLastError(), "k_get_state launch");
   return 0;
 }
 int launch_set_control_native(const DModel& dm, const Batch& b, const double* ctrl, int t, void* s) {
-  k_set_control_native<<<nblocks(b, 128), 128, 0, (cudaStream_t)s>>>(dm, b, ctrl, t);
+  if (dm.sz.nu == 0) return 0;
+  k_set_control_native<<<(unsigned)(((long)b.nenv * dm.sz.nu + 255) / 256), 256, 0, (cudaStream_t)s>>>(dm, b, ctrl, t);
   g_launches++;
   CK(cudaPeekAtLastError(), "k_set_control_native launch");
   return 0;
