@@ -122,6 +122,7 @@ __device__ __forceinline__ int pgs4_sweeps(const Options& opt, int nv, bool act,
       const double2* pa = (const double2*)(recA + i * RECD);
 #pragma unroll
       for (int q = 0; q < NQ / 2; q++) { const double2 v = pa[q]; A[2 * q] = v.x; A[2 * q + 1] = v.y; }
+      if (NQ & 1) A[NQ - 1] = (recA + i * RECD)[NQ - 1];
       const double2* pt = (const double2*)(recT + i * RECD);
       const double2 t0 = pt[0], t1 = pt[1];
       AT[0] = t0.x; AT[1] = t0.y; AT[2] = t1.x; AT[3] = t1.y;   // AT[3] = b
@@ -360,7 +361,10 @@ __global__ void __launch_bounds__(32) k_pgs4(DModel m, Batch b, int flags, const
   E.gAR = d.efc_AR().p;
   E.ord = order_tab + (size_t)order_iters * (nefc > 0 ? nefc * (nefc - 1) / 2 : 0);
   // packed (staged) layout if the records of the eight environments fit the warp's shared memory
-  const int NQc = top <= 4 * 4 + 3 ? 4 : top <= 4 * 8 + 3 ? 8 : top <= 4 * 12 + 3 ? 12 : 16;
+  // register classes (chain elements per lane): a row costs about 28 cycles per chain element, so the classes are fine
+  // (every length from 4 to 16)
+  const int nqt = (top & ~3) >> 2;   // chain length of the largest problem in the warp
+  const int NQc = nqt <= 4 ? 4 : nqt;
   // each environment's records are sized by its OWN row length (a small neighbour of a large problem stays small);
   // the class code reads up to NQc chain elements per lane, so reads past an environment's own chain length land
   // in finite data of the SAME environment (its next lane / record, or the zero pad after its last record) and meet
@@ -448,13 +452,24 @@ __global__ void __launch_bounds__(32) k_pgs4(DModel m, Batch b, int flags, const
   PROF(if (threadIdx.x == 0 && blockIdx.x < 8192) g_pgs4_prof[blockIdx.x][7] = clock64() - prof_t0;)
   int iter;
   if (staged) {
-    if (NQc == 4) iter = pgs4_sweeps<4, 1, true>(m.opt, m.sz.nv, act, E, k);
-    else if (NQc == 8) iter = pgs4_sweeps<8, 1, true>(m.opt, m.sz.nv, act, E, k);
-    else if (NQc == 12) iter = pgs4_sweeps<12, 1, true>(m.opt, m.sz.nv, act, E, k);
-    else iter = pgs4_sweeps<16, 1, true>(m.opt, m.sz.nv, act, E, k);
+    switch (NQc) {
+      case 4: iter = pgs4_sweeps<4, 1, true>(m.opt, m.sz.nv, act, E, k); break;
+      case 5: iter = pgs4_sweeps<5, 1, true>(m.opt, m.sz.nv, act, E, k); break;
+      case 6: iter = pgs4_sweeps<6, 1, true>(m.opt, m.sz.nv, act, E, k); break;
+      case 7: iter = pgs4_sweeps<7, 1, true>(m.opt, m.sz.nv, act, E, k); break;
+      case 8: iter = pgs4_sweeps<8, 1, true>(m.opt, m.sz.nv, act, E, k); break;
+      case 9: iter = pgs4_sweeps<9, 1, true>(m.opt, m.sz.nv, act, E, k); break;
+      case 10: iter = pgs4_sweeps<10, 1, true>(m.opt, m.sz.nv, act, E, k); break;
+      case 11: iter = pgs4_sweeps<11, 1, true>(m.opt, m.sz.nv, act, E, k); break;
+      case 12: iter = pgs4_sweeps<12, 1, true>(m.opt, m.sz.nv, act, E, k); break;
+      case 13: iter = pgs4_sweeps<13, 1, true>(m.opt, m.sz.nv, act, E, k); break;
+      case 14: iter = pgs4_sweeps<14, 1, true>(m.opt, m.sz.nv, act, E, k); break;
+      case 15: iter = pgs4_sweeps<15, 1, true>(m.opt, m.sz.nv, act, E, k); break;
+      default: iter = pgs4_sweeps<16, 1, true>(m.opt, m.sz.nv, act, E, k); break;
+    }
   } else {
     if (NQc == 4) iter = pgs4_sweeps<4, 2, false>(m.opt, m.sz.nv, act, E, k);
-    else if (NQc == 8) iter = pgs4_sweeps<8, 2, false>(m.opt, m.sz.nv, act, E, k);
+    else if (NQc <= 8) iter = pgs4_sweeps<8, 2, false>(m.opt, m.sz.nv, act, E, k);
     else iter = pgs4_sweeps<16, 1, false>(m.opt, m.sz.nv, act, E, k);   // (12 takes the 16 code here: the fallback is rare)
   }
   __syncwarp();
