@@ -444,7 +444,22 @@ int mjb_rollout(mjbBatch* B, int nstep, unsigned int control_spec, const double*
   const int nchunk = (gs.size() == 1 && d_state && nstep >= 8) ? 4 : 1;
   std::vector<void*> chunk_ev;
   std::vector<int> chunk_end;
-  for (int t = 0; t < nstep && !rc; t++) {
+  // persistent kernel (mjb_krollout.cu): one launch per chunk of steps, no device-wide barrier inside a chunk
+  bool persistent = !rc && gs.size() == 1 && !d_sens && (!d_control || control_spec == ST_CTRL) &&
+                    backend::rollout_persistent_available(B->dm, B->b, nstep);
+  if (persistent) {
+    const int per = (nstep + nchunk - 1) / nchunk;
+    for (int t0 = 0; t0 < nstep && !rc; t0 += per) {
+      const int t1 = t0 + per < nstep ? t0 + per : nstep;
+      rc = backend::launch_rollout_persistent(B->dm, B->b, t0, t1, nstep, 1 | 2, 4, 1, d_control, d_state, nstate, B->stream);
+      if (rc == -1) { persistent = false; rc = 0; break; }   // the batch does not fit the mapping (decided before any launch)
+      if (nchunk > 1 && !rc) {
+        void* ev = backend::event_record(B->stream);
+        if (ev) { chunk_ev.push_back(ev); chunk_end.push_back(t1); }
+      }
+    }
+  }
+  for (int t = 0; t < nstep && !rc && !persistent; t++) {
     for (size_t gi = 0; gi < gs.size(); gi++) {
       auto& g = gs[gi];
       if (d_control && !rc) rc = backend::launch_set_control(B->dm, g.b, d_control + (size_t)g.e0 * nstep * ncontrol, nstep, t, control_spec, ncontrol, g.stream);
@@ -501,9 +516,15 @@ int mjb_step_host(mjbBatch* B, const double* ctrl, double* state_out) {
 int mjb_rollout_device(mjbBatch* B, int nstep, const double* d_ctrl, double* d_state) {
   if (!B || nstep < 0) return fail(MJB_ERR_ARG, "mjb_rollout_device: bad arguments");
   const int nstate = 1 + B->hm.dm.sz.nq + B->hm.dm.sz.nv + B->hm.dm.sz.na;
-  // one fused launch per step: a persistent multi-step kernel measured ~2x slower (warps drift apart and
-  // the instruction working set no longer fits the instruction caches; per-step launches re-converge them)
+  // per-step launches (fused step or split step) unless the persistent rollout kernel applies; a persistent kernel
+  // whose WARPS drift apart was measured ~2x slower in round 1 (the instruction working set no longer fits the
+  // instruction caches) - mjb_krollout.cu keeps the warps of a CTA in step and lets only the CTAs drift
   std::vector<EnvGroup> gs = env_groups(B, nstep);
+  if (gs.size() == 1 && backend::rollout_persistent_available(B->dm, B->b, nstep)) {
+    // every step in one persistent launch (mjb_krollout.cu): each CTA carries its own environments through the steps
+    const int rc = backend::launch_rollout_persistent(B->dm, B->b, 0, nstep, nstep, 1, 0, 0, d_ctrl, d_state, nstate, B->stream);
+    if (rc != -1) return rc;
+  }
   int rc = groups_fork(B, gs);
   for (int t = 0; t < nstep && !rc; t++) {
     for (size_t gi = 0; gi < gs.size(); gi++) {   // native layouts are [..][elem][env]: a group starts e0 elements further

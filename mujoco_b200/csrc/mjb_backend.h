@@ -39,6 +39,12 @@ bool split_step_available(const DModel& dm, const Batch& b);
 int launch_split_step(const DModel& dm, const Batch& b, int first, int later, void* stream, void* stagger = nullptr);
 // one split step, synchronous, with the duration (ms) of its four launches: first half, solve, second half, redo
 int profile_split_step(const DModel& dm, const Batch& b, void* stream, float* ms);
+// persistent rollout kernel (mjb_krollout.cu): steps [t0, t1) of an nstep rollout in one launch, every CTA carrying its
+// own environments through the steps without a device-wide barrier.  layout 0: native ctrl [step][nu][stride] / state
+// [step][nstate][stride]; layout 1: reference ctrl [env][step][nu] / state [env][step][nstate].  ctrl / state may be null.
+bool rollout_persistent_available(const DModel& dm, const Batch& b, int nstep);
+int launch_rollout_persistent(const DModel& dm, const Batch& b, int t0, int t1, int nstep, int first, int later, int layout,
+                              const double* ctrl, double* state, int nstate, void* stream);
 int launch_rk4(const DModel& dm, const Batch& b, int phase, int flags, void* stream);   // rk4_phase of every env
 int launch_reset(const DModel& dm, const Batch& b, void* stream);
 // rollout helpers; control/state are DEVICE buffers laid out [nenv][nstep][n] (reference layout)

@@ -14,6 +14,7 @@
 // the lanes; each element is computed by one lane with the reference's operation order.
 #pragma once
 #include "mjb_smooth.h"
+#include "mjb_prof.h"
 
 namespace mjb {
 
@@ -481,42 +482,59 @@ MJB_HD void project_constraint(const Env& d) {
   if (!nefc || d.solver != SOL_PGS) return;
   FD J = d.efc_J(), Y = d.efc_Y(), AR = d.efc_AR(), qLD = d.qLD(), R = d.efc_R();
   FD sq = d.scr_nv();
+  MJB_PROF_BEGIN
   MJB_PFOR(i, nv) sq[i] = 1 / sqrt(qLD[m.M_rowadr[i] + m.M_rownnz[i] - 1]);
   MJB_PSYNC();
-  MJB_PFOR(r, nefc) {   // one lane per row: serial half back-substitution (mj_solveM2) in a
-    double x[kMaxDenseNv];   // lane-private array (the dependent read-modify-write chain never leaves the SM)
+  // one lane per row: half back-substitution x <- L^-T x (mj_solveM2) in GATHER form: x[j] is final once every
+  // descendant i > j has been subtracted, in descending i (the order of the reference's scatter loop, terms with
+  // x[i] == 0 skipped as there); the accumulator is a register and x lives in the row of Y itself, so the only
+  // dependent memory round trip is one store -> load per dof instead of one per nonzero of L
+  MJB_PFOR(r, nefc) {
     FD src = J + (long)r * nv, dst = Y + (long)r * nv;
-    for (int c = 0; c < nv; c++) x[c] = src[c];
-    for (int i = nv - 1; i > 0; i--) {
-      if (m.dof_simplenum[i]) continue;
-      const double xi = x[i];
-      if (xi != 0) {
-        const int start = m.M_rowadr[i], end = start + m.M_rownnz[i] - 1;
-        for (int adr = start; adr < end; adr++) x[m.M_colind[adr]] -= qLD[adr] * xi;
+    for (int j = nv - 1; j >= 0; j--) {
+      double s = src[j];
+      const int a0 = m.mt_adr[j], a1 = m.mt_adr[j + 1];
+      for (int a = a0; a < a1; a++) {
+        const double xi = dst[m.mt_dof[a]];
+        const double t = s - qLD[m.mt_qadr[a]] * xi;
+        s = xi != 0 ? t : s;
       }
+      dst[j] = s;
     }
-    for (int i = 0; i < nv; i++) dst[i] = x[i] * sq[i];
+    for (int j = 0; j < nv; j++) dst[j] = dst[j] * sq[j];
   }
   MJB_PSYNC();
+  MJB_PROF_MARK(11)
   // AR[i][c] = sum_j Y[c][j] * Y[i][j], j ascending, skipping Y[i][j] == 0 (mju_sqrMatTD); one lane
   // per lower-triangle element, mirrored; R added on the diagonal
   const int ntri = nefc * (nefc + 1) / 2;
   MJB_PFOR(t, ntri) {
-    int i = (int)((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
+    int i = (int)((sqrtf(8.0f * t + 1.0f) - 1.0f) * 0.5f);
     while ((i + 1) * (i + 2) / 2 <= t) i++;
     while (i * (i + 1) / 2 > t) i--;
     const int c = t - i * (i + 1) / 2;
     FD yi = Y + (long)i * nv, yc = Y + (long)c * nv;
     double s = 0;
-    for (int j = 0; j < nv; j++) {
+    int j = 0;
+    for (; j + 4 <= nv; j += 4) {     // loads of four terms in flight; a skipped term leaves s unchanged
+      const double v0 = yi[j], v1 = yi[j + 1], v2 = yi[j + 2], v3 = yi[j + 3];
+      const double p0 = yc[j] * v0, p1 = yc[j + 1] * v1, p2 = yc[j + 2] * v2, p3 = yc[j + 3] * v3;
+      double u = s + p0; s = v0 != 0 ? u : s;
+      u = s + p1; s = v1 != 0 ? u : s;
+      u = s + p2; s = v2 != 0 ? u : s;
+      u = s + p3; s = v3 != 0 ? u : s;
+    }
+    for (; j < nv; j++) {
       const double v = yi[j];
-      if (v != 0) s += yc[j] * v;
+      const double u = s + yc[j] * v;
+      s = v != 0 ? u : s;
     }
     if (i == c) s += R[i];
     AR[(long)i * nefc + c] = s;
     AR[(long)c * nefc + i] = s;
   }
   MJB_PSYNC();
+  MJB_PROF_MARK(12)
 }
 
 // row . f in mju_dot's accumulation order on raw pointers

@@ -7,6 +7,8 @@
 // Compiled with -fmad=false: contact in/out decisions must round like the reference's C build.
 #include <cuda_runtime.h>
 
+#include <cstring>
+
 #include <cstdio>
 #include <cstdlib>
 #include <string>
@@ -230,6 +232,36 @@ int launch_split_step(const DModel& dm, const Batch& b, int first, int later, vo
     CK(cudaPeekAtLastError(), "redo launch");
   }
   return 0;
+}
+
+// persistent rollout (mjb_krollout.cu): eligible when the step is the lean 16-lane split step and the batch fits one
+// CTA per SM.  OFF by default (MJB_PERSISTENT=1 or mjb_set_debug("persistent", 1) turn it on): measured on B200,
+// humanoid x4096, it runs 1.23-1.40 ms per step against 1.19 for the per-step launches - dropping the device-wide
+// barrier removes the wait for the slowest of 4096 environments, but inside one 2.5 MB kernel the halves of the step
+// run 20-35 % slower (the PGS pool takes 64-100 KB of the L1 they live on) and the solve 50 % slower
+// (profiles/r02_experiments.md section 7).  Kept as a tested alternative, bit-identical to the split step.
+static int g_persistent = -1;
+static bool lean_model(const DModel& dm, const Batch& b) {
+  return dm.sz.nsensor == 0 && dm.sz.neq == 0 && dm.sz.ntree == 1 && dm.opt.integrator != INT_IMPLICITFAST && !dm.sz.actfeat && !dm.sz.colbox && !dm.sz.epot && !dm.sz.ekin && !b.xfrc;
+}
+bool rollout_persistent_available(const DModel& dm, const Batch& b, int nstep) {
+  if (g_persistent < 0) { const char* e = getenv("MJB_PERSISTENT"); g_persistent = e ? atoi(e) : 0; }
+  static const int part_lanes = [] { const char* e = getenv("MJB_PART_LANES"); return e ? atoi(e) : 16; }();
+  return g_persistent > 0 && nstep >= 2 && part_lanes == 16 && split_step_available(dm, b) && lean_model(dm, b);
+}
+int launch_rollout_persistent(const DModel& dm, const Batch& b, int t0, int t1, int nstep, int first, int later, int layout,
+                              const double* ctrl, double* state, int nstate, void* s) {
+  const int rc = launch_krollout_lean(dm, b, t0, t1, nstep, first, later, layout, ctrl, state, nstate, s);
+  if (rc == -1) return -1;   // does not fit the mapping: the caller steps launch by launch
+  if (rc) return cuda_fail(cudaGetLastError(), "persistent rollout setup");
+  g_launches++;
+  CK(cudaPeekAtLastError(), "k_rollout launch");
+  return 0;
+}
+int set_debug(const char* key, int value) {
+  if (!strcmp(key, "pgs4_slots")) { pgs4_set_force_slots(value); return 0; }
+  if (!strcmp(key, "persistent")) { g_persistent = value ? 1 : 0; return 0; }
+  return -1;
 }
 
 // one split step with CUDA events around each launch (bench.py: per-kernel durations on the launching stream)

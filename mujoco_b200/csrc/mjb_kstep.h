@@ -30,6 +30,9 @@ void launch_kpart2_lean16(const DModel& dm, const Batch& b, int mask, int flags,
 void launch_kpart1_lean8(const DModel& dm, const Batch& b, int mask, int flags, void* stream);
 void launch_kpart2_lean8(const DModel& dm, const Batch& b, int mask, int flags, void* stream);
 int launch_pgs4(const DModel& dm, const Batch& b, int flags, void* stream);
+int launch_krollout_lean(const DModel& dm, const Batch& b, int t0, int t1, int nstep, int first, int later, int layout,
+                         const double* ctrl, double* state, int nstate, void* stream);   // mjb_krollout.cu
+void pgs4_set_force_slots(int on);
 }  // namespace backend
 
 #if defined(MJB_KSTEP_INSTANCE) && defined(__CUDACC__)

@@ -34,6 +34,8 @@ int d2h_2d(void* dst, size_t dpitch, const void* src, size_t spitch, size_t widt
 }
 long launches() { return g_launches; }
 int set_debug(const char*, int) { return 0; }
+bool rollout_persistent_available(const DModel&, const Batch&, int) { return false; }   // the emulation steps launch by launch
+int launch_rollout_persistent(const DModel&, const Batch&, int, int, int, int, int, int, const double*, double*, int, void*) { return -1; }
 
 int launch_stages(const DModel& dm, const Batch& b, int mask, int flags, void*) {
   g_launches++;

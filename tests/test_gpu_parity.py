@@ -515,6 +515,57 @@ def test_pgs_slot_layout_fallback(monkeypatch):
     assert np.array_equal(packed, slots) and np.array_equal(niter, b.field("solver_niter")[:, 0])
 
 
+@pytest.mark.parametrize("nenv", [64, 333, 4096])
+def test_persistent_rollout_equals_split_step(nenv):
+    """mjb_krollout.cu (every step of a rollout in one persistent launch, CTAs drifting apart) against the per-step
+    launches of the split step (the default path): identical states, iteration counts and warnings, bit for bit - through the reference
+    layout (mjb_rollout, host arrays, rollout skip rule) and through the native device layout (mjb_rollout_device).
+    One environment starts in a state that makes its acceleration blow up (reset + second forward pass inside the
+    persistent kernel), one carries a NaN (warned environments stop stepping and stop taking controls)."""
+    import torch
+    assert available()
+    nstep = 24
+    o = Oracle(HUMANOID)
+    o.set_opt("solver", 0)
+    s0 = perturbed_states(o, min(nenv, 256), seed=5, height=[0.2, 0.3, 0.5, 0.8, 1.3], qvel_std=0.5, qpos_std=0.2)
+    s0 = np.tile(s0, ((nenv + len(s0) - 1) // len(s0), 1))[:nenv].copy()
+    nq = o.size("nq")
+    s0[3, 1 + nq:1 + nq + 6] = 1e9          # huge velocity: bad qacc / bad qvel inside the rollout
+    s0[5, 2] = np.nan                       # bad qpos from the first step on
+    nu = o.size("nu")
+    ctrl = np.random.default_rng(6).uniform(-1, 1, (nenv, nstep, nu))
+    m = mb.Model(HUMANOID)
+    m.set_option("solver", mb.SOLVER_PGS)
+    b = mb.Batch(m, nenv, nconmax=48, njmax=128)
+    out, niter, warn = {}, {}, {}
+    for mode in (1, 0):
+        b.set_debug("persistent", mode)
+        out[mode] = b.rollout(s0, ctrl)
+        niter[mode] = b.field("solver_niter")[:, 0].copy()
+        warn[mode] = b.field("warning").copy()
+    b.set_debug("persistent", 0)
+    assert np.array_equal(out[1], out[0], equal_nan=True)
+    assert np.array_equal(niter[1], niter[0]) and np.array_equal(warn[1], warn[0])
+    assert warn[1][3].any() and warn[1][5].any()
+    # native layout on the device
+    stride = b.env_stride()
+    c = torch.zeros((nstep, nu, stride), dtype=torch.float64, device="cuda")
+    c[:, :, :nenv] = torch.from_numpy(np.ascontiguousarray(ctrl.transpose(1, 2, 0))).cuda()
+    nstate = s0.shape[1]
+    dev = {}
+    for mode in (1, 0):
+        b.set_debug("persistent", mode)
+        b.reset()
+        b.set_state(s0)
+        st = torch.zeros((nstep, nstate, stride), dtype=torch.float64, device="cuda")
+        torch.cuda.synchronize()
+        b.rollout_device(nstep, c.data_ptr(), st.data_ptr())
+        torch.cuda.ExternalStream(b.stream()).synchronize()
+        dev[mode] = st[:, :, :nenv].cpu().numpy()
+    b.set_debug("persistent", 0)
+    assert np.array_equal(dev[1], dev[0], equal_nan=True)
+
+
 def test_single_environment_symbols_gpu():
     """the loop of sample/testspeed.cc:123 - `mj_step(m, d)` on the reference's own mjModel / mjData - with the
     symbol resolved in libmjb200.so instead of libmujoco (dlopen + dlsym through ctypes), next to the reference

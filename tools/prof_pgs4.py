@@ -4,7 +4,7 @@ import numpy as np
 sys.path.insert(0, '/root/repo'); sys.path.insert(0, '/root/repo/tests')
 import torch
 import mujoco_b200 as mb
-cdll = ctypes.CDLL('/root/repo/build/prof/libmjb200_prof.so')
+cdll = ctypes.CDLL('/root/repo/prof_build/libmjb200_prof.so')
 lib = mb._bind(cdll)
 m = mb.Model('/root/repo/models/humanoid.mjb', library=lib); m.set_option('solver', 0)
 nenv = 4096

@@ -4,7 +4,7 @@ import numpy as np
 sys.path.insert(0, '/root/repo'); sys.path.insert(0, '/root/repo/tests')
 import torch
 import mujoco_b200 as mb
-cdll = ctypes.CDLL('/root/repo/build/prof/libmjb200_prof.so')
+cdll = ctypes.CDLL('/root/repo/prof_build/libmjb200_prof.so')
 lib = mb._bind(cdll)
 m = mb.Model('/root/repo/models/humanoid.mjb', library=lib); m.set_option('solver', 0)
 nenv = 4096
@@ -14,7 +14,7 @@ stream = torch.cuda.ExternalStream(b.stream())
 g = torch.Generator(device='cuda'); g.manual_seed(0)
 b.reset()
 names = ['kinematics+com+tendon', 'makeM+factor', 'collision', 'make_constraint', 'project (Y, AR)', 'transmission',
-         'fwd_velocity', 'actuation+acceleration', 'constraint_begin', 'dual_finish', 'euler']
+         'fwd_velocity', 'actuation+acceleration', 'constraint_begin', 'dual_finish', 'euler', 'project: half solve (Y)', 'project: AR']
 for rep in range(3):
     n = 300 if rep == 0 else 10
     c = (torch.rand((n, nu, stride), generator=g, device='cuda', dtype=torch.float64) * 2 - 1).contiguous()
