@@ -236,7 +236,7 @@ int launch_split_step(const DModel& dm, const Batch& b, int first, int later, vo
 
 // persistent rollout (mjb_krollout.cu): eligible when the step is the lean 16-lane split step and the batch fits one
 // CTA per SM.  OFF by default (MJB_PERSISTENT=1 or mjb_set_debug("persistent", 1) turn it on): measured on B200,
-// humanoid x4096, it runs 1.23-1.40 ms per step against 1.19 for the per-step launches - dropping the device-wide
+// humanoid x4096, it runs 1.22-1.40 ms per step against 1.19 for the per-step launches - dropping the device-wide
 // barrier removes the wait for the slowest of 4096 environments, but inside one 2.5 MB kernel the halves of the step
 // run 20-35 % slower (the PGS pool takes 64-100 KB of the L1 they live on) and the solve 50 % slower
 // (profiles/r02_experiments.md section 7).  Kept as a tested alternative, bit-identical to the split step.

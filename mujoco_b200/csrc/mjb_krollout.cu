@@ -17,7 +17,7 @@
 // instruction-cache misses).  Per step a CTA waits for the slowest of ITS 28 environments instead of 4096.
 //
 // Status: correct and tested, but NOT the default (mjb_kernels.cu rollout_persistent_available): on B200, humanoid x4096,
-// a step costs 1.23-1.40 ms here against 1.19 ms for the three launches.  The phases themselves are slower inside this
+// a step costs 1.22-1.40 ms here against 1.19 ms for the three launches.  The phases themselves are slower inside this
 // kernel - first half 712-877 k cycles per warp depending on the L1 left by the PGS pool (63 / 99 / 160 KB pool: 712 /
 // 765 / 877 k), solve 794 k per warp against ~510 k in k_pgs4 - which costs more than the barrier removal gains
 // (profiles/r02_experiments.md section 7).
@@ -87,7 +87,8 @@ struct RolloutPool {
     for (;;) {
       if (lane == 0) need[w] = n;
       barrier();
-      const int off = place();
+      const int off = __shfl_sync(0xffffffffu, place(), 0);   // (uniform by construction; the shuffle tells the compiler)
+      remaining = __shfl_sync(0xffffffffu, remaining, 0);
       barrier();
       if (off != -1) { p = pool + (off > 0 ? off / 8 : 0); bytes = off == -2 ? 0 : n; return; }
       barrier();   // the placed warps of this pass are done: their space is free
@@ -100,6 +101,7 @@ struct RolloutPool {
       if (lane == 0) need[w] = -1;
       barrier();
       place();
+      remaining = __shfl_sync(0xffffffffu, remaining, 0);
       barrier();
     }
     entered = false;
@@ -116,7 +118,10 @@ static __device__ unsigned long long g_rollout_prof[160][kRolloutWarps][8];
 template <int FEAT>
 __global__ void __launch_bounds__(32 * kRolloutWarps, 1) k_rollout(DModel m, Batch b, RolloutArgs a) {
   extern __shared__ double rollout_smem[];
-  const int w = threadIdx.x >> 5, l = threadIdx.x & 31, sub = l >> 4, l16 = l & 15;
+  // the warp index through a shuffle: the compiler then knows it is warp-uniform and keeps the warp-synchronous code
+  // of the solve free of divergence guards (BRA.DIV around every shuffle otherwise: +19 % instructions per PGS row)
+  const int w = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  const int l = threadIdx.x & 31, sub = l >> 4, l16 = l & 15;
   const int base = blockIdx.x * a.envs_per_cta;
   const int here = min(a.envs_per_cta, b.nenv - base);   // environments of this CTA
   if (here <= 0) return;
@@ -160,6 +165,7 @@ __global__ void __launch_bounds__(32 * kRolloutWarps, 1) k_rollout(DModel m, Bat
     } else {
       cta_barrier();
       RMARK(1)
+      __syncwarp();     // (a convergence point the compiler can see: the halves above run under sub-warp masks)
       reg_inc<216>();
       {
         RolloutPool pool{rollout_smem + 16 + kPgs4Beta, a.pool_bytes, (volatile int*)rollout_smem, beta_tab, w, l};
@@ -221,8 +227,8 @@ int launch_krollout_lean(const DModel& dm, const Batch& b, int t0, int t1, int n
   a.envs_per_cta = 2 * ((b.nenv + 2 * sms - 1) / (2 * sms));
   if (a.envs_per_cta > 2 * kRolloutWarps) return -1;
   if ((a.envs_per_cta + 7) / 8 > kRolloutPgsWarps) return -1;
-  static const int pool_kb = [] { const char* e = getenv("MJB_ROLLOUT_POOL_KB"); const int v = e ? atoi(e) : 0; return v > 0 && v <= 200 ? v : 63; }();
-  const size_t smem = (size_t)pool_kb * 1024;     // + 1 KB of static shared memory = the 64 KB carve-out
+  static const int pool_kb = [] { const char* e = getenv("MJB_ROLLOUT_POOL_KB"); const int v = e ? atoi(e) : 0; return v > 0 && v <= 200 ? v : 99; }();
+  const size_t smem = (size_t)pool_kb * 1024;     // + 1 KB of static shared memory = the 100 KB carve-out (measured best: 63 / 99 / 131 KB -> 1.320 / 1.220 / 1.246 ms)
   a.pool_bytes = (int)smem - 128 - 8 * kPgs4Beta;
   if (pgs4_table(dm, &a.tab, &a.tab_iters)) return -3;
   a.t0 = t0; a.t1 = t1; a.nstep = nstep; a.first = first; a.later = later; a.layout = layout;
