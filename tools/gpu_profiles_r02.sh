@@ -11,3 +11,5 @@ timeout 900 ncu --set full --import-source on --clock-control none --launch-skip
 ncu -i gpurun_out/r02_split_full.ncu-rep --page raw --csv > gpurun_out/r02_split_full_raw.csv 2>/dev/null
 cuobjdump -res-usage mujoco_b200/libmjb200.so 2>/dev/null | grep -A1 "k_pgs4\|k_step_warpILi0ELi16ELi0ELi[12]\|k_step_warpILi0ELi32ELi0ELi0" | grep -v "^--" > gpurun_out/r02_res_usage.txt
 ls -la gpurun_out | tail -12
+MJB_PERSISTENT=1 timeout 300 python tools/bench_config.py models/humanoid.mjb 0 4096 200 300 2>&1 | tail -1 > gpurun_out/r02_persistent.txt; cat gpurun_out/r02_persistent.txt
+timeout 300 python tools/bench_config.py models/humanoid.mjb 0 4096 200 300 2>&1 | tail -1 > gpurun_out/r02_split.txt; cat gpurun_out/r02_split.txt
