@@ -169,11 +169,19 @@ MJB_API int mjb_run_stages(mjbBatch* b, int first, int last);
  * solve, finish + integrate half, redo launch}.  MJB_ERR_UNSUPPORTED when the batch steps with one fused launch. */
 MJB_API int mjb_step_profile(mjbBatch* b, float* ms4);
 
-/* test switches (process-wide).  "pgs4_slots" = 1: the PGS kernel takes its fallback shared-memory layout. */
+/* test switches (process-wide).  "pgs4_slots" = 1: the PGS kernel takes its fallback shared-memory layout;
+ * "persistent" = 1: multi-step rollouts of eligible batches run in the persistent rollout kernel. */
 MJB_API int mjb_set_debug(const char* key, int value);
 
 /* CUDA stream used by the batch (cudaStream_t as void*), e.g. for event timing by the caller */
 MJB_API void* mjb_stream(mjbBatch* b);
+
+/* Run the batch on the CALLER's stream from now on (cudaStream_t as void*; NULL: back to the batch's own stream).
+ * Every launch and copy of the batch is then ordered with the caller's other work on that stream, as a caller of the
+ * reference orders mj_step with its own code by program order.  The batch's own stream is drained first; the
+ * caller keeps ownership of its stream and must keep it alive while it is set.  mjb_set_debug("persistent", 1) also
+ * makes multi-step rollouts of eligible batches run as ONE persistent launch (mjb_krollout.cu; off by default). */
+MJB_API int mjb_set_stream(mjbBatch* b, void* stream);
 
 #ifdef __cplusplus
 }

@@ -77,6 +77,7 @@ def _bind(cdll):
     L.mjb_step_profile.argtypes = [vp, vp]
     L.mjb_set_debug.argtypes = [cp, i]
     L.mjb_stream.restype = vp
+    L.mjb_set_stream.argtypes = [vp, vp]
     L.mjb_stream.argtypes = [vp]
     return L
 
@@ -232,6 +233,10 @@ class Batch:
 
     def stream(self):
         return self.L.mjb_stream(self.ptr)
+
+    def set_stream(self, stream):
+        """run the batch on the caller's CUDA stream (cudaStream_t as int; 0 / None: the batch's own stream)"""
+        self._chk(self.L.mjb_set_stream(self.ptr, stream or None))
 
     def env_stride(self):
         return int(self.L.mjb_env_stride(self.ptr))

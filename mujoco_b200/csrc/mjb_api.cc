@@ -38,6 +38,7 @@ struct mjbBatch_ {
   double* d_db = nullptr;
   Batch b;               // device storage
   void* stream = nullptr;
+  void* own_stream = nullptr;   // the stream created with the batch (stream == own_stream unless mjb_set_stream replaced it)
   int device = 0;
   double* io_ctrl = nullptr;    // staging for mjb_step_host
   double* io_state = nullptr;
@@ -134,6 +135,7 @@ mjbBatch* mjb_make_batch(const struct mjModel_* m, int nenv, int nconmax, int nj
   if (H.sz.nlim > 6 * H.sz.njmax) { set_error("njmax too small for the model's limit candidates"); delete B; return nullptr; }
   B->device = device;
   B->stream = backend::stream_create();
+  B->own_stream = B->stream;
   // device copy of the model blobs, pointers rebased
   B->d_ib = (int*)backend::dev_alloc(B->hm.ib.size() * sizeof(int));
   B->d_db = (double*)backend::dev_alloc(B->hm.db.size() * sizeof(double));
@@ -183,13 +185,20 @@ void mjb_free_batch(mjbBatch* B) {
   backend::dev_free(B->stage);
   for (void* r : B->roll) backend::dev_free(r);
   if (B->copy_stream) { backend::sync(B->copy_stream); backend::stream_destroy(B->copy_stream); }
-  backend::stream_destroy(B->stream);
+  backend::stream_destroy(B->own_stream);
   delete B;
 }
 
 int mjb_nenv(const mjbBatch* B) { return B ? B->b.nenv : 0; }
 long mjb_env_stride(const mjbBatch* B) { return B ? (long)B->b.stride : 0; }
 void* mjb_stream(mjbBatch* B) { return B ? B->stream : nullptr; }
+
+int mjb_set_stream(mjbBatch* B, void* stream) {
+  if (!B) return fail(MJB_ERR_ARG, "mjb_set_stream: null batch");
+  if (int rc = backend::sync(B->stream)) return rc;      // nothing of the batch is left in flight on the old stream
+  B->stream = stream ? stream : B->own_stream;
+  return 0;
+}
 long mjb_kernel_launches(const mjbBatch*) { return backend::launches(); }
 
 int mjb_reset(mjbBatch* B) {

@@ -479,7 +479,7 @@ MJB_HD void mul_jacT_vec(const Env& d, FD res, FD vec) {
 MJB_HD void project_constraint(const Env& d) {
   const DModel& m = d.m;
   const int nefc = d.nefc()[0], nv = m.sz.nv;
-  if (!nefc || d.solver != SOL_PGS) return;
+  if (!nefc || (d.solver != SOL_PGS && m.opt.noslip_iterations <= 0)) return;   // mj_isDual
   FD J = d.efc_J(), Y = d.efc_Y(), AR = d.efc_AR(), qLD = d.qLD(), R = d.efc_R();
   FD sq = d.scr_nv();
   MJB_PROF_BEGIN
@@ -1185,6 +1185,99 @@ MJB_HD void solve_pgs(const Env& d) {
     dual_state_ptr(d, force, floss, nefc, ne, nf);
   }
   MJB_PSYNC();
+}
+
+// ---- NoSlip post-solver (solNoSlip, engine_solver.c:767-957): Gauss-Seidel sweeps over the friction rows with the
+// regulariser R taken out of AR (flg_subR), run after the main solver when opt.noslip_iterations > 0 - dry-friction
+// rows one at a time, pyramidal contacts one pair of opposing edges at a time (a 2x2 problem along f0 + f1 = const).
+// The rows of one solve are visited in their stored order and every scalar (residuals through mju_dot, improvement)
+// accumulates in the reference's order, so the sweep is serial: lane 0 runs it.  Per island when islands are on.
+MJB_HD void solve_noslip(const Env& d) {
+  const DModel& m = d.m;
+  const int nefc = d.nefc()[0], ne = d.ne()[0], nf = d.nf()[0];
+  const int maxiter = m.opt.noslip_iterations;
+  if (!nefc || maxiter <= 0) return;
+  double* force = d.efc_force().p;
+  const double* floss = d.efc_frictionloss().p;
+  dual_state_ptr(d, force, floss, nefc, ne, nf);
+  MJB_LANE0 {
+    const double* AR = d.efc_AR().p; const double* R = d.efc_R().p; const double* b = d.efc_b().p;
+    const int* type = d.efc_type().p; const int* id = d.efc_id().p; const int* cdim = d.con_dim().p;
+    const bool isl = use_islands(d);
+    const int nsolve = isl ? d.nisland()[0] : 1;
+    const int* iadr = d.island_iefcadr().p;
+    const int* imap = d.map_iefc2efc().p;
+    int* niter = d.solver_niter().p;
+    const double scale = 1 / (m.opt.meaninertia * (m.sz.nv > 1 ? m.sz.nv : 1));
+    auto resid = [&](int i) { return (b[i] + dot_ptr(AR + (long)i * nefc, force, nefc)) - R[i] * force[i]; };
+    for (int k = 0; k < nsolve; k++) {
+      const int* rows = isl ? imap + iadr[k] : nullptr;
+      const int nrow = isl ? iadr[k + 1] - iadr[k] : nefc;
+      int iter = 0;
+      while (iter < maxiter) {
+        double improvement = 0;
+        if (iter == 0)
+          for (int c = 0; c < nrow; c++) { const int i = rows ? rows[c] : c; improvement += 0.5 * force[i] * force[i] * R[i]; }
+        // dry friction
+        for (int c = 0; c < nrow; c++) {
+          const int i = rows ? rows[c] : c;
+          if (i < ne || i >= ne + nf) continue;
+          const double ainv = 1 / fmax(kMinVal, AR[(long)i * (nefc + 1)] - R[i]);
+          const double res = resid(i), old = force[i];
+          double f = old - res * ainv;
+          if (f < -floss[i]) f = -floss[i];
+          else if (f > floss[i]) f = floss[i];
+          force[i] = f;
+          const double delta = f - old;
+          improvement -= 0.5 * delta * delta / ainv + delta * res;
+        }
+        // contact friction: pairs of opposing pyramid edges
+        for (int c = 0; c < nrow; c++) {
+          const int i = rows ? rows[c] : c;
+          if (i < ne + nf || type[i] != CNSTR_CONTACT_PYRAMIDAL) continue;
+          const int dim = cdim[id[i]];
+          for (int j = i; j < i + 2 * (dim - 1); j += 2) {
+            const double res0 = resid(j), res1 = resid(j + 1);
+            const double old0 = force[j], old1 = force[j + 1];
+            double A00 = AR[(long)j * nefc + j], A01 = AR[(long)j * nefc + j + 1];
+            double A10 = AR[(long)(j + 1) * nefc + j], A11 = AR[(long)(j + 1) * nefc + j + 1];
+            A00 = fmax(1e-10, A00 - R[j]);
+            A11 = fmax(1e-10, A11 - R[j + 1]);
+            const double Ac[4] = {A00, A01, A10, A11}, old[2] = {old0, old1}, rs[2] = {res0, res1};
+            const double bc0 = res0 - dot_ptr(Ac, old, 2), bc1 = res1 - dot_ptr(Ac + 2, old, 2);
+            const double mid = 0.5 * (old0 + old1);
+            const double K1 = A00 + A11 - A01 - A10;
+            const double K0 = mid * (A00 - A11) + bc0 - bc1;
+            double f0, f1;
+            if (K1 < kMinVal) { f0 = mid; f1 = mid; }
+            else {
+              const double y = -K0 / K1;
+              if (y < -mid) { f0 = 0; f1 = 2 * mid; }
+              else if (y > mid) { f0 = 2 * mid; f1 = 0; }
+              else { f0 = mid + y; f1 = mid - y; }
+            }
+            // costChange (engine_solver.c:206-230): 0.5 delta' A delta + delta . res, in mju_mulVecMatVec / mju_dot order;
+            // a positive change restores the pair
+            const double dl[2] = {f0 - old0, f1 - old1};
+            double q = 0;
+            q += dl[0] * dot_ptr(Ac, dl, 2);
+            q += dl[1] * dot_ptr(Ac + 2, dl, 2);
+            double change = 0.5 * q + dot_ptr(dl, rs, 2);
+            if (change > 1e-10) { f0 = old0; f1 = old1; change = 0; }
+            force[j] = f0; force[j + 1] = f1;
+            improvement -= change;
+          }
+          c += 2 * (dim - 1) - 1;
+        }
+        improvement *= scale;
+        iter++;
+        if (improvement < m.opt.noslip_tolerance) break;
+      }
+      if (k < NISLAND) niter[k] += iter;
+    }
+  }
+  MJB_PSYNC();
+  dual_state_ptr(d, force, floss, nefc, ne, nf);
 }
 
 // dual finish: qfrc_constraint = J' f, qacc = qacc_smooth + M^-1 qfrc_constraint

@@ -766,10 +766,11 @@ MJB_HD void stage_velocity(const Env& d) {
 MJB_HD void stage_solve(const Env& d) {
   if (d.solver == SOL_PGS) solve_pgs(d);
   else solve_primal(d, d.solver == SOL_NEWTON);
+  if (d.m.opt.noslip_iterations > 0) solve_noslip(d);   // engine_forward.c:1216-1243
 }
 MJB_HD void stage_finish_forward(const Env& d) {
   MJB_PROF_BEGIN
-  if (d.solver == SOL_PGS) dual_finish(d);
+  if (d.solver == SOL_PGS || d.m.opt.noslip_iterations > 0) dual_finish(d);   // engine_forward.c:1247
   MJB_PROF_MARK(9)
 }
 // ---- sensors (engine_sensor.c: mj_computeSensorPos :525-836, Vel :839-955, Acc :958-1385, apply_cutoff

@@ -210,7 +210,7 @@ bool split_step_available(const DModel& dm, const Batch& b) {
   static int want = -1;
   if (want < 0) { const char* s = getenv("MJB_SPLIT"); want = s ? atoi(s) : 1; }
   const bool islands = dm.sz.ntree > 1 && !(dm.opt.disableflags & DSBL_ISLAND);
-  return want && b.warp_per_env && b.nlane == 32 && dm.opt.solver == SOL_PGS && !islands &&
+  return want && b.warp_per_env && b.nlane == 32 && dm.opt.solver == SOL_PGS && !islands && dm.opt.noslip_iterations <= 0 &&
          (dm.opt.integrator == INT_EULER || dm.opt.integrator == INT_IMPLICITFAST);
 }
 int launch_split_step(const DModel& dm, const Batch& b, int first, int later, void* s, void* stagger) {

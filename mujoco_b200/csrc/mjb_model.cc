@@ -384,7 +384,7 @@ int check_model(const mjModel* m) {
         FAIL("implicitfast with a standalone free body (body %d)", b);
     }
   }
-  if (m->opt.noslip_iterations > 0) FAIL("noslip solver");
+  if (m->opt.noslip_iterations > 0 && m->opt.cone != mjCONE_PYRAMIDAL) FAIL("noslip solver with elliptic cones");
   if (m->opt.enableflags & (mjENBL_OVERRIDE | mjENBL_SLEEP | mjENBL_DIAGEXACT))
     FAIL("enable flags override/sleep/diagexact");
   if (m->opt.density != 0 || m->opt.viscosity != 0) {   // inertia-box fluid model only
@@ -502,6 +502,7 @@ int build_host_model(const mjModel* m, int nconmax, int njmax, HostModel* out) {
   O.meaninertia = m->stat.meaninertia;
   O.integrator = m->opt.integrator; O.cone = m->opt.cone; O.solver = m->opt.solver;
   O.iterations = m->opt.iterations; O.ls_iterations = m->opt.ls_iterations;
+  O.noslip_iterations = m->opt.noslip_iterations; O.noslip_tolerance = m->opt.noslip_tolerance;
   O.disableflags = m->opt.disableflags; O.enableflags = m->opt.enableflags;
   O.dense = is_sparse(m) ? 0 : 1;
 

@@ -83,11 +83,11 @@ struct Sizes {
 };
 
 struct Options {
-  double timestep, impratio, tolerance, ls_tolerance;
+  double timestep, impratio, tolerance, ls_tolerance, noslip_tolerance;
   double gravity[3];
   double density, viscosity, wind[3];   // medium (inertia-box fluid model)
   double meaninertia;   // m->stat.meaninertia
-  int integrator, cone, solver, iterations, ls_iterations, disableflags, enableflags;
+  int integrator, cone, solver, iterations, ls_iterations, noslip_iterations, disableflags, enableflags;
   int dense;            // mj_isSparse(m) == 0
   int eulerdamp;        // any dof takes the implicit-damping branch of mj_EulerSkip
   int has_limits;       // any limited joint or tendon

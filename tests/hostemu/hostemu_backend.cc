@@ -47,7 +47,7 @@ int launch_stages(const DModel& dm, const Batch& b, int mask, int flags, void*) 
 bool split_step_available(const DModel& dm, const Batch& b) {
   const char* s = getenv("MJB_SPLIT");
   const bool islands = dm.sz.ntree > 1 && !(dm.opt.disableflags & DSBL_ISLAND);
-  return (s ? atoi(s) : 1) && b.warp_per_env && dm.opt.solver == SOL_PGS && !islands &&
+  return (s ? atoi(s) : 1) && b.warp_per_env && dm.opt.solver == SOL_PGS && !islands && dm.opt.noslip_iterations <= 0 &&
          (dm.opt.integrator == INT_EULER || dm.opt.integrator == INT_IMPLICITFAST);
 }
 int launch_split_step(const DModel& dm, const Batch& b, int first, int later, void*, void*) {

@@ -388,6 +388,26 @@ def test_condim_4_and_6_vs_oracle():
     assert b.field("con_dim").max() >= 4
 
 
+@pytest.mark.parametrize("model,solver", [("humanoid", mb.SOLVER_PGS), ("humanoid", mb.SOLVER_NEWTON), ("ant_balls", mb.SOLVER_NEWTON)])
+def test_noslip_post_solver_vs_oracle(model, solver):
+    """opt.noslip_iterations > 0 on the device (solNoSlip after the main solver, then mj_dualFinish for every solver;
+    PGS batches take the fused kernel: the split step has no place for the post-solver)"""
+    assert available()
+    path = os.path.join(ROOT, "models", model + ".mjb")
+    nenv, nstep = 32, 80
+    m, b, o = make_pair(path, solver, nenv=nenv, nconmax=48, njmax=220, noslip_iterations=4)
+    s0 = perturbed_states(o, nenv, seed=31, height=[0.25, 0.4, 0.6], qvel_std=0.6, qpos_std=0.1)
+    ctrl = np.random.default_rng(32).uniform(-1, 1, (nenv, nstep, o.size("nu")))
+    out = b.rollout(s0, ctrl)
+    ref, stats, _ = o.rollout(s0, ctrl, nthread=os.cpu_count() or 1)
+    assert stats[:, 0].sum() > 0 and stats[:, 3].sum() == 0 and (b.warnings() == 0).all()
+    err = (np.abs(out - ref) / np.maximum(1.0, np.abs(ref).max(axis=(0, 1)))).max(axis=(0, 2))
+    print("noslip rollout rel err: step 30 %.3e, step %d %.3e" % (err[:30].max(), nstep, err.max()))
+    assert err[:30].max() < RTOL_TIGHT and err.max() < RTOL_TRAJ
+    for t in (5, 40):
+        compare_forward(b, o, ref[:, t, :], ctrl[:, t, :], rtol=RTOL_TIGHT, check_dual=True)
+
+
 def test_bad_state_warning_and_padding_gpu():
     """rollout.cc:127-155 on the device: an environment that raises a warning stops stepping and pads its outputs;
     mj_checkPos auto-resets to qpos0 (engine_forward.c:54-69).  Goes through the split step (first half checks
@@ -564,6 +584,47 @@ def test_persistent_rollout_equals_split_step(nenv):
         dev[mode] = st[:, :, :nenv].cpu().numpy()
     b.set_debug("persistent", 0)
     assert np.array_equal(dev[1], dev[0], equal_nan=True)
+
+
+def test_caller_stream_gpu():
+    """mjb_set_stream: the batch runs on the caller's CUDA stream, ordered with the caller's own work on it (here a
+    torch kernel that produces the controls right before the rollout consumes them, no synchronisation in between);
+    same states as on the batch's own stream"""
+    import torch
+    assert available()
+    nenv, nstep = 128, 12
+    o = Oracle(HUMANOID)
+    o.set_opt("solver", 0)
+    s0 = perturbed_states(o, nenv, seed=21, height=[0.3, 0.6, 1.0], qvel_std=0.3, qpos_std=0.1)
+    m = mb.Model(HUMANOID)
+    m.set_option("solver", mb.SOLVER_PGS)
+    b = mb.Batch(m, nenv, nconmax=48, njmax=128)
+    nu, stride, nstate = m.size("nu"), b.env_stride(), s0.shape[1]
+    base = torch.rand((nstep, nu, stride), dtype=torch.float64, device="cuda", generator=torch.Generator(device="cuda").manual_seed(3))
+    out = {}
+    for mode in ("own", "caller"):
+        b.reset()
+        b.set_state(s0)
+        st = torch.zeros((nstep, nstate, stride), dtype=torch.float64, device="cuda")
+        torch.cuda.synchronize()
+        if mode == "caller":
+            ts = torch.cuda.Stream()
+            b.set_stream(ts.cuda_stream)
+            assert b.stream() == ts.cuda_stream
+            with torch.cuda.stream(ts):
+                c = base * 2 - 1                      # produced on the caller's stream ...
+                b.rollout_device(nstep, c.data_ptr(), st.data_ptr())   # ... and consumed by the launches queued behind it
+                total = st.sum()                      # the caller's next kernel sees the finished states
+            ts.synchronize()
+            assert torch.isfinite(total)
+            b.set_stream(0)
+        else:
+            c = base * 2 - 1
+            torch.cuda.synchronize()
+            b.rollout_device(nstep, c.data_ptr(), st.data_ptr())
+            torch.cuda.ExternalStream(b.stream()).synchronize()
+        out[mode] = st[:, :, :nenv].cpu().numpy()
+    assert np.array_equal(out["own"], out["caller"])
 
 
 def test_single_environment_symbols_gpu():

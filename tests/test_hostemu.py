@@ -783,3 +783,28 @@ def test_refsite_and_slidercrank_transmissions_bit_exact(solver):
             o.reset(); o.set_state(ref[e, t]); o.dfield("ctrl")[:] = ctrl[e, t]; o.forward()
             assert np.array_equal(b.field("actuator_length")[e], np.array(o.dfield("actuator_length")))
             assert np.array_equal(b.field("actuator_velocity")[e], np.array(o.dfield("actuator_velocity")))
+
+
+@pytest.mark.parametrize("model,solver", [(HUMANOID, mb.SOLVER_PGS), (HUMANOID, mb.SOLVER_NEWTON), (ANT, mb.SOLVER_CG),
+                                          ("ant_frictionloss", mb.SOLVER_NEWTON), ("ant_condim", mb.SOLVER_PGS),
+                                          ("ant_balls", mb.SOLVER_NEWTON)])
+def test_noslip_post_solver_bit_exact(model, solver):
+    """opt.noslip_iterations > 0 (solNoSlip, engine_solver.c:767-957): after the main solver - dual or primal - the
+    friction rows are re-solved with the regulariser taken out of AR (dry-friction rows one by one, pyramidal contacts
+    one pair of opposing edges at a time), then mj_dualFinish maps the forces back for every solver; the dual
+    projection (efc_AR) is therefore also built for Newton / CG.  Monolithic and per island (ant_balls: several trees).
+    Forward fields (forces, states, iteration counts incl. the noslip sweeps) and rollouts are bit-identical."""
+    path = model if model.endswith(".mjb") else os.path.join(ROOT, "models", model + ".mjb")
+    nenv, nstep = 6, 60
+    m, b, o = make_pair(path, solver, library=hostemu_lib(), nenv=nenv, nconmax=48, njmax=220, noslip_iterations=4)
+    assert o.opt("noslip_iterations") == 4
+    s0 = perturbed_states(o, nenv, seed=31, height=[0.25, 0.4, 0.6], qvel_std=0.6, qpos_std=0.1)
+    ctrl = np.random.default_rng(32).uniform(-1, 1, (nenv, nstep, o.size("nu")))
+    compare_forward(b, o, s0, ctrl[:, 0], rtol=0, exact=True, check_dual=True)
+    out = b.rollout(s0, ctrl)
+    ref, stats, _ = o.rollout(s0, ctrl, nthread=4)
+    assert stats[:, 0].sum() > 0 and stats[:, 3].sum() == 0
+    assert np.array_equal(out, ref)
+    # the post-solver changes the trajectory (otherwise this test would not see it)
+    m2, b2, o2 = make_pair(path, solver, library=hostemu_lib(), nenv=nenv, nconmax=48, njmax=220)
+    assert not np.array_equal(b2.rollout(s0, ctrl), out)
