@@ -329,17 +329,19 @@ def main():
     # the reference's own batched call shape (rollout.cc): nstep steps per call, controls for all steps in, states
     # of all steps out, host buffers
     kr = min(K, 20)
-    h_c = np.random.default_rng(3).uniform(-1, 1, (NENV, kr, nu))
+    # page-locked arrays for the call's inputs and outputs (the reference API takes preallocated `state=` the same way)
+    h_c = torch.from_numpy(np.random.default_rng(3).uniform(-1, 1, (NENV, kr, nu))).pin_memory().numpy()
+    h_out = torch.empty((NENV, kr, nstate), dtype=torch.float64).pin_memory().numpy()
     s_now = batch.get_state()
-    batch.rollout(s_now, h_c)
+    batch.rollout(s_now, h_c, state=h_out)
     if world > 1:
         dist.barrier()
     t0 = time.perf_counter()
-    batch.rollout(s_now, h_c)
+    batch.rollout(s_now, h_c, state=h_out)
     r_s = time.perf_counter() - t0
     e2e["rollout_call"] = {"value": NENV * world * kr / r_s, "unit": "env-steps/s", "steps_per_call": kr,
                            "h2d_bytes_per_step": NENV * nu * 8, "d2h_bytes_per_step": NENV * nstate * 8,
-                           "call": "mjb_rollout (the rollout.cc contract): pageable host arrays in / out, initial state set per call"}
+                           "call": "mjb_rollout (the rollout.cc contract): control [nenv,nstep,nu] in, states [nenv,nstep,nstate] out, page-locked host arrays, initial state set per call"}
 
     # ---- CPU baseline (rank 0, N=1 only): reference engine on a bounded sample, all host cores
     cpu = None

@@ -286,10 +286,13 @@ class Batch:
         return int(self.L.mjb_kernel_launches(self.ptr))
 
     def rollout(self, initial_state, control=None, nstep=None, control_spec=STATE_CTRL,
-                initial_warmstart=None, return_state=True, return_sensordata=False):
+                initial_warmstart=None, return_state=True, return_sensordata=False, state=None, sensordata=None):
         """mirror of mujoco.rollout.rollout: initial_state [nenv,nstate], control [nenv,nstep,ncontrol]
         -> state [nenv,nstep,nstate] (mjSTATE_FULLPHYSICS); with return_sensordata also
-        sensordata [nenv,nstep,nsensordata] (returned as a pair, like the reference)"""
+        sensordata [nenv,nstep,nsensordata] (returned as a pair, like the reference).
+        state / sensordata: optional preallocated output arrays (python/mujoco/rollout.py:45-60 takes them the same
+        way); with page-locked arrays (e.g. the numpy view of a pinned torch tensor) for control and outputs the
+        copies of a call run at full PCIe speed and overlap the stepping."""
         s0 = np.ascontiguousarray(initial_state, dtype=np.float64)
         nstate = self.state_size()
         if s0.shape != (self.nenv, nstate):
@@ -314,8 +317,16 @@ class Batch:
             if w.shape != (self.nenv, nv):
                 raise ValueError(f"initial_warmstart must have shape {(self.nenv, nv)}")
             wptr = w.ctypes.data
-        out = np.zeros((self.nenv, nstep, nstate)) if return_state else None
-        sens = np.zeros((self.nenv, nstep, self.model.size("nsensordata"))) if return_sensordata else None
+        def _out(given, shape, want):
+            if not want:
+                return None
+            if given is None:
+                return np.empty(shape)
+            if given.shape != shape or given.dtype != np.float64 or not given.flags["C_CONTIGUOUS"]:
+                raise ValueError(f"preallocated output must be a C-contiguous float64 array of shape {shape}")
+            return given
+        out = _out(state, (self.nenv, nstep, nstate), return_state)
+        sens = _out(sensordata, (self.nenv, nstep, self.model.size("nsensordata")), return_sensordata)
         self._chk(self.L.mjb_rollout(self.ptr, int(nstep), control_spec, s0.ctypes.data, wptr, cptr,
                                      out.ctypes.data if return_state else None,
                                      sens.ctypes.data if return_sensordata else None))
