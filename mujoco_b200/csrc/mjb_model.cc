@@ -367,7 +367,8 @@ int check_model(const mjModel* m) {
     if (m->sensor_history[2 * i] > 0 || m->sensor_delay[i] > 0 || m->sensor_interval[2 * i] > 0) FAIL("sensor %d: history / delay / interval", i);
   }
   for (int i = 0; i < m->npair; i++) {
-    if (m->pair_solreffriction[mjNREF * i] || m->pair_solreffriction[mjNREF * i + 1]) FAIL("contact pair %d: solreffriction", i);
+    // solreffriction only shapes the friction rows of ELLIPTIC cones (mj_makeImpedance); pyramidal rows take solref
+    if ((m->pair_solreffriction[mjNREF * i] || m->pair_solreffriction[mjNREF * i + 1]) && m->opt.cone != mjCONE_PYRAMIDAL) FAIL("contact pair %d: solreffriction", i);
     if (m->pair_adhesion[i] != 0) FAIL("contact pair %d: adhesion", i);
   }
   if (m->nhistory) FAIL("history buffers / delays");
@@ -385,8 +386,8 @@ int check_model(const mjModel* m) {
     }
   }
   if (m->opt.noslip_iterations > 0 && m->opt.cone != mjCONE_PYRAMIDAL) FAIL("noslip solver with elliptic cones");
-  if (m->opt.enableflags & (mjENBL_OVERRIDE | mjENBL_SLEEP | mjENBL_DIAGEXACT))
-    FAIL("enable flags override/sleep/diagexact");
+  if (m->opt.enableflags & (mjENBL_SLEEP | mjENBL_DIAGEXACT))
+    FAIL("enable flags sleep/diagexact");
   if (m->opt.density != 0 || m->opt.viscosity != 0) {   // inertia-box fluid model only
     for (int i = 0; i < m->ngeom; i++) if (m->geom_fluid[mjNFLUID * i] > 0) FAIL("geom %d: ellipsoid fluid model", i);
     if (m->opt.integrator == mjINT_IMPLICITFAST) FAIL("fluid forces with implicitfast (velocity derivatives of the fluid forces)");
@@ -898,6 +899,18 @@ int build_host_model(const mjModel* m, int nconmax, int njmax, HostModel* out) {
   }
   for (; contacts_on && pairadr < m->npair; pairadr++)   // predefined pairs past the last body pair
     if (int rc = push_predefined(pairadr)) return rc;
+  // mjENBL_OVERRIDE (mj_assignMargin / Ref / Imp / Friction, engine_core_constraint.c:176-217): every contact takes the
+  // margin, solver parameters and friction of mjOption; the gap stays the pair's own
+  if (m->opt.enableflags & mjENBL_OVERRIDE) {
+    for (size_t p = 0; p < pg1.size(); p++) {
+      const double gap = pmargin[p] - pinc[p];
+      pinc[p] = m->opt.o_margin;
+      pmargin[p] = m->opt.o_margin + gap;
+      for (int c = 0; c < mjNREF; c++) psolref[mjNREF * p + c] = m->opt.o_solref[c];
+      for (int c = 0; c < mjNIMP; c++) psolimp[mjNIMP * p + c] = m->opt.o_solimp[c];
+      for (int c = 0; c < 5; c++) pfric[5 * p + c] = std::max((double)mjMINMU, m->opt.o_friction[c]);
+    }
+  }
   S.npair = (int)pg1.size();
   B.addI(&D.pair_geom1, pg1.data(), pg1.size());
   B.addI(&D.pair_geom2, pg2.data(), pg2.size());

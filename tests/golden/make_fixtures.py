@@ -37,6 +37,7 @@ MODELS = {
     "boxes": os.path.join(ROOT, "models", "boxes.xml"),      # cylinder / box colliders
     "ant_pairs": os.path.join(ROOT, "models", "ant_pairs.xml"),   # predefined contact pairs
     "ant_trn": os.path.join(ROOT, "models", "ant_trn.xml"),       # site + reference site and slider-crank transmissions
+    "ant_override": os.path.join(ROOT, "models", "ant_override.xml"),   # mjENBL_OVERRIDE contact parameters
 }
 
 

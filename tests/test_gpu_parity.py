@@ -408,6 +408,24 @@ def test_noslip_post_solver_vs_oracle(model, solver):
         compare_forward(b, o, ref[:, t, :], ctrl[:, t, :], rtol=RTOL_TIGHT, check_dual=True)
 
 
+def test_contact_override_gpu():
+    """mjENBL_OVERRIDE on the device (models/ant_override.xml: every contact takes mjOption's o_margin / o_solref /
+    o_solimp / o_friction; a pair with solreffriction under pyramidal cones)"""
+    assert available()
+    path = os.path.join(ROOT, "models", "ant_override.mjb")
+    nenv, nstep = 16, 100
+    m, b, o = make_pair(path, mb.SOLVER_NEWTON, nenv=nenv, nconmax=48, njmax=220)
+    s0 = perturbed_states(o, nenv, seed=14, height=[0.35, 0.5, 0.75], qvel_std=0.8, qpos_std=0.05)
+    ctrl = np.random.default_rng(15).uniform(-1, 1, (nenv, nstep, o.size("nu")))
+    out = b.rollout(s0, ctrl)
+    ref, stats, _ = o.rollout(s0, ctrl, nthread=os.cpu_count() or 1)
+    assert stats[:, 0].sum() > 0 and stats[:, 3].sum() == 0 and (b.warnings() == 0).all()
+    err = (np.abs(out - ref) / np.maximum(1.0, np.abs(ref).max(axis=(0, 1)))).max(axis=(0, 2))
+    assert err[:30].max() < RTOL_TIGHT and err.max() < RTOL_TRAJ
+    for t in (10, 60):
+        compare_forward(b, o, ref[:, t, :], ctrl[:, t, :], rtol=RTOL_TIGHT, check_dual=False)
+
+
 def test_bad_state_warning_and_padding_gpu():
     """rollout.cc:127-155 on the device: an environment that raises a warning stops stepping and pads its outputs;
     mj_checkPos auto-resets to qpos0 (engine_forward.c:54-69).  Goes through the split step (first half checks

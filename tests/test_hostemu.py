@@ -808,3 +808,24 @@ def test_noslip_post_solver_bit_exact(model, solver):
     # the post-solver changes the trajectory (otherwise this test would not see it)
     m2, b2, o2 = make_pair(path, solver, library=hostemu_lib(), nenv=nenv, nconmax=48, njmax=220)
     assert not np.array_equal(b2.rollout(s0, ctrl), out)
+
+
+@pytest.mark.parametrize("solver", [mb.SOLVER_NEWTON, mb.SOLVER_PGS])
+def test_contact_override_bit_exact(solver):
+    """mjENBL_OVERRIDE (mj_assignMargin / Ref / Imp / Friction, engine_core_constraint.c:176-217): margin, solref, solimp
+    and friction of every contact - dynamic geom pairs and predefined pairs - come from mjOption's o_* members; a pair's
+    solreffriction is accepted under pyramidal cones (only elliptic friction rows would read it) -
+    models/ant_override.xml"""
+    path = os.path.join(ROOT, "models", "ant_override.mjb")
+    nenv, nstep = 6, 100
+    m, b, o = make_pair(path, solver, library=hostemu_lib(), nenv=nenv, nconmax=48, njmax=220)
+    s0 = perturbed_states(o, nenv, seed=14, height=[0.35, 0.5, 0.75], qvel_std=0.8, qpos_std=0.05)
+    ctrl = np.random.default_rng(15).uniform(-1, 1, (nenv, nstep, o.size("nu")))
+    compare_forward(b, o, s0, ctrl[:, 0], rtol=0, exact=True, check_dual=(solver == mb.SOLVER_PGS))
+    out = b.rollout(s0, ctrl)
+    ref, stats, _ = o.rollout(s0, ctrl, nthread=4)
+    assert stats[:, 0].sum() > 0 and stats[:, 3].sum() == 0
+    assert np.array_equal(out, ref)
+    e = int(np.argmax(b.field("ncon")[:, 0]))
+    assert b.field("ncon")[e, 0] > 0 and np.allclose(b.field("con_friction")[e][:5], [0.7, 0.7, 0.01, 0.0002, 0.0002])
+    assert np.allclose(b.field("con_solref")[e][:2], [0.015, 0.8])
