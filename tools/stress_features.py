@@ -13,9 +13,10 @@ nenv = int(sys.argv[1]) if len(sys.argv) > 1 else 32
 nstep = int(sys.argv[2]) if len(sys.argv) > 2 else 80
 seeds = int(sys.argv[3]) if len(sys.argv) > 3 else 2
 MODELS = ["humanoid", "ant", "ant_frictionloss", "ant_balls", "ant_sensors", "ant_servo", "ant_equality", "ant_connect",
-          "ant_weld", "ant_condim", "ant_fluid", "ant_touch", "ant_mocap", "ant_act", "ant_pairs", "ant_trn", "boxes"]
+          "ant_weld", "ant_condim", "ant_fluid", "ant_touch", "ant_mocap", "ant_act", "ant_pairs", "ant_trn", "ant_override", "boxes"]
 rows = []
-for name in MODELS:
+CASES = [(n, {}) for n in MODELS] + [(n, {"noslip_iterations": 3}) for n in ("humanoid", "ant_condim", "ant_balls", "ant_frictionloss")]
+for name, extra in CASES:
     path = os.path.join(ROOT, "models", name + ".mjb")
     for solver, sname in ((mb.SOLVER_PGS, "pgs"), (mb.SOLVER_NEWTON, "newton"), (mb.SOLVER_CG, "cg")):
         worst30 = worst = single = 0.0
@@ -23,7 +24,7 @@ for name in MODELS:
         t0 = time.time()
         try:
             for seed in range(seeds):
-                m, b, o = make_pair(path, solver, nenv=nenv, nconmax=96, njmax=400)
+                m, b, o = make_pair(path, solver, nenv=nenv, nconmax=96, njmax=400, **extra)
                 nq, nv, nu = o.size("nq"), o.size("nv"), o.size("nu")
                 rng = np.random.default_rng(1000 * seed + 7)
                 if name == "boxes":
@@ -59,10 +60,10 @@ for name in MODELS:
                             o.step()
                             r = o.get_state()
                             single = max(single, float(np.abs(got[e] - r).max() / max(1.0, np.abs(r).max())))
-            rows.append({"model": name, "solver": sname, "nenv": nenv, "nstep": nstep, "seeds": seeds, "rel_err_30": worst30,
+            rows.append({"model": name + ("+noslip" if extra else ""), "solver": sname, "nenv": nenv, "nstep": nstep, "seeds": seeds, "rel_err_30": worst30,
                          "rel_err_all": worst, "rel_err_single_step": single, "envs_with_reference_warnings": nwarn, "seconds": round(time.time() - t0, 2)})
         except mb.MjbError as ex:
-            rows.append({"model": name, "solver": sname, "refused": str(ex)[:100]})
+            rows.append({"model": name + ("+noslip" if extra else ""), "solver": sname, "refused": str(ex)[:100]})
         print(rows[-1], flush=True)
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
 json.dump({"rows": rows}, open(os.path.join(ROOT, "gpurun_out", "r02_stress.json"), "w"), indent=1)
