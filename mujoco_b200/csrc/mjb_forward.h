@@ -640,7 +640,89 @@ MJB_HD void euler_advance(const Env& d) {
   MJB_PSYNC();
 }
 
-// implicitfast integrator (mj_implicitSkip, engine_forward.c:1649-1771, without standalone free bodies):
+// standalone free bodies under implicitfast (engine_forward.c:1742-1762): the symmetric solve drops the derivative of
+// the bias (gyroscopic) force; a body that is a whole tree by itself - one free joint, no children - gets its six
+// accelerations from a local unsymmetric solve instead, A = M - h dqfrc_smooth/dqvel with the bias block of
+// mjd_freeBias_vel (engine_derivative.c:706-905), by the partially pivoted 6x6 LU of engine_util_solve.c:855-925.
+// qHblk: the body's 6x6 lower triangle of qH = M - h qDeriv (its qDeriv block is diagonal here: the model check
+// refuses actuators on such a body).  rhs -> x.
+MJB_HD void free_body_implicit(const Env& d, int body, int adr, const double* qHlow, const double* rhs, double* x) {
+  const DModel& m = d.m;
+  const double h = m.opt.timestep, mass = m.body_mass[body];
+  double R[9], Xi[9], s[3], w[3];
+  FD xmat = d.xmat(), ximat = d.ximat(), xipos = d.xipos(), xpos = d.xpos(), qvel = d.qvel();
+  for (int i = 0; i < 9; i++) { R[i] = xmat[9 * body + i]; Xi[i] = ximat[9 * body + i]; }
+  for (int i = 0; i < 3; i++) s[i] = xipos[3 * body + i] - xpos[3 * body + i];
+  const double v0 = qvel[adr + 3], v1 = qvel[adr + 4], v2 = qvel[adr + 5];
+  for (int i = 0; i < 3; i++) w[i] = R[3 * i] * v0 + R[3 * i + 1] * v1 + R[3 * i + 2] * v2;
+  const double* inertia = m.body_inertia + 3 * body;
+  double XI[9], Iw[9];
+  for (int i = 0; i < 3; i++) for (int c = 0; c < 3; c++) XI[3 * i + c] = Xi[3 * i + c] * inertia[c];
+  Iw[0] = XI[0] * Xi[0] + XI[1] * Xi[1] + XI[2] * Xi[2];
+  Iw[4] = XI[3] * Xi[3] + XI[4] * Xi[4] + XI[5] * Xi[5];
+  Iw[8] = XI[6] * Xi[6] + XI[7] * Xi[7] + XI[8] * Xi[8];
+  Iw[1] = Iw[3] = XI[0] * Xi[3] + XI[1] * Xi[4] + XI[2] * Xi[5];
+  Iw[2] = Iw[6] = XI[0] * Xi[6] + XI[1] * Xi[7] + XI[2] * Xi[8];
+  Iw[5] = Iw[7] = XI[3] * Xi[6] + XI[4] * Xi[7] + XI[5] * Xi[8];
+  const double ws[3] = {w[1] * s[2] - w[2] * s[1], w[2] * s[0] - w[0] * s[2], w[0] * s[1] - w[1] * s[0]};
+  double Iww[3];
+  for (int i = 0; i < 3; i++) Iww[i] = Iw[3 * i] * w[0] + Iw[3 * i + 1] * w[1] + Iw[3 * i + 2] * w[2];
+  const double wds = w[0] * s[0] + w[1] * s[1] + w[2] * s[2];
+  double K[9];
+  K[0] = s[0] * w[0] - wds;   K[1] = s[0] * w[1] - ws[2];  K[2] = s[0] * w[2] + ws[1];
+  K[3] = s[1] * w[0] + ws[2]; K[4] = s[1] * w[1] - wds;    K[5] = s[1] * w[2] - ws[0];
+  K[6] = s[2] * w[0] - ws[1]; K[7] = s[2] * w[1] + ws[0];  K[8] = s[2] * w[2] - wds;
+  double lin[9], C[9], tmp[9], rot[9];
+  for (int i = 0; i < 3; i++) for (int c = 0; c < 3; c++) lin[3 * i + c] = K[3 * i] * R[c] + K[3 * i + 1] * R[3 + c] + K[3 * i + 2] * R[6 + c];
+  for (int c = 0; c < 3; c++) {
+    const double sk0 = s[1] * K[6 + c] - s[2] * K[3 + c], sk1 = s[2] * K[c] - s[0] * K[6 + c], sk2 = s[0] * K[3 + c] - s[1] * K[c];
+    const double wi0 = w[1] * Iw[6 + c] - w[2] * Iw[3 + c], wi1 = w[2] * Iw[c] - w[0] * Iw[6 + c], wi2 = w[0] * Iw[3 + c] - w[1] * Iw[c];
+    C[c] = -mass * sk0 + wi0 + (c == 1 ? Iww[2] : (c == 2 ? -Iww[1] : 0));
+    C[3 + c] = -mass * sk1 + wi1 + (c == 0 ? -Iww[2] : (c == 2 ? Iww[0] : 0));
+    C[6 + c] = -mass * sk2 + wi2 + (c == 0 ? Iww[1] : (c == 1 ? -Iww[0] : 0));
+  }
+  for (int i = 0; i < 3; i++) for (int c = 0; c < 3; c++) tmp[3 * i + c] = R[i] * C[c] + R[3 + i] * C[3 + c] + R[6 + i] * C[6 + c];        // R' C
+  for (int i = 0; i < 3; i++) for (int c = 0; c < 3; c++) rot[3 * i + c] = tmp[3 * i] * R[c] + tmp[3 * i + 1] * R[3 + c] + tmp[3 * i + 2] * R[6 + c];
+  double A[36];
+  for (int i = 0; i < 36; i++) A[i] = 0;
+  for (int r = 0; r < 6; r++) {
+    const int ra = m.M_rowadr[adr + r], rn = m.M_rownnz[adr + r];
+    for (int k = 0; k < rn; k++) { const int c = m.M_colind[ra + k] - adr; A[6 * r + c] = qHlow[ra + k]; A[6 * c + r] = qHlow[ra + k]; }
+  }
+  const double hm = -h * mass;
+  for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) { A[6 * r + 3 + c] += hm * lin[3 * r + c]; A[6 * (3 + r) + 3 + c] += h * rot[3 * r + c]; }
+  int pivot[6];
+  for (int k = 0; k < 6; k++) {
+    pivot[k] = k;
+    double maxval = fabs(A[6 * k + k]);
+    int maxrow = k;
+    for (int i = k + 1; i < 6; i++) { const double val = fabs(A[6 * i + k]); if (val > maxval) { maxval = val; maxrow = i; } }
+    if (maxval < kMinVal) return;     // singular: the symmetric solution stays
+    if (maxrow != k) {
+      pivot[k] = maxrow;
+      for (int j = 0; j < 6; j++) { const double t = A[6 * k + j]; A[6 * k + j] = A[6 * maxrow + j]; A[6 * maxrow + j] = t; }
+    }
+    const double dinv = 1.0 / A[6 * k + k];
+    for (int i = k + 1; i < 6; i++) {
+      A[6 * i + k] *= dinv;
+      const double aik = A[6 * i + k];
+      for (int j = k + 1; j < 6; j++) A[6 * i + j] -= aik * A[6 * k + j];
+    }
+  }
+  double y[6];
+  for (int i = 0; i < 6; i++) y[i] = rhs[i];
+  for (int i = 0; i < 6; i++) {
+    if (pivot[i] != i) { const double t = y[i]; y[i] = y[pivot[i]]; y[pivot[i]] = t; }
+    for (int j = 0; j < i; j++) y[i] -= A[6 * i + j] * y[j];
+  }
+  for (int i = 5; i >= 0; i--) {
+    for (int j = i + 1; j < 6; j++) y[i] -= A[6 * i + j] * y[j];
+    y[i] /= A[6 * i + i];
+  }
+  for (int i = 0; i < 6; i++) x[i] = y[i];
+}
+
+// implicitfast integrator (mj_implicitSkip, engine_forward.c:1649-1771; standalone free bodies: free_body_implicit):
 // qH = M - h * d(qfrc_actuator + qfrc_passive)/d(qvel) on M's sparsity (mjd_smooth_vel with flg_bias = 0,
 // engine_derivative.c:3145-3170: actuator velocity gains mjd_actuator_vel :2350-2500, then dof and tendon
 // damping mjd_passive_vel :3040-3140; entries outside the tree sparsity are dropped as in the reference),
@@ -734,6 +816,18 @@ MJB_HD void implicitfast_advance(const Env& d) {
   MJB_PFOR(i, nv) acc[i] = qfs[i] + qfc[i];
   MJB_PSYNC();
   solve_LD(d, acc, qH, d.qHDiagInv());
+  if (m.sz.freebody) {   // one lane per standalone free body: its six rows are decoupled from every other dof
+    MJB_PFOR(j, m.sz.njnt) {
+      const int body = m.jnt_bodyid[j];
+      if (m.jnt_type[j] != JNT_FREE || m.body_jntnum[body] != 1 || m.body_subtreemass[body] != m.body_mass[body]) continue;
+      const int adr = m.jnt_dofadr[j];
+      double rhs[6], x[6];
+      for (int i = 0; i < 6; i++) { rhs[i] = qfs[adr + i] + qfc[adr + i]; x[i] = acc[adr + i]; }
+      free_body_implicit(d, body, adr, qH.p, rhs, x);
+      for (int i = 0; i < 6; i++) acc[adr + i] = x[i];
+    }
+    MJB_PSYNC();
+  }
   advance_act(d, d.act_dot());
   MJB_PFOR(i, nv) qvel[i] += acc[i] * h;
   MJB_PSYNC();

@@ -377,12 +377,20 @@ int check_model(const mjModel* m) {
   if (m->opt.integrator == mjINT_IMPLICIT) FAIL("the fully implicit integrator (RNE velocity derivatives, sparse LU)");
   if (m->opt.integrator == mjINT_IMPLICITFAST) {
     if (m->ntendon > m->nv) FAIL("implicitfast with more tendons than dofs");
-    // standalone free bodies take a separate unsymmetric 6x6 solve (mjd_freeMhat): not built
+    // standalone free bodies take a separate unsymmetric 6x6 solve (mjd_freeMhat -> free_body_implicit); its matrix is
+    // assembled from the lower triangle of qH, which is the whole story only while the body's qDeriv block is
+    // diagonal (damping): actuators acting on such a body are refused
     for (int j = 0; j < m->njnt; j++) {
       const int b = m->jnt_bodyid[j];
-      if (m->jnt_type[j] == mjJNT_FREE && m->body_jntnum[b] == 1 && m->tree_dofnum[m->dof_treeid[m->jnt_dofadr[j]]] == 6 &&
-          m->body_subtreemass[b] == m->body_mass[b])
-        FAIL("implicitfast with a standalone free body (body %d)", b);
+      if (!(m->jnt_type[j] == mjJNT_FREE && m->body_jntnum[b] == 1 && m->tree_dofnum[m->dof_treeid[m->jnt_dofadr[j]]] == 6 &&
+            m->body_subtreemass[b] == m->body_mass[b])) continue;
+      for (int u = 0; u < m->nu; u++) {
+        const int tt = m->actuator_trntype[u], id0 = m->actuator_trnid[2 * u], id1 = m->actuator_trnid[2 * u + 1];
+        bool hit = false;
+        if ((tt == mjTRN_JOINT || tt == mjTRN_JOINTINPARENT) && id0 == j) hit = true;
+        if ((tt == mjTRN_SITE || tt == mjTRN_SLIDERCRANK) && (m->site_bodyid[id0] == b || (id1 >= 0 && m->site_bodyid[id1] == b))) hit = true;
+        if (hit) FAIL("implicitfast: actuator %d acts on the standalone free body %d", u, b);
+      }
     }
   }
   if (m->opt.noslip_iterations > 0 && m->opt.cone != mjCONE_PYRAMIDAL) FAIL("noslip solver with elliptic cones");
@@ -475,6 +483,12 @@ int build_host_model(const mjModel* m, int nconmax, int njmax, HostModel* out) {
   for (int i = 0; i < m->nu; i++) if (m->actuator_trntype[i] == mjTRN_SITE || m->actuator_trntype[i] == mjTRN_SLIDERCRANK) S.sitetrn = 1;
   S.gravcomp = m->flg_gravcomp ? 1 : 0;
   S.colbox = 0;   // set while the candidate pairs are built
+  S.freebody = 0;
+  if (m->opt.integrator == mjINT_IMPLICITFAST)
+    for (int j = 0; j < m->njnt; j++) {
+      const int b = m->jnt_bodyid[j];
+      if (m->jnt_type[j] == mjJNT_FREE && m->body_jntnum[b] == 1 && m->body_subtreemass[b] == m->body_mass[b]) S.freebody = 1;
+    }
   if (S.gravcomp) S.actfeat = 1;
   S.nq = m->nq; S.nv = m->nv; S.nu = m->nu; S.na = m->na; S.nbody = m->nbody; S.njnt = m->njnt;
   S.ngeom = m->ngeom; S.ntendon = m->ntendon; S.nwrap = m->nwrap; S.nJten = m->nJten; S.nC = m->nC;

@@ -72,6 +72,7 @@ struct Sizes {
   int epot, ekin;   // 1 when the potential / kinetic energy is computed (mjENBL_ENERGY or an energy sensor)
   int subtreevel;   // 1 when a sensor needs mj_subtreeVel (subtree_linvel / subtree_angmom are allocated then)
   int rnepost;   // 1 when a sensor needs mj_rnePostConstraint (cacc / cfrc_int / cfrc_ext are allocated then)
+  int freebody;  // 1 when implicitfast meets a standalone free body (local unsymmetric 6x6 solve, mjb_forward.h free_body_implicit)
   int colbox;    // 1 when a candidate pair needs a cylinder / box collider (FEAT_COLBOX code paths)
   int npair;     // static candidate geom pairs (host-built, reference order)
   int nconmax;   // per-env contact cap

@@ -426,6 +426,31 @@ def test_contact_override_gpu():
         compare_forward(b, o, ref[:, t, :], ctrl[:, t, :], rtol=RTOL_TIGHT, check_dual=False)
 
 
+def test_implicitfast_standalone_free_bodies_gpu():
+    """implicitfast on free-floating boxes / cylinders (models/boxes.xml): the local unsymmetric 6x6 solve with the
+    gyroscopic block for bodies that are a tree by themselves"""
+    assert available()
+    path = os.path.join(ROOT, "models", "boxes.mjb")
+    nenv, nstep = 16, 80
+    m, b, o = make_pair(path, mb.SOLVER_NEWTON, nenv=nenv, nconmax=96, njmax=400, integrator=mb.INT_IMPLICITFAST)
+    nq, nv = o.size("nq"), o.size("nv")
+    rng = np.random.default_rng(41)
+    o.reset()
+    s0 = np.tile(o.get_state(), (nenv, 1))
+    for e in range(nenv):
+        for k in range(9):
+            s0[e, 1 + 7 * k + 2] += rng.uniform(-0.05, 0.3)
+            s0[e, 1 + 7 * k + 3:1 + 7 * k + 7] = rng.normal(size=4)
+        s0[e, 1 + nq:] = rng.normal(0, 2.5, nv)
+    ctrl = rng.uniform(-1, 1, (nenv, nstep, o.size("nu")))
+    out = b.rollout(s0, ctrl)
+    ref, stats, _ = o.rollout(s0, ctrl, nthread=os.cpu_count() or 1)
+    assert stats[:, 3].sum() == 0 and (b.warnings() == 0).all()
+    err = (np.abs(out - ref) / np.maximum(1.0, np.abs(ref).max(axis=(0, 1)))).max(axis=(0, 2))
+    print("implicitfast free bodies rel err: step 30 %.3e, step %d %.3e" % (err[:30].max(), nstep, err.max()))
+    assert err[:30].max() < RTOL_TIGHT and err.max() < RTOL_TRAJ
+
+
 def test_bad_state_warning_and_padding_gpu():
     """rollout.cc:127-155 on the device: an environment that raises a warning stops stepping and pads its outputs;
     mj_checkPos auto-resets to qpos0 (engine_forward.c:54-69).  Goes through the split step (first half checks

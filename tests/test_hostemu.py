@@ -309,11 +309,35 @@ def test_implicitfast_bit_exact(model, solver):
     assert np.array_equal(out, ref)
 
 
-def test_implicitfast_refuses_standalone_free_bodies():
-    m = mb.Model(os.path.join(ROOT, "models", "ant_balls.mjb"), library=hostemu_lib())
-    m.set_option("integrator", mb.INT_IMPLICITFAST)
-    with pytest.raises(mb.MjbError, match="standalone free body"):
-        mb.Batch(m, 1)
+@pytest.mark.parametrize("model,solver", [("ant_balls", mb.SOLVER_NEWTON), ("ant_balls", mb.SOLVER_PGS), ("boxes", mb.SOLVER_NEWTON)])
+def test_implicitfast_standalone_free_bodies_bit_exact(model, solver):
+    """implicitfast with bodies that are a whole tree by themselves (one free joint, no children): their six
+    accelerations come from the local unsymmetric solve of engine_forward.c:1742-1762 - M - h dqfrc_smooth/dqvel with
+    the gyroscopic (bias) block of mjd_freeBias_vel, partially pivoted 6x6 LU - instead of the symmetric qH solve.
+    Spinning balls next to the ant (islands) and the tumbling boxes / cylinders of models/boxes.xml."""
+    path = os.path.join(ROOT, "models", model + ".mjb")
+    nenv, nstep = 6, 80
+    m, b, o = make_pair(path, solver, library=hostemu_lib(), nenv=nenv, nconmax=96, njmax=400, integrator=mb.INT_IMPLICITFAST)
+    nq, nv = o.size("nq"), o.size("nv")
+    rng = np.random.default_rng(41)
+    if model == "boxes":
+        o.reset()
+        s0 = np.tile(o.get_state(), (nenv, 1))
+        for e in range(nenv):
+            for k in range(9):
+                s0[e, 1 + 7 * k + 2] += rng.uniform(-0.05, 0.3)
+                s0[e, 1 + 7 * k + 3:1 + 7 * k + 7] = rng.normal(size=4)
+            s0[e, 1 + nq:] = rng.normal(0, 2.5, nv)        # fast spins: the gyroscopic block matters
+    else:
+        s0 = perturbed_states(o, nenv, seed=42, height=[0.35, 0.5, 0.75], qvel_std=2.0, qpos_std=0.1)
+    ctrl = rng.uniform(-1, 1, (nenv, nstep, o.size("nu")))
+    out = b.rollout(s0, ctrl)
+    ref, stats, _ = o.rollout(s0, ctrl, nthread=4)
+    assert stats[:, 3].sum() == 0
+    assert np.array_equal(out, ref)
+    # the local solve changes the result: Euler-style symmetric-only integration of the same model differs
+    m2, b2, o2 = make_pair(path, solver, library=hostemu_lib(), nenv=nenv, nconmax=96, njmax=400, integrator=mb.INT_EULER)
+    assert not np.array_equal(b2.rollout(s0, ctrl), out)
 
 
 @pytest.mark.parametrize("solver", [mb.SOLVER_PGS, mb.SOLVER_NEWTON, mb.SOLVER_CG])
